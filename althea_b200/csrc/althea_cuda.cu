@@ -1,0 +1,732 @@
+// The extern "C" shim: context, resource table (imported / wrapped / owned device memory), and the entry points that
+// turn the reference's parameter blocks into kernel launches. See include/althea_cuda.h for what each one replaces.
+// No CPU fallback anywhere: a compute entry point either launches sm_100a kernels or returns an error.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/althea_cuda.h"
+#include "launchers.h"
+
+namespace {
+
+thread_local std::string g_createError;
+
+enum class ResKind { Image, Buffer, Semaphore };
+
+struct Resource {
+  ResKind kind = ResKind::Buffer;
+  void* dptr = nullptr;
+  size_t bytes = 0;
+  uint32_t format = 0, w = 0, h = 0, mips = 1, layers = 1;
+  size_t pitch0 = 0; // row pitch of level 0 (bytes)
+  bool owned = false;
+  cudaExternalMemory_t extMem = nullptr;
+  cudaExternalSemaphore_t extSem = nullptr;
+  bool timeline = false;
+};
+
+struct TimingEntry {
+  const char* name;
+  cudaEvent_t start, stop;
+};
+
+} // namespace
+
+struct althea_cuda_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint32_t flags = 0;
+  std::string lastError;
+  std::unordered_map<uint64_t, Resource> resources;
+  uint64_t nextHandle = 1;
+  uint64_t launches = 0;
+  // internal scratch: SSAO occluded-ray counts
+  void* aoScratch = nullptr;
+  size_t aoScratchBytes = 0;
+  // timing
+  bool timing = false;
+  std::vector<TimingEntry> pending;
+  std::vector<cudaEvent_t> eventPool;
+  std::map<std::string, std::pair<double, uint32_t>> totals;
+  std::vector<const char*> totalNames;
+};
+
+namespace {
+
+int fail(althea_cuda_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->lastError = buf;
+  else g_createError = buf;
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                              \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess) return fail(ctx, ALTHEA_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+size_t bytesPerTexel(uint32_t fmt) {
+  switch (fmt) {
+  case ALTHEA_FORMAT_R8G8B8A8_UNORM: return 4;
+  case ALTHEA_FORMAT_R16G16B16A16_SFLOAT: return 8;
+  case ALTHEA_FORMAT_R32_SFLOAT:
+  case ALTHEA_FORMAT_D32_SFLOAT: return 4;
+  case ALTHEA_FORMAT_R32G32B32A32_SFLOAT: return 16;
+  case ALTHEA_FORMAT_R8_UINT: return 1;
+  default: return 0;
+  }
+}
+inline uint32_t mipDim(uint32_t d, uint32_t k) { uint32_t v = d >> k; return v ? v : 1u; }
+size_t chainBytes(uint32_t fmt, uint32_t w, uint32_t h, uint32_t mips) {
+  size_t n = 0, bpp = bytesPerTexel(fmt);
+  for (uint32_t k = 0; k < mips; ++k) n += (size_t)mipDim(w, k) * mipDim(h, k) * bpp;
+  return n;
+}
+
+Resource* find(althea_cuda_ctx* ctx, uint64_t handle, ResKind kind) {
+  auto it = ctx->resources.find(handle);
+  if (it == ctx->resources.end() || it->second.kind != kind) return nullptr;
+  return &it->second;
+}
+
+// view of (level, layer) of an image
+bool levelView(const Resource& r, uint32_t level, uint32_t layer, ImgView* out) {
+  if (level >= r.mips || layer >= r.layers) return false;
+  size_t bpp = bytesPerTexel(r.format);
+  size_t layerBytes = (r.mips == 1) ? r.pitch0 * r.h : chainBytes(r.format, r.w, r.h, r.mips);
+  size_t off = layerBytes * layer;
+  for (uint32_t k = 0; k < level; ++k) off += (size_t)mipDim(r.w, k) * mipDim(r.h, k) * bpp;
+  out->ptr = static_cast<const char*>(r.dptr) + off;
+  out->w = (int)mipDim(r.w, level);
+  out->h = (int)mipDim(r.h, level);
+  out->pitch = (int)((r.mips == 1) ? r.pitch0 : (size_t)out->w * bpp);
+  return true;
+}
+bool chainView(const Resource& r, uint32_t layer, ChainView* out) {
+  if (r.mips > (uint32_t)kMaxMips) return false;
+  out->mips = (int)r.mips;
+  for (uint32_t k = 0; k < r.mips; ++k)
+    if (!levelView(r, k, layer, &out->level[k])) return false;
+  return true;
+}
+
+int getImage(althea_cuda_ctx* ctx, uint64_t handle, uint32_t format, const char* what, Resource** out, bool optional = false) {
+  *out = nullptr;
+  if (handle == 0) {
+    if (optional) return ALTHEA_OK;
+    return fail(ctx, ALTHEA_ERR_BAD_HANDLE, "%s: image handle is 0", what);
+  }
+  Resource* r = find(ctx, handle, ResKind::Image);
+  if (!r) return fail(ctx, ALTHEA_ERR_BAD_HANDLE, "%s: handle %llu is not a live image", what, (unsigned long long)handle);
+  uint32_t f = r->format == ALTHEA_FORMAT_D32_SFLOAT ? (uint32_t)ALTHEA_FORMAT_R32_SFLOAT : r->format;
+  if (format && f != format) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "%s: expected VkFormat %u, image has %u", what, format, r->format);
+  *out = r;
+  return ALTHEA_OK;
+}
+
+// ---- stream / semaphore / timing plumbing ------------------------------------------------------------------------
+struct Scope {
+  althea_cuda_ctx* ctx;
+  cudaStream_t stream;
+};
+
+int beginWork(althea_cuda_ctx* ctx, const althea_sync* sync, cudaStream_t* stream) {
+  *stream = (sync && sync->cuda_stream) ? (cudaStream_t)sync->cuda_stream : ctx->stream;
+  if (sync && sync->wait_sem) {
+    Resource* s = find(ctx, sync->wait_sem, ResKind::Semaphore);
+    if (!s) return fail(ctx, ALTHEA_ERR_BAD_HANDLE, "wait_sem %llu is not a live semaphore", (unsigned long long)sync->wait_sem);
+    cudaExternalSemaphoreWaitParams wp;
+    memset(&wp, 0, sizeof wp);
+    wp.params.fence.value = sync->wait_value;
+    CUDA_TRY(ctx, cudaWaitExternalSemaphoresAsync(&s->extSem, &wp, 1, *stream));
+  }
+  return ALTHEA_OK;
+}
+int endWork(althea_cuda_ctx* ctx, const althea_sync* sync, cudaStream_t stream) {
+  CUDA_TRY(ctx, cudaGetLastError());
+  if (sync && sync->signal_sem) {
+    Resource* s = find(ctx, sync->signal_sem, ResKind::Semaphore);
+    if (!s) return fail(ctx, ALTHEA_ERR_BAD_HANDLE, "signal_sem %llu is not a live semaphore", (unsigned long long)sync->signal_sem);
+    cudaExternalSemaphoreSignalParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.params.fence.value = sync->signal_value;
+    CUDA_TRY(ctx, cudaSignalExternalSemaphoresAsync(&s->extSem, &sp, 1, stream));
+  }
+  return ALTHEA_OK;
+}
+
+cudaEvent_t takeEvent(althea_cuda_ctx* ctx) {
+  if (!ctx->eventPool.empty()) {
+    cudaEvent_t e = ctx->eventPool.back();
+    ctx->eventPool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// launches `fn` as one counted, optionally event-timed kernel launch
+template <typename F> void timedLaunch(althea_cuda_ctx* ctx, const char* name, cudaStream_t stream, F&& fn) {
+  if (ctx->timing) {
+    TimingEntry t{name, takeEvent(ctx), takeEvent(ctx)};
+    cudaEventRecord(t.start, stream);
+    fn();
+    cudaEventRecord(t.stop, stream);
+    ctx->pending.push_back(t);
+  } else {
+    fn();
+  }
+  ctx->launches += 1;
+}
+
+void drainTimings(althea_cuda_ctx* ctx) {
+  for (TimingEntry& t : ctx->pending) {
+    cudaEventSynchronize(t.stop);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, t.start, t.stop);
+    auto it = ctx->totals.find(t.name);
+    if (it == ctx->totals.end()) {
+      ctx->totals[t.name] = std::make_pair((double)ms, 1u);
+      ctx->totalNames.push_back(t.name);
+    } else {
+      it->second.first += ms;
+      it->second.second += 1;
+    }
+    ctx->eventPool.push_back(t.start);
+    ctx->eventPool.push_back(t.stop);
+  }
+  ctx->pending.clear();
+}
+
+// projection * view in the oracle's op order (column by column, summed left to right, no contraction: this TU's host
+// code is compiled with -ffp-contract=off via -Xcompiler)
+void matmul44(const float* A, const float* B, float* R) {
+  for (int c = 0; c < 4; ++c)
+    for (int r = 0; r < 4; ++r) {
+      float s = A[0 * 4 + r] * B[c * 4 + 0];
+      s = s + A[1 * 4 + r] * B[c * 4 + 1];
+      s = s + A[2 * 4 + r] * B[c * 4 + 2];
+      s = s + A[3 * 4 + r] * B[c * 4 + 3];
+      R[c * 4 + r] = s;
+    }
+}
+
+int fillFrameParams(althea_cuda_ctx* ctx, const althea_global_uniforms* u, const althea_gbuffer* gb, const althea_ibl* ibl,
+                    uint64_t lightsBuf, uint64_t shadow, uint64_t reflection, bool needPosition, FrameParams* P) {
+  if (!u || !gb || !ibl) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "uniforms, gbuffer and ibl must be non-null");
+  memset(P, 0, sizeof *P);
+  P->g = *u;
+  matmul44(u->projection, u->view, P->projView);
+  Resource *depth, *position, *normal, *albedo, *mro, *env, *pre, *irr, *lut, *refl, *sh;
+  int rc;
+  if ((rc = getImage(ctx, gb->normal, ALTHEA_FORMAT_R16G16B16A16_SFLOAT, "gbuffer.normal", &normal))) return rc;
+  if ((rc = getImage(ctx, gb->albedo, ALTHEA_FORMAT_R8G8B8A8_UNORM, "gbuffer.albedo", &albedo))) return rc;
+  if ((rc = getImage(ctx, gb->mro, ALTHEA_FORMAT_R8G8B8A8_UNORM, "gbuffer.mro", &mro))) return rc;
+  if ((rc = getImage(ctx, gb->depth, ALTHEA_FORMAT_R32_SFLOAT, "gbuffer.depth", &depth, needPosition))) return rc;
+  if ((rc = getImage(ctx, gb->position, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "gbuffer.position", &position, !needPosition))) return rc;
+  if ((rc = getImage(ctx, ibl->env, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "ibl.env", &env))) return rc;
+  if ((rc = getImage(ctx, ibl->prefiltered, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "ibl.prefiltered", &pre))) return rc;
+  if ((rc = getImage(ctx, ibl->irradiance, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "ibl.irradiance", &irr))) return rc;
+  if ((rc = getImage(ctx, ibl->brdf_lut, ALTHEA_FORMAT_R8G8B8A8_UNORM, "ibl.brdf_lut", &lut))) return rc;
+  if ((rc = getImage(ctx, reflection, ALTHEA_FORMAT_R16G16B16A16_SFLOAT, "reflection", &refl))) return rc;
+  if ((rc = getImage(ctx, shadow, ALTHEA_FORMAT_R32_SFLOAT, "shadow_cube_array", &sh, true))) return rc;
+  P->W = (int)normal->w;
+  P->H = (int)normal->h;
+  auto sameSize = [&](Resource* r) { return !r || (r->w == normal->w && r->h == normal->h); };
+  if (!sameSize(albedo) || !sameSize(mro) || !sameSize(depth) || !sameSize(position) || !sameSize(refl))
+    return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "G-buffer and reflection images must all be %ux%u", normal->w, normal->h);
+  levelView(*normal, 0, 0, &P->normal);
+  levelView(*albedo, 0, 0, &P->albedo);
+  levelView(*mro, 0, 0, &P->mro);
+  if (depth) levelView(*depth, 0, 0, &P->depth);
+  if (position) levelView(*position, 0, 0, &P->position);
+  levelView(*env, 0, 0, &P->env);
+  levelView(*irr, 0, 0, &P->irr);
+  levelView(*lut, 0, 0, &P->lut);
+  if (!chainView(*pre, 0, &P->pre) || !chainView(*refl, 0, &P->refl)) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "too many mip levels");
+  if (u->lightCount < 0) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "lightCount < 0");
+  if (u->lightCount > 0) {
+    Resource* lb = find(ctx, lightsBuf, ResKind::Buffer);
+    if (!lb) return fail(ctx, ALTHEA_ERR_BAD_HANDLE, "lights_buf %llu is not a live buffer", (unsigned long long)lightsBuf);
+    if (lb->bytes < (size_t)u->lightCount * sizeof(althea_point_light))
+      return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "lights_buf holds %zu bytes, lightCount=%d needs %zu", lb->bytes, u->lightCount,
+                  (size_t)u->lightCount * sizeof(althea_point_light));
+    P->lights = static_cast<const float*>(lb->dptr);
+    if (sh) {
+      if (sh->layers < 6u * (uint32_t)u->lightCount || sh->w != sh->h)
+        return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "shadow_cube_array needs square faces and >= %d layers (has %u)", 6 * u->lightCount, sh->layers);
+      levelView(*sh, 0, 0, &P->shadow);
+      ImgView l1;
+      P->shadowLayerStride = sh->layers > 1 && levelView(*sh, 0, 1, &l1) ? (size_t)((const char*)l1.ptr - (const char*)P->shadow.ptr) : 0;
+      P->shadowRes = (int)sh->w;
+    }
+  }
+  return ALTHEA_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int althea_cuda_abi_version(void) { return ALTHEA_CUDA_ABI_VERSION; }
+
+int althea_cuda_create(althea_cuda_ctx** out_ctx, int cuda_device, const uint8_t vk_device_uuid[16]) {
+  if (!out_ctx) return fail(nullptr, ALTHEA_ERR_INVALID_ARGUMENT, "out_ctx is null");
+  *out_ctx = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, ALTHEA_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(e));
+  if (cuda_device < 0 || cuda_device >= count) return fail(nullptr, ALTHEA_ERR_INVALID_ARGUMENT, "cuda_device %d out of range [0,%d)", cuda_device, count);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, cuda_device)) != cudaSuccess) return fail(nullptr, ALTHEA_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, ALTHEA_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library carries sm_100a code only", cuda_device, prop.major, prop.minor);
+  if (vk_device_uuid && memcmp(vk_device_uuid, prop.uuid.bytes, 16) != 0)
+    return fail(nullptr, ALTHEA_ERR_INVALID_ARGUMENT, "CUDA device %d is not the Vulkan device (deviceUUID mismatch)", cuda_device);
+  if ((e = cudaSetDevice(cuda_device)) != cudaSuccess) return fail(nullptr, ALTHEA_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  althea_cuda_ctx* ctx = new althea_cuda_ctx();
+  ctx->device = cuda_device;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, ALTHEA_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  *out_ctx = ctx;
+  return ALTHEA_OK;
+}
+
+void althea_cuda_destroy(althea_cuda_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  drainTimings(ctx);
+  for (auto& kv : ctx->resources) {
+    Resource& r = kv.second;
+    if (r.extSem) cudaDestroyExternalSemaphore(r.extSem);
+    if (r.extMem) cudaDestroyExternalMemory(r.extMem);
+    else if (r.owned && r.dptr) cudaFree(r.dptr);
+  }
+  for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
+  if (ctx->aoScratch) cudaFree(ctx->aoScratch);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* althea_cuda_last_error(const althea_cuda_ctx* ctx) { return ctx ? ctx->lastError.c_str() : g_createError.c_str(); }
+
+int althea_cuda_set_flags(althea_cuda_ctx* ctx, uint32_t flags) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  ctx->flags = flags;
+  return ALTHEA_OK;
+}
+
+int althea_cuda_enable_timing(althea_cuda_ctx* ctx, int enable) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  ctx->timing = enable != 0;
+  return ALTHEA_OK;
+}
+int althea_cuda_get_timings(althea_cuda_ctx* ctx, const char** names, float* total_ms, uint32_t* launches, int cap) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  drainTimings(ctx);
+  int n = 0;
+  for (const char* name : ctx->totalNames) {
+    if (n >= cap) break;
+    auto& t = ctx->totals[name];
+    if (names) names[n] = name;
+    if (total_ms) total_ms[n] = (float)t.first;
+    if (launches) launches[n] = t.second;
+    ++n;
+  }
+  return n;
+}
+int althea_cuda_reset_timings(althea_cuda_ctx* ctx) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  drainTimings(ctx);
+  ctx->totals.clear();
+  ctx->totalNames.clear();
+  return ALTHEA_OK;
+}
+uint64_t althea_cuda_launch_count(const althea_cuda_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+size_t althea_cuda_image_bytes(uint32_t vk_format, uint32_t w, uint32_t h, uint32_t mips, uint32_t layers) {
+  if (!bytesPerTexel(vk_format) || !w || !h || !mips || !layers) return 0;
+  return chainBytes(vk_format, w, h, mips) * layers;
+}
+
+static int registerImage(althea_cuda_ctx* ctx, Resource& r, size_t pitch, size_t available, uint64_t* out_handle) {
+  size_t bpp = bytesPerTexel(r.format);
+  if (!bpp) return fail(ctx, ALTHEA_ERR_UNSUPPORTED, "VkFormat %u is not on the deferred path", r.format);
+  if (!r.w || !r.h || !r.mips || !r.layers) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "image extent/mips/layers must be non-zero");
+  if (r.mips > (uint32_t)kMaxMips) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "mips %u > %d", r.mips, kMaxMips);
+  size_t tight = (size_t)r.w * bpp;
+  if (pitch == 0) pitch = tight;
+  if (pitch < tight || (pitch % bpp) != 0) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "pitch %zu invalid for width %u x %zu B", pitch, r.w, bpp);
+  if (r.mips > 1 && pitch != tight) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "mip chains must be tightly packed (pitch %zu != %zu)", pitch, tight);
+  r.pitch0 = pitch;
+  r.bytes = (r.mips == 1 ? pitch * r.h : chainBytes(r.format, r.w, r.h, r.mips)) * r.layers;
+  if (available && available < r.bytes) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "image needs %zu bytes, only %zu provided", r.bytes, available);
+  if (((uintptr_t)r.dptr % 16) != 0 || (pitch % (bpp < 16 ? bpp : 16)) != 0)
+    return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "image base must be 16-byte aligned");
+  r.kind = ResKind::Image;
+  uint64_t h = ctx->nextHandle++;
+  ctx->resources[h] = r;
+  *out_handle = h;
+  return ALTHEA_OK;
+}
+
+int althea_cuda_import_image(althea_cuda_ctx* ctx, int fd, uint64_t alloc_size, uint64_t offset, uint32_t vk_format, uint32_t w, uint32_t h,
+                             uint32_t mips, uint32_t layers, uint32_t flags, uint64_t pitch, uint64_t* out_handle) {
+  if (!ctx || !out_handle) return ALTHEA_ERR_INVALID_ARGUMENT;
+  if (flags & ALTHEA_IMAGE_OPTIMAL_TILING)
+    return fail(ctx, ALTHEA_ERR_UNSUPPORTED,
+                "optimal-tiled images cannot be mapped as linear memory; create the image with VK_IMAGE_TILING_LINEAR or copy it to an "
+                "exportable buffer (INTEGRATION.md)");
+  cudaExternalMemoryHandleDesc hd;
+  memset(&hd, 0, sizeof hd);
+  hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+  hd.handle.fd = fd;
+  hd.size = alloc_size;
+  Resource r;
+  CUDA_TRY(ctx, cudaImportExternalMemory(&r.extMem, &hd)); // on success CUDA owns the fd
+  cudaExternalMemoryBufferDesc bd;
+  memset(&bd, 0, sizeof bd);
+  bd.offset = offset;
+  bd.size = alloc_size - offset;
+  cudaError_t e = cudaExternalMemoryGetMappedBuffer(&r.dptr, r.extMem, &bd);
+  if (e != cudaSuccess) {
+    cudaDestroyExternalMemory(r.extMem);
+    return fail(ctx, ALTHEA_ERR_CUDA, "cudaExternalMemoryGetMappedBuffer: %s", cudaGetErrorString(e));
+  }
+  r.format = vk_format; r.w = w; r.h = h; r.mips = mips; r.layers = layers;
+  int rc = registerImage(ctx, r, (size_t)pitch, (size_t)(alloc_size - offset), out_handle);
+  if (rc != ALTHEA_OK) cudaDestroyExternalMemory(r.extMem);
+  return rc;
+}
+
+int althea_cuda_import_buffer(althea_cuda_ctx* ctx, int fd, uint64_t size, uint64_t offset, uint64_t* out_handle) {
+  if (!ctx || !out_handle) return ALTHEA_ERR_INVALID_ARGUMENT;
+  cudaExternalMemoryHandleDesc hd;
+  memset(&hd, 0, sizeof hd);
+  hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+  hd.handle.fd = fd;
+  hd.size = size;
+  Resource r;
+  CUDA_TRY(ctx, cudaImportExternalMemory(&r.extMem, &hd));
+  cudaExternalMemoryBufferDesc bd;
+  memset(&bd, 0, sizeof bd);
+  bd.offset = offset;
+  bd.size = size - offset;
+  cudaError_t e = cudaExternalMemoryGetMappedBuffer(&r.dptr, r.extMem, &bd);
+  if (e != cudaSuccess) {
+    cudaDestroyExternalMemory(r.extMem);
+    return fail(ctx, ALTHEA_ERR_CUDA, "cudaExternalMemoryGetMappedBuffer: %s", cudaGetErrorString(e));
+  }
+  r.kind = ResKind::Buffer;
+  r.bytes = (size_t)(size - offset);
+  uint64_t h = ctx->nextHandle++;
+  ctx->resources[h] = r;
+  *out_handle = h;
+  return ALTHEA_OK;
+}
+
+int althea_cuda_import_semaphore(althea_cuda_ctx* ctx, int fd, int is_timeline, uint64_t* out_handle) {
+  if (!ctx || !out_handle) return ALTHEA_ERR_INVALID_ARGUMENT;
+  cudaExternalSemaphoreHandleDesc sd;
+  memset(&sd, 0, sizeof sd);
+  sd.type = is_timeline ? cudaExternalSemaphoreHandleTypeTimelineSemaphoreFd : cudaExternalSemaphoreHandleTypeOpaqueFd;
+  sd.handle.fd = fd;
+  Resource r;
+  CUDA_TRY(ctx, cudaImportExternalSemaphore(&r.extSem, &sd));
+  r.kind = ResKind::Semaphore;
+  r.timeline = is_timeline != 0;
+  uint64_t h = ctx->nextHandle++;
+  ctx->resources[h] = r;
+  *out_handle = h;
+  return ALTHEA_OK;
+}
+
+int althea_cuda_wrap_linear_image(althea_cuda_ctx* ctx, void* dptr, size_t pitch, uint32_t vk_format, uint32_t w, uint32_t h, uint32_t mips,
+                                  uint32_t layers, uint64_t* out_handle) {
+  if (!ctx || !out_handle) return ALTHEA_ERR_INVALID_ARGUMENT;
+  if (!dptr) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "dptr is null");
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, dptr);
+  if (e != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+    cudaGetLastError();
+    return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "dptr %p is not device memory", dptr);
+  }
+  Resource r;
+  r.dptr = dptr;
+  r.format = vk_format; r.w = w; r.h = h; r.mips = mips; r.layers = layers;
+  return registerImage(ctx, r, pitch, 0, out_handle);
+}
+
+int althea_cuda_wrap_buffer(althea_cuda_ctx* ctx, void* dptr, size_t size, uint64_t* out_handle) {
+  if (!ctx || !out_handle) return ALTHEA_ERR_INVALID_ARGUMENT;
+  if (!dptr || !size) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "dptr/size is null");
+  Resource r;
+  r.kind = ResKind::Buffer;
+  r.dptr = dptr;
+  r.bytes = size;
+  uint64_t h = ctx->nextHandle++;
+  ctx->resources[h] = r;
+  *out_handle = h;
+  return ALTHEA_OK;
+}
+
+int althea_cuda_create_image(althea_cuda_ctx* ctx, uint32_t vk_format, uint32_t w, uint32_t h, uint32_t mips, uint32_t layers, uint64_t* out_handle) {
+  if (!ctx || !out_handle) return ALTHEA_ERR_INVALID_ARGUMENT;
+  size_t bytes = althea_cuda_image_bytes(vk_format, w, h, mips, layers);
+  if (!bytes) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "bad image description (format %u, %ux%u, mips %u, layers %u)", vk_format, w, h, mips, layers);
+  Resource r;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaMalloc(&r.dptr, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  }
+  r.owned = true;
+  r.format = vk_format; r.w = w; r.h = h; r.mips = mips; r.layers = layers;
+  int rc = registerImage(ctx, r, 0, bytes, out_handle);
+  if (rc != ALTHEA_OK) cudaFree(r.dptr);
+  return rc;
+}
+
+int althea_cuda_create_buffer(althea_cuda_ctx* ctx, size_t size, uint64_t* out_handle) {
+  if (!ctx || !out_handle || !size) return ALTHEA_ERR_INVALID_ARGUMENT;
+  Resource r;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaMalloc(&r.dptr, size);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu): %s", size, cudaGetErrorString(e));
+  }
+  r.kind = ResKind::Buffer;
+  r.owned = true;
+  r.bytes = size;
+  uint64_t h = ctx->nextHandle++;
+  ctx->resources[h] = r;
+  *out_handle = h;
+  return ALTHEA_OK;
+}
+
+static Resource* findMem(althea_cuda_ctx* ctx, uint64_t handle) {
+  auto it = ctx->resources.find(handle);
+  if (it == ctx->resources.end() || it->second.kind == ResKind::Semaphore) return nullptr;
+  return &it->second;
+}
+
+int althea_cuda_upload(althea_cuda_ctx* ctx, uint64_t handle, const void* host, size_t bytes, void* stream) {
+  if (!ctx || !host) return ALTHEA_ERR_INVALID_ARGUMENT;
+  Resource* r = findMem(ctx, handle);
+  if (!r) return fail(ctx, ALTHEA_ERR_BAD_HANDLE, "upload: handle %llu is not live memory", (unsigned long long)handle);
+  if (bytes > r->bytes) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "upload of %zu bytes into a %zu-byte resource", bytes, r->bytes);
+  CUDA_TRY(ctx, cudaMemcpyAsync(r->dptr, host, bytes, cudaMemcpyHostToDevice, stream ? (cudaStream_t)stream : ctx->stream));
+  return ALTHEA_OK;
+}
+int althea_cuda_download(althea_cuda_ctx* ctx, uint64_t handle, void* host, size_t bytes, void* stream) {
+  if (!ctx || !host) return ALTHEA_ERR_INVALID_ARGUMENT;
+  Resource* r = findMem(ctx, handle);
+  if (!r) return fail(ctx, ALTHEA_ERR_BAD_HANDLE, "download: handle %llu is not live memory", (unsigned long long)handle);
+  if (bytes > r->bytes) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "download of %zu bytes from a %zu-byte resource", bytes, r->bytes);
+  CUDA_TRY(ctx, cudaMemcpyAsync(host, r->dptr, bytes, cudaMemcpyDeviceToHost, stream ? (cudaStream_t)stream : ctx->stream));
+  return ALTHEA_OK;
+}
+int althea_cuda_device_pointer(althea_cuda_ctx* ctx, uint64_t handle, void** out_dptr, size_t* out_bytes) {
+  if (!ctx || !out_dptr) return ALTHEA_ERR_INVALID_ARGUMENT;
+  Resource* r = findMem(ctx, handle);
+  if (!r) return fail(ctx, ALTHEA_ERR_BAD_HANDLE, "handle %llu is not live memory", (unsigned long long)handle);
+  *out_dptr = r->dptr;
+  if (out_bytes) *out_bytes = r->bytes;
+  return ALTHEA_OK;
+}
+
+int althea_cuda_release(althea_cuda_ctx* ctx, uint64_t handle) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  auto it = ctx->resources.find(handle);
+  if (it == ctx->resources.end()) return fail(ctx, ALTHEA_ERR_BAD_HANDLE, "release: handle %llu is not live", (unsigned long long)handle);
+  Resource& r = it->second;
+  if (r.extSem) cudaDestroyExternalSemaphore(r.extSem);
+  if (r.extMem) cudaDestroyExternalMemory(r.extMem);
+  else if (r.owned && r.dptr) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(r.dptr);
+  }
+  ctx->resources.erase(it);
+  return ALTHEA_OK;
+}
+
+int althea_cuda_synchronize(althea_cuda_ctx* ctx, void* stream) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  CUDA_TRY(ctx, cudaStreamSynchronize(stream ? (cudaStream_t)stream : ctx->stream));
+  return ALTHEA_OK;
+}
+
+// ---- per-frame stages -----------------------------------------------------------------------------------------------
+int althea_cuda_ssr_capture(althea_cuda_ctx* ctx, const althea_global_uniforms* uniforms, const althea_gbuffer* gbuffer, const althea_ibl* ibl,
+                            uint64_t lights_buf, uint64_t shadow_cube_array, uint64_t reflection, const althea_sync* sync) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  FrameParams P;
+  int rc = fillFrameParams(ctx, uniforms, gbuffer, ibl, lights_buf, shadow_cube_array, reflection, /*needPosition=*/false, &P);
+  if (rc) return rc;
+  cudaStream_t stream;
+  if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
+  timedLaunch(ctx, "ssr_capture", stream, [&] { parity ? althea_parity::launch_ssr_capture(P, stream) : althea_fast::launch_ssr_capture(P, stream); });
+  return endWork(ctx, sync, stream);
+}
+
+int althea_cuda_glossy_convolve(althea_cuda_ctx* ctx, uint64_t reflection, const althea_sync* sync) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  Resource* refl;
+  int rc = getImage(ctx, reflection, ALTHEA_FORMAT_R16G16B16A16_SFLOAT, "reflection", &refl);
+  if (rc) return rc;
+  cudaStream_t stream;
+  if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
+  for (uint32_t level = 1; level < refl->mips; ++level) { // ReflectionBuffer.cpp:224-278
+    ConvolveParams C;
+    levelView(*refl, level - 1, 0, &C.src);
+    levelView(*refl, level, 0, &C.dst);
+    C.vertical = (int)(level & 1u);
+    timedLaunch(ctx, "glossy_convolve", stream, [&] { parity ? althea_parity::launch_glossy_convolve(C, stream) : althea_fast::launch_glossy_convolve(C, stream); });
+  }
+  return endWork(ctx, sync, stream);
+}
+
+int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniforms* uniforms, const althea_gbuffer* gbuffer, const althea_ibl* ibl,
+                               uint64_t lights_buf, uint64_t shadow_cube_array, uint64_t reflection, uint64_t out_color, uint64_t ao_counts,
+                               uint32_t flags, const althea_sync* sync) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  FrameParams P;
+  int rc = fillFrameParams(ctx, uniforms, gbuffer, ibl, lights_buf, shadow_cube_array, reflection, /*needPosition=*/true, &P);
+  if (rc) return rc;
+  Resource *out, *ao;
+  if ((rc = getImage(ctx, out_color, 0, "out_color", &out))) return rc;
+  if (out->format != ALTHEA_FORMAT_R16G16B16A16_SFLOAT && out->format != ALTHEA_FORMAT_R32G32B32A32_SFLOAT)
+    return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "out_color must be RGBA16F or RGBA32F (has VkFormat %u)", out->format);
+  if ((int)out->w != P.W || (int)out->h != P.H) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "out_color must be %dx%d", P.W, P.H);
+  levelView(*out, 0, 0, &P.out);
+  P.outIsF32 = out->format == ALTHEA_FORMAT_R32G32B32A32_SFLOAT;
+  P.flags = flags;
+  if ((rc = getImage(ctx, ao_counts, ALTHEA_FORMAT_R8_UINT, "ao_counts", &ao, true))) return rc;
+  if ((flags & ALTHEA_SHADE_AO_FROM_IMAGE) && !ao) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "AO_FROM_IMAGE needs ao_counts");
+  const bool needAo = !(flags & ALTHEA_SHADE_NO_SSAO);
+  if (needAo) {
+    if (ao) {
+      if ((int)ao->w != P.W || (int)ao->h != P.H) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "ao_counts must be %dx%d", P.W, P.H);
+      levelView(*ao, 0, 0, &P.ao);
+    } else {
+      size_t need = (size_t)P.W * P.H;
+      if (ctx->aoScratchBytes < need) {
+        if (ctx->aoScratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->aoScratch); ctx->aoScratch = nullptr; ctx->aoScratchBytes = 0; }
+        cudaError_t e = cudaMalloc(&ctx->aoScratch, need);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(ao scratch %zu): %s", need, cudaGetErrorString(e)); }
+        ctx->aoScratchBytes = need;
+      }
+      P.ao.ptr = ctx->aoScratch; P.ao.w = P.W; P.ao.h = P.H; P.ao.pitch = P.W;
+    }
+  }
+  cudaStream_t stream;
+  if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
+  if (needAo && !(flags & ALTHEA_SHADE_AO_FROM_IMAGE))
+    timedLaunch(ctx, "ssao", stream, [&] { parity ? althea_parity::launch_ssao(P, stream) : althea_fast::launch_ssao(P, stream); });
+  timedLaunch(ctx, "deferred_shade", stream, [&] { parity ? althea_parity::launch_deferred_shade(P, stream) : althea_fast::launch_deferred_shade(P, stream); });
+  return endWork(ctx, sync, stream);
+}
+
+// ---- IBL precompute -------------------------------------------------------------------------------------------------
+int althea_cuda_generate_mips(althea_cuda_ctx* ctx, uint64_t image, const althea_sync* sync) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  Resource* img;
+  int rc = getImage(ctx, image, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "image", &img);
+  if (rc) return rc;
+  cudaStream_t stream;
+  if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  for (uint32_t layer = 0; layer < img->layers; ++layer)
+    for (uint32_t level = 1; level < img->mips; ++level) {
+      MipGenParams M;
+      levelView(*img, level - 1, layer, &M.src);
+      levelView(*img, level, layer, &M.dst);
+      M.channels = 4;
+      timedLaunch(ctx, "mip_downsample", stream, [&] { althea_iblk::launch_mip_downsample(M, stream); });
+    }
+  return endWork(ctx, sync, stream);
+}
+
+int althea_cuda_ibl_precompute(althea_cuda_ctx* ctx, uint64_t env_with_mips, const althea_ibl_precompute_desc* desc, uint64_t out_irradiance,
+                               uint64_t out_prefiltered, const althea_sync* sync) {
+  if (!ctx || !desc) return ALTHEA_ERR_INVALID_ARGUMENT;
+  Resource *env, *irr, *pre;
+  int rc;
+  if ((rc = getImage(ctx, env_with_mips, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "env_with_mips", &env))) return rc;
+  if ((rc = getImage(ctx, out_irradiance, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "out_irradiance", &irr, true))) return rc;
+  if ((rc = getImage(ctx, out_prefiltered, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "out_prefiltered", &pre, true))) return rc;
+  if (desc->layout > ALTHEA_IBL_LAYOUT_CUBE || desc->sequence > ALTHEA_IBL_SEQ_HAMMERSLEY) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "bad layout/sequence");
+  const bool cube = desc->layout == ALTHEA_IBL_LAYOUT_CUBE;
+  if (cube && ((irr && irr->layers != 6) || (pre && pre->layers != 6))) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "cube outputs need 6 layers");
+  IblParams I;
+  memset(&I, 0, sizeof I);
+  if (!chainView(*env, 0, &I.env)) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "env has too many mips");
+  I.layout = (int)desc->layout;
+  I.sequence = (int)desc->sequence;
+  I.numSamples = desc->prefilter_samples ? (int)desc->prefilter_samples : 10000;
+  I.thetaSamples = desc->theta_samples ? (int)desc->theta_samples : 300;
+  // GenIrradianceMap.comp:119-124 with width/height = the env map's (ImageBasedLighting.cpp:328-333)
+  I.phiSamples = (int)((float)env->h * (float)I.thetaSamples / (float)env->w);
+  I.mip = log2f((float)env->w / (float)I.thetaSamples);
+  cudaStream_t stream;
+  if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  const uint32_t layers = cube ? 6u : 1u;
+  if (irr)
+    for (uint32_t face = 0; face < layers; ++face) {
+      levelView(*irr, 0, face, &I.out);
+      I.face = (int)face;
+      timedLaunch(ctx, "ibl_irradiance", stream, [&] { althea_iblk::launch_ibl_irradiance(I, stream); });
+    }
+  if (pre)
+    for (uint32_t level = 0; level < pre->mips; ++level) {
+      // equirect (reference): roughness = i/4 for the 5 images (ImageBasedLighting.cpp:384); cube: k/(n-1)
+      I.roughness = cube ? (pre->mips > 1 ? (float)level / (float)(pre->mips - 1) : 0.0f) : (float)level / 4.0f;
+      for (uint32_t face = 0; face < layers; ++face) {
+        levelView(*pre, level, face, &I.out);
+        I.face = (int)face;
+        timedLaunch(ctx, "ibl_prefilter", stream, [&] { althea_iblk::launch_ibl_prefilter(I, stream); });
+      }
+    }
+  return endWork(ctx, sync, stream);
+}
+
+int althea_cuda_brdf_lut(althea_cuda_ctx* ctx, uint32_t samples, uint64_t out_lut, const althea_sync* sync) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  Resource* lut;
+  int rc = getImage(ctx, out_lut, 0, "out_lut", &lut);
+  if (rc) return rc;
+  if (lut->format != ALTHEA_FORMAT_R8G8B8A8_UNORM && lut->format != ALTHEA_FORMAT_R32G32B32A32_SFLOAT)
+    return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "out_lut must be RGBA8 or RGBA32F");
+  if (lut->w != lut->h) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "out_lut must be square");
+  LutParams L;
+  levelView(*lut, 0, 0, &L.out);
+  L.outIsF32 = lut->format == ALTHEA_FORMAT_R32G32B32A32_SFLOAT;
+  L.samples = samples ? (int)samples : 1024;
+  cudaStream_t stream;
+  if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  timedLaunch(ctx, "brdf_lut", stream, [&] { althea_iblk::launch_brdf_lut(L, stream); });
+  return endWork(ctx, sync, stream);
+}
+
+} // extern "C"

@@ -1,0 +1,324 @@
+// Per-frame kernels of the deferred screen-space path, sm_100a.
+//
+//   ssr_capture_kernel      <- Shaders/SSR.vert + SSR.frag (reflection mip 0)
+//   glossy_convolve_kernel  <- Shaders/SSRGlossyConvolve.comp (one launch per mip, ReflectionBuffer.cpp:224-278)
+//   ssao_kernel             <- Shaders/SSAO.glsl computeSSAO (occluded-ray count per pixel)
+//   deferred_shade_kernel   <- Shaders/DeferredPass.vert/.frag + PBR/PBRMaterial.glsl pbrMaterial
+//
+// Compiled twice (fast / parity), see device_math.cuh. One thread per pixel; a warp covers a 16x2 pixel strip, so
+// G-buffer reads are 128-byte coalesced rows (128-bit loads for position, 64-bit for normal/reflection).
+#include "device_math.cuh"
+#include "launchers.h"
+
+namespace ALTHEA_NS {
+
+// ---- run-time equirect IBL lookups: CLAMP_TO_EDGE (ImageBasedLighting.cpp:469-475,519-524,556-560) ----------------
+ADEV V2 equirectUv(V3 d) { // PBRMaterial.glsl:5-7
+  float yaw = atan2f(d.z, d.x);
+  float pitch = -atan2f(d.y, sqrtf(d.x * d.x + d.z * d.z));
+  V2 uv;
+  uv.x = (0.5f * yaw) / kPi + 0.5f;
+  uv.y = pitch / kPi + 0.5f;
+  return uv;
+}
+ADEV V3 sampleEnvMapLod0(const FrameParams& P, V3 dir) { // DeferredPass.frag:33-39
+  V2 uv = equirectUv(dir);
+  return xyz(bilinear<FmtRGBA32F, AddrClamp>(P.env, uv.x, uv.y));
+}
+ADEV V3 sampleEnvMapRough(const FrameParams& P, V3 dir, float roughness) { // PBRMaterial.glsl:4-11
+  V2 uv = equirectUv(dir);
+  return xyz(trilinear<FmtRGBA32F, AddrClamp>(P.pre, uv.x, uv.y, 4.0f * roughness));
+}
+ADEV V3 sampleIrrMap(const FrameParams& P, V3 n) { // PBRMaterial.glsl:13-19
+  V2 uv = equirectUv(n);
+  return xyz(bilinear<FmtRGBA32F, AddrClamp>(P.irr, uv.x, uv.y));
+}
+
+// cube-array lookup (Vulkan face selection table; the bilinear footprint clamps inside the face)
+ADEV float sampleShadowCube(const FrameParams& P, V3 q, int light) {
+  float ax = fabsf(q.x), ay = fabsf(q.y), az = fabsf(q.z);
+  int face;
+  float sc, tc, ma;
+  if (ax >= ay && ax >= az) { ma = ax; if (q.x >= 0.0f) { face = 0; sc = -q.z; tc = -q.y; } else { face = 1; sc = q.z; tc = -q.y; } }
+  else if (ay >= az)        { ma = ay; if (q.y >= 0.0f) { face = 2; sc = q.x; tc = q.z; } else { face = 3; sc = q.x; tc = -q.z; } }
+  else                      { ma = az; if (q.z >= 0.0f) { face = 4; sc = q.x; tc = -q.y; } else { face = 5; sc = -q.x; tc = -q.y; } }
+  float s = 0.5f * sc / ma + 0.5f, t = 0.5f * tc / ma + 0.5f;
+  ImgView layer = P.shadow;
+  layer.ptr = static_cast<const char*>(P.shadow.ptr) + (size_t)(6 * light + face) * P.shadowLayerStride;
+  return bilinearR32F<AddrClamp>(layer, s, t);
+}
+
+// ---- PBRMaterial.glsl:41-70 ---------------------------------------------------------------------------------------
+ADEV float ndfGgx(float NdotH, float a2) {
+  float tmp = NdotH * NdotH * (a2 - 1.0f) + 1.0f;
+  float denom = kPi * tmp * tmp;
+  return a2 / denom;
+}
+ADEV float pow5(float x) {
+#ifdef ALTHEA_PARITY
+  return powf(x, 5.0f);
+#else
+  float x2 = x * x;
+  return x2 * x2 * x;
+#endif
+}
+ADEV V3 fresnelSchlick(float NdotV, V3 F0, float roughness) {
+  float om = 1.0f - roughness;
+  V3 m = mk3(max_glsl(om, F0.x), max_glsl(om, F0.y), max_glsl(om, F0.z));
+  return F0 + (m - F0) * pow5(1.0f - NdotV);
+}
+ADEV float geometrySchlickGgx(float NdotV, float k) { return NdotV / (NdotV * (1.0f - k) + k); }
+ADEV float geometrySmith(float NdotL, float NdotV, float k) { return geometrySchlickGgx(NdotV, k) * geometrySchlickGgx(NdotL, k); }
+
+// PBRMaterial.glsl:72-162 with the current (worldPos, V, N, ...) signature
+ADEV V3 pbrMaterial(const FrameParams& P, V3 worldPos, V3 V, V3 N, V3 baseColor, V3 reflectedColor, V3 irradianceColor, float metallic,
+                    float roughness, float ambientOcclusion) {
+  float NdotV = max_glsl(dot3(N, -V), 0.0f);
+  V3 F0 = mix3(mk3(0.04f, 0.04f, 0.04f), baseColor, metallic);
+  float a = roughness * roughness;
+  float a2 = a * a;
+  float kDirect = (a + 1.0f) * (a + 1.0f) / 8.0f;
+  V3 color = mk3(0.0f, 0.0f, 0.0f);
+  const V3 one = mk3(1.0f, 1.0f, 1.0f);
+  V3 dielectricBase = mix3(baseColor, mk3(0.0f, 0.0f, 0.0f), metallic);
+  {
+    V3 F = fresnelSchlick(NdotV, F0, roughness);
+    V3 diffuseColor = (one - F) * dielectricBase;
+    V4 lut = bilinear<FmtRGBA8, AddrClamp>(P.lut, NdotV, roughness);
+    V3 ambientSpecular = reflectedColor * (F * lut.x + mk3(lut.y, lut.y, lut.y));
+    color = color + (irradianceColor * diffuseColor + ambientSpecular) * ambientOcclusion;
+  }
+  const int lightCount = P.g.lightCount;
+  for (int i = 0; i < lightCount; ++i) {
+    const float4* lp = reinterpret_cast<const float4*>(P.lights) + 2 * i;
+    float4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
+    V3 L = mk3(l0.x, l0.y, l0.z) - worldPos;
+    float LdistSq = dot3(L, L);
+    float Ldist = sqrtf(LdistSq);
+    L = L / Ldist;
+    if (P.shadowRes > 0) {
+      float closestDepth = sampleShadowCube(P, mk3(L.x, -L.y, -L.z), i);
+      closestDepth *= 1000.0f;
+      if (closestDepth < (Ldist - 0.5f)) continue;
+    }
+    V3 radiance = mk3(l1.x, l1.y, l1.z) / LdistSq;
+    V3 H = normalize3(V + L);
+    float NdotL = max_glsl(dot3(N, L), 0.0f);
+    float NdotH = max_glsl(dot3(N, H), 0.0f);
+    V3 F = fresnelSchlick(NdotH, F0, roughness);
+    V3 diffuseColor = ((one - F) * dielectricBase) / kPi;
+    V3 specularColor = ((ndfGgx(NdotH, a2) * F) * geometrySmith(NdotL, NdotV, kDirect)) / (4.0f * NdotL * NdotV + 0.0001f);
+    color = color + ((diffuseColor + specularColor) * radiance) * NdotL;
+  }
+  return color;
+}
+
+// DeferredPass.vert:10-22 == SSR.vert:15-23 at the pixel centre
+ADEV V3 viewDirection(const FrameParams& P, float u, float v) {
+  V4 p = mul44(P.g.inverseProjection, mk4(u * 2.0f - 1.0f, v * 2.0f - 1.0f, 0.0f, 1.0f));
+  return mul33(P.g.inverseView, xyz(p));
+}
+
+// Misc/ReconstructPosition.glsl:4-22
+ADEV V3 reconstructPosition(const FrameParams& P, float u, float v, float dRaw) {
+  const float near = 0.01f, far = 1000.0f;
+  float d = far * near / (dRaw * (far - near) - far);
+  V4 dirH = mul44(P.g.inverseProjection, mk4(2.0f * u - 1.0f, 2.0f * v - 1.0f, 2.0f, 1.0f));
+  V3 cam = mk3(P.g.inverseView[12], P.g.inverseView[13], P.g.inverseView[14]);
+  V3 zc = mk3(P.g.inverseView[8], P.g.inverseView[9], P.g.inverseView[10]);
+#ifdef ALTHEA_PARITY
+  V4 h = mk4(dirH.x / dirH.w, dirH.y / dirH.w, dirH.z / dirH.w, 0.0f);
+  V4 wd = mul44(P.g.inverseView, h);
+  V3 dir = normalize3(xyz(wd));
+  float f = dot3(dir, zc);
+  return cam + (d * dir) / f;
+#else
+  // normalize() cancels against the division by dot(dir, zAxis), and so does the 1/w: pos = cam + d * wd / dot(wd, z)
+  V3 wd = mul33(P.g.inverseView, xyz(dirH));
+  return cam + wd * (d / dot3(wd, zc));
+#endif
+}
+
+ADEV bool outside01(float u, float v) { return u < 0.0f || u > 1.0f || v < 0.0f || v > 1.0f; }
+ADEV V2 projectUv(const FrameParams& P, V3 p) { // 0.5 * clip.xy / clip.w + 0.5
+  V4 pe = mul44(P.projView, mk4(p.x, p.y, p.z, 1.0f));
+  V2 uv;
+  uv.x = 0.5f * pe.x / pe.w + 0.5f;
+  uv.y = 0.5f * pe.y / pe.w + 0.5f;
+  return uv;
+}
+
+// ---- SSR ------------------------------------------------------------------------------------------------------------
+ADEV V4 environmentLitSample(const FrameParams& P, V3 currentPos, float u, float v, V3 rayDir, V3 normal) { // SSR.frag:55-78
+  V3 baseColor = xyz(bilinear<FmtRGBA8, AddrClamp>(P.albedo, u, v));
+  V3 mro = xyz(bilinear<FmtRGBA8, AddrClamp>(P.mro, u, v));
+  V3 rd = normalize3(rayDir);
+  V3 reflectedDirection = reflect3(rd, normal);
+  V3 reflectedColor = sampleEnvMapRough(P, reflectedDirection, mro.y);
+  V3 irradianceColor = sampleIrrMap(P, normal);
+  V3 m = pbrMaterial(P, currentPos, rd, normal, baseColor, reflectedColor, irradianceColor, mro.x, mro.y, 1.0f);
+  return mk4(m.x, m.y, m.z, 1.0f);
+}
+
+__global__ void __launch_bounds__(256) ssr_capture_kernel(const __grid_constant__ FrameParams P) {
+  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (x >= P.W || y >= P.H) return;
+  const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
+  V4 normal4 = FmtRGBA16F::load(P.normal, x, y);
+  V4 out = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (normal4.w != 0.0f) { // SSR.frag:136-141
+    const float dOwn = __ldg(rowPtr<float>(P.depth, y) + x);
+    const V3 worldPos = reconstructPosition(P, u, v, dOwn);
+    const V3 normal = normalize3(xyz(normal4));
+    const V3 rayDir = reflect3(normalize3(viewDirection(P, u, v)), normal);
+    // raymarchGBuffer, SSR.frag:80-133
+    V2 uvEnd = projectUv(P, worldPos + rayDir * 10000.0f);
+    float dx = uvEnd.x - u, dy = uvEnd.y - v;
+    float dl = sqrtf(dx * dx + dy * dy);
+    const float stepX = (dx / dl) * 0.005f, stepY = (dy / dl) * 0.005f;
+    const V3 perpRef = normalize3(cross3(cross3(rayDir, normal), rayDir));
+    float cu = u, cv = v;
+    float prevProjection = 0.0f;
+    for (int i = 0; i < 128; ++i) {
+      cu += stepX;
+      cv += stepY;
+      if (outside01(cu, cv)) break;
+      float dRaw = bilinearR32F<AddrClamp>(P.depth, cu, cv);
+      V3 currentPos = reconstructPosition(P, cu, cv, dRaw);
+      V3 dir = normalize3(currentPos - worldPos);
+      float currentProjection = dot3(dir, perpRef);
+      float f = dot3(dir, rayDir);
+      if (currentProjection * prevProjection <= 0.0f && f > 0.999f && i > 0) {
+        V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, cu, cv)));
+        if (dot3(currentNormal, rayDir) < 0.0f) {
+          out = environmentLitSample(P, currentPos, cu, cv, rayDir, currentNormal);
+          break;
+        }
+      }
+      prevProjection = currentProjection;
+    }
+  }
+  // blend-on-write over the (0,0,0,0) clear (GraphicsPipeline.cpp:138-154): rgb*a, a
+  rowPtrW<uint2>(P.refl.level[0], y)[x] = packHalf4(mk4(out.x * out.w, out.y * out.w, out.z * out.w, out.w));
+}
+
+// ---- glossy convolve ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) glossy_convolve_kernel(const __grid_constant__ ConvolveParams C) {
+  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+  const int w = C.dst.w, h = C.dst.h;
+  if (x >= w || y >= h) return;
+  const float u = (float)x / (float)w, v = (float)y / (float)h; // texelPos / size, no half texel
+  const float resolution = (float)w;                            // width for both axes (SSRGlossyConvolve.comp:41)
+  const float dirx = C.vertical ? 0.0f : 1.0f, diry = C.vertical ? 1.0f : 0.0f;
+  const float a1x = (1.411764705882353f * dirx) / resolution, a1y = (1.411764705882353f * diry) / resolution;
+  const float a2x = (3.2941176470588234f * dirx) / resolution, a2y = (3.2941176470588234f * diry) / resolution;
+  const float a3x = (5.176470588235294f * dirx) / resolution, a3y = (5.176470588235294f * diry) / resolution;
+  V4 color = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+  color = color + bilinear<FmtRGBA16F, AddrClamp>(C.src, u, v) * 0.1964825501511404f;
+  color = color + bilinear<FmtRGBA16F, AddrClamp>(C.src, u + a1x, v + a1y) * 0.2969069646728344f;
+  color = color + bilinear<FmtRGBA16F, AddrClamp>(C.src, u - a1x, v - a1y) * 0.2969069646728344f;
+  color = color + bilinear<FmtRGBA16F, AddrClamp>(C.src, u + a2x, v + a2y) * 0.09447039785044732f;
+  color = color + bilinear<FmtRGBA16F, AddrClamp>(C.src, u - a2x, v - a2y) * 0.09447039785044732f;
+  color = color + bilinear<FmtRGBA16F, AddrClamp>(C.src, u + a3x, v + a3y) * 0.010381362401148057f;
+  color = color + bilinear<FmtRGBA16F, AddrClamp>(C.src, u - a3x, v - a3y) * 0.010381362401148057f;
+  rowPtrW<uint2>(C.dst, y)[x] = packHalf4(color);
+}
+
+// ---- SSAO -----------------------------------------------------------------------------------------------------------
+ADEV int ssaoCount(const FrameParams& P, int px, int py, float u0, float v0, V3 worldPos, V3 normal) {
+  HashRng rng;
+  rng.sx = (uint32_t)px;
+  rng.sy = (uint32_t)py;
+  const TangentFrame tbn = localToWorld(normal);
+  int ao = 0;
+  for (int ray = 0; ray < 24; ++ray) {
+    float x0 = rng.next(), x1 = rng.next(), x2 = rng.next();
+    V3 rayDir = frameApply(tbn, normalize3(mk3(2.0f * x0 - 1.0f, 2.0f * x1 - 1.0f, x2)));
+    V2 uvEnd = projectUv(P, worldPos + rayDir * 0.5f);
+    V3 perpRef = normalize3(cross3(cross3(rayDir, normal), rayDir));
+    V3 prevPos = worldPos;
+    float prevProjection = 0.0f; // i == 0 taps the pixel's own texel: currentProjection == 0 exactly
+    for (int i = 1; i < 12; ++i) {
+      float t = (float)i / 12.0f;
+      float cu = mixf(u0, uvEnd.x, t), cv = mixf(v0, uvEnd.y, t);
+      if (outside01(cu, cv)) break;
+      V3 currentPos = xyz(bilinear<FmtRGBA32F, AddrClamp>(P.position, cu, cv));
+      float currentProjection = dot3(currentPos - worldPos, perpRef);
+      float worldStep = length3(currentPos - prevPos);
+      if (currentProjection * prevProjection < 0.0f && worldStep <= 2.0f) {
+        V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, cu, cv)));
+        if (dot3(currentNormal, rayDir) < 0.0f) {
+          ao += 1;
+          break;
+        }
+      }
+      prevPos = currentPos;
+      prevProjection = currentProjection;
+    }
+  }
+  return ao;
+}
+
+__global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ FrameParams P) {
+  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (x >= P.W || y >= P.H) return;
+  V4 position = FmtRGBA32F::load(P.position, x, y);
+  uint8_t count = 255;
+  if (position.w != 0.0f) {
+    const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
+    V3 normal = normalize3(xyz(FmtRGBA16F::load(P.normal, x, y)));
+    count = (uint8_t)ssaoCount(P, x, y, u, v, xyz(position), normal);
+  }
+  rowPtrW<uint8_t>(P.ao, y)[x] = count;
+}
+
+// ---- deferred shading -----------------------------------------------------------------------------------------------
+ADEV V3 tonemap(V3 c, float exposure) {
+  return mk3(1.0f - expf(-c.x * exposure), 1.0f - expf(-c.y * exposure), 1.0f - expf(-c.z * exposure));
+}
+
+__global__ void __launch_bounds__(256) deferred_shade_kernel(const __grid_constant__ FrameParams P) {
+  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (x >= P.W || y >= P.H) return;
+  const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
+  const V3 direction = viewDirection(P, u, v);
+  V4 position = FmtRGBA32F::load(P.position, x, y);
+  V3 outc;
+  if (position.w == 0.0f) { // DeferredPass.frag:45-53
+    outc = sampleEnvMapLod0(P, direction);
+  } else {
+    V3 normal = normalize3(xyz(FmtRGBA16F::load(P.normal, x, y)));
+    V3 baseColor = xyz(FmtRGBA8::load(P.albedo, x, y));
+    V3 mro = xyz(FmtRGBA8::load(P.mro, x, y));
+    V3 vdir = normalize3(direction);
+    V3 reflectedDirection = reflect3(vdir, normal);
+    V4 reflectedColor = trilinear<FmtRGBA16F, AddrClamp>(P.refl, u, v, 4.0f * mro.y);
+    V3 envReflected = sampleEnvMapRough(P, reflectedDirection, mro.y);
+    V3 rc;
+    if (reflectedColor.w < 0.01f) rc = envReflected;
+    else rc = mix3(envReflected, xyz(reflectedColor) / reflectedColor.w, reflectedColor.w);
+    V3 irradianceColor = sampleIrrMap(P, normal);
+    if (!(P.flags & ALTHEA_SHADE_NO_SSAO)) {
+      uint8_t cnt = __ldg(rowPtr<uint8_t>(P.ao, y) + x);
+      mro.z = 1.0f - (float)cnt / 24.0f;
+    }
+    outc = pbrMaterial(P, xyz(position), vdir, normal, baseColor, rc, irradianceColor, mro.x, mro.y, mro.z);
+  }
+  if (!(P.flags & ALTHEA_SHADE_SKIP_TONEMAP)) outc = tonemap(outc, P.g.exposure);
+  if (P.outIsF32) rowPtrW<float4>(P.out, y)[x] = make_float4(outc.x, outc.y, outc.z, 1.0f);
+  else rowPtrW<uint2>(P.out, y)[x] = packHalf4(mk4(outc.x, outc.y, outc.z, 1.0f));
+}
+
+// ---- launchers ------------------------------------------------------------------------------------------------------
+static inline dim3 tileGrid(int w, int h) { return dim3((unsigned)((w + 15) / 16), (unsigned)((h + 15) / 16)); }
+
+void launch_ssr_capture(const FrameParams& P, cudaStream_t s) { ssr_capture_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
+void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s) { glossy_convolve_kernel<<<tileGrid(C.dst.w, C.dst.h), 256, 0, s>>>(C); }
+void launch_ssao(const FrameParams& P, cudaStream_t s) { ssao_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
+void launch_deferred_shade(const FrameParams& P, cudaStream_t s) { deferred_shade_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
+
+} // namespace ALTHEA_NS

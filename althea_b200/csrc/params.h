@@ -1,0 +1,64 @@
+// Kernel parameter blocks shared by the host shim (althea_cuda.cu) and the kernels. Plain structs, passed by value
+// as __grid_constant__ kernel parameters.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/althea_cuda.h"
+
+struct ImgView { // one mip level of one layer of a linear image
+  const void* ptr;
+  int w, h;
+  int pitch; // bytes
+};
+constexpr int kMaxMips = 14;
+struct ChainView {
+  ImgView level[kMaxMips];
+  int mips;
+};
+
+struct FrameParams {
+  althea_global_uniforms g; // byte-for-byte the reference's GlobalUniforms (416 B)
+  float projView[16];       // projection * view, computed once on the host in the oracle's op order
+  int W, H;
+  ImgView depth, position, normal, albedo, mro; // GBufferResources
+  ImgView env, irr, lut;                        // IBLResources
+  ChainView pre;                                // prefiltered env, 5 mips
+  ChainView refl;                               // reflection buffer mips
+  const float* lights;                          // althea_point_light[lightCount]
+  ImgView shadow;                               // layer 0 of the cube array; layer l at ptr + l*shadowLayerStride
+  size_t shadowLayerStride;
+  int shadowRes; // 0 => unshadowed
+  ImgView out;   // deferred colour target
+  int outIsF32;
+  ImgView ao; // R8_UINT occluded-ray counts
+  uint32_t flags;
+};
+
+struct ConvolveParams {
+  ImgView src, dst;
+  int vertical; // (level & 1): direction = (0,1) else (1,0)  (ReflectionBuffer.cpp:257-258)
+};
+
+struct MipGenParams {
+  ImgView src, dst;
+  int channels; // 4 (RGBA32F) only
+};
+
+struct IblParams {
+  ChainView env; // RGBA32F equirect with full mip chain
+  ImgView out;   // one mip level of one layer of the output (RGBA32F)
+  int layout;    // ALTHEA_IBL_LAYOUT_*
+  int face;      // cube face of `out`
+  int sequence;  // ALTHEA_IBL_SEQ_*
+  int numSamples;
+  int thetaSamples, phiSamples;
+  float roughness;
+  float mip; // irradiance: log2(envW / thetaSamples)
+};
+
+struct LutParams {
+  ImgView out;
+  int outIsF32;
+  int samples;
+};

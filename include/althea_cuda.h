@@ -1,0 +1,193 @@
+/* althea_cuda.h — C ABI of the B200-native engine for Althea's deferred screen-space path.
+ *
+ * This is the drop-in boundary. The reference (nithinp7/Althea) has no FFI today: the path is a set of C++
+ * methods that record Vulkan commands. Each entry point below replaces the BODY of one of those methods
+ * (the C++ signatures stay as they are, see INTEGRATION.md for the host-side patch):
+ *
+ *   althea_cuda_ssr_capture      <- ScreenSpaceReflection::captureReflection      Src/ScreenSpaceReflection.cpp:60-83
+ *                                   (Shaders/SSR.vert, Shaders/SSR.frag)
+ *   althea_cuda_glossy_convolve  <- ReflectionBuffer::convolveReflectionBuffer     Src/ReflectionBuffer.cpp:163-293
+ *                                   (Shaders/SSRGlossyConvolve.comp)
+ *   althea_cuda_deferred_shade   <- the app-owned deferred lighting pass that binds IBLResources::bind
+ *                                   (Src/ImageBasedLighting.cpp:20-26), GBufferResources::bindTextures
+ *                                   (Src/DeferredRendering.cpp:157-162) and ScreenSpaceReflection::bindTexture
+ *                                   (Shaders/DeferredPass.vert/.frag, Shaders/SSAO.glsl, Shaders/PBR/PBRMaterial.glsl)
+ *   althea_cuda_ibl_precompute   <- ImageBasedLighting.cpp:137-412 precomputeResources (called from
+ *                                   ImageBasedLighting::createResources :415-446)
+ *                                   (Shaders/IBL_Precompute/GenIrradianceMap.comp, PreFilterEnvMap.comp)
+ *   althea_cuda_generate_mips    <- Image::generateMipMaps                         Src/Image.cpp:135-239
+ *   althea_cuda_brdf_lut         <- (no generator in the reference; replaces loading Content/PrecomputedMaps/brdf_lut.png,
+ *                                   ImageBasedLighting.cpp:570-602)
+ *   althea_cuda_import_*         <- the VMA-backed resources of GBufferResources (Src/DeferredRendering.cpp:37-155),
+ *                                   ReflectionBuffer (Src/ReflectionBuffer.cpp:20-99), PointLightCollection
+ *                                   (Src/PointLight.cpp:31-185), IBLResources (Src/ImageBasedLighting.cpp:448-602)
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types. Every call returns 0 on success and a negative
+ * althea_status otherwise; althea_cuda_last_error() gives the message (the reference throws std::runtime_error —
+ * the C++ mirror in althea_b200/host rethrows). Calls on one ctx are made from one thread (the reference's render
+ * thread); work is stream-ordered on the stream named in althea_sync (or the ctx stream). There is NO CPU fallback:
+ * every compute entry point launches sm_100a kernels or fails.
+ */
+#ifndef ALTHEA_CUDA_H
+#define ALTHEA_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALTHEA_CUDA_ABI_VERSION 1
+
+typedef struct althea_cuda_ctx althea_cuda_ctx;
+
+typedef enum althea_status {
+  ALTHEA_OK = 0,
+  ALTHEA_ERR_INVALID_ARGUMENT = -1,
+  ALTHEA_ERR_CUDA = -2,
+  ALTHEA_ERR_UNSUPPORTED = -3,
+  ALTHEA_ERR_BAD_HANDLE = -4,
+  ALTHEA_ERR_OUT_OF_MEMORY = -5
+} althea_status;
+
+/* VkFormat values of the formats on the path (numeric values from vulkan_core.h, so the host passes VkFormat as is) */
+enum {
+  ALTHEA_FORMAT_R8G8B8A8_UNORM = 37,       /* albedo, MRO (DeferredRendering.cpp:79-99), BRDF LUT */
+  ALTHEA_FORMAT_R16G16B16A16_SFLOAT = 97,  /* normal (DeferredRendering.cpp:62-77), reflection buffer (ReflectionBuffer.cpp:36) */
+  ALTHEA_FORMAT_R32_SFLOAT = 100,          /* depth aspect copied out of D32_SFLOAT(_S8); shadow cube array */
+  ALTHEA_FORMAT_R32G32B32A32_SFLOAT = 109, /* position (legacy), IBL maps (ImageBasedLighting.cpp:456,496,542) */
+  ALTHEA_FORMAT_D32_SFLOAT = 126,          /* accepted as an alias of R32_SFLOAT for linear depth copies */
+  ALTHEA_FORMAT_R8_UINT = 13               /* SSAO occluded-ray counts (engine-internal scratch) */
+};
+
+/* ---- context ------------------------------------------------------------------------------------------------- */
+/* vk_device_uuid: VkPhysicalDeviceIDProperties::deviceUUID of the Vulkan device, or NULL to skip the check.        */
+int althea_cuda_create(althea_cuda_ctx** out_ctx, int cuda_device, const uint8_t vk_device_uuid[16]);
+void althea_cuda_destroy(althea_cuda_ctx* ctx);
+const char* althea_cuda_last_error(const althea_cuda_ctx* ctx); /* ctx may be NULL: error of a failed create */
+int althea_cuda_abi_version(void);
+
+#define ALTHEA_CTX_PARITY_MATH 1u /* run the -fmad=false build of the per-frame kernels (bit-matches the CPU oracle's IEEE op order) */
+int althea_cuda_set_flags(althea_cuda_ctx* ctx, uint32_t flags);
+
+/* Per-kernel device timing (CUDA events on the launching stream around every kernel this library launches). */
+int althea_cuda_enable_timing(althea_cuda_ctx* ctx, int enable);
+/* Sums since the last reset. names[i] points at static strings. Returns the number of distinct kernels (<= cap). Synchronises the recorded events. */
+int althea_cuda_get_timings(althea_cuda_ctx* ctx, const char** names, float* total_ms, uint32_t* launches, int cap);
+int althea_cuda_reset_timings(althea_cuda_ctx* ctx);
+/* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
+uint64_t althea_cuda_launch_count(const althea_cuda_ctx* ctx);
+
+/* ---- resources ------------------------------------------------------------------------------------------------- */
+/* Linear image layout used by every entry point: row-major, row 0 = top; for mips > 1 the levels are tightly packed one
+ * after another (level k is max(1,w>>k) x max(1,h>>k), row pitch = width*bytes_per_texel); layers (cube array: 6*cube+face,
+ * faces +X,-X,+Y,-Y,+Z,-Z) are whole mip chains one after another. `pitch` (bytes) applies to mips == 1 only; 0 = tight. */
+size_t althea_cuda_image_bytes(uint32_t vk_format, uint32_t w, uint32_t h, uint32_t mips, uint32_t layers);
+
+#define ALTHEA_IMAGE_CUBE 1u
+#define ALTHEA_IMAGE_OPTIMAL_TILING 2u /* not mappable as a linear buffer: rejected with ALTHEA_ERR_UNSUPPORTED */
+
+/* Vulkan owns the memory, CUDA maps it (cudaImportExternalMemory, opaque fd). Release before the Vulkan object dies. */
+int althea_cuda_import_image(althea_cuda_ctx* ctx, int fd, uint64_t alloc_size, uint64_t offset, uint32_t vk_format,
+                             uint32_t w, uint32_t h, uint32_t mips, uint32_t layers, uint32_t flags, uint64_t pitch,
+                             uint64_t* out_handle);
+int althea_cuda_import_buffer(althea_cuda_ctx* ctx, int fd, uint64_t size, uint64_t offset, uint64_t* out_handle);
+int althea_cuda_import_semaphore(althea_cuda_ctx* ctx, int fd, int is_timeline, uint64_t* out_handle);
+/* Twins that wrap plain device pointers (tests, bench, CUDA-only hosts). The caller keeps ownership. */
+int althea_cuda_wrap_linear_image(althea_cuda_ctx* ctx, void* dptr, size_t pitch, uint32_t vk_format, uint32_t w, uint32_t h,
+                                  uint32_t mips, uint32_t layers, uint64_t* out_handle);
+int althea_cuda_wrap_buffer(althea_cuda_ctx* ctx, void* dptr, size_t size, uint64_t* out_handle);
+/* Context-owned device images/buffers + host transfers (what the C++ mirror classes use when no Vulkan device exists). */
+int althea_cuda_create_image(althea_cuda_ctx* ctx, uint32_t vk_format, uint32_t w, uint32_t h, uint32_t mips, uint32_t layers,
+                             uint64_t* out_handle);
+int althea_cuda_create_buffer(althea_cuda_ctx* ctx, size_t size, uint64_t* out_handle);
+/* host may be pageable or pinned; copies are asynchronous on `stream` (0 = ctx stream) when host is pinned. */
+int althea_cuda_upload(althea_cuda_ctx* ctx, uint64_t handle, const void* host, size_t bytes, void* stream);
+int althea_cuda_download(althea_cuda_ctx* ctx, uint64_t handle, void* host, size_t bytes, void* stream);
+int althea_cuda_device_pointer(althea_cuda_ctx* ctx, uint64_t handle, void** out_dptr, size_t* out_bytes);
+int althea_cuda_release(althea_cuda_ctx* ctx, uint64_t handle);
+int althea_cuda_synchronize(althea_cuda_ctx* ctx, void* stream);
+
+/* ---- parameter blocks (byte-for-byte the reference's) ------------------------------------------------------------ */
+typedef struct althea_global_uniforms { /* 416 B == Include/Althea/GlobalUniforms.h:15-31 == Shaders/Global/GlobalUniforms.glsl:8-24 */
+  float projection[16], inverseProjection[16], view[16], prevView[16], inverseView[16], prevInverseView[16]; /* column-major */
+  float mouseUV[2];
+  int32_t lightCount;
+  uint32_t lightBufferHandle; /* bindless index in the reference; ignored here (lights_buf is passed explicitly) */
+  float time, exposure;
+  uint32_t inputMask, frameCount;
+} althea_global_uniforms;
+
+typedef struct althea_point_light { /* 32 B == Include/Althea/PointLight.h:31-34 == Shaders/PointLights.glsl:7-10 */
+  float position[3], _pad0, emission[3], _pad1;
+} althea_point_light;
+
+typedef struct althea_gbuffer { /* image handles; GBufferResources, Src/DeferredRendering.cpp:37-155 */
+  uint64_t depth;    /* R32_SFLOAT: the depth image written THIS frame (SSR.frag:29 hard-wires depthA) */
+  uint64_t position; /* R32G32B32A32_SFLOAT, .a == 0 => empty (legacy DeferredPass.frag:18,44) */
+  uint64_t normal;   /* R16G16B16A16_SFLOAT, .a == 0 => empty (SSR.frag:136-141) */
+  uint64_t albedo;   /* R8G8B8A8_UNORM */
+  uint64_t mro;      /* R8G8B8A8_UNORM: metallic, roughness, occlusion */
+} althea_gbuffer;
+
+typedef struct althea_ibl { /* IBLResources, Include/Althea/ImageBasedLighting.h:25-43 */
+  uint64_t env;         /* RGBA32F equirect, 1 mip */
+  uint64_t prefiltered; /* RGBA32F equirect, 5 mips, level k = roughness k/4 */
+  uint64_t irradiance;  /* RGBA32F equirect */
+  uint64_t brdf_lut;    /* RGBA8, sampled at (NdotV, roughness) (PBRMaterial.glsl:110) */
+} althea_ibl;
+
+typedef struct althea_sync { /* all zero => plain stream order on the ctx stream */
+  uint64_t wait_sem, wait_value;     /* imported semaphore the work waits on before starting (0 = none) */
+  uint64_t signal_sem, signal_value; /* imported semaphore signalled when the work is done (0 = none) */
+  void* cuda_stream;                 /* cudaStream_t to launch on; NULL => the ctx's own stream */
+} althea_sync;
+
+/* ---- per-frame stages -------------------------------------------------------------------------------------------- */
+/* Writes mip 0 of `reflection` (RGBA16F, >= 1 mip, frame-sized). lights_buf: althea_point_light[lightCount];
+ * shadow_cube_array: R32_SFLOAT, layers = 6*lightCount, texel = length(p-light)/1000 (ShadowMapBindless.frag:41); 0 => unshadowed. */
+int althea_cuda_ssr_capture(althea_cuda_ctx* ctx, const althea_global_uniforms* uniforms, const althea_gbuffer* gbuffer,
+                            const althea_ibl* ibl, uint64_t lights_buf, uint64_t shadow_cube_array, uint64_t reflection,
+                            const althea_sync* sync);
+/* Writes mips 1..mips-1 of `reflection` from mip 0 (7-tap separable Gaussian, axis alternating V,H,V,H). */
+int althea_cuda_glossy_convolve(althea_cuda_ctx* ctx, uint64_t reflection, const althea_sync* sync);
+
+#define ALTHEA_SHADE_SKIP_TONEMAP 1u /* DeferredPass.frag:48-50,86-88 */
+#define ALTHEA_SHADE_NO_SSAO 2u      /* keep the G-buffer occlusion channel instead of computeSSAO */
+#define ALTHEA_SHADE_AO_FROM_IMAGE 4u /* read occluded-ray counts from ao_counts instead of computing them (tests) */
+/* out_color: RGBA16F or RGBA32F, frame-sized. ao_counts: optional R8_UINT frame-sized image; when non-zero the SSAO
+ * kernel writes its per-pixel occluded-ray counts there (or, with AO_FROM_IMAGE, reads them). 0 => internal scratch. */
+int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniforms* uniforms, const althea_gbuffer* gbuffer,
+                               const althea_ibl* ibl, uint64_t lights_buf, uint64_t shadow_cube_array, uint64_t reflection,
+                               uint64_t out_color, uint64_t ao_counts, uint32_t flags, const althea_sync* sync);
+
+/* ---- IBL precompute ------------------------------------------------------------------------------------------------ */
+#define ALTHEA_IBL_LAYOUT_EQUIRECT 0u   /* the reference's layout: outputs are equirect images */
+#define ALTHEA_IBL_LAYOUT_CUBE 1u       /* BASELINE config 2: outputs are 6-layer cube images */
+#define ALTHEA_IBL_SEQ_REFERENCE_HASH 0u /* PreFilterEnvMap.comp:36-42 per-texel hash RNG */
+#define ALTHEA_IBL_SEQ_HAMMERSLEY 1u
+
+typedef struct althea_ibl_precompute_desc {
+  uint32_t layout;            /* ALTHEA_IBL_LAYOUT_* */
+  uint32_t sequence;          /* ALTHEA_IBL_SEQ_* (prefilter only) */
+  uint32_t prefilter_samples; /* 0 => 10000 (PreFilterEnvMap.comp:5) */
+  uint32_t theta_samples;     /* 0 => 300 (GenIrradianceMap.comp:119) */
+} althea_ibl_precompute_desc;
+
+/* Builds the full mip chain of `image` in place from level 0 (LINEAR 2:1 blit chain, Src/Image.cpp:183-213). */
+int althea_cuda_generate_mips(althea_cuda_ctx* ctx, uint64_t image, const althea_sync* sync);
+/* env_with_mips: RGBA32F equirect WITH its full mip chain (ImageBasedLighting.cpp:153-166).
+ * out_irradiance (0 = skip): RGBA32F; equirect layout: any size (the reference uses the env size); cube: layers = 6.
+ * out_prefiltered (0 = skip): RGBA32F with n mips. Equirect layout: the reference's 5 images env>>1..env>>5 ARE the 5 mips
+ *   of this image (level k: roughness k/4). Cube layout: layers = 6, level k: roughness k/(n-1). */
+int althea_cuda_ibl_precompute(althea_cuda_ctx* ctx, uint64_t env_with_mips, const althea_ibl_precompute_desc* desc,
+                               uint64_t out_irradiance, uint64_t out_prefiltered, const althea_sync* sync);
+/* out_lut: RGBA8 (R = scale, G = bias, B = 0, A = 255) or RGBA32F, square. Row 0 holds roughness = 1 (the orientation
+ * of the reference's asset, which PBRMaterial.glsl:110 samples un-flipped). */
+int althea_cuda_brdf_lut(althea_cuda_ctx* ctx, uint32_t samples, uint64_t out_lut, const althea_sync* sync);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALTHEA_CUDA_H */

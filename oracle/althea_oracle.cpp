@@ -1,0 +1,421 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity for the per-frame stages is
+// UNPINNED by the reference: it ships no fixture, test or golden image for SSAO, SSR, the glossy
+// convolve or the deferred shading. The authority is the GLSL text, read as
+// reconciled in SURVEY.md 8(c-bis) R1-R7. The IBL half (althea_oracle_ibl.cpp) IS pinned by the
+// reference's shipped Content/PrecomputedMaps.
+//
+// Per-frame stages of Althea's deferred screen-space path, restated on the CPU:
+//   oracle_ssr_capture      <- Shaders/SSR.vert:15-23, Shaders/SSR.frag:42-149,
+//                              Shaders/Misc/ReconstructPosition.glsl:4-22
+//   oracle_glossy_convolve  <- Shaders/SSRGlossyConvolve.comp:26-55, Src/ReflectionBuffer.cpp:224-278
+//   oracle_ssao             <- Shaders/SSAO.glsl:5-84
+//   oracle_deferred_shade   <- Shaders/DeferredPass.vert:10-22, Shaders/DeferredPass.frag:29-93,
+//                              Shaders/PBR/PBRMaterial.glsl:4-19,41-162
+// Build: g++ -O2 -fopenmp -ffp-contract=off -fno-fast-math -shared -fPIC (oracle/Makefile).
+#include "oracle_math.h"
+#include <cstdlib>
+#include <omp.h>
+#include <vector>
+
+using namespace oracle;
+
+extern "C" {
+
+// Include/Althea/GlobalUniforms.h:15-31 == Shaders/Global/GlobalUniforms.glsl:8-24 (416 bytes)
+struct OracleGlobalUniforms {
+  M4 projection, inverseProjection, view, prevView, inverseView, prevInverseView;
+  float mouseUV[2];
+  int32_t lightCount;
+  uint32_t lightBufferHandle;
+  float time, exposure;
+  uint32_t inputMask, frameCount;
+};
+
+struct OracleGBuffer {
+  int32_t W, H;
+  const float* position;  // RGBA32F, .a == 0 => empty (legacy DeferredPass.frag:18,44); may be null
+  const float* depth;     // D32 as plain floats (DeferredRendering.cpp:42-60)
+  const uint16_t* normal; // RGBA16F (DeferredRendering.cpp:62-77)
+  const uint8_t* albedo;  // RGBA8   (:79-88)
+  const uint8_t* mro;     // RGBA8   (:90-99)
+};
+
+struct OracleIBL {
+  const float* env; int32_t envW, envH;                     // RGBA32F, 1 mip (ImageBasedLighting.cpp:448-481)
+  const float* prefiltered; int32_t preW, preH, preMips;    // RGBA32F, 5 mips in one image (:483-532)
+  const float* irradiance; int32_t irrW, irrH;              // RGBA32F (:534-568)
+  const uint8_t* lut; int32_t lutW, lutH;                   // RGBA8 (:570-602)
+};
+
+struct OracleLights {
+  const float* lights;  // PointLight.h:31-34: {pos.xyz, pad, emission.xyz, pad} x lightCount
+  const float* shadow;  // cube array, layer = 6*light + face, res x res floats = length(p-light)/1000
+  int32_t shadowRes;    // 256 in the reference (PointLight.cpp:55-62); 0 => no shadow maps
+};
+
+enum { ORACLE_SKIP_TONEMAP = 1u, ORACLE_NO_SSAO = 2u };
+
+} // extern "C"
+
+namespace {
+
+struct Ctx {
+  const OracleGlobalUniforms* g;
+  OracleGBuffer gb;
+  OracleIBL ibl;
+  OracleLights li;
+  Tex position() const { return Tex{gb.position, gb.W, gb.H, FMT_RGBA32F}; }
+  Tex depth() const { return Tex{gb.depth, gb.W, gb.H, FMT_R32F}; }
+  Tex normal() const { return Tex{gb.normal, gb.W, gb.H, FMT_RGBA16F}; }
+  Tex albedo() const { return Tex{gb.albedo, gb.W, gb.H, FMT_RGBA8}; }
+  Tex mro() const { return Tex{gb.mro, gb.W, gb.H, FMT_RGBA8}; }
+};
+
+// --- equirect IBL lookups, run-time flavour: CLAMP_TO_EDGE (ImageBasedLighting.cpp:469-475) -----
+V2 equirectUv(V3 d) { // PBRMaterial.glsl:5-7
+  float yaw = atan2f(d.z, d.x);
+  float pitch = -atan2f(d.y, sqrtf(d.x * d.x + d.z * d.z));
+  return {(0.5f * yaw) / kPi + 0.5f, pitch / kPi + 0.5f};
+}
+V3 sampleEnvMapLod0(const Ctx& c, V3 dir) { // DeferredPass.frag:33-39
+  V2 uv = equirectUv(dir);
+  return xyz(bilinear(Tex{c.ibl.env, c.ibl.envW, c.ibl.envH, FMT_RGBA32F}, uv.x, uv.y, ADDR_CLAMP));
+}
+V3 sampleEnvMapRough(const Ctx& c, V3 dir, float roughness) { // PBRMaterial.glsl:4-11
+  V2 uv = equirectUv(dir);
+  TexChain ch{c.ibl.prefiltered, c.ibl.preW, c.ibl.preH, c.ibl.preMips, FMT_RGBA32F};
+  return xyz(trilinear(ch, uv.x, uv.y, 4.0f * roughness, ADDR_CLAMP));
+}
+V3 sampleIrrMap(const Ctx& c, V3 n) { // PBRMaterial.glsl:13-19
+  V2 uv = equirectUv(n);
+  return xyz(bilinear(Tex{c.ibl.irradiance, c.ibl.irrW, c.ibl.irrH, FMT_RGBA32F}, uv.x, uv.y, ADDR_CLAMP));
+}
+
+// --- cube-array lookup (rule A8; deviation: bilinear footprint clamps inside the face) ----------
+float sampleShadowCube(const Ctx& c, V3 q, int light) {
+  float ax = fabsf(q.x), ay = fabsf(q.y), az = fabsf(q.z);
+  int face; float sc, tc, ma;
+  if (ax >= ay && ax >= az) { ma = ax; if (q.x >= 0.0f) { face = 0; sc = -q.z; tc = -q.y; } else { face = 1; sc = q.z; tc = -q.y; } }
+  else if (ay >= az)        { ma = ay; if (q.y >= 0.0f) { face = 2; sc = q.x; tc = q.z; } else { face = 3; sc = q.x; tc = -q.z; } }
+  else                      { ma = az; if (q.z >= 0.0f) { face = 4; sc = q.x; tc = -q.y; } else { face = 5; sc = -q.x; tc = -q.y; } }
+  float s = 0.5f * sc / ma + 0.5f, t = 0.5f * tc / ma + 0.5f;
+  int res = c.li.shadowRes;
+  const float* layer = c.li.shadow + (size_t)(6 * light + face) * res * res;
+  return bilinear(Tex{layer, res, res, FMT_R32F}, s, t, ADDR_CLAMP).x;
+}
+
+// --- PBRMaterial.glsl:41-70 -----------------------------------------------------------------
+float ndfGgx(float NdotH, float a2) {
+  float tmp = NdotH * NdotH * (a2 - 1.0f) + 1.0f;
+  float denom = kPi * tmp * tmp;
+  return a2 / denom;
+}
+V3 fresnelSchlick(float NdotV, V3 F0, float roughness) {
+  float om = 1.0f - roughness;
+  V3 m{maxf(om, F0.x), maxf(om, F0.y), maxf(om, F0.z)};
+  return F0 + (m - F0) * powf(1.0f - NdotV, 5.0f);
+}
+float geometrySchlickGgx(float NdotV, float k) { return NdotV / (NdotV * (1.0f - k) + k); }
+float geometrySmith(float NdotL, float NdotV, float k) { return geometrySchlickGgx(NdotV, k) * geometrySchlickGgx(NdotL, k); }
+
+// PBRMaterial.glsl:72-162, current signature (reconciliation R1)
+V3 pbrMaterial(const Ctx& c, V3 worldPos, V3 V, V3 N, V3 baseColor, V3 reflectedColor, V3 irradianceColor,
+               float metallic, float roughness, float ambientOcclusion) {
+  float NdotV = maxf(dot(N, -V), 0.0f);
+  V3 F0 = mix(V3{0.04f, 0.04f, 0.04f}, baseColor, metallic);
+  float a = roughness * roughness;
+  float a2 = a * a;
+  float kDirect = (a + 1.0f) * (a + 1.0f) / 8.0f;
+  V3 color{0.0f, 0.0f, 0.0f};
+  V3 one{1.0f, 1.0f, 1.0f};
+  V3 dielectricBase = mix(baseColor, V3{0.0f, 0.0f, 0.0f}, metallic);
+  { // :100-114 environment term
+    V3 F = fresnelSchlick(NdotV, F0, roughness);
+    V3 diffuseColor = (one - F) * dielectricBase;
+    V4 lut = bilinear(Tex{c.ibl.lut, c.ibl.lutW, c.ibl.lutH, FMT_RGBA8}, NdotV, roughness, ADDR_CLAMP);
+    V3 ambientSpecular = reflectedColor * (F * lut.x + V3{lut.y, lut.y, lut.y});
+    color = color + (irradianceColor * diffuseColor + ambientSpecular) * ambientOcclusion;
+  }
+  for (int i = 0; i < c.g->lightCount; ++i) { // :117-159
+    const float* lp = c.li.lights + (size_t)i * 8;
+    V3 lightPos{lp[0], lp[1], lp[2]}, emission{lp[4], lp[5], lp[6]};
+    V3 L = lightPos - worldPos;
+    float LdistSq = dot(L, L);
+    float Ldist = sqrtf(LdistSq);
+    L = L / Ldist;
+    if (c.li.shadowRes > 0) {
+      float closestDepth = sampleShadowCube(c, V3{L.x, -L.y, -L.z}, i);
+      closestDepth *= 1000.0f;
+      if (closestDepth < (Ldist - 0.5f)) continue;
+    }
+    V3 radiance = emission / LdistSq;
+    V3 H = normalize(V + L); // sic: V points camera -> surface (R6)
+    float NdotL = maxf(dot(N, L), 0.0f);
+    float NdotH = maxf(dot(N, H), 0.0f);
+    V3 F = fresnelSchlick(NdotH, F0, roughness);
+    V3 diffuseColor = ((one - F) * dielectricBase) / kPi;
+    V3 specularColor = ((ndfGgx(NdotH, a2) * F) * geometrySmith(NdotL, NdotV, kDirect)) / (4.0f * NdotL * NdotV + 0.0001f);
+    color = color + ((diffuseColor + specularColor) * radiance) * NdotL;
+  }
+  return color;
+}
+
+// DeferredPass.vert:10-22 / SSR.vert:15-23, evaluated at the pixel centre (the varying is linear in uv)
+V3 viewDirection(const OracleGlobalUniforms& g, float u, float v) {
+  V4 p = mul(g.inverseProjection, V4{u * 2.0f - 1.0f, v * 2.0f - 1.0f, 0.0f, 1.0f});
+  return mul3(g.inverseView, V3{p.x, p.y, p.z});
+}
+
+// Misc/ReconstructPosition.glsl:4-22
+V3 reconstructPosition(const OracleGlobalUniforms& g, float u, float v, float dRaw) {
+  const float near = 0.01f, far = 1000.0f;
+  float d = far * near / (dRaw * (far - near) - far);
+  V4 dirH = mul(g.inverseProjection, V4{2.0f * u - 1.0f, 2.0f * v - 1.0f, 2.0f, 1.0f});
+  V4 h{dirH.x / dirH.w, dirH.y / dirH.w, dirH.z / dirH.w, 0.0f};
+  V4 wd = mul(g.inverseView, h);
+  V3 dir = normalize(V3{wd.x, wd.y, wd.z});
+  V3 zc{g.inverseView.m[8], g.inverseView.m[9], g.inverseView.m[10]};
+  float f = dot(dir, zc);
+  V3 cam{g.inverseView.m[12], g.inverseView.m[13], g.inverseView.m[14]};
+  return cam + (d * dir) / f;
+}
+
+inline bool outside01(V2 uv) { return uv.x < 0.0f || uv.x > 1.0f || uv.y < 0.0f || uv.y > 1.0f; }
+
+// SSR.frag:55-78
+V4 environmentLitSample(const Ctx& c, V3 currentPos, V2 uv, V3 rayDir, V3 normal) {
+  V3 baseColor = xyz(bilinear(c.albedo(), uv.x, uv.y, ADDR_CLAMP));
+  V3 mro = xyz(bilinear(c.mro(), uv.x, uv.y, ADDR_CLAMP));
+  mro.z = 1.0f;
+  V3 reflectedDirection = reflect(normalize(rayDir), normal);
+  V3 reflectedColor = sampleEnvMapRough(c, reflectedDirection, mro.y);
+  V3 irradianceColor = sampleIrrMap(c, normal);
+  V3 m = pbrMaterial(c, currentPos, normalize(rayDir), normal, baseColor, reflectedColor, irradianceColor, mro.x, mro.y, mro.z);
+  return {m.x, m.y, m.z, 1.0f};
+}
+
+// SSR.frag:80-133
+V4 raymarchGBuffer(const Ctx& c, const M4& projView, V2 currentUV, V3 worldPos, V3 normal, V3 rayDir, int* stepsOut) {
+  V3 endPos = worldPos + rayDir * 10000.0f;
+  V4 pe = mul(projView, V4{endPos.x, endPos.y, endPos.z, 1.0f});
+  V2 uvEnd{0.5f * pe.x / pe.w + 0.5f, 0.5f * pe.y / pe.w + 0.5f};
+  V2 dlt{uvEnd.x - currentUV.x, uvEnd.y - currentUV.y};
+  float dl = sqrtf(dlt.x * dlt.x + dlt.y * dlt.y);
+  V2 uvStep{dlt.x / dl, dlt.y / dl};
+  const float stepSize = 0.005f;
+  V3 perpRef = normalize(cross(cross(rayDir, normal), rayDir));
+  V3 prevPos = worldPos; (void)prevPos;
+  float prevProjection = 0.0f;
+  for (int i = 0; i < 128; ++i) {
+    if (stepsOut) *stepsOut = i + 1;
+    currentUV.x += uvStep.x * stepSize;
+    currentUV.y += uvStep.y * stepSize;
+    if (outside01(currentUV)) return {0.0f, 0.0f, 0.0f, 0.0f};
+    float dRaw = bilinear(c.depth(), currentUV.x, currentUV.y, ADDR_CLAMP).x;
+    V3 currentPos = reconstructPosition(*c.g, currentUV.x, currentUV.y, dRaw);
+    V3 dir = normalize(currentPos - worldPos);
+    float currentProjection = dot(dir, perpRef);
+    float f = dot(dir, rayDir);
+    if (currentProjection * prevProjection <= 0.0f && f > 0.999f && i > 0) {
+      V3 currentNormal = normalize(xyz(bilinear(c.normal(), currentUV.x, currentUV.y, ADDR_CLAMP)));
+      if (dot(currentNormal, rayDir) < 0.0f)
+        return environmentLitSample(c, currentPos, currentUV, rayDir, currentNormal);
+    }
+    prevProjection = currentProjection;
+  }
+  return {0.0f, 0.0f, 0.0f, 0.0f};
+}
+
+// SSAO.glsl:31-84. Returns the number of occluded rays (ao), the shader's result is 1 - ao/24.
+int ssaoCount(const Ctx& c, const M4& projView, int px, int py, V2 uvStart, V3 worldPos, V3 normal) {
+  Rng rng{(uint32_t)px, (uint32_t)py}; // seed = uvec2(gl_FragCoord.xy), DeferredPass.frag:42
+  Frame tbn = localToWorld(normal);
+  int ao = 0;
+  for (int ray = 0; ray < 24; ++ray) {
+    float x0 = rng.next(), x1 = rng.next(), x2 = rng.next();
+    V3 rayDir = tbn.apply(normalize(V3{2.0f * x0 - 1.0f, 2.0f * x1 - 1.0f, x2}));
+    V3 endPos = worldPos + rayDir * 0.5f;
+    V4 pe = mul(projView, V4{endPos.x, endPos.y, endPos.z, 1.0f});
+    V2 uvEnd{0.5f * pe.x / pe.w + 0.5f, 0.5f * pe.y / pe.w + 0.5f};
+    V3 perpRef = normalize(cross(cross(rayDir, normal), rayDir));
+    V3 prevPos = worldPos;
+    float prevProjection = 0.0f;
+    for (int i = 0; i < 12; ++i) {
+      float t = (float)i / 12.0f;
+      V2 uv{mixf(uvStart.x, uvEnd.x, t), mixf(uvStart.y, uvEnd.y, t)};
+      if (outside01(uv)) break;
+      // rule A3: the i == 0 tap is the pixel's own centre => exact fetch of its own texel
+      V3 currentPos = (i == 0) ? worldPos : xyz(bilinear(c.position(), uv.x, uv.y, ADDR_CLAMP));
+      V3 dir = currentPos - worldPos;
+      float currentProjection = dot(dir, perpRef);
+      float worldStep = length(currentPos - prevPos);
+      if (currentProjection * prevProjection < 0.0f && worldStep <= 2.0f && i > 0) {
+        V3 currentNormal = normalize(xyz(bilinear(c.normal(), uv.x, uv.y, ADDR_CLAMP)));
+        if (dot(currentNormal, rayDir) < 0.0f) { ao += 1; break; }
+      }
+      prevPos = currentPos;
+      prevProjection = currentProjection;
+    }
+  }
+  return ao;
+}
+
+} // namespace
+
+extern "C" {
+
+// RNG known-answer helper
+void oracle_rng(uint32_t sx, uint32_t sy, int n, uint32_t* outU, float* outF) {
+  Rng a{sx, sy}, b{sx, sy};
+  for (int i = 0; i < n; ++i) { outU[i] = a.nextU(); outF[i] = b.next(); }
+}
+void oracle_half_roundtrip(const float* in, int n, uint16_t* outH, float* outF) {
+  for (int i = 0; i < n; ++i) { outH[i] = floatToHalf(in[i]); outF[i] = halfToFloat(outH[i]); }
+}
+// generic texture-unit probe for the unit tests of rules A1/A2/A5
+void oracle_sample(const void* data, int w, int h, int mips, int fmt, int addr, const float* uvl, int n, float* out) {
+  TexChain ch{data, w, h, mips, (Format)fmt};
+  for (int i = 0; i < n; ++i) {
+    V4 r = trilinear(ch, uvl[3 * i], uvl[3 * i + 1], uvl[3 * i + 2], (Address)addr);
+    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+  }
+}
+float oracle_sample_cube(const float* shadow, int res, int light, float qx, float qy, float qz) {
+  Ctx c{}; c.li.shadow = shadow; c.li.shadowRes = res;
+  return sampleShadowCube(c, V3{qx, qy, qz}, light);
+}
+void oracle_reconstruct_position(const OracleGlobalUniforms* g, float u, float v, float dRaw, float* out3) {
+  V3 p = reconstructPosition(*g, u, v, dRaw); out3[0] = p.x; out3[1] = p.y; out3[2] = p.z;
+}
+
+// SSR.frag main (:135-149) + A9 blend-on-write onto a (0,0,0,0) clear, stored RGBA16F.
+// outHit (optional): 1 where the march returned a lit sample. outSteps (optional): march steps taken.
+void oracle_ssr_capture(const OracleGlobalUniforms* g, const OracleGBuffer* gb, const OracleIBL* ibl, const OracleLights* li,
+                        uint16_t* outReflection, uint8_t* outHit, uint8_t* outSteps) {
+  Ctx c{g, *gb, *ibl, *li};
+  M4 projView = matmul(g->projection, g->view);
+  const int W = gb->W, H = gb->H;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      float u = ((float)x + 0.5f) / (float)W, v = ((float)y + 0.5f) / (float)H;
+      size_t idx = (size_t)y * W + x;
+      V4 normal4 = texel(c.normal(), x, y);
+      V4 out{0.0f, 0.0f, 0.0f, 0.0f};
+      int steps = 0;
+      if (normal4.w != 0.0f) {
+        V3 position = reconstructPosition(*g, u, v, gb->depth[idx]);
+        V3 normal = normalize(xyz(normal4));
+        V3 reflectedDirection = reflect(normalize(viewDirection(*g, u, v)), normal);
+        out = raymarchGBuffer(c, projView, V2{u, v}, position, normal, reflectedDirection, &steps);
+      }
+      // dst = src.rgb*src.a + dst.rgb*(1-src.a), dst.a = src.a   (GraphicsPipeline.cpp:138-154), dst cleared to 0
+      float r = out.x * out.w, gch = out.y * out.w, b = out.z * out.w;
+      outReflection[idx * 4 + 0] = floatToHalf(r);
+      outReflection[idx * 4 + 1] = floatToHalf(gch);
+      outReflection[idx * 4 + 2] = floatToHalf(b);
+      outReflection[idx * 4 + 3] = floatToHalf(out.w);
+      if (outHit) outHit[idx] = out.w != 0.0f;
+      if (outSteps) outSteps[idx] = (uint8_t)steps;
+    }
+}
+
+// SSRGlossyConvolve.comp + ReflectionBuffer.cpp:224-278. `mips` is the tight RGBA16F chain; level 0 is input.
+void oracle_glossy_convolve(uint16_t* mips, int W, int H, int mipCount) {
+  TexChain ch{mips, W, H, mipCount, FMT_RGBA16F};
+  for (int level = 1; level < mipCount; ++level) {
+    Tex src = ch.level(level - 1);
+    Tex dstT = ch.level(level);
+    uint16_t* dst = (uint16_t*)dstT.data;
+    const int w = dstT.w, h = dstT.h;
+    const float dirx = (level & 1) ? 0.0f : 1.0f, diry = (level & 1) ? 1.0f : 0.0f;
+    const float resolution = (float)w;
+    const float o1 = 1.411764705882353f, o2 = 3.2941176470588234f, o3 = 5.176470588235294f;
+    const float w0 = 0.1964825501511404f, w1 = 0.2969069646728344f, w2 = 0.09447039785044732f, w3 = 0.010381362401148057f;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) {
+        float u = (float)x / (float)w, v = (float)y / (float)h; // no half-texel (rule A4)
+        V4 color{0.0f, 0.0f, 0.0f, 0.0f};
+        auto S = [&](float du, float dv) { return bilinear(src, u + du, v + dv, ADDR_CLAMP); };
+        float a1x = (o1 * dirx) / resolution, a1y = (o1 * diry) / resolution;
+        float a2x = (o2 * dirx) / resolution, a2y = (o2 * diry) / resolution;
+        float a3x = (o3 * dirx) / resolution, a3y = (o3 * diry) / resolution;
+        color = color + S(0.0f, 0.0f) * w0;
+        color = color + S(a1x, a1y) * w1;
+        color = color + S(-a1x, -a1y) * w1;
+        color = color + S(a2x, a2y) * w2;
+        color = color + S(-a2x, -a2y) * w2;
+        color = color + S(a3x, a3y) * w3;
+        color = color + S(-a3x, -a3y) * w3;
+        size_t i = ((size_t)y * w + x) * 4;
+        dst[i] = floatToHalf(color.x); dst[i + 1] = floatToHalf(color.y);
+        dst[i + 2] = floatToHalf(color.z); dst[i + 3] = floatToHalf(color.w);
+      }
+  }
+}
+
+// computeSSAO for every pixel; outCount[y*W+x] = occluded rays (0..24); 255 for empty pixels (never shaded)
+void oracle_ssao(const OracleGlobalUniforms* g, const OracleGBuffer* gb, uint8_t* outCount) {
+  OracleIBL noIbl{}; OracleLights noL{};
+  Ctx c{g, *gb, noIbl, noL};
+  M4 projView = matmul(g->projection, g->view);
+  const int W = gb->W, H = gb->H;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      size_t idx = (size_t)y * W + x;
+      V4 position = texel(c.position(), x, y);
+      if (position.w == 0.0f) { outCount[idx] = 255; continue; }
+      float u = ((float)x + 0.5f) / (float)W, v = ((float)y + 0.5f) / (float)H;
+      V3 normal = normalize(xyz(texel(c.normal(), x, y)));
+      outCount[idx] = (uint8_t)ssaoCount(c, projView, x, y, V2{u, v}, xyz(position), normal);
+    }
+}
+
+// DeferredPass.frag main (:41-93), reconciled per R1/R2/R5(P). aoCount: optional precomputed SSAO counts
+// (lets shading parity be checked independently of AO threshold flips); null => computed here unless NO_SSAO.
+void oracle_deferred_shade(const OracleGlobalUniforms* g, const OracleGBuffer* gb, const OracleIBL* ibl, const OracleLights* li,
+                           const uint16_t* reflectionMips, int reflMipCount, uint32_t flags, const uint8_t* aoCount,
+                           float* outColor /* RGBA32F */) {
+  Ctx c{g, *gb, *ibl, *li};
+  M4 projView = matmul(g->projection, g->view);
+  const int W = gb->W, H = gb->H;
+  TexChain refl{reflectionMips, W, H, reflMipCount, FMT_RGBA16F};
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      size_t idx = (size_t)y * W + x;
+      float u = ((float)x + 0.5f) / (float)W, v = ((float)y + 0.5f) / (float)H;
+      V3 direction = viewDirection(*g, u, v);
+      V4 position = texel(c.position(), x, y);
+      V3 outc;
+      if (position.w == 0.0f) {
+        outc = sampleEnvMapLod0(c, direction);
+        if (!(flags & ORACLE_SKIP_TONEMAP))
+          outc = V3{1.0f - expf(-outc.x * g->exposure), 1.0f - expf(-outc.y * g->exposure), 1.0f - expf(-outc.z * g->exposure)};
+      } else {
+        V3 normal = normalize(xyz(texel(c.normal(), x, y)));
+        V3 baseColor = xyz(texel(c.albedo(), x, y));
+        V3 mro = xyz(texel(c.mro(), x, y));
+        V3 reflectedDirection = reflect(normalize(direction), normal);
+        V4 reflectedColor = trilinear(refl, u, v, 4.0f * mro.y, ADDR_CLAMP);
+        V3 envReflected = sampleEnvMapRough(c, reflectedDirection, mro.y);
+        V3 rc;
+        if (reflectedColor.w < 0.01f) rc = envReflected;
+        else rc = mix(envReflected, xyz(reflectedColor) / reflectedColor.w, reflectedColor.w);
+        V3 irradianceColor = sampleIrrMap(c, normal);
+        if (flags & ORACLE_NO_SSAO) { /* keep the G-buffer occlusion channel */ }
+        else if (aoCount) mro.z = 1.0f - (float)aoCount[idx] / 24.0f;
+        else mro.z = 1.0f - (float)ssaoCount(c, projView, x, y, V2{u, v}, xyz(position), normal) / 24.0f;
+        outc = pbrMaterial(c, xyz(position), normalize(direction), normal, baseColor, rc, irradianceColor, mro.x, mro.y, mro.z);
+        if (!(flags & ORACLE_SKIP_TONEMAP))
+          outc = V3{1.0f - expf(-outc.x * g->exposure), 1.0f - expf(-outc.y * g->exposure), 1.0f - expf(-outc.z * g->exposure)};
+      }
+      outColor[idx * 4 + 0] = outc.x; outColor[idx * 4 + 1] = outc.y; outColor[idx * 4 + 2] = outc.z; outColor[idx * 4 + 3] = 1.0f;
+    }
+}
+
+int oracle_num_threads() { return omp_get_max_threads(); }
+
+} // extern "C"
