@@ -122,7 +122,8 @@ ADEV V3 viewDirection(const FrameParams& P, float u, float v) {
 // Misc/ReconstructPosition.glsl:4-22
 ADEV V3 reconstructPosition(const FrameParams& P, float u, float v, float dRaw) {
   const float near = 0.01f, far = 1000.0f;
-  float d = far * near / (dRaw * (far - near) - far);
+  // one fused multiply-add in BOTH builds: unfused, the cancellation costs ~3 digits of eye depth (see the oracle)
+  float d = far * near / __fmaf_rn(dRaw, far - near, -far);
   V4 dirH = mul44(P.g.inverseProjection, mk4(2.0f * u - 1.0f, 2.0f * v - 1.0f, 2.0f, 1.0f));
   V3 cam = mk3(P.g.inverseView[12], P.g.inverseView[13], P.g.inverseView[14]);
   V3 zc = mk3(P.g.inverseView[8], P.g.inverseView[9], P.g.inverseView[10]);

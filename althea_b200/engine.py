@@ -177,21 +177,20 @@ def _torch():
     return torch
 
 
-def _sync(stream: Optional[int]) -> Optional[_capi.Sync]:
-    if not stream:
-        return None
-    s = _capi.Sync()
-    s.cuda_stream = stream
-    return s
-
-
-def _sync_ref(stream):
-    s = _sync(stream)
-    return (C.byref(s), s) if s is not None else (None, None)
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: how the NULL stream is named when NULL itself means "the ctx stream"
 
 
 def current_stream_ptr(device: int = 0) -> int:
-    return int(_torch().cuda.current_stream(device).cuda_stream)
+    """torch's current stream as a cudaStream_t value the C ABI accepts (the NULL stream is passed as cudaStreamLegacy)."""
+    return int(_torch().cuda.current_stream(device).cuda_stream) or CUDA_STREAM_LEGACY
+
+
+def _sync_ref(stream, device: int = 0):
+    """althea_sync for a launch. stream None/0 => torch's current stream, so engine calls are ordered with the torch copies
+    that fill and read the images (the ctx's own stream is for hosts without torch)."""
+    s = _capi.Sync()
+    s.cuda_stream = stream if stream else current_stream_ptr(device)
+    return C.byref(s), s
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -287,7 +286,7 @@ class ImageBasedLighting:
 
     @staticmethod
     def generateMipMaps(ctx: Context, image: Image, stream: int = 0):
-        ref, keep = _sync_ref(stream)
+        ref, keep = _sync_ref(stream, ctx.device)
         ctx._check(ctx._lib.althea_cuda_generate_mips(ctx._ptr, image.handle, ref))
 
     @staticmethod
@@ -296,14 +295,14 @@ class ImageBasedLighting:
                             theta_samples=0, stream: int = 0):
         """ImageBasedLighting.cpp:137-412: irradiance + GGX-prefiltered mips from an equirect env map with its mip chain."""
         desc = _capi.IblPrecomputeDesc(layout, sequence, prefilter_samples, theta_samples)
-        ref, keep = _sync_ref(stream)
+        ref, keep = _sync_ref(stream, ctx.device)
         ctx._check(ctx._lib.althea_cuda_ibl_precompute(ctx._ptr, env_with_mips.handle, C.byref(desc),
                                                        out_irradiance.handle if out_irradiance else 0,
                                                        out_prefiltered.handle if out_prefiltered else 0, ref))
 
     @staticmethod
     def generateBrdfLut(ctx: Context, out_lut: Image, samples: int = 1024, stream: int = 0):
-        ref, keep = _sync_ref(stream)
+        ref, keep = _sync_ref(stream, ctx.device)
         ctx._check(ctx._lib.althea_cuda_brdf_lut(ctx._ptr, samples, out_lut.handle, ref))
 
     @staticmethod
@@ -342,7 +341,7 @@ class ReflectionBuffer:
         self.image = ctx.new_image(_capi.FORMAT_R16G16B16A16_SFLOAT, width, height, mip_count)
 
     def convolveReflectionBuffer(self, stream: int = 0):
-        ref, keep = _sync_ref(stream)
+        ref, keep = _sync_ref(stream, self.ctx.device)
         self.ctx._check(self.ctx._lib.althea_cuda_glossy_convolve(self.ctx._ptr, self.image.handle, ref))
 
 
@@ -359,7 +358,7 @@ class ScreenSpaceReflection:
     def captureReflection(self, globalUniforms: GlobalUniforms, gBuffer: GBufferResources, ibl: IBLResources,
                           lights: Optional[PointLightCollection], stream: int = 0):
         gb, ib = gBuffer.struct(), ibl.struct()
-        ref, keep = _sync_ref(stream)
+        ref, keep = _sync_ref(stream, self.ctx.device)
         self.ctx._check(self.ctx._lib.althea_cuda_ssr_capture(
             self.ctx._ptr, C.byref(globalUniforms), C.byref(gb), C.byref(ib), lights.buffer.handle if lights else 0,
             lights.shadow_handle if lights else 0, self._reflectionBuffer.image.handle, ref))
@@ -379,7 +378,7 @@ class DeferredPass:
     def draw(self, globalUniforms: GlobalUniforms, gBuffer: GBufferResources, ibl: IBLResources, lights: Optional[PointLightCollection],
              ssr: ScreenSpaceReflection, flags: int = _capi.SHADE_SKIP_TONEMAP, stream: int = 0):
         gb, ib = gBuffer.struct(), ibl.struct()
-        ref, keep = _sync_ref(stream)
+        ref, keep = _sync_ref(stream, self.ctx.device)
         self.ctx._check(self.ctx._lib.althea_cuda_deferred_shade(
             self.ctx._ptr, C.byref(globalUniforms), C.byref(gb), C.byref(ib), lights.buffer.handle if lights else 0,
             lights.shadow_handle if lights else 0, ssr.getReflectionBuffer().image.handle, self.colorTarget.handle,

@@ -192,6 +192,18 @@ def make_scene(n_spheres: int = 64, seed: int = SEED, device="cpu") -> AnalyticS
     return AnalyticScene(centers, radii, albedo, (u(6) < 0.5).to(torch.float64), 0.05 + 0.95 * u(7))
 
 
+def make_ring_scene(n_spheres: int = 160, seed: int = SEED, device="cpu", r_min: float = 3.5, r_max: float = 16.0) -> AnalyticScene:
+    """Spheres on an annulus around the origin, so a camera at (0, 2, 0) sees similar content at every yaw (bench views)."""
+    i = torch.arange(n_spheres, device=device, dtype=torch.int64)
+    u = lambda s: hash_uniform(i, 300 + s, seed).to(torch.float64)  # noqa: E731
+    radii = 0.3 + 0.9 * u(0)
+    ang = 2.0 * math.pi * u(1)
+    rad = torch.sqrt(r_min ** 2 + (r_max ** 2 - r_min ** 2) * u(2))
+    centers = torch.stack([rad * torch.sin(ang), radii, rad * torch.cos(ang)], -1)
+    albedo = torch.stack([u(3), u(4), u(5)], -1)
+    return AnalyticScene(centers, radii, albedo, (u(6) < 0.5).to(torch.float64), 0.05 + 0.95 * u(7))
+
+
 def _raycast(scene: AnalyticScene, origin: torch.Tensor, d: torch.Tensor):
     """Nearest hit of rays origin + t d (d unit). origin broadcastable to d. Returns t (inf = miss) and object id (-1 plane)."""
     inf = torch.full(d.shape[:-1], float("inf"), dtype=d.dtype, device=d.device)
@@ -234,14 +246,15 @@ def s_scene(g: GlobalUniforms, W: int, H: int, scene: AnalyticScene, device="cpu
 
 
 # ---- lights -----------------------------------------------------------------------------------------------------
-def make_lights(n: int, seed: int = SEED, device="cpu") -> torch.Tensor:
-    """(n, 8) float32 PointLight rows: positions U[-10,10]x[1,6]x[-10,10], emission U[5,50]^3."""
+def make_lights(n: int, seed: int = SEED, device="cpu", ring: bool = False) -> torch.Tensor:
+    """(n, 8) float32 PointLight rows: positions U[-10,10]x[1,6]x[-10,10] (z shifted to sit over the test
+    scene, or centred on the origin with ring=True), emission U[5,50]^3."""
     i = torch.arange(n, device=device, dtype=torch.int64)
     u = lambda s: hash_uniform(i, 200 + s, seed)  # noqa: E731
     out = torch.zeros(n, 8, dtype=torch.float32, device=device)
     out[:, 0] = -10.0 + 20.0 * u(0)
     out[:, 1] = 1.0 + 5.0 * u(1)
-    out[:, 2] = -14.0 + 18.0 * u(2)
+    out[:, 2] = (-10.0 + 20.0 * u(2)) if ring else (-14.0 + 18.0 * u(2))
     out[:, 4] = 5.0 + 45.0 * u(3)
     out[:, 5] = 5.0 + 45.0 * u(4)
     out[:, 6] = 5.0 + 45.0 * u(5)

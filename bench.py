@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — deferred+SSAO+SSR Mpixel/s at 4K (BASELINE.json metric), plus IBL prefilter ms.
+
+A "step" = the hot path (ssr_capture -> glossy_convolve x4 -> ssao -> deferred_shade) over this rank's batch of
+VIEWS_PER_GPU synthetic 3840x2160 camera views (BASELINE configs[2] frame: 16 point lights with 256^2 omni shadow cubes,
+SSR + SSAO + glossy mips; sharded by view as in configs[4]: 8 views per GPU, one process per GPU, no data-path
+collective => weak scaling). value = pixels all ranks shaded / time. Inputs are resident in HBM for `value`; `e2e`
+repeats the measurement through the C ABI with the G-buffers in pinned HOST memory (H2D of every view's attachments and
+D2H of its colour target inside the timed region).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W4K, H4K = 3840, 2160
+N_LIGHTS = 16
+SHADOW_RES = 256
+ENV_W, ENV_H = 4096, 2048
+VIEWS_PER_GPU = 8
+METRIC = "deferred+SSAO+SSR Mpixel/s at 4K"
+UNIT = "Mpixel/s"
+
+# algorithmic bytes per pixel (SURVEY.md 8d / DESIGN.md): each buffer read once, written once
+BYTES_PER_PX = {
+    "ssr_capture": 28.0,      # depth 4 + normal 8 + albedo 4 + MRO 4 + write RGBA16F 8
+    "glossy_convolve": 13.28,  # read 8*(1+1/4+1/16+1/64) + write 8*(1/4+...+1/256)
+    "ssao": 25.0,             # position 16 + normal 8 + write count 1
+    "deferred_shade": 51.66,  # position 16 + normal 8 + albedo 4 + MRO 4 + AO count 1 + reflection mips (upper bound) 10.66 + write RGBA16F 8
+}
+FLOPS_PER_PX = {"ssao": 14400.0, "ssr_capture": 11500.0, "deferred_shade": 200.0 + 80.0 * N_LIGHTS, "glossy_convolve": 7 * 4 * 8.0}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md's clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._stop_evt, self.proc = gpu_index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self._stop_evt.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_rank_inputs(ctx, rank: int, views: int, device: str):
+    """All device-resident inputs of this rank: IBL set (built with our own precompute kernels), lights + shadow cubes, and
+    `views` G-buffers. Returns the objects plus the measured IBL precompute timings."""
+    import torch
+
+    from althea_b200 import _capi, engine, scene
+    F32 = _capi.FORMAT_R32G32B32A32_SFLOAT
+    # --- IBL: procedural 4096x2048 HDR env -> mips -> GGX prefilter at the reference's shape (5 mips, 10000 samples, hash RNG)
+    env_t = scene.procedural_env(ENV_W, ENV_H, device)
+    mips = 13
+    chain = ctx.new_image(F32, ENV_W, ENV_H, mips)
+    chain.tensor[: ENV_W * ENV_H * 16].copy_(env_t.view(-1).view(torch.uint8))
+    engine.ImageBasedLighting.generateMipMaps(ctx, chain)
+    pre = ctx.new_image(F32, ENV_W >> 1, ENV_H >> 1, 5)
+    irr_small = ctx.new_image(F32, 512, 256)
+    ctx.enable_timing(True)
+    ctx.reset_timings()
+    engine.ImageBasedLighting.precomputeResources(ctx, chain, irr_small, pre)
+    ctx.synchronize()
+    ibl_t = ctx.timings()
+    ctx.enable_timing(False)
+    ctx.reset_timings()
+    # the reference keeps a full-size irradiance image (ImageBasedLighting.cpp:534-568): same footprint, upsampled content
+    irr_s = irr_small.tensor.view(torch.float32).view(1, 256, 512, 4).permute(0, 3, 1, 2)
+    irr_full = torch.nn.functional.interpolate(irr_s, size=(ENV_H, ENV_W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1).contiguous()
+    irr = ctx.wrap_tensor(irr_full.view(-1), F32, ENV_W, ENV_H)
+    env = ctx.wrap_tensor(env_t.view(-1), F32, ENV_W, ENV_H)
+    lut = ctx.new_image(_capi.FORMAT_R8G8B8A8_UNORM, 512, 512)
+    engine.ImageBasedLighting.generateBrdfLut(ctx, lut, 1024)
+    ibl = engine.IBLResources(env, pre, irr, lut)
+    ibl._keep = (chain, irr_small)
+    # --- scene, lights, shadow cubes (S-scene ring around the camera so every yaw sees similar content)
+    sc = scene.make_ring_scene(160, device=device)
+    lights_t = scene.make_lights(N_LIGHTS, device=device, ring=True)
+    cubes = scene.shadow_cubes(sc, lights_t, SHADOW_RES)
+    lights = engine.PointLightCollection(ctx, N_LIGHTS, SHADOW_RES, True)
+    lights._buf_t.copy_(lights_t.view(-1))
+    lights._lights[:] = lights_t.cpu().numpy()
+    lights._dirty = False
+    lights.shadow_map.tensor.view(torch.float32).copy_(cubes.view(-1))
+    # --- views
+    out = []
+    for v in range(views):
+        gv = rank * views + v  # global view id, yaw = view * 5.625 deg
+        g = scene.make_uniforms(W4K, H4K, pos=(0.0, 2.0, 0.0), yaw=gv * 5.625 * 3.141592653589793 / 180.0, pitch=-0.2, light_count=N_LIGHTS)
+        gbd = scene.s_scene(g, W4K, H4K, sc, device=device)
+        gb = engine.GBufferResources(ctx, W4K, H4K)
+        gb.upload(position=gbd.position, depth=gbd.depth, normal=gbd.normal, albedo=gbd.albedo, mro=gbd.mro)
+        ssr = engine.ScreenSpaceReflection(ctx, W4K, H4K)
+        dp = engine.DeferredPass(ctx, W4K, H4K, _capi.FORMAT_R16G16B16A16_SFLOAT)
+        out.append((g, gb, ssr, dp))
+        del gbd
+    torch.cuda.synchronize()
+    return ibl, lights, out, ibl_t
+
+
+def run_frame(view, ibl, lights, stream):
+    from althea_b200 import _capi
+    g, gb, ssr, dp = view
+    ssr.captureReflection(g, gb, ibl, lights, stream)
+    ssr.convolveReflectionBuffer(stream)
+    dp.draw(g, gb, ibl, lights, ssr, _capi.SHADE_SKIP_TONEMAP, stream)
+
+
+def cpu_baseline_sample(repeats: int = 1):
+    """The oracle (CPU port of the reference's GLSL) on a bounded sample of the same workload, all host threads."""
+    import numpy as np
+    import torch
+
+    from althea_b200 import scene
+    from oracle import oracle as O
+    sw, sh = 1280, 720
+    sc = scene.make_ring_scene(160)
+    g = scene.make_uniforms(sw, sh, pos=(0.0, 2.0, 0.0), yaw=0.0, pitch=-0.2, light_count=N_LIGHTS)
+    gbd = scene.s_scene(g, sw, sh, sc).numpy()
+    lights_t = scene.make_lights(N_LIGHTS, ring=True)
+    cubes = scene.shadow_cubes(sc, lights_t, 64).numpy()
+    env = scene.procedural_env(512, 256).numpy()
+    chain, mips = O.env_mip_chain(env)
+    l0 = 512 * 256 * 4
+    pre = chain[l0:l0 + O.chain_texels(256, 128, 5) * 4].copy()
+    off4 = O.chain_texels(512, 256, 4) * 4
+    irr = chain[off4:off4 + 32 * 16 * 4].reshape(16, 32, 4).copy()
+    lut = np.zeros((64, 64, 4), np.uint8)
+    lut[..., :2] = (np.clip(O.brdf_lut(64, 64)[::-1], 0, 1) * 255 + 0.5).astype(np.uint8)
+    og = O.GlobalUniforms.from_buffer_copy(bytes(g))
+    fr = O.Frame(og, sw, sh, gbd["position"], gbd["depth"], gbd["normal"], gbd["albedo"], gbd["mro"], env, pre, (256, 128), 5, irr, lut,
+                 lights_t.numpy(), cubes, 64)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        refl, hit, _ = O.ssr_capture(fr)
+        ch = O.glossy_convolve(refl)
+        O.deferred_shade(fr, ch, 5, O.SKIP_TONEMAP, None)  # SSAO computed inside, as the shader does
+        times.append(time.perf_counter() - t0)
+    t = min(times)
+    return {"value": sw * sh / t / 1e6, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+            "sample": "1 view of the same S-scene at 1280x720 (1/9 of a 4K view), 16 lights, 64^2 shadow cubes; %d run(s), best %.2f s" % (repeats, t),
+            "seconds": t}
+
+
+def main_reference(args):
+    """--impl reference: the reference's own algorithm on the host CPU. The reference's path is GLSL + Vulkan and cannot be
+    compiled or run here (no Vulkan loader / lavapipe / glslc), so this is the oracle port, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline_sample(1)
+    samples = [cpu_baseline_sample(1) for _ in range(max(1, min(args.steps, 5)))]
+    secs = sum(s["seconds"] for s in samples) / len(samples)
+    value = 1280 * 720 / secs / 1e6
+    cb = dict(samples[0])
+    cb["value"] = value
+    cb.pop("seconds")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(samples), "warmup": min(args.warmup, 1),
+            "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C3/C5 stand-in: S-scene deferred+SSAO+SSR+glossy frame, 16 point lights + omni shadow cubes; CPU arm renders a "
+                                   "bounded sample (one 1280x720 view per step) of the 3840x2160 views"},
+            "cpu_baseline": cb, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--views", type=int, default=VIEWS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = "cuda:%d" % local_rank
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+
+    from althea_b200 import _capi, engine
+    ctx = engine.Context(local_rank)
+    ibl, lights, views, ibl_t = build_rank_inputs(ctx, rank, args.views, device)
+    stream = engine.current_stream_ptr(local_rank)
+    V = len(views)
+    px_per_step = V * W4K * H4K
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        for vw in views:
+            run_frame(vw, ibl, lights, stream)
+
+    for _ in range(args.warmup):
+        step()
+    # ---- timed region: inputs resident in HBM; per-kernel CUDA events on the launching stream for the roofline ----
+    ctx.enable_timing(True)
+    ctx.reset_timings()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count() - launches0
+    kt = ctx.timings()
+    ctx.enable_timing(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * px_per_step / (ms_step * 1e-3) / 1e6
+
+    # ---- e2e: same metric through the C ABI with HOST buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        F = _capi
+        fmts = [("position", F.FORMAT_R32G32B32A32_SFLOAT), ("depth", F.FORMAT_R32_SFLOAT), ("normal", F.FORMAT_R16G16B16A16_SFLOAT),
+                ("albedo", F.FORMAT_R8G8B8A8_UNORM), ("mro", F.FORMAT_R8G8B8A8_UNORM)]
+        host_in = []
+        for (g, gb, ssr, dp) in views:
+            host_in.append({n: getattr(gb, n).tensor.cpu().pin_memory() for n, _ in fmts})
+        host_out = [torch.empty(W4K * H4K * 8, dtype=torch.uint8).pin_memory() for _ in views]
+        h2d = sum(t_.numel() for t_ in host_in[0].values()) * V
+        d2h = host_out[0].numel() * V
+        # device side: ONE set of ctx-owned images reused for every view (the host engine's own G-buffer set)
+        dgb = engine.GBufferResources.__new__(engine.GBufferResources)
+        dgb.ctx, dgb.width, dgb.height = ctx, W4K, H4K
+        for n, f in fmts:
+            setattr(dgb, n, ctx.create_image(f, W4K, H4K))
+        dssr = engine.ScreenSpaceReflection(ctx, W4K, H4K)
+        ddp = engine.DeferredPass(ctx, W4K, H4K, F.FORMAT_R16G16B16A16_SFLOAT)
+
+        def e2e_step():
+            for i, (g, gb, ssr, dp) in enumerate(views):
+                for n, _ in fmts:
+                    ctx.upload(getattr(dgb, n), host_in[i][n].data_ptr(), host_in[i][n].numel(), stream)
+                run_frame((g, dgb, dssr, ddp), ibl, lights, stream)
+                ctx.download(ddp.colorTarget, host_out[i].data_ptr(), host_out[i].numel(), stream)
+
+        e2e_step()
+        barrier()
+        k2 = max(1, min(args.steps, 3))
+        e0.record()
+        for _ in range(k2):
+            e2e_step()
+        e1.record()
+        barrier()
+        t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms2 = float(t2.item()) / k2
+        e2e = {"value": world * px_per_step / (ms2 * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": ms2, "steps": k2}
+
+    if rank == 0:
+        hbm_peak, peak_src, sm_max = peaks()
+        px_frame = W4K * H4K
+        stages = {}
+        for name, rec in kt.items():
+            n = rec["launches"]
+            # glossy_convolve: 4 launches per frame, bytes accounted per frame
+            per_frame_ms = rec["total_ms"] / (args.steps * V)
+            gbs = BYTES_PER_PX.get(name, 0.0) * px_frame / (per_frame_ms * 1e-3) / 1e9 if per_frame_ms > 0 else 0.0
+            tfl = FLOPS_PER_PX.get(name, 0.0) * px_frame / (per_frame_ms * 1e-3) / 1e12 if per_frame_ms > 0 else 0.0
+            stages[name] = {"ms_per_frame": per_frame_ms, "launches": n, "algorithmic_GBps": gbs, "hbm_frac": gbs / hbm_peak,
+                            "algorithmic_TFLOPs": tfl, "fp32_frac_at_sm_max": tfl / (148 * 128 * 2 * sm_max * 1e6 / 1e12)}
+        dom = max(stages, key=lambda k: stages[k]["ms_per_frame"]) if stages else None
+        roofline = None
+        if dom:
+            s = stages[dom]
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": s["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": s["hbm_frac"],
+                        "traffic": None, "peak_source": peak_src,
+                        "note": "%s is FP32-issue / L1-tap bound, not HBM bound (SURVEY.md 8d): fp32 frac %.3f of 148 SM x 128 lanes x 2 x %.0f MHz"
+                                % (dom, s["fp32_frac_at_sm_max"], sm_max)}
+        frame_ms = ms_step / V
+        chain = {"bytes_per_px": 92.0, "achieved_GBps": 92.0 * px_frame / (frame_ms * 1e-3) / 1e9, "hbm_frac": 92.0 * px_frame / (frame_ms * 1e-3) / 1e9 / hbm_peak,
+                 "ms_per_4k_frame": frame_ms, "frames_per_s": 1e3 / frame_ms * world}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "C3/C5 stand-in: %d views/GPU of a 3840x2160 S-scene deferred+SSAO+SSR+glossy frame, 16 point lights + 256^2 omni "
+                                       "shadow cubes, view-sharded (no collective)" % V,
+                           "views_per_gpu": V, "resolution": [W4K, H4K], "lights": N_LIGHTS, "l2_policy": "inputs (%.1f GB/step/GPU) exceed the 126 MB L2"
+                                                                                                      % (V * px_frame * 36 / 1e9),
+                           "math": "fast build (FFMA); parity build checked in tests"},
+                "gpu_launches": int(launches) * world, "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_chain": chain, "stages": stages,
+                "ibl_precompute_ms": {k: v["total_ms"] for k, v in ibl_t.items()},
+                "ibl_config": "reference shape: %dx%d equirect env, 5 GGX mips (2048x1024..128x64), 10000 samples/texel, hash RNG" % (ENV_W, ENV_H)}
+        if not args.no_cpu_baseline:
+            from oracle import oracle as O
+            O.build()
+            line["cpu_baseline"] = {k: v for k, v in cpu_baseline_sample(2).items() if k != "seconds"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

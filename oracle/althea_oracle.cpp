@@ -169,7 +169,10 @@ V3 viewDirection(const OracleGlobalUniforms& g, float u, float v) {
 // Misc/ReconstructPosition.glsl:4-22
 V3 reconstructPosition(const OracleGlobalUniforms& g, float u, float v, float dRaw) {
   const float near = 0.01f, far = 1000.0f;
-  float d = far * near / (dRaw * (far - near) - far);
+  // dRaw*(far-near) - far cancels catastrophically (dRaw ~ 0.999): evaluated unfused it loses ~3 decimal digits of the
+  // eye depth, and the SSR threshold tests amplify that noise into hit flips on ~8 % of pixels (measured on B200).
+  // GLSL leaves contraction to the compiler and every GPU compiler emits one FFMA here, so the oracle pins that reading.
+  float d = far * near / fmaf(dRaw, far - near, -far);
   V4 dirH = mul(g.inverseProjection, V4{2.0f * u - 1.0f, 2.0f * v - 1.0f, 2.0f, 1.0f});
   V4 h{dirH.x / dirH.w, dirH.y / dirH.w, dirH.z / dirH.w, 0.0f};
   V4 wd = mul(g.inverseView, h);

@@ -1,0 +1,68 @@
+"""CPU tests of the boundary: the shared library builds, loads, exports exactly the symbols include/althea_cuda.h
+declares, the parameter blocks have the reference's byte layout, and nothing silently falls back when no GPU exists."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from althea_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "althea_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(althea_cuda_[a-z_]+)\s*\(", text))
+
+
+def test_header_and_binding_agree():
+    assert _declared_symbols() == set(_capi.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    lib = C.CDLL(lib_built)
+    for name in _declared_symbols():
+        assert hasattr(lib, name), name
+    assert _capi.load().althea_cuda_abi_version() == 1
+
+
+def test_parameter_block_layouts():
+    # Include/Althea/GlobalUniforms.h:15-31 -> offsets per SURVEY.md App. B
+    G = _capi.GlobalUniforms
+    assert C.sizeof(G) == 416
+    off = {f[0]: getattr(G, f[0]).offset for f in G._fields_}
+    assert (off["projection"], off["inverseProjection"], off["view"], off["prevView"], off["inverseView"], off["prevInverseView"]) == (
+        0, 64, 128, 192, 256, 320)
+    assert (off["mouseUV"], off["lightCount"], off["lightBufferHandle"], off["time"], off["exposure"], off["inputMask"],
+            off["frameCount"]) == (384, 392, 396, 400, 404, 408, 412)
+    assert C.sizeof(_capi.GBuffer) == 40 and C.sizeof(_capi.IBL) == 32 and C.sizeof(_capi.Sync) == 40
+
+
+def test_image_bytes(lib_built):
+    lib = _capi.load()
+    f = lib.althea_cuda_image_bytes
+    assert f(_capi.FORMAT_R16G16B16A16_SFLOAT, 3840, 2160, 5, 1) == 8 * (3840 * 2160 + 1920 * 1080 + 960 * 540 + 480 * 270 + 240 * 135)
+    assert f(_capi.FORMAT_R32_SFLOAT, 256, 256, 1, 96) == 4 * 256 * 256 * 96
+    assert f(_capi.FORMAT_R32G32B32A32_SFLOAT, 4096, 2048, 13, 1) == 16 * sum(max(1, 4096 >> k) * max(1, 2048 >> k) for k in range(13))
+    assert f(12345, 4, 4, 1, 1) == 0
+
+
+def test_no_cpu_fallback_without_gpu(lib_built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from althea_b200 import engine
+    with pytest.raises(engine.AltheaError, match="no CPU fallback|no CUDA"):
+        engine.Context(0)
+
+
+def test_product_does_not_import_oracle():
+    # the oracle is test infrastructure: nothing under althea_b200/ may reference it
+    pkg = os.path.join(ROOT, "althea_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\"[^\"]*oracle", src, flags=re.M), os.path.join(dirpath, fn)

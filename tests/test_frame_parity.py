@@ -1,0 +1,314 @@
+"""GPU parity tests of the per-frame stages, through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): per-channel max abs error <= 1e-3 and PSNR >= 50 dB on linear-HDR outputs; AO and SSR
+hit masks within 0.1 % of pixels. "abs 1e-3" is applied as |a-b| <= 1e-3 * max(1, |b|): the outputs are HDR (values up
+to ~150), and RGBA16F targets carry half-precision rounding (1 ulp = 2^-10 relative), so a pure absolute bound is
+meaningless above 1.0. The parity build (-fmad=false) is additionally required to reproduce the oracle's threshold
+decisions EXACTLY: SSAO counts and SSR hit masks are integer work and the bar for those is bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, FrameData, GpuFrame, half_to_float, psnr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+MASK_BAR = 1e-3  # 0.1 % of pixels
+
+
+def close(a, b, tol=TOL):
+    return np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b))
+
+
+@pytest.fixture(scope="module")
+def frames():
+    return {"scene": FrameData("scene", 256, 144, n_lights=4, shadow_res=64), "rand": FrameData("rand", 160, 90, n_lights=3, shadow_res=32)}
+
+
+@pytest.fixture(scope="module")
+def oracle_out(frames, oracle):
+    out = {}
+    for k, fd in frames.items():
+        fr = fd.oracle_frame()
+        refl, hit, steps = oracle.ssr_capture(fr)
+        chain = oracle.glossy_convolve(refl)
+        ao = oracle.ssao(fr)
+        col = oracle.deferred_shade(fr, chain, 5, oracle.SKIP_TONEMAP, ao)
+        out[k] = dict(refl=refl, hit=hit, chain=chain, ao=ao, color=col, frame=fr)
+    return out
+
+
+def _ctx(request, which):
+    return request.getfixturevalue("ctx_parity" if which == "parity" else "ctx_fast")
+
+
+@pytest.mark.parametrize("which", ["parity", "fast"])
+@pytest.mark.parametrize("kind", ["scene", "rand"])
+def test_ssr_capture(request, frames, oracle_out, which, kind):
+    ctx = _ctx(request, which)
+    fd, ref = frames[kind], oracle_out[kind]
+    gf = GpuFrame(ctx, fd)
+    gf.ssr.captureReflection(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights)
+    got = gf.reflection_level(0)
+    got_f, ref_f = half_to_float(got), half_to_float(ref["refl"])
+    hit = got_f[..., 3] != 0
+    mismatch = float(np.mean(hit != (ref["hit"] != 0)))
+    assert ref["hit"].mean() > 0.05, "test scene must produce SSR hits"
+    if which == "parity":
+        assert mismatch == 0.0
+    else:
+        assert mismatch <= MASK_BAR
+    agree = hit == (ref["hit"] != 0)
+    ok = close(got_f, ref_f)[agree]
+    assert ok.all(), "max rel err %g" % float(np.max(np.abs(got_f - ref_f)[agree] / np.maximum(1, np.abs(ref_f))[agree]))
+    assert psnr(got_f[agree], ref_f[agree]) >= 50.0
+    # empty pixels (normal.a == 0) write exactly (0,0,0,0)
+    empty = fd.normal[..., 3] == 0
+    assert not got[empty].any()
+
+
+@pytest.mark.parametrize("which", ["parity", "fast"])
+@pytest.mark.parametrize("kind", ["scene", "rand"])
+def test_glossy_convolve(request, frames, oracle_out, which, kind):
+    ctx = _ctx(request, which)
+    fd, ref = frames[kind], oracle_out[kind]
+    gf = GpuFrame(ctx, fd)
+    import torch
+    img = gf.ssr.getReflectionBuffer().image
+    n0 = fd.W * fd.H * 8
+    img.tensor[:n0].copy_(torch.from_numpy(ref["refl"].view(np.uint8).reshape(-1)))  # stage-isolated: oracle's mip 0 in
+    gf.ssr.convolveReflectionBuffer()
+    got = half_to_float(gf.reflection_chain())
+    want = half_to_float(ref["chain"])
+    assert np.array_equal(got[: fd.W * fd.H * 4], want[: fd.W * fd.H * 4])
+    # both sides round to RGBA16F: allow one half ulp flip (2^-10 relative), nothing more
+    assert close(got, want, 2.0 ** -10 + 1e-6).all()
+    if which == "parity":
+        assert np.mean(got != want) < 1e-3  # essentially bit-identical
+
+
+@pytest.mark.parametrize("which", ["parity", "fast"])
+@pytest.mark.parametrize("kind", ["scene", "rand"])
+def test_ssao_counts(request, frames, oracle_out, which, kind):
+    ctx = _ctx(request, which)
+    fd, ref = frames[kind], oracle_out[kind]
+    gf = GpuFrame(ctx, fd)
+    from althea_b200 import _capi
+    gf.ssr.convolveReflectionBuffer()
+    gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+    got = gf.ao_counts()
+    want = ref["ao"]
+    assert (want[want < 255] > 0).mean() > 0.02, "test scene must produce occlusion"
+    assert np.array_equal(got == 255, want == 255)
+    mismatch = float(np.mean(got != want))
+    if which == "parity":
+        assert mismatch == 0.0
+    else:
+        assert mismatch <= MASK_BAR
+        assert np.abs(got.astype(int) - want.astype(int)).max() <= 2
+
+
+@pytest.mark.parametrize("which", ["parity", "fast"])
+@pytest.mark.parametrize("kind", ["scene", "rand"])
+def test_deferred_shade_given_ao_and_reflection(request, frames, oracle_out, which, kind):
+    """Shading parity in isolation: the oracle's reflection chain and AO counts go in, so threshold flips upstream cannot
+    leak into this comparison."""
+    ctx = _ctx(request, which)
+    fd, ref = frames[kind], oracle_out[kind]
+    gf = GpuFrame(ctx, fd)
+    import torch
+    from althea_b200 import _capi
+    gf.ssr.getReflectionBuffer().image.tensor.copy_(torch.from_numpy(ref["chain"].view(np.uint8).reshape(-1)))
+    gf.deferred.aoCounts.tensor.copy_(torch.from_numpy(ref["ao"].reshape(-1)))
+    gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP | _capi.SHADE_AO_FROM_IMAGE)
+    got, want = gf.color(), ref["color"]
+    assert np.isfinite(got).all()
+    assert close(got, want).all(), "max rel err %g" % float(np.max(np.abs(got - want) / np.maximum(1, np.abs(want))))
+    assert psnr(got, want) >= 50.0
+    assert (got[..., 3] == 1.0).all()
+
+
+@pytest.mark.parametrize("which", ["parity", "fast"])
+def test_full_chain(request, frames, oracle_out, which):
+    """SSR -> convolve -> SSAO -> shade, all on the GPU, against the oracle's chain."""
+    ctx = _ctx(request, which)
+    fd, ref = frames["scene"], oracle_out["scene"]
+    gf = GpuFrame(ctx, fd)
+    from althea_b200 import _capi
+    gf.ssr.captureReflection(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights)
+    gf.ssr.convolveReflectionBuffer()
+    gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+    got, want = gf.color(), ref["color"]
+    ok = close(got, want).all(axis=-1)
+    if which == "parity":
+        assert ok.mean() >= 0.9995  # only half-ulp flips of the RGBA16F reflection mips can differ
+    else:
+        assert ok.mean() >= 0.995   # a flipped SSR hit is blurred into its neighbours by the mip chain
+    assert psnr(got, want) >= 50.0
+
+
+def test_against_committed_golden(ctx_parity, oracle):
+    """The committed vectors (tests/golden/frame_golden.npz, written by make_golden.py) must be reproduced on the GPU."""
+    gold = np.load(os.path.join(GOLDEN, "frame_golden.npz"))
+    from althea_b200 import _capi
+    for tag, kind, W, H in (("scene", "scene", 160, 90), ("rand", "rand", 96, 54)):
+        fd = FrameData(kind, W, H, n_lights=4, shadow_res=32)
+        gf = GpuFrame(ctx_parity, fd)
+        gf.ssr.captureReflection(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights)
+        hit = half_to_float(gf.reflection_level(0))[..., 3] != 0
+        assert np.array_equal(hit, gold[tag + "_hit"] != 0)
+        gf.ssr.convolveReflectionBuffer()
+        gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+        assert np.array_equal(gf.ao_counts(), gold[tag + "_ao"])
+        got, want = gf.color(), gold[tag + "_color"]
+        assert close(got, want).all(axis=-1).mean() >= 0.9995
+        assert psnr(got, want) >= 50.0
+
+
+# ---- edge cases -------------------------------------------------------------------------------------------------------
+def test_odd_sizes_tonemap_and_half_output(ctx_parity, oracle):
+    from althea_b200 import _capi
+    fd = FrameData("scene", 101, 67, n_lights=2, shadow_res=16)
+    fr = fd.oracle_frame()
+    refl, hit, _ = oracle.ssr_capture(fr)
+    chain = oracle.glossy_convolve(refl)
+    ao = oracle.ssao(fr)
+    want = oracle.deferred_shade(fr, chain, 5, 0, ao)  # tonemapped
+    gf = GpuFrame(ctx_parity, fd, out_format=_capi.FORMAT_R16G16B16A16_SFLOAT)
+    gf.ssr.captureReflection(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights)
+    gf.ssr.convolveReflectionBuffer()
+    got_chain = half_to_float(gf.reflection_chain())
+    assert close(got_chain, half_to_float(chain), 2.0 ** -10 + 1e-6).all()  # mips 50x33, 25x16, 12x8, 6x4
+    gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, 0)
+    assert np.array_equal(gf.ao_counts(), ao)
+    got = gf.color()
+    assert close(got, want.astype(np.float16).astype(np.float32), 2.0 ** -10 + 1e-6).all(axis=-1).mean() >= 0.999
+    assert got.max() <= 1.0  # 1 - exp(-c * exposure)
+
+
+def test_empty_gbuffer_draws_environment(ctx_fast, oracle):
+    from althea_b200 import _capi
+    fd = FrameData("scene", 64, 36, n_lights=0)
+    fd.position[:] = 0
+    fd.normal[:] = 0
+    fd.depth[:] = 1
+    fd.albedo[:] = 0
+    fd.mro[:] = 0
+    gf = GpuFrame(ctx_fast, fd)
+    gf.ssr.captureReflection(fd.uniforms, gf.gbuffer, gf.ibl, None)
+    assert not gf.reflection_level(0).any()
+    gf.ssr.convolveReflectionBuffer()
+    assert not gf.reflection_chain().any()
+    gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, None, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+    want = oracle.deferred_shade(fd.oracle_frame(), np.zeros_like(gf.reflection_chain()), 5, oracle.SKIP_TONEMAP, None)
+    assert close(gf.color(), want).all()
+    assert (gf.ao_counts() == 255).all()
+
+
+def test_no_lights_and_no_shadow_maps(ctx_parity, oracle):
+    from althea_b200 import _capi
+    fd = FrameData("scene", 96, 54, n_lights=0)
+    fr = fd.oracle_frame()
+    refl, hit, _ = oracle.ssr_capture(fr)
+    gf = GpuFrame(ctx_parity, fd)
+    gf.ssr.captureReflection(fd.uniforms, gf.gbuffer, gf.ibl, None)
+    assert np.array_equal(half_to_float(gf.reflection_level(0))[..., 3] != 0, hit != 0)
+    assert close(half_to_float(gf.reflection_level(0)), half_to_float(refl)).all()
+
+
+def test_error_behaviour(ctx_fast):
+    """The reference throws std::runtime_error; the C ABI returns a status + message, the mirror raises AltheaError."""
+    import ctypes as C
+
+    from althea_b200 import _capi, engine
+    fd = FrameData("scene", 32, 18, n_lights=1, shadow_res=8)
+    gf = GpuFrame(ctx_fast, fd)
+    lib, p = ctx_fast._lib, ctx_fast._ptr
+    gb, ib = gf.gbuffer.struct(), gf.ibl.struct()
+    # bad handle
+    rc = lib.althea_cuda_glossy_convolve(p, 987654, None)
+    assert rc == -4 and b"not a live image" in lib.althea_cuda_last_error(p)
+    # wrong format for the reflection target
+    rc = lib.althea_cuda_ssr_capture(p, C.byref(fd.uniforms), C.byref(gb), C.byref(ib), gf.lights.buffer.handle, gf.lights.shadow_handle,
+                                     gf.gbuffer.albedo.handle, None)
+    assert rc == -1 and b"expected VkFormat 97" in lib.althea_cuda_last_error(p)
+    # size mismatch between G-buffer and reflection buffer
+    small = engine.ScreenSpaceReflection(ctx_fast, 16, 16)
+    with pytest.raises(engine.AltheaError, match="must all be"):
+        small.captureReflection(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights)
+    # lightCount larger than the light buffer
+    u = _capi.GlobalUniforms.from_buffer_copy(bytes(fd.uniforms))
+    u.lightCount = 9
+    with pytest.raises(engine.AltheaError, match="lights_buf holds"):
+        gf.ssr.captureReflection(u, gf.gbuffer, gf.ibl, gf.lights)
+    # release invalidates
+    img = ctx_fast.new_image(_capi.FORMAT_R8_UINT, 8, 8)
+    h = img.handle
+    img.release()
+    assert lib.althea_cuda_release(p, h) == -4
+    # host pointers are rejected by wrap
+    import numpy as np
+    host = np.zeros(64, np.uint8)
+    out = C.c_uint64()
+    rc = lib.althea_cuda_wrap_linear_image(p, host.ctypes.data_as(C.c_void_p), 0, _capi.FORMAT_R8_UINT, 8, 8, 1, 1, C.byref(out))
+    assert rc == -1 and b"not device memory" in lib.althea_cuda_last_error(p)
+
+
+# ---- size-independent properties at the full 4K size (BASELINE configs C3/C5) -------------------------------------------
+def test_properties_at_4k(ctx_fast):
+    import torch
+
+    from althea_b200 import _capi, engine, scene
+    W, H = 3840, 2160
+    dev = "cuda:0"
+    g = scene.make_uniforms(W, H, pos=(0.0, 2.0, 6.0), yaw=0.0, pitch=-0.25, light_count=0)
+    gbd = scene.s_scene(g, W, H, scene.make_scene(64, device=dev), device=dev)
+    gb = engine.GBufferResources(ctx_fast, W, H)
+    gb.upload(position=gbd.position, depth=gbd.depth, normal=gbd.normal, albedo=gbd.albedo, mro=gbd.mro)
+    fd = FrameData("scene", 32, 18, n_lights=0)
+    small = GpuFrame(ctx_fast, fd)  # reuse its IBL set
+    ssr = engine.ScreenSpaceReflection(ctx_fast, W, H)
+    dp = engine.DeferredPass(ctx_fast, W, H, _capi.FORMAT_R16G16B16A16_SFLOAT)
+
+    def run():
+        ssr.captureReflection(g, gb, small.ibl, None)
+        ssr.convolveReflectionBuffer()
+        dp.draw(g, gb, small.ibl, None, ssr, _capi.SHADE_SKIP_TONEMAP)
+        torch.cuda.synchronize()
+        return ssr.getReflectionBuffer().image.tensor.clone(), dp.colorTarget.tensor.clone(), dp.aoCounts.tensor.clone()
+
+    r1, c1, a1 = run()
+    r2, c2, a2 = run()
+    assert torch.equal(r1, r2) and torch.equal(c1, c2) and torch.equal(a1, a2)  # deterministic / idempotent
+    ao = a1.view(H, W)
+    empty = gbd.position[..., 3] == 0
+    assert bool((ao[empty] == 255).all()) and bool((ao[~empty] <= 24).all())
+    refl0 = r1[: W * H * 8].view(torch.float16).view(H, W, 4).float()
+    assert bool((refl0[empty.to(dev)] == 0).all())                # sky writes (0,0,0,0)
+    alpha = refl0[..., 3]
+    assert bool(((alpha == 0) | (alpha == 1)).all())                # hit alpha is exactly 0 or 1
+    assert 0.02 < float(alpha.mean()) < 0.6
+    col = c1.view(torch.float16).view(H, W, 4).float()
+    assert bool(torch.isfinite(col).all()) and bool((col[..., 3] == 1).all())
+    # convolve properties: a constant image stays constant (weights sum to 1 within rounding); linear in its input
+    rb = engine.ReflectionBuffer(ctx_fast, W, H)
+    n0 = W * H * 4
+    t16 = rb.image.tensor.view(torch.float16)
+    t16[:n0] = 0.75
+    rb.convolveReflectionBuffer()
+    torch.cuda.synchronize()
+    assert float((t16.float() - 0.75).abs().max()) <= 2.0 ** -10
+    t16[:n0] = refl0.reshape(-1).half()
+    rb.convolveReflectionBuffer()
+    torch.cuda.synchronize()
+    base = t16.float().clone()
+    assert torch.equal(t16[n0:].view(torch.int16), r1.view(torch.int16)[n0:])  # same input -> same mips as the SSR buffer
+    t16[:n0] = (refl0.reshape(-1) * 0.5).half()
+    rb.convolveReflectionBuffer()
+    torch.cuda.synchronize()
+    scaled = t16.float()
+    big = base.abs() > 1e-3  # away from fp16 subnormals scaling by 2 is exact
+    assert float(((scaled * 2.0 - base).abs()[big] / base.abs()[big]).max()) <= 2.0 ** -9
