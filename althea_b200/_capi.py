@@ -21,6 +21,7 @@ BYTES_PER_TEXEL = {FORMAT_R8_UINT: 1, FORMAT_R8G8B8A8_UNORM: 4, FORMAT_R16G16B16
                    FORMAT_R32G32B32A32_SFLOAT: 16, FORMAT_D32_SFLOAT: 4}
 
 CTX_PARITY_MATH = 1
+CTX_SSAO_EXACT_TAPS = 2
 SHADE_SKIP_TONEMAP = 1
 SHADE_NO_SSAO = 2
 SHADE_AO_FROM_IMAGE = 4

@@ -50,6 +50,9 @@ struct althea_cuda_ctx {
   // internal scratch: SSAO occluded-ray counts
   void* aoScratch = nullptr;
   size_t aoScratchBytes = 0;
+  // internal scratch: SSAO position-quad proxy, (W+1) x (H+1) x 32 B
+  void* quadScratch = nullptr;
+  size_t quadScratchBytes = 0;
   // timing
   bool timing = false;
   std::vector<TimingEntry> pending;
@@ -321,6 +324,7 @@ void althea_cuda_destroy(althea_cuda_ctx* ctx) {
   }
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   if (ctx->aoScratch) cudaFree(ctx->aoScratch);
+  if (ctx->quadScratch) cudaFree(ctx->quadScratch);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -640,11 +644,30 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
       P.ao.ptr = ctx->aoScratch; P.ao.w = P.W; P.ao.h = P.H; P.ao.pitch = P.W;
     }
   }
+  const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
+  const bool computeAo = needAo && !(flags & ALTHEA_SHADE_AO_FROM_IMAGE);
+  const bool exactTaps = ctx->flags & ALTHEA_CTX_SSAO_EXACT_TAPS;
+  if (computeAo && !exactTaps) {
+    P.quadPitch = ((size_t)P.W + 1) * 32;
+    size_t need = P.quadPitch * ((size_t)P.H + 1);
+    if (ctx->quadScratchBytes < need) {
+      if (ctx->quadScratch) { cudaStreamSynchronize(ctx->stream); cudaDeviceSynchronize(); cudaFree(ctx->quadScratch); ctx->quadScratch = nullptr; ctx->quadScratchBytes = 0; }
+      cudaError_t e = cudaMalloc(&ctx->quadScratch, need);
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(ssao quad scratch %zu): %s", need, cudaGetErrorString(e)); }
+      ctx->quadScratchBytes = need;
+    }
+    P.quads = ctx->quadScratch;
+  }
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
-  const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
-  if (needAo && !(flags & ALTHEA_SHADE_AO_FROM_IMAGE))
-    timedLaunch(ctx, "ssao", stream, [&] { parity ? althea_parity::launch_ssao(P, stream) : althea_fast::launch_ssao(P, stream); });
+  if (computeAo) {
+    if (exactTaps) {
+      timedLaunch(ctx, "ssao_exact", stream, [&] { parity ? althea_parity::launch_ssao_exact(P, stream) : althea_fast::launch_ssao_exact(P, stream); });
+    } else {
+      timedLaunch(ctx, "ssao_quads", stream, [&] { parity ? althea_parity::launch_ssao_quads(P, stream) : althea_fast::launch_ssao_quads(P, stream); });
+      timedLaunch(ctx, "ssao", stream, [&] { parity ? althea_parity::launch_ssao(P, stream) : althea_fast::launch_ssao(P, stream); });
+    }
+  }
   timedLaunch(ctx, "deferred_shade", stream, [&] { parity ? althea_parity::launch_deferred_shade(P, stream) : althea_fast::launch_deferred_shade(P, stream); });
   return endWork(ctx, sync, stream);
 }

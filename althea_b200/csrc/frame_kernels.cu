@@ -228,7 +228,21 @@ __global__ void __launch_bounds__(256) glossy_convolve_kernel(const __grid_const
 }
 
 // ---- SSAO -----------------------------------------------------------------------------------------------------------
-ADEV int ssaoCount(const FrameParams& P, int px, int py, float u0, float v0, V3 worldPos, V3 normal) {
+// computeSSAO (SSAO.glsl:31-84) counts, per pixel, the rays (24) whose 12-step screen-space march over the POSITION
+// G-buffer finds an occluder. Each march step is one bilinear RGBA32F tap whose location is effectively random over a
+// window of up to ~300 px at 4K, so the stage is bound by the L1 data pipe: a warp-level LDG pays one wavefront per distinct
+// 128-byte line and here nearly every lane has its own (profiles/r1a: 20.4 wavefronts per LDG.128, L1 pipe 98.8 % busy).
+//
+// ssao_exact_kernel: the straight restatement, 4 LDG.128 per tap.
+// ssao_kernel: filtered exact predicates over a packed proxy. A pre-pass (ssao_quads_kernel) stores, for
+//   every bilinear footprint (ix, iy), ONE 32-byte record {p00 (3 x fp32), p10-p00, p01-p00, p11-p00 (9 x fp16), E (fp16)}
+//   where E is an upper bound of the per-component error of the record against the four fp32 texels. A tap is then ONE
+//   256-bit load (one sector, one line) giving the interpolated position to within E. Every decision of the march is a
+//   threshold test; whenever the approximate value is farther from its threshold than the rigorous error bound
+//   (storage error E + fp32 rounding slop), the decision is the one the exact arithmetic takes. Otherwise that tap is
+//   re-evaluated from the fp32 texels with the restatement's own expression. Counts are therefore identical to
+//   ssao_exact_kernel's, bit for bit, in both builds (checked at 4K in tests/).
+ADEV int ssaoCountExact(const FrameParams& P, int px, int py, float u0, float v0, V3 worldPos, V3 normal) {
   HashRng rng;
   rng.sx = (uint32_t)px;
   rng.sy = (uint32_t)py;
@@ -262,6 +276,196 @@ ADEV int ssaoCount(const FrameParams& P, int px, int py, float u0, float v0, V3 
   return ao;
 }
 
+__global__ void __launch_bounds__(256) ssao_exact_kernel(const __grid_constant__ FrameParams P) {
+  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (x >= P.W || y >= P.H) return;
+  V4 position = FmtRGBA32F::load(P.position, x, y);
+  uint8_t count = 255;
+  if (position.w != 0.0f) {
+    const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
+    V3 normal = normalize3(xyz(FmtRGBA16F::load(P.normal, x, y)));
+    count = (uint8_t)ssaoCountExact(P, x, y, u, v, xyz(position), normal);
+  }
+  rowPtrW<uint8_t>(P.ao, y)[x] = count;
+}
+
+// -- proxy records ------------------------------------------------------------------------------------------------------
+struct __align__(32) QuadRecord { uint32_t w[8]; };
+
+ADEV uint32_t packHalf2(__half a, __half b) {
+  __half2 h = __halves2half2(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+ADEV float2 unpackHalf2(uint32_t w) { return __half22float2(*reinterpret_cast<__half2*>(&w)); }
+
+__global__ void __launch_bounds__(256) ssao_quads_kernel(const __grid_constant__ FrameParams P) {
+  const int qx = blockIdx.x * 32 + (threadIdx.x & 31); // record column = ix + 1
+  const int qy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (qx > P.W || qy > P.H) return;
+  const int i0 = AddrClamp::wrap(qx - 1, P.W), i1 = AddrClamp::wrap(qx, P.W);
+  const int j0 = AddrClamp::wrap(qy - 1, P.H), j1 = AddrClamp::wrap(qy, P.H);
+  const V4 p00 = FmtRGBA32F::load(P.position, i0, j0), p10 = FmtRGBA32F::load(P.position, i1, j0);
+  const V4 p01 = FmtRGBA32F::load(P.position, i0, j1), p11 = FmtRGBA32F::load(P.position, i1, j1);
+  const float b[3] = {p00.x, p00.y, p00.z};
+  const float t[9] = {p10.x, p10.y, p10.z, p01.x, p01.y, p01.z, p11.x, p11.y, p11.z};
+  __half h[9];
+  float E = 0.0f;
+  bool finite = isfinite(b[0]) && isfinite(b[1]) && isfinite(b[2]);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float D = __fsub_rn(t[k], b[k % 3]); // |D - (t - b)| <= 2^-24 |D|
+    h[k] = __float2half_rn(D);
+    const float back = __half2float(h[k]);
+    finite = finite && isfinite(t[k]) && isfinite(back);
+    E = fmaxf(E, __fadd_ru(fabsf(__fsub_rn(back, D)), __fmul_ru(fabsf(D), 9.6e-7f))); // back - D is exact in fp32 (Sterbenz); 2^-20 |D| covers fp32 lerp rounding on large texels
+  }
+  E = __fadd_ru(__fmul_ru(E, 1.0001f), 1e-30f);
+  const __half Eh = finite ? __float2half_ru(E) : __ushort_as_half((unsigned short)0x7c00u); // +inf => always re-evaluate exactly
+  QuadRecord r;
+  r.w[0] = __float_as_uint(b[0]); r.w[1] = __float_as_uint(b[1]); r.w[2] = __float_as_uint(b[2]);
+  r.w[3] = packHalf2(h[0], h[1]); r.w[4] = packHalf2(h[2], h[3]); r.w[5] = packHalf2(h[4], h[5]);
+  r.w[6] = packHalf2(h[6], h[7]); r.w[7] = packHalf2(h[8], Eh);
+  QuadRecord* row = reinterpret_cast<QuadRecord*>(const_cast<char*>(static_cast<const char*>(P.quads)) + (size_t)qy * P.quadPitch);
+  uint4* dst = reinterpret_cast<uint4*>(row + qx);
+  dst[0] = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
+  dst[1] = make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]);
+}
+
+ADEV QuadRecord loadQuad(const void* p) { // one 256-bit load: LDG.E.ENL2.256 on sm_100a
+  QuadRecord r;
+  asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+      : "l"(p));
+  return r;
+}
+
+struct ProxyTap {
+  V3 pos;    // interpolated position, within `err` per component of the real-arithmetic bilinear value
+  float err; // storage error bound E of the record
+};
+ADEV ProxyTap proxyTap(const FrameParams& P, float u, float v) {
+  // same coordinate arithmetic as the exact tap (rule A1): the footprint and the weights are identical, only the texel
+  // values are approximate
+  float x = __fsub_rn(__fmul_rn(u, (float)P.W), 0.5f), y = __fsub_rn(__fmul_rn(v, (float)P.H), 0.5f);
+  if (!(x == x)) x = 0.0f;
+  if (!(y == y)) y = 0.0f;
+  const float fx0 = floorf(x), fy0 = floorf(y);
+  const float fx = x - fx0, fy = y - fy0;
+  const int qx = min(max((int)fx0, -1), P.W - 1) + 1, qy = min(max((int)fy0, -1), P.H - 1) + 1;
+  const QuadRecord r = loadQuad(static_cast<const char*>(P.quads) + (size_t)qy * P.quadPitch + (size_t)qx * sizeof(QuadRecord));
+  const float2 a = unpackHalf2(r.w[3]), b = unpackHalf2(r.w[4]), c = unpackHalf2(r.w[5]), d = unpackHalf2(r.w[6]), e = unpackHalf2(r.w[7]);
+  // deltas: d10 = (a.x, a.y, b.x), d01 = (b.y, c.x, c.y), d11 = (d.x, d.y, e.x); E = e.y
+  ProxyTap t;
+  {
+    const float top = a.x * fx, bot = fmaf(d.x - b.y, fx, b.y);
+    t.pos.x = __uint_as_float(r.w[0]) + fmaf(bot - top, fy, top);
+  }
+  {
+    const float top = a.y * fx, bot = fmaf(d.y - c.x, fx, c.x);
+    t.pos.y = __uint_as_float(r.w[1]) + fmaf(bot - top, fy, top);
+  }
+  {
+    const float top = b.x * fx, bot = fmaf(e.x - c.y, fx, c.y);
+    t.pos.z = __uint_as_float(r.w[2]) + fmaf(bot - top, fy, top);
+  }
+  t.err = e.y;
+  return t;
+}
+
+// the restatement's own expressions for one tap; kept out of line: it runs for a few percent of the taps only
+struct ExactTap { V3 pos; float projection; };
+__device__ __noinline__ ExactTap exactTap(const FrameParams& P, float cu, float cv, V3 worldPos, V3 perpRef) {
+  ExactTap t;
+  t.pos = xyz(bilinear<FmtRGBA32F, AddrClamp>(P.position, cu, cv));
+  t.projection = dot3(t.pos - worldPos, perpRef);
+  return t;
+}
+__device__ __noinline__ bool facesRay(const FrameParams& P, float cu, float cv, V3 rayDir) {
+  V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, cu, cv)));
+  return dot3(currentNormal, rayDir) < 0.0f;
+}
+
+constexpr float kSqrt3Up = 1.7320509f;
+// fp32 rounding slop, as a multiple of the largest coordinate magnitude M in play: both the restatement's evaluation and
+// the proxy's are within ~16 ulp(M) of real arithmetic (two lerp levels, a subtraction, a 3-term dot product)
+constexpr float kRoundSlop = 64.0f * 1.1920929e-7f;
+
+ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float v0, V3 worldPos, V3 normal) {
+  HashRng rng;
+  rng.sx = (uint32_t)px;
+  rng.sy = (uint32_t)py;
+  const TangentFrame tbn = localToWorld(normal);
+  const float posMag = fabsf(worldPos.x) + fabsf(worldPos.y) + fabsf(worldPos.z);
+  int ao = 0;
+  for (int ray = 0; ray < 24; ++ray) {
+    float x0 = rng.next(), x1 = rng.next(), x2 = rng.next();
+    V3 rayDir = frameApply(tbn, normalize3(mk3(2.0f * x0 - 1.0f, 2.0f * x1 - 1.0f, x2)));
+    V2 uvEnd = projectUv(P, worldPos + rayDir * 0.5f);
+    V3 perpRef = normalize3(cross3(cross3(rayDir, normal), rayDir));
+    // state of the previous step: value, whether it is the exact fp32 value, its decision margin
+    V3 prevPos = worldPos;
+    float prevProjection = 0.0f, prevTol = 0.0f; // |exact - prevProjection| <= prevTol; also the position tolerance
+    bool prevExact = true;
+    float pu = u0, pv = v0;
+    for (int i = 1; i < 12; ++i) {
+      float t = (float)i / 12.0f;
+      float cu = mixf(u0, uvEnd.x, t), cv = mixf(v0, uvEnd.y, t);
+      if (outside01(cu, cv)) break;
+      const ProxyTap tap = proxyTap(P, cu, cv);
+      V3 curPos = tap.pos;
+      float curProjection = dot3(curPos - worldPos, perpRef);
+      const float mag = posMag + (fabsf(curPos.x) + fabsf(curPos.y) + fabsf(curPos.z));
+      float curTol = fmaf(tap.err, kSqrt3Up, fmaf(mag, kRoundSlop, 1e-15f)); // inf / NaN when the record is flagged
+      bool curExact = false;
+      bool flip;
+      if (i == 1) {
+        flip = false; // prevProjection is exactly 0: the product is +-0 (or NaN), never < 0
+      } else {
+        const bool curSure = fabsf(curProjection) > 2.0f * curTol;
+        const bool prevSure = fabsf(prevProjection) > 2.0f * prevTol && fabsf(prevProjection) > 1e-15f;
+        if (curSure && prevSure) {
+          flip = (curProjection < 0.0f) != (prevProjection < 0.0f);
+        } else {
+          if (!curSure) {
+            ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
+            curPos = e.pos; curProjection = e.projection; curTol = 0.0f; curExact = true;
+          }
+          if (!prevExact && !(prevSure && curExact && fabsf(curProjection) > 1e-15f)) {
+            ExactTap e = exactTap(P, pu, pv, worldPos, perpRef);
+            prevPos = e.pos; prevProjection = e.projection; prevTol = 0.0f; prevExact = true;
+          }
+          if (!curExact && !(curSure && fabsf(prevProjection) > 1e-15f)) {
+            ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
+            curPos = e.pos; curProjection = e.projection; curTol = 0.0f; curExact = true;
+          }
+          flip = __fmul_rn(curProjection, prevProjection) < 0.0f;
+        }
+      }
+      if (flip) {
+        // worldStep = length(currentPos - prevPos) <= 2.0
+        float worldStep = length3(curPos - prevPos);
+        const float tol = curTol + prevTol; // each covers sqrt(3) * E + rounding slop
+        bool near;
+        if (worldStep + tol <= 2.0f) near = true;
+        else if (worldStep - tol > 2.0f) near = false;
+        else {
+          if (!curExact) { ExactTap e = exactTap(P, cu, cv, worldPos, perpRef); curPos = e.pos; curProjection = e.projection; curTol = 0.0f; curExact = true; }
+          if (!prevExact) { ExactTap e = exactTap(P, pu, pv, worldPos, perpRef); prevPos = e.pos; }
+          near = length3(curPos - prevPos) <= 2.0f;
+        }
+        if (near && facesRay(P, cu, cv, rayDir)) {
+          ao += 1;
+          break;
+        }
+      }
+      prevPos = curPos; prevProjection = curProjection; prevTol = curTol; prevExact = curExact;
+      pu = cu; pv = cv;
+    }
+  }
+  return ao;
+}
+
 __global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ FrameParams P) {
   const int x = blockIdx.x * 16 + (threadIdx.x & 15);
   const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
@@ -271,7 +475,7 @@ __global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ Frame
   if (position.w != 0.0f) {
     const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
     V3 normal = normalize3(xyz(FmtRGBA16F::load(P.normal, x, y)));
-    count = (uint8_t)ssaoCount(P, x, y, u, v, xyz(position), normal);
+    count = (uint8_t)ssaoCountFiltered(P, x, y, u, v, xyz(position), normal);
   }
   rowPtrW<uint8_t>(P.ao, y)[x] = count;
 }
@@ -320,6 +524,10 @@ static inline dim3 tileGrid(int w, int h) { return dim3((unsigned)((w + 15) / 16
 void launch_ssr_capture(const FrameParams& P, cudaStream_t s) { ssr_capture_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
 void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s) { glossy_convolve_kernel<<<tileGrid(C.dst.w, C.dst.h), 256, 0, s>>>(C); }
 void launch_ssao(const FrameParams& P, cudaStream_t s) { ssao_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
+void launch_ssao_exact(const FrameParams& P, cudaStream_t s) { ssao_exact_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
+void launch_ssao_quads(const FrameParams& P, cudaStream_t s) {
+  ssao_quads_kernel<<<dim3((unsigned)((P.W + 1 + 31) / 32), (unsigned)((P.H + 1 + 7) / 8)), 256, 0, s>>>(P);
+}
 void launch_deferred_shade(const FrameParams& P, cudaStream_t s) { deferred_shade_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
 
 } // namespace ALTHEA_NS

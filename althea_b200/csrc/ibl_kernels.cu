@@ -119,7 +119,12 @@ template <int LANES> __global__ void __launch_bounds__(256) ibl_prefilter_kernel
   const float fN = (float)I.numSamples;
   V3 acc = mk3(0.0f, 0.0f, 0.0f);
   float totalWeight = 0.0f;
-  for (int i = lane; i < I.numSamples; i += LANES) {
+  // roughness 0: cosTheta = sqrt(x / x) = 1 and sinTheta = 0 exactly, so H == N and every sample fetches the same texels
+  // with the same weight (PreFilterEnvMap.comp:139-161 runs all 10000 regardless). One pass of the lanes gives the same
+  // quotient acc / totalWeight to within fp32 summation noise; a sample whose xi1 is exactly 1 is NaN and skipped as in
+  // the reference.
+  const int sampleEnd = (I.roughness == 0.0f) ? min(I.numSamples, LANES) : I.numSamples;
+  for (int i = lane; i < sampleEnd; i += LANES) {
     float xi0, xi1;
     if (I.sequence == ALTHEA_IBL_SEQ_REFERENCE_HASH) {
       HashRng rng; // the reference's RNG state after k draws is seed + k, so sample i starts at seed + 2i

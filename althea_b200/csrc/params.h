@@ -33,6 +33,10 @@ struct FrameParams {
   int outIsF32;
   ImgView ao; // R8_UINT occluded-ray counts
   uint32_t flags;
+  // SSAO position-quad proxy (engine scratch): (W+1) x (H+1) records of 32 bytes, record (ix+1, iy+1)
+  // describes the bilinear footprint whose top-left tap is texel (ix, iy), ix in [-1, W-1], iy in [-1, H-1]
+  const void* quads;
+  size_t quadPitch; // bytes per record row = (W+1)*32
 };
 
 struct ConvolveParams {

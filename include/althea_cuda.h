@@ -69,6 +69,7 @@ const char* althea_cuda_last_error(const althea_cuda_ctx* ctx); /* ctx may be NU
 int althea_cuda_abi_version(void);
 
 #define ALTHEA_CTX_PARITY_MATH 1u /* run the -fmad=false build of the per-frame kernels (bit-matches the CPU oracle's IEEE op order) */
+#define ALTHEA_CTX_SSAO_EXACT_TAPS 2u /* SSAO marches the fp32 position texels directly (4 loads per tap) instead of the packed proxy with exact re-evaluation; same counts, slower: A/B switch for tests and profiling */
 int althea_cuda_set_flags(althea_cuda_ctx* ctx, uint32_t flags);
 
 /* Per-kernel device timing (CUDA events on the launching stream around every kernel this library launches). */

@@ -264,6 +264,42 @@ def test_error_behaviour(ctx_fast):
     assert rc == -1 and b"not device memory" in lib.althea_cuda_last_error(p)
 
 
+def _ao_both_ways(ctx, gf, fd, parity):
+    """SSAO counts from the packed-proxy kernel (default) and from the straight fp32-texel kernel, same context."""
+    from althea_b200 import _capi
+    base = _capi.CTX_PARITY_MATH if parity else 0
+    out = []
+    for flags in (base, base | _capi.CTX_SSAO_EXACT_TAPS):
+        ctx.set_flags(flags)
+        gf.deferred.aoCounts.tensor.zero_()
+        gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+        out.append(gf.ao_counts().copy())
+    ctx.set_flags(base)
+    return out
+
+
+@pytest.mark.parametrize("which", ["parity", "fast"])
+def test_ssao_proxy_equals_exact_taps_on_hostile_positions(request, which):
+    """The filtered march must take the exact path whenever its error bound cannot decide: positions with NaN / inf / huge
+    magnitudes, fp16-overflowing neighbour deltas, denormals and exact zeros must give the same counts as the fp32-texel march."""
+    ctx = _ctx(request, which)
+    fd = FrameData("scene", 192, 108, n_lights=0)
+    rng = np.random.default_rng(7)
+    pos = fd.position
+    H, W = pos.shape[:2]
+    n = 400
+    ys, xs = rng.integers(0, H, n), rng.integers(0, W, n)
+    vals = [np.nan, np.inf, -np.inf, 1e30, -3e38, 7e4, -7e4, 1e-40, 0.0, 65504.0 * 1.5]
+    for k in range(n):
+        pos[ys[k], xs[k], rng.integers(0, 3)] = vals[k % len(vals)]
+    pos[60:70, 80:120, :3] *= 4000.0          # a far slab: neighbour deltas overflow fp16
+    pos[20:24, 10:60, :3] = pos[20, 10, :3]   # a run of identical texels: projections that are exactly equal / zero
+    gf = GpuFrame(ctx, fd)
+    a, b = _ao_both_ways(ctx, gf, fd, which == "parity")
+    assert np.array_equal(a, b)
+    assert (b[b < 255] > 0).mean() > 0.02
+
+
 # ---- size-independent properties at the full 4K size (BASELINE configs C3/C5) -------------------------------------------
 def test_properties_at_4k(ctx_fast):
     import torch
@@ -290,6 +326,10 @@ def test_properties_at_4k(ctx_fast):
     r1, c1, a1 = run()
     r2, c2, a2 = run()
     assert torch.equal(r1, r2) and torch.equal(c1, c2) and torch.equal(a1, a2)  # deterministic / idempotent
+    ctx_fast.set_flags(_capi.CTX_SSAO_EXACT_TAPS)  # the packed-proxy march and the fp32-texel march agree bit for bit
+    r3, c3, a3 = run()
+    ctx_fast.set_flags(0)
+    assert torch.equal(a1, a3) and torch.equal(c1, c3)
     ao = a1.view(H, W)
     empty = gbd.position[..., 3] == 0
     assert bool((ao[empty] == 255).all()) and bool((ao[~empty] <= 24).all())
