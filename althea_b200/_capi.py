@@ -102,7 +102,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    """The in-tree library; ALTHEA_CUDA_LIB names an A/B variant built by build.build_variant (kernel tuning only)."""
+    return os.environ.get("ALTHEA_CUDA_LIB") or _build.LIB_PATH
 
 
 def load() -> C.CDLL:

@@ -57,6 +57,28 @@ def is_stale() -> bool:
     return open(stamp).read().strip() != _sources_digest()
 
 
+def build_variant(name: str, extra_flags) -> str:
+    """A/B builds for kernel tuning: lib/libalthea_cuda_<name>.so with extra -D flags; selected at run time with the
+    ALTHEA_CUDA_LIB environment variable (see _capi.library_path). Not part of the default build."""
+    nvcc = _nvcc()
+    obj_dir = os.path.join(OBJ_DIR, name)
+    os.makedirs(obj_dir, exist_ok=True)
+    os.makedirs(LIB_DIR, exist_ok=True)
+    objs, procs = [], []
+    for src, obj, extra in UNITS:
+        out = os.path.join(obj_dir, obj)
+        cmd = [nvcc, *ARCH, *COMMON, *extra, *extra_flags, "-c", os.path.join(CSRC, src), "-o", out]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(out)
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + out)
+    lib = os.path.join(LIB_DIR, "libalthea_cuda_%s.so" % name)
+    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", lib, *objs, "-cudart", "static"])
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH

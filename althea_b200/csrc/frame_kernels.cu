@@ -242,6 +242,21 @@ __global__ void __launch_bounds__(256) glossy_convolve_kernel(const __grid_const
 //   (storage error E + fp32 rounding slop), the decision is the one the exact arithmetic takes. Otherwise that tap is
 //   re-evaluated from the fp32 texels with the restatement's own expression. Counts are therefore identical to
 //   ssao_exact_kernel's, bit for bit, in both builds (checked at 4K in tests/).
+// march parameter t = i / 12 and 1 - t (SSAO.glsl:47-48), folded at compile time (correctly rounded, as at run time)
+__constant__ float kSsaoT[12] = {0.0f / 12.0f, 1.0f / 12.0f, 2.0f / 12.0f, 3.0f / 12.0f, 4.0f / 12.0f, 5.0f / 12.0f,
+                                 6.0f / 12.0f, 7.0f / 12.0f, 8.0f / 12.0f, 9.0f / 12.0f, 10.0f / 12.0f, 11.0f / 12.0f};
+__constant__ float kSsaoOneMinusT[12] = {1.0f - 0.0f / 12.0f, 1.0f - 1.0f / 12.0f, 1.0f - 2.0f / 12.0f, 1.0f - 3.0f / 12.0f,
+                                         1.0f - 4.0f / 12.0f, 1.0f - 5.0f / 12.0f, 1.0f - 6.0f / 12.0f, 1.0f - 7.0f / 12.0f,
+                                         1.0f - 8.0f / 12.0f, 1.0f - 9.0f / 12.0f, 1.0f - 10.0f / 12.0f, 1.0f - 11.0f / 12.0f};
+// == mixf(a, b, i / 12.0f); the contraction is spelled out so that both SSAO kernels of a build march the same coordinates
+ADEV float marchCoord(float a, float b, int i) {
+#ifdef ALTHEA_PARITY
+  return __fadd_rn(__fmul_rn(a, kSsaoOneMinusT[i]), __fmul_rn(b, kSsaoT[i]));
+#else
+  return fmaf(b, kSsaoT[i], __fmul_rn(a, kSsaoOneMinusT[i]));
+#endif
+}
+
 ADEV int ssaoCountExact(const FrameParams& P, int px, int py, float u0, float v0, V3 worldPos, V3 normal) {
   HashRng rng;
   rng.sx = (uint32_t)px;
@@ -256,8 +271,7 @@ ADEV int ssaoCountExact(const FrameParams& P, int px, int py, float u0, float v0
     V3 prevPos = worldPos;
     float prevProjection = 0.0f; // i == 0 taps the pixel's own texel: currentProjection == 0 exactly
     for (int i = 1; i < 12; ++i) {
-      float t = (float)i / 12.0f;
-      float cu = mixf(u0, uvEnd.x, t), cv = mixf(v0, uvEnd.y, t);
+      float cu = marchCoord(u0, uvEnd.x, i), cv = marchCoord(v0, uvEnd.y, i);
       if (outside01(cu, cv)) break;
       V3 currentPos = xyz(bilinear<FmtRGBA32F, AddrClamp>(P.position, cu, cv));
       float currentProjection = dot3(currentPos - worldPos, perpRef);
@@ -307,29 +321,38 @@ __global__ void __launch_bounds__(256) ssao_quads_kernel(const __grid_constant__
   const int j0 = AddrClamp::wrap(qy - 1, P.H), j1 = AddrClamp::wrap(qy, P.H);
   const V4 p00 = FmtRGBA32F::load(P.position, i0, j0), p10 = FmtRGBA32F::load(P.position, i1, j0);
   const V4 p01 = FmtRGBA32F::load(P.position, i0, j1), p11 = FmtRGBA32F::load(P.position, i1, j1);
+  // bilinear(fx, fy) = p00 + A fx + B fy + C fx fy with A = p10 - p00, B = p01 - p00, C = (p11 - p10) - (p01 - p00)
   const float b[3] = {p00.x, p00.y, p00.z};
-  const float t[9] = {p10.x, p10.y, p10.z, p01.x, p01.y, p01.z, p11.x, p11.y, p11.z};
-  __half h[9];
+  const float t10[3] = {p10.x, p10.y, p10.z}, t01[3] = {p01.x, p01.y, p01.z}, t11[3] = {p11.x, p11.y, p11.z};
+  __half hA[3], hB[3], hC[3];
   float E = 0.0f;
-  bool finite = isfinite(b[0]) && isfinite(b[1]) && isfinite(b[2]);
+  bool finite = true;
+  constexpr float kUlp = 6.0e-8f; // 2^-24 rounded up: |fl(a - b) - (a - b)| <= 2^-24 |fl(a - b)|
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const float D = __fsub_rn(t[k], b[k % 3]); // |D - (t - b)| <= 2^-24 |D|
-    h[k] = __float2half_rn(D);
-    const float back = __half2float(h[k]);
-    finite = finite && isfinite(t[k]) && isfinite(back);
-    E = fmaxf(E, __fadd_ru(fabsf(__fsub_rn(back, D)), __fmul_ru(fabsf(D), 9.6e-7f))); // back - D is exact in fp32 (Sterbenz); 2^-20 |D| covers fp32 lerp rounding on large texels
+  for (int c = 0; c < 3; ++c) {
+    const float A = __fsub_rn(t10[c], b[c]), B = __fsub_rn(t01[c], b[c]);
+    const float U = __fsub_rn(t11[c], t10[c]);
+    const float C = __fsub_rn(U, B);
+    hA[c] = __float2half_rn(A); hB[c] = __float2half_rn(B); hC[c] = __float2half_rn(C);
+    const float bA = __half2float(hA[c]), bB = __half2float(hB[c]), bC = __half2float(hC[c]);
+    finite = finite && isfinite(b[c]) && isfinite(t10[c]) && isfinite(t01[c]) && isfinite(t11[c]) && isfinite(bA) && isfinite(bB) && isfinite(bC);
+    // storage error of each coefficient (the half -> float differences are exact in fp32) + rounding of the fp32
+    // differences themselves; fx, fy, fx*fy <= 1, so the sum bounds the error anywhere in the footprint
+    float e = __fadd_ru(__fadd_ru(fabsf(__fsub_rn(bA, A)), fabsf(__fsub_rn(bB, B))), fabsf(__fsub_rn(bC, C)));
+    const float mags = __fadd_ru(__fadd_ru(fabsf(A), __fmul_ru(2.0f, fabsf(B))), __fadd_ru(fabsf(U), fabsf(C)));
+    e = __fadd_ru(e, __fmul_ru(mags, kUlp));
+    // the restatement's own fp32 lerps round relative to the texel MAGNITUDES; covered here for texels much larger than the
+    // interpolated value (the tap-side slop scales with the interpolated value only)
+    e = __fadd_ru(e, __fmul_ru(mags, 9.6e-7f));
+    E = fmaxf(E, e);
   }
   E = __fadd_ru(__fmul_ru(E, 1.0001f), 1e-30f);
   const __half Eh = finite ? __float2half_ru(E) : __ushort_as_half((unsigned short)0x7c00u); // +inf => always re-evaluate exactly
-  QuadRecord r;
-  r.w[0] = __float_as_uint(b[0]); r.w[1] = __float_as_uint(b[1]); r.w[2] = __float_as_uint(b[2]);
-  r.w[3] = packHalf2(h[0], h[1]); r.w[4] = packHalf2(h[2], h[3]); r.w[5] = packHalf2(h[4], h[5]);
-  r.w[6] = packHalf2(h[6], h[7]); r.w[7] = packHalf2(h[8], Eh);
+  // words: base.xyz | (A.x, A.y) | (A.z, B.x) | (B.y, B.z) | (C.x, C.y) | (C.z, E)
   QuadRecord* row = reinterpret_cast<QuadRecord*>(const_cast<char*>(static_cast<const char*>(P.quads)) + (size_t)qy * P.quadPitch);
   uint4* dst = reinterpret_cast<uint4*>(row + qx);
-  dst[0] = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
-  dst[1] = make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]);
+  dst[0] = make_uint4(__float_as_uint(b[0]), __float_as_uint(b[1]), __float_as_uint(b[2]), packHalf2(hA[0], hA[1]));
+  dst[1] = make_uint4(packHalf2(hA[2], hB[0]), packHalf2(hB[1], hB[2]), packHalf2(hC[0], hC[1]), packHalf2(hC[2], Eh));
 }
 
 ADEV QuadRecord loadQuad(const void* p) { // one 256-bit load: LDG.E.ENL2.256 on sm_100a
@@ -344,31 +367,21 @@ struct ProxyTap {
   V3 pos;    // interpolated position, within `err` per component of the real-arithmetic bilinear value
   float err; // storage error bound E of the record
 };
+// (u, v) has passed outside01: x is in [-0.5, W - 0.5], so floor(x) + 1 is a valid record column without clamping. A NaN
+// coordinate converts to column 1 and yields NaN weights, hence a NaN position, which the caller re-evaluates exactly.
 ADEV ProxyTap proxyTap(const FrameParams& P, float u, float v) {
-  // same coordinate arithmetic as the exact tap (rule A1): the footprint and the weights are identical, only the texel
-  // values are approximate
-  float x = __fsub_rn(__fmul_rn(u, (float)P.W), 0.5f), y = __fsub_rn(__fmul_rn(v, (float)P.H), 0.5f);
-  if (!(x == x)) x = 0.0f;
-  if (!(y == y)) y = 0.0f;
+  // same coordinate arithmetic as the exact tap (rule A1): identical footprint and weights, approximate texel values
+  const float x = __fsub_rn(__fmul_rn(u, (float)P.W), 0.5f), y = __fsub_rn(__fmul_rn(v, (float)P.H), 0.5f);
   const float fx0 = floorf(x), fy0 = floorf(y);
   const float fx = x - fx0, fy = y - fy0;
-  const int qx = min(max((int)fx0, -1), P.W - 1) + 1, qy = min(max((int)fy0, -1), P.H - 1) + 1;
+  const int qx = (int)fx0 + 1, qy = (int)fy0 + 1;
   const QuadRecord r = loadQuad(static_cast<const char*>(P.quads) + (size_t)qy * P.quadPitch + (size_t)qx * sizeof(QuadRecord));
   const float2 a = unpackHalf2(r.w[3]), b = unpackHalf2(r.w[4]), c = unpackHalf2(r.w[5]), d = unpackHalf2(r.w[6]), e = unpackHalf2(r.w[7]);
-  // deltas: d10 = (a.x, a.y, b.x), d01 = (b.y, c.x, c.y), d11 = (d.x, d.y, e.x); E = e.y
+  // A = (a.x, a.y, b.x), B = (b.y, c.x, c.y), C = (d.x, d.y, e.x), E = e.y
   ProxyTap t;
-  {
-    const float top = a.x * fx, bot = fmaf(d.x - b.y, fx, b.y);
-    t.pos.x = __uint_as_float(r.w[0]) + fmaf(bot - top, fy, top);
-  }
-  {
-    const float top = a.y * fx, bot = fmaf(d.y - c.x, fx, c.x);
-    t.pos.y = __uint_as_float(r.w[1]) + fmaf(bot - top, fy, top);
-  }
-  {
-    const float top = b.x * fx, bot = fmaf(e.x - c.y, fx, c.y);
-    t.pos.z = __uint_as_float(r.w[2]) + fmaf(bot - top, fy, top);
-  }
+  t.pos.x = fmaf(fmaf(d.x, fy, a.x), fx, fmaf(b.y, fy, __uint_as_float(r.w[0])));
+  t.pos.y = fmaf(fmaf(d.y, fy, a.y), fx, fmaf(c.x, fy, __uint_as_float(r.w[1])));
+  t.pos.z = fmaf(fmaf(e.x, fy, b.x), fx, fmaf(c.y, fy, __uint_as_float(r.w[2])));
   t.err = e.y;
   return t;
 }
@@ -387,9 +400,10 @@ __device__ __noinline__ bool facesRay(const FrameParams& P, float cu, float cv, 
 }
 
 constexpr float kSqrt3Up = 1.7320509f;
-// fp32 rounding slop, as a multiple of the largest coordinate magnitude M in play: both the restatement's evaluation and
-// the proxy's are within ~16 ulp(M) of real arithmetic (two lerp levels, a subtraction, a 3-term dot product)
+// fp32 rounding slop, as a multiple of the coordinate magnitude in play: both the restatement's evaluation and the
+// proxy's are within a few ulp of real arithmetic (two lerp levels, a subtraction, a 3-term dot product); 64 ulp is generous
 constexpr float kRoundSlop = 64.0f * 1.1920929e-7f;
+constexpr float kTiny = 1e-15f; // decisions on |value| <= kTiny are always re-evaluated (products must not underflow)
 
 ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float v0, V3 worldPos, V3 normal) {
   HashRng rng;
@@ -403,55 +417,65 @@ ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float
     V3 rayDir = frameApply(tbn, normalize3(mk3(2.0f * x0 - 1.0f, 2.0f * x1 - 1.0f, x2)));
     V2 uvEnd = projectUv(P, worldPos + rayDir * 0.5f);
     V3 perpRef = normalize3(cross3(cross3(rayDir, normal), rayDir));
-    // state of the previous step: value, whether it is the exact fp32 value, its decision margin
+    // previous step: value, tolerance (|exact - value| <= tol, also the position tolerance), whether its sign is decided,
+    // whether it IS the exact fp32 value
     V3 prevPos = worldPos;
-    float prevProjection = 0.0f, prevTol = 0.0f; // |exact - prevProjection| <= prevTol; also the position tolerance
-    bool prevExact = true;
-    float pu = u0, pv = v0;
+    float prevProjection = 0.0f, prevTol = 0.0f;
+    bool prevSure = false, prevExact = true;
+#pragma unroll 1
     for (int i = 1; i < 12; ++i) {
-      float t = (float)i / 12.0f;
-      float cu = mixf(u0, uvEnd.x, t), cv = mixf(v0, uvEnd.y, t);
+      const float cu = marchCoord(u0, uvEnd.x, i), cv = marchCoord(v0, uvEnd.y, i);
       if (outside01(cu, cv)) break;
       const ProxyTap tap = proxyTap(P, cu, cv);
       V3 curPos = tap.pos;
       float curProjection = dot3(curPos - worldPos, perpRef);
       const float mag = posMag + (fabsf(curPos.x) + fabsf(curPos.y) + fabsf(curPos.z));
-      float curTol = fmaf(tap.err, kSqrt3Up, fmaf(mag, kRoundSlop, 1e-15f)); // inf / NaN when the record is flagged
+      float curTol = fmaf(tap.err, kSqrt3Up, fmaf(mag, kRoundSlop, kTiny)); // inf / NaN when the record is flagged
+      bool curSure = fabsf(curProjection) > 2.0f * curTol;
       bool curExact = false;
-      bool flip;
-      if (i == 1) {
-        flip = false; // prevProjection is exactly 0: the product is +-0 (or NaN), never < 0
-      } else {
-        const bool curSure = fabsf(curProjection) > 2.0f * curTol;
-        const bool prevSure = fabsf(prevProjection) > 2.0f * prevTol && fabsf(prevProjection) > 1e-15f;
+      bool flip = false; // i == 1: prevProjection is exactly 0, the product is +-0 (or NaN), never < 0
+      if (i > 1) {
         if (curSure && prevSure) {
           flip = (curProjection < 0.0f) != (prevProjection < 0.0f);
         } else {
+          const float pu = marchCoord(u0, uvEnd.x, i - 1), pv = marchCoord(v0, uvEnd.y, i - 1);
           if (!curSure) {
             ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
             curPos = e.pos; curProjection = e.projection; curTol = 0.0f; curExact = true;
+            curSure = fabsf(curProjection) > kTiny;
           }
-          if (!prevExact && !(prevSure && curExact && fabsf(curProjection) > 1e-15f)) {
+          if (!prevSure && !prevExact) {
+            ExactTap e = exactTap(P, pu, pv, worldPos, perpRef);
+            prevPos = e.pos; prevProjection = e.projection; prevTol = 0.0f; prevExact = true;
+            prevSure = fabsf(prevProjection) > kTiny;
+          }
+          // a value at most kTiny in magnitude can push the fp32 product into underflow: then both factors must be exact
+          if (!curSure && !prevExact) {
             ExactTap e = exactTap(P, pu, pv, worldPos, perpRef);
             prevPos = e.pos; prevProjection = e.projection; prevTol = 0.0f; prevExact = true;
           }
-          if (!curExact && !(curSure && fabsf(prevProjection) > 1e-15f)) {
+          if (!prevSure && !curExact) {
             ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
             curPos = e.pos; curProjection = e.projection; curTol = 0.0f; curExact = true;
+            curSure = fabsf(curProjection) > kTiny;
           }
           flip = __fmul_rn(curProjection, prevProjection) < 0.0f;
         }
       }
       if (flip) {
         // worldStep = length(currentPos - prevPos) <= 2.0
-        float worldStep = length3(curPos - prevPos);
+        const float worldStep = length3(curPos - prevPos);
         const float tol = curTol + prevTol; // each covers sqrt(3) * E + rounding slop
         bool near;
         if (worldStep + tol <= 2.0f) near = true;
         else if (worldStep - tol > 2.0f) near = false;
         else {
-          if (!curExact) { ExactTap e = exactTap(P, cu, cv, worldPos, perpRef); curPos = e.pos; curProjection = e.projection; curTol = 0.0f; curExact = true; }
-          if (!prevExact) { ExactTap e = exactTap(P, pu, pv, worldPos, perpRef); prevPos = e.pos; }
+          if (!curExact) {
+            ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
+            curPos = e.pos; curProjection = e.projection; curTol = 0.0f; curExact = true;
+            curSure = fabsf(curProjection) > kTiny;
+          }
+          if (!prevExact) prevPos = exactTap(P, marchCoord(u0, uvEnd.x, i - 1), marchCoord(v0, uvEnd.y, i - 1), worldPos, perpRef).pos;
           near = length3(curPos - prevPos) <= 2.0f;
         }
         if (near && facesRay(P, cu, cv, rayDir)) {
@@ -459,14 +483,16 @@ ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float
           break;
         }
       }
-      prevPos = curPos; prevProjection = curProjection; prevTol = curTol; prevExact = curExact;
-      pu = cu; pv = cv;
+      prevPos = curPos; prevProjection = curProjection; prevTol = curTol; prevSure = curSure; prevExact = curExact;
     }
   }
   return ao;
 }
 
-__global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ FrameParams P) {
+#ifndef ALTHEA_SSAO_MIN_BLOCKS
+#define ALTHEA_SSAO_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, ALTHEA_SSAO_MIN_BLOCKS) ssao_kernel(const __grid_constant__ FrameParams P) {
   const int x = blockIdx.x * 16 + (threadIdx.x & 15);
   const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
   if (x >= P.W || y >= P.H) return;

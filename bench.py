@@ -88,7 +88,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_rank_inputs(ctx, rank: int, views: int, device: str):
+def build_rank_inputs(ctx, rank: int, views: int, device: str, quick_ibl: bool = False):
     """All device-resident inputs of this rank: IBL set (built with our own precompute kernels), lights + shadow cubes, and
     `views` G-buffers. Returns the objects plus the measured IBL precompute timings."""
     import torch
@@ -105,7 +105,10 @@ def build_rank_inputs(ctx, rank: int, views: int, device: str):
     irr_small = ctx.new_image(F32, 512, 256)
     ctx.enable_timing(True)
     ctx.reset_timings()
-    engine.ImageBasedLighting.precomputeResources(ctx, chain, irr_small, pre)
+    if quick_ibl:  # tools/stage_bench.py: per-frame kernel tuning does not need converged IBL maps
+        engine.ImageBasedLighting.precomputeResources(ctx, chain, irr_small, pre, prefilter_samples=64, theta_samples=16)
+    else:
+        engine.ImageBasedLighting.precomputeResources(ctx, chain, irr_small, pre)
     ctx.synchronize()
     ibl_t = ctx.timings()
     ctx.enable_timing(False)
