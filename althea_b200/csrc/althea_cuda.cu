@@ -233,6 +233,25 @@ int fillFrameParams(althea_cuda_ctx* ctx, const althea_global_uniforms* u, const
   memset(P, 0, sizeof *P);
   P->g = *u;
   matmul44(u->projection, u->view, P->projView);
+  {
+    const float* ip = u->inverseProjection;
+    const float* iv = u->inverseView;
+    double dx[3], dy[3], dc[3]; // (inverseProjection * (x, y, 2, 1)).xyz = dx x + dy y + dc
+    for (int r = 0; r < 3; ++r) { dx[r] = ip[0 + r]; dy[r] = ip[4 + r]; dc[r] = 2.0 * ip[8 + r] + ip[12 + r]; }
+    double Wx[3], Wy[3], Wc[3];
+    for (int r = 0; r < 3; ++r) {
+      Wx[r] = iv[0 + r] * dx[0] + iv[4 + r] * dx[1] + iv[8 + r] * dx[2];
+      Wy[r] = iv[0 + r] * dy[0] + iv[4 + r] * dy[1] + iv[8 + r] * dy[2];
+      Wc[r] = iv[0 + r] * dc[0] + iv[4 + r] * dc[1] + iv[8 + r] * dc[2];
+    }
+    double s0 = 0, su = 0, sv = 0; // x = 2u - 1, y = 2v - 1
+    for (int r = 0; r < 3; ++r) {
+      const double w0 = Wc[r] - Wx[r] - Wy[r], wu = 2.0 * Wx[r], wv = 2.0 * Wy[r];
+      P->ssrW0[r] = (float)w0; P->ssrWu[r] = (float)wu; P->ssrWv[r] = (float)wv;
+      s0 += w0 * iv[8 + r]; su += wu * iv[8 + r]; sv += wv * iv[8 + r];
+    }
+    P->ssrS[0] = (float)s0; P->ssrS[1] = (float)su; P->ssrS[2] = (float)sv;
+  }
   Resource *depth, *position, *normal, *albedo, *mro, *env, *pre, *irr, *lut, *refl, *sh;
   int rc;
   if ((rc = getImage(ctx, gb->normal, ALTHEA_FORMAT_R16G16B16A16_SFLOAT, "gbuffer.normal", &normal))) return rc;

@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(256) ssr_capture_kernel(const __grid_constant_
     const V3 perpRef = normalize3(cross3(cross3(rayDir, normal), rayDir));
     float cu = u, cv = v;
     float prevProjection = 0.0f;
+#ifdef ALTHEA_PARITY
     for (int i = 0; i < 128; ++i) {
       cu += stepX;
       cv += stepY;
@@ -199,6 +200,51 @@ __global__ void __launch_bounds__(256) ssr_capture_kernel(const __grid_constant_
       }
       prevProjection = currentProjection;
     }
+#else
+    // Same march with the per-step algebra folded (the fast build's contract is the 0.1 % mask bar, not op order):
+    //  * reconstructPosition's matrix products are affine in (cu, cv): wd = W0 + Wu cu + Wv cv, dot(wd, zAxis) = S0 + Su cu +
+    //    Sv cv, precomputed on the host (FrameParams::ssr*), and its two divisions become one reciprocal;
+    //  * dir = normalize(pos - worldPos) is never formed: sign(dot(dir, perpRef)) = sign(dot(v, perpRef)) and
+    //    dot(dir, rayDir) > 0.999  <=>  dot(v, rayDir) > 0 and dot(v, rayDir)^2 > 0.999^2 |v|^2.
+    const V3 camMinusPos = mk3(P.g.inverseView[12], P.g.inverseView[13], P.g.inverseView[14]) - worldPos;
+    const V3 W0 = mk3(P.ssrW0[0], P.ssrW0[1], P.ssrW0[2]), Wu = mk3(P.ssrWu[0], P.ssrWu[1], P.ssrWu[2]), Wv = mk3(P.ssrWv[0], P.ssrWv[1], P.ssrWv[2]);
+    const float* depthBase = static_cast<const float*>(P.depth.ptr);
+    const int depthPitch = P.depth.pitch >> 2; // floats per row
+    const float Wf = (float)P.W, Hf = (float)P.H;
+    const int Wm1 = P.W - 1, Hm1 = P.H - 1;
+    for (int i = 0; i < 128; ++i) {
+      cu += stepX;
+      cv += stepY;
+      if (outside01(cu, cv)) break;
+      // bilinear depth tap, CLAMP_TO_EDGE (rule A1/A2); a + t (b - a) lerps
+      const float xf = __fsub_rn(__fmul_rn(cu, Wf), 0.5f), yf = __fsub_rn(__fmul_rn(cv, Hf), 0.5f);
+      const float fx0 = floorf(xf), fy0 = floorf(yf);
+      const float fx = xf - fx0, fy = yf - fy0;
+      const int ix = (int)fx0, iy = (int)fy0;
+      const int i0 = max(ix, 0), i1 = min(ix + 1, Wm1);
+      const float* r0 = depthBase + max(iy, 0) * depthPitch;
+      const float* r1 = depthBase + min(iy + 1, Hm1) * depthPitch;
+      const float t00 = __ldg(r0 + i0), t10 = __ldg(r0 + i1), t01 = __ldg(r1 + i0), t11 = __ldg(r1 + i1);
+      const float top = fmaf(t10 - t00, fx, t00), bot = fmaf(t11 - t01, fx, t01);
+      const float dRaw = fmaf(bot - top, fy, top);
+      // pos - worldPos = (cam - worldPos) + wd * (far near / ((dRaw (far - near) - far) * dot(wd, zAxis)))
+      const float den = fmaf(dRaw, 1000.0f - 0.01f, -1000.0f) * fmaf(P.ssrS[1], cu, fmaf(P.ssrS[2], cv, P.ssrS[0]));
+      const float k = __fdividef(1000.0f * 0.01f, den);
+      const V3 wd = mk3(fmaf(Wu.x, cu, fmaf(Wv.x, cv, W0.x)), fmaf(Wu.y, cu, fmaf(Wv.y, cv, W0.y)), fmaf(Wu.z, cu, fmaf(Wv.z, cv, W0.z)));
+      const V3 vv = mk3(fmaf(wd.x, k, camMinusPos.x), fmaf(wd.y, k, camMinusPos.y), fmaf(wd.z, k, camMinusPos.z));
+      const float len2 = dot3(vv, vv), along = dot3(vv, rayDir);
+      float currentProjection = dot3(vv, perpRef);
+      if (!(len2 > 0.0f)) currentProjection = __int_as_float(0x7fc00000); // normalize(0) is NaN in the restatement
+      if (currentProjection * prevProjection <= 0.0f && along > 0.0f && along * along > (0.999f * 0.999f) * len2 && i > 0) {
+        V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, cu, cv)));
+        if (dot3(currentNormal, rayDir) < 0.0f) {
+          out = environmentLitSample(P, worldPos + vv, cu, cv, rayDir, currentNormal);
+          break;
+        }
+      }
+      prevProjection = currentProjection;
+    }
+#endif
   }
   // blend-on-write over the (0,0,0,0) clear (GraphicsPipeline.cpp:138-154): rgb*a, a
   rowPtrW<uint2>(P.refl.level[0], y)[x] = packHalf4(mk4(out.x * out.w, out.y * out.w, out.z * out.w, out.w));
@@ -375,7 +421,7 @@ ADEV ProxyTap proxyTap(const FrameParams& P, float u, float v) {
   const float fx0 = floorf(x), fy0 = floorf(y);
   const float fx = x - fx0, fy = y - fy0;
   const int qx = (int)fx0 + 1, qy = (int)fy0 + 1;
-  const QuadRecord r = loadQuad(static_cast<const char*>(P.quads) + (size_t)qy * P.quadPitch + (size_t)qx * sizeof(QuadRecord));
+  const QuadRecord r = loadQuad(static_cast<const QuadRecord*>(P.quads) + (uint32_t)(qy * (P.W + 1) + qx)); // < 2^31 records up to 32K x 32K
   const float2 a = unpackHalf2(r.w[3]), b = unpackHalf2(r.w[4]), c = unpackHalf2(r.w[5]), d = unpackHalf2(r.w[6]), e = unpackHalf2(r.w[7]);
   // A = (a.x, a.y, b.x), B = (b.y, c.x, c.y), C = (d.x, d.y, e.x), E = e.y
   ProxyTap t;
@@ -492,9 +538,13 @@ ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float
 #ifndef ALTHEA_SSAO_MIN_BLOCKS
 #define ALTHEA_SSAO_MIN_BLOCKS 4
 #endif
+#ifndef ALTHEA_SSAO_TILE_W
+#define ALTHEA_SSAO_TILE_W 16
+#endif
+constexpr int kSsaoTileW = ALTHEA_SSAO_TILE_W, kSsaoTileH = 256 / ALTHEA_SSAO_TILE_W;
 __global__ void __launch_bounds__(256, ALTHEA_SSAO_MIN_BLOCKS) ssao_kernel(const __grid_constant__ FrameParams P) {
-  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
-  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+  const int x = blockIdx.x * kSsaoTileW + (threadIdx.x % kSsaoTileW);
+  const int y = blockIdx.y * kSsaoTileH + (threadIdx.x / kSsaoTileW);
   if (x >= P.W || y >= P.H) return;
   V4 position = FmtRGBA32F::load(P.position, x, y);
   uint8_t count = 255;
@@ -549,7 +599,9 @@ static inline dim3 tileGrid(int w, int h) { return dim3((unsigned)((w + 15) / 16
 
 void launch_ssr_capture(const FrameParams& P, cudaStream_t s) { ssr_capture_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
 void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s) { glossy_convolve_kernel<<<tileGrid(C.dst.w, C.dst.h), 256, 0, s>>>(C); }
-void launch_ssao(const FrameParams& P, cudaStream_t s) { ssao_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
+void launch_ssao(const FrameParams& P, cudaStream_t s) {
+  ssao_kernel<<<dim3((unsigned)((P.W + kSsaoTileW - 1) / kSsaoTileW), (unsigned)((P.H + kSsaoTileH - 1) / kSsaoTileH)), 256, 0, s>>>(P);
+}
 void launch_ssao_exact(const FrameParams& P, cudaStream_t s) { ssao_exact_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
 void launch_ssao_quads(const FrameParams& P, cudaStream_t s) {
   ssao_quads_kernel<<<dim3((unsigned)((P.W + 1 + 31) / 32), (unsigned)((P.H + 1 + 7) / 8)), 256, 0, s>>>(P);

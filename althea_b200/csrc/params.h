@@ -20,6 +20,9 @@ struct ChainView {
 struct FrameParams {
   althea_global_uniforms g; // byte-for-byte the reference's GlobalUniforms (416 B)
   float projView[16];       // projection * view, computed once on the host in the oracle's op order
+  // fast-build SSR march: mat3(inverseView) * (inverseProjection * (2u-1, 2v-1, 2, 1)).xyz = W0 + Wu u + Wv v, and its dot
+  // product with the camera z axis inverseView[2].xyz = S[0] + S[1] u + S[2] v (Misc/ReconstructPosition.glsl:9-21)
+  float ssrW0[3], ssrWu[3], ssrWv[3], ssrS[3];
   int W, H;
   ImgView depth, position, normal, albedo, mro; // GBufferResources
   ImgView env, irr, lut;                        // IBLResources

@@ -326,10 +326,17 @@ def test_properties_at_4k(ctx_fast):
     r1, c1, a1 = run()
     r2, c2, a2 = run()
     assert torch.equal(r1, r2) and torch.equal(c1, c2) and torch.equal(a1, a2)  # deterministic / idempotent
-    ctx_fast.set_flags(_capi.CTX_SSAO_EXACT_TAPS)  # the packed-proxy march and the fp32-texel march agree bit for bit
-    r3, c3, a3 = run()
-    ctx_fast.set_flags(0)
-    assert torch.equal(a1, a3) and torch.equal(c1, c3)
+    # the packed-proxy march against the fp32-texel march. With -fmad=false every decision is the same IEEE
+    # operation in both kernels: bit for bit. In the fast build the compiler contracts the two kernels' inlined copies of
+    # the tap arithmetic separately, so a projection within an ulp of zero can flip: at most a handful of pixels in 8.3 M.
+    for flags, bar in ((_capi.CTX_PARITY_MATH, 0), (0, 8)):
+        ctx_fast.set_flags(flags)
+        _, _, ap = run()
+        ctx_fast.set_flags(flags | _capi.CTX_SSAO_EXACT_TAPS)
+        _, _, ae = run()
+        ctx_fast.set_flags(0)
+        assert int((ap != ae).sum()) <= bar, "proxy vs fp32-texel SSAO counts differ on %d pixels (flags %d)" % (int((ap != ae).sum()), flags)
+        assert int((ap.int() - ae.int()).abs().max()) <= 1
     ao = a1.view(H, W)
     empty = gbd.position[..., 3] == 0
     assert bool((ao[empty] == 255).all()) and bool((ao[~empty] <= 24).all())
