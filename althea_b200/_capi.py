@@ -67,6 +67,8 @@ SYMBOLS = {
     "althea_cuda_destroy": (None, [C.c_void_p]),
     "althea_cuda_last_error": (C.c_char_p, [C.c_void_p]),
     "althea_cuda_set_flags": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "althea_cuda_set_scissor_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "althea_cuda_band_rows": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "althea_cuda_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "althea_cuda_get_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_int]),
     "althea_cuda_reset_timings": (C.c_int, [C.c_void_p]),

@@ -1,0 +1,111 @@
+"""Row-band split of ONE large frame over the GPUs of a node (BASELINE configs[3]: a 7680x4320 frame over 2/4/8 B200).
+
+SSR rays and SSAO taps may read any screen location, so INPUTS are whole-frame on every rank (the producing rank's G-buffer
+is replicated with a broadcast over NCCL/NVLink); OUTPUTS are per pixel, so each rank shades a contiguous band of rows
+(`Context.set_scissor_rows`, the C ABI's althea_cuda_set_scissor_rows) and the bands are assembled with an all-gather. The
+only stage with cross-band dependence is the glossy convolve: each rank recomputes the halo of reflection rows its band's
+mips need (althea_cuda_band_rows) instead of exchanging halos, so a band is bit-identical to the same rows of a single-GPU
+frame. One process per GPU; torch.distributed is the plumbing (backend "nccl" on the GPUs, "gloo" in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+from . import _capi
+
+
+def band_height(height: int, world: int) -> int:
+    """Rows per band: equal bands of ceil(H / world) rows (the last ranks' bands may be shorter or empty)."""
+    return (height + world - 1) // world
+
+
+def split_rows(height: int, world: int) -> List[Tuple[int, int]]:
+    """[(y0, y1)] per rank, contiguous, covering [0, height)."""
+    bh = band_height(height, world)
+    return [(min(r * bh, height), min((r + 1) * bh, height)) for r in range(world)]
+
+
+def padded_rows(height: int, world: int) -> int:
+    """Rows of the gather buffer: every rank contributes band_height rows so the all-gather is one equal-sized collective."""
+    return band_height(height, world) * world
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def broadcast_tensors(tensors: Sequence, src: int = 0, group=None, async_op: bool = False):
+    """Replicates the producing rank's G-buffer attachments (or the IBL tables at init) on every rank."""
+    dist = _dist()
+    works = [dist.broadcast(t, src=src, group=group, async_op=async_op) for t in tensors]
+    return works if async_op else None
+
+
+def allgather_rows(buf, row_bytes: int, band_rows: int, group=None):
+    """In-place all-gather of row bands: `buf` is a flat uint8 tensor of world * band_rows * row_bytes bytes whose rank-th
+    chunk has been written by this rank; on return every chunk is filled in."""
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = band_rows * row_bytes
+    flat = buf.view(-1)[: world * n]
+    mine = flat[rank * n:(rank + 1) * n]
+    if flat.is_cuda:
+        dist.all_gather_into_tensor(flat, mine, group=group)  # NCCL in place: input is the rank-th slice of the output
+    else:
+        chunks = [flat[r * n:(r + 1) * n] for r in range(world)]
+        dist.all_gather(chunks, mine.clone(), group=group)
+
+
+class BandedFrame:
+    """One frame of W x H pixels rendered in row bands by the ranks of `group`.
+
+    Usage (every rank):
+        bf = BandedFrame(ctx, W, H)                 # allocates the padded colour target and this rank's reflection buffer
+        bf.broadcast_gbuffer(gbuffer, src=0)        # NCCL broadcast of the 5 attachments
+        bf.render(uniforms, gbuffer, ibl, lights)   # ssr_capture -> glossy_convolve -> ssao -> deferred_shade on the band
+        bf.gather()                                 # NCCL all-gather of the bands; bf.color_rows() is then the full frame
+    """
+
+    def __init__(self, ctx, width: int, height: int, out_format: int = _capi.FORMAT_R16G16B16A16_SFLOAT, group=None,
+                 rank: Optional[int] = None, world: Optional[int] = None):
+        import torch
+
+        from . import engine
+        dist = _dist()
+        self.ctx, self.W, self.H, self.group, self.format = ctx, width, height, group, out_format
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        self.band = band_height(height, self.world)
+        self.y0, self.y1 = split_rows(height, self.world)[self.rank]
+        self.row_bytes = width * _capi.BYTES_PER_TEXEL[out_format]
+        self._color_t = torch.zeros(padded_rows(height, self.world) * self.row_bytes, dtype=torch.uint8, device="cuda:%d" % ctx.device)
+        self.deferred = engine.DeferredPass.__new__(engine.DeferredPass)
+        self.deferred.ctx = ctx
+        self.deferred.colorTarget = ctx.wrap_tensor(self._color_t, out_format, width, height)
+        self.deferred.aoCounts = ctx.new_image(_capi.FORMAT_R8_UINT, width, height)
+        self.ssr = engine.ScreenSpaceReflection(ctx, width, height)
+
+    def broadcast_gbuffer(self, gbuffer, src: int = 0):
+        if self.world > 1:
+            broadcast_tensors([gbuffer.position.tensor, gbuffer.depth.tensor, gbuffer.normal.tensor, gbuffer.albedo.tensor, gbuffer.mro.tensor],
+                              src=src, group=self.group)
+
+    def render(self, uniforms, gbuffer, ibl, lights, flags: int = _capi.SHADE_SKIP_TONEMAP, stream: int = 0):
+        if self.y1 <= self.y0:
+            return
+        self.ctx.set_scissor_rows(self.y0, self.y1)
+        try:
+            self.ssr.captureReflection(uniforms, gbuffer, ibl, lights, stream)
+            self.ssr.convolveReflectionBuffer(stream)
+            self.deferred.draw(uniforms, gbuffer, ibl, lights, self.ssr, flags, stream)
+        finally:
+            self.ctx.set_scissor_rows(0, 0)
+
+    def gather(self):
+        if self.world > 1:
+            allgather_rows(self._color_t, self.row_bytes, self.band, self.group)
+
+    def color_rows(self):
+        """(H, W * bytes_per_texel) uint8 view of the assembled colour target."""
+        return self._color_t[: self.H * self.row_bytes].view(self.H, self.row_bytes)

@@ -2,6 +2,7 @@
 // turn the reference's parameter blocks into kernel launches. See include/althea_cuda.h for what each one replaces.
 // No CPU fallback anywhere: a compute entry point either launches sm_100a kernels or returns an error.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -47,6 +48,7 @@ struct althea_cuda_ctx {
   std::unordered_map<uint64_t, Resource> resources;
   uint64_t nextHandle = 1;
   uint64_t launches = 0;
+  uint32_t scissorY0 = 0, scissorY1 = 0; // rows of the final image this ctx shades; y1 == 0 => whole frame
   // internal scratch: SSAO occluded-ray counts
   void* aoScratch = nullptr;
   size_t aoScratchBytes = 0;
@@ -214,6 +216,29 @@ void drainTimings(althea_cuda_ctx* ctx) {
   ctx->pending.clear();
 }
 
+// Row ranges [lo, hi) of every reflection mip that must be present so that rows [y0, y1) of the FINAL image come out the
+// same as in a whole-frame run: the deferred pass fetches the mips trilinearly at the pixel's own uv (DeferredPass.frag:29-31)
+// and level L is a 7-tap blur of level L-1 along y (L odd) or x (L even) (ReflectionBuffer.cpp:224-278). Conservative:
+// a few rows more than strictly needed never change a value, they are only recomputed.
+void bandRows(uint32_t w, uint32_t h, uint32_t mips, uint32_t y0, uint32_t y1, uint32_t* lo, uint32_t* hi) {
+  auto clampRow = [](double v, uint32_t n) { return (uint32_t)(v < 0.0 ? 0.0 : (v > (double)n ? (double)n : v)); };
+  for (uint32_t L = 0; L < mips; ++L) {
+    const double hL = (double)mipDim(h, L);
+    lo[L] = clampRow(floor((double)y0 * hL / (double)h) - 2.0, mipDim(h, L));
+    hi[L] = clampRow(ceil((double)y1 * hL / (double)h) + 2.0, mipDim(h, L));
+  }
+  for (uint32_t L = mips - 1; L >= 1; --L) {
+    const double hS = (double)mipDim(h, L - 1), hD = (double)mipDim(h, L), wD = (double)mipDim(w, L);
+    const double off = (L & 1u) ? 5.176470588235294 * hS / wD : 0.0; // offsets are divided by the WIDTH on both axes (:41)
+    const uint32_t sLo = clampRow(floor((double)lo[L] * hS / hD - 0.5 - off) - 1.0, mipDim(h, L - 1));
+    const uint32_t sHi = clampRow(ceil((double)(hi[L] ? hi[L] - 1 : 0) * hS / hD - 0.5 + off) + 3.0, mipDim(h, L - 1));
+    if (hi[L] > lo[L]) {
+      if (sLo < lo[L - 1]) lo[L - 1] = sLo;
+      if (sHi > hi[L - 1]) hi[L - 1] = sHi;
+    }
+  }
+}
+
 // projection * view in the oracle's op order (column by column, summed left to right, no contraction: this TU's host
 // code is compiled with -ffp-contract=off via -Xcompiler)
 void matmul44(const float* A, const float* B, float* R) {
@@ -267,6 +292,13 @@ int fillFrameParams(althea_cuda_ctx* ctx, const althea_global_uniforms* u, const
   if ((rc = getImage(ctx, shadow, ALTHEA_FORMAT_R32_SFLOAT, "shadow_cube_array", &sh, true))) return rc;
   P->W = (int)normal->w;
   P->H = (int)normal->h;
+  P->y0 = 0;
+  P->y1 = P->H;
+  if (ctx->scissorY1) {
+    if (ctx->scissorY1 > normal->h) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "scissor rows [%u, %u) exceed the frame height %u", ctx->scissorY0, ctx->scissorY1, normal->h);
+    P->y0 = (int)ctx->scissorY0;
+    P->y1 = (int)ctx->scissorY1;
+  }
   auto sameSize = [&](Resource* r) { return !r || (r->w == normal->w && r->h == normal->h); };
   if (!sameSize(albedo) || !sameSize(mro) || !sameSize(depth) || !sameSize(position) || !sameSize(refl))
     return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "G-buffer and reflection images must all be %ux%u", normal->w, normal->h);
@@ -353,6 +385,19 @@ const char* althea_cuda_last_error(const althea_cuda_ctx* ctx) { return ctx ? ct
 int althea_cuda_set_flags(althea_cuda_ctx* ctx, uint32_t flags) {
   if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
   ctx->flags = flags;
+  return ALTHEA_OK;
+}
+
+int althea_cuda_set_scissor_rows(althea_cuda_ctx* ctx, uint32_t y0, uint32_t y1) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  if (y1 != 0 && y1 <= y0) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "scissor rows [%u, %u) are empty", y0, y1);
+  ctx->scissorY0 = y1 ? y0 : 0;
+  ctx->scissorY1 = y1;
+  return ALTHEA_OK;
+}
+int althea_cuda_band_rows(uint32_t w, uint32_t h, uint32_t mips, uint32_t y0, uint32_t y1, uint32_t* out_lo, uint32_t* out_hi) {
+  if (!w || !h || !mips || mips > (uint32_t)kMaxMips || y1 <= y0 || y1 > h || !out_lo || !out_hi) return ALTHEA_ERR_INVALID_ARGUMENT;
+  bandRows(w, h, mips, y0, y1, out_lo, out_hi);
   return ALTHEA_OK;
 }
 
@@ -605,6 +650,13 @@ int althea_cuda_ssr_capture(althea_cuda_ctx* ctx, const althea_global_uniforms* 
   FrameParams P;
   int rc = fillFrameParams(ctx, uniforms, gbuffer, ibl, lights_buf, shadow_cube_array, reflection, /*needPosition=*/false, &P);
   if (rc) return rc;
+  if (ctx->scissorY1) { // the glossy mips of the band need a halo of mip-0 rows: recompute them locally
+    Resource* refl = find(ctx, reflection, ResKind::Image);
+    uint32_t lo[kMaxMips], hi[kMaxMips];
+    bandRows(refl->w, refl->h, refl->mips, ctx->scissorY0, ctx->scissorY1, lo, hi);
+    P.y0 = (int)lo[0];
+    P.y1 = (int)hi[0];
+  }
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
   const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
@@ -620,11 +672,21 @@ int althea_cuda_glossy_convolve(althea_cuda_ctx* ctx, uint64_t reflection, const
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
   const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
+  uint32_t lo[kMaxMips], hi[kMaxMips];
+  if (ctx->scissorY1) {
+    if (ctx->scissorY1 > refl->h) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "scissor rows exceed the frame height %u", refl->h);
+    bandRows(refl->w, refl->h, refl->mips, ctx->scissorY0, ctx->scissorY1, lo, hi);
+  } else {
+    for (uint32_t level = 0; level < refl->mips; ++level) { lo[level] = 0; hi[level] = mipDim(refl->h, level); }
+  }
   for (uint32_t level = 1; level < refl->mips; ++level) { // ReflectionBuffer.cpp:224-278
+    if (hi[level] <= lo[level]) continue;
     ConvolveParams C;
     levelView(*refl, level - 1, 0, &C.src);
     levelView(*refl, level, 0, &C.dst);
     C.vertical = (int)(level & 1u);
+    C.y0 = (int)lo[level];
+    C.y1 = (int)hi[level];
     timedLaunch(ctx, "glossy_convolve", stream, [&] { parity ? althea_parity::launch_glossy_convolve(C, stream) : althea_fast::launch_glossy_convolve(C, stream); });
   }
   return endWork(ctx, sync, stream);

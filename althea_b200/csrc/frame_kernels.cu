@@ -163,8 +163,8 @@ ADEV V4 environmentLitSample(const FrameParams& P, V3 currentPos, float u, float
 
 __global__ void __launch_bounds__(256) ssr_capture_kernel(const __grid_constant__ FrameParams P) {
   const int x = blockIdx.x * 16 + (threadIdx.x & 15);
-  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
-  if (x >= P.W || y >= P.H) return;
+  const int y = P.y0 + blockIdx.y * 16 + (threadIdx.x >> 4); // rows [y0, y1): the scissor (whole frame by default)
+  if (x >= P.W || y >= P.y1) return;
   const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
   V4 normal4 = FmtRGBA16F::load(P.normal, x, y);
   V4 out = mk4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -253,9 +253,9 @@ __global__ void __launch_bounds__(256) ssr_capture_kernel(const __grid_constant_
 // ---- glossy convolve ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) glossy_convolve_kernel(const __grid_constant__ ConvolveParams C) {
   const int x = blockIdx.x * 16 + (threadIdx.x & 15);
-  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+  const int y = C.y0 + blockIdx.y * 16 + (threadIdx.x >> 4); // dst rows [y0, y1)
   const int w = C.dst.w, h = C.dst.h;
-  if (x >= w || y >= h) return;
+  if (x >= w || y >= C.y1) return;
   const float u = (float)x / (float)w, v = (float)y / (float)h; // texelPos / size, no half texel
   const float resolution = (float)w;                            // width for both axes (SSRGlossyConvolve.comp:41)
   const float dirx = C.vertical ? 0.0f : 1.0f, diry = C.vertical ? 1.0f : 0.0f;
@@ -338,8 +338,8 @@ ADEV int ssaoCountExact(const FrameParams& P, int px, int py, float u0, float v0
 
 __global__ void __launch_bounds__(256) ssao_exact_kernel(const __grid_constant__ FrameParams P) {
   const int x = blockIdx.x * 16 + (threadIdx.x & 15);
-  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
-  if (x >= P.W || y >= P.H) return;
+  const int y = P.y0 + blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (x >= P.W || y >= P.y1) return;
   V4 position = FmtRGBA32F::load(P.position, x, y);
   uint8_t count = 255;
   if (position.w != 0.0f) {
@@ -544,8 +544,8 @@ ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float
 constexpr int kSsaoTileW = ALTHEA_SSAO_TILE_W, kSsaoTileH = 256 / ALTHEA_SSAO_TILE_W;
 __global__ void __launch_bounds__(256, ALTHEA_SSAO_MIN_BLOCKS) ssao_kernel(const __grid_constant__ FrameParams P) {
   const int x = blockIdx.x * kSsaoTileW + (threadIdx.x % kSsaoTileW);
-  const int y = blockIdx.y * kSsaoTileH + (threadIdx.x / kSsaoTileW);
-  if (x >= P.W || y >= P.H) return;
+  const int y = P.y0 + blockIdx.y * kSsaoTileH + (threadIdx.x / kSsaoTileW);
+  if (x >= P.W || y >= P.y1) return;
   V4 position = FmtRGBA32F::load(P.position, x, y);
   uint8_t count = 255;
   if (position.w != 0.0f) {
@@ -563,8 +563,8 @@ ADEV V3 tonemap(V3 c, float exposure) {
 
 __global__ void __launch_bounds__(256) deferred_shade_kernel(const __grid_constant__ FrameParams P) {
   const int x = blockIdx.x * 16 + (threadIdx.x & 15);
-  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
-  if (x >= P.W || y >= P.H) return;
+  const int y = P.y0 + blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (x >= P.W || y >= P.y1) return;
   const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
   const V3 direction = viewDirection(P, u, v);
   V4 position = FmtRGBA32F::load(P.position, x, y);
@@ -597,15 +597,15 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const __grid_consta
 // ---- launchers ------------------------------------------------------------------------------------------------------
 static inline dim3 tileGrid(int w, int h) { return dim3((unsigned)((w + 15) / 16), (unsigned)((h + 15) / 16)); }
 
-void launch_ssr_capture(const FrameParams& P, cudaStream_t s) { ssr_capture_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
-void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s) { glossy_convolve_kernel<<<tileGrid(C.dst.w, C.dst.h), 256, 0, s>>>(C); }
+void launch_ssr_capture(const FrameParams& P, cudaStream_t s) { ssr_capture_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
+void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s) { glossy_convolve_kernel<<<tileGrid(C.dst.w, C.y1 - C.y0), 256, 0, s>>>(C); }
 void launch_ssao(const FrameParams& P, cudaStream_t s) {
-  ssao_kernel<<<dim3((unsigned)((P.W + kSsaoTileW - 1) / kSsaoTileW), (unsigned)((P.H + kSsaoTileH - 1) / kSsaoTileH)), 256, 0, s>>>(P);
+  ssao_kernel<<<dim3((unsigned)((P.W + kSsaoTileW - 1) / kSsaoTileW), (unsigned)((P.y1 - P.y0 + kSsaoTileH - 1) / kSsaoTileH)), 256, 0, s>>>(P);
 }
-void launch_ssao_exact(const FrameParams& P, cudaStream_t s) { ssao_exact_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
+void launch_ssao_exact(const FrameParams& P, cudaStream_t s) { ssao_exact_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
 void launch_ssao_quads(const FrameParams& P, cudaStream_t s) {
   ssao_quads_kernel<<<dim3((unsigned)((P.W + 1 + 31) / 32), (unsigned)((P.H + 1 + 7) / 8)), 256, 0, s>>>(P);
 }
-void launch_deferred_shade(const FrameParams& P, cudaStream_t s) { deferred_shade_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
+void launch_deferred_shade(const FrameParams& P, cudaStream_t s) { deferred_shade_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
 
 } // namespace ALTHEA_NS

@@ -24,6 +24,7 @@ struct FrameParams {
   // product with the camera z axis inverseView[2].xyz = S[0] + S[1] u + S[2] v (Misc/ReconstructPosition.glsl:9-21)
   float ssrW0[3], ssrWu[3], ssrWv[3], ssrS[3];
   int W, H;
+  int y0, y1; // rows this launch shades (the scissor; [0, H) by default)
   ImgView depth, position, normal, albedo, mro; // GBufferResources
   ImgView env, irr, lut;                        // IBLResources
   ChainView pre;                                // prefiltered env, 5 mips
@@ -45,6 +46,7 @@ struct FrameParams {
 struct ConvolveParams {
   ImgView src, dst;
   int vertical; // (level & 1): direction = (0,1) else (1,0)  (ReflectionBuffer.cpp:257-258)
+  int y0, y1;   // dst rows to write
 };
 
 struct MipGenParams {

@@ -103,6 +103,11 @@ class Context:
     def set_flags(self, flags: int):
         self._check(self._lib.althea_cuda_set_flags(self._ptr, flags))
 
+    def set_scissor_rows(self, y0: int = 0, y1: int = 0):
+        """Restricts the per-frame stages to what rows [y0, y1) of the final image need (row-band multi-GPU mode);
+        (0, 0) restores the whole frame."""
+        self._check(self._lib.althea_cuda_set_scissor_rows(self._ptr, y0, y1))
+
     # ---- resources ----
     def wrap_tensor(self, tensor, fmt: int, w: int, h: int, mips: int = 1, layers: int = 1) -> Image:
         """Registers a contiguous CUDA torch tensor as a linear image (althea_cuda_wrap_linear_image)."""
@@ -170,6 +175,15 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._lib.althea_cuda_launch_count(self._ptr))
+
+
+def band_rows(w: int, h: int, mips: int, y0: int, y1: int):
+    """[(lo, hi)] per reflection mip: the rows a band [y0, y1) of a w x h frame reads or writes (althea_cuda_band_rows)."""
+    lo, hi = (C.c_uint32 * mips)(), (C.c_uint32 * mips)()
+    rc = _capi.load().althea_cuda_band_rows(w, h, mips, y0, y1, lo, hi)
+    if rc != 0:
+        raise AltheaError("althea_cuda_band_rows(%d, %d, %d, %d, %d) failed: %d" % (w, h, mips, y0, y1, rc))
+    return [(int(lo[k]), int(hi[k])) for k in range(mips)]
 
 
 def _torch():

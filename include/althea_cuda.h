@@ -72,6 +72,15 @@ int althea_cuda_abi_version(void);
 #define ALTHEA_CTX_SSAO_EXACT_TAPS 2u /* SSAO marches the fp32 position texels directly (4 loads per tap) instead of the packed proxy with exact re-evaluation; same counts, slower: A/B switch for tests and profiling */
 int althea_cuda_set_flags(althea_cuda_ctx* ctx, uint32_t flags);
 
+/* Row bands (multi-GPU split of ONE frame, BASELINE configs[3]): restricts ssr_capture / glossy_convolve / deferred_shade on
+ * this ctx to what rows [y0, y1) of the final image need, the Vulkan scissor's role (RenderPass::begin sets viewport and
+ * scissor to the full extent, Src/RenderPass.cpp:247-288). ssr_capture and glossy_convolve widen the band by the halo of
+ * reflection rows the band's glossy mips depend on (recomputed locally, no halo exchange), so the band's pixels come out
+ * bit-identical to a whole-frame run. y1 == 0 restores the whole frame. Inputs are always whole-frame images. */
+int althea_cuda_set_scissor_rows(althea_cuda_ctx* ctx, uint32_t y0, uint32_t y1);
+/* The rows [out_lo[L], out_hi[L]) of reflection mip L that a band [y0, y1) of a w x h frame reads or writes (L < mips). */
+int althea_cuda_band_rows(uint32_t w, uint32_t h, uint32_t mips, uint32_t y0, uint32_t y1, uint32_t* out_lo, uint32_t* out_hi);
+
 /* Per-kernel device timing (CUDA events on the launching stream around every kernel this library launches). */
 int althea_cuda_enable_timing(althea_cuda_ctx* ctx, int enable);
 /* Sums since the last reset. names[i] points at static strings. Returns the number of distinct kernels (<= cap). Synchronises the recorded events. */

@@ -1,0 +1,173 @@
+"""Row-band mode (one frame over several GPUs): host logic on CPU with gloo (world_size 2), band == whole-frame equality on
+one GPU through the scissor, and the NCCL path when two GPUs are visible."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from althea_b200 import bands
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_split_rows_covers_the_frame():
+    for H in (1, 7, 67, 2160, 4320, 4321):
+        for world in (1, 2, 3, 4, 8):
+            sp = bands.split_rows(H, world)
+            assert len(sp) == world and sp[0][0] == 0 and sp[-1][1] == H
+            assert all(a[1] == b[0] for a, b in zip(sp, sp[1:]))
+            assert all(0 <= y1 - y0 <= bands.band_height(H, world) for y0, y1 in sp)
+            assert bands.padded_rows(H, world) >= H
+
+
+def test_band_rows_contain_what_the_band_reads(lib_built):
+    from althea_b200 import engine
+    W, H, mips = 7680, 4320, 5
+    for y0, y1 in bands.split_rows(H, 8) + [(0, H), (100, 101)]:
+        rows = engine.band_rows(W, H, mips, y0, y1)
+        for L, (lo, hi) in enumerate(rows):
+            hL = max(1, H >> L)
+            assert 0 <= lo < hi <= hL
+            # the deferred pass reads level L around v * hL - 0.5 for v in the band
+            assert lo <= max(0, int(np.floor((y0 + 0.5) / H * hL - 0.5))) and hi >= min(hL, int(np.floor((y1 - 0.5) / H * hL - 0.5)) + 2)
+        for L in range(1, mips):  # level L rows come from level L-1 rows around 2r (+- 5.18 * h_src / w_dst on vertical passes)
+            (lo, hi), (slo, shi) = rows[L], rows[L - 1]
+            hS, hD, wD = max(1, H >> (L - 1)), max(1, H >> L), max(1, W >> L)
+            off = 5.176470588235294 * hS / wD if L & 1 else 0.0
+            assert slo <= max(0, int(np.floor(lo * hS / hD - 0.5 - off)))
+            assert shi >= min(hS, int(np.floor((hi - 1) * hS / hD - 0.5 + off)) + 2)
+    full = engine.band_rows(W, H, mips, 0, H)
+    assert full == [(0, max(1, H >> L)) for L in range(mips)]
+    with pytest.raises(engine.AltheaError):
+        engine.band_rows(W, H, mips, 10, 10)
+
+
+def _gloo_worker(rank, world, port, H, W, out):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(1234)
+        frame = torch.randint(0, 255, (H, W), dtype=torch.uint8, generator=g)
+        mine = frame.clone() if rank == 0 else torch.zeros_like(frame)  # only the producing rank has the G-buffer
+        bands.broadcast_tensors([mine], src=0)
+        assert torch.equal(mine, frame)
+        # "shade" the band: any per-pixel function of the WHOLE input (here: depends on a far-away row, as SSR does)
+        def shade(y0, y1):
+            return (mine[y0:y1].to(torch.int32) * 3 + mine.flip(0)[y0:y1].to(torch.int32)).to(torch.uint8)
+        y0, y1 = bands.split_rows(H, world)[rank]
+        bh = bands.band_height(H, world)
+        buf = torch.zeros(bands.padded_rows(H, world) * W, dtype=torch.uint8)
+        buf[y0 * W:y1 * W] = shade(y0, y1).reshape(-1)
+        bands.allgather_rows(buf, W, bh)
+        want = shade(0, H)
+        assert torch.equal(buf[: H * W].view(H, W), want), "rank %d" % rank
+        out.put((rank, True))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("H", [64, 67])
+def test_broadcast_and_allgather_world2_gloo(H):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, H, 48, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5)[0] for _ in range(2)) == [0, 1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["parity", "fast"])
+def test_bands_equal_whole_frame_on_one_gpu(request, which):
+    """Every band, rendered alone with poisoned surroundings, reproduces its rows of the whole-frame result bit for bit."""
+    from helpers import FrameData, GpuFrame
+    from althea_b200 import _capi
+    ctx = request.getfixturevalue("ctx_parity" if which == "parity" else "ctx_fast")
+    fd = FrameData("scene", 320, 181, n_lights=2, shadow_res=32)
+    gf = GpuFrame(ctx, fd)
+
+    def run():
+        gf.ssr.captureReflection(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights)
+        gf.ssr.convolveReflectionBuffer()
+        gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+        torch.cuda.synchronize()
+        return gf.deferred.colorTarget.tensor.clone().view(fd.H, -1), gf.deferred.aoCounts.tensor.clone().view(fd.H, -1)
+
+    full_c, full_a = run()
+    assert float(gf.color()[..., :3].std()) > 0.01
+    for world in (2, 3, 5):
+        for y0, y1 in bands.split_rows(fd.H, world):
+            gf.ssr.getReflectionBuffer().image.tensor.fill_(0xFF)  # NaN halves everywhere the band does not write
+            gf.deferred.colorTarget.tensor.fill_(0x7F)
+            gf.deferred.aoCounts.tensor.fill_(0x7F)
+            ctx.set_scissor_rows(y0, y1)
+            c, a = run()
+            ctx.set_scissor_rows(0, 0)
+            assert torch.equal(c[y0:y1], full_c[y0:y1]), (world, y0, y1)
+            assert torch.equal(a[y0:y1], full_a[y0:y1])
+            assert bool((c[:y0] == 0x7F).all()) and bool((c[y1:] == 0x7F).all())  # nothing outside the band is touched
+    with pytest.raises(Exception):
+        ctx.set_scissor_rows(0, fd.H + 1)
+        run()
+    ctx.set_scissor_rows(0, 0)
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world, device_id=torch.device("cuda:%d" % rank))
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from helpers import FrameData, GpuFrame
+        from althea_b200 import _capi, engine
+        ctx = engine.Context(rank)
+        fd = FrameData("scene", 384, 216, n_lights=2, shadow_res=32)
+        gf = GpuFrame(ctx, fd)
+        gf.ssr.captureReflection(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights)
+        gf.ssr.convolveReflectionBuffer()
+        gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+        torch.cuda.synchronize()
+        want = gf.deferred.colorTarget.tensor.clone()
+        if rank != 0:  # only rank 0 "produced" the G-buffer
+            for img in (gf.gbuffer.position, gf.gbuffer.depth, gf.gbuffer.normal, gf.gbuffer.albedo, gf.gbuffer.mro):
+                img.tensor.zero_()
+        bf = bands.BandedFrame(ctx, fd.W, fd.H, out_format=_capi.FORMAT_R32G32B32A32_SFLOAT)
+        bf.broadcast_gbuffer(gf.gbuffer, src=0)
+        bf.render(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights)
+        bf.gather()
+        torch.cuda.synchronize()
+        ok = torch.equal(bf.color_rows().reshape(-1), want)
+        q.put((rank, bool(ok)))
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_bands_over_two_gpus_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(2))
+    assert res == {0: True, 1: True}

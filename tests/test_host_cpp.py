@@ -1,0 +1,73 @@
+"""The C++ mirror of the reference's interface (althea_b200/host/Althea/*.h): builds on CPU, and on the GPU one frame driven
+from C++ (demo_frame) must equal the same frame driven through the Python mirror bit for bit (same library underneath) and
+match the CPU oracle to the usual bars."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import FrameData, GpuFrame, half_to_float, psnr
+
+
+def test_cpp_mirror_builds(lib_built):
+    from althea_b200.host import build_host
+    exe = build_host.build()
+    assert os.access(exe, os.X_OK)
+    hdr_dir = os.path.join(os.path.dirname(exe), "Althea")
+    # same class names as the reference headers they mirror (Include/Althea/*.h)
+    text = "".join(open(os.path.join(hdr_dir, f)).read() for f in os.listdir(hdr_dir))
+    for name in ("class GBufferResources", "class ReflectionBuffer", "class ScreenSpaceReflection", "struct IBLResources",
+                 "namespace ImageBasedLighting", "class PointLightCollection", "struct PointLight", "GlobalUniforms"):
+        assert name in text, name
+    for method in ("captureReflection", "convolveReflectionBuffer", "createResources", "setLight", "updateResource"):
+        assert method in text, method
+
+
+def _write_inputs(path, fd):
+    n = 0 if fd.lights is None else fd.lights.shape[0]
+    with open(path, "wb") as f:
+        f.write(struct.pack("13i", fd.W, fd.H, n, fd.shadow_res if n else 0, fd.env.shape[1], fd.env.shape[0], fd.pre_size[0], fd.pre_size[1], 5,
+                            fd.irr.shape[1], fd.irr.shape[0], fd.lut.shape[1], fd.lut.shape[0]))
+        f.write(bytes(fd.uniforms))
+        for a in (fd.position, fd.depth, fd.normal, fd.albedo, fd.mro):
+            f.write(np.ascontiguousarray(a).tobytes())
+        if n:
+            f.write(np.ascontiguousarray(fd.lights, np.float32).tobytes())
+            f.write(np.ascontiguousarray(fd.shadow, np.float32).tobytes())
+        for a in (fd.env, fd.pre, fd.irr, fd.lut):
+            f.write(np.ascontiguousarray(a).tobytes())
+
+
+@pytest.mark.gpu
+def test_cpp_frame_equals_python_frame_and_oracle(tmp_path, ctx_parity, oracle):
+    from althea_b200 import _capi
+    from althea_b200.host import build_host
+    exe = build_host.build()
+    fd = FrameData("scene", 160, 90, n_lights=3, shadow_res=32)
+    inp, outp = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    _write_inputs(inp, fd)
+    r = subprocess.run([exe, inp, outp, "--parity"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "demo_frame ok" in r.stdout and "expected failure" in r.stdout and "must all be" in r.stdout
+    raw = np.fromfile(outp, np.uint8)
+    chain_bytes = sum(max(1, fd.W >> k) * max(1, fd.H >> k) * 8 for k in range(5))
+    cpp_chain = raw[:chain_bytes].view(np.uint16)
+    cpp_color = raw[chain_bytes:].view(np.float32).reshape(fd.H, fd.W, 4)
+    # the same frame through the Python mirror
+    gf = GpuFrame(ctx_parity, fd)
+    gf.ssr.captureReflection(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights)
+    gf.ssr.convolveReflectionBuffer()
+    gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+    assert np.array_equal(cpp_chain, gf.reflection_chain())
+    assert np.array_equal(cpp_color, gf.color())
+    # and the oracle
+    fr = fd.oracle_frame()
+    refl, hit, _ = oracle.ssr_capture(fr)
+    chain = oracle.glossy_convolve(refl)
+    want = oracle.deferred_shade(fr, chain, 5, oracle.SKIP_TONEMAP, oracle.ssao(fr))
+    n0 = fd.W * fd.H * 4
+    assert np.array_equal(half_to_float(cpp_chain[:n0]).reshape(fd.H, fd.W, 4)[..., 3] != 0, hit != 0)
+    ok = (np.abs(cpp_color - want) <= 1e-3 * np.maximum(1.0, np.abs(want))).all(axis=-1)
+    assert ok.mean() >= 0.9995 and psnr(cpp_color, want) >= 50.0
