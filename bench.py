@@ -35,7 +35,8 @@ UNIT = "Mpixel/s"
 BYTES_PER_PX = {
     "ssr_capture": 28.0,      # depth 4 + normal 8 + albedo 4 + MRO 4 + write RGBA16F 8
     "glossy_convolve": 13.28,  # read 8*(1+1/4+1/16+1/64) + write 8*(1/4+...+1/256)
-    "ssao": 25.0,             # position 16 + normal 8 + write count 1
+    "ssao": 25.0,             # position 16 + normal 8 + write count 1 (the proxy records are engine scratch, not algorithmic)
+    "ssao_quads": 48.0,       # position 16 read + 32-byte proxy record written per pixel
     "deferred_shade": 51.66,  # position 16 + normal 8 + albedo 4 + MRO 4 + AO count 1 + reflection mips (upper bound) 10.66 + write RGBA16F 8
 }
 FLOPS_PER_PX = {"ssao": 14400.0, "ssr_capture": 11500.0, "deferred_shade": 200.0 + 80.0 * N_LIGHTS, "glossy_convolve": 7 * 4 * 8.0}
@@ -86,6 +87,100 @@ class ClockSampler(threading.Thread):
                 continue
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload (profiles/ncu_traffic.json,
+    written by tools/ncu_summary.py traffic ...); None when no capture is on record."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        rec = json.load(open(p)).get(kernel)
+        if rec:
+            return rec
+    return None
+
+
+def main_bands8k(args, ctx, rank, local_rank, world, device):
+    """BASELINE configs[3]: one synthetic 7680x4320 S-rand G-buffer, rendered in row bands over the ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from althea_b200 import _capi, bands, engine, scene
+    W8, H8 = 7680, 4320
+    ibl, lights, _, _ = build_rank_inputs(ctx, rank, 0, device, quick_ibl=True)
+    g = scene.make_uniforms(W8, H8, pos=(0.0, 0.0, 0.0), yaw=0.0, pitch=0.0, light_count=N_LIGHTS)
+    gb = engine.GBufferResources(ctx, W8, H8)
+    if rank == 0:  # the producing rank; the others receive it by broadcast every step
+        gbd = scene.s_rand(g, W8, H8, device=device)
+        gb.upload(position=gbd.position, depth=gbd.depth, normal=gbd.normal, albedo=gbd.albedo, mro=gbd.mro)
+        del gbd
+    bf = bands.BandedFrame(ctx, W8, H8)
+    stream = engine.current_stream_ptr(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    comm_ms = [0.0, 0.0]
+
+    def step(timed=False):
+        if timed:
+            ev[0].record()
+        bf.broadcast_gbuffer(gb, src=0)
+        if timed:
+            ev[1].record()
+        bf.render(g, gb, ibl, lights, _capi.SHADE_SKIP_TONEMAP, stream)
+        if timed:
+            ev[2].record()
+        bf.gather()
+        if timed:
+            ev[3].record()
+            torch.cuda.synchronize()
+            comm_ms[0] += ev[0].elapsed_time(ev[1])
+            comm_ms[1] += ev[2].elapsed_time(ev[3])
+
+    for _ in range(args.warmup):
+        step()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count() - launches0
+    for _ in range(2):  # untimed-by-the-headline pass that splits communication from compute
+        step(timed=True)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    if rank == 0:
+        hbm_peak, peak_src, _ = peaks()
+        gbytes = W8 * H8 * 36
+        line = {"metric": "deferred+SSAO+SSR Mpixel/s, one 8K frame in row bands", "value": W8 * H8 / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[3]: one 7680x4320 S-rand G-buffer (random depth/normal/albedo/MRO, 5 %% empty), 16 lights; rows split over %d "
+                                       "rank(s); every step = NCCL broadcast of the G-buffer (%.2f GB) + band render with locally recomputed reflection halo + "
+                                       "NCCL all-gather of the RGBA16F bands (%.0f MB)" % (world, gbytes / 1e9, W8 * H8 * 8 / 1e6),
+                           "band_rows": bf.band, "l2_policy": "inputs (1.2 GB) exceed the 126 MB L2"},
+                "gpu_launches": int(launches) * world, "clocks": clocks,
+                "comm": {"broadcast_ms": comm_ms[0] / 2, "allgather_ms": comm_ms[1] / 2, "note": "rank 0, device events, second pass after the timed region"},
+                "roofline_chain": {"bytes_per_px": 92.0, "achieved_GBps": 92.0 * W8 * H8 / (ms_step * 1e-3) / 1e9,
+                                   "hbm_frac": 92.0 * W8 * H8 / (ms_step * 1e-3) / 1e9 / (hbm_peak * world), "peak_source": peak_src}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def build_rank_inputs(ctx, rank: int, views: int, device: str, quick_ibl: bool = False):
@@ -223,6 +318,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--views", type=int, default=VIEWS_PER_GPU)
+    ap.add_argument("--workload", default="views4k", choices=["views4k", "bands8k"],
+                    help="views4k (default, the contract benchmark): 4K views sharded by view, weak scaling. bands8k: ONE 7680x4320 "
+                         "S-rand frame split in row bands, NCCL broadcast of the G-buffer + all-gather of the bands, strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -244,6 +342,8 @@ def main():
 
     from althea_b200 import _capi, engine
     ctx = engine.Context(local_rank)
+    if args.workload == "bands8k":
+        return main_bands8k(args, ctx, rank, local_rank, world, device)
     ibl, lights, views, ibl_t = build_rank_inputs(ctx, rank, args.views, device)
     stream = engine.current_stream_ptr(local_rank)
     V = len(views)
@@ -344,8 +444,10 @@ def main():
         roofline = None
         if dom:
             s = stages[dom]
+            tr = ncu_traffic(dom)
             roofline = {"kernel": dom, "bound": "hbm", "achieved": s["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": s["hbm_frac"],
-                        "traffic": None, "peak_source": peak_src,
+                        "traffic": tr["dram_bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,
+                        "binding_resource": tr.get("binding_resource") if tr else None, "peak_source": peak_src,
                         "note": "%s is FP32-issue / L1-tap bound, not HBM bound (SURVEY.md 8d): fp32 frac %.3f of 148 SM x 128 lanes x 2 x %.0f MHz"
                                 % (dom, s["fp32_frac_at_sm_max"], sm_max)}
         frame_ms = ms_step / V

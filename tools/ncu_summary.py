@@ -90,5 +90,33 @@ def launches(path: str, out: str):
     print("wrote", out)
 
 
+def traffic(path: str, out: str):
+    """profiles/ncu_traffic.json: per kernel, DRAM bytes per launch + the busiest unit (what bench.py's roofline.traffic quotes)."""
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rec = json.load(open(out)) if os.path.exists(out) else {}
+    busy = {"L1 data pipe (LSU wavefronts)": "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+            "L2 (lts throughput)": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "DRAM": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "instruction issue": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "FMA pipe": "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+            "XU pipe": "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"}
+    for r in rows[2:]:
+        name = r[col["Kernel Name"]].split("(")[0].replace("_kernel", "").split("::")[-1]
+        rd = float(r[col["dram__bytes_read.sum"]].replace(",", "")) * scale[units[col["dram__bytes_read.sum"]]]
+        wr = float(r[col["dram__bytes_write.sum"]].replace(",", "")) * scale[units[col["dram__bytes_write.sum"]]]
+        util = {k: float(r[col[m]].replace(",", "")) for k, m in busy.items() if m in col and r[col[m]] != ""}
+        top = max(util, key=util.get)
+        rec[name] = {"dram_bytes_per_launch": rd + wr, "source": "profiles/" + os.path.basename(path).replace(".ncu-rep", "") + " (ncu --set full)",
+                     "binding_resource": "%s %.1f %% of peak" % (top, util[top]), "utilisation_pct": util}
+    json.dump(rec, open(out, "w"), indent=1, sort_keys=True)
+    print("wrote", out)
+
+
 if __name__ == "__main__":
-    {"report": report, "launches": launches}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"report": report, "launches": launches, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
