@@ -27,6 +27,34 @@ struct V2 { float x, y; };
 struct V3 { float x, y, z; };
 struct V4 { float x, y, z, w; };
 
+// Division and square root: IEEE (correctly rounded, ~10 SASS instructions with the slow-path check) in the parity build,
+// one MUFU + one multiply in the fast build. Used for colour arithmetic and directions, never for texel addressing.
+ADEV float rcpf(float x) {
+#ifdef ALTHEA_PARITY
+  return 1.0f / x;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+ADEV float fdiv(float a, float b) {
+#ifdef ALTHEA_PARITY
+  return a / b;
+#else
+  return a * rcpf(b);
+#endif
+}
+ADEV float fsqrt(float x) {
+#ifdef ALTHEA_PARITY
+  return sqrtf(x);
+#else
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+
 ADEV V3 mk3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
 ADEV V4 mk4(float x, float y, float z, float w) { V4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 ADEV V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -35,7 +63,14 @@ ADEV V3 operator-(V3 a) { return mk3(-a.x, -a.y, -a.z); }
 ADEV V3 operator*(V3 a, V3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
 ADEV V3 operator*(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 ADEV V3 operator*(float s, V3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
-ADEV V3 operator/(V3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+ADEV V3 operator/(V3 a, float s) {
+#ifdef ALTHEA_PARITY
+  return mk3(a.x / s, a.y / s, a.z / s);
+#else
+  const float r = rcpf(s);
+  return mk3(a.x * r, a.y * r, a.z * r);
+#endif
+}
 ADEV V4 operator+(V4 a, V4 b) { return mk4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 ADEV V4 operator*(V4 a, float s) { return mk4(a.x * s, a.y * s, a.z * s, a.w * s); }
 ADEV float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }

@@ -15,10 +15,15 @@ namespace ALTHEA_NS {
 // ---- run-time equirect IBL lookups: CLAMP_TO_EDGE (ImageBasedLighting.cpp:469-475,519-524,556-560) ----------------
 ADEV V2 equirectUv(V3 d) { // PBRMaterial.glsl:5-7
   float yaw = atan2f(d.z, d.x);
-  float pitch = -atan2f(d.y, sqrtf(d.x * d.x + d.z * d.z));
+  float pitch = -atan2f(d.y, fsqrt(d.x * d.x + d.z * d.z));
   V2 uv;
+#ifdef ALTHEA_PARITY
   uv.x = (0.5f * yaw) / kPi + 0.5f;
   uv.y = pitch / kPi + 0.5f;
+#else
+  uv.x = fmaf(yaw, 0.5f / kPi, 0.5f);
+  uv.y = fmaf(pitch, 1.0f / kPi, 0.5f);
+#endif
   return uv;
 }
 ADEV V3 sampleEnvMapLod0(const FrameParams& P, V3 dir) { // DeferredPass.frag:33-39
@@ -42,7 +47,12 @@ ADEV float sampleShadowCube(const FrameParams& P, V3 q, int light) {
   if (ax >= ay && ax >= az) { ma = ax; if (q.x >= 0.0f) { face = 0; sc = -q.z; tc = -q.y; } else { face = 1; sc = q.z; tc = -q.y; } }
   else if (ay >= az)        { ma = ay; if (q.y >= 0.0f) { face = 2; sc = q.x; tc = q.z; } else { face = 3; sc = q.x; tc = -q.z; } }
   else                      { ma = az; if (q.z >= 0.0f) { face = 4; sc = q.x; tc = -q.y; } else { face = 5; sc = -q.x; tc = -q.y; } }
+#ifdef ALTHEA_PARITY
   float s = 0.5f * sc / ma + 0.5f, t = 0.5f * tc / ma + 0.5f;
+#else
+  const float hr = 0.5f * rcpf(ma);
+  float s = fmaf(sc, hr, 0.5f), t = fmaf(tc, hr, 0.5f);
+#endif
   ImgView layer = P.shadow;
   layer.ptr = static_cast<const char*>(P.shadow.ptr) + (size_t)(6 * light + face) * P.shadowLayerStride;
   return bilinearR32F<AddrClamp>(layer, s, t);
@@ -52,7 +62,7 @@ ADEV float sampleShadowCube(const FrameParams& P, V3 q, int light) {
 ADEV float ndfGgx(float NdotH, float a2) {
   float tmp = NdotH * NdotH * (a2 - 1.0f) + 1.0f;
   float denom = kPi * tmp * tmp;
-  return a2 / denom;
+  return fdiv(a2, denom);
 }
 ADEV float pow5(float x) {
 #ifdef ALTHEA_PARITY
@@ -67,7 +77,7 @@ ADEV V3 fresnelSchlick(float NdotV, V3 F0, float roughness) {
   V3 m = mk3(max_glsl(om, F0.x), max_glsl(om, F0.y), max_glsl(om, F0.z));
   return F0 + (m - F0) * pow5(1.0f - NdotV);
 }
-ADEV float geometrySchlickGgx(float NdotV, float k) { return NdotV / (NdotV * (1.0f - k) + k); }
+ADEV float geometrySchlickGgx(float NdotV, float k) { return fdiv(NdotV, NdotV * (1.0f - k) + k); }
 ADEV float geometrySmith(float NdotL, float NdotV, float k) { return geometrySchlickGgx(NdotV, k) * geometrySchlickGgx(NdotL, k); }
 
 // PBRMaterial.glsl:72-162 with the current (worldPos, V, N, ...) signature
@@ -94,7 +104,7 @@ ADEV V3 pbrMaterial(const FrameParams& P, V3 worldPos, V3 V, V3 N, V3 baseColor,
     float4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
     V3 L = mk3(l0.x, l0.y, l0.z) - worldPos;
     float LdistSq = dot3(L, L);
-    float Ldist = sqrtf(LdistSq);
+    float Ldist = fsqrt(LdistSq);
     L = L / Ldist;
     if (P.shadowRes > 0) {
       float closestDepth = sampleShadowCube(P, mk3(L.x, -L.y, -L.z), i);
@@ -106,7 +116,11 @@ ADEV V3 pbrMaterial(const FrameParams& P, V3 worldPos, V3 V, V3 N, V3 baseColor,
     float NdotL = max_glsl(dot3(N, L), 0.0f);
     float NdotH = max_glsl(dot3(N, H), 0.0f);
     V3 F = fresnelSchlick(NdotH, F0, roughness);
+#ifdef ALTHEA_PARITY
     V3 diffuseColor = ((one - F) * dielectricBase) / kPi;
+#else
+    V3 diffuseColor = ((one - F) * dielectricBase) * (1.0f / kPi);
+#endif
     V3 specularColor = ((ndfGgx(NdotH, a2) * F) * geometrySmith(NdotL, NdotV, kDirect)) / (4.0f * NdotL * NdotV + 0.0001f);
     color = color + ((diffuseColor + specularColor) * radiance) * NdotL;
   }
