@@ -294,6 +294,8 @@ int fillFrameParams(althea_cuda_ctx* ctx, const althea_global_uniforms* u, const
   P->H = (int)normal->h;
   P->y0 = 0;
   P->y1 = P->H;
+  P->Wf = (float)P->W;
+  P->Hf = (float)P->H;
   if (ctx->scissorY1) {
     if (ctx->scissorY1 > normal->h) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "scissor rows [%u, %u) exceed the frame height %u", ctx->scissorY0, ctx->scissorY1, normal->h);
     P->y0 = (int)ctx->scissorY0;
@@ -738,6 +740,8 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
       ctx->quadScratchBytes = need;
     }
     P.quads = ctx->quadScratch;
+    P.quadRow = P.W + 1;
+    P.quadsOrigin = static_cast<const char*>(ctx->quadScratch) + ((size_t)P.quadRow + 1) * 32;
   }
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;

@@ -429,13 +429,19 @@ struct ProxyTap {
 };
 // (u, v) has passed outside01: x is in [-0.5, W - 0.5], so floor(x) + 1 is a valid record column without clamping. A NaN
 // coordinate converts to column 1 and yields NaN weights, hence a NaN position, which the caller re-evaluates exactly.
-ADEV ProxyTap proxyTap(const FrameParams& P, float u, float v) {
+struct ProxyAddr { const QuadRecord* rec; float fx, fy; };
+ADEV ProxyAddr proxyAddr(const FrameParams& P, float u, float v) {
   // same coordinate arithmetic as the exact tap (rule A1): identical footprint and weights, approximate texel values
-  const float x = __fsub_rn(__fmul_rn(u, (float)P.W), 0.5f), y = __fsub_rn(__fmul_rn(v, (float)P.H), 0.5f);
-  const float fx0 = floorf(x), fy0 = floorf(y);
-  const float fx = x - fx0, fy = y - fy0;
-  const int qx = (int)fx0 + 1, qy = (int)fy0 + 1;
-  const QuadRecord r = loadQuad(static_cast<const QuadRecord*>(P.quads) + (uint32_t)(qy * (P.W + 1) + qx)); // < 2^31 records up to 32K x 32K
+  const float x = __fsub_rn(__fmul_rn(u, P.Wf), 0.5f), y = __fsub_rn(__fmul_rn(v, P.Hf), 0.5f);
+  const int ix = __float2int_rd(x), iy = __float2int_rd(y); // floor; |x| < 2^24, so (float)ix == floorf(x) exactly
+  ProxyAddr a;
+  a.fx = x - (float)ix;
+  a.fy = y - (float)iy;
+  // record (ix + 1, iy + 1); quadsOrigin points at record (1, 1), so the index is iy * (W + 1) + ix (>= -(W + 2))
+  a.rec = static_cast<const QuadRecord*>(P.quadsOrigin) + (iy * P.quadRow + ix);
+  return a;
+}
+ADEV ProxyTap proxyEval(const QuadRecord& r, float fx, float fy) {
   const float2 a = unpackHalf2(r.w[3]), b = unpackHalf2(r.w[4]), c = unpackHalf2(r.w[5]), d = unpackHalf2(r.w[6]), e = unpackHalf2(r.w[7]);
   // A = (a.x, a.y, b.x), B = (b.y, c.x, c.y), C = (d.x, d.y, e.x), E = e.y
   ProxyTap t;
@@ -465,6 +471,10 @@ constexpr float kSqrt3Up = 1.7320509f;
 constexpr float kRoundSlop = 64.0f * 1.1920929e-7f;
 constexpr float kTiny = 1e-15f; // decisions on |value| <= kTiny are always re-evaluated (products must not underflow)
 
+#ifndef ALTHEA_SSAO_UNROLL
+#define ALTHEA_SSAO_UNROLL 2
+#endif
+constexpr int kSsaoUnroll = ALTHEA_SSAO_UNROLL;
 ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float v0, V3 worldPos, V3 normal) {
   HashRng rng;
   rng.sx = (uint32_t)px;
@@ -482,11 +492,13 @@ ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float
     V3 prevPos = worldPos;
     float prevProjection = 0.0f, prevTol = 0.0f;
     bool prevSure = false, prevExact = true;
-#pragma unroll 1
+#pragma unroll kSsaoUnroll
     for (int i = 1; i < 12; ++i) {
       const float cu = marchCoord(u0, uvEnd.x, i), cv = marchCoord(v0, uvEnd.y, i);
       if (outside01(cu, cv)) break;
-      const ProxyTap tap = proxyTap(P, cu, cv);
+      const ProxyAddr pa = proxyAddr(P, cu, cv);
+      const ProxyTap tap = proxyEval(loadQuad(pa.rec), pa.fx, pa.fy);
+      {
       V3 curPos = tap.pos;
       float curProjection = dot3(curPos - worldPos, perpRef);
       const float mag = posMag + (fabsf(curPos.x) + fabsf(curPos.y) + fabsf(curPos.z));
@@ -544,6 +556,7 @@ ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float
         }
       }
       prevPos = curPos; prevProjection = curProjection; prevTol = curTol; prevSure = curSure; prevExact = curExact;
+      }
     }
   }
   return ao;

@@ -41,6 +41,9 @@ struct FrameParams {
   // describes the bilinear footprint whose top-left tap is texel (ix, iy), ix in [-1, W-1], iy in [-1, H-1]
   const void* quads;
   size_t quadPitch; // bytes per record row = (W+1)*32
+  const void* quadsOrigin; // &record(1, 1): the footprint whose top-left tap is texel (0, 0)
+  int quadRow;             // records per row = W + 1
+  float Wf, Hf;            // (float)W, (float)H
 };
 
 struct ConvolveParams {
