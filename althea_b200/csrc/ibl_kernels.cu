@@ -13,17 +13,81 @@
 
 namespace althea_iblk {
 
-// GenIrradianceMap.comp:78-102 == PreFilterEnvMap.comp:98-122. Precompute sampler: REPEAT, linear mips.
-ADEV V3 sampleEnvMapPrecompute(const ChainView& env, V3 dir, float mip) {
-  float pitch = 0.0f, yaw = 0.0f;
-  float lenXz = sqrtf(dir.x * dir.x + dir.z * dir.z);
+// ---- fast scalar math for the integrators ------------------------------------------------------------------------------
+// The precompute is a Monte-Carlo / Riemann integral checked against the oracle to 1e-3 (tests/test_ibl_parity.py), not a
+// chain of threshold decisions, so IEEE division / sqrt / libm transcendentals (10-40 SASS instructions each) are replaced
+// by MUFU forms and short polynomials with ~1e-7 error. This is where the instruction count per sample went from ~700 to
+// ~200 (profiles/r1d_ibl_*).
+ADEV float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+ADEV float lg2_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// atan on [0, 1]: Abramowitz & Stegun 4.4.49, |error| <= 2e-8 in exact arithmetic, 1.1e-7 in fp32
+ADEV float atan01(float q) {
+  const float s = q * q;
+  float p = 0.0028662257f;
+  p = fmaf(p, s, -0.0161657367f);
+  p = fmaf(p, s, 0.0429096138f);
+  p = fmaf(p, s, -0.0752896400f);
+  p = fmaf(p, s, 0.1065626393f);
+  p = fmaf(p, s, -0.1420889944f);
+  p = fmaf(p, s, 0.1999355085f);
+  p = fmaf(p, s, -0.3333314528f);
+  return fmaf(p * s, q, q);
+}
+ADEV float atan2_fast(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  float r = atan01(mx > 0.0f ? mn * rcpf(mx) : 0.0f);
+  if (ay > ax) r = 1.5707963267948966f - r;
+  if (x < 0.0f) r = kPi - r;
+  return y < 0.0f ? -r : r;
+}
+
+struct RepeatOnce { // REPEAT addressing for coordinates known to lie within one period of [0, n): no integer modulo
+  static ADEV int wrap(int i, int n) { i += i < 0 ? n : 0; return i >= n ? i - n : i; }
+};
+
+// one bilinear RGB tap of one level (REPEAT), a + t (b - a) lerps
+ADEV V3 bilinearRgbRepeat(const ImgView& im, float u, float v) {
+  const float x = fmaf(u, (float)im.w, -0.5f), y = fmaf(v, (float)im.h, -0.5f);
+  const float fx0 = floorf(x), fy0 = floorf(y);
+  const float fx = x - fx0, fy = y - fy0;
+  const int ix = (int)fx0, iy = (int)fy0;
+  const int i0 = RepeatOnce::wrap(ix, im.w), i1 = RepeatOnce::wrap(ix + 1, im.w);
+  const int j0 = RepeatOnce::wrap(iy, im.h), j1 = RepeatOnce::wrap(iy + 1, im.h);
+  const float4* r0 = rowPtr<float4>(im, j0);
+  const float4* r1 = rowPtr<float4>(im, j1);
+  const float4 t00 = __ldg(r0 + i0), t10 = __ldg(r0 + i1), t01 = __ldg(r1 + i0), t11 = __ldg(r1 + i1);
+  const float ax = fmaf(t10.x - t00.x, fx, t00.x), bx = fmaf(t11.x - t01.x, fx, t01.x);
+  const float ay = fmaf(t10.y - t00.y, fx, t00.y), by = fmaf(t11.y - t01.y, fx, t01.y);
+  const float az = fmaf(t10.z - t00.z, fx, t00.z), bz = fmaf(t11.z - t01.z, fx, t01.z);
+  return mk3(fmaf(bx - ax, fy, ax), fmaf(by - ay, fy, ay), fmaf(bz - az, fy, az));
+}
+
+// GenIrradianceMap.comp:78-102 == PreFilterEnvMap.comp:98-122: direction -> equirect uv (REPEAT sampler, linear mips)
+ADEV V2 equirectUvPrecompute(V3 dir) {
+  float pitch, yaw = 0.0f;
+  const float lenXz = fsqrt(dir.x * dir.x + dir.z * dir.z);
   if (lenXz > 0.001f) {
-    yaw = atan2f(dir.z, dir.x);
-    pitch = atanf(dir.y / lenXz);
-  } else if (dir.y > 0.0f) pitch = 0.5f * kPi;
-  else pitch = -0.5f * kPi;
-  float u = yaw / (2.0f * kPi) + 0.5f, v = pitch / kPi + 0.5f;
-  return xyz(trilinear<FmtRGBA32F, AddrRepeat>(env, u, v, mip));
+    yaw = atan2_fast(dir.z, dir.x);
+    pitch = atan2_fast(dir.y, lenXz); // == atan(y / lenXz) for lenXz > 0
+  } else pitch = dir.y > 0.0f ? 0.5f * kPi : -0.5f * kPi;
+  V2 uv;
+  uv.x = fmaf(yaw, 0.5f / kPi, 0.5f);
+  uv.y = fmaf(pitch, 1.0f / kPi, 0.5f);
+  return uv;
+}
+// explicit-LOD trilinear fetch, rule A5 (LOD clamped to the chain, LINEAR mip mode)
+ADEV V3 sampleEnvMapPrecompute(const ChainView& env, V3 dir, float mip) {
+  const V2 uv = equirectUvPrecompute(dir);
+  float lod = mip == mip ? mip : 0.0f;
+  lod = fminf(fmaxf(lod, 0.0f), (float)(env.mips - 1));
+  const float l0f = floorf(lod);
+  const int l0 = (int)l0f;
+  const float f = lod - l0f;
+  const V3 s0 = bilinearRgbRepeat(env.level[l0], uv.x, uv.y);
+  if (f == 0.0f) return s0;
+  const V3 s1 = bilinearRgbRepeat(env.level[min(l0 + 1, env.mips - 1)], uv.x, uv.y);
+  return mk3(fmaf(s1.x - s0.x, f, s0.x), fmaf(s1.y - s0.y, f, s0.y), fmaf(s1.z - s0.z, f, s0.z));
 }
 
 ADEV V3 texelNormal(const IblParams& I, int x, int y) {
@@ -117,13 +181,15 @@ template <int LANES> __global__ void __launch_bounds__(256) ibl_prefilter_kernel
   const float a2 = I.roughness * I.roughness;
   const float saTexel = 4.0f * kPi / (6.0f * (float)I.env.level[0].w * (float)I.env.level[0].h);
   const float fN = (float)I.numSamples;
+  const float lg2SaTexel = log2f(saTexel);
+  const float rcpN = 1.0f / fN;
   V3 acc = mk3(0.0f, 0.0f, 0.0f);
   float totalWeight = 0.0f;
   // roughness 0: cosTheta = sqrt(x / x) = 1 and sinTheta = 0 exactly, so H == N and every sample fetches the same texels
-  // with the same weight (PreFilterEnvMap.comp:139-161 runs all 10000 regardless). One pass of the lanes gives the same
-  // quotient acc / totalWeight to within fp32 summation noise; a sample whose xi1 is exactly 1 is NaN and skipped as in
-  // the reference.
-  const int sampleEnd = (I.roughness == 0.0f) ? min(I.numSamples, LANES) : I.numSamples;
+  // with the same weight (PreFilterEnvMap.comp:139-161 runs all 10000 regardless): the quotient acc / totalWeight is that
+  // one sample. A sample whose xi1 is exactly 1 is NaN and skipped as in the reference, so each lane stops after its first
+  // VALID sample.
+  const int sampleEnd = I.numSamples;
   for (int i = lane; i < sampleEnd; i += LANES) {
     float xi0, xi1;
     if (I.sequence == ALTHEA_IBL_SEQ_REFERENCE_HASH) {
@@ -133,26 +199,35 @@ template <int LANES> __global__ void __launch_bounds__(256) ibl_prefilter_kernel
       xi0 = rng.next();
       xi1 = rng.next();
     } else {
-      xi0 = (float)i / fN;
+      xi0 = (float)i * rcpN;
       xi1 = (float)__brev((uint32_t)i) * 2.3283064365386963e-10f;
     }
-    float phi = 2.0f * kPi * xi0;
-    float cosTheta = sqrtf((1.0f - xi1) / (1.0f + (a2 - 1.0f) * xi1));
-    float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
-    V3 H = frameApply(tbn, mk3(cosf(phi) * sinTheta, sinf(phi) * sinTheta, cosTheta));
-    V3 Lraw = (2.0f * dot3(V, H)) * H - V;
-    V3 L = Lraw / sqrtf(dot3(Lraw, Lraw));
-    float NdotL = fmaxf(dot3(N, L), 0.0f); // NaN (xi1 == 1 at roughness 0) -> 0: the sample is skipped
-    float NdotH = fmaxf(dot3(N, H), 0.0f);
-    float HdotV = fmaxf(dot3(H, V), 0.0f);
-    float denom = NdotH * NdotH * (a2 - 1.0f) + 1.0f;
-    float D = a2 / (kPi * denom * denom);
-    float pdf = D * NdotH / (4.0f * HdotV + 0.00001f);
-    float saSample = 1.0f / (fN * pdf + 0.0001f);
-    float mipLevel = I.roughness == 0.0f ? 0.0f : 0.5f * log2f(saSample / saTexel);
+    // phi = 2 pi xi0 in [0, 2 pi]: evaluate sin/cos at phi - pi in [-pi, pi] (MUFU range) and flip the signs
+    float sinPhi, cosPhi;
+    __sincosf(fmaf(xi0, 2.0f * kPi, -kPi), &sinPhi, &cosPhi);
+    sinPhi = -sinPhi;
+    cosPhi = -cosPhi;
+    // cos^2 = (1 - xi) / (1 + (a2 - 1) xi), hence sin^2 = a2 xi / (1 + (a2 - 1) xi): formed directly, because
+    // sqrt(1 - cos^2) (PreFilterEnvMap.comp:88-89) would amplify the reciprocal's last-bit error near cos = 1
+    const float rden = rcpf(fmaf(a2 - 1.0f, xi1, 1.0f));
+    const float cosTheta = fsqrt((1.0f - xi1) * rden); // 0 * inf = NaN at roughness 0, xi1 == 1: sample skipped below, as the reference's 0/0
+    const float sinTheta = fsqrt(a2 * xi1 * rden);
+    const V3 H = frameApply(tbn, mk3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
+    const float VdotH = dot3(V, H); // V == N (PreFilterEnvMap.comp:133-135), so NdotH == HdotV == max(VdotH, 0)
+    const V3 Lraw = (2.0f * VdotH) * H - V;
+    const V3 L = Lraw * rsqrt_fast(dot3(Lraw, Lraw));
+    const float NdotL = fmaxf(dot3(N, L), 0.0f); // NaN -> 0: skipped
+    const float NdotH = fmaxf(VdotH, 0.0f);
+    const float denom = fmaf(NdotH * NdotH, a2 - 1.0f, 1.0f);
+    const float D = a2 * rcpf(kPi * denom * denom);
+    const float pdf = D * NdotH * rcpf(fmaf(4.0f, NdotH, 0.00001f));
+    const float saSample = rcpf(fmaf(fN, pdf, 0.0001f));
+    const float mipLevel = I.roughness == 0.0f ? 0.0f : 0.5f * (lg2_fast(saSample) - lg2SaTexel);
     if (NdotL > 0.0f) {
-      acc = acc + sampleEnvMapPrecompute(I.env, L, mipLevel) * NdotL;
+      const V3 e = sampleEnvMapPrecompute(I.env, L, mipLevel);
+      acc = mk3(fmaf(e.x, NdotL, acc.x), fmaf(e.y, NdotL, acc.y), fmaf(e.z, NdotL, acc.z));
       totalWeight += NdotL;
+      if (I.roughness == 0.0f) break;
     }
   }
   V4 r = laneReduce<LANES>(mk4(acc.x, acc.y, acc.z, totalWeight));
@@ -218,7 +293,7 @@ void launch_ibl_prefilter(const IblParams& I, cudaStream_t s) {
   long long texels = (long long)I.out.w * I.out.h;
   // Hash RNG: neighbouring texels draw unrelated directions, so there is no coherence to lose by giving every texel a
   // warp. Hammersley: all texels share the sequence, so one thread per texel keeps a warp's taps adjacent.
-  if (I.sequence == ALTHEA_IBL_SEQ_HAMMERSLEY && texels >= kThreadPerTexelMin) ibl_prefilter_kernel<1><<<linearGrid(texels), 256, 0, s>>>(I);
+  if (I.roughness == 0.0f || (I.sequence == ALTHEA_IBL_SEQ_HAMMERSLEY && texels >= kThreadPerTexelMin)) ibl_prefilter_kernel<1><<<linearGrid(texels), 256, 0, s>>>(I);
   else ibl_prefilter_kernel<32><<<linearGrid(texels * 32), 256, 0, s>>>(I);
 }
 
