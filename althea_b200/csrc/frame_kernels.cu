@@ -287,6 +287,97 @@ __global__ void __launch_bounds__(256) glossy_convolve_kernel(const __grid_const
   rowPtrW<uint2>(C.dst, y)[x] = packHalf4(color);
 }
 
+// Same pass with the source footprint of the tile staged in shared memory by the TMA engine (cp.async.bulk, one bulk copy per
+// source row, completion on an mbarrier: UBLKCP + SYNCS in SASS). A 7-tap blur reads every source texel ~14 times; from shared
+// memory those re-reads cost no L1 tag lookups, and the global side becomes a few hundred fully coalesced row copies per CTA.
+// The arithmetic (coordinates, tap order, lerps) is the direct kernel's, so the results are identical bit for bit.
+// Preconditions (checked by the launcher, which otherwise uses the direct kernel): source width even and level base 16-byte
+// aligned, so that every staged row segment starts and ends on a 16-byte boundary.
+ADEV uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+ADEV void mbarInit(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+ADEV void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+ADEV void bulkCopyG2S(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)), "l"(src), "r"(bytes),
+               "r"(smemAddr(bar))
+               : "memory");
+}
+ADEV void mbarWait(uint64_t* bar, uint32_t phase) {
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra WAIT_%=;\n}\n" ::"r"(smemAddr(bar)), "r"(phase)
+               : "memory");
+}
+
+struct StagedTile { // the staged source window: columns [x0, x0 + cols), rows [y0, y0 + rows) of the source level
+  const uint2* texels;
+  int x0, y0, cols, rows;
+};
+ADEV V4 stagedLoad(const StagedTile& t, int i, int j) { // (i, j) already clamped to the image by the CLAMP_TO_EDGE rule
+  const int ci = min(max(i - t.x0, 0), t.cols - 1), cj = min(max(j - t.y0, 0), t.rows - 1); // memory safety only: the window covers every tap
+  return unpackHalf4(t.texels[cj * t.cols + ci]);
+}
+ADEV V4 bilinearStaged(const StagedTile& t, int w, int h, float u, float v) {
+  BilinearSetup s = bilinearSetup<AddrClamp>(w, h, u, v);
+  V4 t00 = stagedLoad(t, s.i0, s.j0), t10 = stagedLoad(t, s.i1, s.j0);
+  V4 t01 = stagedLoad(t, s.i0, s.j1), t11 = stagedLoad(t, s.i1, s.j1);
+  return mix4(mix4(t00, t10, s.fx), mix4(t01, t11, s.fx), s.fy);
+}
+
+template <int TW, int TH> __global__ void __launch_bounds__(256) glossy_convolve_staged_kernel(const __grid_constant__ ConvolveParams C) {
+  extern __shared__ __align__(128) unsigned char convolveSmem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int w = C.dst.w, h = C.dst.h, ws = C.src.w, hs = C.src.h;
+  const int tx0 = blockIdx.x * TW, ty0 = C.y0 + blockIdx.y * TH;
+  const int tx1 = min(tx0 + TW, w) - 1, ty1 = min(ty0 + TH, C.y1) - 1; // inclusive dst range of this tile
+  const float resolution = (float)w;
+  const float dirx = C.vertical ? 0.0f : 1.0f, diry = C.vertical ? 1.0f : 0.0f;
+  const float a1x = (1.411764705882353f * dirx) / resolution, a1y = (1.411764705882353f * diry) / resolution;
+  const float a2x = (3.2941176470588234f * dirx) / resolution, a2y = (3.2941176470588234f * diry) / resolution;
+  const float a3x = (5.176470588235294f * dirx) / resolution, a3y = (5.176470588235294f * diry) / resolution;
+  // conservative source window: the outermost taps of the tile's corner texels, one texel of slack for rounding, clamped to
+  // the image (taps beyond the edge clamp onto it), columns widened to even bounds (16-byte row segments)
+  StagedTile T;
+  {
+    const float uLo = (float)tx0 / (float)w - a3x, uHi = (float)tx1 / (float)w + a3x;
+    const float vLo = (float)ty0 / (float)h - a3y, vHi = (float)ty1 / (float)h + a3y;
+    int xLo = (int)floorf(uLo * (float)ws - 0.5f) - 1, xHi = (int)floorf(uHi * (float)ws - 0.5f) + 2;
+    int yLo = (int)floorf(vLo * (float)hs - 0.5f) - 1, yHi = (int)floorf(vHi * (float)hs - 0.5f) + 2;
+    xLo = max(xLo, 0) & ~1;
+    xHi = min(xHi, ws - 1) | 1; // ws is even, so xHi | 1 <= ws - 1
+    yLo = max(yLo, 0);
+    yHi = min(yHi, hs - 1);
+    T.x0 = xLo; T.y0 = yLo; T.cols = xHi - xLo + 1; T.rows = yHi - yLo + 1;
+    T.texels = reinterpret_cast<const uint2*>(convolveSmem);
+  }
+  if (threadIdx.x == 0) mbarInit(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x < 32) { // one warp issues the row copies (a few per lane), lane 0 arms the barrier with the byte count first
+    const uint32_t rowBytes = (uint32_t)T.cols * 8u;
+    if (threadIdx.x == 0) mbarExpectTx(&bar, rowBytes * (uint32_t)T.rows);
+    __syncwarp();
+    for (int r = threadIdx.x; r < T.rows; r += 32)
+      bulkCopyG2S(convolveSmem + (size_t)r * rowBytes, rowPtr<uint2>(C.src, T.y0 + r) + T.x0, rowBytes, &bar);
+  }
+  mbarWait(&bar, 0);
+  for (int k = threadIdx.x; k < TW * TH; k += 256) {
+    const int x = tx0 + (k % TW), y = ty0 + (k / TW);
+    if (x >= w || y >= C.y1) continue;
+    const float u = (float)x / (float)w, v = (float)y / (float)h; // texelPos / size, no half texel
+    V4 color = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    color = color + bilinearStaged(T, ws, hs, u, v) * 0.1964825501511404f;
+    color = color + bilinearStaged(T, ws, hs, u + a1x, v + a1y) * 0.2969069646728344f;
+    color = color + bilinearStaged(T, ws, hs, u - a1x, v - a1y) * 0.2969069646728344f;
+    color = color + bilinearStaged(T, ws, hs, u + a2x, v + a2y) * 0.09447039785044732f;
+    color = color + bilinearStaged(T, ws, hs, u - a2x, v - a2y) * 0.09447039785044732f;
+    color = color + bilinearStaged(T, ws, hs, u + a3x, v + a3y) * 0.010381362401148057f;
+    color = color + bilinearStaged(T, ws, hs, u - a3x, v - a3y) * 0.010381362401148057f;
+    rowPtrW<uint2>(C.dst, y)[x] = packHalf4(color);
+  }
+}
+
 // ---- SSAO -----------------------------------------------------------------------------------------------------------
 // computeSSAO (SSAO.glsl:31-84) counts, per pixel, the rays (24) whose 12-step screen-space march over the POSITION
 // G-buffer finds an occluder. Each march step is one bilinear RGBA32F tap whose location is effectively random over a
@@ -625,7 +716,33 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const __grid_consta
 static inline dim3 tileGrid(int w, int h) { return dim3((unsigned)((w + 15) / 16), (unsigned)((h + 15) / 16)); }
 
 void launch_ssr_capture(const FrameParams& P, cudaStream_t s) { ssr_capture_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
-void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s) { glossy_convolve_kernel<<<tileGrid(C.dst.w, C.y1 - C.y0), 256, 0, s>>>(C); }
+// shared-memory bytes of the largest source window a TW x TH tile can need (mirrors the kernel's window computation)
+static size_t stagedWindowBytes(const ConvolveParams& C, int TW, int TH) {
+  const double rx = (double)C.src.w / C.dst.w, ry = (double)C.src.h / C.dst.h;
+  const double offx = C.vertical ? 0.0 : 5.176470588235294 * C.src.w / C.dst.w, offy = C.vertical ? 5.176470588235294 * C.src.h / C.dst.w : 0.0;
+  const size_t cols = (size_t)(TW * rx + 2.0 * offx) + 8, rows = (size_t)(TH * ry + 2.0 * offy) + 6;
+  return cols * rows * 8;
+}
+void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s) {
+  constexpr int VW = 32, VH = 32, HW = 64, HH = 16; // vertical passes want tall tiles (halo in y), horizontal ones wide tiles
+  const bool aligned = (C.src.w % 2 == 0) && ((uintptr_t)C.src.ptr % 16 == 0) && (C.src.pitch % 16 == 0);
+  const size_t smem = C.vertical ? stagedWindowBytes(C, VW, VH) : stagedWindowBytes(C, HW, HH);
+  const bool big = (long long)C.dst.w * (C.y1 - C.y0) >= 64 * 64; // tiny levels: launch latency dominates, nothing to stage
+  if (aligned && big && smem <= 96 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(glossy_convolve_staged_kernel<VW, VH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(glossy_convolve_staged_kernel<HW, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr = true;
+    }
+    if (C.vertical)
+      glossy_convolve_staged_kernel<VW, VH><<<dim3((unsigned)((C.dst.w + VW - 1) / VW), (unsigned)((C.y1 - C.y0 + VH - 1) / VH)), 256, smem, s>>>(C);
+    else
+      glossy_convolve_staged_kernel<HW, HH><<<dim3((unsigned)((C.dst.w + HW - 1) / HW), (unsigned)((C.y1 - C.y0 + HH - 1) / HH)), 256, smem, s>>>(C);
+    return;
+  }
+  glossy_convolve_kernel<<<tileGrid(C.dst.w, C.y1 - C.y0), 256, 0, s>>>(C);
+}
 void launch_ssao(const FrameParams& P, cudaStream_t s) {
   ssao_kernel<<<dim3((unsigned)((P.W + kSsaoTileW - 1) / kSsaoTileW), (unsigned)((P.y1 - P.y0 + kSsaoTileH - 1) / kSsaoTileH)), 256, 0, s>>>(P);
 }

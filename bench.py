@@ -205,7 +205,19 @@ def build_rank_inputs(ctx, rank: int, views: int, device: str, quick_ibl: bool =
     else:
         engine.ImageBasedLighting.precomputeResources(ctx, chain, irr_small, pre)
     ctx.synchronize()
-    ibl_t = ctx.timings()
+    ibl_t = {"reference_shape": {k: v["total_ms"] for k, v in ctx.timings().items()}}
+    if not quick_ibl and views > 0 and rank == 0:
+        # BASELINE configs[1]: 32^2 diffuse irradiance cube + 512^2 6-mip GGX prefilter cube (Hammersley, 10000 samples) + 512^2 BRDF LUT
+        prec = ctx.new_image(F32, 512, 512, 6, 6)
+        irrc = ctx.new_image(F32, 32, 32, 1, 6)
+        lutc = ctx.new_image(_capi.FORMAT_R8G8B8A8_UNORM, 512, 512)
+        for timed in (False, True):
+            ctx.reset_timings()
+            engine.ImageBasedLighting.precomputeResources(ctx, chain, irrc, prec, layout=_capi.IBL_LAYOUT_CUBE, sequence=_capi.IBL_SEQ_HAMMERSLEY)
+            engine.ImageBasedLighting.generateBrdfLut(ctx, lutc, 1024)
+            ctx.synchronize()
+        ibl_t["config1_cube"] = {k: v["total_ms"] for k, v in ctx.timings().items()}
+        del prec, irrc, lutc
     ctx.enable_timing(False)
     ctx.reset_timings()
     # the reference keeps a full-size irradiance image (ImageBasedLighting.cpp:534-568): same footprint, upsampled content
@@ -489,8 +501,12 @@ def main():
                                                                                                       % (V * px_frame * 36 / 1e9),
                            "math": "fast build (FFMA); parity build checked in tests"},
                 "gpu_launches": int(launches) * world, "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_chain": chain, "stages": stages,
-                "ibl_precompute_ms": {k: v["total_ms"] for k, v in ibl_t.items()},
-                "ibl_config": "reference shape: %dx%d equirect env, 5 GGX mips (2048x1024..128x64), 10000 samples/texel, hash RNG" % (ENV_W, ENV_H)}
+                "ibl_prefilter_ms": ibl_t.get("config1_cube", {}).get("ibl_prefilter"),
+                "ibl_precompute_ms": ibl_t,
+                "ibl_config": {"config1_cube": "BASELINE configs[1]: %dx%d equirect env -> 32^2 irradiance cube (300x150 samples) + 512^2 6-mip GGX prefilter cube "
+                                               "(10000 Hammersley samples/texel) + 512^2 BRDF LUT (1024 samples); second of two runs" % (ENV_W, ENV_H),
+                               "reference_shape": "the reference's own layout: 5 equirect GGX mips 2048x1024..128x64, 10000 hash-RNG samples/texel; irradiance "
+                                                  "at 512x256 (the reference's 4096x2048 irradiance is 64x the work)"}}
         if not args.no_cpu_baseline:
             from oracle import oracle as O
             O.build()
