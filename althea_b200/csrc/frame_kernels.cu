@@ -456,13 +456,34 @@ __global__ void __launch_bounds__(256) ssao_exact_kernel(const __grid_constant__
 }
 
 // -- proxy records ------------------------------------------------------------------------------------------------------
+// 32 bytes per bilinear footprint: p00 (3 x fp32) and five words that each carry TWO coefficients of
+//   bilinear(fx, fy) = p00 + A fx + B fy + C fx fy,  A = p10 - p00, B = p01 - p00, C = (p11 - p10) - (p01 - p00):
+//   word 3: A.x | B.y   word 4: A.y | B.z   word 5: A.z | C.x   word 6: B.x | C.y   word 7: T | C.z
+// The low half is an fp16 (one HADD2.F32 to unpack). The high-half coefficient needs NO unpacking: the march uses the whole
+// 32-bit word as an fp32 value; the pre-pass picks the upper 16 bits so that this value (low half included) is the closest
+// one to the coefficient, i.e. a bf16-grade coefficient whose exact decoded value is known when the error bound is computed.
+// T (rounded up) = 2 (sqrt(3) E + slop * max|p|_1 + tiny): everything of the sign-decision threshold that does not depend
+// on the shaded pixel, E being the bound on the per-component error of the decoded polynomial against the four fp32 texels.
 struct __align__(32) QuadRecord { uint32_t w[8]; };
 
-ADEV uint32_t packHalf2(__half a, __half b) {
-  __half2 h = __halves2half2(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+constexpr float kSqrt3Up = 1.7320509f;
+// fp32 rounding slop, as a multiple of the coordinate magnitude in play: both the restatement's evaluation and the
+// proxy's are within a few ulp of real arithmetic (two lerp levels, a subtraction, a 3-term dot product); 64 ulp is generous
+constexpr float kRoundSlop = 64.0f * 1.1920929e-7f;
+constexpr float kTiny = 1e-15f; // decisions on |value| <= kTiny are always re-evaluated (products must not underflow)
+
+ADEV uint32_t halfBits(float v) { return (uint32_t)__half_as_ushort(__float2half_rn(v)); }
+ADEV float lowHalfToFloat(uint32_t w) { return __low2float(*reinterpret_cast<const __half2*>(&w)); }
+// word with low half `lo` whose value as an fp32 is as close to `target` as the 16 free bits allow (floats of one sign are
+// ordered like their bit patterns, so the nearest pattern is at most half a bf16 step away)
+ADEV uint32_t hiWord(float target, uint32_t lo) {
+  const uint32_t t = __float_as_uint(target);
+  uint32_t w = (t & 0xffff0000u) | lo;
+  const int d = (int)lo - (int)(t & 0xffffu);
+  if (d > 0x8000 && (t & 0x7fff0000u) != 0u) w -= 0x10000u;
+  else if (d < -0x8000) w += 0x10000u; // may reach inf / NaN: caught by the finite check of the decoded value
+  return w;
 }
-ADEV float2 unpackHalf2(uint32_t w) { return __half22float2(*reinterpret_cast<__half2*>(&w)); }
 
 __global__ void __launch_bounds__(256) ssao_quads_kernel(const __grid_constant__ FrameParams P) {
   const int qx = blockIdx.x * 32 + (threadIdx.x & 31); // record column = ix + 1
@@ -472,25 +493,34 @@ __global__ void __launch_bounds__(256) ssao_quads_kernel(const __grid_constant__
   const int j0 = AddrClamp::wrap(qy - 1, P.H), j1 = AddrClamp::wrap(qy, P.H);
   const V4 p00 = FmtRGBA32F::load(P.position, i0, j0), p10 = FmtRGBA32F::load(P.position, i1, j0);
   const V4 p01 = FmtRGBA32F::load(P.position, i0, j1), p11 = FmtRGBA32F::load(P.position, i1, j1);
-  // bilinear(fx, fy) = p00 + A fx + B fy + C fx fy with A = p10 - p00, B = p01 - p00, C = (p11 - p10) - (p01 - p00)
   const float b[3] = {p00.x, p00.y, p00.z};
   const float t10[3] = {p10.x, p10.y, p10.z}, t01[3] = {p01.x, p01.y, p01.z}, t11[3] = {p11.x, p11.y, p11.z};
-  __half hA[3], hB[3], hC[3];
+  float A[3], B[3], C[3], U[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    A[c] = __fsub_rn(t10[c], b[c]);
+    B[c] = __fsub_rn(t01[c], b[c]);
+    U[c] = __fsub_rn(t11[c], t10[c]);
+    C[c] = __fsub_rn(U[c], B[c]);
+  }
+  // low halves first (their bits are part of the high-half values), then the high-half words around them
+  const uint32_t lBy = halfBits(B[1]), lBz = halfBits(B[2]), lCx = halfBits(C[0]), lCy = halfBits(C[1]), lCz = halfBits(C[2]);
+  const uint32_t w3 = hiWord(A[0], lBy), w4 = hiWord(A[1], lBz), w5 = hiWord(A[2], lCx), w6 = hiWord(B[0], lCy);
+  const float dA[3] = {__uint_as_float(w3), __uint_as_float(w4), __uint_as_float(w5)};
+  const float dB[3] = {__uint_as_float(w6), lowHalfToFloat(lBy), lowHalfToFloat(lBz)};
+  const float dC[3] = {lowHalfToFloat(lCx), lowHalfToFloat(lCy), lowHalfToFloat(lCz)};
   float E = 0.0f;
   bool finite = true;
   constexpr float kUlp = 6.0e-8f; // 2^-24 rounded up: |fl(a - b) - (a - b)| <= 2^-24 |fl(a - b)|
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float A = __fsub_rn(t10[c], b[c]), B = __fsub_rn(t01[c], b[c]);
-    const float U = __fsub_rn(t11[c], t10[c]);
-    const float C = __fsub_rn(U, B);
-    hA[c] = __float2half_rn(A); hB[c] = __float2half_rn(B); hC[c] = __float2half_rn(C);
-    const float bA = __half2float(hA[c]), bB = __half2float(hB[c]), bC = __half2float(hC[c]);
-    finite = finite && isfinite(b[c]) && isfinite(t10[c]) && isfinite(t01[c]) && isfinite(t11[c]) && isfinite(bA) && isfinite(bB) && isfinite(bC);
-    // storage error of each coefficient (the half -> float differences are exact in fp32) + rounding of the fp32
-    // differences themselves; fx, fy, fx*fy <= 1, so the sum bounds the error anywhere in the footprint
-    float e = __fadd_ru(__fadd_ru(fabsf(__fsub_rn(bA, A)), fabsf(__fsub_rn(bB, B))), fabsf(__fsub_rn(bC, C)));
-    const float mags = __fadd_ru(__fadd_ru(fabsf(A), __fmul_ru(2.0f, fabsf(B))), __fadd_ru(fabsf(U), fabsf(C)));
+    finite = finite && isfinite(b[c]) && isfinite(t10[c]) && isfinite(t01[c]) && isfinite(t11[c]) && isfinite(dA[c]) && isfinite(dB[c]) && isfinite(dC[c]);
+    // storage error of each coefficient + rounding of the fp32 differences themselves; fx, fy, fx*fy <= 1, so the sum
+    // bounds the error anywhere in the footprint
+    float e = fmaxf(fabsf(__fsub_ru(dA[c], A[c])), fabsf(__fsub_rd(dA[c], A[c])));
+    e = __fadd_ru(e, fmaxf(fabsf(__fsub_ru(dB[c], B[c])), fabsf(__fsub_rd(dB[c], B[c]))));
+    e = __fadd_ru(e, fmaxf(fabsf(__fsub_ru(dC[c], C[c])), fabsf(__fsub_rd(dC[c], C[c]))));
+    const float mags = __fadd_ru(__fadd_ru(fabsf(A[c]), __fmul_ru(2.0f, fabsf(B[c]))), __fadd_ru(fabsf(U[c]), fabsf(C[c])));
     e = __fadd_ru(e, __fmul_ru(mags, kUlp));
     // the restatement's own fp32 lerps round relative to the texel MAGNITUDES; covered here for texels much larger than the
     // interpolated value (the tap-side slop scales with the interpolated value only)
@@ -498,12 +528,22 @@ __global__ void __launch_bounds__(256) ssao_quads_kernel(const __grid_constant__
     E = fmaxf(E, e);
   }
   E = __fadd_ru(__fmul_ru(E, 1.0001f), 1e-30f);
-  const __half Eh = finite ? __float2half_ru(E) : __ushort_as_half((unsigned short)0x7c00u); // +inf => always re-evaluate exactly
-  // words: base.xyz | (A.x, A.y) | (A.z, B.x) | (B.y, B.z) | (C.x, C.y) | (C.z, E)
+  // bound of |p|_1 anywhere in the footprint: a convex combination of the corners, plus the proxy's own deviation
+  float M = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const V4 q = k == 0 ? p00 : k == 1 ? p10 : k == 2 ? p01 : p11;
+    M = fmaxf(M, __fadd_ru(__fadd_ru(fabsf(q.x), fabsf(q.y)), fabsf(q.z)));
+  }
+  M = __fadd_ru(M, __fmul_ru(3.0f, E));
+  const float T = __fmul_ru(2.0f, __fadd_ru(__fmul_ru(E, kSqrt3Up), __fadd_ru(__fmul_ru(M, kRoundSlop), kTiny)));
+  finite = finite && isfinite(T);
+  // T rounded UP to the next bf16 step; +inf (or NaN, with the low half) => the tap is always re-evaluated exactly
+  const uint32_t w7 = (finite ? ((__float_as_uint(T) >> 16) + 1u) << 16 : 0x7f800000u) | lCz;
   QuadRecord* row = reinterpret_cast<QuadRecord*>(const_cast<char*>(static_cast<const char*>(P.quads)) + (size_t)qy * P.quadPitch);
   uint4* dst = reinterpret_cast<uint4*>(row + qx);
-  dst[0] = make_uint4(__float_as_uint(b[0]), __float_as_uint(b[1]), __float_as_uint(b[2]), packHalf2(hA[0], hA[1]));
-  dst[1] = make_uint4(packHalf2(hA[2], hB[0]), packHalf2(hB[1], hB[2]), packHalf2(hC[0], hC[1]), packHalf2(hC[2], Eh));
+  dst[0] = make_uint4(__float_as_uint(b[0]), __float_as_uint(b[1]), __float_as_uint(b[2]), w3);
+  dst[1] = make_uint4(w4, w5, w6, w7);
 }
 
 ADEV QuadRecord loadQuad(const void* p) { // one 256-bit load: LDG.E.ENL2.256 on sm_100a
@@ -515,8 +555,8 @@ ADEV QuadRecord loadQuad(const void* p) { // one 256-bit load: LDG.E.ENL2.256 on
 }
 
 struct ProxyTap {
-  V3 pos;    // interpolated position, within `err` per component of the real-arithmetic bilinear value
-  float err; // storage error bound E of the record
+  V3 pos;       // interpolated position, within E per component of the real-arithmetic bilinear value
+  float twoTol; // the record's T
 };
 // (u, v) has passed outside01: x is in [-0.5, W - 0.5], so floor(x) + 1 is a valid record column without clamping. A NaN
 // coordinate converts to column 1 and yields NaN weights, hence a NaN position, which the caller re-evaluates exactly.
@@ -533,13 +573,14 @@ ADEV ProxyAddr proxyAddr(const FrameParams& P, float u, float v) {
   return a;
 }
 ADEV ProxyTap proxyEval(const QuadRecord& r, float fx, float fy) {
-  const float2 a = unpackHalf2(r.w[3]), b = unpackHalf2(r.w[4]), c = unpackHalf2(r.w[5]), d = unpackHalf2(r.w[6]), e = unpackHalf2(r.w[7]);
-  // A = (a.x, a.y, b.x), B = (b.y, c.x, c.y), C = (d.x, d.y, e.x), E = e.y
+  const float ax = __uint_as_float(r.w[3]), ay = __uint_as_float(r.w[4]), az = __uint_as_float(r.w[5]), bx = __uint_as_float(r.w[6]);
+  const float by = lowHalfToFloat(r.w[3]), bz = lowHalfToFloat(r.w[4]), cx = lowHalfToFloat(r.w[5]), cy = lowHalfToFloat(r.w[6]),
+              cz = lowHalfToFloat(r.w[7]);
   ProxyTap t;
-  t.pos.x = fmaf(fmaf(d.x, fy, a.x), fx, fmaf(b.y, fy, __uint_as_float(r.w[0])));
-  t.pos.y = fmaf(fmaf(d.y, fy, a.y), fx, fmaf(c.x, fy, __uint_as_float(r.w[1])));
-  t.pos.z = fmaf(fmaf(e.x, fy, b.x), fx, fmaf(c.y, fy, __uint_as_float(r.w[2])));
-  t.err = e.y;
+  t.pos.x = fmaf(fmaf(cx, fy, ax), fx, fmaf(bx, fy, __uint_as_float(r.w[0])));
+  t.pos.y = fmaf(fmaf(cy, fy, ay), fx, fmaf(by, fy, __uint_as_float(r.w[1])));
+  t.pos.z = fmaf(fmaf(cz, fy, az), fx, fmaf(bz, fy, __uint_as_float(r.w[2])));
+  t.twoTol = __uint_as_float(r.w[7]);
   return t;
 }
 
@@ -556,98 +597,102 @@ __device__ __noinline__ bool facesRay(const FrameParams& P, float cu, float cv, 
   return dot3(currentNormal, rayDir) < 0.0f;
 }
 
-constexpr float kSqrt3Up = 1.7320509f;
-// fp32 rounding slop, as a multiple of the coordinate magnitude in play: both the restatement's evaluation and the
-// proxy's are within a few ulp of real arithmetic (two lerp levels, a subtraction, a 3-term dot product); 64 ulp is generous
-constexpr float kRoundSlop = 64.0f * 1.1920929e-7f;
-constexpr float kTiny = 1e-15f; // decisions on |value| <= kTiny are always re-evaluated (products must not underflow)
-
 #ifndef ALTHEA_SSAO_UNROLL
 #define ALTHEA_SSAO_UNROLL 2
 #endif
 constexpr int kSsaoUnroll = ALTHEA_SSAO_UNROLL;
+// sign-decided value: v shrunk towards zero by its tolerance; 0 <=> the sign of the exact value is not known
+ADEV float decided(float v, float twoTol) { return copysignf(fmaxf(fabsf(v) - twoTol, 0.0f), v); }
+ADEV float decidedExact(float v) { return fabsf(v) > kTiny ? v : 0.0f; }
+
 ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float v0, V3 worldPos, V3 normal) {
   HashRng rng;
   rng.sx = (uint32_t)px;
   rng.sy = (uint32_t)py;
   const TangentFrame tbn = localToWorld(normal);
-  const float posMag = fabsf(worldPos.x) + fabsf(worldPos.y) + fabsf(worldPos.z);
+  // the shaded pixel's share of the threshold: 2 * slop * |worldPos|_1 (a hair more: the sum below is rounded to nearest)
+  const float posSlop2 = (2.002f * kRoundSlop) * (fabsf(worldPos.x) + fabsf(worldPos.y) + fabsf(worldPos.z));
   int ao = 0;
   for (int ray = 0; ray < 24; ++ray) {
     float x0 = rng.next(), x1 = rng.next(), x2 = rng.next();
     V3 rayDir = frameApply(tbn, normalize3(mk3(2.0f * x0 - 1.0f, 2.0f * x1 - 1.0f, x2)));
     V2 uvEnd = projectUv(P, worldPos + rayDir * 0.5f);
     V3 perpRef = normalize3(cross3(cross3(rayDir, normal), rayDir));
-    // previous step: value, tolerance (|exact - value| <= tol, also the position tolerance), whether its sign is decided,
-    // whether it IS the exact fp32 value
+    // taps before the ray leaves the screen (SSAO.glsl:50). Tap i sits at a(1 - t) + b t with t = i / 12 and a = this pixel's
+    // centre, strictly inside (0, 1): when the end point b is inside [0, 1] too, so is every rounded tap coordinate
+    // (a(1 - t) + b t <= 1 - (1 - a)/12, far more than the two roundings), and no tap needs the test.
+    int n = 12;
+    if (outside01(uvEnd.x, uvEnd.y)) {
+      n = 1;
+      while (n < 12 && !outside01(marchCoord(u0, uvEnd.x, n), marchCoord(v0, uvEnd.y, n))) ++n;
+    }
+    // projection of the proxy position: dot(p, perpRef) - dot(worldPos, perpRef), within a few ulp of |p|_1 + |worldPos|_1
+    // of the restatement's dot(p - worldPos, perpRef) (covered by the slop in T and posSlop2)
+    const float projBias = fmaf(worldPos.z, perpRef.z, fmaf(worldPos.y, perpRef.y, worldPos.x * perpRef.x));
+    // previous step: position, projection, its threshold (0 <=> the value IS the restatement's fp32 value) and its
+    // sign-decided form
     V3 prevPos = worldPos;
-    float prevProjection = 0.0f, prevTol = 0.0f;
-    bool prevSure = false, prevExact = true;
+    float prevProjection = 0.0f, prevTwoTol = 0.0f, prevDecided = 0.0f;
 #pragma unroll kSsaoUnroll
-    for (int i = 1; i < 12; ++i) {
+    for (int i = 1; i < n; ++i) {
       const float cu = marchCoord(u0, uvEnd.x, i), cv = marchCoord(v0, uvEnd.y, i);
-      if (outside01(cu, cv)) break;
       const ProxyAddr pa = proxyAddr(P, cu, cv);
       const ProxyTap tap = proxyEval(loadQuad(pa.rec), pa.fx, pa.fy);
-      {
       V3 curPos = tap.pos;
-      float curProjection = dot3(curPos - worldPos, perpRef);
-      const float mag = posMag + (fabsf(curPos.x) + fabsf(curPos.y) + fabsf(curPos.z));
-      float curTol = fmaf(tap.err, kSqrt3Up, fmaf(mag, kRoundSlop, kTiny)); // inf / NaN when the record is flagged
-      bool curSure = fabsf(curProjection) > 2.0f * curTol;
-      bool curExact = false;
-      bool flip = false; // i == 1: prevProjection is exactly 0, the product is +-0 (or NaN), never < 0
-      if (i > 1) {
-        if (curSure && prevSure) {
-          flip = (curProjection < 0.0f) != (prevProjection < 0.0f);
-        } else {
-          const float pu = marchCoord(u0, uvEnd.x, i - 1), pv = marchCoord(v0, uvEnd.y, i - 1);
-          if (!curSure) {
-            ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
-            curPos = e.pos; curProjection = e.projection; curTol = 0.0f; curExact = true;
-            curSure = fabsf(curProjection) > kTiny;
+      float curProjection = fmaf(curPos.z, perpRef.z, fmaf(curPos.y, perpRef.y, fmaf(curPos.x, perpRef.x, -projBias)));
+      float curTwoTol = tap.twoTol + posSlop2; // inf / NaN when the record is flagged
+      float curDecided = decided(curProjection, curTwoTol);
+      // common case: both signs decided and equal (no crossing). Everything else: the first tap (previous projection exactly
+      // 0: the product is +-0 or NaN, never < 0), a crossing, or a value too close to 0 for the proxy to call
+      if (!(__fmul_rn(curDecided, prevDecided) > 0.0f)) {
+        if (i > 1) {
+          bool flip;
+          if (curDecided != 0.0f && prevDecided != 0.0f) {
+            flip = (curProjection < 0.0f) != (prevProjection < 0.0f); // also a same-sign product that underflowed
+          } else {
+            const float pu = marchCoord(u0, uvEnd.x, i - 1), pv = marchCoord(v0, uvEnd.y, i - 1);
+            if (curDecided == 0.0f) {
+              ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
+              curPos = e.pos; curProjection = e.projection; curTwoTol = 0.0f; curDecided = decidedExact(curProjection);
+            }
+            if (prevDecided == 0.0f && prevTwoTol != 0.0f) {
+              ExactTap e = exactTap(P, pu, pv, worldPos, perpRef);
+              prevPos = e.pos; prevProjection = e.projection; prevTwoTol = 0.0f; prevDecided = decidedExact(prevProjection);
+            }
+            // a value at most kTiny in magnitude can push the fp32 product into underflow: then both factors must be exact
+            if (curDecided == 0.0f && prevTwoTol != 0.0f) {
+              ExactTap e = exactTap(P, pu, pv, worldPos, perpRef);
+              prevPos = e.pos; prevProjection = e.projection; prevTwoTol = 0.0f; prevDecided = decidedExact(prevProjection);
+            }
+            if (prevDecided == 0.0f && curTwoTol != 0.0f) {
+              ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
+              curPos = e.pos; curProjection = e.projection; curTwoTol = 0.0f; curDecided = decidedExact(curProjection);
+            }
+            flip = __fmul_rn(curProjection, prevProjection) < 0.0f;
           }
-          if (!prevSure && !prevExact) {
-            ExactTap e = exactTap(P, pu, pv, worldPos, perpRef);
-            prevPos = e.pos; prevProjection = e.projection; prevTol = 0.0f; prevExact = true;
-            prevSure = fabsf(prevProjection) > kTiny;
+          if (flip) {
+            // worldStep = length(currentPos - prevPos) <= 2.0; each threshold covers twice its position tolerance
+            const float worldStep = length3(curPos - prevPos);
+            const float tol = curTwoTol + prevTwoTol;
+            bool near;
+            if (worldStep + tol <= 2.0f) near = true;
+            else if (worldStep - tol > 2.0f) near = false;
+            else {
+              if (curTwoTol != 0.0f) {
+                ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
+                curPos = e.pos; curProjection = e.projection; curTwoTol = 0.0f; curDecided = decidedExact(curProjection);
+              }
+              if (prevTwoTol != 0.0f) prevPos = exactTap(P, marchCoord(u0, uvEnd.x, i - 1), marchCoord(v0, uvEnd.y, i - 1), worldPos, perpRef).pos;
+              near = length3(curPos - prevPos) <= 2.0f;
+            }
+            if (near && facesRay(P, cu, cv, rayDir)) {
+              ao += 1;
+              break;
+            }
           }
-          // a value at most kTiny in magnitude can push the fp32 product into underflow: then both factors must be exact
-          if (!curSure && !prevExact) {
-            ExactTap e = exactTap(P, pu, pv, worldPos, perpRef);
-            prevPos = e.pos; prevProjection = e.projection; prevTol = 0.0f; prevExact = true;
-          }
-          if (!prevSure && !curExact) {
-            ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
-            curPos = e.pos; curProjection = e.projection; curTol = 0.0f; curExact = true;
-            curSure = fabsf(curProjection) > kTiny;
-          }
-          flip = __fmul_rn(curProjection, prevProjection) < 0.0f;
         }
       }
-      if (flip) {
-        // worldStep = length(currentPos - prevPos) <= 2.0
-        const float worldStep = length3(curPos - prevPos);
-        const float tol = curTol + prevTol; // each covers sqrt(3) * E + rounding slop
-        bool near;
-        if (worldStep + tol <= 2.0f) near = true;
-        else if (worldStep - tol > 2.0f) near = false;
-        else {
-          if (!curExact) {
-            ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
-            curPos = e.pos; curProjection = e.projection; curTol = 0.0f; curExact = true;
-            curSure = fabsf(curProjection) > kTiny;
-          }
-          if (!prevExact) prevPos = exactTap(P, marchCoord(u0, uvEnd.x, i - 1), marchCoord(v0, uvEnd.y, i - 1), worldPos, perpRef).pos;
-          near = length3(curPos - prevPos) <= 2.0f;
-        }
-        if (near && facesRay(P, cu, cv, rayDir)) {
-          ao += 1;
-          break;
-        }
-      }
-      prevPos = curPos; prevProjection = curProjection; prevTol = curTol; prevSure = curSure; prevExact = curExact;
-      }
+      prevPos = curPos; prevProjection = curProjection; prevTwoTol = curTwoTol; prevDecided = curDecided;
     }
   }
   return ao;
