@@ -55,6 +55,9 @@ struct althea_cuda_ctx {
   // internal scratch: SSAO position-quad proxy, (W+1) x (H+1) x 32 B
   void* quadScratch = nullptr;
   size_t quadScratchBytes = 0;
+  // internal scratch: SSR padded depth, (W+2) x (H+2) floats (frame_kernels.cu, ssr_depth_pad_kernel)
+  void* depthPadScratch = nullptr;
+  size_t depthPadScratchBytes = 0;
   // timing
   bool timing = false;
   std::vector<TimingEntry> pending;
@@ -378,6 +381,7 @@ void althea_cuda_destroy(althea_cuda_ctx* ctx) {
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   if (ctx->aoScratch) cudaFree(ctx->aoScratch);
   if (ctx->quadScratch) cudaFree(ctx->quadScratch);
+  if (ctx->depthPadScratch) cudaFree(ctx->depthPadScratch);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -659,9 +663,22 @@ int althea_cuda_ssr_capture(althea_cuda_ctx* ctx, const althea_global_uniforms* 
     P.y0 = (int)lo[0];
     P.y1 = (int)hi[0];
   }
+  { // the padded depth covers the whole frame even under a scissor: a ray may leave the band
+    size_t need = ((size_t)P.W + 2) * ((size_t)P.H + 2) * sizeof(float);
+    if (ctx->depthPadScratchBytes < need) {
+      if (ctx->depthPadScratch) { cudaDeviceSynchronize(); cudaFree(ctx->depthPadScratch); ctx->depthPadScratch = nullptr; ctx->depthPadScratchBytes = 0; }
+      cudaError_t e = cudaMalloc(&ctx->depthPadScratch, need);
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(ssr padded depth %zu): %s", need, cudaGetErrorString(e)); }
+      ctx->depthPadScratchBytes = need;
+    }
+    P.depthPadRow = P.W + 2;
+    P.depthPad = static_cast<const float*>(ctx->depthPadScratch);
+    P.depthPadOrigin = P.depthPad + P.depthPadRow + 1;
+  }
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
   const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
+  timedLaunch(ctx, "ssr_depth_pad", stream, [&] { parity ? althea_parity::launch_ssr_depth_pad(P, stream) : althea_fast::launch_ssr_depth_pad(P, stream); });
   timedLaunch(ctx, "ssr_capture", stream, [&] { parity ? althea_parity::launch_ssr_capture(P, stream) : althea_fast::launch_ssr_capture(P, stream); });
   return endWork(ctx, sync, stream);
 }

@@ -164,6 +164,36 @@ ADEV V2 projectUv(const FrameParams& P, V3 p) { // 0.5 * clip.xy / clip.w + 0.5
 }
 
 // ---- SSR ------------------------------------------------------------------------------------------------------------
+// Padded depth (engine scratch, written by ssr_depth_pad_kernel once per frame): the depth image with a one-texel CLAMP_TO_EDGE
+// border, (W + 2) x (H + 2) floats. The footprint whose top-left tap is texel (ix, iy), ix in [-1, W-1], iy in [-1, H-1], is the
+// 2 x 2 block at padded (ix + 1, iy + 1): a march step needs no clamps and one 32-bit index for its four taps (the clamped
+// four-tap form spends about 30 of its ~100 SASS instructions per step on clamping and 64-bit address arithmetic), and
+// neighbouring lanes still read neighbouring floats. Same texels, same lerps: bit-identical to the clamped form in both builds.
+__global__ void __launch_bounds__(256) ssr_depth_pad_kernel(const __grid_constant__ FrameParams P) {
+  const int qx = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int qy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (qx > P.W + 1 || qy > P.H + 1) return;
+  const float d = __ldg(rowPtr<float>(P.depth, AddrClamp::wrap(qy - 1, P.H)) + AddrClamp::wrap(qx - 1, P.W));
+  const_cast<float*>(P.depthPad)[(size_t)qy * P.depthPadRow + qx] = d;
+}
+struct DepthTap { float t00, t10, t01, t11, fx, fy; };
+// (u, v) has passed outside01, so x is in [-0.5, W - 0.5] and floor(x) is in [-1, W-1] without clamping
+ADEV DepthTap depthTapPadded(const FrameParams& P, float u, float v) {
+  float x = __fsub_rn(__fmul_rn(u, P.Wf), 0.5f), y = __fsub_rn(__fmul_rn(v, P.Hf), 0.5f); // rule A1, never contracted
+#ifdef ALTHEA_PARITY
+  if (!(x == x)) x = 0.0f; // a NaN coordinate is not "outside": the restatement taps texel (0, 0) with zero weights
+  if (!(y == y)) y = 0.0f;
+#endif
+  const int ix = __float2int_rd(x), iy = __float2int_rd(y); // |x| < 2^24: (float)ix == floorf(x) exactly
+  DepthTap q;
+  q.fx = x - (float)ix;
+  q.fy = y - (float)iy;
+  const float* r0 = P.depthPadOrigin + (iy * P.depthPadRow + ix); // origin = &padded(1, 1) = texel (0, 0)
+  const float* r1 = r0 + P.depthPadRow;
+  q.t00 = __ldg(r0); q.t10 = __ldg(r0 + 1); q.t01 = __ldg(r1); q.t11 = __ldg(r1 + 1);
+  return q;
+}
+
 ADEV V4 environmentLitSample(const FrameParams& P, V3 currentPos, float u, float v, V3 rayDir, V3 normal) { // SSR.frag:55-78
   V3 baseColor = xyz(bilinear<FmtRGBA8, AddrClamp>(P.albedo, u, v));
   V3 mro = xyz(bilinear<FmtRGBA8, AddrClamp>(P.mro, u, v));
@@ -200,7 +230,8 @@ __global__ void __launch_bounds__(256) ssr_capture_kernel(const __grid_constant_
       cu += stepX;
       cv += stepY;
       if (outside01(cu, cv)) break;
-      float dRaw = bilinearR32F<AddrClamp>(P.depth, cu, cv);
+      const DepthTap q = depthTapPadded(P, cu, cv);
+      float dRaw = mixf(mixf(q.t00, q.t10, q.fx), mixf(q.t01, q.t11, q.fx), q.fy); // == bilinearR32F<AddrClamp>(P.depth, cu, cv)
       V3 currentPos = reconstructPosition(P, cu, cv, dRaw);
       V3 dir = normalize3(currentPos - worldPos);
       float currentProjection = dot3(dir, perpRef);
@@ -222,28 +253,17 @@ __global__ void __launch_bounds__(256) ssr_capture_kernel(const __grid_constant_
     //    dot(dir, rayDir) > 0.999  <=>  dot(v, rayDir) > 0 and dot(v, rayDir)^2 > 0.999^2 |v|^2.
     const V3 camMinusPos = mk3(P.g.inverseView[12], P.g.inverseView[13], P.g.inverseView[14]) - worldPos;
     const V3 W0 = mk3(P.ssrW0[0], P.ssrW0[1], P.ssrW0[2]), Wu = mk3(P.ssrWu[0], P.ssrWu[1], P.ssrWu[2]), Wv = mk3(P.ssrWv[0], P.ssrWv[1], P.ssrWv[2]);
-    const float* depthBase = static_cast<const float*>(P.depth.ptr);
-    const int depthPitch = P.depth.pitch >> 2; // floats per row
-    const float Wf = (float)P.W, Hf = (float)P.H;
-    const int Wm1 = P.W - 1, Hm1 = P.H - 1;
     for (int i = 0; i < 128; ++i) {
       cu += stepX;
       cv += stepY;
       if (outside01(cu, cv)) break;
-      // bilinear depth tap, CLAMP_TO_EDGE (rule A1/A2); a + t (b - a) lerps
-      const float xf = __fsub_rn(__fmul_rn(cu, Wf), 0.5f), yf = __fsub_rn(__fmul_rn(cv, Hf), 0.5f);
-      const float fx0 = floorf(xf), fy0 = floorf(yf);
-      const float fx = xf - fx0, fy = yf - fy0;
-      const int ix = (int)fx0, iy = (int)fy0;
-      const int i0 = max(ix, 0), i1 = min(ix + 1, Wm1);
-      const float* r0 = depthBase + max(iy, 0) * depthPitch;
-      const float* r1 = depthBase + min(iy + 1, Hm1) * depthPitch;
-      const float t00 = __ldg(r0 + i0), t10 = __ldg(r0 + i1), t01 = __ldg(r1 + i0), t11 = __ldg(r1 + i1);
-      const float top = fmaf(t10 - t00, fx, t00), bot = fmaf(t11 - t01, fx, t01);
-      const float dRaw = fmaf(bot - top, fy, top);
+      // bilinear depth tap, CLAMP_TO_EDGE (rule A1/A2) from the padded copy; a + t (b - a) lerps
+      const DepthTap q = depthTapPadded(P, cu, cv);
+      const float top = fmaf(q.t10 - q.t00, q.fx, q.t00), bot = fmaf(q.t11 - q.t01, q.fx, q.t01);
+      const float dRaw = fmaf(bot - top, q.fy, top);
       // pos - worldPos = (cam - worldPos) + wd * (far near / ((dRaw (far - near) - far) * dot(wd, zAxis)))
       const float den = fmaf(dRaw, 1000.0f - 0.01f, -1000.0f) * fmaf(P.ssrS[1], cu, fmaf(P.ssrS[2], cv, P.ssrS[0]));
-      const float k = __fdividef(1000.0f * 0.01f, den);
+      const float k = (1000.0f * 0.01f) * rcpf(den);
       const V3 wd = mk3(fmaf(Wu.x, cu, fmaf(Wv.x, cv, W0.x)), fmaf(Wu.y, cu, fmaf(Wv.y, cv, W0.y)), fmaf(Wu.z, cu, fmaf(Wv.z, cv, W0.z)));
       const V3 vv = mk3(fmaf(wd.x, k, camMinusPos.x), fmaf(wd.y, k, camMinusPos.y), fmaf(wd.z, k, camMinusPos.z));
       const float len2 = dot3(vv, vv), along = dot3(vv, rayDir);
@@ -554,6 +574,14 @@ ADEV QuadRecord loadQuad(const void* p) { // one 256-bit load: LDG.E.ENL2.256 on
   return r;
 }
 
+ADEV QuadRecord loadQuadNow(const void* p) { // same load, not movable by the compiler: issued where it is written
+  QuadRecord r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "l"(p));
+  return r;
+}
+
 struct ProxyTap {
   V3 pos;       // interpolated position, within E per component of the real-arithmetic bilinear value
   float twoTol; // the record's T
@@ -597,6 +625,9 @@ __device__ __noinline__ bool facesRay(const FrameParams& P, float cu, float cv, 
   return dot3(currentNormal, rayDir) < 0.0f;
 }
 
+#ifndef ALTHEA_SSAO_PREFETCH
+#define ALTHEA_SSAO_PREFETCH 0
+#endif
 #ifndef ALTHEA_SSAO_UNROLL
 #define ALTHEA_SSAO_UNROLL 2
 #endif
@@ -633,11 +664,32 @@ ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float
     // sign-decided form
     V3 prevPos = worldPos;
     float prevProjection = 0.0f, prevTwoTol = 0.0f, prevDecided = 0.0f;
+#if ALTHEA_SSAO_PREFETCH
+    // software pipeline: the record of tap i + 1 is requested before tap i is evaluated, so every thread keeps two gathers
+    // in flight (the taps of a ray are known up front; only a hit, which ends the ray, wastes the extra request)
+    float cu = marchCoord(u0, uvEnd.x, 1), cv = marchCoord(v0, uvEnd.y, 1);
+    ProxyAddr pa = proxyAddr(P, cu, cv);
+    QuadRecord rec;
+    if (n > 1) rec = loadQuadNow(pa.rec);
+#pragma unroll 1
+    for (int i = 1; i < n; ++i) {
+      float nu = cu, nv = cv;
+      ProxyAddr pn = pa;
+      QuadRecord recN = rec;
+      if (i + 1 < n) {
+        nu = marchCoord(u0, uvEnd.x, i + 1);
+        nv = marchCoord(v0, uvEnd.y, i + 1);
+        pn = proxyAddr(P, nu, nv);
+        recN = loadQuadNow(pn.rec);
+      }
+      const ProxyTap tap = proxyEval(rec, pa.fx, pa.fy);
+#else
 #pragma unroll kSsaoUnroll
     for (int i = 1; i < n; ++i) {
       const float cu = marchCoord(u0, uvEnd.x, i), cv = marchCoord(v0, uvEnd.y, i);
       const ProxyAddr pa = proxyAddr(P, cu, cv);
       const ProxyTap tap = proxyEval(loadQuad(pa.rec), pa.fx, pa.fy);
+#endif
       V3 curPos = tap.pos;
       float curProjection = fmaf(curPos.z, perpRef.z, fmaf(curPos.y, perpRef.y, fmaf(curPos.x, perpRef.x, -projBias)));
       float curTwoTol = tap.twoTol + posSlop2; // inf / NaN when the record is flagged
@@ -693,6 +745,9 @@ ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float
         }
       }
       prevPos = curPos; prevProjection = curProjection; prevTwoTol = curTwoTol; prevDecided = curDecided;
+#if ALTHEA_SSAO_PREFETCH
+      cu = nu; cv = nv; pa = pn; rec = recN;
+#endif
     }
   }
   return ao;
@@ -761,6 +816,9 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const __grid_consta
 static inline dim3 tileGrid(int w, int h) { return dim3((unsigned)((w + 15) / 16), (unsigned)((h + 15) / 16)); }
 
 void launch_ssr_capture(const FrameParams& P, cudaStream_t s) { ssr_capture_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
+void launch_ssr_depth_pad(const FrameParams& P, cudaStream_t s) {
+  ssr_depth_pad_kernel<<<dim3((unsigned)((P.W + 2 + 31) / 32), (unsigned)((P.H + 2 + 7) / 8)), 256, 0, s>>>(P);
+}
 // shared-memory bytes of the largest source window a TW x TH tile can need (mirrors the kernel's window computation)
 static size_t stagedWindowBytes(const ConvolveParams& C, int TW, int TH) {
   const double rx = (double)C.src.w / C.dst.w, ry = (double)C.src.h / C.dst.h;

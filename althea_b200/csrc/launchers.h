@@ -8,6 +8,7 @@
 #define ALTHEA_DECLARE_FRAME_LAUNCHERS(ns)                                   \
   namespace ns {                                                             \
   void launch_ssr_capture(const FrameParams& P, cudaStream_t s);             \
+  void launch_ssr_depth_pad(const FrameParams& P, cudaStream_t s);           \
   void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s);      \
   void launch_ssao(const FrameParams& P, cudaStream_t s);                    \
   void launch_ssao_quads(const FrameParams& P, cudaStream_t s);              \

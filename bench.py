@@ -34,6 +34,7 @@ UNIT = "Mpixel/s"
 # algorithmic bytes per pixel (SURVEY.md 8d / DESIGN.md): each buffer read once, written once
 BYTES_PER_PX = {
     "ssr_capture": 28.0,      # depth 4 + normal 8 + albedo 4 + MRO 4 + write RGBA16F 8
+    "ssr_depth_pad": 8.0,     # depth 4 read + padded copy 4 written per pixel (engine scratch)
     "glossy_convolve": 13.28,  # read 8*(1+1/4+1/16+1/64) + write 8*(1/4+...+1/256)
     "ssao": 25.0,             # position 16 + normal 8 + write count 1 (the proxy records are engine scratch, not algorithmic)
     "ssao_quads": 48.0,       # position 16 read + 32-byte proxy record written per pixel
