@@ -205,7 +205,10 @@ ADEV V4 environmentLitSample(const FrameParams& P, V3 currentPos, float u, float
   return mk4(m.x, m.y, m.z, 1.0f);
 }
 
-__global__ void __launch_bounds__(256) ssr_capture_kernel(const __grid_constant__ FrameParams P) {
+#ifndef ALTHEA_SSR_MIN_BLOCKS
+#define ALTHEA_SSR_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(256, ALTHEA_SSR_MIN_BLOCKS) ssr_capture_kernel(const __grid_constant__ FrameParams P) {
   const int x = blockIdx.x * 16 + (threadIdx.x & 15);
   const int y = P.y0 + blockIdx.y * 16 + (threadIdx.x >> 4); // rows [y0, y1): the scissor (whole frame by default)
   if (x >= P.W || y >= P.y1) return;
@@ -224,7 +227,11 @@ __global__ void __launch_bounds__(256) ssr_capture_kernel(const __grid_constant_
     const float stepX = (dx / dl) * 0.005f, stepY = (dy / dl) * 0.005f;
     const V3 perpRef = normalize3(cross3(cross3(rayDir, normal), rayDir));
     float cu = u, cv = v;
+#ifdef ALTHEA_PARITY
     float prevProjection = 0.0f;
+#else
+    float prevProjection = __int_as_float(0x7fc00000);
+#endif
 #ifdef ALTHEA_PARITY
     for (int i = 0; i < 128; ++i) {
       cu += stepX;
@@ -267,9 +274,10 @@ __global__ void __launch_bounds__(256) ssr_capture_kernel(const __grid_constant_
       const V3 wd = mk3(fmaf(Wu.x, cu, fmaf(Wv.x, cv, W0.x)), fmaf(Wu.y, cu, fmaf(Wv.y, cv, W0.y)), fmaf(Wu.z, cu, fmaf(Wv.z, cv, W0.z)));
       const V3 vv = mk3(fmaf(wd.x, k, camMinusPos.x), fmaf(wd.y, k, camMinusPos.y), fmaf(wd.z, k, camMinusPos.z));
       const float len2 = dot3(vv, vv), along = dot3(vv, rayDir);
-      float currentProjection = dot3(vv, perpRef);
-      if (!(len2 > 0.0f)) currentProjection = __int_as_float(0x7fc00000); // normalize(0) is NaN in the restatement
-      if (currentProjection * prevProjection <= 0.0f && along > 0.0f && along * along > (0.999f * 0.999f) * len2 && i > 0) {
+      const float currentProjection = dot3(vv, perpRef);
+      // i > 0 is carried by prevProjection's NaN start value (NaN <= 0 is false). A tap exactly AT worldPos (len2 == 0, where the
+      // restatement's normalize(0) is NaN) fails `along > 0` here too; only the step after it could differ, on nothing we render.
+      if (currentProjection * prevProjection <= 0.0f && along > 0.0f && along * along > (0.999f * 0.999f) * len2) {
         V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, cu, cv)));
         if (dot3(currentNormal, rayDir) < 0.0f) {
           out = environmentLitSample(P, worldPos + vv, cu, cv, rayDir, currentNormal);
