@@ -55,6 +55,7 @@ struct althea_cuda_ctx {
   // internal scratch: SSAO position-quad proxy, (W+1) x (H+1) x 32 B
   void* quadScratch = nullptr;
   size_t quadScratchBytes = 0;
+  unsigned long long* gatherCounter = nullptr; // device counter of the ALTHEA_CTX_SSAO_COUNT_TAPS diagnostic
   // internal scratch: SSR padded depth, (W+2) x (H+2) floats (frame_kernels.cu, ssr_depth_pad_kernel)
   void* depthPadScratch = nullptr;
   size_t depthPadScratchBytes = 0;
@@ -382,6 +383,7 @@ void althea_cuda_destroy(althea_cuda_ctx* ctx) {
   if (ctx->aoScratch) cudaFree(ctx->aoScratch);
   if (ctx->quadScratch) cudaFree(ctx->quadScratch);
   if (ctx->depthPadScratch) cudaFree(ctx->depthPadScratch);
+  if (ctx->gatherCounter) cudaFree(ctx->gatherCounter);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -760,8 +762,16 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
     P.quadRow = P.W + 1;
     P.quadsOrigin = static_cast<const char*>(ctx->quadScratch) + ((size_t)P.quadRow + 1) * 32;
   }
+  if (computeAo && !exactTaps && (ctx->flags & ALTHEA_CTX_SSAO_COUNT_TAPS)) {
+    if (!ctx->gatherCounter) {
+      cudaError_t e = cudaMalloc(&ctx->gatherCounter, sizeof(unsigned long long));
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(gather counter): %s", cudaGetErrorString(e)); }
+    }
+    P.gatherCounter = ctx->gatherCounter;
+  }
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  if (P.gatherCounter) cudaMemsetAsync(P.gatherCounter, 0, sizeof(unsigned long long), stream);
   if (computeAo) {
     if (exactTaps) {
       timedLaunch(ctx, "ssao_exact", stream, [&] { parity ? althea_parity::launch_ssao_exact(P, stream) : althea_fast::launch_ssao_exact(P, stream); });
@@ -854,4 +864,72 @@ int althea_cuda_brdf_lut(althea_cuda_ctx* ctx, uint32_t samples, uint64_t out_lu
   return endWork(ctx, sync, stream);
 }
 
+} // extern "C"
+
+// ---- diagnostics: the machine's rate for the SSAO march's access pattern --------------------------------------------------
+// Every lane reads 32-byte records (one 256-bit load each, as ssao_kernel does) at hash-random positions inside a (2R)^2 window
+// around its 16 x 16 tile of a (w+1) x (h+1) record grid; the measured records/s is the ceiling bench.py holds the SSAO march
+// against (the stage is bound by the L1 data pipe: one wavefront per distinct 128-byte line).
+namespace {
+__device__ __forceinline__ uint32_t diagHash(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+__global__ void __launch_bounds__(256, 4) diag_gather_kernel(const void* recs, uint32_t* sink, int gw, int gh, int w, int h, int taps, int radius) {
+  const int tx = blockIdx.x * 16 + (threadIdx.x & 15), ty = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (tx >= w || ty >= h) return;
+  uint32_t s = diagHash((uint32_t)tx * 9781u + (uint32_t)ty * 6271u + 1u), acc = 0;
+  for (int t = 0; t < taps; ++t) {
+    s = s * 1664525u + 1013904223u;
+    const int dx = (int)((s >> 8) % (2u * (uint32_t)radius)) - radius, dy = (int)((s >> 20) % (2u * (uint32_t)radius)) - radius;
+    const int x = min(max(tx + dx, 0), gw - 1), y = min(max(ty + dy, 0), gh - 1);
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "l"(static_cast<const char*>(recs) + ((size_t)y * gw + x) * 32));
+    acc += r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7;
+  }
+  if (acc == 0x9e3779b9u) sink[0] = acc; // keeps the loads alive; practically never taken
+}
+} // namespace
+
+extern "C" {
+int althea_cuda_diag_ssao_gathers(althea_cuda_ctx* ctx, uint64_t* out_records) {
+  if (!ctx || !out_records) return ALTHEA_ERR_INVALID_ARGUMENT;
+  if (!ctx->gatherCounter) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "no SSAO launch has run with ALTHEA_CTX_SSAO_COUNT_TAPS set");
+  CUDA_TRY(ctx, cudaDeviceSynchronize());
+  unsigned long long v = 0;
+  CUDA_TRY(ctx, cudaMemcpy(&v, ctx->gatherCounter, sizeof v, cudaMemcpyDeviceToHost));
+  *out_records = v;
+  return ALTHEA_OK;
+}
+
+int althea_cuda_diag_gather_ceiling(althea_cuda_ctx* ctx, uint32_t w, uint32_t h, uint32_t radius, uint32_t taps_per_pixel, double* out_records_per_second) {
+  if (!ctx || !out_records_per_second || !w || !h || !radius || !taps_per_pixel) return ALTHEA_ERR_INVALID_ARGUMENT;
+  const int gw = (int)w + 1, gh = (int)h + 1;
+  const size_t need = (size_t)gw * gh * 32;
+  void* recs = nullptr;
+  uint32_t* sink = nullptr;
+  cudaError_t e = cudaMalloc(&recs, need);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(gather records %zu): %s", need, cudaGetErrorString(e)); }
+  e = cudaMalloc(&sink, sizeof(uint32_t));
+  if (e != cudaSuccess) { cudaGetLastError(); cudaFree(recs); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(sink): %s", cudaGetErrorString(e)); }
+  cudaMemsetAsync(recs, 1, need, ctx->stream);
+  const dim3 grid((w + 15) / 16, (h + 15) / 16);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  diag_gather_kernel<<<grid, 256, 0, ctx->stream>>>(recs, sink, gw, gh, (int)w, (int)h, 8, (int)radius); // warm-up
+  cudaEventRecord(e0, ctx->stream);
+  diag_gather_kernel<<<grid, 256, 0, ctx->stream>>>(recs, sink, gw, gh, (int)w, (int)h, (int)taps_per_pixel, (int)radius);
+  cudaEventRecord(e1, ctx->stream);
+  ctx->launches += 2;
+  e = cudaEventSynchronize(e1);
+  float ms = 0.0f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(recs);
+  cudaFree(sink);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_CUDA, "gather ceiling: %s", cudaGetErrorString(e)); }
+  *out_records_per_second = (double)w * h * taps_per_pixel / ((double)ms * 1e-3);
+  return ALTHEA_OK;
+}
 } // extern "C"

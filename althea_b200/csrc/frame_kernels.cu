@@ -644,7 +644,8 @@ constexpr int kSsaoUnroll = ALTHEA_SSAO_UNROLL;
 ADEV float decided(float v, float twoTol) { return copysignf(fmaxf(fabsf(v) - twoTol, 0.0f), v); }
 ADEV float decidedExact(float v) { return fabsf(v) > kTiny ? v : 0.0f; }
 
-ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float v0, V3 worldPos, V3 normal) {
+// COUNT: diagnostic instantiation that also counts the proxy records gathered (bench.py's gather-rate roofline)
+template <bool COUNT> ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float v0, V3 worldPos, V3 normal, unsigned& gathers) {
   HashRng rng;
   rng.sx = (uint32_t)px;
   rng.sy = (uint32_t)py;
@@ -691,12 +692,14 @@ ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float
         recN = loadQuadNow(pn.rec);
       }
       const ProxyTap tap = proxyEval(rec, pa.fx, pa.fy);
+      if (COUNT) gathers += 1u;
 #else
 #pragma unroll kSsaoUnroll
     for (int i = 1; i < n; ++i) {
       const float cu = marchCoord(u0, uvEnd.x, i), cv = marchCoord(v0, uvEnd.y, i);
       const ProxyAddr pa = proxyAddr(P, cu, cv);
       const ProxyTap tap = proxyEval(loadQuad(pa.rec), pa.fx, pa.fy);
+      if (COUNT) gathers += 1u;
 #endif
       V3 curPos = tap.pos;
       float curProjection = fmaf(curPos.z, perpRef.z, fmaf(curPos.y, perpRef.y, fmaf(curPos.x, perpRef.x, -projBias)));
@@ -768,18 +771,20 @@ ADEV int ssaoCountFiltered(const FrameParams& P, int px, int py, float u0, float
 #define ALTHEA_SSAO_TILE_W 16
 #endif
 constexpr int kSsaoTileW = ALTHEA_SSAO_TILE_W, kSsaoTileH = 256 / ALTHEA_SSAO_TILE_W;
-__global__ void __launch_bounds__(256, ALTHEA_SSAO_MIN_BLOCKS) ssao_kernel(const __grid_constant__ FrameParams P) {
+template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_SSAO_MIN_BLOCKS) ssao_kernel(const __grid_constant__ FrameParams P) {
   const int x = blockIdx.x * kSsaoTileW + (threadIdx.x % kSsaoTileW);
   const int y = P.y0 + blockIdx.y * kSsaoTileH + (threadIdx.x / kSsaoTileW);
   if (x >= P.W || y >= P.y1) return;
   V4 position = FmtRGBA32F::load(P.position, x, y);
   uint8_t count = 255;
+  unsigned gathers = 0u;
   if (position.w != 0.0f) {
     const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
     V3 normal = normalize3(xyz(FmtRGBA16F::load(P.normal, x, y)));
-    count = (uint8_t)ssaoCountFiltered(P, x, y, u, v, xyz(position), normal);
+    count = (uint8_t)ssaoCountFiltered<COUNT>(P, x, y, u, v, xyz(position), normal, gathers);
   }
   rowPtrW<uint8_t>(P.ao, y)[x] = count;
+  if (COUNT) atomicAdd(P.gatherCounter, (unsigned long long)gathers);
 }
 
 // ---- deferred shading -----------------------------------------------------------------------------------------------
@@ -855,7 +860,9 @@ void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s) {
   glossy_convolve_kernel<<<tileGrid(C.dst.w, C.y1 - C.y0), 256, 0, s>>>(C);
 }
 void launch_ssao(const FrameParams& P, cudaStream_t s) {
-  ssao_kernel<<<dim3((unsigned)((P.W + kSsaoTileW - 1) / kSsaoTileW), (unsigned)((P.y1 - P.y0 + kSsaoTileH - 1) / kSsaoTileH)), 256, 0, s>>>(P);
+  const dim3 grid((unsigned)((P.W + kSsaoTileW - 1) / kSsaoTileW), (unsigned)((P.y1 - P.y0 + kSsaoTileH - 1) / kSsaoTileH));
+  if (P.gatherCounter) ssao_kernel<true><<<grid, 256, 0, s>>>(P);
+  else ssao_kernel<false><<<grid, 256, 0, s>>>(P);
 }
 void launch_ssao_exact(const FrameParams& P, cudaStream_t s) { ssao_exact_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
 void launch_ssao_quads(const FrameParams& P, cudaStream_t s) {

@@ -44,6 +44,7 @@ struct FrameParams {
   const void* quadsOrigin; // &record(1, 1): the footprint whose top-left tap is texel (0, 0)
   int quadRow;             // records per row = W + 1
   float Wf, Hf;            // (float)W, (float)H
+  unsigned long long* gatherCounter; // diagnostics (ALTHEA_CTX_SSAO_COUNT_TAPS): proxy records gathered by the SSAO march; else null
   // SSR padded depth (engine scratch): the depth image with a one-texel CLAMP_TO_EDGE border, (W+2) x (H+2) floats
   const float* depthPad;
   const float* depthPadOrigin; // &padded(1, 1), i.e. texel (0, 0)

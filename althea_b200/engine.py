@@ -176,6 +176,18 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.althea_cuda_launch_count(self._ptr))
 
+    def ssao_gathers(self) -> int:
+        """Proxy records gathered by the last SSAO launch made with CTX_SSAO_COUNT_TAPS set (diagnostics)."""
+        out = C.c_uint64(0)
+        self._check(self._lib.althea_cuda_diag_ssao_gathers(self._ptr, C.byref(out)))
+        return int(out.value)
+
+    def gather_ceiling(self, w: int, h: int, radius: int, taps_per_pixel: int = 64) -> float:
+        """Measured records/s of divergent 32-byte gathers within +-radius records of each 16x16 tile (diagnostics)."""
+        out = C.c_double(0.0)
+        self._check(self._lib.althea_cuda_diag_gather_ceiling(self._ptr, w, h, radius, taps_per_pixel, C.byref(out)))
+        return float(out.value)
+
 
 def band_rows(w: int, h: int, mips: int, y0: int, y1: int):
     """[(lo, hi)] per reflection mip: the rows a band [y0, y1) of a w x h frame reads or writes (althea_cuda_band_rows)."""

@@ -351,6 +351,8 @@ def main():
     torch.cuda.set_device(local_rank)
     device = "cuda:%d" % local_rank
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(device))
 
     from althea_b200 import _capi, engine
@@ -398,6 +400,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = world * px_per_step / (ms_step * 1e-3) / 1e6
+
+    # ---- what actually binds the SSAO march: divergent 32-byte gathers. Outside the timed region, rank 0: the
+    # number of proxy records one frame gathers (counting instantiation of the kernel) and the device's measured rate for the
+    # same access pattern (one 256-bit load per lane, random positions in a window around the lane's tile).
+    gather = None
+    if rank == 0:
+        ctx.set_flags(_capi.CTX_SSAO_COUNT_TAPS)
+        run_frame(views[0], ibl, lights, stream)
+        torch.cuda.synchronize()
+        records = ctx.ssao_gathers()
+        ctx.set_flags(0)
+        ceilings = {str(r): ctx.gather_ceiling(W4K, H4K, r, 64) for r in (32, 96)}
+        gather = {"records_per_frame": records, "ceiling_records_per_s": ceilings}
 
     # ---- e2e: same metric through the C ABI with HOST buffers (pinned), copies inside the timed region ----
     e2e = None
@@ -491,6 +506,16 @@ def main():
                         "binding_resource": tr.get("binding_resource") if tr else None, "peak_source": peak_src,
                         "note": "%s is FP32-issue / L1-tap bound, not HBM bound (SURVEY.md 8d): fp32 frac %.3f of 148 SM x 128 lanes x 2 x %.0f MHz"
                                 % (dom, s["fp32_frac_at_sm_max"], sm_max)}
+        if roofline and dom == "ssao" and gather:
+            peak = max(gather["ceiling_records_per_s"].values())
+            ach = gather["records_per_frame"] / (stages["ssao"]["ms_per_frame"] * 1e-3)
+            roofline["binding"] = {
+                "resource": "divergent 32-byte gathers (L1 data pipe: one wavefront per distinct 128-byte line)",
+                "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "Grecords/s", "frac": ach / peak,
+                "records_per_launch": gather["records_per_frame"],
+                "peak_how": "althea_cuda_diag_gather_ceiling measured in this run: one 256-bit load per lane at random positions within "
+                            "+-32 / +-96 records of the lane's 16x16 tile over the 3841x2161 record grid (the larger rate is the peak)",
+                "ceilings": {k: v / 1e9 for k, v in gather["ceiling_records_per_s"].items()}}
         frame_ms = ms_step / V
         chain = {"bytes_per_px": 92.0, "achieved_GBps": 92.0 * px_frame / (frame_ms * 1e-3) / 1e9, "hbm_frac": 92.0 * px_frame / (frame_ms * 1e-3) / 1e9 / hbm_peak,
                  "ms_per_4k_frame": frame_ms, "frames_per_s": 1e3 / frame_ms * world}

@@ -70,6 +70,7 @@ int althea_cuda_abi_version(void);
 
 #define ALTHEA_CTX_PARITY_MATH 1u /* run the -fmad=false build of the per-frame kernels (bit-matches the CPU oracle's IEEE op order) */
 #define ALTHEA_CTX_SSAO_EXACT_TAPS 2u /* SSAO marches the fp32 position texels directly (4 loads per tap) instead of the packed proxy with exact re-evaluation; same counts, slower: A/B switch for tests and profiling */
+#define ALTHEA_CTX_SSAO_COUNT_TAPS 4u /* diagnostics: the SSAO march also counts the proxy records it gathers (read with althea_cuda_diag_ssao_gathers); slower */
 int althea_cuda_set_flags(althea_cuda_ctx* ctx, uint32_t flags);
 
 /* Row bands (multi-GPU split of ONE frame, BASELINE configs[3]): restricts ssr_capture / glossy_convolve / deferred_shade on
@@ -88,6 +89,14 @@ int althea_cuda_get_timings(althea_cuda_ctx* ctx, const char** names, float* tot
 int althea_cuda_reset_timings(althea_cuda_ctx* ctx);
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 uint64_t althea_cuda_launch_count(const althea_cuda_ctx* ctx);
+
+/* Diagnostics for bench.py's roofline of the SSAO march, which is bound by the rate of divergent 32-byte gathers (L1 data pipe),
+ * not by HBM. Neither call is on the rendering path. _ssao_gathers: proxy records gathered by the last SSAO launch made with
+ * ALTHEA_CTX_SSAO_COUNT_TAPS set. _gather_ceiling: measures the device's records/s for the same access pattern (one 256-bit
+ * load per lane at random positions within +-radius records of the lane's 16x16 tile, over a (w+1) x (h+1) record grid). */
+int althea_cuda_diag_ssao_gathers(althea_cuda_ctx* ctx, uint64_t* out_records);
+int althea_cuda_diag_gather_ceiling(althea_cuda_ctx* ctx, uint32_t w, uint32_t h, uint32_t radius, uint32_t taps_per_pixel,
+                                    double* out_records_per_second);
 
 /* ---- resources ------------------------------------------------------------------------------------------------- */
 /* Linear image layout used by every entry point: row-major, row 0 = top; for mips > 1 the levels are tightly packed one

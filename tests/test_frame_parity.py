@@ -366,3 +366,25 @@ def test_properties_at_4k(ctx_fast):
     scaled = t16.float()
     big = base.abs() > 1e-3  # away from fp16 subnormals scaling by 2 is exact
     assert float(((scaled * 2.0 - base).abs()[big] / base.abs()[big]).max()) <= 2.0 ** -9
+
+
+def test_gather_diagnostics(ctx_fast):
+    """bench.py's roofline evidence for the SSAO march: the counting instantiation returns the same AO counts and a gather
+    count inside the march's bounds (<= 24 rays x 11 taps per shaded pixel), and the ceiling measurement returns a rate."""
+    from althea_b200 import _capi
+    fd = FrameData("scene", 192, 108, n_lights=0)
+    gf = GpuFrame(ctx_fast, fd)
+    gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+    plain = gf.ao_counts().copy()
+    ctx_fast.set_flags(_capi.CTX_SSAO_COUNT_TAPS)
+    gf.deferred.aoCounts.tensor.zero_()
+    gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+    counted = gf.ao_counts().copy()
+    gathers = ctx_fast.ssao_gathers()
+    ctx_fast.set_flags(0)
+    assert np.array_equal(plain, counted)
+    shaded = int((plain < 255).sum())
+    assert 0 < gathers <= shaded * 24 * 11
+    assert gathers > shaded * 24  # more than one tap per ray on average
+    rate = ctx_fast.gather_ceiling(512, 512, 32, 16)
+    assert rate > 1e9
