@@ -61,6 +61,32 @@ class IblPrecomputeDesc(C.Structure):
 
 assert C.sizeof(GlobalUniforms) == 416
 
+
+class TextureRef(C.Structure):
+    _fields_ = [("image", C.c_uint64), ("sampler", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class Material(C.Structure):
+    """althea_material: the MaterialConstants fields fetchMaterial reads (InstanceDataCommon.h:8-33)."""
+    _fields_ = [("baseColorFactor", C.c_float * 4), ("baseTextureCoordinateIndex", C.c_int32),
+                ("metallicRoughnessTextureCoordinateIndex", C.c_int32), ("normalScale", C.c_float), ("metallicFactor", C.c_float),
+                ("roughnessFactor", C.c_float), ("alphaCutoff", C.c_float), ("baseTexture", TextureRef), ("normalTexture", TextureRef),
+                ("metallicRoughnessTexture", TextureRef)]
+
+
+class Primitive(C.Structure):
+    _fields_ = [("vertices", C.c_uint64), ("indices", C.c_uint64), ("index_count", C.c_uint32), ("front_face_clockwise", C.c_uint32),
+                ("model", C.c_float * 16), ("material", Material)]
+
+
+class PointLightConstants(C.Structure):
+    """althea_point_light_constants == PointLightConstants (Src/PointLight.cpp:72-118)."""
+    _fields_ = [("projection", C.c_float * 16), ("inverseProjection", C.c_float * 16), ("views", (C.c_float * 16) * 6),
+                ("inverseViews", (C.c_float * 16) * 6)]
+
+
+VERTEX_BYTES = 104  # sizeof(althea_vertex)
+
 # every symbol include/althea_cuda.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = {
     "althea_cuda_abi_version": (C.c_int, []),
@@ -97,6 +123,9 @@ SYMBOLS = {
     "althea_cuda_glossy_convolve": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(Sync)]),
     "althea_cuda_deferred_shade": (C.c_int, [C.c_void_p, C.POINTER(GlobalUniforms), C.POINTER(GBuffer), C.POINTER(IBL), C.c_uint64,
                                              C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(Sync)]),
+    "althea_cuda_draw_gbuffer": (C.c_int, [C.c_void_p, C.POINTER(GlobalUniforms), C.POINTER(Primitive), C.c_uint32, C.POINTER(GBuffer), C.POINTER(Sync)]),
+    "althea_cuda_draw_shadow_cubes": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(PointLightConstants), C.POINTER(Primitive), C.c_uint32,
+                                                C.c_uint64, C.POINTER(Sync)]),
     "althea_cuda_generate_mips": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(Sync)]),
     "althea_cuda_ibl_precompute": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(IblPrecomputeDesc), C.c_uint64, C.c_uint64,
                                              C.POINTER(Sync)]),

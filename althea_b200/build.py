@@ -26,6 +26,7 @@ UNITS = [
     ("frame_kernels.cu", "frame_fast.o", ["-DALTHEA_NS=althea_fast"]),
     ("frame_kernels.cu", "frame_parity.o", ["-DALTHEA_NS=althea_parity", "-DALTHEA_PARITY", "-fmad=false"]),
     ("ibl_kernels.cu", "ibl_kernels.o", []),
+    ("raster_kernels.cu", "raster_kernels.o", []),
     ("althea_cuda.cu", "althea_cuda.o", []),
 ]
 

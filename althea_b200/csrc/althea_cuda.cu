@@ -14,6 +14,7 @@
 
 #include "../../include/althea_cuda.h"
 #include "launchers.h"
+#include "raster_launchers.h"
 
 namespace {
 
@@ -40,6 +41,9 @@ struct TimingEntry {
 
 } // namespace
 
+struct RasterScratch;
+static void freeRasterScratch(RasterScratch* r);
+
 struct althea_cuda_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -55,6 +59,7 @@ struct althea_cuda_ctx {
   // internal scratch: SSAO position-quad proxy, (W+1) x (H+1) x 32 B
   void* quadScratch = nullptr;
   size_t quadScratchBytes = 0;
+  struct RasterScratch* raster = nullptr; // scratch of the rasterising producers (draw_gbuffer / draw_shadow_cubes)
   unsigned long long* gatherCounter = nullptr; // device counter of the ALTHEA_CTX_SSAO_COUNT_TAPS diagnostic
   // internal scratch: SSR padded depth, (W+2) x (H+2) floats (frame_kernels.cu, ssr_depth_pad_kernel)
   void* depthPadScratch = nullptr;
@@ -384,6 +389,7 @@ void althea_cuda_destroy(althea_cuda_ctx* ctx) {
   if (ctx->quadScratch) cudaFree(ctx->quadScratch);
   if (ctx->depthPadScratch) cudaFree(ctx->depthPadScratch);
   if (ctx->gatherCounter) cudaFree(ctx->gatherCounter);
+  freeRasterScratch(ctx->raster);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -931,5 +937,276 @@ int althea_cuda_diag_gather_ceiling(althea_cuda_ctx* ctx, uint32_t w, uint32_t h
   if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_CUDA, "gather ceiling: %s", cudaGetErrorString(e)); }
   *out_records_per_second = (double)w * h * taps_per_pixel / ((double)ms * 1e-3);
   return ALTHEA_OK;
+}
+} // extern "C"
+
+// ---- rasterising producers: G-buffer pass and omni shadow cubes (raster_kernels.cu) -----------------------------------------
+struct RasterScratch {
+  void* recs = nullptr; size_t recsBytes = 0;
+  void* work = nullptr; size_t workBytes = 0;
+  void* vis = nullptr; size_t visBytes = 0;
+  void* prims = nullptr; size_t primsBytes = 0;
+  void* views = nullptr; size_t viewsBytes = 0;
+  uint32_t* counters = nullptr;
+  unsigned int* minAlphaDev = nullptr;
+  bool srgbUploaded = false;
+  int sms = 148;
+  std::unordered_map<uint64_t, unsigned> minAlpha; // per base-colour image handle
+};
+static void freeRasterScratch(RasterScratch* r) {
+  if (!r) return;
+  for (void* p : {r->recs, r->work, r->vis, r->prims, r->views, (void*)r->counters, (void*)r->minAlphaDev})
+    if (p) cudaFree(p);
+  delete r;
+}
+
+namespace {
+int growScratch(althea_cuda_ctx* ctx, void** p, size_t* have, size_t need, const char* what) {
+  if (*have >= need) return ALTHEA_OK;
+  if (*p) { cudaDeviceSynchronize(); cudaFree(*p); *p = nullptr; *have = 0; }
+  cudaError_t e = cudaMalloc(p, need);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(%s, %zu bytes): %s", what, need, cudaGetErrorString(e)); }
+  *have = need;
+  return ALTHEA_OK;
+}
+
+int rasterScratch(althea_cuda_ctx* ctx, RasterScratch** out) {
+  if (!ctx->raster) {
+    ctx->raster = new RasterScratch();
+    cudaDeviceGetAttribute(&ctx->raster->sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    CUDA_TRY(ctx, cudaMalloc(&ctx->raster->counters, 4 * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->raster->minAlphaDev, sizeof(unsigned int)));
+  }
+  *out = ctx->raster;
+  return ALTHEA_OK;
+}
+
+int textureOf(althea_cuda_ctx* ctx, const althea_texture_ref& ref, const char* what, RasterTex* out) {
+  memset(out, 0, sizeof *out);
+  if (!ref.image) return ALTHEA_OK;
+  Resource* r;
+  int rc = getImage(ctx, ref.image, ALTHEA_FORMAT_R8G8B8A8_UNORM, what, &r);
+  if (rc) return rc;
+  if (r->mips == 1 && r->pitch0 != (size_t)r->w * 4) return fail(ctx, ALTHEA_ERR_UNSUPPORTED, "%s: textures must be tightly packed", what);
+  if (r->mips > (uint32_t)kMaxMips + 2) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "%s: too many mip levels", what);
+  out->texels = static_cast<const uint8_t*>(r->dptr);
+  out->w = (int)r->w; out->h = (int)r->h; out->mips = (int)r->mips;
+  out->sampler = ref.sampler;
+  return ALTHEA_OK;
+}
+
+// device-side primitive table + the draw-ordered triangle count
+int buildPrims(althea_cuda_ctx* ctx, RasterScratch* R, const althea_primitive* prims, uint32_t n, cudaStream_t stream, uint32_t* triTotal) {
+  if (!prims && n) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "primitives is null");
+  std::vector<RasterPrim> host(n);
+  uint64_t tris = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const althea_primitive& p = prims[i];
+    RasterPrim& d = host[i];
+    memset(&d, 0, sizeof d);
+    Resource* vb = find(ctx, p.vertices, ResKind::Buffer);
+    Resource* ib = find(ctx, p.indices, ResKind::Buffer);
+    if (!vb || !ib) return fail(ctx, ALTHEA_ERR_BAD_HANDLE, "primitive %u: vertices/indices are not live buffers", i);
+    if (p.index_count % 3u) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "primitive %u: index_count %u is not a triangle list", i, p.index_count);
+    if ((size_t)p.index_count * 4 > ib->bytes) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "primitive %u: index buffer holds %zu bytes, index_count=%u", i, ib->bytes, p.index_count);
+    if (vb->bytes < sizeof(althea_vertex)) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "primitive %u: empty vertex buffer", i);
+    d.verts = static_cast<const althea_vertex*>(vb->dptr);
+    d.idx = static_cast<const uint32_t*>(ib->dptr);
+    d.triCount = p.index_count / 3u;
+    d.triOffset = (uint32_t)tris;
+    tris += d.triCount;
+    memcpy(d.model, p.model, sizeof d.model);
+    d.frontCW = p.front_face_clockwise ? 1u : 0u;
+    const althea_material& m = p.material;
+    memcpy(d.mat.baseColorFactor, m.baseColorFactor, sizeof d.mat.baseColorFactor);
+    if (m.baseTextureCoordinateIndex < 0 || m.baseTextureCoordinateIndex > 3 || m.metallicRoughnessTextureCoordinateIndex < 0 || m.metallicRoughnessTextureCoordinateIndex > 3)
+      return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "primitive %u: texture coordinate index out of [0, 3]", i);
+    d.mat.baseUv = m.baseTextureCoordinateIndex;
+    d.mat.mrUv = m.metallicRoughnessTextureCoordinateIndex;
+    d.mat.normalScale = m.normalScale; d.mat.metallicFactor = m.metallicFactor; d.mat.roughnessFactor = m.roughnessFactor; d.mat.alphaCutoff = m.alphaCutoff;
+    int rc;
+    if ((rc = textureOf(ctx, m.baseTexture, "material.baseTexture", &d.mat.base))) return rc;
+    if ((rc = textureOf(ctx, m.normalTexture, "material.normalTexture", &d.mat.normal))) return rc;
+    if ((rc = textureOf(ctx, m.metallicRoughnessTexture, "material.metallicRoughnessTexture", &d.mat.mr))) return rc;
+    // can the fragment's alpha ever fall below the cutoff? (filtered alpha is a convex combination of texel alphas)
+    float minA = 1.0f;
+    if (d.mat.base.texels) {
+      auto it = R->minAlpha.find(m.baseTexture.image);
+      if (it == R->minAlpha.end()) {
+        unsigned init = 255u, got = 255u;
+        CUDA_TRY(ctx, cudaMemcpyAsync(R->minAlphaDev, &init, sizeof init, cudaMemcpyHostToDevice, stream));
+        althea_raster::launch_texture_min_alpha(reinterpret_cast<const uint32_t*>(d.mat.base.texels), (size_t)d.mat.base.w * d.mat.base.h, R->minAlphaDev, stream);
+        ctx->launches += 1;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&got, R->minAlphaDev, sizeof got, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+        it = R->minAlpha.emplace(m.baseTexture.image, got).first;
+      }
+      minA = (float)it->second / 255.0f;
+    }
+    d.opaque = (m.alphaCutoff <= 0.0f || minA * m.baseColorFactor[3] * (1.0f - 1e-5f) >= m.alphaCutoff) ? 1u : 0u;
+  }
+  if (tris > 0x7fffffffull) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "too many triangles (%llu)", (unsigned long long)tris);
+  *triTotal = (uint32_t)tris;
+  int rc = growScratch(ctx, &R->prims, &R->primsBytes, (n ? n : 1u) * sizeof(RasterPrim), "raster primitive table");
+  if (rc) return rc;
+  if (n) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(R->prims, host.data(), n * sizeof(RasterPrim), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(stream)); // `host` is pageable and dies with this scope
+  }
+  if (!R->srgbUploaded) {
+    float table[256];
+    for (int i = 0; i < 256; ++i) {
+      const double c = i / 255.0;
+      table[i] = (float)(c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
+    }
+    althea_raster::upload_srgb_table(table, stream);
+    CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+    R->srgbUploaded = true;
+  }
+  return ALTHEA_OK;
+}
+
+// setup (sized exactly, retried once if the tile work list was too small), then fill
+int runRaster(althea_cuda_ctx* ctx, RasterScratch* R, RasterJob& J, cudaStream_t stream) {
+  const unsigned long long pairs = (unsigned long long)J.triTotal * (unsigned)J.nViews;
+  if (!pairs) return ALTHEA_OK;
+  if (pairs > (1ull << 26)) return fail(ctx, ALTHEA_ERR_UNSUPPORTED, "%llu (triangle, view) pairs in one pass", pairs);
+  int rc = growScratch(ctx, &R->recs, &R->recsBytes, (size_t)pairs * sizeof(RasterRecord), "raster records");
+  if (rc) return rc;
+  size_t workItems = R->workBytes / sizeof(uint2);
+  if (workItems < (size_t)pairs + (1u << 20)) workItems = (size_t)pairs + (1u << 20);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if ((rc = growScratch(ctx, &R->work, &R->workBytes, workItems * sizeof(uint2), "raster tile work list"))) return rc;
+    J.recs = static_cast<RasterRecord*>(R->recs);
+    J.recCap = (uint32_t)pairs;
+    J.work = static_cast<uint2*>(R->work);
+    J.workCap = (uint32_t)(R->workBytes / sizeof(uint2));
+    J.counters = R->counters;
+    CUDA_TRY(ctx, cudaMemsetAsync(R->counters, 0, 4 * sizeof(uint32_t), stream));
+    timedLaunch(ctx, "raster_setup", stream, [&] { althea_raster::launch_raster_setup(J, stream); });
+    uint32_t c[4] = {0, 0, 0, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(c, R->counters, sizeof c, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+    if (!c[2]) {
+      if (c[1]) timedLaunch(ctx, "raster_fill", stream, [&] { althea_raster::launch_raster_fill(J, R->sms, stream); });
+      return ALTHEA_OK;
+    }
+    workItems = (size_t)c[1] + 1024; // the counter kept counting: the exact demand
+  }
+  return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "raster tile work list overflowed twice");
+}
+} // namespace
+
+extern "C" {
+int althea_cuda_draw_gbuffer(althea_cuda_ctx* ctx, const althea_global_uniforms* uniforms, const althea_primitive* primitives, uint32_t primitive_count,
+                             const althea_gbuffer* gbuffer, const althea_sync* sync) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  if (!uniforms || !gbuffer) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "uniforms and gbuffer must be non-null");
+  Resource *depth, *position, *normal, *albedo, *mro;
+  int rc;
+  if ((rc = getImage(ctx, gbuffer->depth, ALTHEA_FORMAT_R32_SFLOAT, "gbuffer.depth", &depth, true))) return rc;
+  if ((rc = getImage(ctx, gbuffer->position, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "gbuffer.position", &position, true))) return rc;
+  if ((rc = getImage(ctx, gbuffer->normal, ALTHEA_FORMAT_R16G16B16A16_SFLOAT, "gbuffer.normal", &normal, true))) return rc;
+  if ((rc = getImage(ctx, gbuffer->albedo, ALTHEA_FORMAT_R8G8B8A8_UNORM, "gbuffer.albedo", &albedo, true))) return rc;
+  if ((rc = getImage(ctx, gbuffer->mro, ALTHEA_FORMAT_R8G8B8A8_UNORM, "gbuffer.mro", &mro, true))) return rc;
+  Resource* all[5] = {depth, position, normal, albedo, mro};
+  Resource* first = nullptr;
+  for (Resource* r : all) {
+    if (!r) continue;
+    if (!first) first = r;
+    if (r->w != first->w || r->h != first->h) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "G-buffer attachments must all be %ux%u", first->w, first->h);
+  }
+  if (!first) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "gbuffer has no attachment to write");
+  if (first->w > 65535u || first->h > 65535u) return fail(ctx, ALTHEA_ERR_UNSUPPORTED, "frame larger than 65535 pixels on a side");
+  RasterScratch* R;
+  if ((rc = rasterScratch(ctx, &R))) return rc;
+  cudaStream_t stream;
+  if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  RasterJob J;
+  memset(&J, 0, sizeof J);
+  if ((rc = buildPrims(ctx, R, primitives, primitive_count, stream, &J.triTotal))) return rc;
+  J.prims = static_cast<const RasterPrim*>(R->prims);
+  J.nPrims = (int)primitive_count;
+  J.W = (int)first->w;
+  J.H = (int)first->h;
+  J.mode = RASTER_MODE_GBUFFER;
+  RasterView view;
+  memset(&view, 0, sizeof view);
+  matmul44(uniforms->projection, uniforms->view, view.a); // Gltf.vert:55 evaluates (projection * view) * worldPos
+  if ((rc = growScratch(ctx, &R->views, &R->viewsBytes, 8 * sizeof(RasterView), "raster views"))) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(R->views, &view, sizeof view, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+  J.views = static_cast<const RasterView*>(R->views);
+  J.nViews = 1;
+  const size_t px = (size_t)J.W * J.H;
+  if ((rc = growScratch(ctx, &R->vis, &R->visBytes, px * sizeof(unsigned long long), "visibility buffer"))) return rc;
+  J.vis = static_cast<unsigned long long*>(R->vis);
+  ImgView v;
+  if (depth) { levelView(*depth, 0, 0, &v); J.outDepth = static_cast<float*>(const_cast<void*>(v.ptr)); J.pitchDepth = v.pitch; }
+  if (position) { levelView(*position, 0, 0, &v); J.outPosition = static_cast<float4*>(const_cast<void*>(v.ptr)); J.pitchPosition = v.pitch; }
+  if (normal) { levelView(*normal, 0, 0, &v); J.outNormal = static_cast<uint2*>(const_cast<void*>(v.ptr)); J.pitchNormal = v.pitch; }
+  if (albedo) { levelView(*albedo, 0, 0, &v); J.outAlbedo = static_cast<uint32_t*>(const_cast<void*>(v.ptr)); J.pitchAlbedo = v.pitch; }
+  if (mro) { levelView(*mro, 0, 0, &v); J.outMro = static_cast<uint32_t*>(const_cast<void*>(v.ptr)); J.pitchMro = v.pitch; }
+  timedLaunch(ctx, "raster_clear", stream, [&] { althea_raster::launch_raster_clear(J.vis, nullptr, px, stream); });
+  if ((rc = runRaster(ctx, R, J, stream))) return rc;
+  timedLaunch(ctx, "gbuffer_resolve", stream, [&] { althea_raster::launch_gbuffer_resolve(J, stream); });
+  return endWork(ctx, sync, stream);
+}
+
+int althea_cuda_draw_shadow_cubes(althea_cuda_ctx* ctx, uint64_t lights_buf, uint32_t light_count, const althea_point_light_constants* constants,
+                                  const althea_primitive* primitives, uint32_t primitive_count, uint64_t shadow_cube_array, const althea_sync* sync) {
+  if (!ctx) return ALTHEA_ERR_INVALID_ARGUMENT;
+  if (!constants) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "constants must be non-null");
+  Resource* sh;
+  int rc = getImage(ctx, shadow_cube_array, ALTHEA_FORMAT_R32_SFLOAT, "shadow_cube_array", &sh);
+  if (rc) return rc;
+  if (sh->w != sh->h || sh->layers < 6u * light_count || sh->mips != 1 || sh->pitch0 != (size_t)sh->w * 4)
+    return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "shadow_cube_array needs square, tightly packed, single-mip faces and >= %u layers (has %u)", 6u * light_count, sh->layers);
+  if (sh->w > 65535u) return fail(ctx, ALTHEA_ERR_UNSUPPORTED, "shadow faces larger than 65535 pixels");
+  Resource* lb = light_count ? find(ctx, lights_buf, ResKind::Buffer) : nullptr;
+  if (light_count && (!lb || lb->bytes < (size_t)light_count * sizeof(althea_point_light)))
+    return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "lights_buf must hold %u althea_point_light records", light_count);
+  RasterScratch* R;
+  if ((rc = rasterScratch(ctx, &R))) return rc;
+  cudaStream_t stream;
+  if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  std::vector<althea_point_light> lights(light_count);
+  if (light_count) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(lights.data(), lb->dptr, light_count * sizeof(althea_point_light), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+  }
+  RasterJob J;
+  memset(&J, 0, sizeof J);
+  if ((rc = buildPrims(ctx, R, primitives, primitive_count, stream, &J.triTotal))) return rc;
+  J.prims = static_cast<const RasterPrim*>(R->prims);
+  J.nPrims = (int)primitive_count;
+  J.W = J.H = (int)sh->w;
+  J.mode = RASTER_MODE_SHADOW;
+  J.nViews = 6;
+  if ((rc = growScratch(ctx, &R->views, &R->viewsBytes, 8 * sizeof(RasterView), "raster views"))) return rc;
+  J.views = static_cast<const RasterView*>(R->views);
+  ImgView l0, l1;
+  levelView(*sh, 0, 0, &l0);
+  J.shadowLayerStride = sh->layers > 1 && levelView(*sh, 0, 1, &l1) ? (size_t)((const char*)l1.ptr - (const char*)l0.ptr) / sizeof(float) : (size_t)sh->w * sh->h;
+  const size_t facePx = (size_t)sh->w * sh->h;
+  for (uint32_t l = 0; l < light_count; ++l) {
+    RasterView views[6];
+    memset(views, 0, sizeof views);
+    for (int f = 0; f < 6; ++f) { // ShadowMapBindless.vert:44-47: csPos = views[gl_ViewIndex] * (worldPos - light), gl_Position = projection * csPos
+      memcpy(views[f].a, constants->views[f], sizeof views[f].a);
+      memcpy(views[f].b, constants->projection, sizeof views[f].b);
+      memcpy(views[f].off, lights[l].position, sizeof views[f].off);
+      views[f].hasB = 1;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(R->views, views, sizeof views, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+    ImgView base;
+    levelView(*sh, 0, 6u * l, &base);
+    J.shadowBase = static_cast<float*>(const_cast<void*>(base.ptr));
+    // the six layers of a light are contiguous: one clear
+    timedLaunch(ctx, "raster_clear", stream, [&] { althea_raster::launch_raster_clear(nullptr, J.shadowBase, J.shadowLayerStride * 5 + facePx, stream); });
+    if ((rc = runRaster(ctx, R, J, stream))) return rc;
+  }
+  return endWork(ctx, sync, stream);
 }
 } // extern "C"

@@ -264,6 +264,22 @@ class PointLightCollection:
         """cubes: (lights, 6, res, res) float32 holding length(p - light)/1000 (ShadowMapBindless.frag:41)."""
         self.shadow_map.tensor.view(dtype=_torch().float32).copy_(_torch().from_numpy(np.ascontiguousarray(cubes, np.float32).reshape(-1)))
 
+    def drawShadowMaps(self, models, stream: int = 0):
+        """PointLightCollection::drawShadowMaps (Src/PointLight.cpp:235-282): renders every light's six cube faces from the
+        models' primitives (`models`: althea_b200.model.UploadedModel instances)."""
+        from . import model as _model
+        if self.shadow_map is None or self.getCount() == 0:
+            return
+        self.updateResource()
+        if not hasattr(self, "_constants"):
+            self._constants = _model.point_light_constants()
+        ref, keep = _sync_ref(stream, self.ctx.device)
+        for k, m in enumerate(models):
+            if k > 0:
+                raise NotImplementedError("pass one UploadedModel holding all primitives (each call clears the cubes)")
+            self.ctx._check(self.ctx._lib.althea_cuda_draw_shadow_cubes(
+                self.ctx._ptr, self.buffer.handle, self.getCount(), C.byref(self._constants), m.array, m.count, self.shadow_map.handle, ref))
+
     @property
     def shadow_handle(self) -> int:
         return self.shadow_map.handle if self.shadow_map is not None else 0
@@ -295,6 +311,19 @@ class GBufferResources:
 
     def struct(self) -> _capi.GBuffer:
         return _capi.GBuffer(self.depth.handle, self.position.handle, self.normal.handle, self.albedo.handle, self.mro.handle)
+
+
+class SceneToGBufferPass:
+    """SceneToGBufferPass (Src/DeferredRendering.cpp:268-330) with the Gltf.vert/.frag subpass: rasterises a model's
+    primitives into the G-buffer attachments."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    def draw(self, globalUniforms: GlobalUniforms, model, gBuffer: GBufferResources, stream: int = 0):
+        gb = gBuffer.struct()
+        ref, keep = _sync_ref(stream, self.ctx.device)
+        self.ctx._check(self.ctx._lib.althea_cuda_draw_gbuffer(self.ctx._ptr, C.byref(globalUniforms), model.array, model.count, C.byref(gb), ref))
 
 
 class IBLResources:

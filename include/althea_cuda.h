@@ -181,6 +181,63 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
                                const althea_ibl* ibl, uint64_t lights_buf, uint64_t shadow_cube_array, uint64_t reflection,
                                uint64_t out_color, uint64_t ao_counts, uint32_t flags, const althea_sync* sync);
 
+/* ---- rasterising producers of the path's inputs ------------------------------------------ */
+/* The engine's own vertex, Include/Althea/Common/InstanceDataCommon.h:45-53 (what Primitive's VertexBuffer<Vertex> holds). */
+typedef struct althea_vertex {
+  float position[3], tangent[3], bitangent[3], normal[3];
+  float uvs[4][2];
+  float weights[4];
+  uint16_t joints[4];
+} althea_vertex; /* 104 bytes */
+
+/* sampler word: wrapU | wrapV << 2 | magNearest << 4 | minNearest << 5 | mipMode << 6 | srgb << 8, the SamplerOptions the
+ * reference derives from the glTF sampler (Src/Sampler.cpp:11-88); wrap: 0 REPEAT, 1 CLAMP_TO_EDGE, 2 MIRRORED_REPEAT;
+ * mipMode: 0 none, 1 NEAREST, 2 LINEAR. Filtering is isotropic (the reference enables the device's maximum anisotropy, which
+ * Vulkan leaves implementation-defined). */
+#define ALTHEA_SAMPLER_WORD(wrapU, wrapV, magNearest, minNearest, mipMode, srgb) \
+  ((uint32_t)(wrapU) | ((uint32_t)(wrapV) << 2) | ((uint32_t)(magNearest) << 4) | ((uint32_t)(minNearest) << 5) | ((uint32_t)(mipMode) << 6) | ((uint32_t)(srgb) << 8))
+typedef struct althea_texture_ref {
+  uint64_t image; /* R8G8B8A8_UNORM image handle with its mip chain; 0 => the reference's 1x1 default for the slot
+                     (white / normal1x1 / white, Src/Material.cpp:36-75, Src/DefaultTextures.cpp:24-31) */
+  uint32_t sampler;
+  uint32_t _pad;
+} althea_texture_ref;
+
+typedef struct althea_material { /* the MaterialConstants fields fetchMaterial reads, InstanceDataCommon.h:8-33 */
+  float baseColorFactor[4];
+  int32_t baseTextureCoordinateIndex, metallicRoughnessTextureCoordinateIndex;
+  float normalScale, metallicFactor, roughnessFactor, alphaCutoff;
+  althea_texture_ref baseTexture, normalTexture, metallicRoughnessTexture;
+} althea_material;
+
+typedef struct althea_primitive { /* one Primitive of a Model, as Model::draw / drawShadowMaps issue it */
+  uint64_t vertices; /* buffer of althea_vertex */
+  uint64_t indices;  /* buffer of uint32 (Primitive's IndexBuffer) */
+  uint32_t index_count;
+  uint32_t front_face_clockwise; /* Primitive::getFrontFace() == VK_FRONT_FACE_CLOCKWISE */
+  float model[16];               /* the node's transform, transformBuffer[nodeIdx] (Gltf.vert:49) */
+  althea_material material;
+} althea_primitive;
+
+typedef struct althea_point_light_constants { /* PointLightConstants, Src/PointLight.cpp:72-118 / Shaders/PointLights.glsl */
+  float projection[16], inverseProjection[16];
+  float views[6][16], inverseViews[6][16];
+} althea_point_light_constants;
+
+/* SceneToGBufferPass + Gltf.vert/.frag: rasterises the primitives in order (depth LESS, back faces culled, alpha-cutoff
+ * discard) into the G-buffer attachments; any of gbuffer's handles may be 0 (not written). position (legacy attachment)
+ * receives (world position, 1); uncovered pixels get the reference's clears (colour 0, depth 1). Skinned primitives:
+ * ALTHEA_ERR_UNSUPPORTED is never raised here because skinning data is not part of althea_primitive; pass skinned
+ * geometry pre-transformed. */
+int althea_cuda_draw_gbuffer(althea_cuda_ctx* ctx, const althea_global_uniforms* uniforms, const althea_primitive* primitives,
+                             uint32_t primitive_count, const althea_gbuffer* gbuffer, const althea_sync* sync);
+/* PointLightCollection::drawShadowMaps + ShadowMapBindless.vert/.frag: for every light, the 6 cube faces of
+ * shadow_cube_array (R32_SFLOAT, square, >= 6*light_count layers) receive min over fragments of length(p - light) / 1000,
+ * cleared to 1. Face cameras come from `constants` exactly as the reference's vertex shader reads them. */
+int althea_cuda_draw_shadow_cubes(althea_cuda_ctx* ctx, uint64_t lights_buf, uint32_t light_count,
+                                  const althea_point_light_constants* constants, const althea_primitive* primitives,
+                                  uint32_t primitive_count, uint64_t shadow_cube_array, const althea_sync* sync);
+
 /* ---- IBL precompute ------------------------------------------------------------------------------------------------ */
 #define ALTHEA_IBL_LAYOUT_EQUIRECT 0u   /* the reference's layout: outputs are equirect images */
 #define ALTHEA_IBL_LAYOUT_CUBE 1u       /* BASELINE config 2: outputs are 6-layer cube images */

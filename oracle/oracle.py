@@ -26,7 +26,7 @@ def build(force: bool = False) -> str:
     """Compiles the restatement with oracle/Makefile (gcc only; building the checker is not using it)."""
     if force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-        for f in ("althea_oracle.cpp", "althea_oracle_ibl.cpp", "oracle_math.h", "Makefile")
+        for f in ("althea_oracle.cpp", "althea_oracle_ibl.cpp", "althea_oracle_raster.cpp", "oracle_math.h", "Makefile")
     ):
         subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -228,4 +228,83 @@ def ibl_prefilter(chain, W, H, mips, out_w, out_h, roughness, texels, layout=LAY
 def brdf_lut(size, samples=1024, k_mode=0):
     out = np.empty((size, size, 2), np.float32)
     lib().oracle_brdf_lut(size, samples, k_mode, _p(out))
+    return out
+
+
+# ---- rasterising producers (althea_oracle_raster.cpp) ---------------------------------------------------------------------
+class _Tex(C.Structure):
+    _fields_ = [("texels", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("mips", C.c_int32), ("sampler", C.c_uint32)]
+
+
+class _Prim(C.Structure):
+    _fields_ = [("verts", C.c_void_p), ("idx", C.c_void_p), ("triCount", C.c_uint32), ("frontCW", C.c_uint32), ("model", C.c_float * 16),
+                ("baseColorFactor", C.c_float * 4), ("baseUv", C.c_int32), ("mrUv", C.c_int32), ("normalScale", C.c_float),
+                ("metallicFactor", C.c_float), ("roughnessFactor", C.c_float), ("alphaCutoff", C.c_float), ("base", _Tex), ("normal", _Tex),
+                ("mr", _Tex)]
+
+
+def _prim_array(prims):
+    """prims: objects with .vertices (n, 26) f32, .indices u32, .model (row-major 4x4), .front_face_clockwise, .material (the
+    fields of MaterialConstants; textures with .levels (list of (h, w, 4) u8) and .sampler). Returns (ctypes array, keep-alive)."""
+    arr = (_Prim * max(1, len(prims)))()
+    keep = []
+
+    def tex(t):
+        r = _Tex()
+        if t is None:
+            return r
+        packed = np.concatenate([np.ascontiguousarray(l, np.uint8).reshape(-1) for l in t.levels])
+        keep.append(packed)
+        r.texels = packed.ctypes.data
+        r.w, r.h, r.mips, r.sampler = t.levels[0].shape[1], t.levels[0].shape[0], len(t.levels), t.sampler
+        return r
+
+    for i, p in enumerate(prims):
+        v = np.ascontiguousarray(p.vertices, np.float32)
+        ix = np.ascontiguousarray(p.indices, np.uint32)
+        keep += [v, ix]
+        a = arr[i]
+        a.verts, a.idx = v.ctypes.data, ix.ctypes.data
+        a.triCount = len(ix) // 3
+        a.frontCW = int(p.front_face_clockwise)
+        cm = np.asarray(p.model, np.float32).T.reshape(-1)
+        m = p.material
+        for k in range(16):
+            a.model[k] = float(cm[k])
+        for k in range(4):
+            a.baseColorFactor[k] = float(m.baseColorFactor[k])
+        a.baseUv, a.mrUv = m.baseTextureCoordinateIndex, m.metallicRoughnessTextureCoordinateIndex
+        a.normalScale, a.metallicFactor, a.roughnessFactor, a.alphaCutoff = m.normalScale, m.metallicFactor, m.roughnessFactor, m.alphaCutoff
+        a.base, a.normal, a.mr = tex(m.baseTexture), tex(m.normalTexture), tex(m.metallicRoughnessTexture)
+    return arr, keep
+
+
+def draw_gbuffer(projection, view, prims, W: int, H: int) -> dict:
+    """Gltf.vert/.frag through a LESS depth test. projection / view: 16 floats, column-major. Returns depth (H, W) f32,
+    position / normal (H, W, 4) f32, albedo / mro (H, W, 4) u8, tri (H, W) u32 (draw-order triangle ordinal, 0xffffffff = none)."""
+    arr, keep = _prim_array(prims)
+    pj = np.ascontiguousarray(projection, np.float32).reshape(-1)
+    vw = np.ascontiguousarray(view, np.float32).reshape(-1)
+    out = {"depth": np.empty((H, W), np.float32), "position": np.empty((H, W, 4), np.float32), "normal": np.empty((H, W, 4), np.float32),
+           "albedo": np.empty((H, W, 4), np.uint8), "mro": np.empty((H, W, 4), np.uint8), "tri": np.empty((H, W), np.uint32)}
+    f = lib().oracle_draw_gbuffer
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+    f(pj.ctypes.data, vw.ctypes.data, C.addressof(arr), len(prims), W, H, out["depth"].ctypes.data, out["position"].ctypes.data,
+      out["normal"].ctypes.data, out["albedo"].ctypes.data, out["mro"].ctypes.data, out["tri"].ctypes.data)
+    return out
+
+
+def draw_shadow_cubes(lights, projection, views, prims, res: int) -> np.ndarray:
+    """ShadowMapBindless.vert/.frag. lights: (n, 8) f32 PointLight records; projection 16 floats; views (6, 16), column-major.
+    Returns (n, 6, res, res) f32 holding min length(p - light) / 1000, 1.0 where nothing was drawn."""
+    arr, keep = _prim_array(prims)
+    lt = np.ascontiguousarray(lights, np.float32).reshape(-1, 8)
+    pj = np.ascontiguousarray(projection, np.float32).reshape(-1)
+    vw = np.ascontiguousarray(views, np.float32).reshape(-1)
+    out = np.empty((lt.shape[0], 6, res, res), np.float32)
+    f = lib().oracle_draw_shadow_cubes
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    f(lt.ctypes.data, lt.shape[0], pj.ctypes.data, vw.ctypes.data, C.addressof(arr), len(prims), res, out.ctypes.data)
     return out

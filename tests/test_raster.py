@@ -1,0 +1,421 @@
+"""The rasterising producers: G-buffer pass and omni shadow cubes.
+
+CPU tests pin the restatement's rules (oracle/althea_oracle_raster.cpp) on cases with known answers: pixel-aligned quads
+(top-left rule), watertight shared edges, draw-order depth ties, culling, triangles through the eye plane, and the consistency
+of the produced shadow cubes with the cube lookup the deferred pass performs. GPU tests compare the CUDA path with the
+restatement: depth bit for bit, shaded attributes within tolerance.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from althea_b200 import model, scene
+from helpers import REFERENCE
+
+NONE = 0xFFFFFFFF
+
+
+def _camera(W, H, pos=(0.0, 0.0, 4.0), yaw=0.0, pitch=0.0):
+    g = scene.make_uniforms(W, H, pos=pos, yaw=yaw, pitch=pitch)
+    return g, list(g.projection), list(g.view)
+
+
+def _tri_prim(points, uv=None, front_cw=False):
+    p = np.asarray(points, np.float32).reshape(-1, 3)
+    n = np.tile(np.array([[0.0, 0.0, 1.0]], np.float32), (len(p), 1))
+    v = model.make_vertices(p, n, uv)
+    return model.PrimitiveData(v, np.arange(len(p), dtype=np.uint32), front_face_clockwise=front_cw)
+
+
+def _ortho_like(W, H):
+    """A camera whose pixel grid maps to world units exactly: eye at z = d, plane z = 0 spans W x H world units."""
+    # perspective with fov such that at distance d the view height is H: tan(fov/2) = H / (2 d)
+    d = 64.0
+    fov = 2.0 * np.degrees(np.arctan(H / (2.0 * d)))
+    g = scene.make_uniforms(W, H, pos=(0.0, 0.0, d), yaw=0.0, pitch=0.0, fov_deg=float(fov))
+    return g, list(g.projection), list(g.view)
+
+
+def _world_of_pixel_corner(W, H, x, y):
+    """world position on the plane z = 0 of pixel-grid coordinate (x, y) (corner coordinates, y down)."""
+    return (x - W / 2.0, H / 2.0 - y, 0.0)
+
+
+# ---- CPU: the restatement's rules ------------------------------------------------------------------------------------------
+def test_top_left_rule_on_a_pixel_aligned_quad(oracle):
+    W, H = 32, 16
+    g, proj, view = _ortho_like(W, H)
+    c = [_world_of_pixel_corner(W, H, x, y) for x, y in ((4, 3), (4, 9), (12, 9), (12, 3))]  # counter-clockwise on screen (y down)
+    q = model.quad(c)
+    out = oracle.draw_gbuffer(proj, view, [q], W, H)
+    cov = out["tri"] != NONE
+    expect = np.zeros((H, W), bool)
+    expect[3:9, 4:12] = True  # pixel centres x + 0.5 in [4, 12), y + 0.5 in [3, 9)
+    assert np.array_equal(cov, expect)
+
+
+def test_shared_edges_are_watertight_and_exclusive(oracle):
+    """A fan of triangles around an interior vertex at an awkward position: every pixel inside the outline is covered, and
+    each by the triangle whose interior holds its centre (no double hits are observable through ids, so: no holes)."""
+    W, H = 64, 48
+    g, proj, view = _camera(W, H, pos=(0.1, -0.07, 3.0))
+    rng = np.random.default_rng(3)
+    centre = np.array([0.013, 0.021, 0.0])
+    ring = [np.array([np.cos(a), np.sin(a), 0.0]) * (1.0 + 0.2 * rng.random()) for a in np.linspace(0, 2 * np.pi, 13)[:-1]]
+    pts = []
+    for i in range(12):
+        pts += [centre, ring[i], ring[(i + 1) % 12]]
+    out = oracle.draw_gbuffer(proj, view, [_tri_prim(pts)], W, H)
+    cov = out["tri"] != NONE
+    # the union is a star-shaped polygon: compare with a point-in-polygon test away from the outline
+    ys, xs = np.nonzero(cov)
+    assert cov.sum() > 400
+    # no holes: every covered row is one contiguous run
+    for y in np.unique(ys):
+        row = np.nonzero(cov[y])[0]
+        assert row[-1] - row[0] + 1 == len(row)
+
+
+def test_depth_ties_keep_the_first_drawn(oracle):
+    W, H = 32, 32
+    g, proj, view = _camera(W, H)
+    tri = [(-1, -1, 0), (1, -1, 0), (0, 1, 0)]
+    a, b = _tri_prim(tri), _tri_prim(tri)
+    out = oracle.draw_gbuffer(proj, view, [a, b], W, H)
+    ids = out["tri"][out["tri"] != NONE]
+    assert len(ids) > 50 and (ids == 0).all()
+    # a nearer triangle drawn later wins
+    c = _tri_prim([(-1, -1, 0.5), (1, -1, 0.5), (0, 1, 0.5)])
+    out = oracle.draw_gbuffer(proj, view, [a, c], W, H)
+    assert (out["tri"][H // 2, W // 2] == 1)
+
+
+def test_back_faces_are_culled_unless_the_front_face_is_clockwise(oracle):
+    W, H = 32, 32
+    g, proj, view = _camera(W, H)
+    ccw = [(-1, -1, 0), (1, -1, 0), (0, 1, 0)]  # counter-clockwise seen from +z (the camera side)
+    cw = [ccw[0], ccw[2], ccw[1]]
+    assert (oracle.draw_gbuffer(proj, view, [_tri_prim(ccw)], W, H)["tri"] != NONE).sum() > 50
+    assert (oracle.draw_gbuffer(proj, view, [_tri_prim(cw)], W, H)["tri"] != NONE).sum() == 0
+    assert (oracle.draw_gbuffer(proj, view, [_tri_prim(cw, front_cw=True)], W, H)["tri"] != NONE).sum() > 50
+    assert (oracle.draw_gbuffer(proj, view, [_tri_prim(ccw, front_cw=True)], W, H)["tri"] != NONE).sum() == 0
+
+
+def test_triangle_through_the_eye_plane(oracle):
+    """A ground quad that extends behind the camera: the visible part is everything below the horizon, depth grows towards it,
+    reconstructed positions lie on the plane."""
+    W, H = 64, 36
+    g, proj, view = _camera(W, H, pos=(0.0, 1.0, 0.0))
+    floor = model.quad([(-50, 0, 50), (50, 0, 50), (50, 0, -50), (-50, 0, -50)])
+    out = oracle.draw_gbuffer(proj, view, [floor], W, H)
+    cov = out["tri"] != NONE
+    assert cov[H // 2 + 1:].all() and not cov[: H // 2 - 1].any()
+    assert np.abs(out["position"][cov][:, 1]).max() < 1e-3
+    col = out["depth"][H // 2 + 1:, W // 2]
+    assert (np.diff(col) < 0).all()  # nearer (smaller depth) towards the bottom of the screen
+    n = out["normal"][cov][:, :3]
+    assert np.abs(n - np.array([0, 1, 0])).max() < 5e-3  # normal1x1.png is (128, 128, 255): a 0.0039 tilt
+
+
+def test_material_fetch(oracle):
+    """Flat normal map and white defaults; factors, the .bg swizzle of metallic-roughness, ao = 0, alpha in normal.a / mro.a."""
+    W, H = 16, 16
+    g, proj, view = _camera(W, H, pos=(0.0, 0.0, 1.0))
+    q = model.quad([(-2, -2, 0), (2, -2, 0), (2, 2, 0), (-2, 2, 0)])
+    q.material = model.MaterialData(baseColorFactor=(0.5, 0.25, 1.0, 0.8), metallicFactor=0.3, roughnessFactor=0.6)
+    mr = np.zeros((4, 4, 4), np.uint8)
+    mr[...] = (10, 204, 102, 255)  # roughness from .g = 0.8, metallic from .b = 0.4
+    q.material.metallicRoughnessTexture = model.TextureData.from_rgba8(mr, model.sampler_word())
+    out = oracle.draw_gbuffer(proj, view, [q], W, H)
+    assert (out["tri"] != NONE).all()
+    assert np.array_equal(out["albedo"][8, 8], [128, 64, 255, 204])
+    assert np.array_equal(out["mro"][8, 8], [round(0.4 * 0.3 * 255), round(0.8 * 0.6 * 255), 0, 204])
+    assert np.abs(out["normal"][8, 8] - [0, 0, 1, 0.8]).max() < 5e-3  # normal1x1.png is (128, 128, 255): 2*128/255 - 1 = 0.0039
+    # alpha below the cutoff discards every fragment
+    q.material.baseColorFactor = (1, 1, 1, 0.4)
+    assert (oracle.draw_gbuffer(proj, view, [q], W, H)["tri"] == NONE).all()
+
+
+def test_mip_selection_and_wrap(oracle):
+    """A 2-texel checker minified heavily averages to grey through the mip chain; magnified it keeps its two colours."""
+    W, H = 32, 32
+    tex = model.checker_texture(size=64, cells=64, a=(255, 255, 255, 255), b=(0, 0, 0, 255), sampler=model.sampler_word(srgb=False))
+    far = model.quad([(-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0)], uv_scale=8.0)
+    far.material.baseTexture = tex
+    g, proj, view = _camera(W, H, pos=(0.0, 0.0, 6.0))
+    out = oracle.draw_gbuffer(proj, view, [far], W, H)
+    a = out["albedo"][out["tri"] != NONE][:, 0].astype(int)
+    assert len(a) > 20 and np.abs(a - 128).max() <= 2
+    near = model.quad([(-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0)], uv_scale=4.0 / 64.0)
+    near.material.baseTexture = tex
+    g, proj, view = _camera(W, H, pos=(0.0, 0.0, 1.2))
+    out = oracle.draw_gbuffer(proj, view, [near], W, H)
+    a = out["albedo"][..., 0]
+    assert a.max() >= 240 and a.min() <= 15
+
+
+def _shadow_scene():
+    """A closed room (inward-facing walls) with a sphere in it."""
+    sp = model.uv_sphere(0.8, (0.5, 0.6, -0.4), 10, 20)
+    floor = model.quad([(-6, -1, 6), (6, -1, 6), (6, -1, -6), (-6, -1, -6)])
+    ceil = model.quad([(-6, 5, -6), (6, 5, -6), (6, 5, 6), (-6, 5, 6)])
+    back = model.quad([(-6, -1, -5), (6, -1, -5), (6, 6, -5), (-6, 6, -5)])
+    front = model.quad([(6, -1, 6), (-6, -1, 6), (-6, 6, 6), (6, 6, 6)])
+    left = model.quad([(-6, -1, 6), (-6, -1, -6), (-6, 6, -6), (-6, 6, 6)])
+    right = model.quad([(6, -1, -6), (6, -1, 6), (6, 6, 6), (6, 6, -6)])
+    return [sp, floor, ceil, back, front, left, right]
+
+
+def _cube_lookup(cubes, d):
+    """The Vulkan cube face selection and (s, t) the deferred pass uses (frame_kernels.cu sampleShadowCube), nearest texel."""
+    ax, ay, az = np.abs(d)
+    if ax >= ay and ax >= az:
+        face, sc, tc, ma = (0, -d[2], -d[1], ax) if d[0] >= 0 else (1, d[2], -d[1], ax)
+    elif ay >= az:
+        face, sc, tc, ma = (2, d[0], d[2], ay) if d[1] >= 0 else (3, d[0], -d[2], ay)
+    else:
+        face, sc, tc, ma = (4, d[0], -d[1], az) if d[2] >= 0 else (5, -d[0], -d[1], az)
+    res = cubes.shape[-1]
+    s, t = 0.5 * sc / ma + 0.5, 0.5 * tc / ma + 0.5
+    return face, min(int(s * res), res - 1), min(int(t * res), res - 1)
+
+
+def test_shadow_cubes_agree_with_the_deferred_pass_lookup(oracle):
+    """The producer's faces against the lookup the consumer performs (PointLights.glsl samples the cube with (L.x, -L.y, -L.z),
+    L = light - surface): for points of a closed room, the texel the consumer reads must hold the point's own distance when
+    the point is lit and a smaller one when the sphere shadows it. The +-X and +-Z faces satisfy this as rendered. The
+    reference's +-Y face cameras are rotated by 180 degrees about the face axis (yaw = 180 at pitch = +-90,
+    Src/PointLight.cpp:100-108): a faithful producer reproduces that, so on those faces the agreement holds after rotating the
+    face, and NOT as rendered (asserted too: it documents the reference's behaviour)."""
+    pc = model.point_light_constants()
+    views = np.array([list(pc.views[f]) for f in range(6)], np.float32)
+    light = np.array([0.3, 2.0, 0.7], np.float32)
+    lights = np.zeros((1, 8), np.float32)
+    lights[0, :3] = light
+    res = 128
+    cubes = oracle.draw_shadow_cubes(lights, list(pc.projection), views, _shadow_scene(), res)[0]
+    assert all((cubes[f] < 1).mean() > 0.99 for f in range(6))  # a closed room: every face sees geometry
+    centre, radius = np.array([0.5, 0.6, -0.4]), 0.8
+
+    def occluded(p):
+        d = light - p
+        ln = np.linalg.norm(d)
+        d = d / ln
+        oc = p - centre
+        b, c = np.dot(oc, d), np.dot(oc, oc) - radius * radius
+        disc = b * b - c
+        return disc > 0 and 0 < -b - np.sqrt(disc) < ln
+
+    rng = np.random.default_rng(11)
+    stats = {flip: {f: [0, 0, 0, 0] for f in range(6)} for flip in (False, True)}  # lit ok, lit n, shadowed ok, shadowed n
+    for _ in range(8000):
+        k = rng.integers(0, 6)
+        a, b = rng.uniform(-5.5, 5.5), rng.uniform(-4.5, 5.5)
+        h = rng.uniform(-0.5, 4.5)
+        p = np.array([(a, -1.0, b), (a, 5.0, b), (a, h, -5.0), (a, h, 6.0), (-6.0, h, b), (6.0, h, b)][k])
+        L = light - p
+        dist = np.linalg.norm(L)
+        face, sx, sy = _cube_lookup(cubes, np.array([L[0], -L[1], -L[2]]) / dist)
+        shadowed = occluded(p)
+        for flip in (False, True):
+            x, y = (res - 1 - sx, res - 1 - sy) if (flip and face in (2, 3)) else (sx, sy)
+            stored = cubes[face, y, x] * 1000.0
+            st = stats[flip][face]
+            if shadowed:
+                st[3] += 1
+                st[2] += stored < dist - 0.3
+            else:
+                st[1] += 1
+                st[0] += abs(stored - dist) < 0.02 * dist + 0.05
+    for f in range(6):
+        lit_ok, lit_n, sh_ok, sh_n = stats[True][f]
+        assert lit_n > 100 and lit_ok / lit_n > 0.99, (f, stats[True][f])
+        if sh_n > 50:
+            assert sh_ok / sh_n > 0.9, (f, stats[True][f])
+    lit_ok, lit_n, sh_ok, sh_n = stats[False][3]  # the -Y face as rendered does not line up with the lookup
+    assert sh_n > 50 and sh_ok / sh_n < 0.2 and lit_ok / lit_n < 0.9
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REFERENCE, "Content/Models/DamagedHelmet.glb")), reason="reference not mounted (GPU box)")
+def test_glb_loader_on_the_reference_asset(oracle):
+    prims = model.load_glb(os.path.join(REFERENCE, "Content/Models/DamagedHelmet.glb"), max_texture_size=256)
+    assert sum(p.triangle_count for p in prims) == 46356 // 3  # 46 356 indices
+    p = prims[0]
+    assert p.material.baseTexture is not None and p.material.normalTexture is not None and p.material.metallicRoughnessTexture is not None
+    nrm = p.vertices[:, 9:12]
+    assert np.abs(np.linalg.norm(nrm, axis=1) - 1).max() < 1e-3
+    t = p.vertices[:, 3:6]
+    assert np.abs(np.sum(t * nrm, axis=1)).max() < 1e-3
+    W, H = 96, 54
+    g, proj, view = _camera(W, H, pos=(0.0, 0.0, 3.0))
+    out = oracle.draw_gbuffer(proj, view, prims, W, H)
+    cov = out["tri"] != NONE
+    assert 0.05 < cov.mean() < 0.6
+    assert np.abs(np.linalg.norm(out["normal"][cov][:, :3], axis=1) - 1).max() < 1e-4
+
+
+# ---- GPU: the CUDA path against the restatement ---------------------------------------------------------------------------
+def _gpu_gbuffer(ctx, uniforms, prims, W, H):
+    import torch
+
+    from althea_b200 import engine
+    up = model.UploadedModel(ctx, prims)
+    gb = engine.GBufferResources(ctx, W, H)
+    engine.SceneToGBufferPass(ctx).draw(uniforms, up, gb)
+    torch.cuda.synchronize()
+    return {
+        "depth": gb.depth.tensor.view(torch.float32).view(H, W).cpu().numpy(),
+        "position": gb.position.tensor.view(torch.float32).view(H, W, 4).cpu().numpy(),
+        "normal": gb.normal.tensor.view(torch.float16).view(H, W, 4).float().cpu().numpy(),
+        "albedo": gb.albedo.tensor.view(H, W, 4).cpu().numpy(),
+        "mro": gb.mro.tensor.view(H, W, 4).cpu().numpy(),
+    }, gb
+
+
+def _compare_gbuffer(got, want, exact=True, max_bad=0):
+    cov = want["tri"] != NONE
+    if exact:
+        assert np.array_equal(got["depth"].view(np.uint32), want["depth"].view(np.uint32))
+        same = np.ones_like(cov)
+    else:
+        same = got["depth"].view(np.uint32) == want["depth"].view(np.uint32)
+        assert (~same).sum() <= max_bad, "%d pixels differ in depth" % (~same).sum()
+    m = cov & same
+    assert np.abs(got["position"][m] - want["position"][m]).max() <= 1e-4 * max(1.0, np.abs(want["position"][m]).max())
+    assert np.abs(got["normal"][m] - want["normal"][m]).max() <= 2e-3  # RGBA16F storage
+    assert np.abs(got["albedo"][m].astype(int) - want["albedo"][m].astype(int)).max() <= 1
+    assert np.abs(got["mro"][m].astype(int) - want["mro"][m].astype(int)).max() <= 1
+    e = ~cov & same
+    assert (got["albedo"][e] == 0).all() and (got["normal"][e] == 0).all() and (got["position"][e] == 0).all()
+
+
+def _textured_scene():
+    sp = model.uv_sphere(1.0, (0.0, 0.0, 0.0), 24, 48)
+    sp.material = model.MaterialData(baseColorFactor=(1.0, 0.9, 0.8, 1.0), metallicFactor=0.7, roughnessFactor=0.9, normalScale=0.8)
+    sp.material.baseTexture = model.checker_texture(64, 8)
+    rng = np.random.default_rng(5)
+    nm = np.zeros((32, 32, 4), np.uint8)
+    nm[..., :2] = rng.integers(96, 160, (32, 32, 2))
+    nm[..., 2:] = 255
+    sp.material.normalTexture = model.TextureData.from_rgba8(nm, model.sampler_word(model.WRAP_MIRROR, model.WRAP_CLAMP))
+    mr = rng.integers(0, 256, (16, 16, 4)).astype(np.uint8)
+    sp.material.metallicRoughnessTexture = model.TextureData.from_rgba8(mr, model.sampler_word(mip_mode=model.MIP_NEAREST))
+    floor = model.quad([(-4, -1, 4), (4, -1, 4), (4, -1, -4), (-4, -1, -4)], 6.0)
+    floor.material.baseTexture = model.checker_texture(128, 16, sampler=model.sampler_word(srgb=True))
+    floor.model = np.array([[1, 0, 0, 0.2], [0, 1, 0, 0.0], [0, 0, 1, -0.3], [0, 0, 0, 1]], np.float32)
+    return [sp, floor]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [(160, 90), (257, 131)])
+def test_gpu_gbuffer_matches_the_restatement(ctx_fast, oracle, size):
+    W, H = size
+    g, proj, view = _camera(W, H, pos=(0.3, 0.8, 3.5), yaw=0.1, pitch=-0.2)
+    prims = _textured_scene()
+    want = oracle.draw_gbuffer(proj, view, prims, W, H)
+    got, _ = _gpu_gbuffer(ctx_fast, g, prims, W, H)
+    assert 0.3 < (want["tri"] != NONE).mean() < 1.0
+    _compare_gbuffer(got, want)
+
+
+@pytest.mark.gpu
+def test_gpu_triangle_soup_and_eye_plane_crossings(ctx_fast, oracle):
+    """Random triangles all around (and through) the camera, degenerate ones included: depth must match bit for bit."""
+    W, H = 192, 108
+    rng = np.random.default_rng(17)
+    pts = rng.uniform(-6, 6, (600, 3, 3)).astype(np.float32)
+    pts[::50, 2] = pts[::50, 1]  # degenerate: two equal vertices
+    soup = _tri_prim(pts.reshape(-1, 3))
+    floor = model.quad([(-50, -1.5, 50), (50, -1.5, 50), (50, -1.5, -50), (-50, -1.5, -50)])
+    g, proj, view = _camera(W, H, pos=(0.0, 0.0, 0.0))
+    prims = [soup, floor, _tri_prim(pts[::-1].reshape(-1, 3), front_cw=True)]
+    want = oracle.draw_gbuffer(proj, view, prims, W, H)
+    got, _ = _gpu_gbuffer(ctx_fast, g, prims, W, H)
+    assert (want["tri"] != NONE).mean() > 0.5
+    _compare_gbuffer(got, want)
+
+
+@pytest.mark.gpu
+def test_gpu_alpha_cutout(ctx_fast, oracle):
+    W, H = 128, 96
+    q = model.quad([(-1.5, -1, 0), (1.5, -1, 0), (1.5, 1, 0), (-1.5, 1, 0)], 1.0)
+    q.material.baseTexture = model.checker_texture(32, 8, alpha_holes=True, sampler=model.sampler_word(srgb=True, mag_nearest=True, mip_mode=model.MIP_NONE))
+    back = model.quad([(-3, -2, -1), (3, -2, -1), (3, 2, -1), (-3, 2, -1)])
+    g, proj, view = _camera(W, H, pos=(0.2, 0.1, 2.5))
+    want = oracle.draw_gbuffer(proj, view, [q, back], W, H)
+    got, _ = _gpu_gbuffer(ctx_fast, g, [q, back], W, H)
+    ids = want["tri"]
+    assert (ids < 2).mean() > 0.1 and ((ids >= 2) & (ids != NONE)).mean() > 0.3  # holes show the quad behind
+    # the alpha test compares a filtered value with the cutoff; contraction differences may move a handful of pixels
+    _compare_gbuffer(got, want, exact=False, max_bad=int(0.001 * W * H))
+
+
+@pytest.mark.gpu
+def test_gpu_shadow_cubes_match_the_restatement(ctx_fast, oracle):
+    import torch
+
+    from althea_b200 import engine
+    res = 64
+    prims = _shadow_scene()
+    lights = engine.PointLightCollection(ctx_fast, 3, shadow_res=res)
+    pos = [(0.3, 2.0, 0.7), (-2.0, 0.5, 1.0), (4.0, 3.0, -3.0)]
+    for i, p in enumerate(pos):
+        lights.setLight(i, engine.PointLight(p, (10.0, 10.0, 10.0)))
+    up = model.UploadedModel(ctx_fast, prims)
+    lights.drawShadowMaps([up])
+    torch.cuda.synchronize()
+    got = lights.shadow_map.tensor.view(torch.float32).view(3, 6, res, res).cpu().numpy()
+    pc = model.point_light_constants()
+    views = np.array([list(pc.views[f]) for f in range(6)], np.float32)
+    lt = np.zeros((3, 8), np.float32)
+    lt[:, :3] = pos
+    want = oracle.draw_shadow_cubes(lt, list(pc.projection), views, prims, res)
+    assert (want < 1).mean() > 0.9
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_gpu_produced_gbuffer_feeds_the_deferred_chain(ctx_fast):
+    """Producer -> consumer at 4K: G-buffer and shadow cubes rasterised from meshes, then SSR capture, glossy mips, SSAO and
+    deferred shading on them; determinism, finiteness, coverage consistent between attachments."""
+    import torch
+
+    from althea_b200 import _capi, engine
+    from helpers import FrameData, GpuFrame
+    W, H = 3840, 2160
+    prims = _textured_scene() + [model.uv_sphere(0.5, (1.6, -0.5, 0.8), 32, 64)]
+    g = scene.make_uniforms(W, H, pos=(0.3, 0.8, 3.5), yaw=0.1, pitch=-0.2, light_count=2)
+    up = model.UploadedModel(ctx_fast, prims)
+    gb = engine.GBufferResources(ctx_fast, W, H)
+    gpass = engine.SceneToGBufferPass(ctx_fast)
+    gpass.draw(g, up, gb)
+    torch.cuda.synchronize()
+    d1 = gb.depth.tensor.clone()
+    n1 = gb.normal.tensor.clone()
+    gpass.draw(g, up, gb)
+    torch.cuda.synchronize()
+    assert torch.equal(d1, gb.depth.tensor) and torch.equal(n1, gb.normal.tensor)  # atomicMin resolution is order-independent
+    depth = gb.depth.tensor.view(torch.float32).view(H, W)
+    pos = gb.position.tensor.view(torch.float32).view(H, W, 4)
+    nrm = gb.normal.tensor.view(torch.float16).view(H, W, 4).float()
+    cov = depth < 1.0
+    assert 0.3 < float(cov.float().mean()) < 1.0
+    assert bool(((pos[..., 3] == 1.0) == cov).all()) and bool(((nrm[..., 3] > 0) == cov).all())
+    assert float((nrm[cov][:, :3].norm(dim=1) - 1).abs().max()) < 2e-3
+    lights = engine.PointLightCollection(ctx_fast, 2, shadow_res=256)
+    lights.setLight(0, engine.PointLight((2.0, 3.0, 2.0), (30.0, 28.0, 25.0)))
+    lights.setLight(1, engine.PointLight((-2.5, 1.5, 1.0), (10.0, 14.0, 20.0)))
+    lights.drawShadowMaps([up])
+    small = GpuFrame(ctx_fast, FrameData("scene", 32, 18, n_lights=0))  # its IBL set
+    ssr = engine.ScreenSpaceReflection(ctx_fast, W, H)
+    dp = engine.DeferredPass(ctx_fast, W, H, _capi.FORMAT_R16G16B16A16_SFLOAT)
+    ssr.captureReflection(g, gb, small.ibl, lights)
+    ssr.convolveReflectionBuffer()
+    dp.draw(g, gb, small.ibl, lights, ssr, 0)
+    torch.cuda.synchronize()
+    col = dp.colorTarget.tensor.view(torch.float16).view(H, W, 4).float()
+    assert bool(torch.isfinite(col).all())
+    assert float(col[..., :3][cov].mean()) > 0.02
+    shadow = lights.shadow_map.tensor.view(torch.float32)
+    assert 0.05 < float((shadow < 1).float().mean()) <= 1.0  # an open scene: most directions see nothing
