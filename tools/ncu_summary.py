@@ -108,6 +108,7 @@ def traffic(path: str, out: str):
             "XU pipe": "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"}
     for r in rows[2:]:
         name = r[col["Kernel Name"]].split("(")[0].replace("_kernel", "").split("::")[-1]
+        name = name.replace("void ", "").split("<")[0]  # template instantiations (ssao<0>, glossy_convolve_staged<32, 32>) share a row
         rd = float(r[col["dram__bytes_read.sum"]].replace(",", "")) * scale[units[col["dram__bytes_read.sum"]]]
         wr = float(r[col["dram__bytes_write.sum"]].replace(",", "")) * scale[units[col["dram__bytes_write.sum"]]]
         util = {k: float(r[col[m]].replace(",", "")) for k, m in busy.items() if m in col and r[col[m]] != ""}
