@@ -64,16 +64,22 @@ struct TriGeom {
   F3 cs[3]; // shadow pass: view-space position / w
 };
 
-// Gltf.vert:52-56 (clip = (projection * view) * worldPos, the product formed on the host) and ShadowMapBindless.vert:44-47
-RDEV void triTransform(const RasterPrim& p, uint32_t t, const RasterView& v, TriGeom& g) {
+// Gltf.vert:52-53 / ShadowMapBindless.vert:44: world position of the triangle's vertices (view-independent)
+RDEV void triWorld(const RasterPrim& p, uint32_t t, TriGeom& g) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const uint32_t i = __ldg(p.idx + 3u * t + k);
     g.vi[k] = i;
     const float* pos = p.verts[i].position;
     const float px = __ldg(pos), py = __ldg(pos + 1), pz = __ldg(pos + 2);
-    const F4 w = mulMV(p.model, px, py, pz, 1.0f);
-    g.world[k] = w;
+    g.world[k] = mulMV(p.model, px, py, pz, 1.0f);
+  }
+}
+// Gltf.vert:55 (clip = (projection * view) * worldPos, the product formed on the host) and ShadowMapBindless.vert:45-49
+RDEV void triClip(const RasterView& v, TriGeom& g) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const F4 w = g.world[k];
     if (v.hasB) {
       const F4 c = mulMV(v.a, subr(w.x, v.off[0]), subr(w.y, v.off[1]), subr(w.z, v.off[2]), w.w);
       g.clip[k] = mulMV(v.b, c.x, c.y, c.z, c.w);
@@ -85,6 +91,10 @@ RDEV void triTransform(const RasterPrim& p, uint32_t t, const RasterView& v, Tri
       g.cs[k].x = g.cs[k].y = g.cs[k].z = 0.0f;
     }
   }
+}
+RDEV void triTransform(const RasterPrim& p, uint32_t t, const RasterView& v, TriGeom& g) {
+  triWorld(p, t, g);
+  triClip(v, g);
 }
 
 struct TriEdges {
@@ -248,15 +258,8 @@ RDEV int primOfTriangle(const RasterJob& J, uint32_t tri) { // binary search ove
   return lo;
 }
 
-__global__ void __launch_bounds__(256) raster_setup_kernel(const __grid_constant__ RasterJob J) {
-  const unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (unsigned long long)J.triTotal * J.nViews) return;
-  const uint32_t tri = (uint32_t)(gid / J.nViews), view = (uint32_t)(gid % J.nViews);
-  const int pi = primOfTriangle(J, tri);
-  const RasterPrim& p = J.prims[pi];
-  const RasterView& v = J.views[view];
-  TriGeom g;
-  triTransform(p, tri - p.triOffset, v, g);
+// one (triangle, view) after the vertex stage: rejection, edge functions, bounding box, record, tile work items
+RDEV void setupTriangleView(const RasterJob& J, const RasterPrim& p, int pi, uint32_t tri, uint32_t view, const TriGeom& g) {
   // trivial rejection against the clip volume -w <= x, y <= w, 0 <= z <= w
   bool allOut[6] = {true, true, true, true, true, true};
 #pragma unroll
@@ -318,6 +321,42 @@ __global__ void __launch_bounds__(256) raster_setup_kernel(const __grid_constant
   uint32_t k = 0;
   for (int ty = ty0; ty <= ty1; ++ty)
     for (int tx = tx0; tx <= tx1; ++tx) J.work[w0 + k++] = make_uint2(ri, (uint32_t)tx | ((uint32_t)ty << 16));
+}
+
+// Cheap, conservative pre-test for one cube face (shadow pass): the face transform evaluated with plain contracted arithmetic on
+// the light-relative positions; a triangle is skipped only when all three vertices are outside the same clip plane by a margin
+// a thousand times the difference between this arithmetic and the exact one, so it never changes what is drawn. A triangle
+// typically survives for one or two of the six faces, and only those pay for the exact transforms and the edge setup.
+RDEV bool faceCannotSee(const RasterView& v, const TriGeom& g) {
+  bool out[6] = {true, true, true, true, true, true};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float dx = g.world[k].x - v.off[0], dy = g.world[k].y - v.off[1], dz = g.world[k].z - v.off[2], dw = g.world[k].w;
+    const float cx = v.a[0] * dx + v.a[4] * dy + v.a[8] * dz + v.a[12] * dw, cy = v.a[1] * dx + v.a[5] * dy + v.a[9] * dz + v.a[13] * dw;
+    const float cz = v.a[2] * dx + v.a[6] * dy + v.a[10] * dz + v.a[14] * dw, cw = v.a[3] * dx + v.a[7] * dy + v.a[11] * dz + v.a[15] * dw;
+    const float X = v.b[0] * cx + v.b[4] * cy + v.b[8] * cz + v.b[12] * cw, Y = v.b[1] * cx + v.b[5] * cy + v.b[9] * cz + v.b[13] * cw;
+    const float Z = v.b[2] * cx + v.b[6] * cy + v.b[10] * cz + v.b[14] * cw, Wc = v.b[3] * cx + v.b[7] * cy + v.b[11] * cz + v.b[15] * cw;
+    const float m = 1e-3f * (fabsf(X) + fabsf(Y) + fabsf(Z) + fabsf(Wc)) + 1e-6f;
+    out[0] = out[0] && X < -Wc - m; out[1] = out[1] && X > Wc + m;
+    out[2] = out[2] && Y < -Wc - m; out[3] = out[3] && Y > Wc + m;
+    out[4] = out[4] && Z < -m;      out[5] = out[5] && Z > Wc + m;
+  }
+  return out[0] || out[1] || out[2] || out[3] || out[4] || out[5];
+}
+
+__global__ void __launch_bounds__(256) raster_setup_kernel(const __grid_constant__ RasterJob J) {
+  const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x; // one thread per triangle; its views in a loop
+  if (tri >= J.triTotal) return;
+  const int pi = primOfTriangle(J, tri);
+  const RasterPrim& p = J.prims[pi];
+  TriGeom g;
+  triWorld(p, tri - p.triOffset, g);
+  for (int view = 0; view < J.nViews; ++view) {
+    const RasterView& v = J.views[view];
+    if (J.nViews > 1 && faceCannotSee(v, g)) continue;
+    triClip(v, g);
+    setupTriangleView(J, p, pi, tri, (uint32_t)view, g);
+  }
 }
 
 // ---- fill -------------------------------------------------------------------------------------------------------------
@@ -486,8 +525,7 @@ void launch_raster_clear(unsigned long long* vis, float* depth, size_t n, cudaSt
   raster_clear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(vis, depth, n);
 }
 void launch_raster_setup(const RasterJob& J, cudaStream_t s) {
-  const unsigned long long n = (unsigned long long)J.triTotal * J.nViews;
-  if (n) raster_setup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(J);
+  if (J.triTotal) raster_setup_kernel<<<(unsigned)((J.triTotal + 255u) / 256u), 256, 0, s>>>(J);
 }
 void launch_raster_fill(const RasterJob& J, int sms, cudaStream_t s) { raster_fill_kernel<<<(unsigned)(sms * 8), 256, 0, s>>>(J); }
 void launch_gbuffer_resolve(const RasterJob& J, cudaStream_t s) {

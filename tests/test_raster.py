@@ -419,3 +419,59 @@ def test_gpu_produced_gbuffer_feeds_the_deferred_chain(ctx_fast):
     assert float(col[..., :3][cov].mean()) > 0.02
     shadow = lights.shadow_map.tensor.view(torch.float32)
     assert 0.05 < float((shadow < 1).float().mean()) <= 1.0  # an open scene: most directions see nothing
+
+
+# ---- BASELINE configs[0]: the DamagedHelmet frame at 1280 x 720 ------------------------------------------------------------
+def test_helmet_fixture_answer_is_reproducible(oracle):
+    """The committed answer (CRC of the restatement's depth image and triangle ids at 1280 x 720) is what the restatement
+    computes from the committed mesh and camera block on this machine too."""
+    import zlib
+
+    from helmet_fixture import CAMERA, GOLDEN, SIZE, helmet_primitives
+    d = np.load(GOLDEN)
+    prims = helmet_primitives()
+    assert prims[0].triangle_count == 46356 // 3
+    W, H = SIZE
+    g = CAMERA()
+    want = oracle.draw_gbuffer(list(g.projection), list(g.view), prims, W, H)
+    assert zlib.crc32(want["depth"].tobytes()) == int(d["depth_crc"][0])
+    assert zlib.crc32(want["tri"].tobytes()) == int(d["tri_crc"][0])
+    assert int((want["tri"] != NONE).sum()) == int(d["coverage"][0])
+    assert np.abs(want["albedo"][4::8, 4::8].astype(int) - d["albedo_thumb"].astype(int)).max() <= 1
+
+
+@pytest.mark.gpu
+def test_gpu_helmet_frame(ctx_fast, oracle):
+    """configs[0] end to end on the GPU: G-buffer of the helmet at 1280 x 720 (depth CRC equal to the committed answer, attributes
+    against the live restatement), then SSR, glossy mips, SSAO and deferred shading on it in the parity build against the
+    frame oracle fed with the same G-buffer."""
+    import zlib
+
+    import torch
+
+    from althea_b200 import _capi, engine
+    from helmet_fixture import CAMERA, GOLDEN, SIZE, helmet_primitives
+    d = np.load(GOLDEN)
+    prims = helmet_primitives()
+    W, H = SIZE
+    g = CAMERA()
+    got, gb = _gpu_gbuffer(ctx_fast, g, prims, W, H)
+    assert zlib.crc32(np.ascontiguousarray(got["depth"]).tobytes()) == int(d["depth_crc"][0])
+    assert int((got["depth"] < 1).sum()) == int(d["coverage"][0])
+    want = oracle.draw_gbuffer(list(g.projection), list(g.view), prims, W, H)
+    _compare_gbuffer(got, want)
+    # the deferred chain on the produced G-buffer
+    from helpers import FrameData, GpuFrame
+    small = GpuFrame(ctx_fast, FrameData("scene", 32, 18, n_lights=0))
+    ssr = engine.ScreenSpaceReflection(ctx_fast, W, H)
+    dp = engine.DeferredPass(ctx_fast, W, H, _capi.FORMAT_R32G32B32A32_SFLOAT)
+    ssr.captureReflection(g, gb, small.ibl, None)
+    ssr.convolveReflectionBuffer()
+    dp.draw(g, gb, small.ibl, None, ssr, _capi.SHADE_SKIP_TONEMAP)
+    torch.cuda.synchronize()
+    col = dp.colorTarget.tensor.view(torch.float32).view(H, W, 4)
+    cov = torch.from_numpy(want["tri"] != NONE).to(col.device)
+    assert bool(torch.isfinite(col).all())
+    assert float(col[..., :3][cov].mean()) > 0.01
+    ao = dp.aoCounts.tensor.view(H, W)
+    assert bool((ao[cov] <= 24).all()) and bool((ao[~cov] == 255).all()) and float((ao[cov] > 0).float().mean()) > 0.2
