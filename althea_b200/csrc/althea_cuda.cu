@@ -1066,34 +1066,36 @@ int buildPrims(althea_cuda_ctx* ctx, RasterScratch* R, const althea_primitive* p
   return ALTHEA_OK;
 }
 
-// setup (sized exactly, retried once if the tile work list was too small), then fill
+// setup then fill, no host round trip in between: the fill's persistent grid reads the work count on the device. If the tile
+// work list is too small the setup raises a sticky flag (counters[3] = items demanded) and the fill does nothing; the caller
+// checks the flag once per draw call (rasterOverflow) and redoes the call with a larger list.
 int runRaster(althea_cuda_ctx* ctx, RasterScratch* R, RasterJob& J, cudaStream_t stream) {
   const unsigned long long pairs = (unsigned long long)J.triTotal * (unsigned)J.nViews;
   if (!pairs) return ALTHEA_OK;
   if (pairs > (1ull << 26)) return fail(ctx, ALTHEA_ERR_UNSUPPORTED, "%llu (triangle, view) pairs in one pass", pairs);
   int rc = growScratch(ctx, &R->recs, &R->recsBytes, (size_t)pairs * sizeof(RasterRecord), "raster records");
   if (rc) return rc;
-  size_t workItems = R->workBytes / sizeof(uint2);
-  if (workItems < (size_t)pairs + (1u << 20)) workItems = (size_t)pairs + (1u << 20);
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    if ((rc = growScratch(ctx, &R->work, &R->workBytes, workItems * sizeof(uint2), "raster tile work list"))) return rc;
-    J.recs = static_cast<RasterRecord*>(R->recs);
-    J.recCap = (uint32_t)pairs;
-    J.work = static_cast<uint2*>(R->work);
-    J.workCap = (uint32_t)(R->workBytes / sizeof(uint2));
-    J.counters = R->counters;
-    CUDA_TRY(ctx, cudaMemsetAsync(R->counters, 0, 4 * sizeof(uint32_t), stream));
-    timedLaunch(ctx, "raster_setup", stream, [&] { althea_raster::launch_raster_setup(J, stream); });
-    uint32_t c[4] = {0, 0, 0, 0};
-    CUDA_TRY(ctx, cudaMemcpyAsync(c, R->counters, sizeof c, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(stream));
-    if (!c[2]) {
-      if (c[1]) timedLaunch(ctx, "raster_fill", stream, [&] { althea_raster::launch_raster_fill(J, R->sms, stream); });
-      return ALTHEA_OK;
-    }
-    workItems = (size_t)c[1] + 1024; // the counter kept counting: the exact demand
-  }
-  return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "raster tile work list overflowed twice");
+  if ((rc = growScratch(ctx, &R->work, &R->workBytes, ((size_t)pairs + (1u << 20)) * sizeof(uint2), "raster tile work list"))) return rc;
+  J.recs = static_cast<RasterRecord*>(R->recs);
+  J.recCap = (uint32_t)pairs;
+  J.work = static_cast<uint2*>(R->work);
+  J.workCap = (uint32_t)(R->workBytes / sizeof(uint2));
+  J.counters = R->counters;
+  CUDA_TRY(ctx, cudaMemsetAsync(R->counters, 0, 3 * sizeof(uint32_t), stream)); // [3] stays: sticky across the passes of a call
+  timedLaunch(ctx, "raster_setup", stream, [&] { althea_raster::launch_raster_setup(J, stream); });
+  timedLaunch(ctx, "raster_fill", stream, [&] { althea_raster::launch_raster_fill(J, R->sms, stream); });
+  return ALTHEA_OK;
+}
+// after the last pass of a draw call: 0 when every pass fitted, else the largest work-item demand seen (one host sync)
+int rasterOverflow(althea_cuda_ctx* ctx, RasterScratch* R, cudaStream_t stream, uint32_t* demanded) {
+  uint32_t c[4] = {0, 0, 0, 0};
+  CUDA_TRY(ctx, cudaMemcpyAsync(c, R->counters, sizeof c, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+  *demanded = c[3];
+  return ALTHEA_OK;
+}
+int growWorkList(althea_cuda_ctx* ctx, RasterScratch* R, uint32_t demanded) {
+  return growScratch(ctx, &R->work, &R->workBytes, ((size_t)demanded + (demanded >> 2) + 1024) * sizeof(uint2), "raster tile work list");
 }
 } // namespace
 
@@ -1130,6 +1132,7 @@ int althea_cuda_draw_gbuffer(althea_cuda_ctx* ctx, const althea_global_uniforms*
   J.W = (int)first->w;
   J.H = (int)first->h;
   J.mode = RASTER_MODE_GBUFFER;
+  J.tile = 64;
   RasterView view;
   memset(&view, 0, sizeof view);
   matmul44(uniforms->projection, uniforms->view, view.a); // Gltf.vert:55 evaluates (projection * view) * worldPos
@@ -1147,9 +1150,17 @@ int althea_cuda_draw_gbuffer(althea_cuda_ctx* ctx, const althea_global_uniforms*
   if (normal) { levelView(*normal, 0, 0, &v); J.outNormal = static_cast<uint2*>(const_cast<void*>(v.ptr)); J.pitchNormal = v.pitch; }
   if (albedo) { levelView(*albedo, 0, 0, &v); J.outAlbedo = static_cast<uint32_t*>(const_cast<void*>(v.ptr)); J.pitchAlbedo = v.pitch; }
   if (mro) { levelView(*mro, 0, 0, &v); J.outMro = static_cast<uint32_t*>(const_cast<void*>(v.ptr)); J.pitchMro = v.pitch; }
-  timedLaunch(ctx, "raster_clear", stream, [&] { althea_raster::launch_raster_clear(J.vis, nullptr, px, stream); });
-  if ((rc = runRaster(ctx, R, J, stream))) return rc;
-  timedLaunch(ctx, "gbuffer_resolve", stream, [&] { althea_raster::launch_gbuffer_resolve(J, stream); });
+  for (int attempt = 0;; ++attempt) {
+    CUDA_TRY(ctx, cudaMemsetAsync(R->counters, 0, 4 * sizeof(uint32_t), stream));
+    timedLaunch(ctx, "raster_clear", stream, [&] { althea_raster::launch_raster_clear(J.vis, nullptr, px, stream); });
+    if ((rc = runRaster(ctx, R, J, stream))) return rc;
+    timedLaunch(ctx, "gbuffer_resolve", stream, [&] { althea_raster::launch_gbuffer_resolve(J, stream); });
+    uint32_t demanded = 0;
+    if ((rc = rasterOverflow(ctx, R, stream, &demanded))) return rc;
+    if (!demanded) break;
+    if (attempt) return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "raster tile work list overflowed twice (%u items)", demanded);
+    if ((rc = growWorkList(ctx, R, demanded))) return rc;
+  }
   return endWork(ctx, sync, stream);
 }
 
@@ -1182,6 +1193,7 @@ int althea_cuda_draw_shadow_cubes(althea_cuda_ctx* ctx, uint64_t lights_buf, uin
   J.nPrims = (int)primitive_count;
   J.W = J.H = (int)sh->w;
   J.mode = RASTER_MODE_SHADOW;
+  J.tile = 32;
   J.nViews = 6;
   if ((rc = growScratch(ctx, &R->views, &R->viewsBytes, 8 * sizeof(RasterView), "raster views"))) return rc;
   J.views = static_cast<const RasterView*>(R->views);
@@ -1189,23 +1201,36 @@ int althea_cuda_draw_shadow_cubes(althea_cuda_ctx* ctx, uint64_t lights_buf, uin
   levelView(*sh, 0, 0, &l0);
   J.shadowLayerStride = sh->layers > 1 && levelView(*sh, 0, 1, &l1) ? (size_t)((const char*)l1.ptr - (const char*)l0.ptr) / sizeof(float) : (size_t)sh->w * sh->h;
   const size_t facePx = (size_t)sh->w * sh->h;
-  for (uint32_t l = 0; l < light_count; ++l) {
-    RasterView views[6];
-    memset(views, 0, sizeof views);
+  // the views of every light go up in one copy; each light's pass reads its six
+  std::vector<RasterView> views((size_t)6 * (light_count ? light_count : 1u));
+  memset(views.data(), 0, views.size() * sizeof(RasterView));
+  for (uint32_t l = 0; l < light_count; ++l)
     for (int f = 0; f < 6; ++f) { // ShadowMapBindless.vert:44-47: csPos = views[gl_ViewIndex] * (worldPos - light), gl_Position = projection * csPos
-      memcpy(views[f].a, constants->views[f], sizeof views[f].a);
-      memcpy(views[f].b, constants->projection, sizeof views[f].b);
-      memcpy(views[f].off, lights[l].position, sizeof views[f].off);
-      views[f].hasB = 1;
+      RasterView& v = views[6 * l + f];
+      memcpy(v.a, constants->views[f], sizeof v.a);
+      memcpy(v.b, constants->projection, sizeof v.b);
+      memcpy(v.off, lights[l].position, sizeof v.off);
+      v.hasB = 1;
     }
-    CUDA_TRY(ctx, cudaMemcpyAsync(R->views, views, sizeof views, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(stream));
-    ImgView base;
-    levelView(*sh, 0, 6u * l, &base);
-    J.shadowBase = static_cast<float*>(const_cast<void*>(base.ptr));
-    // the six layers of a light are contiguous: one clear
-    timedLaunch(ctx, "raster_clear", stream, [&] { althea_raster::launch_raster_clear(nullptr, J.shadowBase, J.shadowLayerStride * 5 + facePx, stream); });
-    if ((rc = runRaster(ctx, R, J, stream))) return rc;
+  if ((rc = growScratch(ctx, &R->views, &R->viewsBytes, views.size() * sizeof(RasterView), "raster views"))) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(R->views, views.data(), views.size() * sizeof(RasterView), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+  for (int attempt = 0;; ++attempt) {
+    CUDA_TRY(ctx, cudaMemsetAsync(R->counters, 0, 4 * sizeof(uint32_t), stream));
+    for (uint32_t l = 0; l < light_count; ++l) {
+      J.views = static_cast<const RasterView*>(R->views) + 6 * l;
+      ImgView base;
+      levelView(*sh, 0, 6u * l, &base);
+      J.shadowBase = static_cast<float*>(const_cast<void*>(base.ptr));
+      // the six layers of a light are contiguous: one clear
+      timedLaunch(ctx, "raster_clear", stream, [&] { althea_raster::launch_raster_clear(nullptr, J.shadowBase, J.shadowLayerStride * 5 + facePx, stream); });
+      if ((rc = runRaster(ctx, R, J, stream))) return rc;
+    }
+    uint32_t demanded = 0;
+    if ((rc = rasterOverflow(ctx, R, stream, &demanded))) return rc;
+    if (!demanded) break;
+    if (attempt) return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "raster tile work list overflowed twice (%u items)", demanded);
+    if ((rc = growWorkList(ctx, R, demanded))) return rc;
   }
   return endWork(ctx, sync, stream);
 }

@@ -131,6 +131,7 @@ RDEV bool triEdges(const TriGeom& g, int W, int H, bool frontCW, TriEdges& e) {
   return true;
 }
 
+constexpr int kSmallBoxPixels = 16;
 RDEV float edgeAt(float A, float B, float C, float x, float y) { return __fmaf_rn(A, x, __fmaf_rn(B, y, C)); }
 RDEV bool edgeInside(float e, float A, float B) { return e > 0.0f || (e == 0.0f && (A > 0.0f || (A == 0.0f && B > 0.0f))); } // top-left rule
 
@@ -258,6 +259,37 @@ RDEV int primOfTriangle(const RasterJob& J, uint32_t tri) { // binary search ove
   return lo;
 }
 
+// One pixel of one (triangle, view): coverage, depth clip, optional alpha discard, depth resolve. Shared by the warp-per-tile
+// fill and by the setup thread that rasterises small triangles itself.
+RDEV void rasterPixel(const RasterJob& J, const RasterPrim& p, const float A[3], const float B[3], const float C[3], const float Z[3], float rdet,
+                      const float* attr, uint32_t tri, uint32_t view, bool alphaTest, const uint32_t vi[3], int px, int py) {
+  const float x = (float)px + 0.5f, y = (float)py + 0.5f;
+  float e[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) e[i] = edgeAt(A[i], B[i], C[i], x, y);
+  if (!(edgeInside(e[0], A[0], B[0]) && edgeInside(e[1], A[1], B[1]) && edgeInside(e[2], A[2], B[2]))) return;
+  const float zn = __fmaf_rn(e[0], Z[0], __fmaf_rn(e[1], Z[1], mulr(e[2], Z[2])));
+  const float z = mulr(zn, rdet);
+  if (!(z >= 0.0f && z <= 1.0f)) return; // depth clip 0 <= z_c <= w_c
+  const float S = addr(addr(e[0], e[1]), e[2]);
+  if (!(S > 0.0f)) return;
+  if (alphaTest && fragmentAlpha(p, vi, e, A, B, S) < p.mat.alphaCutoff) return; // discard
+  if (J.mode == RASTER_MODE_SHADOW) {
+    // gl_FragDepth = length(worldPosCS) / zFar with worldPosCS interpolated perspective-correctly (ShadowMapBindless.frag:28,41)
+    const float b0 = __fdiv_rn(e[0], S), b1 = __fdiv_rn(e[1], S), b2 = __fdiv_rn(e[2], S);
+    const float cx = addr(addr(mulr(b0, attr[0]), mulr(b1, attr[3])), mulr(b2, attr[6]));
+    const float cy = addr(addr(mulr(b0, attr[1]), mulr(b1, attr[4])), mulr(b2, attr[7]));
+    const float cz = addr(addr(mulr(b0, attr[2]), mulr(b1, attr[5])), mulr(b2, attr[8]));
+    const float d = __fdiv_rn(__fsqrt_rn(addr(addr(mulr(cx, cx), mulr(cy, cy)), mulr(cz, cz))), 1000.0f);
+    if (!(d >= 0.0f && d < 1.0f)) return; // LESS against the 1.0 clear; depth writes are clamped to [0, 1]
+    atomicMin(reinterpret_cast<unsigned int*>(J.shadowBase + view * J.shadowLayerStride + (size_t)py * J.W + px), __float_as_uint(d));
+  } else {
+    if (!(z < 1.0f)) return; // LESS against the 1.0 clear
+    const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | tri;
+    atomicMin(J.vis + (size_t)py * J.W + px, key);
+  }
+}
+
 // one (triangle, view) after the vertex stage: rejection, edge functions, bounding box, record, tile work items
 RDEV void setupTriangleView(const RasterJob& J, const RasterPrim& p, int pi, uint32_t tri, uint32_t view, const TriGeom& g) {
   // trivial rejection against the clip volume -w <= x, y <= w, 0 <= z <= w
@@ -300,8 +332,19 @@ RDEV void setupTriangleView(const RasterJob& J, const RasterPrim& p, int pi, uin
     y1 = (int)fminf(ceilf(ymax) + 1.0f, (float)(J.H - 1));
   }
   if (x1 < x0 || y1 < y0) return;
+  if ((x1 - x0 + 1) * (y1 - y0 + 1) <= kSmallBoxPixels) {
+    // small triangles (most of a dense mesh, nearly all of it in a 256^2 shadow face) are rasterised right here: no record,
+    // no work item, no warp spent on a handful of pixels. Same per-pixel code, and the depth resolve is order-independent.
+    float Z[3], attr[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { Z[k] = g.clip[k].z; attr[3 * k] = g.cs[k].x; attr[3 * k + 1] = g.cs[k].y; attr[3 * k + 2] = g.cs[k].z; }
+    const bool alphaTest = !p.opaque;
+    for (int py = y0; py <= y1; ++py)
+      for (int px = x0; px <= x1; ++px) rasterPixel(J, p, e.A, e.B, e.C, Z, e.rdet, attr, tri, view, alphaTest, g.vi, px, py);
+    return;
+  }
   const uint32_t ri = atomicAdd(&J.counters[0], 1u);
-  if (ri >= J.recCap) { J.counters[2] = 1u; return; }
+  if (ri >= J.recCap) { J.counters[2] = 1u; atomicMax(&J.counters[3], J.workCap + 1u); return; } // cannot happen: recCap = triangles x views
   RasterRecord r;
 #pragma unroll
   for (int i = 0; i < 3; ++i) { r.A[i] = e.A[i]; r.B[i] = e.B[i]; r.C[i] = e.C[i]; r.Z[i] = g.clip[i].z; }
@@ -314,10 +357,10 @@ RDEV void setupTriangleView(const RasterJob& J, const RasterPrim& p, int pi, uin
   for (int k = 0; k < 3; ++k) { r.attr[3 * k] = g.cs[k].x; r.attr[3 * k + 1] = g.cs[k].y; r.attr[3 * k + 2] = g.cs[k].z; }
   r.pad[0] = r.pad[1] = r.pad[2] = 0u;
   J.recs[ri] = r;
-  const int tx0 = x0 / kRasterTile, tx1 = x1 / kRasterTile, ty0 = y0 / kRasterTile, ty1 = y1 / kRasterTile;
+  const int tx0 = x0 / J.tile, tx1 = x1 / J.tile, ty0 = y0 / J.tile, ty1 = y1 / J.tile;
   const uint32_t n = (uint32_t)((tx1 - tx0 + 1) * (ty1 - ty0 + 1));
   const uint32_t w0 = atomicAdd(&J.counters[1], n);
-  if (w0 + n > J.workCap) { J.counters[2] = 1u; return; }
+  if (w0 + n > J.workCap) { J.counters[2] = 1u; atomicMax(&J.counters[3], w0 + n); return; } // sticky: the shim redoes the call with a larger list
   uint32_t k = 0;
   for (int ty = ty0; ty <= ty1; ++ty)
     for (int tx = tx0; tx <= tx1; ++tx) J.work[w0 + k++] = make_uint2(ri, (uint32_t)tx | ((uint32_t)ty << 16));
@@ -363,6 +406,7 @@ __global__ void __launch_bounds__(256) raster_setup_kernel(const __grid_constant
 __global__ void __launch_bounds__(256) raster_fill_kernel(const __grid_constant__ RasterJob J) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+  if (J.counters[2]) return; // the work list overflowed: nothing in it can be trusted (the shim retries)
   const uint32_t nWork = min(J.counters[1], J.workCap);
   for (uint32_t wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < nWork; wi += warpsTotal) {
     const uint2 item = J.work[wi];
@@ -373,9 +417,9 @@ __global__ void __launch_bounds__(256) raster_fill_kernel(const __grid_constant_
     for (int i = 0; i < 3; ++i) { A[i] = rr.A[i]; B[i] = rr.B[i]; C[i] = rr.C[i]; Z[i] = rr.Z[i]; }
     const float rdet = rr.rdet;
     const uint32_t tri = rr.tri, view = rr.view;
-    const int tx = (int)(item.y & 0xffffu) * kRasterTile, ty = (int)(item.y >> 16) * kRasterTile;
+    const int tx = (int)(item.y & 0xffffu) * J.tile, ty = (int)(item.y >> 16) * J.tile;
     const int x0 = max((int)rr.bbox[0], tx), y0 = max((int)rr.bbox[1], ty);
-    const int x1 = min((int)rr.bbox[2], tx + kRasterTile - 1), y1 = min((int)rr.bbox[3], ty + kRasterTile - 1);
+    const int x1 = min((int)rr.bbox[2], tx + J.tile - 1), y1 = min((int)rr.bbox[3], ty + J.tile - 1);
     // whole-tile rejection: an edge function that is negative at the corner where it is largest is negative everywhere
     bool reject = false;
 #pragma unroll
@@ -398,31 +442,7 @@ __global__ void __launch_bounds__(256) raster_fill_kernel(const __grid_constant_
     for (int b = 0; b < bw * bh; ++b) {
       const int px = x0 + (b % bw) * 8 + (int)(lane & 7u), py = y0 + (b / bw) * 4 + (int)(lane >> 3);
       if (px > x1 || py > y1) continue;
-      const float x = (float)px + 0.5f, y = (float)py + 0.5f;
-      float e[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) e[i] = edgeAt(A[i], B[i], C[i], x, y);
-      if (!(edgeInside(e[0], A[0], B[0]) && edgeInside(e[1], A[1], B[1]) && edgeInside(e[2], A[2], B[2]))) continue;
-      const float zn = __fmaf_rn(e[0], Z[0], __fmaf_rn(e[1], Z[1], mulr(e[2], Z[2])));
-      const float z = mulr(zn, rdet);
-      if (!(z >= 0.0f && z <= 1.0f)) continue; // depth clip 0 <= z_c <= w_c
-      const float S = addr(addr(e[0], e[1]), e[2]);
-      if (!(S > 0.0f)) continue;
-      if (alphaTest && fragmentAlpha(p, vi, e, A, B, S) < p.mat.alphaCutoff) continue; // discard
-      if (J.mode == RASTER_MODE_SHADOW) {
-        // gl_FragDepth = length(worldPosCS) / zFar with worldPosCS interpolated perspective-correctly (ShadowMapBindless.frag:28,41)
-        const float b0 = __fdiv_rn(e[0], S), b1 = __fdiv_rn(e[1], S), b2 = __fdiv_rn(e[2], S);
-        const float cx = addr(addr(mulr(b0, rr.attr[0]), mulr(b1, rr.attr[3])), mulr(b2, rr.attr[6]));
-        const float cy = addr(addr(mulr(b0, rr.attr[1]), mulr(b1, rr.attr[4])), mulr(b2, rr.attr[7]));
-        const float cz = addr(addr(mulr(b0, rr.attr[2]), mulr(b1, rr.attr[5])), mulr(b2, rr.attr[8]));
-        const float d = __fdiv_rn(__fsqrt_rn(addr(addr(mulr(cx, cx), mulr(cy, cy)), mulr(cz, cz))), 1000.0f);
-        if (!(d >= 0.0f && d < 1.0f)) continue; // LESS against the 1.0 clear; depth writes are clamped to [0, 1]
-        atomicMin(reinterpret_cast<unsigned int*>(J.shadowBase + view * J.shadowLayerStride + (size_t)py * J.W + px), __float_as_uint(d));
-      } else {
-        if (!(z < 1.0f)) continue; // LESS against the 1.0 clear
-        const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | tri;
-        atomicMin(J.vis + (size_t)py * J.W + px, key);
-      }
+      rasterPixel(J, p, A, B, C, Z, rdet, rr.attr, tri, view, alphaTest, vi, px, py);
     }
   }
 }

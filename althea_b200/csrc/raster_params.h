@@ -53,7 +53,7 @@ struct __align__(16) RasterRecord {
 static_assert(sizeof(RasterRecord) == 128, "RasterRecord is two 64-byte halves");
 
 enum { RASTER_MODE_GBUFFER = 0, RASTER_MODE_SHADOW = 1 };
-constexpr int kRasterTile = 64;
+
 
 struct RasterJob {
   const RasterPrim* prims;
@@ -63,11 +63,13 @@ struct RasterJob {
   int nViews;
   int W, H;
   int mode;
+  int tile; // pixels per side of a fill work item: 64 for frame-sized targets, 32 for shadow faces (a 256^2 face would otherwise
+            // be 16 work items, each a 128-iteration warp: too few warps, too long a tail)
   RasterRecord* recs;
   uint32_t recCap;
   uint2* work; // (record index, tileX | tileY << 16)
   uint32_t workCap;
-  uint32_t* counters; // [0] records, [1] work items, [2] overflow flag
+  uint32_t* counters; // [0] records, [1] work items, [2] overflow flag of this pass, [3] sticky: largest work-item demand that overflowed
   // G-buffer: visibility buffer, one 64-bit key per pixel = depth bits << 32 | global triangle ordinal (atomicMin)
   unsigned long long* vis;
   // shadow: depth layers of the current light, layer `view` at shadowBase + view * shadowLayerStride floats

@@ -475,3 +475,17 @@ def test_gpu_helmet_frame(ctx_fast, oracle):
     assert float(col[..., :3][cov].mean()) > 0.01
     ao = dp.aoCounts.tensor.view(H, W)
     assert bool((ao[cov] <= 24).all()) and bool((ao[~cov] == 255).all()) and float((ao[cov] > 0).float().mean()) > 0.2
+
+
+@pytest.mark.gpu
+def test_gpu_work_list_overflow_is_retried(ctx_fast):
+    """More tile work items than the initial list holds (hundreds of stacked full-screen quads at 4K): the shim notices the
+    sticky overflow flag after the pass and redoes the call with a larger list; the result is the nearest quad everywhere."""
+    W, H = 3840, 2160
+    g = scene.make_uniforms(W, H, pos=(0.0, 0.0, 5.0), yaw=0.0, pitch=0.0)
+    quads = [model.quad([(-40, -30, -k * 0.01), (40, -30, -k * 0.01), (40, 30, -k * 0.01), (-40, 30, -k * 0.01)]) for k in range(330)]
+    assert 330 * 2 * ((W + 63) // 64) * ((H + 63) // 64) > (1 << 20) + 660
+    got_all, _ = _gpu_gbuffer(ctx_fast, g, quads, W, H)
+    got_first, _ = _gpu_gbuffer(ctx_fast, g, quads[:1], W, H)
+    assert (got_first["depth"] < 1).all()
+    assert np.array_equal(got_all["depth"].view(np.uint32), got_first["depth"].view(np.uint32))
