@@ -4,6 +4,7 @@
 #include "CudaApplication.h"
 #include "GlobalUniforms.h"
 #include "ImageBasedLighting.h"
+#include "Model.h"
 #include "PointLight.h"
 #include "ScreenSpaceReflection.h"
 
@@ -28,6 +29,22 @@ public:
 
 private:
   ImageResource _depthA, _position, _normal, _albedo, _metallicRoughnessOcclusion;
+};
+
+// SceneToGBufferPass (Include/Althea/DeferredRendering.h:132-155, Src/DeferredRendering.cpp:268-330) with its glTF subpass
+// (Gltf.vert/.frag): rasterises the models' primitives into the G-buffer attachments.
+class SceneToGBufferPass {
+public:
+  SceneToGBufferPass() = default;
+  explicit SceneToGBufferPass(const CudaApplication& app) : _app(&app) {}
+  void draw(const GlobalUniforms& globals, const std::vector<Model>& models, const GBufferResources& gBuffer, const althea_sync* sync = nullptr) {
+    const std::vector<althea_primitive> prims = describeModels(models);
+    const althea_gbuffer gb = gBuffer.getHandles();
+    _app->check(althea_cuda_draw_gbuffer(_app->ctx(), &globals, prims.data(), (uint32_t)prims.size(), &gb, sync), "althea_cuda_draw_gbuffer");
+  }
+
+private:
+  const CudaApplication* _app = nullptr;
 };
 
 class DeferredPass {

@@ -1,9 +1,11 @@
 // One deferred frame through the C++ mirror of the reference's interface (althea_b200/host/Althea/*.h):
 //   demo_frame <inputs.bin> <outputs.bin> [--parity]
+//   demo_frame --raster <scene.bin> <outputs.bin>      the rasterising producers: shadow cubes + G-buffer from meshes
 // inputs.bin is written by tests/test_host_cpp.py (layout below); outputs.bin receives the reflection mip chain (RGBA16F)
 // followed by the lit colour target (RGBA32F). The order of calls is the reference's per-frame order.
 #include <Althea/DeferredRendering.h>
 #include <Althea/ImageBasedLighting.h>
+#include <Althea/Model.h>
 #include <Althea/PointLight.h>
 #include <Althea/ScreenSpaceReflection.h>
 
@@ -23,7 +25,80 @@ std::vector<char> readBlock(std::ifstream& f, size_t n) {
 }
 } // namespace
 
+// scene.bin (tests/test_host_cpp.py): int32 W, H, nLights, shadowRes, nPrims; GlobalUniforms; PointLight[nLights]; per primitive:
+// int32 nVerts, nIdx, frontCW, hasBaseTexture; float model[16]; float factors[8] (baseColorFactor, normalScale, metallic,
+// roughness, alphaCutoff); Vertex[nVerts]; uint32[nIdx]; if hasBaseTexture: int32 w, h, mips, sampler; RGBA8 texels of all levels.
+// outputs: depth, position, normal, albedo, MRO attachments, then the shadow cube array.
+static int rasterDemo(const char* in, const char* out) {
+  std::ifstream f(in, std::ios::binary);
+  if (!f) throw std::runtime_error("cannot open scene");
+  int32_t hd[5];
+  f.read(reinterpret_cast<char*>(hd), sizeof hd);
+  const int W = hd[0], H = hd[1], nLights = hd[2], shadowRes = hd[3], nPrims = hd[4];
+  GlobalUniforms globals;
+  f.read(reinterpret_cast<char*>(&globals), sizeof globals);
+  CudaApplication app(0);
+  PointLightCollection lights(app, (size_t)nLights, nLights > 0, (uint32_t)shadowRes);
+  for (int i = 0; i < nLights; ++i) {
+    PointLight l;
+    f.read(reinterpret_cast<char*>(&l), sizeof l);
+    lights.setLight((uint32_t)i, l);
+  }
+  std::vector<Model> models(1);
+  for (int p = 0; p < nPrims; ++p) {
+    int32_t ph[4];
+    f.read(reinterpret_cast<char*>(ph), sizeof ph);
+    float model[16], factors[8];
+    f.read(reinterpret_cast<char*>(model), sizeof model);
+    f.read(reinterpret_cast<char*>(factors), sizeof factors);
+    std::vector<Vertex> verts((size_t)ph[0]);
+    std::vector<uint32_t> idx((size_t)ph[1]);
+    f.read(reinterpret_cast<char*>(verts.data()), (std::streamsize)(verts.size() * sizeof(Vertex)));
+    f.read(reinterpret_cast<char*>(idx.data()), (std::streamsize)(idx.size() * sizeof(uint32_t)));
+    Material m;
+    std::memcpy(m.baseColorFactor, factors, 16);
+    m.normalScale = factors[4]; m.metallicFactor = factors[5]; m.roughnessFactor = factors[6]; m.alphaCutoff = factors[7];
+    if (ph[3]) {
+      int32_t th[4];
+      f.read(reinterpret_cast<char*>(th), sizeof th);
+      const size_t bytes = althea_cuda_image_bytes(ALTHEA_FORMAT_R8G8B8A8_UNORM, (uint32_t)th[0], (uint32_t)th[1], (uint32_t)th[2], 1);
+      std::vector<char> texels = readBlock(f, bytes);
+      m.baseTexture = std::make_shared<Texture>(app, texels.data(), (uint32_t)th[0], (uint32_t)th[1], (uint32_t)th[2], (uint32_t)th[3]);
+    }
+    if (!f) throw std::runtime_error("scene file truncated");
+    models[0].addPrimitive(Primitive(app, verts, idx, model, std::move(m), ph[2] != 0));
+  }
+  GBufferResources gBuffer(app, (uint32_t)W, (uint32_t)H);
+  SceneToGBufferPass gpass(app);
+  lights.drawShadowMaps(models);
+  gpass.draw(globals, models, gBuffer);  // step 5
+  app.waitIdle();
+  std::ofstream o(out, std::ios::binary);
+  for (ImageResource* img : {&gBuffer.getDepthA(), &gBuffer.getPosition(), &gBuffer.getNormal(), &gBuffer.getAlbedo(), &gBuffer.getMetallicRoughnessOcclusion()}) {
+    std::vector<char> b(img->byteSize());
+    img->download(b.data(), b.size());
+    app.waitIdle();
+    o.write(b.data(), (std::streamsize)b.size());
+  }
+  if (nLights > 0) {
+    std::vector<char> b((size_t)nLights * 6 * shadowRes * shadowRes * 4);
+    app.check(althea_cuda_download(app.ctx(), lights.shadowMapHandle(), b.data(), b.size(), nullptr), "althea_cuda_download(shadow cubes)");
+    app.waitIdle();
+    o.write(b.data(), (std::streamsize)b.size());
+  }
+  std::printf("demo_frame raster ok: %dx%d, %d primitives, %d lights, %llu kernel launches\n", W, H, nPrims, nLights, (unsigned long long)app.launchCount());
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 4 && std::strcmp(argv[1], "--raster") == 0) {
+    try {
+      return rasterDemo(argv[2], argv[3]);
+    } catch (const std::exception& e) {
+      std::fprintf(stderr, "demo_frame failed: %s\n", e.what());
+      return 1;
+    }
+  }
   if (argc < 3) { std::fprintf(stderr, "usage: demo_frame inputs.bin outputs.bin [--parity]\n"); return 2; }
   const bool parity = argc > 3 && std::strcmp(argv[3], "--parity") == 0;
   try {
