@@ -336,6 +336,7 @@ def main():
                          "S-rand frame split in row bands, NCCL broadcast of the G-buffer + all-gather of the bands, strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-producers", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)
@@ -413,6 +414,35 @@ def main():
         ctx.set_flags(0)
         ceilings = {str(r): ctx.gather_ceiling(W4K, H4K, r, 64) for r in (32, 96)}
         gather = {"records_per_frame": records, "ceiling_records_per_s": ceilings}
+
+    # ---- the rasterising producers upstream of the path, informational, outside the timed region:
+    # G-buffer pass at 4K and the 16 x 6 shadow-cube faces of a 1.06 M triangle mesh scene (tools/raster_bench.py)
+    producers = None
+    if rank == 0 and not args.no_producers:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import numpy as np
+        import raster_bench
+        from althea_b200 import model as _model
+        up = _model.UploadedModel(ctx, raster_bench.build_scene(512))
+        gpass = engine.SceneToGBufferPass(ctx)
+        pgb = engine.GBufferResources(ctx, W4K, H4K)
+        pl = engine.PointLightCollection(ctx, N_LIGHTS, shadow_res=SHADOW_RES)
+        prng = np.random.default_rng(1)
+        for i in range(N_LIGHTS):
+            pl.setLight(i, engine.PointLight((prng.uniform(-4, 4), prng.uniform(0, 4), prng.uniform(-3, 4)), (10.0, 10.0, 10.0)))
+        pg = views[0][0]
+        producers = {"scene": "procedural mesh scene, %d triangles (512x1024 textured sphere, a small sphere, six room quads)" % up.triangle_count}
+        for name, fn in (("draw_gbuffer_4k_ms", lambda: gpass.draw(pg, up, pgb, stream)), ("draw_shadow_cubes_16x6x256_ms", lambda: pl.drawShadowMaps([up], stream))):
+            fn()
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(3):
+                fn()
+            p1.record()
+            torch.cuda.synchronize()
+            producers[name] = p0.elapsed_time(p1) / 3
+        del up, pgb, pl
 
     # ---- e2e: same metric through the C ABI with HOST buffers (pinned), copies inside the timed region ----
     e2e = None
@@ -526,7 +556,7 @@ def main():
                            "views_per_gpu": V, "resolution": [W4K, H4K], "lights": N_LIGHTS, "l2_policy": "inputs (%.1f GB/step/GPU) exceed the 126 MB L2"
                                                                                                       % (V * px_frame * 36 / 1e9),
                            "math": "fast build (FFMA); parity build checked in tests"},
-                "gpu_launches": int(launches) * world, "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_chain": chain, "stages": stages,
+                "gpu_launches": int(launches) * world, "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_chain": chain, "stages": stages, "producers": producers,
                 "ibl_prefilter_ms": ibl_t.get("config1_cube", {}).get("ibl_prefilter"),
                 "ibl_precompute_ms": ibl_t,
                 "ibl_config": {"config1_cube": "BASELINE configs[1]: %dx%d equirect env -> 32^2 irradiance cube (300x150 samples) + 512^2 6-mip GGX prefilter cube "
