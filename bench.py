@@ -90,6 +90,29 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pins this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers of the e2e leg are
+    allocated: with 8 ranks each moving ~3 GB per step over PCIe, buffers on the far socket halve the copy rate. Best effort."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def ncu_traffic(kernel: str):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload (profiles/ncu_traffic.json,
     written by tools/ncu_summary.py traffic ...); None when no capture is on record."""
@@ -270,6 +293,12 @@ def cpu_baseline_sample(repeats: int = 1):
 
     from althea_b200 import scene
     from oracle import oracle as O
+    # all the host's cores: undo torchrun's OMP_NUM_THREADS=1 and this rank's NUMA pinning (bind_to_gpu_numa_node)
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count()))
+    except OSError:
+        pass
+    O.set_num_threads(len(os.sched_getaffinity(0)))
     sw, sh = 1280, 720
     sc = scene.make_ring_scene(160)
     g = scene.make_uniforms(sw, sh, pos=(0.0, 2.0, 0.0), yaw=0.0, pitch=-0.2, light_count=N_LIGHTS)
@@ -351,6 +380,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = "cuda:%d" % local_rank
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries the one JSON line
@@ -510,7 +540,7 @@ def main():
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         ms2 = float(t2.item()) / k2
         e2e = {"value": world * px_per_step / (ms2 * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": ms2, "steps": k2,
+               "ms_per_step": ms2, "steps": k2, "numa_node": numa_node,
                "how": "C ABI with pinned host buffers: upload of 5 G-buffer attachments per view, frame, download of the RGBA16F colour target; "
                       "double-buffered, copies overlapped with kernels on separate streams"}
 

@@ -420,5 +420,7 @@ void oracle_deferred_shade(const OracleGlobalUniforms* g, const OracleGBuffer* g
 }
 
 int oracle_num_threads() { return omp_get_max_threads(); }
+// torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline legs of bench.py ask for the host's cores explicitly
+void oracle_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 } // extern "C"

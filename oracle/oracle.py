@@ -90,6 +90,11 @@ def num_threads() -> int:
     return int(lib().oracle_num_threads())
 
 
+def set_num_threads(n: int) -> None:
+    """OpenMP threads of the restatement (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
+    lib().oracle_set_num_threads(int(n))
+
+
 def rng(sx: int, sy: int, n: int):
     u = np.empty(n, np.uint32)
     f = np.empty(n, np.float32)
