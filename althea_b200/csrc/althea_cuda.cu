@@ -305,6 +305,48 @@ int fillFrameParams(althea_cuda_ctx* ctx, const althea_global_uniforms* u, const
   P->y1 = P->H;
   P->Wf = (float)P->W;
   P->Hf = (float)P->H;
+  { // SSAO ray-depth proxy: the view ray through texel (x, y), scaled to view z = -1, is affine in (x, y) for a perspective camera
+    const float* ip = u->inverseProjection;
+    const float* iv = u->inverseView;
+    auto dirV = [&](double nx, double ny, double* d) {
+      double q[4];
+      for (int r = 0; r < 4; ++r) q[r] = ip[0 + r] * nx + ip[4 + r] * ny + ip[8 + r] * 1.0 + ip[12 + r];
+      for (int r = 0; r < 3; ++r) d[r] = q[r] / -q[2];
+    };
+    double d00[3], d10[3], d01[3];
+    dirV(-1.0, -1.0, d00); dirV(1.0, -1.0, d10); dirV(-1.0, 1.0, d01);
+    double vc[3], vx[3], vy[3];
+    for (int r = 0; r < 3; ++r) {
+      const double gx = 0.5 * (d10[r] - d00[r]), gy = 0.5 * (d01[r] - d00[r]); // per unit of ndc
+      vx[r] = 2.0 * gx / P->W;
+      vy[r] = 2.0 * gy / P->H;
+      vc[r] = d00[r] + gx / P->W + gy / P->H; // ndc of texel (0, 0)'s centre is (1/W - 1, 1/H - 1)
+    }
+    for (int r = 0; r < 3; ++r) {
+      P->ssaoDc[r] = (float)(iv[0 + r] * vc[0] + iv[4 + r] * vc[1] + iv[8 + r] * vc[2]);
+      P->ssaoDx[r] = (float)(iv[0 + r] * vx[0] + iv[4 + r] * vx[1] + iv[8 + r] * vx[2]);
+      P->ssaoDy[r] = (float)(iv[0 + r] * vy[0] + iv[4 + r] * vy[1] + iv[8 + r] * vy[2]);
+      P->ssaoFwd[r] = -iv[8 + r];
+      P->ssaoCam[r] = iv[12 + r];
+    }
+    { // world origin in model coordinates: solve [Dc Dx Dy] o = -cam (Cramer, double)
+      const double m[3][3] = {{P->ssaoDc[0], P->ssaoDx[0], P->ssaoDy[0]}, {P->ssaoDc[1], P->ssaoDx[1], P->ssaoDy[1]}, {P->ssaoDc[2], P->ssaoDx[2], P->ssaoDy[2]}};
+      const double rhs[3] = {-(double)P->ssaoCam[0], -(double)P->ssaoCam[1], -(double)P->ssaoCam[2]};
+      auto det3 = [](const double a[3][3]) {
+        return a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) + a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+      };
+      const double d = det3(m);
+      for (int c = 0; c < 3; ++c) {
+        double mc[3][3];
+        for (int r = 0; r < 3; ++r)
+          for (int k = 0; k < 3; ++k) mc[r][k] = k == c ? rhs[r] : m[r][k];
+        P->ssaoOrigin[c] = d != 0.0 ? (float)(det3(mc) / d) : 0.0f; // a degenerate camera only costs speed: E0 flags the records
+      }
+    }
+    auto dotf = [](const float* a, const float* b) { return (double)a[0] * b[0] + (double)a[1] * b[1] + (double)a[2] * b[2]; };
+    P->ssaoGram[0] = (float)dotf(P->ssaoDc, P->ssaoDc); P->ssaoGram[1] = (float)dotf(P->ssaoDx, P->ssaoDx); P->ssaoGram[2] = (float)dotf(P->ssaoDy, P->ssaoDy);
+    P->ssaoGram[3] = (float)(2.0 * dotf(P->ssaoDc, P->ssaoDx)); P->ssaoGram[4] = (float)(2.0 * dotf(P->ssaoDc, P->ssaoDy)); P->ssaoGram[5] = (float)(2.0 * dotf(P->ssaoDx, P->ssaoDy));
+  }
   if (ctx->scissorY1) {
     if (ctx->scissorY1 > normal->h) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "scissor rows [%u, %u) exceed the frame height %u", ctx->scissorY0, ctx->scissorY1, normal->h);
     P->y0 = (int)ctx->scissorY0;
@@ -766,18 +808,20 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
     }
     P.quads = ctx->quadScratch;
     P.quadRow = P.W + 1;
-    P.quadsOrigin = static_cast<const char*>(ctx->quadScratch) + ((size_t)P.quadRow + 1) * 32;
+    P.quadKind = (ctx->flags & ALTHEA_CTX_SSAO_RAY_DEPTH_PROXY) ? 1 : 0;
+    P.quadPitch = ((size_t)P.W + 1) * (P.quadKind ? 16 : 32);
+    P.quadsOrigin = static_cast<const char*>(ctx->quadScratch) + ((size_t)P.quadRow + 1) * (P.quadKind ? 16 : 32);
   }
   if (computeAo && !exactTaps && (ctx->flags & ALTHEA_CTX_SSAO_COUNT_TAPS)) {
     if (!ctx->gatherCounter) {
-      cudaError_t e = cudaMalloc(&ctx->gatherCounter, sizeof(unsigned long long));
+      cudaError_t e = cudaMalloc(&ctx->gatherCounter, 2 * sizeof(unsigned long long));
       if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(gather counter): %s", cudaGetErrorString(e)); }
     }
     P.gatherCounter = ctx->gatherCounter;
   }
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
-  if (P.gatherCounter) cudaMemsetAsync(P.gatherCounter, 0, sizeof(unsigned long long), stream);
+  if (P.gatherCounter) cudaMemsetAsync(P.gatherCounter, 0, 2 * sizeof(unsigned long long), stream);
   if (computeAo) {
     if (exactTaps) {
       timedLaunch(ctx, "ssao_exact", stream, [&] { parity ? althea_parity::launch_ssao_exact(P, stream) : althea_fast::launch_ssao_exact(P, stream); });
@@ -904,6 +948,15 @@ int althea_cuda_diag_ssao_gathers(althea_cuda_ctx* ctx, uint64_t* out_records) {
   unsigned long long v = 0;
   CUDA_TRY(ctx, cudaMemcpy(&v, ctx->gatherCounter, sizeof v, cudaMemcpyDeviceToHost));
   *out_records = v;
+  return ALTHEA_OK;
+}
+int althea_cuda_diag_ssao_exact_fallbacks(althea_cuda_ctx* ctx, uint64_t* out_taps) {
+  if (!ctx || !out_taps) return ALTHEA_ERR_INVALID_ARGUMENT;
+  if (!ctx->gatherCounter) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "no SSAO launch has run with ALTHEA_CTX_SSAO_COUNT_TAPS set");
+  CUDA_TRY(ctx, cudaDeviceSynchronize());
+  unsigned long long v = 0;
+  CUDA_TRY(ctx, cudaMemcpy(&v, ctx->gatherCounter + 1, sizeof v, cudaMemcpyDeviceToHost));
+  *out_taps = v;
   return ALTHEA_OK;
 }
 

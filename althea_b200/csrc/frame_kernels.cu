@@ -715,19 +715,23 @@ template <bool COUNT> ADEV int ssaoCountFiltered(const FrameParams& P, int px, i
           } else {
             const float pu = marchCoord(u0, uvEnd.x, i - 1), pv = marchCoord(v0, uvEnd.y, i - 1);
             if (curDecided == 0.0f) {
+              if (COUNT) gathers += 65536u;
               ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
               curPos = e.pos; curProjection = e.projection; curTwoTol = 0.0f; curDecided = decidedExact(curProjection);
             }
             if (prevDecided == 0.0f && prevTwoTol != 0.0f) {
+              if (COUNT) gathers += 65536u;
               ExactTap e = exactTap(P, pu, pv, worldPos, perpRef);
               prevPos = e.pos; prevProjection = e.projection; prevTwoTol = 0.0f; prevDecided = decidedExact(prevProjection);
             }
             // a value at most kTiny in magnitude can push the fp32 product into underflow: then both factors must be exact
             if (curDecided == 0.0f && prevTwoTol != 0.0f) {
+              if (COUNT) gathers += 65536u;
               ExactTap e = exactTap(P, pu, pv, worldPos, perpRef);
               prevPos = e.pos; prevProjection = e.projection; prevTwoTol = 0.0f; prevDecided = decidedExact(prevProjection);
             }
             if (prevDecided == 0.0f && curTwoTol != 0.0f) {
+              if (COUNT) gathers += 65536u;
               ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
               curPos = e.pos; curProjection = e.projection; curTwoTol = 0.0f; curDecided = decidedExact(curProjection);
             }
@@ -742,7 +746,8 @@ template <bool COUNT> ADEV int ssaoCountFiltered(const FrameParams& P, int px, i
             else if (worldStep - tol > 2.0f) near = false;
             else {
               if (curTwoTol != 0.0f) {
-                ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
+                if (COUNT) gathers += 65536u;
+              ExactTap e = exactTap(P, cu, cv, worldPos, perpRef);
                 curPos = e.pos; curProjection = e.projection; curTwoTol = 0.0f; curDecided = decidedExact(curProjection);
               }
               if (prevTwoTol != 0.0f) prevPos = exactTap(P, marchCoord(u0, uvEnd.x, i - 1), marchCoord(v0, uvEnd.y, i - 1), worldPos, perpRef).pos;
@@ -764,6 +769,237 @@ template <bool COUNT> ADEV int ssaoCountFiltered(const FrameParams& P, int px, i
   return ao;
 }
 
+// -- ray-depth proxy (round 1e) -------------------------------------------------------------------------------------------
+// A position G-buffer written by a perspective camera holds, at texel (x, y), a point of the view ray through that texel:
+//   p(x, y) = cam + D(x, y) t,  D(x, y) = Dc + Dx x + Dy y (the ray scaled to view z = -1),  t = dot(p - cam, fwd) (eye depth).
+// So a footprint's four texels are described by four SCALARS, and the record shrinks from 32 to 16 bytes: t00 (fp32), the
+// coefficients a = t10 - t00, b = t01 - t00, c = (t11 - t10) - (t01 - t00) of its bilinear interpolant (3 x fp16) and the sign
+// threshold T (bf16, rounded up). Half the bytes per tap is what the march needs most: it is bound by divergent gathers, whose
+// rate the device sustains ~15-40 % higher for 16-byte records (tools/microbench/gather.cu), because twice as many footprints
+// fit in L1. (a and b keep full fp32 precision in the record's spare words; only the second-order term c is fp16.)
+// The bilinear position is  cam + D00 Tb + Dx Tx + Dy Ty  with Tb = bilinear t, Tx = fx ((1 - fy) t10 + fy t11),
+// Ty = fy ((1 - fx) t01 + fx t11) (D is affine, so the weights regroup), hence its projection on perpRef is
+//   c0 + Tb (ac + au ix + av iy) + Tx au + Ty av,   c0 = dot(cam - pos, perpRef), ac/au/av = dot(Dc/Dx/Dy, perpRef) per ray:
+// no position is ever formed in the common case. Model and truth are both bilinear in (fx, fy), so their difference peaks at a
+// corner: the pre-pass measures E there against the real texels (this also absorbs G-buffers that are NOT camera-consistent:
+// E grows, the record cannot decide, the tap is re-evaluated exactly). Decisions follow the same rule as for the position
+// records: a sign is taken from the proxy only when |value| exceeds T + the shaded pixel's slop; every flip candidate and every
+// undecided tap is re-evaluated from the fp32 texels with the restatement's own expression, so counts are bit-identical.
+struct __align__(16) RayRecord { uint32_t w[4]; }; // t00 | a (fp32) | c (fp16), T (bf16 in the high half) | b (fp32)
+// rounding slop of the two evaluations (the restatement's lerps + dot product, the model's), as a multiple of the magnitudes in
+// play: worst case ~16 ulp by operation count, 32 budgeted on each of the record's and the pixel's share
+constexpr float kRaySlop = 32.0f * 1.1920929e-7f;
+
+__global__ void __launch_bounds__(256) ssao_rayquads_kernel(const __grid_constant__ FrameParams P) {
+  const int qx = blockIdx.x * 32 + (threadIdx.x & 31); // record column = ix + 1
+  const int qy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (qx > P.W || qy > P.H) return;
+  RayRecord* dst = reinterpret_cast<RayRecord*>(const_cast<char*>(static_cast<const char*>(P.quads)) + (size_t)qy * P.quadPitch) + qx;
+  RayRecord rec;
+  const int ix = qx - 1, iy = qy - 1;
+  bool ok = ix >= 0 && iy >= 0 && ix + 1 < P.W && iy + 1 < P.H; // border footprints clamp onto one texel: not affine, always exact
+  float tt[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  V4 tex[4];
+  const V3 cam = mk3(P.ssaoCam[0], P.ssaoCam[1], P.ssaoCam[2]), fwd = mk3(P.ssaoFwd[0], P.ssaoFwd[1], P.ssaoFwd[2]);
+  if (ok) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      tex[k] = FmtRGBA32F::load(P.position, ix + (k & 1), iy + (k >> 1));
+      tt[k] = dot3(xyz(tex[k]) - cam, fwd);
+      ok = ok && isfinite(tex[k].x) && isfinite(tex[k].y) && isfinite(tex[k].z) && isfinite(tt[k]);
+    }
+  }
+  // Empty pixels hold the clear colour (0, 0, 0, 0) (Src/DeferredRendering.cpp:101-102), which is no point of a view ray. A
+  // footprint of four zero texels interpolates to exactly zero: its record is a marker (t00 = NaN pattern) and the march
+  // substitutes the model coordinates of the world origin (FrameParams::ssaoOrigin). Footprints that mix empty and covered
+  // texels (silhouettes against the sky) measure a large E below and are re-evaluated exactly.
+  bool sky = ok;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sky = sky && tex[k].x == 0.0f && tex[k].y == 0.0f && tex[k].z == 0.0f;
+  if (sky) {
+    const V3 o = mk3(P.ssaoOrigin[0], P.ssaoOrigin[1], P.ssaoOrigin[2]);
+    const float ex = fmaf(o.z, P.ssaoDy[0], fmaf(o.y, P.ssaoDx[0], fmaf(o.x, P.ssaoDc[0], cam.x)));
+    const float ey = fmaf(o.z, P.ssaoDy[1], fmaf(o.y, P.ssaoDx[1], fmaf(o.x, P.ssaoDc[1], cam.y)));
+    const float ez = fmaf(o.z, P.ssaoDy[2], fmaf(o.y, P.ssaoDx[2], fmaf(o.x, P.ssaoDc[2], cam.z)));
+    const float E0 = fmaxf(fabsf(ex), fmaxf(fabsf(ey), fabsf(ez))); // how far the model puts the origin from (0, 0, 0)
+    const float camL1s = fabsf(cam.x) + fabsf(cam.y) + fabsf(cam.z);
+    const float Ts = __fmul_ru(2.0f, __fadd_ru(__fmul_ru(__fmul_ru(E0, 1.001f), kSqrt3Up), __fadd_ru(__fmul_ru(camL1s, kRaySlop), kTiny)));
+    rec.w[0] = 0x7fc00000u;
+    rec.w[1] = 0u;
+    rec.w[3] = 0u;
+    rec.w[2] = isfinite(Ts) ? ((__float_as_uint(Ts) >> 16) + 1u) << 16 : 0x7f800000u;
+    *dst = rec;
+    return;
+  }
+  float a = __fsub_rn(tt[1], tt[0]), b = __fsub_rn(tt[2], tt[0]), c = __fsub_rn(__fsub_rn(tt[3], tt[1]), b);
+  const uint32_t hc = halfBits(c);
+  c = lowHalfToFloat(hc); // as the march decodes it
+  ok = ok && isfinite(a) && isfinite(b) && isfinite(c);
+  float E = 0.0f, M = 0.0f;
+  if (ok) {
+    // decoded corner depths and the model position at each corner against the texel itself
+    const float td[4] = {tt[0], tt[0] + a, tt[0] + b, ((tt[0] + a) + b) + c};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float fxk = (float)(ix + (k & 1)), fyk = (float)(iy + (k >> 1));
+      const V3 D = mk3(fmaf(P.ssaoDy[0], fyk, fmaf(P.ssaoDx[0], fxk, P.ssaoDc[0])), fmaf(P.ssaoDy[1], fyk, fmaf(P.ssaoDx[1], fxk, P.ssaoDc[1])),
+                       fmaf(P.ssaoDy[2], fyk, fmaf(P.ssaoDx[2], fxk, P.ssaoDc[2])));
+      const V3 m = mk3(fmaf(D.x, td[k], cam.x), fmaf(D.y, td[k], cam.y), fmaf(D.z, td[k], cam.z));
+      E = fmaxf(E, fmaxf(fabsf(m.x - tex[k].x), fmaxf(fabsf(m.y - tex[k].y), fabsf(m.z - tex[k].z))));
+      M = fmaxf(M, __fadd_ru(__fadd_ru(fabsf(tex[k].x), fabsf(tex[k].y)), fabsf(tex[k].z)));
+    }
+  }
+  // everything of the sign threshold that does not depend on the shaded pixel: model error (inflated: it was itself measured in
+  // fp32), rounding slop of both evaluations on the magnitudes in play (texels and camera position), and the underflow guard
+  const float camL1 = fabsf(cam.x) + fabsf(cam.y) + fabsf(cam.z);
+  const float T = __fmul_ru(2.0f, __fadd_ru(__fmul_ru(__fmul_ru(E, 1.001f), kSqrt3Up), __fadd_ru(__fmul_ru(__fadd_ru(M, camL1), kRaySlop), kTiny)));
+  ok = ok && isfinite(T);
+  rec.w[0] = __float_as_uint(tt[0]);
+  rec.w[1] = __float_as_uint(a);
+  rec.w[3] = __float_as_uint(b);
+  rec.w[2] = hc | (ok ? ((__float_as_uint(T) >> 16) + 1u) << 16 : 0x7f800000u); // T rounded UP to bf16; +inf => always exact
+  *dst = rec;
+}
+
+struct RayConsts { float c0, ac, au, av; }; // per ray: dot products of (cam - pos), Dc, Dx, Dy with perpRef
+// A tap in MODEL coordinates (A, B, C): position = cam + Dc A + Dx B + Dy C, with A = Tb, B = ix Tb + Tx, C = iy Tb + Ty
+// (D00 = Dc + Dx ix + Dy iy regrouped). Projection and step length are evaluated in these coordinates; no position is formed.
+struct RayTap { V3 abc; float projection, twoTol; };
+ADEV RayTap rayTap(const FrameParams& P, const RayConsts& rc, float u, float v) {
+  // same coordinate arithmetic as the exact tap (rule A1): identical footprint and weights
+  const float x = __fsub_rn(__fmul_rn(u, P.Wf), 0.5f), y = __fsub_rn(__fmul_rn(v, P.Hf), 0.5f);
+  const int ix = __float2int_rd(x), iy = __float2int_rd(y);
+  const float fix = (float)ix, fiy = (float)iy;
+  const float fx = x - fix, fy = y - fiy;
+  const uint4 r = __ldg(static_cast<const uint4*>(P.quadsOrigin) + (iy * P.quadRow + ix));
+  const float t00 = __uint_as_float(r.x), a = __uint_as_float(r.y), b = __uint_as_float(r.w), c = lowHalfToFloat(r.z);
+  const float Tb = fmaf(fmaf(c, fy, a), fx, fmaf(b, fy, t00));  // bilinear eye depth
+  const float Tx = fx * fmaf(b + c, fy, t00 + a);              // fx ((1 - fy) t10 + fy t11)
+  const float Ty = fy * fmaf(a + c, fx, t00 + b);              // fy ((1 - fx) t01 + fx t11)
+  RayTap t;
+  const bool sky = r.x == 0x7fc00000u; // four empty texels: the world origin, in model coordinates
+  t.abc = mk3(sky ? P.ssaoOrigin[0] : Tb, sky ? P.ssaoOrigin[1] : fmaf(fix, Tb, Tx), sky ? P.ssaoOrigin[2] : fmaf(fiy, Tb, Ty));
+  t.projection = fmaf(t.abc.z, rc.av, fmaf(t.abc.y, rc.au, fmaf(t.abc.x, rc.ac, rc.c0)));
+  t.twoTol = __uint_as_float(r.z); // bf16 T with the fp16 of c below it: a hair above T, never below
+  return t;
+}
+ADEV V3 modelToWorld(const FrameParams& P, V3 m) {
+  return mk3(fmaf(m.z, P.ssaoDy[0], fmaf(m.y, P.ssaoDx[0], fmaf(m.x, P.ssaoDc[0], P.ssaoCam[0]))),
+             fmaf(m.z, P.ssaoDy[1], fmaf(m.y, P.ssaoDx[1], fmaf(m.x, P.ssaoDc[1], P.ssaoCam[1]))),
+             fmaf(m.z, P.ssaoDy[2], fmaf(m.y, P.ssaoDx[2], fmaf(m.x, P.ssaoDc[2], P.ssaoCam[2]))));
+}
+// |Dc a + Dx b + Dy c| from the Gram matrix of (Dc, Dx, Dy) (FrameParams::ssaoGram: cc, xx, yy, 2cx, 2cy, 2xy)
+ADEV float modelLength(const FrameParams& P, V3 d) {
+  const float q = fmaf(d.x, fmaf(d.x, P.ssaoGram[0], fmaf(d.y, P.ssaoGram[3], d.z * P.ssaoGram[4])), fmaf(d.y, fmaf(d.y, P.ssaoGram[1], d.z * P.ssaoGram[5]), d.z * d.z * P.ssaoGram[2]));
+  return sqrtf(fmaxf(q, 0.0f));
+}
+
+__device__ __noinline__ V3 perpRefOf(V3 rayDir, V3 normal) { return normalize3(cross3(cross3(rayDir, normal), rayDir)); }
+
+template <bool COUNT> ADEV int ssaoCountRayProxy(const FrameParams& P, int px, int py, float u0, float v0, V3 worldPos, V3 normal, unsigned& gathers) {
+  HashRng rng;
+  rng.sx = (uint32_t)px;
+  rng.sy = (uint32_t)py;
+  const TangentFrame tbn = localToWorld(normal);
+  const V3 cam = mk3(P.ssaoCam[0], P.ssaoCam[1], P.ssaoCam[2]);
+  const V3 camMinusPos = cam - worldPos;
+  const V3 Dc = mk3(P.ssaoDc[0], P.ssaoDc[1], P.ssaoDc[2]), Dx = mk3(P.ssaoDx[0], P.ssaoDx[1], P.ssaoDx[2]), Dy = mk3(P.ssaoDy[0], P.ssaoDy[1], P.ssaoDy[2]);
+  // the shaded pixel's share of the threshold (the record's share carries the texels' and the camera's magnitudes)
+  const float posSlop2 = (2.002f * kRaySlop) * ((fabsf(worldPos.x) + fabsf(worldPos.y) + fabsf(worldPos.z)) + (fabsf(cam.x) + fabsf(cam.y) + fabsf(cam.z)));
+  int ao = 0;
+  for (int ray = 0; ray < 24; ++ray) {
+    float x0 = rng.next(), x1 = rng.next(), x2 = rng.next();
+    V3 rayDir = frameApply(tbn, normalize3(mk3(2.0f * x0 - 1.0f, 2.0f * x1 - 1.0f, x2)));
+    V2 uvEnd = projectUv(P, worldPos + rayDir * 0.5f);
+    int n = 12; // taps before the ray leaves the screen (SSAO.glsl:50), as in ssaoCountFiltered
+    if (outside01(uvEnd.x, uvEnd.y)) {
+      n = 1;
+      while (n < 12 && !outside01(marchCoord(u0, uvEnd.x, n), marchCoord(v0, uvEnd.y, n))) ++n;
+    }
+    // perpRef only lives in the four dot products the fast path needs; the rare exact path gets it back from perpRefOf (kept out
+    // of line so the compiler cannot keep the vector in registers across the march to share it)
+    RayConsts rc;
+    {
+      const V3 perpRef = normalize3(cross3(cross3(rayDir, normal), rayDir));
+      rc.c0 = dot3(camMinusPos, perpRef); rc.ac = dot3(Dc, perpRef); rc.au = dot3(Dx, perpRef); rc.av = dot3(Dy, perpRef);
+    }
+    // previous step: projection, its threshold (0 <=> the value IS the restatement's fp32 value, and prevPos is valid), its
+    // sign-decided form
+    V3 prevPos = worldPos;
+    float prevProjection = 0.0f, prevTwoTol = 0.0f, prevDecided = 0.0f;
+#pragma unroll kSsaoUnroll
+    for (int i = 1; i < n; ++i) {
+      const float cu = marchCoord(u0, uvEnd.x, i), cv = marchCoord(v0, uvEnd.y, i);
+      const RayTap tap = rayTap(P, rc, cu, cv);
+      if (COUNT) gathers += 1u;
+      V3 curPos = tap.abc; // MODEL coordinates while curTwoTol != 0, the exact world position once it is 0
+      float curProjection = tap.projection;
+      float curTwoTol = tap.twoTol + posSlop2; // inf / NaN when the record is flagged
+      float curDecided = decided(curProjection, curTwoTol);
+      if (!(__fmul_rn(curDecided, prevDecided) > 0.0f)) {
+        if (i > 1) {
+          bool flip;
+          if (curDecided != 0.0f && prevDecided != 0.0f) {
+            flip = (curProjection < 0.0f) != (prevProjection < 0.0f); // also a same-sign product that underflowed
+          } else {
+            const float pu = marchCoord(u0, uvEnd.x, i - 1), pv = marchCoord(v0, uvEnd.y, i - 1);
+            if (curDecided == 0.0f) {
+              if (COUNT) gathers += 65536u;
+              ExactTap e = exactTap(P, cu, cv, worldPos, perpRefOf(rayDir, normal));
+              curPos = e.pos; curProjection = e.projection; curTwoTol = 0.0f; curDecided = decidedExact(curProjection);
+            }
+            if (prevDecided == 0.0f && prevTwoTol != 0.0f) {
+              if (COUNT) gathers += 65536u;
+              ExactTap e = exactTap(P, pu, pv, worldPos, perpRefOf(rayDir, normal));
+              prevPos = e.pos; prevProjection = e.projection; prevTwoTol = 0.0f; prevDecided = decidedExact(prevProjection);
+            }
+            // a value at most kTiny in magnitude can push the fp32 product into underflow: then both factors must be exact
+            if (curDecided == 0.0f && prevTwoTol != 0.0f) {
+              if (COUNT) gathers += 65536u;
+              ExactTap e = exactTap(P, pu, pv, worldPos, perpRefOf(rayDir, normal));
+              prevPos = e.pos; prevProjection = e.projection; prevTwoTol = 0.0f; prevDecided = decidedExact(prevProjection);
+            }
+            if (prevDecided == 0.0f && curTwoTol != 0.0f) {
+              if (COUNT) gathers += 65536u;
+              ExactTap e = exactTap(P, cu, cv, worldPos, perpRefOf(rayDir, normal));
+              curPos = e.pos; curProjection = e.projection; curTwoTol = 0.0f; curDecided = decidedExact(curProjection);
+            }
+            flip = __fmul_rn(curProjection, prevProjection) < 0.0f;
+          }
+          if (flip) {
+            // worldStep = length(currentPos - prevPos) <= 2.0. Both taps in model coordinates (the usual case): the length of
+            // their difference through the Gram matrix, no position formed. One of them already exact: the other's model position.
+            const float pu = marchCoord(u0, uvEnd.x, i - 1), pv = marchCoord(v0, uvEnd.y, i - 1);
+            float worldStep;
+            if (curTwoTol != 0.0f && prevTwoTol != 0.0f) worldStep = modelLength(P, curPos - prevPos);
+            else worldStep = length3((curTwoTol != 0.0f ? modelToWorld(P, curPos) : curPos) - (prevTwoTol != 0.0f ? modelToWorld(P, prevPos) : prevPos));
+            // each threshold covers twice its tap's position error; the last term is the Gram form's own rounding
+            const float tol = (curTwoTol + prevTwoTol) + 1e-5f * worldStep;
+            bool near;
+            if (worldStep + tol <= 2.0f) near = true;
+            else if (worldStep - tol > 2.0f) near = false;
+            else {
+              if (COUNT) gathers += 65536u;
+              if (curTwoTol != 0.0f) {
+                ExactTap e = exactTap(P, cu, cv, worldPos, perpRefOf(rayDir, normal));
+                curPos = e.pos; curProjection = e.projection; curTwoTol = 0.0f; curDecided = decidedExact(curProjection);
+              }
+              if (prevTwoTol != 0.0f) prevPos = exactTap(P, pu, pv, worldPos, perpRefOf(rayDir, normal)).pos;
+              near = length3(curPos - prevPos) <= 2.0f;
+            }
+            if (near && facesRay(P, cu, cv, rayDir)) {
+              ao += 1;
+              break;
+            }
+          }
+        }
+      }
+      prevPos = curPos; prevProjection = curProjection; prevTwoTol = curTwoTol; prevDecided = curDecided;
+    }
+  }
+  return ao;
+}
+
 #ifndef ALTHEA_SSAO_MIN_BLOCKS
 #define ALTHEA_SSAO_MIN_BLOCKS 4
 #endif
@@ -771,7 +1007,7 @@ template <bool COUNT> ADEV int ssaoCountFiltered(const FrameParams& P, int px, i
 #define ALTHEA_SSAO_TILE_W 16
 #endif
 constexpr int kSsaoTileW = ALTHEA_SSAO_TILE_W, kSsaoTileH = 256 / ALTHEA_SSAO_TILE_W;
-template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_SSAO_MIN_BLOCKS) ssao_kernel(const __grid_constant__ FrameParams P) {
+template <bool COUNT, int KIND> __global__ void __launch_bounds__(256, ALTHEA_SSAO_MIN_BLOCKS) ssao_kernel(const __grid_constant__ FrameParams P) {
   const int x = blockIdx.x * kSsaoTileW + (threadIdx.x % kSsaoTileW);
   const int y = P.y0 + blockIdx.y * kSsaoTileH + (threadIdx.x / kSsaoTileW);
   if (x >= P.W || y >= P.y1) return;
@@ -781,10 +1017,13 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_SSAO_MIN_BLO
   if (position.w != 0.0f) {
     const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
     V3 normal = normalize3(xyz(FmtRGBA16F::load(P.normal, x, y)));
-    count = (uint8_t)ssaoCountFiltered<COUNT>(P, x, y, u, v, xyz(position), normal, gathers);
+    count = (uint8_t)(KIND ? ssaoCountRayProxy<COUNT>(P, x, y, u, v, xyz(position), normal, gathers) : ssaoCountFiltered<COUNT>(P, x, y, u, v, xyz(position), normal, gathers));
   }
   rowPtrW<uint8_t>(P.ao, y)[x] = count;
-  if (COUNT) atomicAdd(P.gatherCounter, (unsigned long long)gathers);
+  if (COUNT) { // two device counters: records gathered, taps re-evaluated from the fp32 texels
+    atomicAdd(P.gatherCounter, (unsigned long long)(gathers & 0xffffu));
+    atomicAdd(P.gatherCounter + 1, (unsigned long long)(gathers >> 16));
+  }
 }
 
 // ---- deferred shading -----------------------------------------------------------------------------------------------
@@ -861,12 +1100,19 @@ void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s) {
 }
 void launch_ssao(const FrameParams& P, cudaStream_t s) {
   const dim3 grid((unsigned)((P.W + kSsaoTileW - 1) / kSsaoTileW), (unsigned)((P.y1 - P.y0 + kSsaoTileH - 1) / kSsaoTileH));
-  if (P.gatherCounter) ssao_kernel<true><<<grid, 256, 0, s>>>(P);
-  else ssao_kernel<false><<<grid, 256, 0, s>>>(P);
+  if (P.quadKind) {
+    if (P.gatherCounter) ssao_kernel<true, 1><<<grid, 256, 0, s>>>(P);
+    else ssao_kernel<false, 1><<<grid, 256, 0, s>>>(P);
+  } else {
+    if (P.gatherCounter) ssao_kernel<true, 0><<<grid, 256, 0, s>>>(P);
+    else ssao_kernel<false, 0><<<grid, 256, 0, s>>>(P);
+  }
 }
 void launch_ssao_exact(const FrameParams& P, cudaStream_t s) { ssao_exact_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
 void launch_ssao_quads(const FrameParams& P, cudaStream_t s) {
-  ssao_quads_kernel<<<dim3((unsigned)((P.W + 1 + 31) / 32), (unsigned)((P.H + 1 + 7) / 8)), 256, 0, s>>>(P);
+  const dim3 grid((unsigned)((P.W + 1 + 31) / 32), (unsigned)((P.H + 1 + 7) / 8));
+  if (P.quadKind) ssao_rayquads_kernel<<<grid, 256, 0, s>>>(P);
+  else ssao_quads_kernel<<<grid, 256, 0, s>>>(P);
 }
 void launch_deferred_shade(const FrameParams& P, cudaStream_t s) { deferred_shade_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
 

@@ -44,6 +44,12 @@ struct FrameParams {
   const void* quadsOrigin; // &record(1, 1): the footprint whose top-left tap is texel (0, 0)
   int quadRow;             // records per row = W + 1
   float Wf, Hf;            // (float)W, (float)H
+  // SSAO ray-depth proxy: position of texel (x, y) modelled as cam + (Dc + Dx x + Dy y) * t with t the eye depth
+  // dot(p - cam, fwd); the 16-byte records hold t of a footprint's four texels. quadKind: 0 = 32-byte position records, 1 = these
+  float ssaoCam[3], ssaoFwd[3], ssaoDc[3], ssaoDx[3], ssaoDy[3];
+  float ssaoGram[6]; // Dc.Dc, Dx.Dx, Dy.Dy, 2 Dc.Dx, 2 Dc.Dy, 2 Dx.Dy
+  float ssaoOrigin[3]; // model coordinates of the world origin: Dc o0 + Dx o1 + Dy o2 = -cam (where empty pixels' cleared positions lie)
+  int quadKind;
   unsigned long long* gatherCounter; // diagnostics (ALTHEA_CTX_SSAO_COUNT_TAPS): proxy records gathered by the SSAO march; else null
   // SSR padded depth (engine scratch): the depth image with a one-texel CLAMP_TO_EDGE border, (W+2) x (H+2) floats
   const float* depthPad;

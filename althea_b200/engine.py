@@ -182,6 +182,12 @@ class Context:
         self._check(self._lib.althea_cuda_diag_ssao_gathers(self._ptr, C.byref(out)))
         return int(out.value)
 
+    def ssao_exact_fallbacks(self) -> int:
+        """Taps of that launch that were re-evaluated from the fp32 texels (diagnostics, ray-depth proxy)."""
+        out = C.c_uint64(0)
+        self._check(self._lib.althea_cuda_diag_ssao_exact_fallbacks(self._ptr, C.byref(out)))
+        return int(out.value)
+
     def gather_ceiling(self, w: int, h: int, radius: int, taps_per_pixel: int = 64) -> float:
         """Measured records/s of divergent 32-byte gathers within +-radius records of each 16x16 tile (diagnostics)."""
         out = C.c_double(0.0)

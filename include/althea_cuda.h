@@ -70,6 +70,7 @@ int althea_cuda_abi_version(void);
 
 #define ALTHEA_CTX_PARITY_MATH 1u /* run the -fmad=false build of the per-frame kernels (bit-matches the CPU oracle's IEEE op order) */
 #define ALTHEA_CTX_SSAO_EXACT_TAPS 2u /* SSAO marches the fp32 position texels directly (4 loads per tap) instead of the packed proxy with exact re-evaluation; same counts, slower: A/B switch for tests and profiling */
+#define ALTHEA_CTX_SSAO_RAY_DEPTH_PROXY 8u /* SSAO marches 16-byte ray-depth records (eye depth of a footprint's four texels along the camera's view rays) instead of the 32-byte position records; same counts bit for bit; faster on frames without sky, slightly slower with it: opt-in */
 #define ALTHEA_CTX_SSAO_COUNT_TAPS 4u /* diagnostics: the SSAO march also counts the proxy records it gathers (read with althea_cuda_diag_ssao_gathers); slower */
 int althea_cuda_set_flags(althea_cuda_ctx* ctx, uint32_t flags);
 
@@ -95,6 +96,8 @@ uint64_t althea_cuda_launch_count(const althea_cuda_ctx* ctx);
  * ALTHEA_CTX_SSAO_COUNT_TAPS set. _gather_ceiling: measures the device's records/s for the same access pattern (one 256-bit
  * load per lane at random positions within +-radius records of the lane's 16x16 tile, over a (w+1) x (h+1) record grid). */
 int althea_cuda_diag_ssao_gathers(althea_cuda_ctx* ctx, uint64_t* out_records);
+/* ... and the taps of that launch that had to be re-evaluated from the fp32 texels (ray-depth proxy only). */
+int althea_cuda_diag_ssao_exact_fallbacks(althea_cuda_ctx* ctx, uint64_t* out_taps);
 int althea_cuda_diag_gather_ceiling(althea_cuda_ctx* ctx, uint32_t w, uint32_t h, uint32_t radius, uint32_t taps_per_pixel,
                                     double* out_records_per_second);
 

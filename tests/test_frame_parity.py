@@ -265,9 +265,14 @@ def test_error_behaviour(ctx_fast):
 
 
 def _ao_both_ways(ctx, gf, fd, parity):
-    """SSAO counts from the packed-proxy kernel (default) and from the straight fp32-texel kernel, same context."""
+    """SSAO counts from the packed-proxy kernels (position records: the default; ray-depth records: opt-in) and from the
+    straight fp32-texel kernel, same context. Returns (position proxy, exact taps); asserts the ray-depth proxy equals them."""
     from althea_b200 import _capi
     base = _capi.CTX_PARITY_MATH if parity else 0
+    ctx.set_flags(base | _capi.CTX_SSAO_RAY_DEPTH_PROXY)
+    gf.deferred.aoCounts.tensor.zero_()
+    gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+    ray = gf.ao_counts().copy()
     out = []
     for flags in (base, base | _capi.CTX_SSAO_EXACT_TAPS):
         ctx.set_flags(flags)
@@ -275,6 +280,7 @@ def _ao_both_ways(ctx, gf, fd, parity):
         gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
         out.append(gf.ao_counts().copy())
     ctx.set_flags(base)
+    assert np.array_equal(ray, out[1]), "ray-depth proxy differs from the fp32-texel march on %d pixels" % int((ray != out[1]).sum())
     return out
 
 
@@ -329,7 +335,7 @@ def test_properties_at_4k(ctx_fast):
     # the packed-proxy march against the fp32-texel march. With -fmad=false every decision is the same IEEE
     # operation in both kernels: bit for bit. In the fast build the compiler contracts the two kernels' inlined copies of
     # the tap arithmetic separately, so a projection within an ulp of zero can flip: at most a handful of pixels in 8.3 M.
-    for flags, bar in ((_capi.CTX_PARITY_MATH, 0), (0, 8)):
+    for flags, bar in ((_capi.CTX_PARITY_MATH, 0), (0, 8), (_capi.CTX_PARITY_MATH | _capi.CTX_SSAO_RAY_DEPTH_PROXY, 0), (_capi.CTX_SSAO_RAY_DEPTH_PROXY, 8)):
         ctx_fast.set_flags(flags)
         _, _, ap = run()
         ctx_fast.set_flags(flags | _capi.CTX_SSAO_EXACT_TAPS)
@@ -381,6 +387,7 @@ def test_gather_diagnostics(ctx_fast):
     gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
     counted = gf.ao_counts().copy()
     gathers = ctx_fast.ssao_gathers()
+    assert 0 <= ctx_fast.ssao_exact_fallbacks() < gathers // 4
     ctx_fast.set_flags(0)
     assert np.array_equal(plain, counted)
     shaded = int((plain < 255).sum())

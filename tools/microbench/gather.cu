@@ -25,7 +25,10 @@ template <int MODE> __global__ void __launch_bounds__(256, 4) gather(const Rec* 
     const int x = min(max(tx + dx, 0), GW - 1), y = min(max(ty + dy, 0), GH - 1);
     const int idx = y * GW + x;
     const bool useTex = MODE == 1 || (MODE == 2 && (t & 1)) || (MODE == 3 && (t % 3 == 2));
-    if (useTex) {
+    if (MODE == 4) { // 16-byte records: the same grid at half the bytes (one LDG.128 per tap)
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(recs) + idx);
+      acc += a.x ^ a.y ^ a.z ^ a.w;
+    } else if (useTex) {
       uint4 a = tex1Dfetch<uint4>(tex, 2 * idx), b = tex1Dfetch<uint4>(tex, 2 * idx + 1);
       acc += a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w;
     } else {
@@ -76,11 +79,12 @@ int main() {
   cudaTextureObject_t tex = 0;
   cudaError_t e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
   if (e != cudaSuccess) { printf("texture: %s\n", cudaGetErrorString(e)); return 1; }
-  for (int R : {8, 32, 96}) {
+  for (int R : {8, 32, 64, 96}) {
     run<0>("ldg256", recs, tex, out, R, p.multiProcessorCount, ghz);
     run<1>("tex2x128", recs, tex, out, R, p.multiProcessorCount, ghz);
     run<2>("mix 1:1", recs, tex, out, R, p.multiProcessorCount, ghz);
     run<3>("mix 2:1", recs, tex, out, R, p.multiProcessorCount, ghz);
+    run<4>("ldg128 (16-byte records)", recs, tex, out, R, p.multiProcessorCount, ghz);
   }
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }

@@ -20,14 +20,14 @@ if which == "test":
     gb.upload(position=gbd.position, depth=gbd.depth, normal=gbd.normal, albedo=gbd.albedo, mro=gbd.mro)
     lights = None
 res = {}
-for name, flags in (("fast", 0), ("fast_exact", _capi.CTX_SSAO_EXACT_TAPS), ("parity", _capi.CTX_PARITY_MATH),
+for name, flags in (("fast", 0), ("fast_ray", _capi.CTX_SSAO_RAY_DEPTH_PROXY), ("parity_ray", _capi.CTX_PARITY_MATH | _capi.CTX_SSAO_RAY_DEPTH_PROXY), ("fast_exact", _capi.CTX_SSAO_EXACT_TAPS), ("parity", _capi.CTX_PARITY_MATH),
                     ("parity_exact", _capi.CTX_PARITY_MATH | _capi.CTX_SSAO_EXACT_TAPS)):
     ctx.set_flags(flags)
     dp.aoCounts.tensor.zero_()
     dp.draw(g, gb, ibl, lights, ssr, _capi.SHADE_SKIP_TONEMAP, stream)
     torch.cuda.synchronize()
     res[name] = dp.aoCounts.tensor.clone()
-for a, b in (("fast", "fast_exact"), ("parity", "parity_exact"), ("fast", "parity")):
+for a, b in (("fast", "fast_exact"), ("parity", "parity_exact"), ("fast_ray", "fast_exact"), ("parity_ray", "parity_exact"), ("fast", "parity")):
     d = (res[a] != res[b])
     idx = d.nonzero().flatten()[:8].tolist()
     print(a, "vs", b, ": mismatching pixels", int(d.sum()), "of", d.numel(), "max |diff|", int((res[a].int() - res[b].int()).abs().max()),
