@@ -206,7 +206,7 @@ ADEV V4 environmentLitSample(const FrameParams& P, V3 currentPos, float u, float
 }
 
 #ifndef ALTHEA_SSR_MIN_BLOCKS
-#define ALTHEA_SSR_MIN_BLOCKS 1
+#define ALTHEA_SSR_MIN_BLOCKS 4 // 64 registers: the march is latency-bound, a fourth resident CTA is worth more than the registers
 #endif
 __global__ void __launch_bounds__(256, ALTHEA_SSR_MIN_BLOCKS) ssr_capture_kernel(const __grid_constant__ FrameParams P) {
   const int x = blockIdx.x * 16 + (threadIdx.x & 15);
@@ -260,28 +260,45 @@ __global__ void __launch_bounds__(256, ALTHEA_SSR_MIN_BLOCKS) ssr_capture_kernel
     //    dot(dir, rayDir) > 0.999  <=>  dot(v, rayDir) > 0 and dot(v, rayDir)^2 > 0.999^2 |v|^2.
     const V3 camMinusPos = mk3(P.g.inverseView[12], P.g.inverseView[13], P.g.inverseView[14]) - worldPos;
     const V3 W0 = mk3(P.ssrW0[0], P.ssrW0[1], P.ssrW0[2]), Wu = mk3(P.ssrWu[0], P.ssrWu[1], P.ssrWu[2]), Wv = mk3(P.ssrWv[0], P.ssrWv[1], P.ssrWv[2]);
+    //  * along the march (cu, cv) = (u, v) + (i + 1) step, so wd and dot(wd, zAxis) are affine in the step number, and so are
+    //    dot(wd, rayDir) and dot(wd, perpRef): the two tests of a step need  along = cR + k aR(i),  projection = cP + k aP(i)
+    //    with k the reciprocal above: seven arithmetic instructions instead of the twenty-two of forming wd, vv and two dot
+    //    products. The vector itself is only built on the rare step that passes both sign tests.
+    const V3 dW = mk3(fmaf(Wu.x, stepX, Wv.x * stepY), fmaf(Wu.y, stepX, Wv.y * stepY), fmaf(Wu.z, stepX, Wv.z * stepY));
+    const V3 Wat = mk3(fmaf(Wu.x, u, fmaf(Wv.x, v, W0.x)), fmaf(Wu.y, u, fmaf(Wv.y, v, W0.y)), fmaf(Wu.z, u, fmaf(Wv.z, v, W0.z)));
+    const float aR0 = dot3(Wat, rayDir), daR = dot3(dW, rayDir), aP0 = dot3(Wat, perpRef), daP = dot3(dW, perpRef);
+    const float cR = dot3(camMinusPos, rayDir), cP = dot3(camMinusPos, perpRef);
+    const float S0 = fmaf(P.ssrS[1], u, fmaf(P.ssrS[2], v, P.ssrS[0])), dS = fmaf(P.ssrS[1], stepX, P.ssrS[2] * stepY);
+    // |vv|^2 = |cam - pos|^2 + 2 k dot(cam - pos, wd) + k^2 |wd|^2 with dot(cam - pos, wd) affine and |wd|^2 quadratic in the step
+    const float cc = dot3(camMinusPos, camMinusPos), cw0 = 2.0f * dot3(camMinusPos, Wat), dcw = 2.0f * dot3(camMinusPos, dW);
+    const float ww0 = dot3(Wat, Wat), ww1 = 2.0f * dot3(Wat, dW), ww2 = dot3(dW, dW);
+    float fi = 0.0f;
     for (int i = 0; i < 128; ++i) {
       cu += stepX;
       cv += stepY;
+      fi += 1.0f;
       if (outside01(cu, cv)) break;
       // bilinear depth tap, CLAMP_TO_EDGE (rule A1/A2) from the padded copy; a + t (b - a) lerps
       const DepthTap q = depthTapPadded(P, cu, cv);
       const float top = fmaf(q.t10 - q.t00, q.fx, q.t00), bot = fmaf(q.t11 - q.t01, q.fx, q.t01);
       const float dRaw = fmaf(bot - top, q.fy, top);
       // pos - worldPos = (cam - worldPos) + wd * (far near / ((dRaw (far - near) - far) * dot(wd, zAxis)))
-      const float den = fmaf(dRaw, 1000.0f - 0.01f, -1000.0f) * fmaf(P.ssrS[1], cu, fmaf(P.ssrS[2], cv, P.ssrS[0]));
+      const float den = fmaf(dRaw, 1000.0f - 0.01f, -1000.0f) * fmaf(fi, dS, S0);
       const float k = (1000.0f * 0.01f) * rcpf(den);
-      const V3 wd = mk3(fmaf(Wu.x, cu, fmaf(Wv.x, cv, W0.x)), fmaf(Wu.y, cu, fmaf(Wv.y, cv, W0.y)), fmaf(Wu.z, cu, fmaf(Wv.z, cv, W0.z)));
-      const V3 vv = mk3(fmaf(wd.x, k, camMinusPos.x), fmaf(wd.y, k, camMinusPos.y), fmaf(wd.z, k, camMinusPos.z));
-      const float len2 = dot3(vv, vv), along = dot3(vv, rayDir);
-      const float currentProjection = dot3(vv, perpRef);
-      // i > 0 is carried by prevProjection's NaN start value (NaN <= 0 is false). A tap exactly AT worldPos (len2 == 0, where the
+      const float along = fmaf(k, fmaf(fi, daR, aR0), cR);
+      const float currentProjection = fmaf(k, fmaf(fi, daP, aP0), cP);
+      // i > 0 is carried by prevProjection's NaN start value (NaN <= 0 is false). A tap exactly AT worldPos (where the
       // restatement's normalize(0) is NaN) fails `along > 0` here too; only the step after it could differ, on nothing we render.
-      if (currentProjection * prevProjection <= 0.0f && along > 0.0f && along * along > (0.999f * 0.999f) * len2) {
-        V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, cu, cv)));
-        if (dot3(currentNormal, rayDir) < 0.0f) {
-          out = environmentLitSample(P, worldPos + vv, cu, cv, rayDir, currentNormal);
-          break;
+      if (currentProjection * prevProjection <= 0.0f && along > 0.0f) {
+        const float len2 = fmaf(k, fmaf(k, fmaf(fi, fmaf(fi, ww2, ww1), ww0), fmaf(fi, dcw, cw0)), cc);
+        if (along * along > (0.999f * 0.999f) * len2) {
+          V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, cu, cv)));
+          if (dot3(currentNormal, rayDir) < 0.0f) {
+            const V3 wd = mk3(fmaf(Wu.x, cu, fmaf(Wv.x, cv, W0.x)), fmaf(Wu.y, cu, fmaf(Wv.y, cv, W0.y)), fmaf(Wu.z, cu, fmaf(Wv.z, cv, W0.z)));
+            const V3 vv = mk3(fmaf(wd.x, k, camMinusPos.x), fmaf(wd.y, k, camMinusPos.y), fmaf(wd.z, k, camMinusPos.z));
+            out = environmentLitSample(P, worldPos + vv, cu, cv, rayDir, currentNormal);
+            break;
+          }
         }
       }
       prevProjection = currentProjection;
