@@ -416,11 +416,13 @@ def main():
         time.sleep(0.3)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()  # no-op unless a profiler runs with --profile-from-start off: the ncu launch list is this region
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
     launches = ctx.launch_count() - launches0
