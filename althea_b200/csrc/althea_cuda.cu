@@ -56,6 +56,9 @@ struct althea_cuda_ctx {
   // internal scratch: SSAO occluded-ray counts
   void* aoScratch = nullptr;
   size_t aoScratchBytes = 0;
+  // internal scratch: positions reconstructed from depth when the G-buffer has no position attachment (mode D)
+  void* positionScratch = nullptr;
+  size_t positionScratchBytes = 0;
   // internal scratch: SSAO position-quad proxy, (W+1) x (H+1) x 32 B
   void* quadScratch = nullptr;
   size_t quadScratchBytes = 0;
@@ -291,8 +294,11 @@ int fillFrameParams(althea_cuda_ctx* ctx, const althea_global_uniforms* u, const
   if ((rc = getImage(ctx, gb->normal, ALTHEA_FORMAT_R16G16B16A16_SFLOAT, "gbuffer.normal", &normal))) return rc;
   if ((rc = getImage(ctx, gb->albedo, ALTHEA_FORMAT_R8G8B8A8_UNORM, "gbuffer.albedo", &albedo))) return rc;
   if ((rc = getImage(ctx, gb->mro, ALTHEA_FORMAT_R8G8B8A8_UNORM, "gbuffer.mro", &mro))) return rc;
-  if ((rc = getImage(ctx, gb->depth, ALTHEA_FORMAT_R32_SFLOAT, "gbuffer.depth", &depth, needPosition))) return rc;
-  if ((rc = getImage(ctx, gb->position, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "gbuffer.position", &position, !needPosition))) return rc;
+  // SSR needs the depth image. The lighting pass needs positions: the legacy RGBA32F attachment when the host has one
+  // (mode P), else they are reconstructed from depth into engine scratch (mode D: what today's
+  // GBufferResources provides, Src/DeferredRendering.cpp:42-99 has no position attachment)
+  if ((rc = getImage(ctx, gb->position, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "gbuffer.position", &position, true))) return rc;
+  if ((rc = getImage(ctx, gb->depth, ALTHEA_FORMAT_R32_SFLOAT, "gbuffer.depth", &depth, needPosition && position != nullptr))) return rc;
   if ((rc = getImage(ctx, ibl->env, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "ibl.env", &env))) return rc;
   if ((rc = getImage(ctx, ibl->prefiltered, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "ibl.prefiltered", &pre))) return rc;
   if ((rc = getImage(ctx, ibl->irradiance, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, "ibl.irradiance", &irr))) return rc;
@@ -428,6 +434,7 @@ void althea_cuda_destroy(althea_cuda_ctx* ctx) {
   }
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   if (ctx->aoScratch) cudaFree(ctx->aoScratch);
+  if (ctx->positionScratch) cudaFree(ctx->positionScratch);
   if (ctx->quadScratch) cudaFree(ctx->quadScratch);
   if (ctx->depthPadScratch) cudaFree(ctx->depthPadScratch);
   if (ctx->gatherCounter) cudaFree(ctx->gatherCounter);
@@ -794,6 +801,17 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
       P.ao.ptr = ctx->aoScratch; P.ao.w = P.W; P.ao.h = P.H; P.ao.pitch = P.W;
     }
   }
+  const bool reconstruct = P.position.ptr == nullptr; // mode D
+  if (reconstruct) {
+    size_t need = (size_t)P.W * P.H * 16;
+    if (ctx->positionScratchBytes < need) {
+      if (ctx->positionScratch) { cudaDeviceSynchronize(); cudaFree(ctx->positionScratch); ctx->positionScratch = nullptr; ctx->positionScratchBytes = 0; }
+      cudaError_t e = cudaMalloc(&ctx->positionScratch, need);
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(position scratch %zu): %s", need, cudaGetErrorString(e)); }
+      ctx->positionScratchBytes = need;
+    }
+    P.position.ptr = ctx->positionScratch; P.position.w = P.W; P.position.h = P.H; P.position.pitch = P.W * 16;
+  }
   const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
   const bool computeAo = needAo && !(flags & ALTHEA_SHADE_AO_FROM_IMAGE);
   const bool exactTaps = ctx->flags & ALTHEA_CTX_SSAO_EXACT_TAPS;
@@ -822,6 +840,8 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
   if (P.gatherCounter) cudaMemsetAsync(P.gatherCounter, 0, 2 * sizeof(unsigned long long), stream);
+  if (reconstruct)
+    timedLaunch(ctx, "reconstruct_position", stream, [&] { parity ? althea_parity::launch_reconstruct_position(P, stream) : althea_fast::launch_reconstruct_position(P, stream); });
   if (computeAo) {
     if (exactTaps) {
       timedLaunch(ctx, "ssao_exact", stream, [&] { parity ? althea_parity::launch_ssao_exact(P, stream) : althea_fast::launch_ssao_exact(P, stream); });

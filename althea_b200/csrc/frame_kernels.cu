@@ -1043,6 +1043,24 @@ template <bool COUNT, int KIND> __global__ void __launch_bounds__(256, ALTHEA_SS
   }
 }
 
+// ---- mode D: positions from depth ------------------------------------------------------------------------------------
+// Today's GBufferResources has no position attachment (Src/DeferredRendering.cpp:42-99); the lighting pass and SSAO then work on
+// reconstructPosition(uv, depth) (Misc/ReconstructPosition.glsl:4-22), emptiness coming from normal.a == 0 as in SSR.frag:136-141.
+// One pass writes them to engine scratch in the legacy attachment's layout, so everything downstream is the mode-P path.
+__global__ void __launch_bounds__(256) reconstruct_position_kernel(const __grid_constant__ FrameParams P) {
+  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int y = blockIdx.y * 16 + (threadIdx.x >> 4); // whole frame: SSAO taps reach outside a scissor band
+  if (x >= P.W || y >= P.H) return;
+  float4 out = make_float4(0.0f, 0.0f, 0.0f, 0.0f); // the attachment's clear colour where nothing was drawn
+  const V4 normal4 = FmtRGBA16F::load(P.normal, x, y);
+  if (normal4.w != 0.0f) {
+    const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
+    const V3 p = reconstructPosition(P, u, v, __ldg(rowPtr<float>(P.depth, y) + x));
+    out = make_float4(p.x, p.y, p.z, 1.0f);
+  }
+  rowPtrW<float4>(P.position, y)[x] = out;
+}
+
 // ---- deferred shading -----------------------------------------------------------------------------------------------
 ADEV V3 tonemap(V3 c, float exposure) {
   return mk3(1.0f - expf(-c.x * exposure), 1.0f - expf(-c.y * exposure), 1.0f - expf(-c.z * exposure));
@@ -1131,6 +1149,7 @@ void launch_ssao_quads(const FrameParams& P, cudaStream_t s) {
   if (P.quadKind) ssao_rayquads_kernel<<<grid, 256, 0, s>>>(P);
   else ssao_quads_kernel<<<grid, 256, 0, s>>>(P);
 }
+void launch_reconstruct_position(const FrameParams& P, cudaStream_t s) { reconstruct_position_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
 void launch_deferred_shade(const FrameParams& P, cudaStream_t s) { deferred_shade_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
 
 } // namespace ALTHEA_NS

@@ -295,10 +295,12 @@ class GBufferResources:
     """Src/DeferredRendering.cpp:37-155: depth (R32F view of D32), normal RGBA16F, albedo RGBA8, MRO RGBA8, plus the legacy
     RGBA32F position target DeferredPass.frag reads (mode P)."""
 
-    def __init__(self, ctx: Context, width: int, height: int):
+    def __init__(self, ctx: Context, width: int, height: int, with_position: bool = True):
+        """with_position=False is today's GBufferResources (no legacy position attachment): the lighting pass and SSAO then
+        work on positions reconstructed from depth (mode D)."""
         self.ctx, self.width, self.height = ctx, width, height
         self.depth = ctx.new_image(_capi.FORMAT_R32_SFLOAT, width, height)
-        self.position = ctx.new_image(_capi.FORMAT_R32G32B32A32_SFLOAT, width, height)
+        self.position = ctx.new_image(_capi.FORMAT_R32G32B32A32_SFLOAT, width, height) if with_position else None
         self.normal = ctx.new_image(_capi.FORMAT_R16G16B16A16_SFLOAT, width, height)
         self.albedo = ctx.new_image(_capi.FORMAT_R8G8B8A8_UNORM, width, height)
         self.mro = ctx.new_image(_capi.FORMAT_R8G8B8A8_UNORM, width, height)
@@ -307,7 +309,7 @@ class GBufferResources:
         """Fills the attachments from host (numpy) or device (torch) arrays of raw texel data (tests / bench inputs)."""
         torch = _torch()
         for img, src in ((self.position, position), (self.depth, depth), (self.normal, normal), (self.albedo, albedo), (self.mro, mro)):
-            if src is None:
+            if src is None or img is None:
                 continue
             if isinstance(src, np.ndarray):
                 src = torch.from_numpy(np.ascontiguousarray(src).view(np.uint8).reshape(-1))
@@ -316,7 +318,7 @@ class GBufferResources:
             img.tensor.copy_(src, non_blocking=True)
 
     def struct(self) -> _capi.GBuffer:
-        return _capi.GBuffer(self.depth.handle, self.position.handle, self.normal.handle, self.albedo.handle, self.mro.handle)
+        return _capi.GBuffer(self.depth.handle, self.position.handle if self.position is not None else 0, self.normal.handle, self.albedo.handle, self.mro.handle)
 
 
 class SceneToGBufferPass:

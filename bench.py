@@ -34,6 +34,7 @@ UNIT = "Mpixel/s"
 # algorithmic bytes per pixel (SURVEY.md 8d / DESIGN.md): each buffer read once, written once
 BYTES_PER_PX = {
     "ssr_capture": 28.0,      # depth 4 + normal 8 + albedo 4 + MRO 4 + write RGBA16F 8
+    "reconstruct_position": 28.0,  # mode D: depth 4 + normal 8 read, RGBA32F position scratch 16 written
     "ssr_depth_pad": 8.0,     # depth 4 read + padded copy 4 written per pixel (engine scratch)
     "glossy_convolve": 13.28,  # read 8*(1+1/4+1/16+1/64) + write 8*(1/4+...+1/256)
     "ssao": 25.0,             # position 16 + normal 8 + write count 1 (the proxy records are engine scratch, not algorithmic)
@@ -207,7 +208,7 @@ def main_bands8k(args, ctx, rank, local_rank, world, device):
         dist.destroy_process_group()
 
 
-def build_rank_inputs(ctx, rank: int, views: int, device: str, quick_ibl: bool = False):
+def build_rank_inputs(ctx, rank: int, views: int, device: str, quick_ibl: bool = False, with_position: bool = True):
     """All device-resident inputs of this rank: IBL set (built with our own precompute kernels), lights + shadow cubes, and
     `views` G-buffers. Returns the objects plus the measured IBL precompute timings."""
     import torch
@@ -268,7 +269,9 @@ def build_rank_inputs(ctx, rank: int, views: int, device: str, quick_ibl: bool =
         gv = rank * views + v  # global view id, yaw = view * 5.625 deg
         g = scene.make_uniforms(W4K, H4K, pos=(0.0, 2.0, 0.0), yaw=gv * 5.625 * 3.141592653589793 / 180.0, pitch=-0.2, light_count=N_LIGHTS)
         gbd = scene.s_scene(g, W4K, H4K, sc, device=device)
-        gb = engine.GBufferResources(ctx, W4K, H4K)
+        # with_position=False: the four attachments today's GBufferResources holds (Src/DeferredRendering.cpp:42-99); the engine
+        # reconstructs positions from depth inside the frame (mode D). True: the legacy RGBA32F position attachment as well (mode P)
+        gb = engine.GBufferResources(ctx, W4K, H4K, with_position=with_position)
         gb.upload(position=gbd.position, depth=gbd.depth, normal=gbd.normal, albedo=gbd.albedo, mro=gbd.mro)
         ssr = engine.ScreenSpaceReflection(ctx, W4K, H4K)
         dp = engine.DeferredPass(ctx, W4K, H4K, _capi.FORMAT_R16G16B16A16_SFLOAT)
@@ -366,6 +369,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-producers", action="store_true")
+    ap.add_argument("--gbuffer-mode", default="D", choices=["D", "P"],
+                    help="D (default): depth / normal / albedo / MRO, what the reference's GBufferResources holds; positions are reconstructed from "
+                         "depth inside the frame. P: the legacy RGBA32F position attachment is an input too (SURVEY.md 8(c-bis) R5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)
@@ -390,7 +396,8 @@ def main():
     ctx = engine.Context(local_rank)
     if args.workload == "bands8k":
         return main_bands8k(args, ctx, rank, local_rank, world, device)
-    ibl, lights, views, ibl_t = build_rank_inputs(ctx, rank, args.views, device)
+    mode_p = args.gbuffer_mode == "P"
+    ibl, lights, views, ibl_t = build_rank_inputs(ctx, rank, args.views, device, with_position=mode_p)
     stream = engine.current_stream_ptr(local_rank)
     V = len(views)
     px_per_step = V * W4K * H4K
@@ -480,8 +487,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         F = _capi
-        fmts = [("position", F.FORMAT_R32G32B32A32_SFLOAT), ("depth", F.FORMAT_R32_SFLOAT), ("normal", F.FORMAT_R16G16B16A16_SFLOAT),
-                ("albedo", F.FORMAT_R8G8B8A8_UNORM), ("mro", F.FORMAT_R8G8B8A8_UNORM)]
+        fmts = ([("position", F.FORMAT_R32G32B32A32_SFLOAT)] if mode_p else []) + [
+            ("depth", F.FORMAT_R32_SFLOAT), ("normal", F.FORMAT_R16G16B16A16_SFLOAT), ("albedo", F.FORMAT_R8G8B8A8_UNORM), ("mro", F.FORMAT_R8G8B8A8_UNORM)]
         host_in = []
         for (g, gb, ssr, dp) in views:
             host_in.append({n: getattr(gb, n).tensor.cpu().pin_memory() for n, _ in fmts})
@@ -496,7 +503,7 @@ def main():
         dgbs, ddps = [], []
         for _ in range(NBUF):
             dgb = engine.GBufferResources.__new__(engine.GBufferResources)
-            dgb.ctx, dgb.width, dgb.height = ctx, W4K, H4K
+            dgb.ctx, dgb.width, dgb.height, dgb.position = ctx, W4K, H4K, None
             for n, f in fmts:
                 setattr(dgb, n, ctx.create_image(f, W4K, H4K))
             dgbs.append(dgb)
@@ -543,7 +550,7 @@ def main():
         ms2 = float(t2.item()) / k2
         e2e = {"value": world * px_per_step / (ms2 * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms2, "steps": k2, "numa_node": numa_node,
-               "how": "C ABI with pinned host buffers: upload of 5 G-buffer attachments per view, frame, download of the RGBA16F colour target; "
+               "how": "C ABI with pinned host buffers: upload of the %d G-buffer attachments per view, frame, download of the RGBA16F colour target; " % len(fmts) +
                       "double-buffered, copies overlapped with kernels on separate streams"}
 
     if rank == 0:
@@ -586,8 +593,9 @@ def main():
                 "config": {"workload": "C3/C5 stand-in: %d views/GPU of a 3840x2160 S-scene deferred+SSAO+SSR+glossy frame, 16 point lights + 256^2 omni "
                                        "shadow cubes, view-sharded (no collective)" % V,
                            "views_per_gpu": V, "resolution": [W4K, H4K], "lights": N_LIGHTS, "l2_policy": "inputs (%.1f GB/step/GPU) exceed the 126 MB L2"
-                                                                                                      % (V * px_frame * 36 / 1e9),
-                           "math": "fast build (FFMA); parity build checked in tests"},
+                                                                                                      % (V * px_frame * (36 if mode_p else 20) / 1e9),
+                           "math": "fast build (FFMA); parity build checked in tests",
+                           "gbuffer": "mode %s: %s" % (args.gbuffer_mode, "depth + normal + albedo + MRO attachments (20 B/px), positions reconstructed from depth inside the frame" if not mode_p else "legacy position attachment as input (36 B/px)")},
                 "gpu_launches": int(launches) * world, "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_chain": chain, "stages": stages, "producers": producers,
                 "ibl_prefilter_ms": ibl_t.get("config1_cube", {}).get("ibl_prefilter"),
                 "ibl_precompute_ms": ibl_t,

@@ -147,7 +147,9 @@ typedef struct althea_point_light { /* 32 B == Include/Althea/PointLight.h:31-34
 
 typedef struct althea_gbuffer { /* image handles; GBufferResources, Src/DeferredRendering.cpp:37-155 */
   uint64_t depth;    /* R32_SFLOAT: the depth image written THIS frame (SSR.frag:29 hard-wires depthA) */
-  uint64_t position; /* R32G32B32A32_SFLOAT, .a == 0 => empty (legacy DeferredPass.frag:18,44) */
+  uint64_t position; /* R32G32B32A32_SFLOAT, .a == 0 => empty (legacy DeferredPass.frag:18,44); 0 => the lighting pass and SSAO use
+                        positions reconstructed from `depth` (Misc/ReconstructPosition.glsl), empty where normal.a == 0: what a
+                        host without the legacy attachment passes (today's GBufferResources) */
   uint64_t normal;   /* R16G16B16A16_SFLOAT, .a == 0 => empty (SSR.frag:136-141) */
   uint64_t albedo;   /* R8G8B8A8_UNORM */
   uint64_t mro;      /* R8G8B8A8_UNORM: metallic, roughness, occlusion */

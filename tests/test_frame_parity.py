@@ -395,3 +395,38 @@ def test_gather_diagnostics(ctx_fast):
     assert gathers > shaded * 24  # more than one tap per ray on average
     rate = ctx_fast.gather_ceiling(512, 512, 32, 16)
     assert rate > 1e9
+
+
+@pytest.mark.parametrize("which", ["parity", "fast"])
+def test_mode_d_positions_from_depth(request, oracle, which):
+    """A G-buffer without the legacy position attachment (today's GBufferResources): the lighting pass and SSAO work on
+    positions reconstructed from depth, empty where normal.a == 0. Equal to the mode-P path fed with the restatement's
+    reconstructPosition of every pixel: bit for bit in the parity build, to the mask / colour bars in the fast build."""
+    from althea_b200 import _capi, engine
+    ctx = _ctx(request, which)
+    fd = FrameData("scene", 160, 90, n_lights=2, shadow_res=32)
+    H, W = fd.H, fd.W
+    og = oracle.GlobalUniforms.from_buffer_copy(bytes(fd.uniforms))
+    nrm_a = half_to_float(fd.normal)[..., 3]
+    pos = np.zeros((H, W, 4), np.float32)
+    for y in range(H):
+        for x in range(W):
+            if nrm_a[y, x] != 0:
+                pos[y, x, :3] = oracle.reconstruct_position(og, np.float32(x + 0.5) / np.float32(W), np.float32(y + 0.5) / np.float32(H), fd.depth[y, x])
+                pos[y, x, 3] = 1.0
+    fd.position = pos  # the mode-P twin: the same positions handed over as an attachment
+    gp = GpuFrame(ctx, fd)
+    gp.deferred.draw(fd.uniforms, gp.gbuffer, gp.ibl, gp.lights, gp.ssr, _capi.SHADE_SKIP_TONEMAP)
+    want_ao, want_col = gp.ao_counts().copy(), gp.color().copy()
+    gd = GpuFrame(ctx, fd)
+    gd.gbuffer = engine.GBufferResources(ctx, W, H, with_position=False)
+    gd.gbuffer.upload(depth=fd.depth, normal=fd.normal, albedo=fd.albedo, mro=fd.mro)
+    gd.deferred.draw(fd.uniforms, gd.gbuffer, gd.ibl, gd.lights, gd.ssr, _capi.SHADE_SKIP_TONEMAP)
+    got_ao, got_col = gd.ao_counts(), gd.color()
+    if which == "parity":
+        assert np.array_equal(got_ao, want_ao) and np.array_equal(got_col, want_col)
+    else:
+        assert (got_ao != want_ao).mean() <= 1e-3
+        ok = (np.abs(got_col - want_col) <= 1e-3 * np.maximum(1.0, np.abs(want_col))).all(axis=-1)
+        assert ok.mean() >= 0.999
+    assert (got_ao[nrm_a == 0] == 255).all() and (got_ao[nrm_a != 0] <= 24).all()
