@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -1086,6 +1087,7 @@ int buildPrims(althea_cuda_ctx* ctx, RasterScratch* R, const althea_primitive* p
     d.verts = static_cast<const althea_vertex*>(vb->dptr);
     d.idx = static_cast<const uint32_t*>(ib->dptr);
     d.triCount = p.index_count / 3u;
+    d.vertCount = (uint32_t)std::min<size_t>(vb->bytes / sizeof(althea_vertex), 0xffffffffu);
     d.triOffset = (uint32_t)tris;
     tris += d.triCount;
     memcpy(d.model, p.model, sizeof d.model);

@@ -68,7 +68,7 @@ struct TriGeom {
 RDEV void triWorld(const RasterPrim& p, uint32_t t, TriGeom& g) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const uint32_t i = __ldg(p.idx + 3u * t + k);
+    const uint32_t i = min(__ldg(p.idx + 3u * t + k), p.vertCount - 1u); // an index past the buffer reads its last vertex
     g.vi[k] = i;
     const float* pos = p.verts[i].position;
     const float px = __ldg(pos), py = __ldg(pos + 1), pz = __ldg(pos + 2);
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(256) raster_fill_kernel(const __grid_constant_
     if (alphaTest) {
       const uint32_t t = tri - p.triOffset;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) vi[k] = __ldg(p.idx + 3u * t + k);
+      for (int k = 0; k < 3; ++k) vi[k] = min(__ldg(p.idx + 3u * t + k), p.vertCount - 1u);
     }
     // 8 x 4 pixel blocks, one pixel per lane
     const int bw = (x1 - x0 + 8) >> 3, bh = (y1 - y0 + 4) >> 2;

@@ -26,6 +26,7 @@ struct RasterPrim { // one Primitive::draw
   const althea_vertex* verts;
   const uint32_t* idx;
   uint32_t triCount, triOffset; // triOffset: triangles of the primitives drawn before this one (draw order breaks depth ties)
+  uint32_t vertCount, pad0;     // vertices in the buffer: indices are clamped to it (robustBufferAccess-style, never out of bounds)
   float model[16];
   uint32_t frontCW; // VK_FRONT_FACE_CLOCKWISE (Primitive::getFrontFace)
   uint32_t opaque;  // the shim proved alpha >= alphaCutoff everywhere: no per-fragment alpha test

@@ -255,6 +255,117 @@ def test_glb_loader_on_the_reference_asset(oracle):
     assert np.abs(np.linalg.norm(out["normal"][cov][:, :3], axis=1) - 1).max() < 1e-4
 
 
+def _write_glb(path, pos, nrm, uv, idx, png_rgba, with_tangents=False):
+    """A minimal binary glTF 2.0: one node (translated), one mesh primitive, one material with a PNG base colour texture."""
+    import io
+    import json
+    import struct
+
+    from PIL import Image as PILImage
+    buf = io.BytesIO()
+    PILImage.fromarray(png_rgba, "RGBA").save(buf, format="PNG")
+    png = buf.getvalue()
+    chunks, views, accessors = [], [], []
+
+    def add(data, target=None):
+        off = sum(len(c) for c in chunks)
+        pad = (-len(data)) % 4
+        chunks.append(data + b"\0" * pad)
+        v = {"buffer": 0, "byteOffset": off, "byteLength": len(data)}
+        if target:
+            v["target"] = target
+        views.append(v)
+        return len(views) - 1
+
+    def acc(arr, ctype, typ, target=None):
+        accessors.append({"bufferView": add(np.ascontiguousarray(arr).tobytes(), target), "componentType": ctype, "count": len(arr), "type": typ})
+        return len(accessors) - 1
+
+    a_pos, a_nrm, a_uv = acc(pos.astype(np.float32), 5126, "VEC3", 34962), acc(nrm.astype(np.float32), 5126, "VEC3", 34962), acc(uv.astype(np.float32), 5126, "VEC2", 34962)
+    a_idx = acc(idx.astype(np.uint16), 5123, "SCALAR", 34963)
+    attrs = {"POSITION": a_pos, "NORMAL": a_nrm, "TEXCOORD_0": a_uv}
+    if with_tangents:
+        tan = np.tile(np.array([[1.0, 0.0, 0.0, 1.0]], np.float32), (len(pos), 1))
+        attrs["TANGENT"] = acc(tan, 5126, "VEC4", 34962)
+    img_view = add(png)
+    gltf = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}],
+            "nodes": [{"mesh": 0, "translation": [0.5, 0.0, -1.0], "scale": [2.0, 2.0, 2.0]}],
+            "meshes": [{"primitives": [{"attributes": attrs, "indices": a_idx, "material": 0}]}],
+            "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}, "baseColorFactor": [1.0, 0.5, 0.25, 1.0], "metallicFactor": 0.2,
+                                                     "roughnessFactor": 0.7}, "alphaCutoff": 0.3}],
+            "textures": [{"source": 0, "sampler": 0}], "samplers": [{"wrapS": 33071, "wrapT": 33648, "minFilter": 9729, "magFilter": 9728}],
+            "images": [{"bufferView": img_view, "mimeType": "image/png"}], "bufferViews": views, "accessors": accessors,
+            "buffers": [{"byteLength": sum(len(c) for c in chunks)}]}
+    js = json.dumps(gltf).encode()
+    js += b" " * ((-len(js)) % 4)
+    binc = b"".join(chunks)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<III", 0x46546C67, 2, 12 + 8 + len(js) + 8 + len(binc)))
+        f.write(struct.pack("<II", len(js), 0x4E4F534A) + js)
+        f.write(struct.pack("<II", len(binc), 0x004E4942) + binc)
+
+
+@pytest.mark.parametrize("with_tangents", [False, True])
+def test_glb_loader_on_a_synthetic_file(tmp_path, oracle, with_tangents):
+    """load_glb on a file written here (the reference's assets are not on the GPU box): node transform, material factors, sampler
+    translation, texture decode + mip chain, and the two vertex paths of Primitive.cpp (tangents from the file: indexed vertices;
+    no tangents: vertices de-indexed, tangents generated)."""
+    pos = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], np.float32)
+    nrm = np.tile(np.array([[0, 0, 1]], np.float32), (4, 1))
+    uv = np.array([[0, 1], [1, 1], [1, 0], [0, 0]], np.float32)
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+    tex = np.zeros((8, 8, 4), np.uint8)
+    tex[..., 0], tex[..., 3] = 200, 255
+    tex[:4, :, 1] = 255
+    path = str(tmp_path / "quad.glb")
+    _write_glb(path, pos, nrm, uv, idx, tex, with_tangents)
+    prims = model.load_glb(path)
+    assert len(prims) == 1
+    p = prims[0]
+    assert p.triangle_count == 2
+    assert len(p.vertices) == (4 if with_tangents else 6)  # Primitive.cpp:147: generated tangents need unshared vertices
+    m = p.material
+    assert m.baseColorFactor == (1.0, 0.5, 0.25, 1.0) and m.metallicFactor == pytest.approx(0.2) and m.roughnessFactor == pytest.approx(0.7)
+    assert m.alphaCutoff == pytest.approx(0.3) and m.normalTexture is None and m.metallicRoughnessTexture is None
+    t = m.baseTexture
+    assert t.width == 8 and t.height == 8 and len(t.levels) == 1  # minFilter LINEAR: no mips (Src/Sampler.cpp:78-85)
+    assert t.sampler == model.sampler_word(model.WRAP_CLAMP, model.WRAP_MIRROR, True, False, model.MIP_NONE, True)
+    assert np.array_equal(t.levels[0], tex)
+    assert np.allclose(p.model, np.array([[2, 0, 0, 0.5], [0, 2, 0, 0], [0, 0, 2, -1], [0, 0, 0, 1]], np.float32))
+    tang, bit, n = p.vertices[:, 3:6], p.vertices[:, 6:9], p.vertices[:, 9:12]
+    assert np.allclose(n, [0, 0, 1]) and np.allclose(np.abs(tang), [1, 0, 0], atol=1e-6) and np.allclose(np.abs(bit), [0, 1, 0], atol=1e-6)
+    # and it renders: the quad (scaled by 2, moved) in front of the camera, coloured by factor * texture
+    W, H = 48, 32
+    g, proj, view = _camera(W, H, pos=(0.5, 0.0, 3.0))
+    out = oracle.draw_gbuffer(proj, view, prims, W, H)
+    cov = out["tri"] != NONE
+    assert 0.2 < cov.mean() < 0.9
+    r = out["albedo"][cov][:, 0]
+    assert r.min() > 100  # sRGB 200 -> linear 0.578 -> * 1.0 -> 147
+    assert set(np.unique(out["albedo"][cov][:, 1] > 60)) == {False, True}  # the green half of the texture and the other half
+
+
+def test_triangles_sharing_an_edge_never_both_claim_a_pixel(oracle):
+    """Random quads split along a diagonal, random cameras: the two triangles' coverages are disjoint and their union is the
+    coverage of drawing both (top-left rule + exactly opposite edge values on the shared edge)."""
+    rng = np.random.default_rng(23)
+    W, H = 72, 56
+    for trial in range(12):
+        c = rng.uniform(-1.5, 1.5, (4, 3))
+        c[:, 2] = rng.uniform(-1.0, 1.0)  # planar in z up to a shear below
+        c[:, 2] += 0.3 * c[:, 0]
+        g, proj, view = _camera(W, H, pos=tuple(rng.uniform(-0.3, 0.3, 2)) + (4.0,), yaw=float(rng.uniform(-0.1, 0.1)), pitch=float(rng.uniform(-0.1, 0.1)))
+        a = _tri_prim([c[0], c[1], c[2]])
+        b = _tri_prim([c[0], c[2], c[3]])
+        ca = oracle.draw_gbuffer(proj, view, [a], W, H)["tri"] != NONE
+        cb = oracle.draw_gbuffer(proj, view, [b], W, H)["tri"] != NONE
+        both = oracle.draw_gbuffer(proj, view, [a, b], W, H)["tri"] != NONE
+        if ca.sum() == 0 or cb.sum() == 0:  # the quad faces away from this camera (or is bow-tied): nothing to check
+            continue
+        assert not (ca & cb).any(), trial
+        assert np.array_equal(ca | cb, both), trial
+
+
 # ---- GPU: the CUDA path against the restatement ---------------------------------------------------------------------------
 def _gpu_gbuffer(ctx, uniforms, prims, W, H):
     import torch
