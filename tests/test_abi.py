@@ -66,3 +66,28 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\"[^\"]*oracle", src, flags=re.M), os.path.join(dirpath, fn)
+
+
+def test_header_is_plain_c_and_structs_match_the_binding(tmp_path):
+    """include/althea_cuda.h is the boundary a C host binds: it must compile as C99 on its own, and the structs the Python
+    binding mirrors must have the sizes and offsets the C compiler gives them."""
+    import subprocess
+    src = tmp_path / "probe.c"
+    src.write_text('''#include <stddef.h>
+#include <stdio.h>
+#include "althea_cuda.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(althea_vertex), sizeof(althea_texture_ref), sizeof(althea_material), sizeof(althea_primitive),
+         sizeof(althea_point_light_constants), offsetof(althea_primitive, model), offsetof(althea_primitive, material),
+         offsetof(althea_material, baseTexture));
+  printf("%zu %zu %zu %zu\\n", sizeof(althea_global_uniforms), sizeof(althea_point_light), sizeof(althea_gbuffer), sizeof(althea_sync));
+  return 0;
+}
+''')
+    exe = tmp_path / "probe"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    a, b = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    P, M = _capi.Primitive, _capi.Material
+    assert [int(v) for v in a.split()] == [_capi.VERTEX_BYTES, C.sizeof(_capi.TextureRef), C.sizeof(M), C.sizeof(P), C.sizeof(_capi.PointLightConstants),
+                                           P.model.offset, P.material.offset, M.baseTexture.offset]
+    assert [int(v) for v in b.split()] == [416, 32, C.sizeof(_capi.GBuffer), C.sizeof(_capi.Sync)]
