@@ -155,6 +155,35 @@ def test_mip_selection_and_wrap(oracle):
     assert a.max() >= 240 and a.min() <= 15
 
 
+def test_wrap_modes_and_nearest_filtering(oracle):
+    """uv running from -1 to 2 across a quad over a 4-texel ramp: REPEAT shows the ramp three times, CLAMP_TO_EDGE holds the end
+    texels outside [0, 1], MIRRORED_REPEAT reverses the outer copies; NEAREST magnification returns texel values unblended."""
+    W, H = 96, 8
+    ramp = np.zeros((1, 4, 4), np.uint8)
+    ramp[0, :, 0] = (0, 85, 170, 255)
+    ramp[..., 3] = 255
+    ramp = np.repeat(ramp, 4, axis=0)
+    g, proj, view = _ortho_like(W, H)
+    corners = [_world_of_pixel_corner(W, H, x, y) for x, y in ((0, 0), (0, H), (W, H), (W, 0))]
+
+    def render(wrap):
+        q = model.quad(corners)
+        # quad(): uv (0,0) (1,0) (1,1) (0,1) at the corners in order; remap u to run -1 .. 2 along x (corner order: x = 0, 0, W, W)
+        q.vertices[:, 12] = np.array([-1.0, -1.0, 2.0, 2.0], np.float32)
+        q.vertices[:, 13] = np.array([0.0, 1.0, 1.0, 0.0], np.float32)
+        q.material.baseTexture = model.TextureData.from_rgba8(ramp, model.sampler_word(wrap, wrap, mag_nearest=True, mip_mode=model.MIP_NONE, srgb=False))
+        out = oracle.draw_gbuffer(proj, view, [q], W, H)
+        assert (out["tri"] != NONE).all()
+        return out["albedo"][H // 2, :, 0].astype(int)
+
+    # 96 pixels over 3 uv units: 32 pixels per unit, 8 pixels per texel
+    texel = np.array([0, 85, 170, 255])
+    unit = np.repeat(texel, 8)
+    assert np.array_equal(render(model.WRAP_REPEAT), np.tile(unit, 3))
+    assert np.array_equal(render(model.WRAP_CLAMP), np.concatenate([np.full(32, 0), unit, np.full(32, 255)]))
+    assert np.array_equal(render(model.WRAP_MIRROR), np.concatenate([unit[::-1], unit, unit[::-1]]))
+
+
 def _shadow_scene():
     """A closed room (inward-facing walls) with a sphere in it."""
     sp = model.uv_sphere(0.8, (0.5, 0.6, -0.4), 10, 20)
