@@ -1048,7 +1048,7 @@ int rasterScratch(althea_cuda_ctx* ctx, RasterScratch** out) {
   if (!ctx->raster) {
     ctx->raster = new RasterScratch();
     cudaDeviceGetAttribute(&ctx->raster->sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    CUDA_TRY(ctx, cudaMalloc(&ctx->raster->counters, 4 * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->raster->counters, 8 * sizeof(uint32_t)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->raster->minAlphaDev, sizeof(unsigned int)));
   }
   *out = ctx->raster;
@@ -1141,36 +1141,37 @@ int buildPrims(althea_cuda_ctx* ctx, RasterScratch* R, const althea_primitive* p
   return ALTHEA_OK;
 }
 
-// setup then fill, no host round trip in between: the fill's persistent grid reads the work count on the device. If the tile
-// work list is too small the setup raises a sticky flag (counters[3] = items demanded) and the fill does nothing; the caller
-// checks the flag once per draw call (rasterOverflow) and redoes the call with a larger list.
+// setup then fill, no host round trip in between: the fill's persistent grid reads the work count on the device. Record and
+// tile-work lists are sized by demand, not by the worst case (every triangle visible in every view): if one is too small the
+// setup raises the pass's overflow flag, keeps counting what it would have needed (counters[3], [4]) and the fill does nothing;
+// the caller checks once per draw call (rasterOverflow) and redoes the call with larger lists.
 int runRaster(althea_cuda_ctx* ctx, RasterScratch* R, RasterJob& J, cudaStream_t stream) {
+  if (!J.triTotal || !J.nViews) return ALTHEA_OK;
   const unsigned long long pairs = (unsigned long long)J.triTotal * (unsigned)J.nViews;
-  if (!pairs) return ALTHEA_OK;
-  if (pairs > (1ull << 26)) return fail(ctx, ALTHEA_ERR_UNSUPPORTED, "%llu (triangle, view) pairs in one pass", pairs);
-  int rc = growScratch(ctx, &R->recs, &R->recsBytes, (size_t)pairs * sizeof(RasterRecord), "raster records");
-  if (rc) return rc;
-  if ((rc = growScratch(ctx, &R->work, &R->workBytes, ((size_t)pairs + (1u << 20)) * sizeof(uint2), "raster tile work list"))) return rc;
+  const size_t recWant = (size_t)std::min<unsigned long long>(pairs, 1ull << 21); // 2 M records (256 MB) to start with
+  int rc;
+  if (R->recsBytes < recWant * sizeof(RasterRecord) && (rc = growScratch(ctx, &R->recs, &R->recsBytes, recWant * sizeof(RasterRecord), "raster records"))) return rc;
+  if (R->workBytes < ((size_t)1 << 22) * sizeof(uint2) && (rc = growScratch(ctx, &R->work, &R->workBytes, ((size_t)1 << 22) * sizeof(uint2), "raster tile work list"))) return rc;
   J.recs = static_cast<RasterRecord*>(R->recs);
-  J.recCap = (uint32_t)pairs;
+  J.recCap = (uint32_t)std::min<size_t>(R->recsBytes / sizeof(RasterRecord), 0xffffffffu);
   J.work = static_cast<uint2*>(R->work);
-  J.workCap = (uint32_t)(R->workBytes / sizeof(uint2));
+  J.workCap = (uint32_t)std::min<size_t>(R->workBytes / sizeof(uint2), 0xffffffffu);
   J.counters = R->counters;
-  CUDA_TRY(ctx, cudaMemsetAsync(R->counters, 0, 3 * sizeof(uint32_t), stream)); // [3] stays: sticky across the passes of a call
+  CUDA_TRY(ctx, cudaMemsetAsync(R->counters, 0, 3 * sizeof(uint32_t), stream)); // [3], [4] stay: sticky across the passes of a call
   timedLaunch(ctx, "raster_setup", stream, [&] { althea_raster::launch_raster_setup(J, stream); });
   timedLaunch(ctx, "raster_fill", stream, [&] { althea_raster::launch_raster_fill(J, R->sms, stream); });
   return ALTHEA_OK;
 }
-// after the last pass of a draw call: 0 when every pass fitted, else the largest work-item demand seen (one host sync)
-int rasterOverflow(althea_cuda_ctx* ctx, RasterScratch* R, cudaStream_t stream, uint32_t* demanded) {
-  uint32_t c[4] = {0, 0, 0, 0};
+// after the last pass of a draw call: grows whichever list overflowed (one host sync); *again = the call must be redone
+int rasterOverflow(althea_cuda_ctx* ctx, RasterScratch* R, cudaStream_t stream, bool* again) {
+  uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CUDA_TRY(ctx, cudaMemcpyAsync(c, R->counters, sizeof c, cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(stream));
-  *demanded = c[3];
+  *again = c[3] != 0 || c[4] != 0;
+  int rc;
+  if (c[3] && (rc = growScratch(ctx, &R->work, &R->workBytes, ((size_t)c[3] + (c[3] >> 2) + 1024) * sizeof(uint2), "raster tile work list"))) return rc;
+  if (c[4] && (rc = growScratch(ctx, &R->recs, &R->recsBytes, ((size_t)c[4] + (c[4] >> 2) + 1024) * sizeof(RasterRecord), "raster records"))) return rc;
   return ALTHEA_OK;
-}
-int growWorkList(althea_cuda_ctx* ctx, RasterScratch* R, uint32_t demanded) {
-  return growScratch(ctx, &R->work, &R->workBytes, ((size_t)demanded + (demanded >> 2) + 1024) * sizeof(uint2), "raster tile work list");
 }
 } // namespace
 
@@ -1226,15 +1227,14 @@ int althea_cuda_draw_gbuffer(althea_cuda_ctx* ctx, const althea_global_uniforms*
   if (albedo) { levelView(*albedo, 0, 0, &v); J.outAlbedo = static_cast<uint32_t*>(const_cast<void*>(v.ptr)); J.pitchAlbedo = v.pitch; }
   if (mro) { levelView(*mro, 0, 0, &v); J.outMro = static_cast<uint32_t*>(const_cast<void*>(v.ptr)); J.pitchMro = v.pitch; }
   for (int attempt = 0;; ++attempt) {
-    CUDA_TRY(ctx, cudaMemsetAsync(R->counters, 0, 4 * sizeof(uint32_t), stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(R->counters, 0, 8 * sizeof(uint32_t), stream));
     timedLaunch(ctx, "raster_clear", stream, [&] { althea_raster::launch_raster_clear(J.vis, nullptr, px, stream); });
     if ((rc = runRaster(ctx, R, J, stream))) return rc;
     timedLaunch(ctx, "gbuffer_resolve", stream, [&] { althea_raster::launch_gbuffer_resolve(J, stream); });
-    uint32_t demanded = 0;
-    if ((rc = rasterOverflow(ctx, R, stream, &demanded))) return rc;
-    if (!demanded) break;
-    if (attempt) return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "raster tile work list overflowed twice (%u items)", demanded);
-    if ((rc = growWorkList(ctx, R, demanded))) return rc;
+    bool again = false;
+    if ((rc = rasterOverflow(ctx, R, stream, &again))) return rc;
+    if (!again) break;
+    if (attempt >= 2) return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "raster lists overflowed three times");
   }
   return endWork(ctx, sync, stream);
 }
@@ -1290,22 +1290,19 @@ int althea_cuda_draw_shadow_cubes(althea_cuda_ctx* ctx, uint64_t lights_buf, uin
   if ((rc = growScratch(ctx, &R->views, &R->viewsBytes, views.size() * sizeof(RasterView), "raster views"))) return rc;
   CUDA_TRY(ctx, cudaMemcpyAsync(R->views, views.data(), views.size() * sizeof(RasterView), cudaMemcpyHostToDevice, stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(stream));
-  for (int attempt = 0;; ++attempt) {
-    CUDA_TRY(ctx, cudaMemsetAsync(R->counters, 0, 4 * sizeof(uint32_t), stream));
-    for (uint32_t l = 0; l < light_count; ++l) {
-      J.views = static_cast<const RasterView*>(R->views) + 6 * l;
-      ImgView base;
-      levelView(*sh, 0, 6u * l, &base);
-      J.shadowBase = static_cast<float*>(const_cast<void*>(base.ptr));
-      // the six layers of a light are contiguous: one clear
-      timedLaunch(ctx, "raster_clear", stream, [&] { althea_raster::launch_raster_clear(nullptr, J.shadowBase, J.shadowLayerStride * 5 + facePx, stream); });
-      if ((rc = runRaster(ctx, R, J, stream))) return rc;
-    }
-    uint32_t demanded = 0;
-    if ((rc = rasterOverflow(ctx, R, stream, &demanded))) return rc;
-    if (!demanded) break;
-    if (attempt) return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "raster tile work list overflowed twice (%u items)", demanded);
-    if ((rc = growWorkList(ctx, R, demanded))) return rc;
+  // ONE pass for every light: the layers of the cube array are contiguous (layer = 6 * light + face = the view index), so a
+  // triangle's vertices are fetched and transformed to world space once and tested against all 6 * light_count faces
+  J.views = static_cast<const RasterView*>(R->views);
+  J.nViews = (int)(6u * light_count);
+  J.shadowBase = static_cast<float*>(const_cast<void*>(l0.ptr));
+  for (int attempt = 0; light_count; ++attempt) {
+    CUDA_TRY(ctx, cudaMemsetAsync(R->counters, 0, 8 * sizeof(uint32_t), stream));
+    timedLaunch(ctx, "raster_clear", stream, [&] { althea_raster::launch_raster_clear(nullptr, J.shadowBase, J.shadowLayerStride * (6u * light_count - 1u) + facePx, stream); });
+    if ((rc = runRaster(ctx, R, J, stream))) return rc;
+    bool again = false;
+    if ((rc = rasterOverflow(ctx, R, stream, &again))) return rc;
+    if (!again) break;
+    if (attempt >= 2) return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "raster lists overflowed three times");
   }
   return endWork(ctx, sync, stream);
 }

@@ -344,7 +344,7 @@ RDEV void setupTriangleView(const RasterJob& J, const RasterPrim& p, int pi, uin
     return;
   }
   const uint32_t ri = atomicAdd(&J.counters[0], 1u);
-  if (ri >= J.recCap) { J.counters[2] = 1u; atomicMax(&J.counters[3], J.workCap + 1u); return; } // cannot happen: recCap = triangles x views
+  if (ri >= J.recCap) { J.counters[2] = 1u; atomicMax(&J.counters[4], ri + 1u); return; } // sticky demand: the shim redoes the call with a larger list
   RasterRecord r;
 #pragma unroll
   for (int i = 0; i < 3; ++i) { r.A[i] = e.A[i]; r.B[i] = e.B[i]; r.C[i] = e.C[i]; r.Z[i] = g.clip[i].z; }

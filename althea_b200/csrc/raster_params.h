@@ -70,7 +70,7 @@ struct RasterJob {
   uint32_t recCap;
   uint2* work; // (record index, tileX | tileY << 16)
   uint32_t workCap;
-  uint32_t* counters; // [0] records, [1] work items, [2] overflow flag of this pass, [3] sticky: largest work-item demand that overflowed
+  uint32_t* counters; // [0] records, [1] work items, [2] overflow flag of this pass, [3] / [4] sticky: largest work-item / record demand that overflowed
   // G-buffer: visibility buffer, one 64-bit key per pixel = depth bits << 32 | global triangle ordinal (atomicMin)
   unsigned long long* vis;
   // shadow: depth layers of the current light, layer `view` at shadowBase + view * shadowLayerStride floats
