@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1148,10 +1149,15 @@ int buildPrims(althea_cuda_ctx* ctx, RasterScratch* R, const althea_primitive* p
 int runRaster(althea_cuda_ctx* ctx, RasterScratch* R, RasterJob& J, cudaStream_t stream) {
   if (!J.triTotal || !J.nViews) return ALTHEA_OK;
   const unsigned long long pairs = (unsigned long long)J.triTotal * (unsigned)J.nViews;
-  const size_t recWant = (size_t)std::min<unsigned long long>(pairs, 1ull << 21); // 2 M records (256 MB) to start with
+  size_t recStart = (size_t)1 << 21, workStart = (size_t)1 << 22; // 2 M records (256 MB) and 4 M tile items to start with
+  if (const char* e = getenv("ALTHEA_RASTER_INITIAL_LISTS")) { // test hook: tiny lists force the overflow-and-redo path
+    const long v = atol(e);
+    if (v > 0) recStart = workStart = (size_t)v;
+  }
+  const size_t recWant = (size_t)std::min<unsigned long long>(pairs, recStart);
   int rc;
   if (R->recsBytes < recWant * sizeof(RasterRecord) && (rc = growScratch(ctx, &R->recs, &R->recsBytes, recWant * sizeof(RasterRecord), "raster records"))) return rc;
-  if (R->workBytes < ((size_t)1 << 22) * sizeof(uint2) && (rc = growScratch(ctx, &R->work, &R->workBytes, ((size_t)1 << 22) * sizeof(uint2), "raster tile work list"))) return rc;
+  if (R->workBytes < workStart * sizeof(uint2) && (rc = growScratch(ctx, &R->work, &R->workBytes, workStart * sizeof(uint2), "raster tile work list"))) return rc;
   J.recs = static_cast<RasterRecord*>(R->recs);
   J.recCap = (uint32_t)std::min<size_t>(R->recsBytes / sizeof(RasterRecord), 0xffffffffu);
   J.work = static_cast<uint2*>(R->work);

@@ -629,3 +629,37 @@ def test_gpu_work_list_overflow_is_retried(ctx_fast):
     got_first, _ = _gpu_gbuffer(ctx_fast, g, quads[:1], W, H)
     assert (got_first["depth"] < 1).all()
     assert np.array_equal(got_all["depth"].view(np.uint32), got_first["depth"].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_gpu_record_and_work_lists_grow_on_demand(lib_built, oracle, monkeypatch):
+    """The record and tile-work lists start small and grow when a pass overflows them (sticky demand counters, the call is
+    redone). With the lists forced to 8 entries the G-buffer and the shadow cubes must still match the restatement exactly."""
+    import torch
+
+    from althea_b200 import engine
+    monkeypatch.setenv("ALTHEA_RASTER_INITIAL_LISTS", "8")
+    ctx = engine.Context(0)  # a fresh context: its scratch starts at the forced size
+    try:
+        W, H = 160, 90
+        g, proj, view = _camera(W, H, pos=(0.3, 0.8, 3.5), yaw=0.1, pitch=-0.2)
+        prims = _textured_scene()
+        want = oracle.draw_gbuffer(proj, view, prims, W, H)
+        got, _ = _gpu_gbuffer(ctx, g, prims, W, H)
+        _compare_gbuffer(got, want)
+        res = 64
+        room = _shadow_scene()
+        lights = engine.PointLightCollection(ctx, 2, shadow_res=res)
+        pos = [(0.3, 2.0, 0.7), (-2.0, 0.5, 1.0)]
+        for i, p in enumerate(pos):
+            lights.setLight(i, engine.PointLight(p, (10.0, 10.0, 10.0)))
+        lights.drawShadowMaps([model.UploadedModel(ctx, room)])
+        torch.cuda.synchronize()
+        cubes = lights.shadow_map.tensor.view(torch.float32).view(2, 6, res, res).cpu().numpy()
+        pc = model.point_light_constants()
+        lt = np.zeros((2, 8), np.float32)
+        lt[:, :3] = pos
+        want_c = oracle.draw_shadow_cubes(lt, list(pc.projection), np.array([list(pc.views[f]) for f in range(6)], np.float32), room, res)
+        assert np.array_equal(cubes.view(np.uint32), want_c.view(np.uint32))
+    finally:
+        ctx.close()
