@@ -1020,6 +1020,8 @@ struct RasterScratch {
   void* recs = nullptr; size_t recsBytes = 0;
   void* work = nullptr; size_t workBytes = 0;
   void* vis = nullptr; size_t visBytes = 0;
+  void* openBound = nullptr; size_t openBoundBytes = 0; // alpha blending: per-pixel peel bound (4 B/px)
+  void* layerTri = nullptr; size_t layerTriBytes = 0;   // and the translucent layers' triangle ordinals (allocated on first need)
   void* prims = nullptr; size_t primsBytes = 0;
   void* views = nullptr; size_t viewsBytes = 0;
   uint32_t* counters = nullptr;
@@ -1030,7 +1032,7 @@ struct RasterScratch {
 };
 static void freeRasterScratch(RasterScratch* r) {
   if (!r) return;
-  for (void* p : {r->recs, r->work, r->vis, r->prims, r->views, (void*)r->counters, (void*)r->minAlphaDev})
+  for (void* p : {r->recs, r->work, r->vis, r->openBound, r->layerTri, r->prims, r->views, (void*)r->counters, (void*)r->minAlphaDev})
     if (p) cudaFree(p);
   delete r;
 }
@@ -1169,11 +1171,12 @@ int runRaster(althea_cuda_ctx* ctx, RasterScratch* R, RasterJob& J, cudaStream_t
   return ALTHEA_OK;
 }
 // after the last pass of a draw call: grows whichever list overflowed (one host sync); *again = the call must be redone
-int rasterOverflow(althea_cuda_ctx* ctx, RasterScratch* R, cudaStream_t stream, bool* again) {
+int rasterOverflow(althea_cuda_ctx* ctx, RasterScratch* R, cudaStream_t stream, bool* again, uint32_t* openPixels = nullptr) {
   uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CUDA_TRY(ctx, cudaMemcpyAsync(c, R->counters, sizeof c, cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(stream));
   *again = c[3] != 0 || c[4] != 0;
+  if (openPixels) *openPixels = c[5];
   int rc;
   if (c[3] && (rc = growScratch(ctx, &R->work, &R->workBytes, ((size_t)c[3] + (c[3] >> 2) + 1024) * sizeof(uint2), "raster tile work list"))) return rc;
   if (c[4] && (rc = growScratch(ctx, &R->recs, &R->recsBytes, ((size_t)c[4] + (c[4] >> 2) + 1024) * sizeof(RasterRecord), "raster records"))) return rc;
@@ -1226,21 +1229,43 @@ int althea_cuda_draw_gbuffer(althea_cuda_ctx* ctx, const althea_global_uniforms*
   const size_t px = (size_t)J.W * J.H;
   if ((rc = growScratch(ctx, &R->vis, &R->visBytes, px * sizeof(unsigned long long), "visibility buffer"))) return rc;
   J.vis = static_cast<unsigned long long*>(R->vis);
+  if ((rc = growScratch(ctx, &R->openBound, &R->openBoundBytes, px * sizeof(uint32_t), "peel bounds"))) return rc;
+  J.openBound = static_cast<uint32_t*>(R->openBound);
   ImgView v;
   if (depth) { levelView(*depth, 0, 0, &v); J.outDepth = static_cast<float*>(const_cast<void*>(v.ptr)); J.pitchDepth = v.pitch; }
   if (position) { levelView(*position, 0, 0, &v); J.outPosition = static_cast<float4*>(const_cast<void*>(v.ptr)); J.pitchPosition = v.pitch; }
   if (normal) { levelView(*normal, 0, 0, &v); J.outNormal = static_cast<uint2*>(const_cast<void*>(v.ptr)); J.pitchNormal = v.pitch; }
   if (albedo) { levelView(*albedo, 0, 0, &v); J.outAlbedo = static_cast<uint32_t*>(const_cast<void*>(v.ptr)); J.pitchAlbedo = v.pitch; }
   if (mro) { levelView(*mro, 0, 0, &v); J.outMro = static_cast<uint32_t*>(const_cast<void*>(v.ptr)); J.pitchMro = v.pitch; }
+  uint32_t open = 0;
   for (int attempt = 0;; ++attempt) {
     CUDA_TRY(ctx, cudaMemsetAsync(R->counters, 0, 8 * sizeof(uint32_t), stream));
     timedLaunch(ctx, "raster_clear", stream, [&] { althea_raster::launch_raster_clear(J.vis, nullptr, px, stream); });
+    J.bound = nullptr;
     if ((rc = runRaster(ctx, R, J, stream))) return rc;
     timedLaunch(ctx, "gbuffer_resolve", stream, [&] { althea_raster::launch_gbuffer_resolve(J, stream); });
     bool again = false;
-    if ((rc = rasterOverflow(ctx, R, stream, &again))) return rc;
+    if ((rc = rasterOverflow(ctx, R, stream, &again, &open))) return rc;
     if (!again) break;
     if (attempt >= 2) return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "raster lists overflowed three times");
+  }
+  // Translucent depth winners (alpha < 1 after the cutoff): the attachments are alpha-blended in draw order
+  // (Src/GraphicsPipeline.cpp:138-154), so what was drawn under them matters. Peel it, one layer per pass, until every open
+  // pixel reaches an opaque fragment or the clear colour (at most kPeelLayers layers; deeper ones are dropped).
+  constexpr int kPeelLayers = 4;
+  if (open) {
+    if ((rc = growScratch(ctx, &R->layerTri, &R->layerTriBytes, px * sizeof(uint32_t) * kPeelLayers, "translucent layer stack"))) return rc;
+    J.layerTri = static_cast<uint32_t*>(R->layerTri);
+    timedLaunch(ctx, "gbuffer_peel", stream, [&] { althea_raster::launch_gbuffer_peel(J, 0, 0, stream); });
+    for (int pass = 1; pass < kPeelLayers && open; ++pass) {
+      timedLaunch(ctx, "raster_clear", stream, [&] { althea_raster::launch_raster_clear(J.vis, nullptr, px, stream); });
+      J.bound = J.openBound;
+      if ((rc = runRaster(ctx, R, J, stream))) return rc; // same triangles as pass 0: the lists are large enough
+      CUDA_TRY(ctx, cudaMemsetAsync(R->counters + 5, 0, sizeof(uint32_t), stream));
+      timedLaunch(ctx, "gbuffer_peel", stream, [&] { althea_raster::launch_gbuffer_peel(J, pass, pass == kPeelLayers - 1, stream); });
+      bool again = false;
+      if ((rc = rasterOverflow(ctx, R, stream, &again, &open))) return rc;
+    }
   }
   return endWork(ctx, sync, stream);
 }

@@ -12,6 +12,8 @@
 // rasterisation does. The shadow pass min-reduces gl_FragDepth = |view-space position| / 1000 straight into the cube layers.
 // gbuffer_resolve_kernel then shades each pixel once from its winning triangle (perspective-correct attributes, analytic uv
 // derivatives for the mip level), so texture work is never spent on hidden fragments.
+// The reference alpha-blends its colour attachments in draw order; pixels whose winner is translucent are peeled layer by layer
+// (gbuffer_peel_kernel) and composited with the blend equation and the attachment formats' roundings.
 //
 // Coverage rules (the restatement in oracle/althea_oracle_raster.cpp spells out the same operations): pixel centres; top-left
 // tie rule; 0 <= z <= w depth clip; back faces culled (VK_CULL_MODE_BACK_BIT, Include/Althea/GraphicsPipeline.h:171) with the
@@ -268,6 +270,7 @@ RDEV void rasterPixel(const RasterJob& J, const RasterPrim& p, const float A[3],
 #pragma unroll
   for (int i = 0; i < 3; ++i) e[i] = edgeAt(A[i], B[i], C[i], x, y);
   if (!(edgeInside(e[0], A[0], B[0]) && edgeInside(e[1], A[1], B[1]) && edgeInside(e[2], A[2], B[2]))) return;
+  if (J.bound && !(tri + 1u < J.bound[(size_t)py * J.W + px])) return; // peel pass: only what was drawn before the layer found last (bound = its ordinal + 1; 0 = closed pixel)
   const float zn = __fmaf_rn(e[0], Z[0], __fmaf_rn(e[1], Z[1], mulr(e[2], Z[2])));
   const float z = mulr(zn, rdet);
   if (!(z >= 0.0f && z <= 1.0f)) return; // depth clip 0 <= z_c <= w_c
@@ -460,74 +463,158 @@ RDEV uint32_t packUnorm4(float x, float y, float z, float w) { // UNORM8 convers
   return q(x) | (q(y) << 8) | (q(z) << 16) | (q(w) << 24);
 }
 
+// What one fragment's shader invocation outputs (Gltf.frag:44-49), before the blend and the attachment formats
+struct Shaded {
+  float n[3], alpha, albedo[3], metallic, roughness;
+  float4 position;
+};
+// vertex stage, interpolation and fetchMaterial for triangle `tri` at pixel (px, py)
+RDEV Shaded shadeFragment(const RasterJob& J, uint32_t tri, int px, int py) {
+  const RasterPrim& p = J.prims[primOfTriangle(J, tri)];
+  TriGeom g;
+  triTransform(p, tri - p.triOffset, J.views[0], g);
+  TriEdges E;
+  triEdges(g, J.W, J.H, p.frontCW != 0u, E); // it passed the depth test once already: same values
+  const float x = (float)px + 0.5f, y = (float)py + 0.5f;
+  float e[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) e[i] = edgeAt(E.A[i], E.B[i], E.C[i], x, y);
+  const float S = addr(addr(e[0], e[1]), e[2]);
+  const float b0 = e[0] / S, b1 = e[1] / S, b2 = e[2] / S;
+  // Gltf.vert:52-59: world position and mat3(model) * tbn per vertex, interpolated perspective-correctly
+  F3 T = {0.0f, 0.0f, 0.0f}, Bt = T, N = T;
+  const float bw[3] = {b0, b1, b2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const althea_vertex& vtx = p.verts[g.vi[k]];
+    float t3[3], b3[3], n3[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { t3[c] = __ldg(vtx.tangent + c); b3[c] = __ldg(vtx.bitangent + c); n3[c] = __ldg(vtx.normal + c); }
+    const F3 tw = mulM3V(p.model, t3), bwv = mulM3V(p.model, b3), nw = mulM3V(p.model, n3);
+    T.x += bw[k] * tw.x; T.y += bw[k] * tw.y; T.z += bw[k] * tw.z;
+    Bt.x += bw[k] * bwv.x; Bt.y += bw[k] * bwv.y; Bt.z += bw[k] * bwv.z;
+    N.x += bw[k] * nw.x; N.y += bw[k] * nw.y; N.z += bw[k] * nw.z;
+  }
+  Shaded out;
+  out.position = make_float4(b0 * g.world[0].x + b1 * g.world[1].x + b2 * g.world[2].x, b0 * g.world[0].y + b1 * g.world[1].y + b2 * g.world[2].y,
+                             b0 * g.world[0].z + b1 * g.world[1].z + b2 * g.world[2].z, 1.0f);
+  // fetchMaterial, InstanceData.glsl:28-69
+  const RasterMaterial& m = p.mat;
+  F2 uvb[3], uvm[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { uvb[k] = vertexUv(p, g.vi[k], m.baseUv); uvm[k] = vertexUv(p, g.vi[k], m.mrUv); }
+  const UvSample ub = interpUv(e, E.A, E.B, S, uvb), um = interpUv(e, E.A, E.B, S, uvm);
+  F4 one; one.x = one.y = one.z = one.w = 1.0f;
+  F4 flat; flat.x = flat.y = 128.0f / 255.0f; flat.z = 1.0f; flat.w = 1.0f; // Content/Engine/Textures/normal1x1.png
+  F4 base = sampleTexture(m.base, one, ub.uv, ub.ddx, ub.ddy);
+  base.x *= m.baseColorFactor[0]; base.y *= m.baseColorFactor[1]; base.z *= m.baseColorFactor[2]; base.w *= m.baseColorFactor[3];
+  const F4 nm = sampleTexture(m.normal, flat, ub.uv, ub.ddx, ub.ddy);
+  const float tsx = (2.0f * nm.x - 1.0f) * m.normalScale, tsy = (2.0f * nm.y - 1.0f) * m.normalScale, tsz = 2.0f * nm.z - 1.0f;
+  float nx = tsx * T.x + tsy * Bt.x + tsz * N.x, ny = tsx * T.y + tsy * Bt.y + tsz * N.y, nz = tsx * T.z + tsy * Bt.z + tsz * N.z;
+  const float nl = sqrtf(nx * nx + ny * ny + nz * nz);
+  out.n[0] = nx / nl; out.n[1] = ny / nl; out.n[2] = nz / nl;
+  const F4 mr = sampleTexture(m.mr, one, um.uv, um.ddx, um.ddy);
+  out.metallic = mr.z * m.metallicFactor; // .bg (InstanceData.glsl:52-55)
+  out.roughness = mr.y * m.roughnessFactor;
+  out.albedo[0] = base.x; out.albedo[1] = base.y; out.albedo[2] = base.z;
+  out.alpha = base.w;
+  return out;
+}
+
+// The reference blends EVERY colour attachment (SRC_ALPHA, ONE_MINUS_SRC_ALPHA on colour; ONE, ZERO on alpha,
+// Src/GraphicsPipeline.cpp:138-154): a fragment that passes the depth test leaves rgb = src.rgb a + dst.rgb (1 - a), a = src.a,
+// rounded to the attachment's format. One blend step on the three attachments' contents (kept as the floats their formats hold):
+struct Attach { float n[4], a[4], m[4]; };
+RDEV float roundHalf(float v) { return __half2float(__float2half_rn(v)); }
+RDEV float roundUnorm(float v) { return __fdiv_rn((float)__float2int_rn(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f), 255.0f); }
+RDEV void blendOver(Attach& d, const Shaded& s) {
+  const float a = s.alpha, ia = subr(1.0f, a);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    d.n[c] = roundHalf(addr(mulr(s.n[c], a), mulr(d.n[c], ia)));
+    d.a[c] = roundUnorm(addr(mulr(s.albedo[c], a), mulr(d.a[c], ia)));
+  }
+  d.m[0] = roundUnorm(addr(mulr(s.metallic, a), mulr(d.m[0], ia)));
+  d.m[1] = roundUnorm(addr(mulr(s.roughness, a), mulr(d.m[1], ia)));
+  d.m[2] = roundUnorm(mulr(d.m[2], ia)); // desc.ao = 0.0 (InstanceData.glsl:60)
+  d.n[3] = roundHalf(a);
+  d.a[3] = d.m[3] = roundUnorm(a);
+}
+RDEV void writeAttachments(const RasterJob& J, int px, int py, const Attach& d) {
+  if (J.outNormal) {
+    __half2 lo = __floats2half2_rn(d.n[0], d.n[1]), hi = __floats2half2_rn(d.n[2], d.n[3]);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&lo);
+    v.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<char*>(J.outNormal) + (size_t)py * J.pitchNormal + (size_t)px * 8) = v;
+  }
+  if (J.outAlbedo) *reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(J.outAlbedo) + (size_t)py * J.pitchAlbedo + (size_t)px * 4) = packUnorm4(d.a[0], d.a[1], d.a[2], d.a[3]);
+  if (J.outMro) *reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(J.outMro) + (size_t)py * J.pitchMro + (size_t)px * 4) = packUnorm4(d.m[0], d.m[1], d.m[2], d.m[3]);
+}
+
+// Pass 0: every pixel from its depth winner. An opaque winner (alpha == 1, the overwhelmingly common case) erases whatever was
+// drawn below it, so the pixel is final. A translucent winner is written blended over the clear colour for now and the pixel is
+// left OPEN (openBound = its triangle ordinal + 1): what lies under it is peeled in draw order by the passes below.
 __global__ void __launch_bounds__(256) gbuffer_resolve_kernel(const __grid_constant__ RasterJob J) {
   const int px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
   if (px >= J.W || py >= J.H) return;
-  const unsigned long long key = J.vis[(size_t)py * J.W + px];
+  const size_t pix = (size_t)py * J.W + px;
+  const unsigned long long key = J.vis[pix];
   float depth = 1.0f;
   float4 position = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  uint2 normalH = make_uint2(0u, 0u);
-  uint32_t albedo = 0u, mro = 0u;
+  Attach d;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) d.n[c] = d.a[c] = d.m[c] = 0.0f; // the clears (Src/DeferredRendering.cpp:101-104)
+  uint32_t open = 0u;
   if (key != ~0ull) {
     const uint32_t tri = (uint32_t)(key & 0xffffffffu);
     depth = __uint_as_float((uint32_t)(key >> 32));
-    const RasterPrim& p = J.prims[primOfTriangle(J, tri)];
-    TriGeom g;
-    triTransform(p, tri - p.triOffset, J.views[0], g);
-    TriEdges E;
-    triEdges(g, J.W, J.H, p.frontCW != 0u, E); // it won the depth test, so it passed once already: same values
-    const float x = (float)px + 0.5f, y = (float)py + 0.5f;
-    float e[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) e[i] = edgeAt(E.A[i], E.B[i], E.C[i], x, y);
-    const float S = addr(addr(e[0], e[1]), e[2]);
-    const float b0 = e[0] / S, b1 = e[1] / S, b2 = e[2] / S;
-    // Gltf.vert:52-59: world position and mat3(model) * tbn per vertex, interpolated perspective-correctly
-    F3 T = {0.0f, 0.0f, 0.0f}, Bt = T, N = T;
-    const float bw[3] = {b0, b1, b2};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const althea_vertex& vtx = p.verts[g.vi[k]];
-      float t3[3], b3[3], n3[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { t3[c] = __ldg(vtx.tangent + c); b3[c] = __ldg(vtx.bitangent + c); n3[c] = __ldg(vtx.normal + c); }
-      const F3 tw = mulM3V(p.model, t3), bwv = mulM3V(p.model, b3), nw = mulM3V(p.model, n3);
-      T.x += bw[k] * tw.x; T.y += bw[k] * tw.y; T.z += bw[k] * tw.z;
-      Bt.x += bw[k] * bwv.x; Bt.y += bw[k] * bwv.y; Bt.z += bw[k] * bwv.z;
-      N.x += bw[k] * nw.x; N.y += bw[k] * nw.y; N.z += bw[k] * nw.z;
-    }
-    position = make_float4(b0 * g.world[0].x + b1 * g.world[1].x + b2 * g.world[2].x, b0 * g.world[0].y + b1 * g.world[1].y + b2 * g.world[2].y,
-                           b0 * g.world[0].z + b1 * g.world[1].z + b2 * g.world[2].z, 1.0f);
-    // fetchMaterial, InstanceData.glsl:28-69
-    const RasterMaterial& m = p.mat;
-    F2 uvb[3], uvm[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { uvb[k] = vertexUv(p, g.vi[k], m.baseUv); uvm[k] = vertexUv(p, g.vi[k], m.mrUv); }
-    const UvSample ub = interpUv(e, E.A, E.B, S, uvb), um = interpUv(e, E.A, E.B, S, uvm);
-    F4 one; one.x = one.y = one.z = one.w = 1.0f;
-    F4 flat; flat.x = flat.y = 128.0f / 255.0f; flat.z = 1.0f; flat.w = 1.0f; // Content/Engine/Textures/normal1x1.png
-    F4 base = sampleTexture(m.base, one, ub.uv, ub.ddx, ub.ddy);
-    base.x *= m.baseColorFactor[0]; base.y *= m.baseColorFactor[1]; base.z *= m.baseColorFactor[2]; base.w *= m.baseColorFactor[3];
-    const F4 nm = sampleTexture(m.normal, flat, ub.uv, ub.ddx, ub.ddy);
-    const float tsx = (2.0f * nm.x - 1.0f) * m.normalScale, tsy = (2.0f * nm.y - 1.0f) * m.normalScale, tsz = 2.0f * nm.z - 1.0f;
-    float nx = tsx * T.x + tsy * Bt.x + tsz * N.x, ny = tsx * T.y + tsy * Bt.y + tsz * N.y, nz = tsx * T.z + tsy * Bt.z + tsz * N.z;
-    const float nl = sqrtf(nx * nx + ny * ny + nz * nz);
-    nx /= nl; ny /= nl; nz /= nl;
-    const F4 mr = sampleTexture(m.mr, one, um.uv, um.ddx, um.ddy);
-    const float metallic = mr.z * m.metallicFactor, roughness = mr.y * m.roughnessFactor; // .bg (InstanceData.glsl:52-55)
-    const float alpha = base.w;
-    // Gltf.frag:44-49
-    __half2 lo = __floats2half2_rn(nx, ny), hi = __floats2half2_rn(nz, alpha);
-    normalH.x = *reinterpret_cast<uint32_t*>(&lo);
-    normalH.y = *reinterpret_cast<uint32_t*>(&hi);
-    albedo = packUnorm4(base.x, base.y, base.z, base.w);
-    mro = packUnorm4(metallic, roughness, 0.0f, alpha); // desc.ao = 0.0 (InstanceData.glsl:60)
+    const Shaded s = shadeFragment(J, tri, px, py);
+    position = s.position;
+    blendOver(d, s);
+    if (s.alpha != 1.0f) open = tri + 1u; // ordinal + 1: 0 means final
   }
   if (J.outDepth) *reinterpret_cast<float*>(reinterpret_cast<char*>(J.outDepth) + (size_t)py * J.pitchDepth + (size_t)px * 4) = depth;
   if (J.outPosition) *reinterpret_cast<float4*>(reinterpret_cast<char*>(J.outPosition) + (size_t)py * J.pitchPosition + (size_t)px * 16) = position;
-  if (J.outNormal) *reinterpret_cast<uint2*>(reinterpret_cast<char*>(J.outNormal) + (size_t)py * J.pitchNormal + (size_t)px * 8) = normalH;
-  if (J.outAlbedo) *reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(J.outAlbedo) + (size_t)py * J.pitchAlbedo + (size_t)px * 4) = albedo;
-  if (J.outMro) *reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(J.outMro) + (size_t)py * J.pitchMro + (size_t)px * 4) = mro;
+  writeAttachments(J, px, py, d);
+  J.openBound[pix] = open;
+  if (open) atomicAdd(&J.counters[5], 1u);
+}
+
+// Peel pass k >= 1 (only when pass 0 left pixels open). J.vis now holds, for every open pixel, the depth winner among the
+// triangles drawn BEFORE the layer found last (the fill ran with J.bound = openBound): the fragment that was on top when that
+// layer was blended. It is pushed on the pixel's stack; the pixel closes when the new layer is opaque, when nothing lies below
+// (the clear colour), or at the last pass; closing composites the stack bottom-up with blendOver and writes the attachments.
+__global__ void __launch_bounds__(256) gbuffer_peel_kernel(const __grid_constant__ RasterJob J, int pass, int lastPass) {
+  const int px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (px >= J.W || py >= J.H) return;
+  const size_t pix = (size_t)py * J.W + px, npx = (size_t)J.W * J.H;
+  const uint32_t bound = J.openBound[pix];
+  if (!bound && pass > 0) return; // closed
+  // layer stack: layerTri[k * npx + pix] = triangle ordinal of the k-th layer from the top
+  if (pass == 0) { // registers the pass-0 winner of an open pixel as layer 0
+    if (bound) J.layerTri[pix] = bound - 1u;
+    return;
+  }
+  const unsigned long long key = J.vis[pix];
+  bool close = lastPass != 0;
+  int count = pass; // layers 0 .. pass-1 are on the stack
+  if (key == ~0ull) close = true; // nothing was drawn below: the clear colour
+  else {
+    const uint32_t tri = (uint32_t)(key & 0xffffffffu);
+    J.layerTri[(size_t)pass * npx + pix] = tri;
+    count = pass + 1;
+    const Shaded s = shadeFragment(J, tri, px, py);
+    if (s.alpha == 1.0f) close = true;
+    else J.openBound[pix] = tri + 1u;
+  }
+  if (!close) { atomicAdd(&J.counters[5], 1u); return; }
+  Attach d;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) d.n[c] = d.a[c] = d.m[c] = 0.0f;
+  for (int k = count - 1; k >= 0; --k) blendOver(d, shadeFragment(J, J.layerTri[(size_t)k * npx + pix], px, py));
+  writeAttachments(J, px, py, d);
+  J.openBound[pix] = 0u;
 }
 
 // min alpha of a texture's level 0 (cached per image by the shim: a material whose alpha can never fall below its cutoff skips
@@ -550,6 +637,9 @@ void launch_raster_setup(const RasterJob& J, cudaStream_t s) {
 void launch_raster_fill(const RasterJob& J, int sms, cudaStream_t s) { raster_fill_kernel<<<(unsigned)(sms * 8), 256, 0, s>>>(J); }
 void launch_gbuffer_resolve(const RasterJob& J, cudaStream_t s) {
   gbuffer_resolve_kernel<<<dim3((unsigned)((J.W + 15) / 16), (unsigned)((J.H + 15) / 16)), 256, 0, s>>>(J);
+}
+void launch_gbuffer_peel(const RasterJob& J, int pass, int lastPass, cudaStream_t s) {
+  gbuffer_peel_kernel<<<dim3((unsigned)((J.W + 15) / 16), (unsigned)((J.H + 15) / 16)), 256, 0, s>>>(J, pass, lastPass);
 }
 void launch_texture_min_alpha(const uint32_t* texels, size_t n, unsigned int* out, cudaStream_t s) {
   const unsigned blocks = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);

@@ -70,9 +70,15 @@ struct RasterJob {
   uint32_t recCap;
   uint2* work; // (record index, tileX | tileY << 16)
   uint32_t workCap;
-  uint32_t* counters; // [0] records, [1] work items, [2] overflow flag of this pass, [3] / [4] sticky: largest work-item / record demand that overflowed
+  uint32_t* counters; // [0] records, [1] work items, [2] overflow flag of this pass, [3] / [4] sticky: largest work-item / record demand that overflowed, [5] pixels left open by the last resolve / peel pass
   // G-buffer: visibility buffer, one 64-bit key per pixel = depth bits << 32 | global triangle ordinal (atomicMin)
   unsigned long long* vis;
+  // alpha blending of the G-buffer attachments (raster_kernels.cu, gbuffer_peel_kernel): per pixel, 1 + the triangle ordinal below
+  // which the next peel pass looks (0 = the pixel is final); `bound` is that array while a peel pass fills, null in pass 0;
+  // layerTri[k * W * H + pixel] = the k-th translucent layer from the top
+  uint32_t* openBound;
+  const uint32_t* bound;
+  uint32_t* layerTri;
   // shadow: depth layers of the current light, layer `view` at shadowBase + view * shadowLayerStride floats
   float* shadowBase;
   size_t shadowLayerStride;

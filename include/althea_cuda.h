@@ -231,7 +231,9 @@ typedef struct althea_point_light_constants { /* PointLightConstants, Src/PointL
 
 /* SceneToGBufferPass + Gltf.vert/.frag: rasterises the primitives in order (depth LESS, back faces culled, alpha-cutoff
  * discard) into the G-buffer attachments; any of gbuffer's handles may be 0 (not written). position (legacy attachment)
- * receives (world position, 1); uncovered pixels get the reference's clears (colour 0, depth 1). Skinned primitives:
+ * receives (world position, 1); uncovered pixels get the reference's clears (colour 0, depth 1). The colour attachments are
+ * alpha-blended in draw order as the reference's pipelines do (Src/GraphicsPipeline.cpp:138-154; up to four translucent layers
+ * per pixel). Skinned primitives:
  * ALTHEA_ERR_UNSUPPORTED is never raised here because skinning data is not part of althea_primitive; pass skinned
  * geometry pre-transformed. */
 int althea_cuda_draw_gbuffer(althea_cuda_ctx* ctx, const althea_global_uniforms* uniforms, const althea_primitive* primitives,

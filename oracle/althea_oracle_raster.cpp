@@ -12,7 +12,8 @@
 //   * a fragment exists where the pixel centre is inside the triangle (top-left rule), evaluated with edge functions in
 //     2-D homogeneous coordinates (x, y, w) so triangles that cross the eye plane need no geometric clipping;
 //   * depth clip 0 <= z_c <= w_c, back faces culled by the sign of the homogeneous determinant;
-//   * triangles are processed in draw order with a LESS depth test against a 1.0 clear (first fragment wins ties);
+//   * triangles are processed in draw order with a LESS depth test against a 1.0 clear (first fragment wins ties); colour
+//     attachments are alpha-blended as every pipeline of the reference does (Src/GraphicsPipeline.cpp:138-154);
 //   * attributes are interpolated perspective-correctly; texture level of detail comes from analytic uv derivatives,
 //     isotropic (rho = max(|d uv/dx * size|, |d uv/dy * size|)), trilinear.
 // Build: g++ -O2 -fopenmp -ffp-contract=off -fno-fast-math (oracle/Makefile): no a*b+c is ever fused unless std::fmaf says so.
@@ -268,6 +269,7 @@ void oracle_draw_gbuffer(const float* projection, const float* view, const Oracl
   const size_t n = (size_t)W * H;
   std::vector<float> zbuf(n, 1.0f);
   std::vector<uint32_t> ids(n, 0xffffffffu);
+  std::vector<std::vector<uint32_t>> chain(n); // per pixel: the triangles whose fragment passed the depth test, in draw order
   std::vector<uint32_t> offsets(nPrims + 1, 0u);
   for (int i = 0; i < nPrims; ++i) offsets[i + 1] = offsets[i] + prims[i].triCount;
   // in draw order; rows in parallel inside a triangle would be pointless for small triangles, so: serial triangles, LESS test
@@ -298,37 +300,45 @@ void oracle_draw_gbuffer(const float* projection, const float* view, const Oracl
           if (!(f.z < zbuf[o])) continue; // VK_COMPARE_OP_LESS
           zbuf[o] = f.z;
           ids[o] = offsets[pi] + t;
+          chain[o].push_back(offsets[pi] + t);
         }
     }
   }
-  // shade the surviving fragment of every pixel (what the last passing fragment shader invocation wrote)
+  // Colour attachments are BLENDED, always: every pipeline of the reference enables blending with SRC_ALPHA / ONE_MINUS_SRC_ALPHA
+  // on colour and ONE / ZERO on alpha (Src/GraphicsPipeline.cpp:138-154), so each fragment that passes the depth test leaves
+  //   rgb = src.rgb * a + dst.rgb * (1 - a),  a = src.a   in the attachment's format (RGBA16F normal, UNORM8 albedo / MRO).
+  // The fragments that pass at a pixel are `chain[pixel]`, in draw order with strictly decreasing depth; an opaque one (a == 1)
+  // erases what was below it, so only the tail of the chain from the last opaque fragment on needs shading.
 #pragma omp parallel for schedule(dynamic, 4)
   for (int py = 0; py < H; ++py)
     for (int px = 0; px < W; ++px) {
       const size_t o = (size_t)py * W + px;
-      float outN[4] = {0, 0, 0, 0}, outP[4] = {0, 0, 0, 0};
+      float outN[4] = {0, 0, 0, 0}, outP[4] = {0, 0, 0, 0}; // the clears (Src/DeferredRendering.cpp:101-104)
       uint8_t outA[4] = {0, 0, 0, 0}, outM[4] = {0, 0, 0, 0};
-      if (ids[o] != 0xffffffffu) {
+      const std::vector<uint32_t>& ch = chain[o];
+      struct Layer { float n[4], a[4], m[4], pos[3]; };
+      std::vector<Layer> layers; // top first
+      for (size_t k = ch.size(); k-- > 0;) {
         int pi = 0;
-        while (offsets[pi + 1] <= ids[o]) ++pi;
+        while (offsets[pi + 1] <= ch[k]) ++pi;
         const OraclePrim& p = prims[pi];
-        const Tri g = setupTriangle(p, ids[o] - offsets[pi], pv, nullptr, nullptr, W, H);
+        const Tri g = setupTriangle(p, ch[k] - offsets[pi], pv, nullptr, nullptr, W, H);
         Frag f;
         fragment(g, px, py, f);
         const float b[3] = {f.e[0] / f.S, f.e[1] / f.S, f.e[2] / f.S};
         float T[3] = {0, 0, 0}, Bt[3] = {0, 0, 0}, N[3] = {0, 0, 0};
-        for (int k = 0; k < 3; ++k) { // Gltf.vert:59: vertTbn = mat3(model) * tbn
-          const float* v = p.verts + (size_t)g.vi[k] * kVertexFloats;
+        for (int q = 0; q < 3; ++q) { // Gltf.vert:59: vertTbn = mat3(model) * tbn
+          const float* v = p.verts + (size_t)g.vi[q] * kVertexFloats;
           float tw[3], bw[3], nw[3];
           mulM3V(p.model, v + 3, tw);
           mulM3V(p.model, v + 6, bw);
           mulM3V(p.model, v + 9, nw);
-          for (int c = 0; c < 3; ++c) { T[c] += b[k] * tw[c]; Bt[c] += b[k] * bw[c]; N[c] += b[k] * nw[c]; }
+          for (int c = 0; c < 3; ++c) { T[c] += b[q] * tw[c]; Bt[c] += b[q] * bw[c]; N[c] += b[q] * nw[c]; }
         }
-        outP[0] = b[0] * g.world[0].x + b[1] * g.world[1].x + b[2] * g.world[2].x;
-        outP[1] = b[0] * g.world[0].y + b[1] * g.world[1].y + b[2] * g.world[2].y;
-        outP[2] = b[0] * g.world[0].z + b[1] * g.world[1].z + b[2] * g.world[2].z;
-        outP[3] = 1.0f;
+        Layer L;
+        L.pos[0] = b[0] * g.world[0].x + b[1] * g.world[1].x + b[2] * g.world[2].x;
+        L.pos[1] = b[0] * g.world[0].y + b[1] * g.world[1].y + b[2] * g.world[2].y;
+        L.pos[2] = b[0] * g.world[0].z + b[1] * g.world[1].z + b[2] * g.world[2].z;
         const UvSample ub = interpUv(g, f, p, p.baseUv), um = interpUv(g, f, p, p.mrUv);
         V4 base = sampleTexture(p.base, V4{1, 1, 1, 1}, ub.uv, ub.ddx, ub.ddy);
         base.x *= p.baseColorFactor[0]; base.y *= p.baseColorFactor[1]; base.z *= p.baseColorFactor[2]; base.w *= p.baseColorFactor[3];
@@ -339,9 +349,32 @@ void oracle_draw_gbuffer(const float* projection, const float* view, const Oracl
         const float nl = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
         const V4 mr = sampleTexture(p.mr, V4{1, 1, 1, 1}, um.uv, um.ddx, um.ddy);
         const float metallic = mr.z * p.metallicFactor, roughness = mr.y * p.roughnessFactor; // .bg
-        outN[0] = nn[0] / nl; outN[1] = nn[1] / nl; outN[2] = nn[2] / nl; outN[3] = base.w;
-        outA[0] = unorm8(base.x); outA[1] = unorm8(base.y); outA[2] = unorm8(base.z); outA[3] = unorm8(base.w);
-        outM[0] = unorm8(metallic); outM[1] = unorm8(roughness); outM[2] = unorm8(0.0f); outM[3] = unorm8(base.w);
+        // Gltf.frag:44-49: the three colour outputs of this fragment
+        L.n[0] = nn[0] / nl; L.n[1] = nn[1] / nl; L.n[2] = nn[2] / nl; L.n[3] = base.w;
+        L.a[0] = base.x; L.a[1] = base.y; L.a[2] = base.z; L.a[3] = base.w;
+        L.m[0] = metallic; L.m[1] = roughness; L.m[2] = 0.0f; L.m[3] = base.w; // desc.ao = 0.0 (InstanceData.glsl:60)
+        layers.push_back(L);
+        if (base.w == 1.0f) break; // opaque: nothing below it survives the blend
+      }
+      if (!layers.empty()) {
+        float dN[4] = {0, 0, 0, 0}, dA[4] = {0, 0, 0, 0}, dM[4] = {0, 0, 0, 0}; // attachment contents, as read back from their formats
+        for (size_t k = layers.size(); k-- > 0;) { // bottom-up, each step stored in the attachment's format
+          const Layer& L = layers[k];
+          const float a = L.n[3], ia = 1.0f - a;
+          for (int c = 0; c < 3; ++c) {
+            dN[c] = (float)(_Float16)(L.n[c] * a + dN[c] * ia);
+            dA[c] = (float)unorm8(L.a[c] * a + dA[c] * ia) / 255.0f;
+            dM[c] = (float)unorm8(L.m[c] * a + dM[c] * ia) / 255.0f;
+          }
+          dN[3] = (float)(_Float16)a;
+          dA[3] = dM[3] = (float)unorm8(a) / 255.0f;
+        }
+        for (int c = 0; c < 4; ++c) {
+          outN[c] = dN[c];
+          outA[c] = unorm8(dA[c]);
+          outM[c] = unorm8(dM[c]);
+        }
+        outP[0] = layers[0].pos[0]; outP[1] = layers[0].pos[1]; outP[2] = layers[0].pos[2]; outP[3] = 1.0f; // our extension: the nearest fragment
       }
       if (depth) depth[o] = zbuf[o];
       if (triId) triId[o] = ids[o];
