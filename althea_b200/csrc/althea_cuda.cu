@@ -1321,6 +1321,25 @@ int althea_cuda_draw_shadow_cubes(althea_cuda_ctx* ctx, uint64_t lights_buf, uin
   if ((rc = growScratch(ctx, &R->views, &R->viewsBytes, views.size() * sizeof(RasterView), "raster views"))) return rc;
   CUDA_TRY(ctx, cudaMemcpyAsync(R->views, views.data(), views.size() * sizeof(RasterView), cudaMemcpyHostToDevice, stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+  { // which face looks along which axis: a view matrix maps world to view space and the camera looks down -z of view space, so its
+    // forward direction in world space is minus the third row of the rotation, -(a[2], a[6], a[10])
+    bool ok = true;
+    int seen = 0;
+    for (int f = 0; f < 6 && ok; ++f) {
+      const float* a = constants->views[f];
+      const float fwd[3] = {-a[2], -a[6], -a[10]};
+      int axis = -1;
+      for (int j = 0; j < 3; ++j)
+        if (fabsf(fwd[j]) > 0.9999f) axis = 2 * j + (fwd[j] < 0.0f ? 1 : 0);
+      // a plain rigid camera at the origin with the reference's 90 degree, aspect 1 projection: otherwise no shortcut
+      ok = axis >= 0 && !(seen & (1 << axis)) && a[12] == 0.0f && a[13] == 0.0f && a[14] == 0.0f && a[3] == 0.0f && a[7] == 0.0f && a[11] == 0.0f && a[15] == 1.0f;
+      if (ok) { J.faceOfAxis[axis] = f; seen |= 1 << axis; }
+    }
+    const float* pr = constants->projection;
+    ok = ok && seen == 63 && fabsf(fabsf(pr[0]) - 1.0f) < 1e-5f && fabsf(fabsf(pr[5]) - 1.0f) < 1e-5f && pr[11] == -1.0f && pr[15] == 0.0f &&
+         pr[1] == 0.0f && pr[2] == 0.0f && pr[3] == 0.0f && pr[4] == 0.0f && pr[6] == 0.0f && pr[7] == 0.0f && pr[8] == 0.0f && pr[9] == 0.0f && pr[12] == 0.0f && pr[13] == 0.0f;
+    J.cubeFaces = ok ? 1 : 0;
+  }
   // ONE pass for every light: the layers of the cube array are contiguous (layer = 6 * light + face = the view index), so a
   // triangle's vertices are fetched and transformed to world space once and tested against all 6 * light_count faces
   J.views = static_cast<const RasterView*>(R->views);

@@ -397,6 +397,42 @@ __global__ void __launch_bounds__(256) raster_setup_kernel(const __grid_constant
   const RasterPrim& p = J.prims[pi];
   TriGeom g;
   triWorld(p, tri - p.triOffset, g);
+  if (J.cubeFaces) {
+    // Shadow cubes: views come six per light (view = 6 light + face) and the faces' frusta are the six 90-degree pyramids around
+    // the light's axes (J.faceOfAxis: which face looks along +X, -X, +Y, -Y, +Z, -Z; the shim only sets cubeFaces when the face
+    // cameras ARE axis-aligned). A triangle whose three vertices lie strictly inside ONE pyramid, by a margin far above the float
+    // noise of the face matrices, lies inside it entirely (the pyramid is convex) and outside the other five: only that face is
+    // set up. Everything else (triangles across pyramid boundaries, or next to the light) takes the six conservative tests.
+    for (int light = 0; light < J.nViews / 6; ++light) {
+      const RasterView& v0 = J.views[6 * light];
+      int only = -1;
+      {
+        int axis = -2;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float dx = g.world[k].x - v0.off[0], dy = g.world[k].y - v0.off[1], dz = g.world[k].z - v0.off[2];
+          const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+          int a;
+          float major, m1, m2;
+          if (ax >= ay && ax >= az) { a = dx >= 0.0f ? 0 : 1; major = ax; m1 = ay; m2 = az; }
+          else if (ay >= az) { a = dy >= 0.0f ? 2 : 3; major = ay; m1 = ax; m2 = az; }
+          else { a = dz >= 0.0f ? 4 : 5; major = az; m1 = ax; m2 = ay; }
+          const bool strict = fmaxf(m1, m2) <= major * 0.998f && major > 1e-6f && g.world[k].w == 1.0f;
+          if (!strict) a = -1;
+          axis = (axis == -2) ? a : (axis == a ? axis : -1);
+        }
+        if (axis >= 0) only = J.faceOfAxis[axis];
+      }
+      for (int f = 0; f < 6; ++f) {
+        if (only >= 0 && f != only) continue;
+        const RasterView& v = J.views[6 * light + f];
+        if (faceCannotSee(v, g)) continue;
+        triClip(v, g);
+        setupTriangleView(J, p, pi, tri, (uint32_t)(6 * light + f), g);
+      }
+    }
+    return;
+  }
   for (int view = 0; view < J.nViews; ++view) {
     const RasterView& v = J.views[view];
     if (J.nViews > 1 && faceCannotSee(v, g)) continue;

@@ -64,6 +64,8 @@ struct RasterJob {
   int nViews;
   int W, H;
   int mode;
+  int cubeFaces;     // shadow pass with axis-aligned face cameras: views are six per light and faceOfAxis is valid
+  int faceOfAxis[6]; // face index (0..5) whose camera looks along +X, -X, +Y, -Y, +Z, -Z
   int tile; // pixels per side of a fill work item: 64 for frame-sized targets, 32 for shadow faces (a 256^2 face would otherwise
             // be 16 work items, each a 128-iteration warp: too few warps, too long a tail)
   RasterRecord* recs;
