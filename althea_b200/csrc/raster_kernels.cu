@@ -591,7 +591,7 @@ RDEV void writeAttachments(const RasterJob& J, int px, int py, const Attach& d) 
 // Pass 0: every pixel from its depth winner. An opaque winner (alpha == 1, the overwhelmingly common case) erases whatever was
 // drawn below it, so the pixel is final. A translucent winner is written blended over the clear colour for now and the pixel is
 // left OPEN (openBound = its triangle ordinal + 1): what lies under it is peeled in draw order by the passes below.
-__global__ void __launch_bounds__(256) gbuffer_resolve_kernel(const __grid_constant__ RasterJob J) {
+__global__ void __launch_bounds__(256, 4) gbuffer_resolve_kernel(const __grid_constant__ RasterJob J) { // 64 registers: four CTAs per SM, as before the blend
   const int px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
   if (px >= J.W || py >= J.H) return;
   const size_t pix = (size_t)py * J.W + px;
