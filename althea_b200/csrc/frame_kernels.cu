@@ -599,14 +599,6 @@ ADEV QuadRecord loadQuad(const void* p) { // one 256-bit load: LDG.E.ENL2.256 on
   return r;
 }
 
-ADEV QuadRecord loadQuadNow(const void* p) { // same load, not movable by the compiler: issued where it is written
-  QuadRecord r;
-  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
-               : "l"(p));
-  return r;
-}
-
 struct ProxyTap {
   V3 pos;       // interpolated position, within E per component of the real-arithmetic bilinear value
   float twoTol; // the record's T
@@ -650,9 +642,6 @@ __device__ __noinline__ bool facesRay(const FrameParams& P, float cu, float cv, 
   return dot3(currentNormal, rayDir) < 0.0f;
 }
 
-#ifndef ALTHEA_SSAO_PREFETCH
-#define ALTHEA_SSAO_PREFETCH 0
-#endif
 #ifndef ALTHEA_SSAO_UNROLL
 #define ALTHEA_SSAO_UNROLL 2
 #endif
@@ -690,34 +679,12 @@ template <bool COUNT> ADEV int ssaoCountFiltered(const FrameParams& P, int px, i
     // sign-decided form
     V3 prevPos = worldPos;
     float prevProjection = 0.0f, prevTwoTol = 0.0f, prevDecided = 0.0f;
-#if ALTHEA_SSAO_PREFETCH
-    // software pipeline: the record of tap i + 1 is requested before tap i is evaluated, so every thread keeps two gathers
-    // in flight (the taps of a ray are known up front; only a hit, which ends the ray, wastes the extra request)
-    float cu = marchCoord(u0, uvEnd.x, 1), cv = marchCoord(v0, uvEnd.y, 1);
-    ProxyAddr pa = proxyAddr(P, cu, cv);
-    QuadRecord rec;
-    if (n > 1) rec = loadQuadNow(pa.rec);
-#pragma unroll 1
-    for (int i = 1; i < n; ++i) {
-      float nu = cu, nv = cv;
-      ProxyAddr pn = pa;
-      QuadRecord recN = rec;
-      if (i + 1 < n) {
-        nu = marchCoord(u0, uvEnd.x, i + 1);
-        nv = marchCoord(v0, uvEnd.y, i + 1);
-        pn = proxyAddr(P, nu, nv);
-        recN = loadQuadNow(pn.rec);
-      }
-      const ProxyTap tap = proxyEval(rec, pa.fx, pa.fy);
-      if (COUNT) gathers += 1u;
-#else
 #pragma unroll kSsaoUnroll
     for (int i = 1; i < n; ++i) {
       const float cu = marchCoord(u0, uvEnd.x, i), cv = marchCoord(v0, uvEnd.y, i);
       const ProxyAddr pa = proxyAddr(P, cu, cv);
       const ProxyTap tap = proxyEval(loadQuad(pa.rec), pa.fx, pa.fy);
       if (COUNT) gathers += 1u;
-#endif
       V3 curPos = tap.pos;
       float curProjection = fmaf(curPos.z, perpRef.z, fmaf(curPos.y, perpRef.y, fmaf(curPos.x, perpRef.x, -projBias)));
       float curTwoTol = tap.twoTol + posSlop2; // inf / NaN when the record is flagged
@@ -778,9 +745,6 @@ template <bool COUNT> ADEV int ssaoCountFiltered(const FrameParams& P, int px, i
         }
       }
       prevPos = curPos; prevProjection = curProjection; prevTwoTol = curTwoTol; prevDecided = curDecided;
-#if ALTHEA_SSAO_PREFETCH
-      cu = nu; cv = nv; pa = pn; rec = recN;
-#endif
     }
   }
   return ao;
