@@ -263,7 +263,7 @@ RDEV int primOfTriangle(const RasterJob& J, uint32_t tri) { // binary search ove
 
 // One pixel of one (triangle, view): coverage, depth clip, optional alpha discard, depth resolve. Shared by the warp-per-tile
 // fill and by the setup thread that rasterises small triangles itself.
-RDEV void rasterPixel(const RasterJob& J, const RasterPrim& p, const float A[3], const float B[3], const float C[3], const float Z[3], float rdet,
+RDEV void rasterPixel(const RasterJob& J, const RasterPrim& p, const float A[3], const float B[3], const float C[3], const float Z[3], const float Wc[3],
                       const float* attr, uint32_t tri, uint32_t view, bool alphaTest, const uint32_t vi[3], int px, int py) {
   const float x = (float)px + 0.5f, y = (float)py + 0.5f;
   float e[3];
@@ -272,7 +272,10 @@ RDEV void rasterPixel(const RasterJob& J, const RasterPrim& p, const float A[3],
   if (!(edgeInside(e[0], A[0], B[0]) && edgeInside(e[1], A[1], B[1]) && edgeInside(e[2], A[2], B[2]))) return;
   if (J.bound && !(tri + 1u < J.bound[(size_t)py * J.W + px])) return; // peel pass: only what was drawn before the layer found last (bound = its ordinal + 1; 0 = closed pixel)
   const float zn = __fmaf_rn(e[0], Z[0], __fmaf_rn(e[1], Z[1], mulr(e[2], Z[2])));
-  const float z = mulr(zn, rdet);
+  // normalised by the SAME edge values (sum e_i W_i = |det| in exact arithmetic): their rounding errors, which grow as the
+  // triangle shrinks, then cancel between numerator and denominator instead of landing on the depth
+  const float wn = __fmaf_rn(e[0], Wc[0], __fmaf_rn(e[1], Wc[1], mulr(e[2], Wc[2])));
+  const float z = __fdiv_rn(zn, wn);
   if (!(z >= 0.0f && z <= 1.0f)) return; // depth clip 0 <= z_c <= w_c
   const float S = addr(addr(e[0], e[1]), e[2]);
   if (!(S > 0.0f)) return;
@@ -338,19 +341,19 @@ RDEV void setupTriangleView(const RasterJob& J, const RasterPrim& p, int pi, uin
   if ((x1 - x0 + 1) * (y1 - y0 + 1) <= kSmallBoxPixels) {
     // small triangles (most of a dense mesh, nearly all of it in a 256^2 shadow face) are rasterised right here: no record,
     // no work item, no warp spent on a handful of pixels. Same per-pixel code, and the depth resolve is order-independent.
-    float Z[3], attr[9];
+    float Z[3], Wc[3], attr[9];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { Z[k] = g.clip[k].z; attr[3 * k] = g.cs[k].x; attr[3 * k + 1] = g.cs[k].y; attr[3 * k + 2] = g.cs[k].z; }
+    for (int k = 0; k < 3; ++k) { Z[k] = g.clip[k].z; Wc[k] = g.clip[k].w; attr[3 * k] = g.cs[k].x; attr[3 * k + 1] = g.cs[k].y; attr[3 * k + 2] = g.cs[k].z; }
     const bool alphaTest = !p.opaque;
     for (int py = y0; py <= y1; ++py)
-      for (int px = x0; px <= x1; ++px) rasterPixel(J, p, e.A, e.B, e.C, Z, e.rdet, attr, tri, view, alphaTest, g.vi, px, py);
+      for (int px = x0; px <= x1; ++px) rasterPixel(J, p, e.A, e.B, e.C, Z, Wc, attr, tri, view, alphaTest, g.vi, px, py);
     return;
   }
   const uint32_t ri = atomicAdd(&J.counters[0], 1u);
   if (ri >= J.recCap) { J.counters[2] = 1u; atomicMax(&J.counters[4], ri + 1u); return; } // sticky demand: the shim redoes the call with a larger list
   RasterRecord r;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { r.A[i] = e.A[i]; r.B[i] = e.B[i]; r.C[i] = e.C[i]; r.Z[i] = g.clip[i].z; }
+  for (int i = 0; i < 3; ++i) { r.A[i] = e.A[i]; r.B[i] = e.B[i]; r.C[i] = e.C[i]; r.Z[i] = g.clip[i].z; r.Wc[i] = g.clip[i].w; }
   r.rdet = e.rdet;
   r.tri = tri;
   r.view = view;
@@ -358,7 +361,6 @@ RDEV void setupTriangleView(const RasterJob& J, const RasterPrim& p, int pi, uin
   r.bbox[0] = (uint16_t)x0; r.bbox[1] = (uint16_t)y0; r.bbox[2] = (uint16_t)x1; r.bbox[3] = (uint16_t)y1;
 #pragma unroll
   for (int k = 0; k < 3; ++k) { r.attr[3 * k] = g.cs[k].x; r.attr[3 * k + 1] = g.cs[k].y; r.attr[3 * k + 2] = g.cs[k].z; }
-  r.pad[0] = r.pad[1] = r.pad[2] = 0u;
   J.recs[ri] = r;
   const int tx0 = x0 / J.tile, tx1 = x1 / J.tile, ty0 = y0 / J.tile, ty1 = y1 / J.tile;
   const uint32_t n = (uint32_t)((tx1 - tx0 + 1) * (ty1 - ty0 + 1));
@@ -451,10 +453,9 @@ __global__ void __launch_bounds__(256) raster_fill_kernel(const __grid_constant_
     const uint2 item = J.work[wi];
     const RasterRecord& rr = J.recs[item.x];
     // the record, once per warp (two 64-byte halves, broadcast loads)
-    float A[3], B[3], C[3], Z[3];
+    float A[3], B[3], C[3], Z[3], Wc[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { A[i] = rr.A[i]; B[i] = rr.B[i]; C[i] = rr.C[i]; Z[i] = rr.Z[i]; }
-    const float rdet = rr.rdet;
+    for (int i = 0; i < 3; ++i) { A[i] = rr.A[i]; B[i] = rr.B[i]; C[i] = rr.C[i]; Z[i] = rr.Z[i]; Wc[i] = rr.Wc[i]; }
     const uint32_t tri = rr.tri, view = rr.view;
     const int tx = (int)(item.y & 0xffffu) * J.tile, ty = (int)(item.y >> 16) * J.tile;
     const int x0 = max((int)rr.bbox[0], tx), y0 = max((int)rr.bbox[1], ty);
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(256) raster_fill_kernel(const __grid_constant_
     for (int b = 0; b < bw * bh; ++b) {
       const int px = x0 + (b % bw) * 8 + (int)(lane & 7u), py = y0 + (b / bw) * 4 + (int)(lane >> 3);
       if (px > x1 || py > y1) continue;
-      rasterPixel(J, p, A, B, C, Z, rdet, rr.attr, tri, view, alphaTest, vi, px, py);
+      rasterPixel(J, p, A, B, C, Z, Wc, rr.attr, tri, view, alphaTest, vi, px, py);
     }
   }
 }

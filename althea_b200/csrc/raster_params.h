@@ -42,14 +42,14 @@ struct RasterView { // clip = hasB ? b * (a * (world - (off, 0))) : a * world
 // one surviving (triangle, view): edge functions in pixel units, pre-multiplied by sign(det) so that inside <=> e_i >= 0
 struct __align__(16) RasterRecord {
   float A[3], B[3], C[3]; // e_i(x, y) = A_i x + B_i y + C_i at pixel centres (x, y) = (px + 0.5, py + 0.5)
-  float Z[3];             // clip-space z of the three vertices: z_ndc = (e0 Z0 + e1 Z1 + e2 Z2) * rdet
+  float Z[3];             // clip-space z of the three vertices: z_ndc = (e0 Z0 + e1 Z1 + e2 Z2) / (e0 W0 + e1 W1 + e2 W2)
   float rdet;             // 1 / |det|
   uint32_t tri;           // global triangle ordinal (draw order)
   uint32_t view;
   uint32_t prim;
   uint16_t bbox[4]; // x0, y0, x1, y1 inclusive
   float attr[9];    // shadow pass: view-space positions of the three vertices (ShadowMapBindless.vert:45-49)
-  uint32_t pad[3];
+  float Wc[3];      // clip-space w of the three vertices
 };
 static_assert(sizeof(RasterRecord) == 128, "RasterRecord is two 64-byte halves");
 

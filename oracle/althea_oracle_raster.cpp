@@ -222,7 +222,9 @@ bool fragment(const Tri& g, int px, int py, Frag& f) {
   for (int i = 0; i < 3; ++i) f.e[i] = std::fmaf(g.A[i], x, std::fmaf(g.B[i], y, g.C[i]));
   if (!(edgeInside(f.e[0], g.A[0], g.B[0]) && edgeInside(f.e[1], g.A[1], g.B[1]) && edgeInside(f.e[2], g.A[2], g.B[2]))) return false;
   const float zn = std::fmaf(f.e[0], g.clip[0].z, std::fmaf(f.e[1], g.clip[1].z, f.e[2] * g.clip[2].z));
-  f.z = zn * g.rdet;
+  // normalised by the same edge values (sum e_i w_i = |det| in exact arithmetic), so that their rounding errors cancel
+  const float wn = std::fmaf(f.e[0], g.clip[0].w, std::fmaf(f.e[1], g.clip[1].w, f.e[2] * g.clip[2].w));
+  f.z = zn / wn;
   if (!(f.z >= 0.0f && f.z <= 1.0f)) return false;
   f.S = (f.e[0] + f.e[1]) + f.e[2];
   return f.S > 0.0f;
