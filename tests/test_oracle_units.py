@@ -117,3 +117,148 @@ def test_depth_reconstruction_roundtrip(oracle):
         p = oracle.reconstruct_position(og, u, v, ndc[2])
         # fp32 depth near 1.0 has ~6e-8 resolution, which is ~0.03 units at 60 units distance with near=0.01
         np.testing.assert_allclose(p, world[:3], atol=2e-3 * abs(eye[2]) + 1e-3)
+
+
+def test_deferred_pixels_against_an_independent_float64_evaluation(oracle):
+    """Known-answer pin for the shading stage: with constant-colour IBL maps and a constant BRDF LUT every
+    texture lookup has a closed-form value, so each pixel's colour follows from the published equations alone
+    (Shaders/DeferredPass.vert:10-22, DeferredPass.frag:41-93, PBR/PBRMaterial.glsl:41-162). Evaluated here in float64
+    straight from those equations and compared with the oracle's fp32 result."""
+    W, H = 12, 10
+    rs = np.random.default_rng(7)
+    n_lights = 3
+    g = scene.make_uniforms(W, H, pos=(0.5, 1.0, 4.0), yaw=0.3, pitch=-0.15, light_count=n_lights)
+    og = oracle.GlobalUniforms.from_buffer_copy(bytes(g))
+    invP = np.array(list(g.inverseProjection), np.float64).reshape(4, 4).T
+    invV = np.array(list(g.inverseView), np.float64).reshape(4, 4).T
+
+    env_c, pre_c, irr_c = np.array([0.3, 0.5, 0.7]), np.array([0.9, 0.4, 0.2]), np.array([0.25, 0.35, 0.15])
+    const = lambda c, h, w: np.broadcast_to(np.append(c, 1.0).astype(np.float32), (h, w, 4)).copy()
+    env, irr = const(env_c, 8, 16), const(irr_c, 4, 8)
+    pre_w, pre_h = 16, 8
+    pre = np.broadcast_to(np.append(pre_c, 1.0).astype(np.float32), (oracle.chain_texels(pre_w, pre_h, 5), 4)).copy().ravel()
+    lut = np.zeros((4, 4, 4), np.uint8)
+    lut[..., 0], lut[..., 1] = 153, 51                      # envBRDF = (0.6, 0.2) everywhere
+    lights = np.zeros((n_lights, 8), np.float32)
+    lights[:, 0:3] = rs.uniform(-3, 3, (n_lights, 3))
+    lights[:, 4:7] = rs.uniform(2, 20, (n_lights, 3))
+
+    position = np.zeros((H, W, 4), np.float32)
+    position[..., :3] = rs.uniform(-2, 2, (H, W, 3))
+    position[..., 3] = 1.0
+    position[0, 0, 3] = position[H - 1, W - 1, 3] = 0.0     # two empty pixels: the sky branch
+    nrm = rs.normal(size=(H, W, 3))
+    nrm *= rs.uniform(0.5, 2.0, (H, W, 1)) / np.linalg.norm(nrm, axis=-1, keepdims=True)  # the shader normalises
+    normal16 = np.zeros((H, W, 4), np.float16)
+    normal16[..., :3] = nrm
+    albedo = rs.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    mro = rs.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    ao = rs.integers(0, 25, (H, W), dtype=np.uint8)
+    depth = np.full((H, W), 0.5, np.float32)
+    chain = np.zeros(oracle.chain_texels(W, H, 5) * 4, np.uint16)  # reflection alpha 0 => prefiltered map is used
+
+    # shadow cubes with one value per light: light 1 stores distance 0 (everything behind it is shadowed), the others
+    # store 1.0 = 1000 units (nothing is)
+    cubes = np.ones((n_lights * 6, 4, 4), np.float32)
+    cubes[6:12] = 0.0
+    fr = oracle.Frame(og, W, H, position, depth, normal16.view(np.uint16), albedo, mro, env, pre, (pre_w, pre_h), 5, irr,
+                      lut, lights, cubes, 4)
+    got = oracle.deferred_shade(fr, chain, 5, oracle.SKIP_TONEMAP, ao)
+
+    def fresnel(c, F0, rough):
+        return F0 + (np.maximum(1.0 - rough, F0) - F0) * (1.0 - c) ** 5
+
+    def g1(c, k):
+        return c / (c * (1.0 - k) + k)
+
+    worst = 0.0
+    for y in range(H):
+        for x in range(W):
+            u, v = (x + 0.5) / W, (y + 0.5) / H
+            if position[y, x, 3] == 0.0:
+                want = env_c
+            else:
+                d = invV[:3, :3] @ (invP @ np.array([2 * u - 1, 2 * v - 1, 0.0, 1.0]))[:3]
+                V = d / np.linalg.norm(d)
+                N = normal16[y, x, :3].astype(np.float64)
+                N /= np.linalg.norm(N)
+                base = albedo[y, x, :3] / 255.0
+                metallic, rough = mro[y, x, 0] / 255.0, mro[y, x, 1] / 255.0
+                occl = 1.0 - ao[y, x] / 24.0
+                NdotV = max(N @ -V, 0.0)
+                F0 = 0.04 * (1 - metallic) + base * metallic
+                a = rough * rough
+                a2 = a * a
+                k = (a + 1.0) ** 2 / 8.0
+                F = fresnel(NdotV, F0, rough)
+                want = (irr_c * (1 - F) * base * (1 - metallic) + pre_c * (F * 0.6 + 0.2)) * occl
+                P = position[y, x, :3].astype(np.float64)
+                for i, li in enumerate(lights.astype(np.float64)):
+                    L = li[0:3] - P
+                    d2 = L @ L
+                    if i == 1 and 0.0 < np.sqrt(d2) - 0.5:
+                        continue
+                    L = L / np.sqrt(d2)
+                    Hh = (V + L) / np.linalg.norm(V + L)    # as published: V points from the eye to the surface
+                    NdotL, NdotH = max(N @ L, 0.0), max(N @ Hh, 0.0)
+                    Fl = fresnel(NdotH, F0, rough)
+                    diff = (1 - Fl) * base * (1 - metallic) / np.pi
+                    t = NdotH * NdotH * (a2 - 1.0) + 1.0
+                    spec = a2 / (np.pi * t * t) * Fl * g1(NdotV, k) * g1(NdotL, k) / (4 * NdotL * NdotV + 0.0001)
+                    want = want + (diff + spec) * (li[4:7] / d2) * NdotL
+            err = np.abs(got[y, x, :3] - want) / (np.abs(want) + 1e-3)
+            worst = max(worst, err.max())
+            assert got[y, x, 3] == 1.0
+    assert worst < 1e-5, worst
+
+
+def _bilinear_clamp64(img, u, v):
+    """Vulkan linear filter, CLAMP_TO_EDGE, unnormalised coordinate = uv * size - 0.5; float64. img (h, w, 4); u, v arrays."""
+    h, w = img.shape[:2]
+    x, y = u * w - 0.5, v * h - 0.5
+    x0, y0 = np.floor(x), np.floor(y)
+    fx, fy = (x - x0)[..., None], (y - y0)[..., None]
+    xi0, xi1 = np.clip(x0, 0, w - 1).astype(int), np.clip(x0 + 1, 0, w - 1).astype(int)
+    yi0, yi1 = np.clip(y0, 0, h - 1).astype(int), np.clip(y0 + 1, 0, h - 1).astype(int)
+    top = img[yi0, xi0] * (1 - fx) + img[yi0, xi1] * fx
+    bot = img[yi1, xi0] * (1 - fx) + img[yi1, xi1] * fx
+    return top * (1 - fy) + bot * fy
+
+
+@pytest.mark.parametrize("W,H", [(64, 40), (37, 23)])
+def test_glossy_convolve_against_an_independent_float64_evaluation(oracle, W, H):
+    """Second, independent evaluation of Shaders/SSRGlossyConvolve.comp:26-55 with the host loop of
+    Src/ReflectionBuffer.cpp:224-278 (level sizes, alternating direction, offsets divided by the TARGET width, texel
+    coordinate without the half-texel), in numpy float64. Each level is evaluated from the oracle's previous level, so
+    differences cannot compound; the oracle's halves must be the float64 value rounded to half, give or take one ulp
+    where the fp32 sum lands on the other side of a rounding boundary."""
+    rs = np.random.default_rng(3)
+    mip0 = rs.uniform(0, 4, (H, W, 4)).astype(np.float16)
+    mip0[..., 3] = rs.uniform(0, 1, (H, W)) * (rs.uniform(size=(H, W)) < 0.6)
+    chain = oracle.glossy_convolve(mip0.view(np.uint16), 5).view(np.float16)
+    offs = [1.411764705882353, 3.2941176470588234, 5.176470588235294]
+    wts = [0.2969069646728344, 0.09447039785044732, 0.010381362401148057]
+    base, prev = 0, mip0.astype(np.float64)
+    for level in range(1, 5):
+        base += prev.shape[0] * prev.shape[1] * 4
+        w, h = max(W >> level, 1), max(H >> level, 1)
+        got = chain[base:base + w * h * 4].reshape(h, w, 4)
+        d = np.array([0.0, 1.0]) if level & 1 else np.array([1.0, 0.0])
+        yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+        u, v = xx / w, yy / h
+        want = _bilinear_clamp64(prev, u, v) * 0.1964825501511404
+        for o, wt in zip(offs, wts):
+            du, dv = o * d[0] / w, o * d[1] / w
+            want += (_bilinear_clamp64(prev, u + du, v + dv) + _bilinear_clamp64(prev, u - du, v - dv)) * wt
+        want16 = want.astype(np.float16)
+        ulp = np.abs(got.view(np.int16).astype(np.int32) - want16.view(np.int16).astype(np.int32))
+        assert ulp.max() <= 1, (level, ulp.max())
+        assert (ulp == 0).mean() > 0.97, (level, (ulp == 0).mean())
+        prev = got.astype(np.float64)
+
+
+def test_glossy_convolve_keeps_a_constant_image_constant(oracle):
+    """The seven weights sum to 1 (to 1e-16), so a constant reflection buffer stays constant through all four levels."""
+    mip0 = np.full((48, 80, 4), 0.75, np.float16)
+    chain = oracle.glossy_convolve(mip0.view(np.uint16), 5).view(np.float16)
+    assert np.all(chain == np.float16(0.75))
