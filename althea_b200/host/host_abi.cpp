@@ -1,0 +1,44 @@
+// C ABI over the header-only host mirrors (include/althea_host.h). Built by build_host.build_lib() with plain g++.
+#include "althea_host.h"
+
+#include "Althea/GeometryUtilities.h"
+
+using namespace AltheaEngine::tangent_space_detail;
+
+extern "C" {
+
+int althea_host_abi_version(void) { return ALTHEA_HOST_ABI_VERSION; }
+
+int althea_host_compute_flat_normals(const float* position, uint64_t face_count, float* normal_out) {
+  if (!position || !normal_out) return -1;
+  for (uint64_t f = 0; f < face_count; ++f) {
+    const float* p = position + 9 * f;
+    const F3 a{p[0], p[1], p[2]}, b{p[3], p[4], p[5]}, c{p[6], p[7], p[8]};
+    const F3 ab = b - a, ac = c - a;
+    const F3 n = unit(F3{ab.y * ac.z - ab.z * ac.y, ab.z * ac.x - ab.x * ac.z, ab.x * ac.y - ab.y * ac.x});
+    for (int k = 0; k < 3; ++k) {
+      normal_out[9 * f + 3 * k] = n.x;
+      normal_out[9 * f + 3 * k + 1] = n.y;
+      normal_out[9 * f + 3 * k + 2] = n.z;
+    }
+  }
+  return 0;
+}
+
+int althea_host_compute_tangent_space(const float* position, const float* normal, const float* uv, uint64_t face_count,
+                                      float* tangent_out, float* bitangent_out) {
+  if (!position || !normal || !uv || !tangent_out || !bitangent_out) return -1;
+  if (face_count == 0) return 0;
+  std::vector<float> sign(face_count * 3);
+  generate(position, normal, uv, (size_t)face_count, tangent_out, sign.data());
+  for (uint64_t c = 0; c < face_count * 3; ++c) {
+    const float* N = normal + 3 * c;
+    const float* T = tangent_out + 3 * c;
+    bitangent_out[3 * c] = sign[c] * (N[1] * T[2] - N[2] * T[1]);
+    bitangent_out[3 * c + 1] = sign[c] * (N[2] * T[0] - N[0] * T[2]);
+    bitangent_out[3 * c + 2] = sign[c] * (N[0] * T[1] - N[1] * T[0]);
+  }
+  return 0;
+}
+
+} // extern "C"

@@ -4,8 +4,8 @@ a GLB (binary glTF 2.0) loader that builds the engine's `Vertex` buffers the way
 procedural meshes for tests. Host plumbing only: nothing here computes pixels.
 
 Differences from the reference's loader, all upstream of the C ABI (which takes finished Vertex buffers):
-  * tangents missing from the file are generated per triangle from the uv derivatives and orthonormalised against the vertex
-    normal; the reference calls MikkTSpace (Include/Althea/GeometryUtilities.h:51-70, third-party mikktspace.c, not restated);
+  * tangents missing from the file come from libalthea_host.so (include/althea_host.h, host/Althea/GeometryUtilities.h), a
+    from-scratch generator held bit for bit to the reference's MikkTSpace build (tests/test_tangent_space.py);
   * skins and animations are ignored (the producers take pre-transformed geometry).
 """
 from __future__ import annotations
@@ -209,23 +209,48 @@ def _node_matrix(node) -> np.ndarray:
     return m
 
 
-def _triangle_tangents(pos, nrm, uv):
-    """Per-triangle tangent from the uv derivatives, Gram-Schmidt against each vertex normal (de-indexed input, 3 per face)."""
-    p = pos.reshape(-1, 3, 3).astype(np.float64)
-    t = uv.reshape(-1, 3, 2).astype(np.float64)
-    e1, e2 = p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]
-    d1, d2 = t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]
-    det = d1[:, 0] * d2[:, 1] - d2[:, 0] * d1[:, 1]
-    det = np.where(np.abs(det) < 1e-20, 1.0, det)
-    tan = (e1 * d2[:, 1:2] - e2 * d1[:, 1:2]) / det[:, None]
-    tan = np.repeat(tan, 3, axis=0)
-    n = nrm.astype(np.float64)
-    tan = tan - n * np.sum(n * tan, axis=1, keepdims=True)
-    ln = np.linalg.norm(tan, axis=1, keepdims=True)
-    fallback = np.cross(np.where(np.abs(n[:, 0:1]) > 0.9, [[0.0, 1.0, 0.0]], [[1.0, 0.0, 0.0]]), n)
-    tan = np.where(ln > 1e-12, tan / np.maximum(ln, 1e-30), fallback / np.maximum(np.linalg.norm(fallback, axis=1, keepdims=True), 1e-30))
-    sign = np.repeat(np.where(det < 0, -1.0, 1.0), 3)[:, None]
-    return tan.astype(np.float32), (sign * np.cross(n, tan)).astype(np.float32)
+_host_lib = None
+
+
+def _host():
+    """althea_b200/lib/libalthea_host.so (include/althea_host.h); built on first use, a missing compiler is an error."""
+    global _host_lib
+    if _host_lib is None:
+        import ctypes as C
+        from .host import build_host
+        lib = C.CDLL(build_host.build_lib())
+        if lib.althea_host_abi_version() != 1:
+            raise RuntimeError("libalthea_host.so: ABI version mismatch")
+        lib.althea_host_compute_flat_normals.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.althea_host_compute_tangent_space.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        _host_lib = lib
+    return _host_lib
+
+
+def compute_flat_normals(pos) -> np.ndarray:
+    """GeometryUtilities::computeFlatNormals (Include/Althea/GeometryUtilities.h:32-48) on a de-indexed triangle list."""
+    pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+    faces = len(pos) // 3
+    out = np.zeros((faces * 3, 3), np.float32)
+    if _host().althea_host_compute_flat_normals(pos.ctypes.data, faces, out.ctypes.data) != 0:
+        raise RuntimeError("althea_host_compute_flat_normals failed")
+    return out
+
+
+def compute_tangent_space(pos, nrm, uv):
+    """GeometryUtilities::computeTangentSpace (Include/Althea/GeometryUtilities.h:51-70,137-155): MikkTSpace-equivalent tangents
+    and sign * cross(normal, tangent) bitangents for a de-indexed triangle list. Returns (tangent, bitangent), (3 * faces, 3)."""
+    pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+    nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 3)
+    uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+    faces = len(pos) // 3
+    if len(nrm) != len(pos) or len(uv) != len(pos):
+        raise ValueError("position, normal and uv must have one row per corner")
+    tang, bit = np.zeros((faces * 3, 3), np.float32), np.zeros((faces * 3, 3), np.float32)
+    if _host().althea_host_compute_tangent_space(pos.ctypes.data, nrm.ctypes.data, uv.ctypes.data, faces, tang.ctypes.data,
+                                                 bit.ctypes.data) != 0:
+        raise RuntimeError("althea_host_compute_tangent_space failed")
+    return tang, bit
 
 
 def load_glb(path: str, max_texture_size: Optional[int] = None) -> List[PrimitiveData]:
@@ -302,17 +327,21 @@ def load_glb(path: str, max_texture_size: Optional[int] = None) -> List[Primitiv
                 idx = _accessor(gltf, bin_chunk, prim["indices"]).reshape(-1).astype(np.uint32) if "indices" in prim else np.arange(len(pos), dtype=np.uint32)
                 mat = material(prim.get("material"))
                 duplicate = nrm is None or tan4 is None  # Primitive.cpp:147: flat normals / generated tangents need unshared vertices
+                idx = idx[: len(idx) // 3 * 3]
                 if duplicate:
                     pos, uvs = pos[idx], [u[idx] for u in uvs]
                     nrm = nrm[idx] if nrm is not None else None
+                    tan4 = tan4[idx] if tan4 is not None else None
                     idx = np.arange(len(pos), dtype=np.uint32)
-                    if nrm is None:  # GeometryUtilities::computeFlatNormals
-                        p3 = pos.reshape(-1, 3, 3)
-                        fn = np.cross(p3[:, 1] - p3[:, 0], p3[:, 2] - p3[:, 0])
-                        fn /= np.maximum(np.linalg.norm(fn, axis=1, keepdims=True), 1e-30)
-                        nrm = np.repeat(fn, 3, axis=0).astype(np.float32)
-                    uvn = uvs[mat.baseTextureCoordinateIndex] if len(uvs) > mat.baseTextureCoordinateIndex else np.zeros((len(pos), 2), np.float32)
-                    tang, bit = _triangle_tangents(pos, nrm, uvn)
+                    if nrm is None:  # Primitive.cpp:185-187
+                        nrm = compute_flat_normals(pos)
+                    if tan4 is None:  # Primitive.cpp:189-191, on the NORMAL MAP's uv set (Material.cpp:69)
+                        nuv = int((gltf["materials"][prim["material"]].get("normalTexture") or {}).get("texCoord", 0)) if "material" in prim else 0
+                        uvn = uvs[nuv] if len(uvs) > nuv else np.zeros((len(pos), 2), np.float32)
+                        tang, bit = compute_tangent_space(pos, nrm, uvn)
+                    else:
+                        tang = tan4[:, :3]
+                        bit = tan4[:, 3:4] * np.cross(nrm, tang)
                 else:
                     tang = tan4[:, :3]
                     bit = tan4[:, 3:4] * np.cross(nrm, tang)  # Primitive.cpp:341-343
@@ -320,7 +349,7 @@ def load_glb(path: str, max_texture_size: Optional[int] = None) -> List[Primitiv
                 v[:, 0:3], v[:, 3:6], v[:, 6:9], v[:, 9:12] = pos, tang, bit, nrm
                 for k, u in enumerate(uvs[:4]):
                     v[:, 12 + 2 * k: 14 + 2 * k] = u
-                out.append(PrimitiveData(v, idx[: len(idx) // 3 * 3], world.astype(np.float32), mat, False))
+                out.append(PrimitiveData(v, idx, world.astype(np.float32), mat, False))
         for c in node.get("children", []):
             visit(c, world)
 

@@ -1,0 +1,42 @@
+/* althea_host.h — C ABI of the host-side (CPU, no CUDA) geometry preparation that feeds the G-buffer producer.
+ *
+ * These are the vertex-stream fix-ups the reference performs while it loads a glTF primitive, before any vertex
+ * reaches the GPU (Src/Primitive.cpp:147-191). They are host work in the reference too; they live in their own
+ * library (althea_b200/lib/libalthea_host.so, plain g++) so that tools without a GPU can prepare models.
+ *
+ *   althea_host_compute_flat_normals   <- GeometryUtilities::computeFlatNormals    Include/Althea/GeometryUtilities.h:32-48
+ *   althea_host_compute_tangent_space  <- GeometryUtilities::computeTangentSpace   Include/Althea/GeometryUtilities.h:51-70,137-155
+ *                                         (MikkTSpace genTangSpaceDefault, Extern/MikkTSpace/mikktspace.c, through the
+ *                                         m_setTSpaceBasic callback)
+ *
+ * Inputs are de-indexed triangle lists, three consecutive vertices per face, tightly packed floats, exactly what
+ * Primitive.cpp hands over after duplicating vertices (:147). Returns 0 on success, -1 on a null pointer.
+ */
+#ifndef ALTHEA_HOST_H
+#define ALTHEA_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALTHEA_HOST_ABI_VERSION 1
+
+int althea_host_abi_version(void);
+
+/* normal_out[9 * f + 3 * k ..] = normalize(cross(p1 - p0, p2 - p0)) of face f for its three vertices k */
+int althea_host_compute_flat_normals(const float* position /* 9 floats per face */, uint64_t face_count,
+                                     float* normal_out /* 9 floats per face */);
+
+/* tangent_out and bitangent_out: 9 floats per face each. bitangent = sign * cross(normal, tangent) with the sign the
+ * tangent-space generator reports for the corner; corners nothing can be derived for get tangent (1, 0, 0), sign -1. */
+int althea_host_compute_tangent_space(const float* position /* 9 per face */, const float* normal /* 9 per face */,
+                                      const float* uv /* 6 per face: the normal map's uv set */, uint64_t face_count,
+                                      float* tangent_out, float* bitangent_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALTHEA_HOST_H */

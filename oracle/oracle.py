@@ -32,6 +32,16 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def build_ref():
+    """oracle/_ref/libmikktspace_ref.so: the reference's vendored tangent-space generator, compiled from the sources where they
+    lie (`make ref`). Only possible where /root/reference is mounted; elsewhere the prebuilt file (if it travelled) is used.
+    Returns the path or None."""
+    out = os.path.join(_HERE, "_ref", "libmikktspace_ref.so")
+    if os.path.isfile("/root/reference/Extern/MikkTSpace/mikktspace.c"):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    return out if os.path.exists(out) else None
+
+
 class GlobalUniforms(C.Structure):
     """Include/Althea/GlobalUniforms.h:15-31 (416 bytes)."""
     _fields_ = [

@@ -34,7 +34,7 @@ def helmet_primitives(path: str = GOLDEN):
     idx = d["idx"].astype(np.uint32)
     pos, nrm, uv = d["pos"][idx], d["nrm"].astype(np.float32)[idx], d["uv"][idx]
     nrm = nrm / np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
-    tang, bit = model._triangle_tangents(pos, nrm, uv)
+    tang, bit = model.compute_tangent_space(pos, nrm, uv)  # GeometryUtilities::computeTangentSpace, as Primitive.cpp:189-191
     v = np.zeros((len(pos), model.VERTEX_FLOATS), np.float32)
     v[:, 0:3], v[:, 3:6], v[:, 6:9], v[:, 9:12], v[:, 12:14] = pos, tang, bit, nrm, uv
     f = d["factors"]

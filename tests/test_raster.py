@@ -354,8 +354,13 @@ def test_glb_loader_on_the_reference_asset(oracle):
     assert p.material.baseTexture is not None and p.material.normalTexture is not None and p.material.metallicRoughnessTexture is not None
     nrm = p.vertices[:, 9:12]
     assert np.abs(np.linalg.norm(nrm, axis=1) - 1).max() < 1e-3
+    # the file ships no TANGENT: generated as the reference does (tests/test_tangent_space.py holds them to its MikkTSpace
+    # build); all but a handful of corners on zero-uv-area triangles are unit and perpendicular to the normal
     t = p.vertices[:, 3:6]
-    assert np.abs(np.sum(t * nrm, axis=1)).max() < 1e-3
+    assert (np.abs(np.linalg.norm(t, axis=1) - 1) > 1e-5).sum() < 20   # the generator leaves a tangent it cannot derive at zero
+    assert (np.abs(np.sum(t * nrm, axis=1)) > 1e-3).sum() < 20
+    b = p.vertices[:, 6:9]
+    assert np.abs(np.abs(np.sum(b * np.cross(nrm, t), axis=1)) - np.sum(np.cross(nrm, t) ** 2, axis=1)).max() < 1e-5
     W, H = 96, 54
     g, proj, view = _camera(W, H, pos=(0.0, 0.0, 3.0))
     out = oracle.draw_gbuffer(proj, view, prims, W, H)

@@ -1,0 +1,212 @@
+"""Tangent-space generation (the loader side of the G-buffer producer): althea_host_compute_tangent_space
+(include/althea_host.h, althea_b200/host/Althea/GeometryUtilities.h) against the REFERENCE's own generator.
+
+This is the one piece of the reference that builds here from its own sources: the vendored MikkTSpace C file
+(Extern/MikkTSpace/mikktspace.c, linked by CMakeLists.txt:55,112 and called from Include/Althea/GeometryUtilities.h:51-70).
+`make -C oracle ref` compiles it where it lies into oracle/_ref/. Its answers for the meshes of tests/tangent_cases.py and for
+the reference's DamagedHelmet primitive are committed in tests/golden/tangent_space.npz (tests/golden/make_tangent_golden.py), so
+the pin also holds where /root/reference is absent; when the library is present the comparison is repeated live on hundreds of
+shuffled meshes. CPU only."""
+import ctypes as C
+import os
+import re
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from althea_b200 import model
+from althea_b200.host import build_host
+from helpers import GOLDEN, REFERENCE, ROOT
+import tangent_cases as tc
+
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libmikktspace_ref.so")
+
+
+def _golden():
+    return np.load(os.path.join(GOLDEN, "tangent_space.npz"))
+
+
+def _reference():
+    """The reference's library, built on demand when its sources are mounted; None on a machine that has neither."""
+    if os.path.isdir(os.path.join(REFERENCE, "Extern", "MikkTSpace")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(REF_LIB):
+        return None
+    return C.CDLL(REF_LIB)
+
+
+def _reference_tangents(ref, pos, nrm, uv):
+    faces = len(pos) // 3
+    tang, sign = np.zeros((3 * faces, 3), np.float32), np.zeros(3 * faces, np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    assert ref.ref_mikktspace(p(pos), p(nrm), p(uv), faces, p(tang), p(sign)) == 1
+    return tang, sign
+
+
+def test_host_library_exports_what_the_header_declares():
+    lib = build_host.build_lib()
+    header = open(os.path.join(ROOT, "include", "althea_host.h")).read()
+    declared = set(re.findall(r"\b(althea_host_\w+)\s*\(", header))
+    assert declared == {"althea_host_abi_version", "althea_host_compute_flat_normals", "althea_host_compute_tangent_space"}
+    exported = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+    for name in declared:
+        assert re.search(r"\bT %s\b" % name, exported), name
+    # plain C: the header compiles as C99 on its own
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                    os.path.join(ROOT, "include", "althea_host.h")], check=True)
+    # and the library does not link CUDA
+    needed = subprocess.run(["readelf", "-d", lib], capture_output=True, text=True, check=True).stdout
+    assert "cuda" not in needed.lower()
+
+
+@pytest.mark.parametrize("name", sorted(tc.CASES))
+def test_tangents_equal_the_reference_librarys_bit_for_bit(name):
+    g = _golden()
+    pos, nrm, uv = tc.CASES[name]()
+    assert zlib.crc32(pos.tobytes() + nrm.tobytes() + uv.tobytes()) == int(g[name + "_input_crc"][0]), "case generator changed"
+    tang, bit = model.compute_tangent_space(pos, nrm, uv)
+    want_t, want_s = g[name + "_tangent"], g[name + "_sign"].astype(np.float32)
+    assert np.array_equal(tang.view(np.uint32), want_t.view(np.uint32))
+    assert np.array_equal(bit, want_s[:, None] * np.cross(nrm, want_t))  # GeometryUtilities.h:153-154
+    # the cases are not trivial: both handednesses, shared (smoothed) tangents, and corners nothing could be derived for
+    if name in ("sphere_mirrored", "hostile", "random_soup"):
+        assert 0.02 < (want_s > 0).mean() < 0.98
+    if name == "hostile":
+        assert np.all(want_t == [1.0, 0.0, 0.0], axis=1).any()
+
+
+def test_tangents_of_the_reference_asset():
+    """DamagedHelmet (BASELINE configs[0]) ships without TANGENT, so this is the input the reference really generates for."""
+    from helmet_fixture import helmet_primitives
+    g = _golden()
+    v = helmet_primitives()[0].vertices
+    tang, bit, nrm = np.ascontiguousarray(v[:, 3:6]), v[:, 6:9], v[:, 9:12]
+    assert len(tang) == 46356
+    assert zlib.crc32(tang.tobytes()) == int(g["helmet_tangent_crc"][0])
+    assert np.array_equal(tang[::97], g["helmet_thumb"])
+    sign = np.sign(np.sum(bit * np.cross(nrm, tang), axis=1)).astype(np.float32)
+    sign[sign == 0] = -1.0  # zero tangent: the stored sign cannot be recovered from the product; the CRC below is skipped then
+    if not (np.linalg.norm(tang, axis=1) == 0).any():
+        assert zlib.crc32(sign.tobytes()) == int(g["helmet_sign_crc"][0])
+
+
+def test_flat_normals():
+    pos, _, _ = tc.grid(7, 5)
+    got = model.compute_flat_normals(pos)
+    f = pos.reshape(-1, 3, 3).astype(np.float64)
+    want = np.cross(f[:, 1] - f[:, 0], f[:, 2] - f[:, 0])
+    want /= np.linalg.norm(want, axis=1, keepdims=True)
+    assert np.abs(got.reshape(-1, 3, 3) - want[:, None]).max() < 1e-6
+    assert np.array_equal(got[0::3], got[1::3]) and np.array_equal(got[0::3], got[2::3])
+
+
+def test_empty_and_invalid_input():
+    t, b = model.compute_tangent_space(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros((0, 2)))
+    assert t.shape == (0, 3) and b.shape == (0, 3)
+    with pytest.raises(ValueError):
+        model.compute_tangent_space(np.zeros((3, 3)), np.zeros((6, 3)), np.zeros((3, 2)))
+    lib = C.CDLL(build_host.build_lib())
+    assert lib.althea_host_compute_tangent_space(None, None, None, C.c_uint64(1), None, None) == -1
+    # a single triangle, all collapsed, all wild: defined outputs, no crash
+    one = np.zeros((3, 3), np.float32)
+    t, b = model.compute_tangent_space(one, np.tile([0, 0, 1.0], (3, 1)), np.zeros((3, 2)))
+    assert np.array_equal(t, np.tile([1.0, 0, 0], (3, 1)).astype(np.float32))
+
+
+def test_live_against_the_reference_library_on_shuffled_meshes():
+    """Hundreds of meshes with faces permuted and corners rotated. Expected to be identical, with one documented exception:
+    the library leaves the LAST run of its sorted edge list unsorted (its sub-sorts fire when the next run begins, so never for
+    the final one), and whether triangles across the edges of that one vertex get paired then depends on the incidental order
+    its randomised quicksort left them in. We always pair them. The exception is therefore confined to corners at one vertex
+    and its edge neighbours; everything else must be bit-identical, and most meshes must be identical outright."""
+    ref = _reference()
+    if ref is None:
+        pytest.skip("reference sources not mounted and oracle/_ref not built")
+    identical = total = 0
+    for seed in range(300):
+        rs = np.random.default_rng(seed)
+        kind = seed % 3
+        if kind == 0:
+            pos, nrm, uv = tc.grid(3 + seed % 9, seed, flat=(seed % 2 == 0))
+        elif kind == 1:
+            pos, nrm, uv = tc.sphere(3 + seed % 7, 3 + seed % 10, seed % 4 == 1)
+        else:
+            pos, nrm, uv = tc.hostile(seed)
+        faces = len(pos) // 3
+        perm, rot = rs.permutation(faces), rs.integers(0, 3, faces)
+        ci = (perm[:, None] * 3 + (np.arange(3)[None, :] + rot[:, None]) % 3).reshape(-1)
+        pos, nrm, uv = (np.ascontiguousarray(a[ci]) for a in (pos, nrm, uv))
+        want_t, want_s = _reference_tangents(ref, pos, nrm, uv)
+        got_t, got_b = model.compute_tangent_space(pos, nrm, uv)
+        bad = np.flatnonzero(np.any(got_t != want_t, axis=1) | np.any(got_b != want_s[:, None] * np.cross(nrm, want_t), axis=1))
+        total += 1
+        if len(bad) == 0:
+            identical += 1
+            continue
+        # all differing corners sit at one vertex X or at vertices sharing a triangle with X
+        key = {tuple(p) for p in pos[bad]}
+        tris = pos.reshape(-1, 3, 3)
+        ok = False
+        for x in key:
+            touching = np.any(np.all(tris == np.array(x, np.float32), axis=2), axis=1)
+            ring = {tuple(p) for p in tris[touching].reshape(-1, 3)}
+            if key <= ring:
+                ok = True
+                break
+        assert ok, "seed %d: differences are not confined to one vertex neighbourhood" % seed
+        assert len(bad) <= 40, (seed, len(bad))
+    assert identical >= 0.95 * total, (identical, total)
+
+
+def test_cpp_mirror_template_on_the_engine_vertex(tmp_path, lib_built):
+    """GeometryUtilities::computeFlatNormals / computeTangentSpace as the reference calls them (templates over the engine's
+    Vertex, Primitive.cpp:185-191), compiled against host/Althea/Model.h's Vertex and run on a mesh: same answer as the C ABI."""
+    from althea_b200 import build as cuda_build
+    pos, nrm, uv = tc.hostile(4)
+    src = tmp_path / "tangent_main.cpp"
+    src.write_text(r'''
+#include "Althea/Model.h"
+#include "Althea/GeometryUtilities.h"
+#include <cstdio>
+#include <vector>
+using namespace AltheaEngine;
+int main(int argc, char** argv) {
+  if (argc != 3) return 1;
+  FILE* f = fopen(argv[1], "rb");
+  int n = 0;
+  if (!f || fread(&n, 4, 1, f) != 1) return 2;
+  std::vector<float> in((size_t)n * 8);
+  if (fread(in.data(), 4, in.size(), f) != in.size()) return 3;
+  fclose(f);
+  std::vector<Vertex> v(n);
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < 3; ++k) { v[i].position[k] = in[8 * i + k]; v[i].normal[k] = in[8 * i + 3 + k]; }
+    v[i].uvs[1][0] = in[8 * i + 6]; v[i].uvs[1][1] = in[8 * i + 7];
+  }
+  std::vector<Vertex> flat = v;
+  GeometryUtilities::computeFlatNormals(flat);
+  GeometryUtilities::computeTangentSpace(v, 1);
+  FILE* o = fopen(argv[2], "wb");
+  for (int i = 0; i < n; ++i) { fwrite(v[i].tangent, 4, 3, o); fwrite(v[i].bitangent, 4, 3, o); fwrite(flat[i].normal, 4, 3, o); }
+  fclose(o);
+  return 0;
+}
+''')
+    exe = tmp_path / "tangent_main"
+    host_dir = os.path.join(ROOT, "althea_b200", "host")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-I", host_dir, str(src), "-L", cuda_build.LIB_DIR, "-lalthea_cuda", "-Wl,-rpath," + cuda_build.LIB_DIR, "-ldl", "-lpthread",
+                    "-lrt", "-o", str(exe)], check=True)
+    inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(np.int32(len(pos)).tobytes())
+        f.write(np.concatenate([pos, nrm, uv], axis=1).astype(np.float32).tobytes())
+    subprocess.run([str(exe), str(inp), str(outp)], check=True)
+    got = np.fromfile(outp, np.float32).reshape(-1, 9)
+    want_t, want_b = model.compute_tangent_space(pos, nrm, uv)
+    assert np.array_equal(got[:, 0:3], want_t) and np.array_equal(got[:, 3:6], want_b)
+    flat = model.compute_flat_normals(pos)
+    ok = np.isfinite(flat).all(axis=1)          # collapsed faces have no normal (0/0), in the reference as well
+    assert np.array_equal(got[:, 6:9][ok], flat[ok])
