@@ -7,7 +7,9 @@ frexp-normalised TRUNCATED mantissas) and re-loads them with `Utilities::loadHdr
 This module writes and reads the same files from the CUDA-generated maps, so the untouched engine loader picks them up and
 the run-time data carries the same RGBE quantisation as the reference's.
 
-Host-side IO only (numpy); the maps themselves come from althea_cuda_ibl_precompute.
+Host-side IO only: the codec is the C++ mirror of Utilities::saveHdri / loadHdri (host/Althea/Utilities.h behind
+include/althea_host.h), held byte for byte to the reference's stb build (tests/test_hdr_cache.py); float_to_rgbe /
+rgbe_to_float below are its numpy twins for array-level work. The maps themselves come from althea_cuda_ibl_precompute.
 """
 from __future__ import annotations
 
@@ -42,69 +44,47 @@ def rgbe_to_float(rgbe: np.ndarray) -> np.ndarray:
     return out
 
 
+def _host():
+    from . import model
+    lib = model._host()
+    if not getattr(lib, "_hdr_bound", False):
+        import ctypes as C
+        lib.althea_host_save_hdri.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_void_p]
+        lib.althea_host_load_hdri_info.argtypes = [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.althea_host_load_hdri.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64]
+        lib._hdr_bound = True
+    return lib
+
+
 def write_hdr(path: str, rgba: np.ndarray) -> None:
-    """stbi_write_hdr's container: '#?RADIANCE' header, -Y H +X W, one RLE-framed scanline per row (channel-planar)."""
-    rgbe = float_to_rgbe(rgba)
-    h, w = rgbe.shape[:2]
+    """Utilities::saveHdri through libalthea_host.so (host/Althea/Utilities.h): the file stbi_write_hdr would write, byte for
+    byte after the header's comment line. rgba: (H, W, 3 or 4) float; alpha is not stored."""
+    a = np.asarray(rgba, np.float32)
+    if a.ndim != 3 or a.shape[2] not in (3, 4):
+        raise ValueError("write_hdr takes an (H, W, 3|4) image")
+    if a.shape[2] == 3:
+        a = np.concatenate([a, np.ones(a.shape[:2] + (1,), np.float32)], -1)
+    a = np.ascontiguousarray(a)
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-    with open(path, "wb") as f:
-        f.write(b"#?RADIANCE\n# Written by althea_b200 (stb_image_write.h layout)\nFORMAT=32-bit_rle_rgbe\n")
-        f.write(("EXPOSURE=          1.0000000000000\n\n-Y %d +X %d\n" % (h, w)).encode())
-        if w < 8 or w >= 32768:  # stb writes such images flat
-            f.write(rgbe.tobytes())
-            return
-        head = bytes([2, 2, (w >> 8) & 0xFF, w & 0xFF])
-        for y in range(h):
-            f.write(head)
-            for c in range(4):
-                row = rgbe[y, :, c]
-                for x0 in range(0, w, 128):  # literal packets only (count <= 128): valid RLE framing, no run detection needed
-                    chunk = row[x0:x0 + 128]
-                    f.write(bytes([len(chunk)]))
-                    f.write(chunk.tobytes())
+    rc = _host().althea_host_save_hdri(os.fsencode(path), a.shape[1], a.shape[0], a.ctypes.data)
+    if rc != 0:
+        raise OSError("althea_host_save_hdri(%s) failed: %d" % (path, rc))
 
 
 def read_hdr(path: str) -> np.ndarray:
-    """Radiance RGBE -> (H, W, 3) float32 as stbi_loadf decodes it (flat or RLE scanlines)."""
-    buf = open(path, "rb").read()
-    pos = 0
-    if not (buf.startswith(b"#?RADIANCE") or buf.startswith(b"#?RGBE")):
-        raise ValueError("%s is not a Radiance HDR file" % path)
-    while True:
-        end = buf.index(b"\n", pos)
-        line = buf[pos:end]
-        pos = end + 1
-        if line == b"":
-            break
-    end = buf.index(b"\n", pos)
-    tok = buf[pos:end].split()
-    pos = end + 1
-    if len(tok) != 4 or tok[0] != b"-Y" or tok[2] != b"+X":
-        raise ValueError("unsupported HDR orientation in %s" % path)
-    h, w = int(tok[1]), int(tok[3])
-    data = np.frombuffer(buf, np.uint8)
-    out = np.empty((h, w, 4), np.uint8)
-    if w < 8 or w >= 32768 or not (data[pos] == 2 and data[pos + 1] == 2 and not (data[pos + 2] & 0x80)):
-        out[:] = data[pos:pos + h * w * 4].reshape(h, w, 4)
-        return rgbe_to_float(out)
-    for y in range(h):
-        if data[pos] != 2 or data[pos + 1] != 2 or ((int(data[pos + 2]) << 8) | int(data[pos + 3])) != w:
-            raise ValueError("corrupt RLE scanline %d in %s" % (y, path))
-        pos += 4
-        for c in range(4):
-            x = 0
-            while x < w:
-                count = int(data[pos])
-                pos += 1
-                if count > 128:
-                    count -= 128
-                    out[y, x:x + count, c] = data[pos]
-                    pos += 1
-                else:
-                    out[y, x:x + count, c] = data[pos:pos + count]
-                    pos += count
-                x += count
-    return rgbe_to_float(out)
+    """Utilities::loadHdri through libalthea_host.so: Radiance RGBE -> (H, W, 3) float32 exactly as stbi_loadf decodes it."""
+    import ctypes as C
+    w, h = C.c_int32(), C.c_int32()
+    rc = _host().althea_host_load_hdri_info(os.fsencode(path), C.byref(w), C.byref(h))
+    if rc == -2:
+        raise FileNotFoundError(path)
+    if rc != 0:
+        raise ValueError("%s is not a Radiance HDR file (%d)" % (path, rc))
+    out = np.empty((h.value, w.value, 4), np.float32)
+    rc = _host().althea_host_load_hdri(os.fsencode(path), out.ctypes.data, out.size)
+    if rc != 0:
+        raise ValueError("%s: decode failed (%d)" % (path, rc))
+    return np.ascontiguousarray(out[..., :3])
 
 
 def cache_paths(content_dir: str, env_name: str) -> Tuple[str, list]:

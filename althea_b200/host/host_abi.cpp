@@ -2,6 +2,7 @@
 #include "althea_host.h"
 
 #include "Althea/GeometryUtilities.h"
+#include "Althea/Utilities.h"
 
 using namespace AltheaEngine::tangent_space_detail;
 
@@ -38,6 +39,47 @@ int althea_host_compute_tangent_space(const float* position, const float* normal
     bitangent_out[3 * c + 1] = sign[c] * (N[2] * T[0] - N[0] * T[2]);
     bitangent_out[3 * c + 2] = sign[c] * (N[0] * T[1] - N[1] * T[0]);
   }
+  return 0;
+}
+
+int althea_host_save_hdri(const char* path, int32_t width, int32_t height, const float* rgba) {
+  if (!path || !rgba || width <= 0 || height <= 0) return -1;
+  try {
+    AltheaEngine::Utilities::saveHdri(path, width, height, reinterpret_cast<const std::byte*>(rgba), (size_t)width * height * 16);
+  } catch (const std::exception&) {
+    return -2;
+  }
+  return 0;
+}
+
+static int loadHdri(const char* path, int32_t* width, int32_t* height, std::vector<float>& rgba) {
+  std::vector<uint8_t> file;
+  try {
+    file = AltheaEngine::Utilities::readFile(path);
+  } catch (const std::exception&) {
+    return -2;
+  }
+  int w = 0, h = 0;
+  if (!AltheaEngine::Utilities::decodeHdri(file.data(), file.size(), w, h, rgba)) return -3;
+  *width = w;
+  *height = h;
+  return 0;
+}
+
+int althea_host_load_hdri_info(const char* path, int32_t* width, int32_t* height) {
+  if (!path || !width || !height) return -1;
+  std::vector<float> rgba;
+  return loadHdri(path, width, height, rgba);
+}
+
+int althea_host_load_hdri(const char* path, float* rgba_out, uint64_t capacity_floats) {
+  if (!path || !rgba_out) return -1;
+  std::vector<float> rgba;
+  int32_t w = 0, h = 0;
+  const int rc = loadHdri(path, &w, &h, rgba);
+  if (rc != 0) return rc;
+  if (capacity_floats < rgba.size()) return -4;
+  std::memcpy(rgba_out, rgba.data(), rgba.size() * sizeof(float));
   return 0;
 }
 

@@ -8,8 +8,13 @@
  *   althea_host_compute_tangent_space  <- GeometryUtilities::computeTangentSpace   Include/Althea/GeometryUtilities.h:51-70,137-155
  *                                         (MikkTSpace genTangSpaceDefault, Extern/MikkTSpace/mikktspace.c, through the
  *                                         m_setTSpaceBasic callback)
+ *   althea_host_save_hdri              <- Utilities::saveHdri                       Src/Utilities.cpp:244-255
+ *                                         (stb_image_write.h stbi_write_hdr: Radiance RGBE, run-length coded rows)
+ *   althea_host_load_hdri(_info)       <- Utilities::loadHdri                       Src/Utilities.cpp:189-213
+ *                                         (stb_image.h stbi_loadf_from_memory, 4 channels requested)
+ *     the pair ImageBasedLighting::createResources uses for its on-disk cache, Src/ImageBasedLighting.cpp:415-446
  *
- * Inputs are de-indexed triangle lists, three consecutive vertices per face, tightly packed floats, exactly what
+ * Geometry inputs are de-indexed triangle lists, three consecutive vertices per face, tightly packed floats, exactly what
  * Primitive.cpp hands over after duplicating vertices (:147). Returns 0 on success, -1 on a null pointer.
  */
 #ifndef ALTHEA_HOST_H
@@ -35,6 +40,17 @@ int althea_host_compute_flat_normals(const float* position /* 9 floats per face 
 int althea_host_compute_tangent_space(const float* position /* 9 per face */, const float* normal /* 9 per face */,
                                       const float* uv /* 6 per face: the normal map's uv set */, uint64_t face_count,
                                       float* tangent_out, float* bitangent_out);
+
+/* Writes width x height RGBA32F texels (row 0 first; alpha is not stored) as a Radiance .hdr file, byte-identical to
+ * stbi_write_hdr's output except for the header's comment line. -1: bad argument, -2: the file cannot be written. */
+int althea_host_save_hdri(const char* path, int32_t width, int32_t height, const float* rgba);
+
+/* Size of a .hdr file's image. -1: bad argument, -2: cannot be read, -3: not a Radiance RGBE file stbi_loadf would accept. */
+int althea_host_load_hdri_info(const char* path, int32_t* width, int32_t* height);
+
+/* Decodes into rgba_out (4 floats per texel, alpha = 1, as loadHdri returns it). capacity_floats must be at least
+ * 4 * width * height of althea_host_load_hdri_info; -4 if it is not. */
+int althea_host_load_hdri(const char* path, float* rgba_out, uint64_t capacity_floats);
 
 #ifdef __cplusplus
 }

@@ -72,3 +72,137 @@ def test_cache_round_trip_on_gpu(tmp_path, ctx_fast):
     flat = np.concatenate([p.reshape(-1) for p in pre])
     reloaded = ctx_fast.image_from_numpy(flat, F32, 128, 64, 5)
     assert reloaded.mips == 5
+
+
+# ---- pinned by the reference's own IO library ----------------------------------------------------------------------------
+def _payload(file_bytes: bytes) -> bytes:
+    """Everything after the free-text comment line of the header (ours names this repo, stb's names stb)."""
+    return file_bytes[file_bytes.index(b"FORMAT="):]
+
+
+def test_writer_and_reader_equal_the_references_stb_on_the_committed_vector(tmp_path):
+    """tests/golden/stb_written.hdr was written by the reference's stbi_write_hdr and decoded by its stbi_loadf
+    (tests/golden/make_hdr_golden.py): our writer must produce the same bytes, our reader the same floats."""
+    g = np.load(os.path.join(GOLDEN, "stb_written.npz"))
+    theirs = open(os.path.join(GOLDEN, "stb_written.hdr"), "rb").read()
+    out = str(tmp_path / "ours.hdr")
+    hdr_cache.write_hdr(out, g["image"])
+    ours = open(out, "rb").read()
+    assert ours.startswith(b"#?RADIANCE\n") and _payload(ours) == _payload(theirs)
+    assert np.array_equal(hdr_cache.read_hdr(os.path.join(GOLDEN, "stb_written.hdr")), g["decoded"][..., :3])
+    assert (g["decoded"][..., 3] == 1).all()
+    # the numpy twins agree with the C++ codec
+    assert np.array_equal(hdr_cache.rgbe_to_float(hdr_cache.float_to_rgbe(g["image"])), g["decoded"][..., :3])
+    # runs longer than 127 and literal stretches longer than 128 are both in the vector
+    assert len(theirs) < g["image"].shape[0] * g["image"].shape[1] * 4
+
+
+def _stb():
+    import ctypes as C
+    import subprocess
+
+    from helpers import ROOT
+    if os.path.isdir(os.path.join(REFERENCE, "Extern", "stb")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    path = os.path.join(ROOT, "oracle", "_ref", "libstb_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("reference sources not mounted and oracle/_ref not built")
+    lib = C.CDLL(path)
+    lib.ref_stbi_loadf_from_memory.restype = C.POINTER(C.c_float)
+    return lib
+
+
+def _stb_loadf(lib, path):
+    import ctypes as C
+    buf = open(path, "rb").read()
+    w, h = C.c_int(), C.c_int()
+    p = lib.ref_stbi_loadf_from_memory(buf, len(buf), C.byref(w), C.byref(h))
+    if not p:
+        return None
+    a = np.ctypeslib.as_array(p, (h.value, w.value, 4)).copy()
+    lib.ref_stbi_free(p)
+    return a
+
+
+def test_live_against_the_references_stb(tmp_path):
+    """Random images of awkward sizes: identical payload bytes, identical decode in both directions; malformed files are
+    rejected by both."""
+    import ctypes as C
+    lib = _stb()
+    rs = np.random.default_rng(0)
+    for k, (w, h) in enumerate([(53, 37), (5, 9), (8, 3), (300, 20), (1024, 8), (129, 4), (7, 7), (32767, 1), (128, 2), (131, 3)]):
+        img = np.exp(rs.uniform(-14, 10, (h, w, 4))).astype(np.float32)
+        if k % 2 == 0:
+            img[:, : w // 2] = img[:1, :1]
+            img[1::2] = 0
+        if k % 3 == 0:
+            img = np.round(img * 4) / 4          # coarse values: many short runs of two and three
+        img = np.ascontiguousarray(img, np.float32)
+        a, b = str(tmp_path / ("a%d.hdr" % k)), str(tmp_path / ("b%d.hdr" % k))
+        hdr_cache.write_hdr(a, img)
+        assert lib.ref_stbi_write_hdr(b.encode(), w, h, img.ctypes.data_as(C.c_void_p)) == 1
+        assert _payload(open(a, "rb").read()) == _payload(open(b, "rb").read()), (w, h)
+        theirs = _stb_loadf(lib, a)
+        assert np.array_equal(hdr_cache.read_hdr(b), theirs[..., :3]) and np.array_equal(hdr_cache.read_hdr(a), theirs[..., :3])
+    good = open(str(tmp_path / "a0.hdr"), "rb").read()
+    for name, bad in (("no_format", good.replace(b"FORMAT=32-bit_rle_rgbe", b"FORMAT=32-bit_rle_xyze")),
+                      ("not_hdr", b"#?RADIANT\nnothing of the kind\n"), ("bad_layout", good.replace(b"-Y ", b"+Y "))):
+        p = str(tmp_path / (name + ".hdr"))
+        open(p, "wb").write(bad)
+        assert _stb_loadf(lib, p) is None, name
+        with pytest.raises(ValueError):
+            hdr_cache.read_hdr(p)
+    with pytest.raises(FileNotFoundError):
+        hdr_cache.read_hdr(str(tmp_path / "missing.hdr"))
+    # stricter than stb on purpose: a file cut short is an error here (stb pads the missing bytes with zeros and carries on)
+    open(str(tmp_path / "cut.hdr"), "wb").write(good[: len(good) // 2])
+    with pytest.raises(ValueError):
+        hdr_cache.read_hdr(str(tmp_path / "cut.hdr"))
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference not mounted (GPU box)")
+def test_the_references_shipped_cache_files_survive_a_rewrite_byte_for_byte(tmp_path):
+    """Content/PrecomputedMaps/*/Prefiltered5.hdr were written by the engine itself (saveHdri). Decoding them and writing the
+    floats back with our writer reproduces the engine's files byte for byte (after the comment line), and both decoders agree
+    on every file of the shipped cache."""
+    lib = _stb()
+    for env in ("LuxuryRoom", "NeoclassicalInterior", "ThatchChapel"):
+        for name in ("Prefiltered5.hdr", "Prefiltered3.hdr"):
+            src = os.path.join(REFERENCE, "Content/PrecomputedMaps", env, name)
+            a = hdr_cache.read_hdr(src)
+            assert np.array_equal(a, _stb_loadf(lib, src)[..., :3])
+            out = str(tmp_path / (env + name))
+            hdr_cache.write_hdr(out, a)
+            assert _payload(open(out, "rb").read()) == _payload(open(src, "rb").read()), (env, name)
+
+
+def test_cpp_mirror_utilities_load_and_save(tmp_path):
+    """Utilities::loadHdri / saveHdri with the reference's names and result struct (Include/Althea/Utilities.h:29-53), driven from
+    C++: load the committed stb-written file, save it again, same payload; a missing file throws as the reference's does."""
+    import subprocess
+
+    from helpers import ROOT
+    src = tmp_path / "hdr_main.cpp"
+    src.write_text(r'''
+#include "Althea/Utilities.h"
+#include <cstdio>
+using namespace AltheaEngine;
+int main(int argc, char** argv) {
+  if (argc != 3) return 1;
+  Utilities::ImageFile img;
+  Utilities::loadHdri(argv[1], img);
+  if (img.channels != 4 || img.bytesPerChannel != 4 || img.data.size() != (size_t)img.width * img.height * 16) return 2;
+  Utilities::saveHdri(argv[2], img.width, img.height, img.data.data(), img.data.size());
+  try { Utilities::loadHdri("/nonexistent/none.hdr", img); return 3; } catch (const std::runtime_error&) {}
+  std::printf("%d %d\n", img.width, img.height);
+  return 0;
+}
+''')
+    exe = tmp_path / "hdr_main"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "althea_b200", "host"),
+                    str(src), "-o", str(exe)], check=True)
+    golden = os.path.join(GOLDEN, "stb_written.hdr")
+    out = str(tmp_path / "again.hdr")
+    r = subprocess.run([str(exe), golden, out], check=True, capture_output=True, text=True)
+    assert r.stdout.split() == ["300", "24"]
+    assert _payload(open(out, "rb").read()) == _payload(open(golden, "rb").read())
