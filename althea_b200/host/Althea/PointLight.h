@@ -1,6 +1,7 @@
 // Include/Althea/PointLight.h:31-153: the light SSBO, the omni shadow cube array the deferred pass and SSR read, and
 // drawShadowMaps (Src/PointLight.cpp:235-282), which renders the cubes from the models' primitives.
 #pragma once
+#include "Camera.h"
 #include "CudaApplication.h"
 #include "Model.h"
 
@@ -56,32 +57,12 @@ public:
                                               _shadowMap.handle(), sync),
                 "althea_cuda_draw_shadow_cubes");
   }
-  // PointLightConstants as the constructor builds them (PointLight.cpp:72-118): a 90 degree, aspect 1, 0.01 / 1000 camera at the
-  // origin facing X+ X- Y+ Y- Z+ Z- through Camera::setRotationDegrees (Src/Camera.cpp:40-65), views = affineInverse(transform)
+  // PointLightConstants as the constructor builds them (PointLight.cpp:72-118): a 90 degree, aspect 1, 0.01 / 1000 Camera at the
+  // origin turned to X+ X- Y+ Y- Z+ Z- through setRotationDegrees, views = computeView(), inverses by glm::inverse (Camera.h)
   static althea_point_light_constants pointLightConstants() {
     althea_point_light_constants c;
-    std::memset(&c, 0, sizeof c);
-    const float t = std::tan(0.5f * 1.57079632679489661923f), zn = 0.01f, zf = 1000.0f;
-    c.projection[0] = 1.0f / t;  c.projection[5] = -(1.0f / t);  c.projection[10] = zf / (zn - zf);  c.projection[11] = -1.0f;
-    c.projection[14] = -(zf * zn) / (zf - zn);
-    c.inverseProjection[0] = t;  c.inverseProjection[5] = -t;  c.inverseProjection[11] = 1.0f / c.projection[14];
-    c.inverseProjection[14] = -1.0f;  c.inverseProjection[15] = c.projection[10] / c.projection[14];
-    const float deg = 0.01745329251994329577f;
-    const float rot[6][2] = {{90.0f, 0.0f}, {-90.0f, 0.0f}, {180.0f, 90.0f}, {180.0f, -90.0f}, {180.0f, 0.0f}, {0.0f, 0.0f}};
-    for (int f = 0; f < 6; ++f) {
-      const float yaw = rot[f][0] * deg, pitch = rot[f][1] * deg, cp = std::cos(pitch);
-      const float z[3] = {std::sin(yaw) * cp, -std::sin(pitch), std::cos(yaw) * cp};
-      float x[3] = {z[2], 0.0f, -z[0]}; // cross((0, 1, 0), z)
-      const float inv = 1.0f / std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-      for (float& v : x) v *= inv;
-      const float y[3] = {z[1] * x[2] - x[1] * z[2], z[2] * x[0] - x[2] * z[0], z[0] * x[1] - x[0] * z[1]};
-      float* iv = c.inverseViews[f];
-      float* vw = c.views[f];
-      for (int k = 0; k < 3; ++k) { iv[k] = x[k]; iv[4 + k] = y[k]; iv[8 + k] = z[k]; }
-      iv[15] = 1.0f;
-      for (int r = 0; r < 3; ++r) { vw[4 * 0 + r] = iv[4 * r + 0]; vw[4 * 1 + r] = iv[4 * r + 1]; vw[4 * 2 + r] = iv[4 * r + 2]; } // rotation^T
-      vw[15] = 1.0f;
-    }
+    static_assert(sizeof c == 14 * 16 * sizeof(float), "projection, inverseProjection, views[6], inverseViews[6]");
+    pointLightConstantMatrices(reinterpret_cast<float*>(&c));
     return c;
   }
   // texel = length(p - light) / 1000 (Shaders/ShadowMapBindless.frag:41), layer = 6 * light + face

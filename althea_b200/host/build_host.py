@@ -30,7 +30,8 @@ def build_lib(force: bool = False) -> str:
     """althea_b200/lib/libalthea_host.so: the CPU-side geometry preparation (include/althea_host.h). Plain g++, no CUDA;
     fp contraction off so the fp32 arithmetic is the same on every host."""
     srcs = [os.path.join(_HERE, "host_abi.cpp"), os.path.join(_HERE, "Althea", "GeometryUtilities.h"),
-            os.path.join(_HERE, "Althea", "Utilities.h"), os.path.join(ROOT, "include", "althea_host.h")]
+            os.path.join(_HERE, "Althea", "Utilities.h"), os.path.join(_HERE, "Althea", "Camera.h"),
+            os.path.join(ROOT, "include", "althea_host.h")]
     if not force and os.path.exists(HOST_LIB) and all(os.path.getmtime(HOST_LIB) >= os.path.getmtime(p) for p in srcs):
         return HOST_LIB
     os.makedirs(_build.LIB_DIR, exist_ok=True)

@@ -1,6 +1,7 @@
 // C ABI over the header-only host mirrors (include/althea_host.h). Built by build_host.build_lib() with plain g++.
 #include "althea_host.h"
 
+#include "Althea/Camera.h"
 #include "Althea/GeometryUtilities.h"
 #include "Althea/Utilities.h"
 
@@ -80,6 +81,31 @@ int althea_host_load_hdri(const char* path, float* rgba_out, uint64_t capacity_f
   if (rc != 0) return rc;
   if (capacity_floats < rgba.size()) return -4;
   std::memcpy(rgba_out, rgba.data(), rgba.size() * sizeof(float));
+  return 0;
+}
+
+int althea_host_camera(float fov_degrees, float aspect, float near_plane, float far_plane, const float position[3], float yaw_radians,
+                       float pitch_radians, float* projection16, float* transform16, float* view16, float* inverse_projection16) {
+  if (!position) return -1;
+  AltheaEngine::Camera camera(fov_degrees, aspect, near_plane, far_plane);
+  camera.setPosition(position[0], position[1], position[2]);
+  camera.setRotationRadians(yaw_radians, pitch_radians);
+  if (projection16) std::memcpy(projection16, camera.getProjection().data(), 64);
+  if (transform16) std::memcpy(transform16, camera.getTransform().data(), 64);
+  if (view16) {
+    const AltheaEngine::Mat4 v = camera.computeView();
+    std::memcpy(view16, v.data(), 64);
+  }
+  if (inverse_projection16) {
+    const AltheaEngine::Mat4 ip = AltheaEngine::inverse(camera.getProjection());
+    std::memcpy(inverse_projection16, ip.data(), 64);
+  }
+  return 0;
+}
+
+int althea_host_point_light_constants(float* matrices224) {
+  if (!matrices224) return -1;
+  AltheaEngine::pointLightConstantMatrices(matrices224);
   return 0;
 }
 

@@ -362,56 +362,29 @@ def load_glb(path: str, max_texture_size: Optional[int] = None) -> List[Primitiv
 # ---- C-ABI structs ------------------------------------------------------------------------------------------------------
 def point_light_constants() -> _capi.PointLightConstants:
     """PointLightConstants as the PointLightCollection constructor builds them (Src/PointLight.cpp:72-118): a 90 degree, aspect 1,
-    near 0.01 / far 1000 camera at the origin facing the six axes; Camera maths in fp32 as GLM evaluates it
-    (Src/Camera.cpp:40-65,90-103), including the float noise of sin/cos at 180 and +-90 degrees that orients the +-Y faces."""
-    f32 = np.float32
-
-    def perspective():
-        t = np.tan(f32(np.radians(f32(90.0))) / f32(2.0), dtype=f32)
-        m = np.zeros((4, 4), f32)  # m[col][row]
-        m[0][0] = f32(1.0) / (f32(1.0) * t)
-        m[1][1] = f32(1.0) / t
-        m[2][2] = f32(1000.0) / (f32(0.01) - f32(1000.0))
-        m[2][3] = -f32(1.0)
-        m[3][2] = -(f32(1000.0) * f32(0.01)) / (f32(1000.0) - f32(0.01))
-        m[1][1] *= -f32(1.0)
-        return m
-
-    def transform(yaw_deg, pitch_deg):
-        yaw, pitch = f32(np.radians(f32(yaw_deg))), f32(np.radians(f32(pitch_deg)))
-        limit = f32(np.pi) - f32(0.01)
-        pitch = np.clip(pitch, -limit, limit)
-        cp = np.cos(pitch, dtype=f32)
-        z = np.array([np.sin(yaw, dtype=f32) * cp, -np.sin(pitch, dtype=f32), np.cos(yaw, dtype=f32) * cp], f32)
-        up = np.array([0, 1, 0], f32)
-        x = np.array([up[1] * z[2] - z[1] * up[2], up[2] * z[0] - z[2] * up[0], up[0] * z[1] - z[0] * up[1]], f32)
-        x = x * (f32(1.0) / np.sqrt(np.dot(x, x), dtype=f32))  # glm::normalize = v * inversesqrt(dot(v, v))
-        y = np.array([z[1] * x[2] - x[1] * z[2], z[2] * x[0] - x[2] * z[0], z[0] * x[1] - x[0] * z[1]], f32)
-        m = np.eye(4, dtype=f32)  # m[col]
-        m[0, :3], m[1, :3], m[2, :3] = x, y, z
-        return m
-
-    def affine_inverse(m):  # glm::affineInverse: inverse of the 3x3 block, translation -inv * t
-        r = m[:3, :3].T.astype(np.float64)  # rows = matrix rows
-        inv = np.linalg.inv(r).astype(f32)
-        out = np.eye(4, dtype=f32)
-        out[:3, :3] = inv.T
-        out[3, :3] = -(inv @ m[3, :3])
-        return out
-
+    near 0.01 / far 1000 Camera at the origin turned to the six axes, views = computeView(), inverses by glm::inverse. Computed by
+    the C++ mirror of the reference's Camera (host/Althea/Camera.h through libalthea_host.so), which is bit-identical to the
+    reference's class built against its GLM, including the rounding noise of sin/cos at 180 and +-90 degrees that orients the
+    +-Y faces (tests/test_camera_pin.py)."""
+    lib = _host()
+    lib.althea_host_point_light_constants.argtypes = [C.c_void_p]
     pc = _capi.PointLightConstants()
-    proj = perspective()
-    inv_proj = np.linalg.inv(proj.T.astype(np.float64)).T.astype(f32)
-    for i in range(16):
-        pc.projection[i] = float(proj.reshape(-1)[i])
-        pc.inverseProjection[i] = float(inv_proj.reshape(-1)[i])
-    for f, (yaw, pitch) in enumerate(((90.0, 0.0), (-90.0, 0.0), (180.0, 90.0), (180.0, -90.0), (180.0, 0.0), (0.0, 0.0))):
-        xf = transform(yaw, pitch)
-        view = affine_inverse(xf)
-        for i in range(16):
-            pc.views[f][i] = float(view.reshape(-1)[i])
-            pc.inverseViews[f][i] = float(xf.reshape(-1)[i])
+    assert C.sizeof(pc) == 14 * 64
+    if lib.althea_host_point_light_constants(C.addressof(pc)) != 0:
+        raise RuntimeError("althea_host_point_light_constants failed")
     return pc
+
+
+def camera_matrices(fov_degrees: float, aspect: float, near: float, far: float, position, yaw: float, pitch: float):
+    """The reference's Camera (Src/Camera.cpp:7-110) for one pose: (projection, transform, view, inverse projection), each a
+    (4, 4) float32 array in glm's column-major storage (row i of the array is column i of the matrix)."""
+    lib = _host()
+    lib.althea_host_camera.argtypes = [C.c_float] * 4 + [C.c_void_p, C.c_float, C.c_float] + [C.c_void_p] * 4
+    pos = np.ascontiguousarray(position, np.float32)
+    out = [np.zeros((4, 4), np.float32) for _ in range(4)]
+    if lib.althea_host_camera(fov_degrees, aspect, near, far, pos.ctypes.data, yaw, pitch, *[o.ctypes.data for o in out]) != 0:
+        raise RuntimeError("althea_host_camera failed")
+    return tuple(out)
 
 
 class UploadedModel:

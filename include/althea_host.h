@@ -13,6 +13,10 @@
  *   althea_host_load_hdri(_info)       <- Utilities::loadHdri                       Src/Utilities.cpp:189-213
  *                                         (stb_image.h stbi_loadf_from_memory, 4 channels requested)
  *     the pair ImageBasedLighting::createResources uses for its on-disk cache, Src/ImageBasedLighting.cpp:415-446
+ *   althea_host_camera                 <- Camera (Include/Althea/Camera.h, Src/Camera.cpp:7-110): projection, transform, view
+ *   althea_host_point_light_constants  <- the PointLightConstants PointLightCollection's constructor derives from six
+ *                                         Cameras, Src/PointLight.cpp:72-118 (the `constants` argument of
+ *                                         althea_cuda_draw_shadow_cubes)
  *
  * Geometry inputs are de-indexed triangle lists, three consecutive vertices per face, tightly packed floats, exactly what
  * Primitive.cpp hands over after duplicating vertices (:147). Returns 0 on success, -1 on a null pointer.
@@ -51,6 +55,16 @@ int althea_host_load_hdri_info(const char* path, int32_t* width, int32_t* height
 /* Decodes into rgba_out (4 floats per texel, alpha = 1, as loadHdri returns it). capacity_floats must be at least
  * 4 * width * height of althea_host_load_hdri_info; -4 if it is not. */
 int althea_host_load_hdri(const char* path, float* rgba_out, uint64_t capacity_floats);
+
+/* One Camera: constructed with (fov, aspect, near, far), then setPosition and setRotationRadians. Each output is 16 floats,
+ * column-major as glm::mat4: getProjection(), getTransform(), computeView(), and glm::inverse of the projection. Any output
+ * pointer may be NULL. Bit-identical to the reference's class built against its GLM (tests/test_camera_pin.py). */
+int althea_host_camera(float fov_degrees, float aspect, float near_plane, float far_plane, const float position[3],
+                       float yaw_radians, float pitch_radians, float* projection16, float* transform16, float* view16,
+                       float* inverse_projection16);
+
+/* 14 matrices of 16 floats: projection, inverseProjection, views[6], inverseViews[6] == althea_point_light_constants. */
+int althea_host_point_light_constants(float* matrices224);
 
 #ifdef __cplusplus
 }
