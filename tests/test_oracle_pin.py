@@ -84,3 +84,23 @@ def test_brdf_lut_matches_reference_asset(oracle):
     assert d[8:-8, 8:-8].max() < 0.15
     wrong = np.abs(oracle.brdf_lut(450, 64, 0) - ref).mean()
     assert wrong > 10 * d.mean()    # the un-flipped reading is clearly not what the asset holds
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference not mounted (GPU box)")
+def test_committed_brdf_lut_is_what_the_engine_decodes():
+    """tests/golden/brdf_lut.npz was expanded from the palette PNG with Pillow; the engine decodes it with stb
+    (Src/Utilities.cpp:104-150 -> stbi_load_from_memory, 4 channels). Same texels from the reference's own stb build."""
+    import ctypes as C
+    import subprocess
+
+    from helpers import ROOT, golden_lut
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libstb_ref.so"))
+    ref.ref_stbi_load_from_memory.restype = C.POINTER(C.c_ubyte)
+    buf = open(os.path.join(REFERENCE, "Content/PrecomputedMaps/brdf_lut.png"), "rb").read()
+    w, h = C.c_int(), C.c_int()
+    p = ref.ref_stbi_load_from_memory(buf, len(buf), C.byref(w), C.byref(h))
+    assert p
+    texels = np.ctypeslib.as_array(p, (h.value, w.value, 4)).copy()
+    ref.ref_stbi_free(p)
+    assert np.array_equal(texels, golden_lut())
