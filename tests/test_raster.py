@@ -459,6 +459,90 @@ def test_glb_loader_on_a_synthetic_file(tmp_path, oracle, with_tangents):
     assert set(np.unique(out["albedo"][cov][:, 1] > 60)) == {False, True}  # the green half of the texture and the other half
 
 
+def test_gltf_json_container_loads_like_the_glb(tmp_path):
+    """The same asset as a .gltf: JSON next to an external .bin, one image as a file (with a space in its name, percent-encoded in
+    the uri) and the buffer optionally as a base64 data: URI. Same primitives as the binary container."""
+    import base64
+    import io
+    import json
+    import struct
+
+    from PIL import Image as PILImage
+    pos = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], np.float32)
+    nrm = np.tile(np.array([[0, 0, 1]], np.float32), (4, 1))
+    uv = np.array([[0, 1], [1, 1], [1, 0], [0, 0]], np.float32)
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+    tex = np.zeros((8, 8, 4), np.uint8)
+    tex[..., 0], tex[..., 3] = 200, 255
+    tex[:4, :, 1] = 255
+    glb = str(tmp_path / "quad.glb")
+    _write_glb(glb, pos, nrm, uv, idx, tex, True)
+    want = model.load_glb(glb)[0]
+    data = open(glb, "rb").read()
+    jlen = struct.unpack_from("<I", data, 12)[0]
+    gltf = json.loads(data[20:20 + jlen])
+    binc = data[20 + jlen + 8:]
+    img_view = gltf["bufferViews"][gltf["images"][0]["bufferView"]]
+    png = binc[img_view["byteOffset"]: img_view["byteOffset"] + img_view["byteLength"]]
+    (tmp_path / "sub").mkdir()
+    open(str(tmp_path / "sub" / "base colour.png"), "wb").write(png)
+    gltf["images"] = [{"uri": "sub/base%20colour.png"}]
+    for variant, uri in (("file", "quad.bin"), ("data", "data:application/octet-stream;base64," + base64.b64encode(binc).decode())):
+        gltf["buffers"] = [{"byteLength": len(binc), "uri": uri}]
+        open(str(tmp_path / "quad.bin"), "wb").write(binc)
+        path = str(tmp_path / ("quad_%s.gltf" % variant))
+        open(path, "w").write(json.dumps(gltf))
+        got = model.load_gltf(path)
+        assert len(got) == 1
+        assert np.array_equal(got[0].vertices, want.vertices) and np.array_equal(got[0].indices, want.indices)
+        assert np.array_equal(got[0].model, want.model)
+        assert np.array_equal(got[0].material.baseTexture.levels[0], want.material.baseTexture.levels[0])
+        assert got[0].material.baseTexture.sampler == want.material.baseTexture.sampler
+    open(str(tmp_path / "junk.gltf"), "wb").write(b"\x00\x01 not json")
+    with pytest.raises(ValueError):
+        model.load_gltf(str(tmp_path / "junk.gltf"))
+    open(str(tmp_path / "other.gltf"), "w").write("{}")
+    with pytest.raises(ValueError):
+        model.load_gltf(str(tmp_path / "other.gltf"))
+
+
+_REFERENCE_MODELS = {  # primitives, triangles, distinct textures; SURVEY.md 8(f): Sponza = 103 primitives / 262 k triangles / 69 images
+    "DamagedHelmet.glb": (1, 15452, 3), "AntiqueCamera.glb": (2, 20066, 6), "Buggy.glb": (236, 531955, 0),
+    "MetalRoughSpheres.glb": (5, 501776, 2), "FlightHelmet/FlightHelmet.gltf": (6, 94722, 15), "Sponza/glTF/Sponza.gltf": (103, 262267, 69)}
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "Content/Models")), reason="reference not mounted (GPU box)")
+@pytest.mark.parametrize("name", sorted(_REFERENCE_MODELS))
+def test_loader_reads_every_model_the_reference_ships(name):
+    prims = model.load_gltf(os.path.join(REFERENCE, "Content/Models", name), max_texture_size=32)
+    n_prims, n_tris, n_tex = _REFERENCE_MODELS[name]
+    assert len(prims) == n_prims and sum(p.triangle_count for p in prims) == n_tris
+    textures = {id(t) for p in prims for t in (p.material.baseTexture, p.material.normalTexture, p.material.metallicRoughnessTexture) if t is not None}
+    assert len(textures) == n_tex
+    for p in prims:
+        v = p.vertices
+        assert np.isfinite(v[:, :12]).all() and int(p.indices.max()) < len(v) and len(p.indices) % 3 == 0
+        n = np.linalg.norm(v[:, 9:12], axis=1)
+        assert (np.abs(n - 1) < 1e-2).mean() > 0.99            # unit normals (a few degenerate faces give NaN-free zeros)
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REFERENCE, "Content/Models/Sponza/glTF/Sponza.gltf")), reason="reference not mounted (GPU box)")
+def test_sponza_frame_through_the_restatement(oracle):
+    """BASELINE configs[1]'s scene (Sponza) from its .gltf: a view down the atrium fills the frame, with cut-out foliage and
+    several hundred distinct triangles' worth of detail; then the deferred chain runs on that G-buffer."""
+    prims = model.load_gltf(os.path.join(REFERENCE, "Content/Models/Sponza/glTF/Sponza.gltf"), max_texture_size=32)
+    W, H = 128, 72
+    g = scene.make_uniforms(W, H, pos=(-8.0, 2.0, 0.0), yaw=-np.pi / 2, pitch=0.0)
+    out = oracle.draw_gbuffer(list(g.projection), list(g.view), prims, W, H)
+    cov = out["tri"] != NONE
+    assert cov.mean() > 0.99
+    assert len(np.unique(out["tri"][cov])) > 1000
+    assert 2.0 < np.linalg.norm(out["position"][cov][:, :3] - [-8.0, 2.0, 0.0], axis=1).max() < 40.0   # the far end of the nave
+    nrm = out["normal"][cov][:, :3]
+    unit = np.abs(np.linalg.norm(nrm, axis=1) - out["normal"][cov][:, 3]) < 5e-3   # unit normal x coverage alpha, RGBA16F
+    assert unit.mean() > 0.97                                   # the rest: foliage texels blended over what is behind them
+
+
 def test_triangles_sharing_an_edge_never_both_claim_a_pixel(oracle):
     """Random quads split along a diagonal, random cameras: the two triangles' coverages are disjoint and their union is the
     coverage of drawing both (top-left rule + exactly opposite edge values on the shared edge)."""
