@@ -6,7 +6,8 @@ procedural meshes for tests. Host plumbing only: nothing here computes pixels.
 Differences from the reference's loader, all upstream of the C ABI (which takes finished Vertex buffers):
   * tangents missing from the file come from libalthea_host.so (include/althea_host.h, host/Althea/GeometryUtilities.h), a
     from-scratch generator held bit for bit to the reference's MikkTSpace build (tests/test_tangent_space.py);
-  * skins and animations are ignored (the producers take pre-transformed geometry).
+  * skinned primitives are transformed on the host exactly as Gltf.vert:37-54 would (weights x joint matrices, bind pose: no
+    animation is played) and handed over with an identity transform, because the producers take pre-transformed geometry.
 """
 from __future__ import annotations
 
@@ -363,6 +364,45 @@ def load_gltf(path: str, max_texture_size: Optional[int] = None) -> List[Primiti
 
     out: List[PrimitiveData] = []
 
+    # Node transforms as Model::_updateTransforms leaves them in the matrix buffer (Src/Model.cpp:341-356): global transform times
+    # the node's inverse bind pose (identity unless a skin names the node as a joint, Model.cpp:193-216). No animation is applied,
+    # so every node sits at the transform the file gives it.
+    nodes = gltf.get("nodes", [])
+    node_global = [None] * len(nodes)
+
+    def globals_of(node_idx, parent):
+        node_global[node_idx] = parent @ _node_matrix(nodes[node_idx])
+        for c in nodes[node_idx].get("children", []):
+            globals_of(c, node_global[node_idx])
+
+    for n in gltf["scenes"][gltf.get("scene", 0)]["nodes"]:
+        globals_of(n, np.eye(4))
+    inverse_bind = [np.eye(4) for _ in nodes]
+    for skin in gltf.get("skins", []):
+        if "inverseBindMatrices" in skin:
+            ibm = _accessor(gltf, buffers, skin["inverseBindMatrices"]).astype(np.float64).reshape(-1, 4, 4)
+            for j, joint in enumerate(skin["joints"]):
+                inverse_bind[joint] = ibm[j].T  # accessor matrices are column-major
+    node_matrix = [None if g is None else (g @ inverse_bind[i]).astype(np.float32) for i, g in enumerate(node_global)]
+
+    def skin_vertices(v, skin_idx, joints, weights):
+        """Gltf.vert:37-54 for a skinned primitive, applied on the host (the producers take pre-transformed geometry):
+        model = sum over the four influences with weight > 0 of weight * matrix[jointMap[joint]]; position and the TBN columns go
+        through it; the primitive is then drawn with an identity transform. fp32, in the shader's order of operations."""
+        joint_nodes = np.asarray(gltf["skins"][skin_idx]["joints"], np.int64)
+        mats = np.stack([node_matrix[j] if node_matrix[j] is not None else np.eye(4, dtype=np.float32) for j in joint_nodes])
+        model_m = np.zeros((len(v), 4, 4), np.float32)
+        for i in range(4):
+            w = weights[:, i].astype(np.float32)
+            use = w > 0
+            model_m[use] += w[use, None, None] * mats[joints[use, i].astype(np.int64)]
+        p = v[:, 0:3]
+        v[:, 0:3] = ((model_m[:, :3, 0] * p[:, 0:1] + model_m[:, :3, 1] * p[:, 1:2]) + model_m[:, :3, 2] * p[:, 2:3]) + model_m[:, :3, 3]
+        for a in (3, 6, 9):  # tangent, bitangent, normal: mat3(model) * column
+            c = v[:, a:a + 3].copy()
+            v[:, a:a + 3] = (model_m[:, :3, 0] * c[:, 0:1] + model_m[:, :3, 1] * c[:, 1:2]) + model_m[:, :3, 2] * c[:, 2:3]
+        return v
+
     def visit(node_idx, parent):
         node = gltf["nodes"][node_idx]
         world = parent @ _node_matrix(node)
@@ -379,6 +419,7 @@ def load_gltf(path: str, max_texture_size: Optional[int] = None) -> List[Primiti
                 mat = material(prim.get("material"))
                 duplicate = nrm is None or tan4 is None  # Primitive.cpp:147: flat normals / generated tangents need unshared vertices
                 idx = idx[: len(idx) // 3 * 3]
+                src_index = idx.copy() if duplicate else None
                 if duplicate:
                     pos, uvs = pos[idx], [u[idx] for u in uvs]
                     nrm = nrm[idx] if nrm is not None else None
@@ -400,7 +441,17 @@ def load_gltf(path: str, max_texture_size: Optional[int] = None) -> List[Primiti
                 v[:, 0:3], v[:, 3:6], v[:, 6:9], v[:, 9:12] = pos, tang, bit, nrm
                 for k, u in enumerate(uvs[:4]):
                     v[:, 12 + 2 * k: 14 + 2 * k] = u
-                out.append(PrimitiveData(v, idx, world.astype(np.float32), mat, False))
+                prim_world = world.astype(np.float32)
+                if "JOINTS_0" in at and "WEIGHTS_0" in at and "skin" in node:  # Primitive.cpp:320: isSkinned
+                    joints = _accessor(gltf, buffers, at["JOINTS_0"])
+                    weights = _accessor(gltf, buffers, at["WEIGHTS_0"]).astype(np.float32)  # u8 / u16 weights arrive normalised
+                    if src_index is not None:
+                        joints, weights = joints[src_index], weights[src_index]
+                    v[:, 20:24] = weights
+                    v[:, 24:26] = np.ascontiguousarray(joints.astype(np.uint16)).view(np.float32)
+                    v = skin_vertices(v, node["skin"], joints, weights)
+                    prim_world = np.eye(4, dtype=np.float32)
+                out.append(PrimitiveData(v, idx, prim_world, mat, False))
         for c in node.get("children", []):
             visit(c, world)
 

@@ -506,6 +506,83 @@ def test_gltf_json_container_loads_like_the_glb(tmp_path):
         model.load_gltf(str(tmp_path / "other.gltf"))
 
 
+def test_skinned_primitive_is_transformed_like_the_vertex_shader(tmp_path, oracle):
+    """Gltf.vert:37-54 on the host: a strip skinned to two joints (u8 joints, normalised u16 weights, indexed, with tangents).
+    The loaded vertices must be sum_i w_i * (global(joint_i) * inverseBind(joint_i)) * position, evaluated here in float64 from the
+    file's numbers, the primitive's own transform must be the identity (the mesh node's transform does not apply to a skinned
+    primitive), and the result renders where that puts it."""
+    import json
+    import struct
+    pos = np.array([[-0.5, 0, 0], [0.5, 0, 0], [-0.5, 1, 0], [0.5, 1, 0], [-0.5, 2, 0], [0.5, 2, 0]], np.float32)
+    nrm = np.tile(np.array([[0, 0, 1]], np.float32), (6, 1))
+    tan = np.tile(np.array([[1, 0, 0, 1]], np.float32), (6, 1))
+    uv = pos[:, :2].copy()
+    idx = np.array([0, 1, 2, 2, 1, 3, 2, 3, 4, 4, 3, 5], np.uint16)
+    joints = np.array([[0, 1, 0, 0]] * 6, np.uint8)
+    w1 = np.array([0.0, 0.0, 0.5, 0.5, 1.0, 1.0])
+    weights = np.zeros((6, 4), np.uint16)
+    weights[:, 1] = np.round(w1 * 65535)
+    weights[:, 0] = 65535 - weights[:, 1]
+    c, s_ = np.cos(0.6), np.sin(0.6)
+    ibm = np.stack([np.eye(4), np.array([[1, 0, 0, 0], [0, 1, 0, -1.0], [0, 0, 1, 0], [0, 0, 0, 1]])]).astype(np.float32)
+    chunks, views, accessors = [], [], []
+
+    def acc(arr, ctype, typ, normalized=False):
+        data = np.ascontiguousarray(arr).tobytes()
+        off = sum(len(x) for x in chunks)
+        chunks.append(data + b"\0" * ((-len(data)) % 4))
+        views.append({"buffer": 0, "byteOffset": off, "byteLength": len(data)})
+        a = {"bufferView": len(views) - 1, "componentType": ctype, "count": len(arr), "type": typ}
+        if normalized:
+            a["normalized"] = True
+        accessors.append(a)
+        return len(accessors) - 1
+
+    attrs = {"POSITION": acc(pos, 5126, "VEC3"), "NORMAL": acc(nrm, 5126, "VEC3"), "TANGENT": acc(tan, 5126, "VEC4"),
+             "TEXCOORD_0": acc(uv, 5126, "VEC2"), "JOINTS_0": acc(joints, 5121, "VEC4"), "WEIGHTS_0": acc(weights, 5123, "VEC4", True)}
+    a_idx = acc(idx, 5123, "SCALAR")
+    a_ibm = acc(np.stack([m.T for m in ibm]).reshape(2, 16), 5126, "MAT4")  # column-major
+    quat = [0.0, 0.0, float(np.sin(0.3)), float(np.cos(0.3))]              # 0.6 rad about z
+    gltf = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0, 1]}],
+            "nodes": [{"mesh": 0, "skin": 0, "translation": [100.0, 0.0, 0.0]},           # must NOT move the skinned primitive
+                      {"children": [2], "translation": [0.25, 0.0, -1.0]}, {"translation": [0.0, 1.0, 0.0], "rotation": quat}],
+            "skins": [{"joints": [1, 2], "inverseBindMatrices": a_ibm}],
+            "meshes": [{"primitives": [{"attributes": attrs, "indices": a_idx}]}],
+            "bufferViews": views, "accessors": accessors, "buffers": [{"byteLength": sum(len(x) for x in chunks)}]}
+    js = json.dumps(gltf).encode()
+    js += b" " * ((-len(js)) % 4)
+    binc = b"".join(chunks)
+    path = str(tmp_path / "skinned.glb")
+    with open(path, "wb") as f:
+        f.write(struct.pack("<III", 0x46546C67, 2, 12 + 8 + len(js) + 8 + len(binc)))
+        f.write(struct.pack("<II", len(js), 0x4E4F534A) + js)
+        f.write(struct.pack("<II", len(binc), 0x004E4942) + binc)
+    prims = model.load_gltf(path)
+    assert len(prims) == 1 and np.array_equal(prims[0].model, np.eye(4, dtype=np.float32))
+    v = prims[0].vertices
+    assert len(v) == 6 and np.array_equal(prims[0].indices, idx)
+    g0 = np.eye(4)
+    g0[:3, 3] = [0.25, 0.0, -1.0]
+    l1 = np.array([[c, -s_, 0, 0], [s_, c, 0, 1.0], [0, 0, 1, 0], [0, 0, 0, 1]])
+    m = [g0 @ ibm[0].astype(np.float64), g0 @ l1 @ ibm[1].astype(np.float64)]
+    wn = weights.astype(np.float64) / 65535.0
+    for k in range(6):
+        blend = wn[k, 0] * m[0] + wn[k, 1] * m[1]
+        want = blend @ np.append(pos[k], 1.0)
+        assert np.abs(v[k, 0:3] - want[:3]).max() < 1e-6
+        assert np.abs(v[k, 3:6] - blend[:3, :3] @ [1, 0, 0]).max() < 1e-6       # tangent
+        assert np.abs(v[k, 9:12] - blend[:3, :3] @ [0, 0, 1]).max() < 1e-6      # normal
+    assert np.allclose(v[:, 20:24], wn, atol=1e-7) and np.array_equal(v[:, 24:26].copy().view(np.uint16).reshape(6, 4), joints)
+    # the top of the strip swings 0.6 rad about the second joint; the mesh node's x = 100 is nowhere to be seen
+    assert v[:, 0].max() < 2.0 and v[4, 0] < v[0, 0]
+    W, H = 64, 48
+    g, proj, view = _camera(W, H, pos=(0.0, 1.0, 3.0))
+    out = oracle.draw_gbuffer(proj, view, prims, W, H)
+    cov = out["tri"] != NONE
+    assert 0.02 < cov.mean() < 0.5
+    assert np.abs(out["position"][cov][:, 2] + 1.0).max() < 1e-4                # the whole strip lies in the plane z = -1
+
+
 _REFERENCE_MODELS = {  # primitives, triangles, distinct textures; SURVEY.md 8(f): Sponza = 103 primitives / 262 k triangles / 69 images
     "DamagedHelmet.glb": (1, 15452, 3), "AntiqueCamera.glb": (2, 20066, 6), "Buggy.glb": (236, 531955, 0),
     "MetalRoughSpheres.glb": (5, 501776, 2), "FlightHelmet/FlightHelmet.gltf": (6, 94722, 15), "Sponza/glTF/Sponza.gltf": (103, 262267, 69)}
