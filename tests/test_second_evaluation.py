@@ -350,3 +350,121 @@ def test_deferred_frame_against_a_float64_evaluation():
     # tone-mapped values live in [0, 1): absolute error. fp32 atan2 / pow against float64 leaves ~1e-6.
     assert err[ok].max() < 2e-5, err[ok].max()
     assert (fd.shadow.min() * 1000 < 50) and covered.mean() > 0.5       # shadows and geometry are really in play
+
+
+# ---- IBL precompute (the pinned half as well: a tight check next to the RGBE-bounded pin of test_oracle_pin.py) --------------
+def _chain_levels(flat_chain, w, h, mips):
+    levels, off = [], 0
+    for l in range(mips):
+        lw, lh = max(w >> l, 1), max(h >> l, 1)
+        levels.append(flat_chain[off:off + lw * lh * 4].reshape(lh, lw, 4).astype(np.float64))
+        off += lw * lh * 4
+    return levels
+
+
+def _bilinear_repeat(img, u, v):
+    h, w = img.shape[:2]
+    x, y = u * w - 0.5, v * h - 0.5
+    x0, y0 = np.floor(x), np.floor(y)
+    fx, fy = (x - x0)[..., None], (y - y0)[..., None]
+    xi0, xi1 = x0.astype(int) % w, (x0.astype(int) + 1) % w
+    yi0, yi1 = y0.astype(int) % h, (y0.astype(int) + 1) % h
+    top = img[yi0, xi0] * (1 - fx) + img[yi0, xi1] * fx
+    bot = img[yi1, xi0] * (1 - fx) + img[yi1, xi1] * fx
+    return top * (1 - fy) + bot * fy
+
+
+def _env_lookup64(levels, d, mip):
+    """sampleEnvMap of the precompute shaders (GenIrradianceMap.comp:78-102): REPEAT sampler, LINEAR mip filter."""
+    len_xz = np.hypot(d[..., 0], d[..., 2])
+    safe = len_xz > 0.001
+    yaw = np.where(safe, np.arctan2(d[..., 2], d[..., 0]), 0.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        pitch = np.where(safe, np.arctan(d[..., 1] / len_xz), np.where(d[..., 1] > 0, 0.5 * np.pi, -0.5 * np.pi))
+    u, v = yaw / (2 * np.pi) + 0.5, pitch / np.pi + 0.5
+    mip = np.clip(np.broadcast_to(mip, u.shape), 0, len(levels) - 1)
+    l0 = np.minimum(np.floor(mip).astype(int), len(levels) - 1)
+    l1 = np.minimum(l0 + 1, len(levels) - 1)
+    fr = (mip - l0)[..., None]
+    out = np.zeros(u.shape + (4,))
+    for l in range(len(levels)):
+        m0, m1 = l0 == l, (l1 == l) & (l1 != l0)
+        if m0.any() or m1.any():
+            s = _bilinear_repeat(levels[l], u, v)
+            out += np.where(m0[..., None], s * (1 - fr), 0) + np.where(m1[..., None], s * fr, 0)
+    return out[..., :3]
+
+
+def _local_to_world(n):
+    if abs(n[0]) > abs(n[1]):
+        t = np.array([-n[2], 0.0, n[0]]) / np.sqrt(n[0] ** 2 + n[2] ** 2)
+    else:
+        t = np.array([0.0, n[2], -n[1]]) / np.sqrt(n[1] ** 2 + n[2] ** 2)
+    return t, np.cross(n, t), n
+
+
+def _texel_normal(x, y, w, h):
+    yaw, pitch = np.pi * (2.0 * x / w - 1.0), np.pi * (y / h - 0.5)
+    return np.array([np.cos(pitch) * np.cos(yaw), np.sin(pitch), np.cos(pitch) * np.sin(yaw)])
+
+
+def test_irradiance_against_a_float64_evaluation():
+    """Shaders/IBL_Precompute/GenIrradianceMap.comp:106-155 at a few texels of a 512 x 256 map, all 300 x 150 samples."""
+    from helpers import golden_env
+    env = golden_env()
+    H, W = env.shape[:2]
+    chain, mips = O.env_mip_chain(env)
+    levels = _chain_levels(chain, W, H, mips)
+    texels = [(0, 128, 0), (100, 40, 0), (511, 255, 0), (256, 1, 0), (333, 200, 0)]
+    got = O.ibl_irradiance(chain, W, H, mips, W, H, texels)
+    theta_n, phi_n = 300, int(H * 300 / W)
+    mip = np.log2(W / 300.0)
+    th = np.arange(theta_n) * 2 * np.pi / theta_n
+    ph = np.arange(phi_n) * 0.5 * np.pi / phi_n
+    T, P = np.meshgrid(th, ph, indexing="ij")
+    local = np.stack([np.cos(T) * np.sin(P), np.sin(T) * np.sin(P), np.cos(P)], -1)
+    for (x, y, _), g in zip(texels, got):
+        t, b, n = _local_to_world(_texel_normal(x, y, W, H))
+        d = local[..., 0:1] * t + local[..., 1:2] * b + local[..., 2:3] * n
+        s = _env_lookup64(levels, d, mip) * (np.cos(P) * np.sin(P))[..., None]
+        want = np.pi * s.sum(axis=(0, 1)) / theta_n / phi_n
+        assert np.abs(g[:3] - want).max() < 5e-5 * np.abs(want).max(), (x, y, g[:3], want)   # observed 4e-6
+        assert g[3] == 1.0
+
+
+@pytest.mark.parametrize("roughness", [0.0, 0.25, 0.75, 1.0])
+def test_prefilter_against_a_float64_evaluation(roughness):
+    """Shaders/IBL_Precompute/PreFilterEnvMap.comp:126-177 with the shader's own hash sequence (:38-44) and GGX sampling
+    (:84-92), 10000 samples per texel. The sample directions depend only on integer hashing, so the two evaluations see the
+    same samples; what differs is fp32 against float64 in the warps, the mip choice and the sum."""
+    from helpers import golden_env
+    env = golden_env()
+    H, W = env.shape[:2]
+    chain, mips = O.env_mip_chain(env)
+    levels = _chain_levels(chain, W, H, mips)
+    ow, oh = W >> 1, H >> 1
+    texels = [(17, 64, 0), (200, 100, 0), (128, 5, 0)]
+    got = O.ibl_prefilter(chain, W, H, mips, ow, oh, roughness, texels)
+    n_samples = 10000
+    a2 = roughness * roughness
+    for (x, y, _), g in zip(texels, got):
+        xi = shader_rng(np.array([x]), np.array([y]), 2 * n_samples)[:, 0].reshape(n_samples, 2)
+        phi = 2 * np.pi * xi[:, 0]
+        cos_t = np.sqrt((1 - xi[:, 1]) / (1 + (a2 - 1) * xi[:, 1]))
+        sin_t = np.sqrt(1 - cos_t * cos_t)
+        t, b, n = _local_to_world(_texel_normal(x, y, ow, oh))
+        Hh = (np.cos(phi) * sin_t)[:, None] * t + (np.sin(phi) * sin_t)[:, None] * b + cos_t[:, None] * n
+        V = n
+        L = normalize(2.0 * (Hh @ V)[:, None] * Hh - V)
+        NdotL, NdotH, HdotV = np.maximum(L @ n, 0), np.maximum(Hh @ n, 0), np.maximum(Hh @ V, 0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            D = a2 / (np.pi * (NdotH * NdotH * (a2 - 1) + 1) ** 2)   # 0 / 0 at roughness 0, where the mip is fixed anyway
+        pdf = D * NdotH / (4 * HdotV + 0.00001)
+        sa_texel = 4 * np.pi / (6.0 * W * H)
+        sa_sample = 1.0 / (n_samples * pdf + 0.0001)
+        with np.errstate(divide="ignore"):
+            mip = np.zeros(n_samples) if roughness == 0.0 else 0.5 * np.log2(sa_sample / sa_texel)
+        use = NdotL > 0
+        col = _env_lookup64(levels, L[use], mip[use]) * NdotL[use, None]
+        want = col.sum(0) / NdotL[use].sum()
+        assert np.abs(g[:3] - want).max() < 5e-5 * np.abs(want).max(), (x, y, roughness, g[:3], want)   # observed 3e-6
