@@ -295,12 +295,23 @@ def main_mesh4k(args, ctx, rank, local_rank, world, device):
     from althea_b200 import _capi, engine, scene
     from althea_b200 import model as _model
     ibl, _, _, _ = build_rank_inputs(ctx, rank, 0, device, quick_ibl=True)
-    up = _model.UploadedModel(ctx, raster_bench.build_scene(512))
+    if args.model:  # a glTF asset from disk, e.g. the reference's Content/Models/Sponza/glTF/Sponza.gltf (BASELINE configs[1])
+        prims = _model.load_gltf(args.model, max_texture_size=args.model_texture_size)
+        cam = [float(v) for v in args.model_camera.split(",")]
+    else:
+        prims = raster_bench.build_scene(512)
+    up = _model.UploadedModel(ctx, prims)
     lights = engine.PointLightCollection(ctx, N_LIGHTS, shadow_res=SHADOW_RES)
     prng = np.random.default_rng(1)
-    for i in range(N_LIGHTS):
-        lights.setLight(i, engine.PointLight((prng.uniform(-4, 4), prng.uniform(0, 4), prng.uniform(-3, 4)), (10.0, 10.0, 10.0)))
-    g = scene.make_uniforms(W4K, H4K, pos=(0.3, 0.8, 3.5), yaw=0.1 + 0.05 * rank, pitch=-0.2, light_count=N_LIGHTS)
+    if args.model:
+        box = [float(v) for v in args.model_light_box.split(",")]  # xmin, xmax, ymin, ymax, zmin, zmax
+        for i in range(N_LIGHTS):
+            lights.setLight(i, engine.PointLight((prng.uniform(box[0], box[1]), prng.uniform(box[2], box[3]), prng.uniform(box[4], box[5])), (10.0, 10.0, 10.0)))
+        g = scene.make_uniforms(W4K, H4K, pos=tuple(cam[:3]), yaw=cam[3] + 0.05 * rank, pitch=cam[4], light_count=N_LIGHTS)
+    else:
+        for i in range(N_LIGHTS):
+            lights.setLight(i, engine.PointLight((prng.uniform(-4, 4), prng.uniform(0, 4), prng.uniform(-3, 4)), (10.0, 10.0, 10.0)))
+        g = scene.make_uniforms(W4K, H4K, pos=(0.3, 0.8, 3.5), yaw=0.1 + 0.05 * rank, pitch=-0.2, light_count=N_LIGHTS)
     gb = engine.GBufferResources(ctx, W4K, H4K, with_position=False)
     gpass = engine.SceneToGBufferPass(ctx)
     ssr = engine.ScreenSpaceReflection(ctx, W4K, H4K)
@@ -346,8 +357,9 @@ def main_mesh4k(args, ctx, rank, local_rank, world, device):
             "metric": "shadow cubes + G-buffer + deferred+SSAO+SSR Mpixel/s at 4K, from geometry", "value": world * W4K * H4K / (ms_step * 1e-3) / 1e6, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[2] shape from geometry: %d-triangle procedural mesh scene, 16 point lights; per step: 16 x 6 x 256^2 omni shadow "
-                                   "cubes + 3840x2160 G-buffer (rasterising producers) + SSR + glossy mips + SSAO + deferred shading" % up.triangle_count,
+            "config": {"workload": "configs[2] shape from geometry: %d-triangle %s, 16 point lights; per step: 16 x 6 x 256^2 omni shadow "
+                                   "cubes + 3840x2160 G-buffer (rasterising producers) + SSR + glossy mips + SSAO + deferred shading"
+                                   % (up.triangle_count, ("glTF scene " + os.path.basename(args.model)) if args.model else "procedural mesh scene"),
                        "coverage": cov, "l2_policy": "one frame's attachments (0.3 GB) exceed the 126 MB L2"},
             "gpu_launches": int(launches) * world, "clocks": clocks,
             "stages": {k: {"ms_per_step": v["total_ms"] / args.steps, "launches": v["launches"]} for k, v in kt.items()}}))
@@ -442,6 +454,10 @@ def main():
                     help="views4k (default, the contract benchmark): 4K views sharded by view, weak scaling. bands8k: ONE 7680x4320 "
                          "S-rand frame split in row bands, NCCL broadcast of the G-buffer + all-gather of the bands, strong scaling. mesh4k: a frame from "
                          "geometry (shadow cubes and G-buffer rasterised from a mesh scene, then the deferred chain), one camera per rank")
+    ap.add_argument("--model", default=None, help="mesh4k: render this .glb / .gltf instead of the procedural scene")
+    ap.add_argument("--model-texture-size", type=int, default=1024, help="mesh4k --model: cap on the texture edge")
+    ap.add_argument("--model-camera", default="-8,2,0,-1.5707963,0", help="mesh4k --model: x,y,z,yaw,pitch (default: down Sponza's nave)")
+    ap.add_argument("--model-light-box", default="-12,12,0.5,8,-3,3", help="mesh4k --model: xmin,xmax,ymin,ymax,zmin,zmax for the 16 lights")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-producers", action="store_true")
