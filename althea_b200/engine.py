@@ -14,6 +14,7 @@ althea_b200/host/Althea/*.h.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -392,6 +393,38 @@ class ImageBasedLighting:
         res = IBLResources(env, pre, irr, lut)
         res._chain = chain
         return res
+
+
+    @staticmethod
+    def createResourcesFromContent(ctx: Context, content_dir: str, env_name: str, stream: int = 0) -> IBLResources:
+        """createResources(app, commandBuffer, envMapName) as the reference runs it (ImageBasedLighting.cpp:415-605): the
+        environment map is <content_dir>/HDRI_Skybox/<env_name>.hdr; if any of PrecomputedMaps/<env_name>/IrradianceMap.hdr,
+        Prefiltered1..5.hdr is missing the maps are computed (on the GPU here) and written out; then ALL maps are loaded back from
+        the .hdr files, so the run-time data always carries the files' RGBE quantisation, cache hit or miss. The BRDF LUT is
+        PrecomputedMaps/brdf_lut.png when present (the reference ships it), generated otherwise."""
+        from . import hdr_cache
+        env_path = hdr_cache.environment_map_path(content_dir, env_name)
+        env_rgb = hdr_cache.read_hdr(env_path)
+        env_rgba = np.concatenate([env_rgb, np.ones(env_rgb.shape[:2] + (1,), np.float32)], -1)
+        if not hdr_cache.cache_complete(content_dir, env_name):
+            fresh = ImageBasedLighting.createResources(ctx, env_rgba, lut_size=16, stream=stream)
+            ctx.synchronize()
+            hdr_cache.save_precomputed_maps(content_dir, env_name, fresh.irradianceMap, fresh.prefilteredMap)
+            del fresh
+        irr, pre = hdr_cache.load_precomputed_maps(content_dir, env_name)
+        F32 = _capi.FORMAT_R32G32B32A32_SFLOAT
+        env = ctx.image_from_numpy(env_rgba, F32, env_rgba.shape[1], env_rgba.shape[0])
+        irr_img = ctx.image_from_numpy(irr, F32, irr.shape[1], irr.shape[0])
+        pre_img = ctx.image_from_numpy(np.concatenate([p.reshape(-1) for p in pre]), F32, pre[0].shape[1], pre[0].shape[0], len(pre))
+        lut_path = os.path.join(content_dir, "PrecomputedMaps", "brdf_lut.png")
+        if os.path.exists(lut_path):
+            from PIL import Image as PILImage
+            lut_np = np.ascontiguousarray(np.asarray(PILImage.open(lut_path).convert("RGBA"), np.uint8))
+            lut = ctx.image_from_numpy(lut_np, _capi.FORMAT_R8G8B8A8_UNORM, lut_np.shape[1], lut_np.shape[0])
+        else:
+            lut = ctx.new_image(_capi.FORMAT_R8G8B8A8_UNORM, 512, 512)
+            ImageBasedLighting.generateBrdfLut(ctx, lut, stream=stream)
+        return IBLResources(env, pre_img, irr_img, lut)
 
 
 class ReflectionBuffer:

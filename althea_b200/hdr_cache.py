@@ -99,6 +99,14 @@ def cache_complete(content_dir: str, env_name: str) -> bool:
     return os.path.exists(irr) and all(os.path.exists(p) for p in pre)
 
 
+def environment_map_path(content_dir: str, env_name: str) -> str:
+    """<content_dir>/HDRI_Skybox/<env_name>.hdr; missing => the reference's error (ImageBasedLighting.cpp:421-425)."""
+    p = os.path.join(content_dir, "HDRI_Skybox", env_name + ".hdr")
+    if not os.path.exists(p):
+        raise RuntimeError("Specified environment map does not exist!")
+    return p
+
+
 def save_precomputed_maps(content_dir: str, env_name: str, irradiance, prefiltered) -> None:
     """Downloads the CUDA-generated maps (engine.Image objects, RGBA32F; prefiltered = 5 mips) and writes the six files."""
     irr_path, pre_paths = cache_paths(content_dir, env_name)

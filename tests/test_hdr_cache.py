@@ -206,3 +206,73 @@ int main(int argc, char** argv) {
     r = subprocess.run([str(exe), golden, out], check=True, capture_output=True, text=True)
     assert r.stdout.split() == ["300", "24"]
     assert _payload(open(out, "rb").read()) == _payload(open(golden, "rb").read())
+
+
+# ---- createResources(envMapName): the reference's cache-or-compute flow, host logic on CPU --------------------------------
+class _FakeImage:
+    def __init__(self, arr, fmt, w, h, mips):
+        self.arr, self.format, self.w, self.h, self.mips = np.asarray(arr), fmt, w, h, mips
+
+    def level_numpy(self, k):
+        off = sum(max(1, self.w >> i) * max(1, self.h >> i) * 4 for i in range(k))
+        n = max(1, self.w >> k) * max(1, self.h >> k) * 4
+        return self.arr.reshape(-1)[off:off + n].copy()
+
+
+class _FakeCtx:
+    """Stands in for engine.Context where only host-side bookkeeping is exercised (no CUDA on this machine)."""
+
+    def __init__(self):
+        self.images, self.syncs = [], 0
+
+    def image_from_numpy(self, arr, fmt, w, h, mips=1, layers=1):
+        self.images.append(_FakeImage(arr, fmt, w, h, mips))
+        return self.images[-1]
+
+    def synchronize(self, stream=0):
+        self.syncs += 1
+
+
+def test_create_resources_from_content_follows_the_reference_flow(tmp_path, monkeypatch):
+    """ImageBasedLighting.cpp:415-446: missing env map -> the reference's error; incomplete cache -> compute, write the six files,
+    then load everything back from disk; complete cache -> no compute at all. The GPU work is stubbed out here (it is covered by
+    test_cache_round_trip_on_gpu and test_ibl_parity); what is checked is which files are read and written and what reaches the
+    device."""
+    from PIL import Image as PILImage
+
+    from althea_b200 import _capi, engine
+    content = str(tmp_path / "Content")
+    ctx = _FakeCtx()
+    with pytest.raises(RuntimeError, match="Specified environment map does not exist"):
+        engine.ImageBasedLighting.createResourcesFromContent(ctx, content, "Studio")
+    rs = np.random.default_rng(2)
+    env = np.exp(rs.uniform(-3, 3, (32, 64, 3))).astype(np.float32)
+    hdr_cache.write_hdr(os.path.join(content, "HDRI_Skybox", "Studio.hdr"), env)
+    lut = rs.integers(0, 256, (8, 8, 4), dtype=np.uint8)
+    lut[..., 3] = 255
+    os.makedirs(os.path.join(content, "PrecomputedMaps"), exist_ok=True)
+    PILImage.fromarray(lut, "RGBA").save(os.path.join(content, "PrecomputedMaps", "brdf_lut.png"))
+    computed = []
+
+    def fake_create(c, env_rgba, brdf_lut_rgba8=None, lut_size=512, stream=0):
+        computed.append(env_rgba.shape)
+        H, W = env_rgba.shape[:2]
+        irr = _FakeImage(np.full((H, W, 4), 0.25, np.float32), 0, W, H, 1)
+        pre = _FakeImage(np.concatenate([np.full((H >> (k + 1)) * (W >> (k + 1)) * 4, 0.5 + k, np.float32) for k in range(5)]), 0, W >> 1, H >> 1, 5)
+        return engine.IBLResources(None, pre, irr, None)
+
+    monkeypatch.setattr(engine.ImageBasedLighting, "createResources", staticmethod(fake_create))
+    res = engine.ImageBasedLighting.createResourcesFromContent(ctx, content, "Studio")
+    assert computed == [(32, 64, 4)] and ctx.syncs == 1 and hdr_cache.cache_complete(content, "Studio")
+    env_img, irr_img, pre_img, lut_img = ctx.images
+    assert (env_img.w, env_img.h, env_img.mips) == (64, 32, 1) and (irr_img.w, irr_img.h) == (64, 32)
+    assert (pre_img.w, pre_img.h, pre_img.mips) == (32, 16, 5) and pre_img.arr.size == sum((16 >> k) * (32 >> k) * 4 for k in range(5))
+    assert np.array_equal(env_img.arr[..., :3], hdr_cache.read_hdr(os.path.join(content, "HDRI_Skybox", "Studio.hdr")))
+    assert np.allclose(irr_img.arr[..., :3], 0.25) and (irr_img.arr[..., 3] == 1).all()          # 0.25 is exact in RGBE
+    assert pre_img.arr[0] == 0.5 and pre_img.arr[-4] == 4.5
+    assert lut_img.format == _capi.FORMAT_R8G8B8A8_UNORM and np.array_equal(lut_img.arr, lut)
+    assert res.irradianceMap is irr_img and res.prefilteredMap is pre_img
+    # second call: the cache is complete, nothing is computed
+    ctx2 = _FakeCtx()
+    engine.ImageBasedLighting.createResourcesFromContent(ctx2, content, "Studio")
+    assert computed == [(32, 64, 4)] and ctx2.syncs == 0 and len(ctx2.images) == 4
