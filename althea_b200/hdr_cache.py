@@ -45,15 +45,8 @@ def rgbe_to_float(rgbe: np.ndarray) -> np.ndarray:
 
 
 def _host():
-    from . import model
-    lib = model._host()
-    if not getattr(lib, "_hdr_bound", False):
-        import ctypes as C
-        lib.althea_host_save_hdri.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_void_p]
-        lib.althea_host_load_hdri_info.argtypes = [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
-        lib.althea_host_load_hdri.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64]
-        lib._hdr_bound = True
-    return lib
+    from . import _hostapi
+    return _hostapi.load()
 
 
 def write_hdr(path: str, rgba: np.ndarray) -> None:

@@ -244,22 +244,10 @@ def _node_matrix(node) -> np.ndarray:
     return m
 
 
-_host_lib = None
-
-
 def _host():
-    """althea_b200/lib/libalthea_host.so (include/althea_host.h); built on first use, a missing compiler is an error."""
-    global _host_lib
-    if _host_lib is None:
-        import ctypes as C
-        from .host import build_host
-        lib = C.CDLL(build_host.build_lib())
-        if lib.althea_host_abi_version() != 1:
-            raise RuntimeError("libalthea_host.so: ABI version mismatch")
-        lib.althea_host_compute_flat_normals.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
-        lib.althea_host_compute_tangent_space.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
-        _host_lib = lib
-    return _host_lib
+    """The host-side library (include/althea_host.h), bound in _hostapi.py."""
+    from . import _hostapi
+    return _hostapi.load()
 
 
 def compute_flat_normals(pos) -> np.ndarray:
@@ -469,7 +457,6 @@ def point_light_constants() -> _capi.PointLightConstants:
     reference's class built against its GLM, including the rounding noise of sin/cos at 180 and +-90 degrees that orients the
     +-Y faces (tests/test_camera_pin.py)."""
     lib = _host()
-    lib.althea_host_point_light_constants.argtypes = [C.c_void_p]
     pc = _capi.PointLightConstants()
     assert C.sizeof(pc) == 14 * 64
     if lib.althea_host_point_light_constants(C.addressof(pc)) != 0:
@@ -481,7 +468,6 @@ def camera_matrices(fov_degrees: float, aspect: float, near: float, far: float, 
     """The reference's Camera (Src/Camera.cpp:7-110) for one pose: (projection, transform, view, inverse projection), each a
     (4, 4) float32 array in glm's column-major storage (row i of the array is column i of the matrix)."""
     lib = _host()
-    lib.althea_host_camera.argtypes = [C.c_float] * 4 + [C.c_void_p, C.c_float, C.c_float] + [C.c_void_p] * 4
     pos = np.ascontiguousarray(position, np.float32)
     out = [np.zeros((4, 4), np.float32) for _ in range(4)]
     if lib.althea_host_camera(fov_degrees, aspect, near, far, pos.ctypes.data, yaw, pitch, *[o.ctypes.data for o in out]) != 0:

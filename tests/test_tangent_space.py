@@ -54,6 +54,14 @@ def test_host_library_exports_what_the_header_declares():
                         "althea_host_point_light_constants"}
     exported = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
     assert set(re.findall(r"\bT (althea_host_\w+)", exported)) == declared
+    from althea_b200 import _hostapi
+    assert set(_hostapi.SIGNATURES) == declared                    # header == binding == exports
+    for name, (_, args) in _hostapi.SIGNATURES.items():           # and the same number of parameters as the C prototype
+        proto = re.search(r"^int\s+%s\s*\(([^;]*?)\)\s*;" % name, header, re.S | re.M).group(1)
+        proto = re.sub(r"/\*.*?\*/", "", proto, flags=re.S).strip()
+        n = 0 if proto in ("", "void") else proto.count(",") + 1
+        assert n == len(args), name
+    assert _hostapi.load().althea_host_abi_version() == _hostapi.ABI_VERSION
     # plain C: the header compiles as C99 on its own
     subprocess.run(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
                     os.path.join(ROOT, "include", "althea_host.h")], check=True)
