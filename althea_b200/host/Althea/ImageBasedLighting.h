@@ -1,8 +1,12 @@
 // Include/Althea/ImageBasedLighting.h:17-54: IBLResources + namespace ImageBasedLighting::createResources.
 #pragma once
 #include "CudaApplication.h"
+#include "Utilities.h"
 
 #include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
 
 namespace AltheaEngine {
 
@@ -41,6 +45,81 @@ inline IBLResources createResources(const CudaApplication& app, const float* env
     app.check(althea_cuda_brdf_lut(app.ctx(), 1024, r.brdfLut.handle(), nullptr), "althea_cuda_brdf_lut");
   }
   app.waitIdle(); // `chain` is released on return
+  return r;
+}
+
+inline bool fileExists(const std::string& path) {
+  if (FILE* f = std::fopen(path.c_str(), "rb")) {
+    std::fclose(f);
+    return true;
+  }
+  return false;
+}
+
+// createResources(app, commandBuffer, envMapName) as the reference runs it (Src/ImageBasedLighting.cpp:415-605):
+// <contentDir>/HDRI_Skybox/<envMapName>.hdr must exist; when any of PrecomputedMaps/<envMapName>/IrradianceMap.hdr,
+// Prefiltered1..5.hdr is missing the maps are computed and saved (Utilities::saveHdri); then every map is loaded back from
+// its file (Utilities::loadHdri), so the run-time data carries the files' RGBE quantisation on a cache hit and on a miss.
+// The BRDF LUT asset is a PNG in the reference; this mirror has no PNG decoder, the caller passes the decoded texels or
+// gets the generated table.
+inline IBLResources createResources(const CudaApplication& app, const std::string& contentDir, const std::string& envMapName,
+                                    const uint8_t* brdfLutRgba8 = nullptr, uint32_t lutSize = 512) {
+  const std::string envFile = contentDir + "/HDRI_Skybox/" + envMapName + ".hdr";
+  if (!fileExists(envFile)) throw std::runtime_error("Specified environment map does not exist!");
+  const std::string dir = contentDir + "/PrecomputedMaps/" + envMapName + "/";
+  std::string prefiltered[5];
+  bool needToPrecomputeIBL = false;
+  for (int i = 0; i < 5; ++i) {
+    prefiltered[i] = dir + "Prefiltered" + std::to_string(i + 1) + ".hdr";
+    needToPrecomputeIBL |= !fileExists(prefiltered[i]);
+  }
+  const std::string irradiance = dir + "IrradianceMap.hdr";
+  needToPrecomputeIBL |= !fileExists(irradiance);
+
+  Utilities::ImageFile env;
+  Utilities::loadHdri(envFile, env);
+  const uint32_t W = (uint32_t)env.width, H = (uint32_t)env.height;
+  if (needToPrecomputeIBL) { // the directory must exist, as in the reference
+    IBLResources fresh = createResources(app, reinterpret_cast<const float*>(env.data.data()), W, H, nullptr, 16);
+    std::vector<std::byte> texels((size_t)W * H * 16);
+    fresh.irradianceMap.download(texels.data(), texels.size());
+    app.waitIdle();
+    Utilities::saveHdri(irradiance, (int)W, (int)H, texels.data(), texels.size());
+    std::vector<std::byte> chain(fresh.prefilteredMap.byteSize());
+    fresh.prefilteredMap.download(chain.data(), chain.size());
+    app.waitIdle();
+    size_t offset = 0;
+    for (int i = 0; i < 5; ++i) {
+      const uint32_t w = (W / 2) >> i ? (W / 2) >> i : 1, h = (H / 2) >> i ? (H / 2) >> i : 1;
+      Utilities::saveHdri(prefiltered[i], (int)w, (int)h, chain.data() + offset, (size_t)w * h * 16);
+      offset += (size_t)w * h * 16;
+    }
+  }
+
+  IBLResources r;
+  r.environmentMap = ImageResource(app, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, W, H);
+  r.environmentMap.upload(env.data.data(), env.data.size());
+  Utilities::ImageFile irr;
+  Utilities::loadHdri(irradiance, irr);
+  r.irradianceMap = ImageResource(app, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, (uint32_t)irr.width, (uint32_t)irr.height);
+  r.irradianceMap.upload(irr.data.data(), irr.data.size());
+  std::vector<std::byte> levels;
+  uint32_t w0 = 0, h0 = 0;
+  for (int i = 0; i < 5; ++i) {
+    Utilities::ImageFile level;
+    Utilities::loadHdri(prefiltered[i], level);
+    if (i == 0) { w0 = (uint32_t)level.width; h0 = (uint32_t)level.height; }
+    levels.insert(levels.end(), level.data.begin(), level.data.end());
+  }
+  r.prefilteredMap = ImageResource(app, ALTHEA_FORMAT_R32G32B32A32_SFLOAT, w0, h0, 5);
+  if (levels.size() != r.prefilteredMap.byteSize()) throw std::runtime_error("Prefiltered1..5.hdr do not form a 5-level mip chain");
+  r.prefilteredMap.upload(levels.data(), levels.size());
+  r.brdfLut = ImageResource(app, ALTHEA_FORMAT_R8G8B8A8_UNORM, lutSize, lutSize);
+  if (brdfLutRgba8)
+    r.brdfLut.upload(brdfLutRgba8, (size_t)lutSize * lutSize * 4);
+  else
+    app.check(althea_cuda_brdf_lut(app.ctx(), 1024, r.brdfLut.handle(), nullptr), "althea_cuda_brdf_lut");
+  app.waitIdle();
   return r;
 }
 } // namespace ImageBasedLighting

@@ -276,3 +276,23 @@ def test_create_resources_from_content_follows_the_reference_flow(tmp_path, monk
     ctx2 = _FakeCtx()
     engine.ImageBasedLighting.createResourcesFromContent(ctx2, content, "Studio")
     assert computed == [(32, 64, 4)] and ctx2.syncs == 0 and len(ctx2.images) == 4
+
+
+def test_cpp_mirror_create_resources_by_name_compiles(tmp_path):
+    """The C++ twin of createResourcesFromContent (host/Althea/ImageBasedLighting.h): reference signature shape
+    createResources(app, ..., envMapName), built on Utilities::loadHdri / saveHdri. Compile check (running it needs a GPU; the
+    pieces it calls are covered by demo_frame's GPU test and by the Utilities test above)."""
+    import subprocess
+
+    from helpers import ROOT
+    src = tmp_path / "ibl_probe.cpp"
+    src.write_text('''
+#include "Althea/ImageBasedLighting.h"
+using namespace AltheaEngine;
+uint64_t probe(const CudaApplication& app) {
+  IBLResources r = ImageBasedLighting::createResources(app, "/srv/Content", "LuxuryRoom");
+  return r.getHandles().irradiance;
+}
+''')
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                    "-I", os.path.join(ROOT, "althea_b200", "host"), str(src)], check=True)
