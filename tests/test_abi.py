@@ -91,3 +91,15 @@ int main(void) {
     assert [int(v) for v in a.split()] == [_capi.VERTEX_BYTES, C.sizeof(_capi.TextureRef), C.sizeof(M), C.sizeof(P), C.sizeof(_capi.PointLightConstants),
                                            P.model.offset, P.material.offset, M.baseTexture.offset]
     assert [int(v) for v in b.split()] == [416, 32, C.sizeof(_capi.GBuffer), C.sizeof(_capi.Sync)]
+
+
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md section 7 indexes every symbol of both headers (prefix-abbreviated rows such as `_destroy` count)."""
+    import re
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for header, prefix in (("althea_cuda.h", "althea_cuda"), ("althea_host.h", "althea_host")):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        names = set(re.findall(r"\b(%s_\w+)\s*\(" % prefix, text))
+        for name in names:
+            short = name[len(prefix):]
+            assert name in doc or ("`%s`" % short) in doc, name
