@@ -26,6 +26,7 @@ from helpers import FrameData  # noqa: E402
 
 SPAN = 8
 C = 0.999
+PYRAMID = False   # True: bounds from a min/max mip pyramid (2 x 2 blocks of one level) instead of an exact sliding window
 
 
 def view_ray(g, u, v):
@@ -97,7 +98,23 @@ def study(kind, W, H):
     # conservative scene depth range over a span's footprint: a square filter as large as the span can reach, plus the
     # bilinear footprint
     size = int(np.ceil(SPAN * 0.005 * max(W, H))) + 3
-    dmin, dmax = minimum_filter(depth, size=size, mode="nearest"), maximum_filter(depth, size=size, mode="nearest")
+    if PYRAMID:
+        # what a kernel would have: a min/max mip pyramid; a window of `size` texels is covered by the 2 x 2 blocks of the level
+        # whose blocks are at least that large, i.e. a sliding (2 * block)-sized window aligned to the block grid
+        level = int(np.ceil(np.log2(size)))
+        blk = 1 << level
+        hb, wb = -(-H // blk), -(-W // blk)
+        pad = np.pad(depth, ((0, hb * blk - H), (0, wb * blk - W)), mode="edge")
+        bmin = pad.reshape(hb, blk, wb, blk).min(axis=(1, 3))
+        bmax = pad.reshape(hb, blk, wb, blk).max(axis=(1, 3))
+        # block pair starting at the block that holds (centre - blk / 2)
+        def lookup(b, my, mx, red):
+            y0 = np.clip((my - blk // 2) // blk, 0, hb - 1)
+            x0 = np.clip((mx - blk // 2) // blk, 0, wb - 1)
+            y1, x1 = np.minimum(y0 + 1, hb - 1), np.minimum(x0 + 1, wb - 1)
+            return red(red(b[y0, x0], b[y0, x1]), red(b[y1, x0], b[y1, x1]))
+    else:
+        dmin, dmax = minimum_filter(depth, size=size, mode="nearest"), maximum_filter(depth, size=size, mode="nearest")
     spans = skipped = wrong = taps_total = taps_skipped = 0
     for s0 in range(0, 128, SPAN):
         alive = valid & (steps > s0)                      # pixels whose march reaches this span
@@ -106,7 +123,10 @@ def study(kind, W, H):
         mid = uv0 + step * (s0 + 1 + (SPAN - 1) / 2.0)
         mx = np.clip((mid[..., 0] * W).astype(int), 0, W - 1)
         my = np.clip((mid[..., 1] * H).astype(int), 0, H - 1)
-        lo_d, hi_d = dmin[my, mx], dmax[my, mx]
+        if PYRAMID:
+            lo_d, hi_d = lookup(bmin, my, mx, np.minimum), lookup(bmax, my, mx, np.maximum)
+        else:
+            lo_d, hi_d = dmin[my, mx], dmax[my, mx]
         hit_free = alive.copy()
         any_candidate = np.zeros((H, W), bool)
         for k in range(SPAN):
@@ -130,8 +150,8 @@ def study(kind, W, H):
         wrong += (hit_free & any_candidate).sum()
         taps_total += n_taps[alive].sum()
         taps_skipped += n_taps[hit_free].sum()
-    print("%s %dx%d: %d-step spans proven hit-free %.1f %% (taps saved %.1f %%, minus one re-seed tap per skipped span: %.1f %%); "
-          "unsound proofs: %d" % (kind, W, H, SPAN, 100.0 * skipped / spans, 100.0 * taps_skipped / taps_total,
+    print("%s%s %dx%d: %d-step spans proven hit-free %.1f %% (taps saved %.1f %%, minus one re-seed tap per skipped span: %.1f %%); "
+          "unsound proofs: %d" % (kind, " (pyramid)" if PYRAMID else "", W, H, SPAN, 100.0 * skipped / spans, 100.0 * taps_skipped / taps_total,
                                   100.0 * (taps_skipped - skipped) / taps_total, wrong))
     return wrong
 
@@ -139,4 +159,6 @@ def study(kind, W, H):
 if __name__ == "__main__":
     W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (384, 216)
     bad = study("scene", W, H) + study("rand", W // 2, H // 2)
+    PYRAMID = True
+    bad += study("scene", W, H)
     sys.exit(1 if bad else 0)
