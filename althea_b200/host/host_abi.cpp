@@ -1,6 +1,8 @@
 // C ABI over the header-only host mirrors (include/althea_host.h). Built by build_host.build_lib() with plain g++.
 #include "althea_host.h"
 
+#include <exception>
+
 #include "Althea/Camera.h"
 #include "Althea/GeometryUtilities.h"
 #include "Althea/Utilities.h"
@@ -31,8 +33,14 @@ int althea_host_compute_tangent_space(const float* position, const float* normal
                                       float* tangent_out, float* bitangent_out) {
   if (!position || !normal || !uv || !tangent_out || !bitangent_out) return -1;
   if (face_count == 0) return 0;
-  std::vector<float> sign(face_count * 3);
-  generate(position, normal, uv, (size_t)face_count, tangent_out, sign.data());
+  if (face_count > 0x55555555ull) return -1; // corner indices are 32-bit
+  std::vector<float> sign;
+  try {
+    sign.resize(face_count * 3);
+    generate(position, normal, uv, (size_t)face_count, tangent_out, sign.data());
+  } catch (const std::exception&) { // out of memory: nothing may cross the C boundary
+    return -2;
+  }
   for (uint64_t c = 0; c < face_count * 3; ++c) {
     const float* N = normal + 3 * c;
     const float* T = tangent_out + 3 * c;

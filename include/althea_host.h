@@ -19,7 +19,8 @@
  *                                         althea_cuda_draw_shadow_cubes)
  *
  * Geometry inputs are de-indexed triangle lists, three consecutive vertices per face, tightly packed floats, exactly what
- * Primitive.cpp hands over after duplicating vertices (:147). Returns 0 on success, -1 on a null pointer.
+ * Primitive.cpp hands over after duplicating vertices (:147). Returns 0 on success, -1 on a null pointer or an impossible
+ * size, -2 when memory runs out.
  */
 #ifndef ALTHEA_HOST_H
 #define ALTHEA_HOST_H
