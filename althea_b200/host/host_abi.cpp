@@ -69,7 +69,11 @@ static int loadHdri(const char* path, int32_t* width, int32_t* height, std::vect
     return -2;
   }
   int w = 0, h = 0;
-  if (!AltheaEngine::Utilities::decodeHdri(file.data(), file.size(), w, h, rgba)) return -3;
+  try {
+    if (!AltheaEngine::Utilities::decodeHdri(file.data(), file.size(), w, h, rgba)) return -3;
+  } catch (const std::exception&) { // a header announcing more texels than memory holds
+    return -3;
+  }
   *width = w;
   *height = h;
   return 0;
