@@ -468,3 +468,22 @@ def test_prefilter_against_a_float64_evaluation(roughness):
         col = _env_lookup64(levels, L[use], mip[use]) * NdotL[use, None]
         want = col.sum(0) / NdotL[use].sum()
         assert np.abs(g[:3] - want).max() < 5e-5 * np.abs(want).max(), (x, y, roughness, g[:3], want)   # observed 3e-6
+
+
+def test_ssr_span_skip_proof_is_sound_on_a_small_frame():
+    """tools/ssr_skip_study.py (the plan of DESIGN.md section 8 item 2): the conservative proof never declares a span hit-free that
+    contains a step with f > 0.999, with window bounds and with pyramid bounds."""
+    import importlib
+    import os
+    import sys
+
+    from helpers import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    study = importlib.import_module("ssr_skip_study")
+    try:
+        study.PYRAMID = False
+        assert study.study("scene", 96, 54) == 0
+        study.PYRAMID = True
+        assert study.study("scene", 96, 54) == 0
+    finally:
+        study.PYRAMID = False
