@@ -24,6 +24,7 @@ CTX_PARITY_MATH = 1
 CTX_SSAO_EXACT_TAPS = 2
 CTX_SSAO_COUNT_TAPS = 4
 CTX_SSAO_RAY_DEPTH_PROXY = 8
+CTX_SSAO_NO_CULL = 16
 SHADE_SKIP_TONEMAP = 1
 SHADE_NO_SSAO = 2
 SHADE_AO_FROM_IMAGE = 4
@@ -103,6 +104,7 @@ SYMBOLS = {
     "althea_cuda_launch_count": (C.c_uint64, [C.c_void_p]),
     "althea_cuda_diag_ssao_gathers": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "althea_cuda_diag_ssao_exact_fallbacks": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "althea_cuda_diag_ssao_cull": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "althea_cuda_diag_gather_ceiling": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]),
     "althea_cuda_image_bytes": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "althea_cuda_import_image": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,

@@ -65,7 +65,10 @@ struct althea_cuda_ctx {
   void* quadScratch = nullptr;
   size_t quadScratchBytes = 0;
   struct RasterScratch* raster = nullptr; // scratch of the rasterising producers (draw_gbuffer / draw_shadow_cubes)
-  unsigned long long* gatherCounter = nullptr; // device counter of the ALTHEA_CTX_SSAO_COUNT_TAPS diagnostic
+  unsigned long long* gatherCounter = nullptr; // device counters (4) of the ALTHEA_CTX_SSAO_COUNT_TAPS diagnostic
+  // internal scratch: SSAO plane records (three levels, padded) and the per-tile hand-over flags of the cull kernel
+  void* planeScratch = nullptr;
+  size_t planeScratchBytes = 0;
   // internal scratch: SSR padded depth, (W+2) x (H+2) floats (frame_kernels.cu, ssr_depth_pad_kernel)
   void* depthPadScratch = nullptr;
   size_t depthPadScratchBytes = 0;
@@ -353,6 +356,20 @@ int fillFrameParams(althea_cuda_ctx* ctx, const althea_global_uniforms* u, const
     }
     auto dotf = [](const float* a, const float* b) { return (double)a[0] * b[0] + (double)a[1] * b[1] + (double)a[2] * b[2]; };
     P->ssaoGram[0] = (float)dotf(P->ssaoDc, P->ssaoDc); P->ssaoGram[1] = (float)dotf(P->ssaoDx, P->ssaoDx); P->ssaoGram[2] = (float)dotf(P->ssaoDy, P->ssaoDy);
+    { // constants of the SSAO coarse sign test (frame_kernels.cu, ssao_cull_kernel)
+      auto l1 = [](const float* a) { return fabs((double)a[0]) + fabs((double)a[1]) + fabs((double)a[2]); };
+      double dmax = 0.0; // |D|_1 is convex in (x, y): its maximum over the image sits at a corner
+      for (int c = 0; c < 4; ++c) {
+        const double cx = (c & 1) ? P->W - 1 : 0, cy = (c & 2) ? P->H - 1 : 0;
+        double v = 0.0;
+        for (int r = 0; r < 3; ++r) v += fabs((double)P->ssaoDc[r] + (double)P->ssaoDx[r] * cx + (double)P->ssaoDy[r] * cy);
+        dmax = std::max(dmax, v);
+      }
+      P->ssaoDmax1 = (float)(dmax * 1.0001);
+      P->ssaoDmag = (float)((l1(P->ssaoDc) + l1(P->ssaoDx) * P->W + l1(P->ssaoDy) * P->H) * 1.0001);
+      P->ssaoCamL1 = (float)(l1(P->ssaoCam) * 1.0001);
+      P->ssaoFocalPx = (float)std::max(0.5 * P->W * fabs((double)u->projection[0]), 0.5 * P->H * fabs((double)u->projection[5]));
+    }
     P->ssaoGram[3] = (float)(2.0 * dotf(P->ssaoDc, P->ssaoDx)); P->ssaoGram[4] = (float)(2.0 * dotf(P->ssaoDc, P->ssaoDy)); P->ssaoGram[5] = (float)(2.0 * dotf(P->ssaoDx, P->ssaoDy));
   }
   if (ctx->scissorY1) {
@@ -438,6 +455,7 @@ void althea_cuda_destroy(althea_cuda_ctx* ctx) {
   if (ctx->aoScratch) cudaFree(ctx->aoScratch);
   if (ctx->positionScratch) cudaFree(ctx->positionScratch);
   if (ctx->quadScratch) cudaFree(ctx->quadScratch);
+  if (ctx->planeScratch) cudaFree(ctx->planeScratch);
   if (ctx->depthPadScratch) cudaFree(ctx->depthPadScratch);
   if (ctx->gatherCounter) cudaFree(ctx->gatherCounter);
   freeRasterScratch(ctx->raster);
@@ -832,16 +850,46 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
     P.quadPitch = ((size_t)P.W + 1) * (P.quadKind ? 16 : 32);
     P.quadsOrigin = static_cast<const char*>(ctx->quadScratch) + ((size_t)P.quadRow + 1) * (P.quadKind ? 16 : 32);
   }
+  // the coarse sign test needs a perspective camera's G-buffer model (it degrades to the march tile by tile when the
+  // positions do not fit it) and the position records; the ray-depth records keep their own march
+  const bool cull = computeAo && !exactTaps && !(ctx->flags & (ALTHEA_CTX_SSAO_NO_CULL | ALTHEA_CTX_SSAO_RAY_DEPTH_PROXY));
+  P.ssaoTileList = nullptr;
+  P.ssaoRecip = nullptr;
+  if (cull) {
+    size_t need = 0, off[3];
+    for (int l = 0; l < 3; ++l) {
+      const int S = 8 << l;
+      P.ssaoPlaneNx[l] = (P.W + S - 1) / S;
+      P.ssaoPlaneNy[l] = (P.H + S - 1) / S;
+      P.ssaoPlaneRow[l] = P.ssaoPlaneNx[l] + 2 * kSsaoPlanePad + 1;
+      off[l] = need;
+      need += (size_t)P.ssaoPlaneRow[l] * (P.ssaoPlaneNy[l] + 2 * kSsaoPlanePad + 1) * 16;
+    }
+    const size_t listOff = need;
+    need += ((size_t)((P.W + 15) / 16) * ((P.H + 15) / 16) + 1) * sizeof(unsigned);
+    const size_t recipOff = (need + 255) & ~(size_t)255;
+    need = recipOff + (size_t)P.W * P.H * sizeof(float);
+    if (ctx->planeScratchBytes < need) {
+      if (ctx->planeScratch) { cudaDeviceSynchronize(); cudaFree(ctx->planeScratch); ctx->planeScratch = nullptr; ctx->planeScratchBytes = 0; }
+      cudaError_t e = cudaMalloc(&ctx->planeScratch, need);
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(ssao plane scratch %zu): %s", need, cudaGetErrorString(e)); }
+      ctx->planeScratchBytes = need;
+    }
+    for (int l = 0; l < 3; ++l)
+      P.ssaoPlanes[l] = reinterpret_cast<const float4*>(static_cast<const char*>(ctx->planeScratch) + off[l]) + ((size_t)kSsaoPlanePad * P.ssaoPlaneRow[l] + kSsaoPlanePad);
+    P.ssaoTileList = reinterpret_cast<unsigned*>(static_cast<char*>(ctx->planeScratch) + listOff);
+    P.ssaoRecip = reinterpret_cast<float*>(static_cast<char*>(ctx->planeScratch) + recipOff);
+  }
   if (computeAo && !exactTaps && (ctx->flags & ALTHEA_CTX_SSAO_COUNT_TAPS)) {
     if (!ctx->gatherCounter) {
-      cudaError_t e = cudaMalloc(&ctx->gatherCounter, 2 * sizeof(unsigned long long));
+      cudaError_t e = cudaMalloc(&ctx->gatherCounter, 4 * sizeof(unsigned long long));
       if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(gather counter): %s", cudaGetErrorString(e)); }
     }
     P.gatherCounter = ctx->gatherCounter;
   }
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
-  if (P.gatherCounter) cudaMemsetAsync(P.gatherCounter, 0, 2 * sizeof(unsigned long long), stream);
+  if (P.gatherCounter) cudaMemsetAsync(P.gatherCounter, 0, 4 * sizeof(unsigned long long), stream);
   if (reconstruct)
     timedLaunch(ctx, "reconstruct_position", stream, [&] { parity ? althea_parity::launch_reconstruct_position(P, stream) : althea_fast::launch_reconstruct_position(P, stream); });
   if (computeAo) {
@@ -849,6 +897,10 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
       timedLaunch(ctx, "ssao_exact", stream, [&] { parity ? althea_parity::launch_ssao_exact(P, stream) : althea_fast::launch_ssao_exact(P, stream); });
     } else {
       timedLaunch(ctx, "ssao_quads", stream, [&] { parity ? althea_parity::launch_ssao_quads(P, stream) : althea_fast::launch_ssao_quads(P, stream); });
+      if (cull) {
+        timedLaunch(ctx, "ssao_planes", stream, [&] { parity ? althea_parity::launch_ssao_planes(P, stream) : althea_fast::launch_ssao_planes(P, stream); });
+        timedLaunch(ctx, "ssao_cull", stream, [&] { parity ? althea_parity::launch_ssao_cull(P, stream) : althea_fast::launch_ssao_cull(P, stream); });
+      }
       timedLaunch(ctx, "ssao", stream, [&] { parity ? althea_parity::launch_ssao(P, stream) : althea_fast::launch_ssao(P, stream); });
     }
   }
@@ -979,6 +1031,16 @@ int althea_cuda_diag_ssao_exact_fallbacks(althea_cuda_ctx* ctx, uint64_t* out_ta
   unsigned long long v = 0;
   CUDA_TRY(ctx, cudaMemcpy(&v, ctx->gatherCounter + 1, sizeof v, cudaMemcpyDeviceToHost));
   *out_taps = v;
+  return ALTHEA_OK;
+}
+
+int althea_cuda_diag_ssao_cull(althea_cuda_ctx* ctx, uint64_t out_counts[4]) {
+  if (!ctx || !out_counts) return ALTHEA_ERR_INVALID_ARGUMENT;
+  if (!ctx->gatherCounter) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "no SSAO launch has run with ALTHEA_CTX_SSAO_COUNT_TAPS set");
+  CUDA_TRY(ctx, cudaDeviceSynchronize());
+  unsigned long long v[4] = {0, 0, 0, 0};
+  CUDA_TRY(ctx, cudaMemcpy(v, ctx->gatherCounter, sizeof v, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 4; ++k) out_counts[k] = v[k];
   return ALTHEA_OK;
 }
 

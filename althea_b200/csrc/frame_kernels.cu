@@ -510,6 +510,7 @@ __global__ void __launch_bounds__(256) ssao_exact_kernel(const __grid_constant__
 // T (rounded up) = 2 (sqrt(3) E + slop * max|p|_1 + tiny): everything of the sign-decision threshold that does not depend
 // on the shaded pixel, E being the bound on the per-component error of the decoded polynomial against the four fp32 texels.
 struct __align__(32) QuadRecord { uint32_t w[8]; };
+constexpr float kPlaneErr = 3.0e-6f; // SSAO plane records (below): model error allowed per texel of a decidable block, relative to |p|_1 + |cam|_1
 
 constexpr float kSqrt3Up = 1.7320509f;
 // fp32 rounding slop, as a multiple of the coordinate magnitude in play: both the restatement's evaluation and the
@@ -538,6 +539,19 @@ __global__ void __launch_bounds__(256) ssao_quads_kernel(const __grid_constant__
   const int j0 = AddrClamp::wrap(qy - 1, P.H), j1 = AddrClamp::wrap(qy, P.H);
   const V4 p00 = FmtRGBA32F::load(P.position, i0, j0), p10 = FmtRGBA32F::load(P.position, i1, j0);
   const V4 p01 = FmtRGBA32F::load(P.position, i0, j1), p11 = FmtRGBA32F::load(P.position, i1, j1);
+  if (P.ssaoRecip && qx < P.W && qy < P.H) { // this thread's p11 is texel (qx, qy): its reciprocal eye depth for ssao_planes_kernel
+    const V3 cam = mk3(P.ssaoCam[0], P.ssaoCam[1], P.ssaoCam[2]);
+    const float t = dot3(xyz(p11) - cam, mk3(P.ssaoFwd[0], P.ssaoFwd[1], P.ssaoFwd[2]));
+    const float w = __frcp_rn(t);
+    // the texel against its model point cam + D(x, y) t
+    const float fx = (float)qx, fy = (float)qy;
+    const V3 D = mk3(fmaf(P.ssaoDy[0], fy, fmaf(P.ssaoDx[0], fx, P.ssaoDc[0])), fmaf(P.ssaoDy[1], fy, fmaf(P.ssaoDx[1], fx, P.ssaoDc[1])),
+                     fmaf(P.ssaoDy[2], fy, fmaf(P.ssaoDx[2], fx, P.ssaoDc[2])));
+    const float err = fmaxf(fabsf(fmaf(D.x, t, cam.x) - p11.x), fmaxf(fabsf(fmaf(D.y, t, cam.y) - p11.y), fabsf(fmaf(D.z, t, cam.z) - p11.z)));
+    const float mag = (fabsf(p11.x) + fabsf(p11.y) + fabsf(p11.z)) + P.ssaoCamL1;
+    const bool ok = (t > 0.0f) && (w < __int_as_float(0x7f800000)) && (err <= kPlaneErr * mag); // NaN anywhere fails a comparison
+    P.ssaoRecip[(size_t)qy * P.W + qx] = ok ? w : __int_as_float(0x7fc00000);
+  }
   const float b[3] = {p00.x, p00.y, p00.z};
   const float t10[3] = {p10.x, p10.y, p10.z}, t01[3] = {p01.x, p01.y, p01.z}, t11[3] = {p11.x, p11.y, p11.z};
   float A[3], B[3], C[3], U[3];
@@ -988,22 +1002,424 @@ template <bool COUNT> ADEV int ssaoCountRayProxy(const FrameParams& P, int px, i
 #define ALTHEA_SSAO_TILE_W 16
 #endif
 constexpr int kSsaoTileW = ALTHEA_SSAO_TILE_W, kSsaoTileH = 256 / ALTHEA_SSAO_TILE_W;
+// One CTA per 16 x 16 tile in raster order (concurrently running tiles share L2 lines), or, after
+// ssao_cull_kernel, four consecutive entries of the list of tiles it handed over (mostly-undecidable neighbourhoods) per CTA.
 template <bool COUNT, int KIND> __global__ void __launch_bounds__(256, ALTHEA_SSAO_MIN_BLOCKS) ssao_kernel(const __grid_constant__ FrameParams P) {
-  const int x = blockIdx.x * kSsaoTileW + (threadIdx.x % kSsaoTileW);
-  const int y = P.y0 + blockIdx.y * kSsaoTileH + (threadIdx.x / kSsaoTileW);
-  if (x >= P.W || y >= P.y1) return;
-  V4 position = FmtRGBA32F::load(P.position, x, y);
-  uint8_t count = 255;
+  const int tilesX = (P.W + kSsaoTileW - 1) / kSsaoTileW;
+  const unsigned listed = P.ssaoTileList ? __ldg(P.ssaoTileList) : 0u;
   unsigned gathers = 0u;
-  if (position.w != 0.0f) {
-    const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
-    V3 normal = normalize3(xyz(FmtRGBA16F::load(P.normal, x, y)));
-    count = (uint8_t)(KIND ? ssaoCountRayProxy<COUNT>(P, x, y, u, v, xyz(position), normal, gathers) : ssaoCountFiltered<COUNT>(P, x, y, u, v, xyz(position), normal, gathers));
+  for (unsigned k = P.ssaoTileList ? blockIdx.x * 4u : blockIdx.x, e = P.ssaoTileList ? min(k + 4u, listed) : k + 1u; k < e; ++k) {
+    const int tile = P.ssaoTileList ? (int)__ldg(P.ssaoTileList + 1 + k) : (int)k;
+    const int x = (tile % tilesX) * kSsaoTileW + (threadIdx.x % kSsaoTileW);
+    const int y = P.y0 + (tile / tilesX) * kSsaoTileH + (threadIdx.x / kSsaoTileW);
+    if (x >= P.W || y >= P.y1) continue;
+    V4 position = FmtRGBA32F::load(P.position, x, y);
+    uint8_t count = 255;
+    if (position.w != 0.0f) {
+      const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
+      V3 normal = normalize3(xyz(FmtRGBA16F::load(P.normal, x, y)));
+      count = (uint8_t)(KIND ? ssaoCountRayProxy<COUNT>(P, x, y, u, v, xyz(position), normal, gathers) : ssaoCountFiltered<COUNT>(P, x, y, u, v, xyz(position), normal, gathers));
+    }
+    rowPtrW<uint8_t>(P.ao, y)[x] = count;
   }
-  rowPtrW<uint8_t>(P.ao, y)[x] = count;
   if (COUNT) { // two device counters: records gathered, taps re-evaluated from the fp32 texels
     atomicAdd(P.gatherCounter, (unsigned long long)(gathers & 0xffffu));
     atomicAdd(P.gatherCounter + 1, (unsigned long long)(gathers >> 16));
+  }
+}
+
+// ---- SSAO, round 2: coarse sign test over per-block plane records, exact steps compacted across the warp ------------------
+// A march step can only score when dot(p - pos, perpRef) changes sign between two consecutive taps (SSAO.glsl:68). A position
+// G-buffer written by a perspective camera holds p(x, y) = cam + D(x, y) t with D affine in the texel coordinates and t the eye
+// depth, so a texel's projection is  c0 + t g(x, y) = t c0 (w - L(x, y)),  w = 1 / t,  c0 = dot(cam - pos, perpRef),
+// g = dot(D, perpRef),  L = -g / c0: its SIGN is that of w - L up to the constant sign of c0, and L (the ray's plane in
+// reciprocal depth) is affine on the screen. A planar surface has w affine on the screen too, so ONE 16-byte record per block of
+// texels, {alpha, beta, gamma, r} with |w_k - (alpha + beta x_k + gamma y_k)| <= r for every texel the block covers, decides the
+// sign at every texel of a tap's footprint (hence of the bilinear tap, a convex combination; and of its fp32 evaluation, by
+// the margins below) whenever |w_plane - L| at the tap exceeds r plus the slack of the ray. The records of the tile's
+// neighbourhood (32 x 32 blocks of 8, 16 or 32 texels, picked per tile from its nearest depth) are staged in shared memory by
+// the TMA engine, so a tap costs one LDS.128 instead of a divergent 32-byte gather from L2.
+//   phase 1 (per ray, all lanes in lockstep, no break): the 11 taps are classified (+, -, undecided); a step whose two taps are
+//     decided and equal cannot flip and is dropped; every other step is pushed on the warp's queue as (lane, ray, step);
+//   phase 2 (whenever 32 items wait): each lane takes one item, rebuilds that ray (the hash RNG is random access) and
+//     evaluates the step with the filtered exact predicates of ssaoCountFiltered on the 32-byte position records.
+// computeSSAO breaks at a ray's first scoring step and counts rays, so the count is the number of rays with ANY scoring step:
+// steps are independent and can be evaluated in any order. Counts are those of ssao_exact_kernel, bit for bit (tests/).
+// Tiles whose neighbourhood is mostly undecidable (random depth, foliage) are flagged and left to ssao_kernel.
+//
+// Margins of the coarse decision (DESIGN.md 4.1 spells out the derivation). Texel k's real-arithmetic projection is
+//   pi_k = c0 + g_k / w_k + eps_k,  |eps_k| <= sqrt(3) err_k + 2^-20 (|cam|_1 + |pos|_1 + |p_k|_1)
+// (err_k: distance of the texel from its model point, bounded by kPlaneErr (|p_k|_1 + |cam|_1) in every decidable block; the
+// rest: rounding of c0, g), and the restatement's fp32 tap is within 64 ulp (|pos|_1 + |p|_1) of the bilinear combination.
+// With |p_k|_1 <= |cam|_1 + Dmax1 / w_k and w_k <= |L_k| + |w_k - L_k| the sign of the tap is that of w - L whenever
+//   |w_k - L_k| (1 - kappa) > kappa |L_k| + kNu Dmax1 / |c0|,  kappa = kNu (2 |cam|_1 + |pos|_1) / |c0|,
+// at all four texels; rays with kappa > 0.01 take the exact path for all their steps (1 / (1 - kappa) <= 1.0102 otherwise).
+constexpr float kNu = 1.7e-5f;       // sqrt(3) * 4e-6 (true model error) + 2^-20 (coefficients) + 64 ulp (the fp32 tap), rounded up
+constexpr int kPlaneWin = 32;        // blocks per side of the staged window
+#ifndef ALTHEA_CULL_REACH
+#define ALTHEA_CULL_REACH 0.6f
+#endif
+constexpr float kCullReach = ALTHEA_CULL_REACH; // screen reach of a tile's rays, in focal lengths per unit of (depth - 0.5): picks the window's block size
+
+// one warp per record
+__global__ void __launch_bounds__(256) ssao_planes_kernel(const __grid_constant__ FrameParams P) {
+  const int lane = threadIdx.x & 31;
+  long long rec = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  int level = 0;
+  for (; level < 3; ++level) {
+    const long long n = (long long)P.ssaoPlaneRow[level] * (P.ssaoPlaneNy[level] + 2 * kSsaoPlanePad + 1);
+    if (rec < n) break;
+    rec -= n;
+  }
+  if (level == 3) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.ssaoTileList[0] = 0u; // the list ssao_cull_kernel (next in the stream) appends to
+  const int S = 8 << level;
+  const int row = P.ssaoPlaneRow[level];
+  const int bx = (int)(rec % row) - kSsaoPlanePad, by = (int)(rec / row) - kSsaoPlanePad;
+  float4* out = const_cast<float4*>(P.ssaoPlanes[level]) + ((long long)by * row + bx);
+  const float inf = __int_as_float(0x7f800000);
+  if (bx < 0 || by < 0 || bx >= P.ssaoPlaneNx[level] || by >= P.ssaoPlaneNy[level]) {
+    if (lane == 0) *out = make_float4(0.0f, 0.0f, 0.0f, inf);
+    return;
+  }
+  // texels the record answers for: the block, one texel before it and two after it (a tap assigned to this block by the
+  // march's rounded coordinates has its footprint in there), inside the image (taps whose footprint clamps are left to the
+  // exact path by the march)
+  const int X0 = bx * S, Y0 = by * S;
+  const int xlo = max(X0 - 1, 0), xhi = min(X0 + S + 1, P.W - 1), ylo = max(Y0 - 1, 0), yhi = min(Y0 + S + 1, P.H - 1);
+  const int nx = xhi - xlo + 1, ny = yhi - ylo + 1;
+  auto recip = [&](int x, int y) { return __ldg(P.ssaoRecip + ((size_t)y * P.W + x)); }; // NaN: texel off the camera model
+  // plane through the centre texel with the secant slopes of the middle row / column (for a quadratic surface these are the
+  // least-squares slopes); the offset is re-centred on the residual range below
+  const int xc = (xlo + xhi) >> 1, yc = (ylo + yhi) >> 1;
+  const float beta = nx > 1 ? (recip(xhi, yc) - recip(xlo, yc)) / (float)(xhi - xlo) : 0.0f;
+  const float gamma = ny > 1 ? (recip(xc, yhi) - recip(xc, ylo)) / (float)(yhi - ylo) : 0.0f;
+  const float alpha = recip(xc, yc) - (beta * (float)xc + gamma * (float)yc);
+  float rlo = inf, rhi = -inf, wmax = 0.0f;
+  bool ok = true;
+  for (int k = lane; k < nx * ny; k += 32) {
+    const int x = xlo + k % nx, y = ylo + k / nx;
+    const float w = recip(x, y);
+    const float res = w - fmaf(beta, (float)x, fmaf(gamma, (float)y, alpha));
+    ok = ok && (res == res);
+    rlo = fminf(rlo, res);
+    rhi = fmaxf(rhi, res);
+    wmax = fmaxf(wmax, w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rlo = fminf(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
+    rhi = fmaxf(rhi, __shfl_xor_sync(0xffffffffu, rhi, o));
+    wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    ok = __shfl_xor_sync(0xffffffffu, (int)ok, o) && ok;
+  }
+  if (lane == 0) {
+    const float mid = 0.5f * (rlo + rhi);
+    const float a2 = alpha + mid;
+    // half the residual range (+ the rounding of the re-centring), one texel and a bit of the plane's slope (the footprint's
+    // texels lie within 1 + 1e-3 texels of the tap), the rounding of the plane's evaluation here and in the march, the
+    // rounding of the reciprocals
+    float r = 0.5f * (rhi - rlo) + 4.0e-7f * (fabsf(mid) + fabsf(rlo) + fabsf(rhi));
+    r += 1.01f * (fabsf(beta) + fabsf(gamma));
+    r += 4.8e-7f * (fabsf(a2) + fabsf(alpha) + fabsf(beta) * (float)(xhi + 1) + fabsf(gamma) * (float)(yhi + 1));
+    r += 2.4e-7f * wmax;
+    r *= 1.000001f;
+    const bool fin = ok && isfinite(a2) && isfinite(beta) && isfinite(gamma) && isfinite(r);
+    *out = fin ? make_float4(a2, beta, gamma, r) : make_float4(0.0f, 0.0f, 0.0f, inf);
+  }
+}
+
+// the ray of one pixel: SSAO.glsl:36-45 (the hash RNG's state after k draws is seed + k, so ray r starts at seed + 3 r)
+struct SsaoRay { V3 rayDir, perpRef; V2 uvEnd; };
+ADEV SsaoRay ssaoRay(const FrameParams& P, const TangentFrame& tbn, V3 worldPos, V3 normal, int px, int py, int ray) {
+  HashRng rng;
+  rng.sx = (uint32_t)px + 3u * (uint32_t)ray;
+  rng.sy = (uint32_t)py + 3u * (uint32_t)ray;
+  const float x0 = rng.next(), x1 = rng.next(), x2 = rng.next();
+  SsaoRay r;
+  r.rayDir = frameApply(tbn, normalize3(mk3(2.0f * x0 - 1.0f, 2.0f * x1 - 1.0f, x2)));
+  r.uvEnd = projectUv(P, worldPos + r.rayDir * 0.5f);
+  r.perpRef = normalize3(cross3(cross3(r.rayDir, normal), r.rayDir));
+  return r;
+}
+// taps before the ray leaves the screen (SSAO.glsl:50), see ssaoCountFiltered. The tap coordinates move monotonically away
+// from the pixel's centre by far more than an ulp per tap when the end point is outside, so "inside" holds for a prefix of
+// the taps and the first tap outside is found by bisection (tap 0 is the pixel's own centre, inside).
+ADEV int ssaoTapCount(float u0, float v0, V2 uvEnd) {
+  if (!outside01(uvEnd.x, uvEnd.y)) return 12;
+  int lo = 0, hi = 12; // tap lo is inside, tap hi is outside (tap 12 = the end point)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int mid = (lo + hi) >> 1;
+    if (mid > lo) {
+      if (outside01(marchCoord(u0, uvEnd.x, mid), marchCoord(v0, uvEnd.y, mid))) hi = mid;
+      else lo = mid;
+    }
+  }
+  return hi;
+}
+
+// Sign class of one tap the plane records could not call: +1 / -1 = sign of the restatement's fp32 projection (|value| > kTiny),
+// 0 = a value so small (or NaN) that only the fp32 product of the step's two exact projections says whether it flips.
+template <bool COUNT> ADEV int ssaoTapClass(const FrameParams& P, float cu, float cv, V3 worldPos, V3 perpRef, unsigned& gathers) {
+  const float posSlop2 = (2.002f * kRoundSlop) * (fabsf(worldPos.x) + fabsf(worldPos.y) + fabsf(worldPos.z));
+  const float projBias = fmaf(worldPos.z, perpRef.z, fmaf(worldPos.y, perpRef.y, worldPos.x * perpRef.x));
+  const ProxyAddr pa = proxyAddr(P, cu, cv);
+  const ProxyTap t = proxyEval(loadQuad(pa.rec), pa.fx, pa.fy);
+  if (COUNT) gathers += 1u;
+  const float projection = fmaf(t.pos.z, perpRef.z, fmaf(t.pos.y, perpRef.y, fmaf(t.pos.x, perpRef.x, -projBias)));
+  if (fabsf(projection) > t.twoTol + posSlop2) return projection < 0.0f ? -1 : 1; // the sign of the exact value, which is > kTiny
+  if (COUNT) gathers += 65536u;
+  const float e = exactTap(P, cu, cv, worldPos, perpRef).projection;
+  return fabsf(e) > kTiny ? (e < 0.0f ? -1 : 1) : 0;
+}
+// A step whose two taps have opposite sign classes (or, `exact`, a class-0 tap): the rest of SSAO.glsl:68-74
+template <bool COUNT> ADEV bool ssaoFlipScores(const FrameParams& P, float u0, float v0, V3 worldPos, V3 rayDir, V3 perpRef, float uvEndX, float uvEndY, int i, bool exact,
+                                               unsigned& gathers) {
+  const float pu = marchCoord(u0, uvEndX, i - 1), pv = marchCoord(v0, uvEndY, i - 1);
+  const float cu = marchCoord(u0, uvEndX, i), cv = marchCoord(v0, uvEndY, i);
+  bool near;
+  if (exact) {
+    if (COUNT) gathers += 2u * 65536u;
+    const ExactTap ec = exactTap(P, cu, cv, worldPos, perpRef), ep = exactTap(P, pu, pv, worldPos, perpRef);
+    if (!(__fmul_rn(ec.projection, ep.projection) < 0.0f)) return false;
+    near = length3(ec.pos - ep.pos) <= 2.0f;
+  } else {
+    const float posSlop2 = (2.002f * kRoundSlop) * (fabsf(worldPos.x) + fabsf(worldPos.y) + fabsf(worldPos.z));
+    const ProxyAddr pa = proxyAddr(P, pu, pv), ca = proxyAddr(P, cu, cv);
+    const ProxyTap pt = proxyEval(loadQuad(pa.rec), pa.fx, pa.fy), ct = proxyEval(loadQuad(ca.rec), ca.fx, ca.fy);
+    if (COUNT) gathers += 2u;
+    // worldStep = length(currentPos - prevPos) <= 2.0; each threshold covers twice its tap's position tolerance
+    const float worldStep = length3(ct.pos - pt.pos);
+    const float tol = (ct.twoTol + posSlop2) + (pt.twoTol + posSlop2);
+    if (worldStep + tol <= 2.0f) near = true;
+    else if (worldStep - tol > 2.0f) near = false;
+    else {
+      if (COUNT) gathers += 2u * 65536u;
+      near = length3(exactTap(P, cu, cv, worldPos, perpRef).pos - exactTap(P, pu, pv, worldPos, perpRef).pos) <= 2.0f;
+    }
+  }
+  return near && facesRay(P, cu, cv, rayDir);
+}
+
+ADEV float invSf(int level) { return level == 0 ? 0.125f : level == 1 ? 0.0625f : 0.03125f; }
+constexpr int kFlipRing = 64; // flip items waiting per warp: at most 31 left over + one per lane
+#ifndef ALTHEA_CULL_MIN_BLOCKS
+#define ALTHEA_CULL_MIN_BLOCKS 4
+#endif
+template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLOCKS) ssao_cull_kernel(const __grid_constant__ FrameParams P) {
+  __shared__ __align__(128) float4 win[kPlaneWin * kPlaneWin];
+  __shared__ uint16_t tapQueue[8][32 * 11];      // (lane, tap) of the current ray's undecided taps
+  __shared__ unsigned tapResult[8][32];          // per lane: bit i = tap i negative, bit 16 + i = tap i of class 0
+  __shared__ float flipRing[8][6][kFlipRing];    // tag, uvEnd, rayDir of the steps that change sign
+  __shared__ float rayState[8][8][32];           // the current ray of every lane: uvEnd, perpRef, rayDir (read across lanes)
+  __shared__ unsigned hitMask[8][32];
+  __shared__ float redMin[8];
+  __shared__ int badSum[8];
+  __shared__ __align__(8) uint64_t bar;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tileX = blockIdx.x * 16, tileY = P.y0 + blockIdx.y * 16;
+  const int x = tileX + (lane & 15), y = tileY + warp * 2 + (lane >> 4);
+  const bool inside = x < P.W && y < P.y1;
+  V4 position = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (inside) position = FmtRGBA32F::load(P.position, x, y);
+  const bool covered = inside && position.w != 0.0f;
+  const V3 worldPos = xyz(position);
+  // nearest covered depth of the tile -> block size of the window (a ray is 0.5 world units long)
+  float tmin = covered ? dot3(worldPos - mk3(P.ssaoCam[0], P.ssaoCam[1], P.ssaoCam[2]), mk3(P.ssaoFwd[0], P.ssaoFwd[1], P.ssaoFwd[2])) : __int_as_float(0x7f800000);
+  if (!(tmin > 0.0f)) tmin = 0.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+  if (lane == 0) redMin[warp] = tmin;
+  if (threadIdx.x == 0) mbarInit(&bar, 1);
+  __syncthreads();
+  tmin = fminf(fminf(fminf(redMin[0], redMin[1]), fminf(redMin[2], redMin[3])), fminf(fminf(redMin[4], redMin[5]), fminf(redMin[6], redMin[7])));
+  if (tmin == __int_as_float(0x7f800000)) { // nothing to shade in this tile
+    if (inside) rowPtrW<uint8_t>(P.ao, y)[x] = 255;
+    return;
+  }
+  const float reach = kCullReach * P.ssaoFocalPx / fmaxf(tmin - 0.5f, 1e-3f);
+  const int level = reach <= 15.0f * 8.0f - 4.0f ? 0 : reach <= 15.0f * 16.0f - 4.0f ? 1 : 2;
+  const int S = 8 << level;
+  // window: blocks [wbx, wbx + 32) x [wby, wby + 32), the tile's first block in column / row 15
+  const int wbx = (tileX >> (3 + level)) - 15, wby = (tileY >> (3 + level)) - 15;
+  if (warp == 0) {
+    if (lane == 0) mbarExpectTx(&bar, kPlaneWin * kPlaneWin * 16);
+    __syncwarp();
+    const float4* src = P.ssaoPlanes[level] + ((long long)(wby + lane) * P.ssaoPlaneRow[level] + wbx);
+    bulkCopyG2S(&win[lane * kPlaneWin], src, kPlaneWin * 16, &bar);
+  }
+  hitMask[warp][lane] = 0u;
+  mbarWait(&bar, 0);
+  { // a neighbourhood that mostly cannot decide is marched by ssao_kernel instead: undecidable records among the blocks the
+    // tile's rays can reach
+    const int rb = min(15, (int)(reach * invSf(level)) + 2);
+    const int row = threadIdx.x >> 3, col0 = (threadIdx.x & 7) * 4;
+    int bad = 0;
+    if (row >= 15 - rb && row <= 16 + rb) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (col0 + k >= 15 - rb && col0 + k <= 16 + rb) bad += win[row * kPlaneWin + col0 + k].w == __int_as_float(0x7f800000) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if (lane == 0) badSum[warp] = bad;
+    __syncthreads();
+    int all = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) all += badSum[k];
+    if (all * 8 > 7 * (2 * rb + 2) * (2 * rb + 2)) { // the exact evaluations run at full lane occupancy here: worth it up to ~7 / 8 undecidable
+      if (threadIdx.x == 0) P.ssaoTileList[1u + atomicAdd(P.ssaoTileList, 1u)] = blockIdx.y * gridDim.x + blockIdx.x;
+      return;
+    }
+  }
+  // ---- per pixel
+  const float u0 = ((float)x + 0.5f) / (float)P.W, v0 = ((float)y + 0.5f) / (float)P.H;
+  V3 normal = mk3(0.0f, 0.0f, 1.0f);
+  if (covered) normal = normalize3(xyz(FmtRGBA16F::load(P.normal, x, y)));
+  const TangentFrame tbn = localToWorld(normal);
+  const float kappaNum = kNu * (2.0f * P.ssaoCamL1 + (fabsf(worldPos.x) + fabsf(worldPos.y) + fabsf(worldPos.z))) + kTiny;
+  // block coordinates of a tap inside the window come out of the mantissa of  x / S + magic: with 4 (9) fraction bits the
+  // low bits of the x (y) word are (block << 4) ((block << 9)): the byte offset of the record's column (row) in the window
+  const float invS = 1.0f / (float)S;
+  const float offX = 786432.0f - (float)wbx, offY = 24576.0f - (float)wby; // 1.5 * 2^19, 1.5 * 2^14
+  const char* winBytes = reinterpret_cast<const char*>(win);
+  const float xs0 = (float)x, ys0 = (float)y;
+  uint16_t* tq = tapQueue[warp];
+  float (*fr)[kFlipRing] = flipRing[warp];
+  float (*rs)[32] = rayState[warp];
+  int fhead = 0, ftail = 0; // FIFO of flip items, warp-uniform
+  unsigned gathers = 0u, lookups = 0u, tapItems = 0u;
+  // evaluates min(32, waiting) flip items, oldest first, one per lane
+  auto drainFlips = [&]() {
+    const int count = min(ftail - fhead, 32);
+    const bool live = lane < count;
+    const int e = (fhead + (live ? lane : 0)) & (kFlipRing - 1);
+    const unsigned tag = __float_as_uint(fr[0][e]); // lane | step << 5 | ray << 9 | exact << 14
+    const int src = (int)(tag & 31u);
+    const V3 sp = mk3(__shfl_sync(0xffffffffu, worldPos.x, src), __shfl_sync(0xffffffffu, worldPos.y, src), __shfl_sync(0xffffffffu, worldPos.z, src));
+    const float su = __shfl_sync(0xffffffffu, u0, src), sv = __shfl_sync(0xffffffffu, v0, src);
+    const V3 sn = mk3(__shfl_sync(0xffffffffu, normal.x, src), __shfl_sync(0xffffffffu, normal.y, src), __shfl_sync(0xffffffffu, normal.z, src));
+    if (live) {
+      const V3 rd = mk3(fr[3][e], fr[4][e], fr[5][e]);
+      const bool exact = (tag >> 14) & 1u;
+      // perpRef only enters the projections of a class-0 step (rare): rebuilt as ssaoRay builds it
+      const V3 pr = exact ? perpRefOf(rd, sn) : rd;
+      if (ssaoFlipScores<COUNT>(P, su, sv, sp, rd, pr, fr[1][e], fr[2][e], (int)((tag >> 5) & 15u), exact, gathers)) atomicOr(&hitMask[warp][src], 1u << ((tag >> 9) & 31u));
+    }
+    fhead += count;
+    __syncwarp();
+  };
+  for (int ray = 0; ray < 24; ++ray) {
+    const SsaoRay R = ssaoRay(P, tbn, worldPos, normal, x, y, ray);
+    const int n = covered ? ssaoTapCount(u0, v0, R.uvEnd) : 0;
+    rs[0][lane] = R.uvEnd.x; rs[1][lane] = R.uvEnd.y;
+    rs[2][lane] = R.perpRef.x; rs[3][lane] = R.perpRef.y; rs[4][lane] = R.perpRef.z;
+    rs[5][lane] = R.rayDir.x; rs[6][lane] = R.rayDir.y; rs[7][lane] = R.rayDir.z;
+    unsigned decMask = 0u, negMask = 0u;
+    { // ray constants of the coarse test
+      const V3 cam = mk3(P.ssaoCam[0], P.ssaoCam[1], P.ssaoCam[2]);
+      const float c0 = dot3(cam - worldPos, R.perpRef);
+      const float au = dot3(mk3(P.ssaoDx[0], P.ssaoDx[1], P.ssaoDx[2]), R.perpRef), av = dot3(mk3(P.ssaoDy[0], P.ssaoDy[1], P.ssaoDy[2]), R.perpRef);
+      const float ac = dot3(mk3(P.ssaoDc[0], P.ssaoDc[1], P.ssaoDc[2]), R.perpRef);
+      float invC0;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(invC0) : "f"(c0));
+      const float aInv = fabsf(invC0);
+      const float Lx = -au * invC0, Ly = -av * invC0;
+      const float xEnd = fmaf(R.uvEnd.x, P.Wf, -0.5f), yEnd = fmaf(R.uvEnd.y, P.Hf, -0.5f);
+      const float dxs = (xEnd - xs0) * (1.0f / 12.0f), dys = (yEnd - ys0) * (1.0f / 12.0f);
+      const float L0 = -(fmaf(au, xs0, fmaf(av, ys0, ac))) * invC0;
+      const float dL = fmaf(Lx, dxs, Ly * dys);
+      const float Labs = fmaxf(fabsf(L0), fabsf(fmaf(11.0f, dL, L0))) + (fabsf(Lx) + fabsf(Ly));
+      const float kappa = kappaNum * aInv;
+      // slack of the ray: the footprint's extent in L, the margin rule, the rounding of L (16 ulp of the largest term of
+      // dot(D, perpRef) / c0) and of w - L
+      float rayConst = 1.01f * (fabsf(Lx) + fabsf(Ly)) + 1.0102f * fmaf(kappa, Labs, kNu * P.ssaoDmax1 * aInv) + 9.6e-7f * P.ssaoDmag * aInv + 4.8e-7f * Labs;
+      // rays the records cannot answer for take the exact path for all their taps: a last tap outside the window, a plane
+      // through (nearly) the camera. (A footprint that clamps at the image border repeats a texel the block covers.)
+      const float lastI = (float)(max(n, 2) - 1);
+      const float xl = fmaf(lastI, dxs, xs0), yl = fmaf(lastI, dys, ys0);
+      const float wx = xl * invS - (float)wbx, wy = yl * invS - (float)wby; // window coordinates of the last tap, in blocks
+      const bool answerable = wx >= 0.25f && wx <= (float)kPlaneWin - 0.25f && wy >= 0.25f && wy <= (float)kPlaneWin - 0.25f && kappa <= 0.01f;
+      if (!answerable) rayConst = __int_as_float(0x7f800000);
+#pragma unroll
+      for (int i = 1; i < 12; ++i) {
+        const float fi = (float)i;
+        // unanswerable rays may have wild coordinates: the masked offset stays inside the window, the value is never used
+        const float tx = fmaf(fi, dxs, xs0), ty = fmaf(fi, dys, ys0);
+        const float vx = fmaf(tx, invS, offX), vy = fmaf(ty, invS, offY);
+        const unsigned off = (__float_as_uint(vx) & 0x1f0u) | (__float_as_uint(vy) & 0x3e00u);
+        const float4 rec = *reinterpret_cast<const float4*>(winBytes + off);
+        const float d = fmaf(rec.y, tx, fmaf(rec.z, ty, rec.x)) - fmaf(fi, dL, L0);
+        if (fabsf(d) > rec.w + rayConst) decMask |= 1u << i;
+        if (d < 0.0f) negMask |= 1u << i;
+      }
+      if (c0 < 0.0f) negMask = ~negMask; // the projection is t c0 (w - L): its sign, not that of w - L
+    }
+    // taps 1 .. n - 1 take part in steps 2 .. n - 1 (none when n < 3)
+    const unsigned tapMask = n >= 3 ? (1u << n) - 2u : 0u;
+    unsigned undecided = tapMask & ~decMask;
+    negMask &= decMask;
+    if (COUNT) { lookups += __popc(tapMask); tapItems += __popc(undecided); }
+    // ---- the undecided taps of this ray, compacted over the warp and classified from the position records
+    tapResult[warp][lane] = 0u;
+    const int cnt = __popc(undecided);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    for (int pos = incl - cnt; undecided; ++pos) {
+      const int i = __ffs(undecided) - 1;
+      undecided &= undecided - 1u;
+      tq[pos] = (uint16_t)(lane | (i << 5));
+    }
+    __syncwarp();
+    for (int base = 0; base < total; base += 32) {
+      const bool live = base + lane < total;
+      const unsigned item = live ? (unsigned)tq[base + lane] : (unsigned)lane;
+      const int src = (int)(item & 31u), i = (int)(item >> 5);
+      const V3 sp = mk3(__shfl_sync(0xffffffffu, worldPos.x, src), __shfl_sync(0xffffffffu, worldPos.y, src), __shfl_sync(0xffffffffu, worldPos.z, src));
+      const float su = __shfl_sync(0xffffffffu, u0, src), sv = __shfl_sync(0xffffffffu, v0, src);
+      if (live) {
+        const int cls = ssaoTapClass<COUNT>(P, marchCoord(su, rs[0][src], i), marchCoord(sv, rs[1][src], i), sp, mk3(rs[2][src], rs[3][src], rs[4][src]), gathers);
+        if (cls <= 0) atomicOr(&tapResult[warp][src], cls < 0 ? 1u << i : 0x10000u << i);
+      }
+    }
+    __syncwarp();
+    // ---- steps whose taps differ in sign (or have a class-0 tap) go on the flip ring with what their evaluation needs
+    const unsigned res = tapResult[warp][lane];
+    negMask |= res & 0xffffu;
+    const unsigned zero = res >> 16;
+    const unsigned stepMask = tapMask & ~2u; // steps 2 .. n - 1
+    const unsigned exactSteps = (zero | (zero << 1)) & stepMask;
+    unsigned flips = (((negMask ^ (negMask << 1)) & stepMask) & ~exactSteps) | (exactSteps << 16);
+    while (__any_sync(0xffffffffu, flips != 0u)) {
+      const bool has = flips != 0u;
+      const unsigned b = __ballot_sync(0xffffffffu, has);
+      if (has) {
+        const int bit = __ffs(flips) - 1;
+        flips &= flips - 1u;
+        const int e = (ftail + __popc(b & ((1u << lane) - 1u))) & (kFlipRing - 1);
+        fr[0][e] = __uint_as_float((unsigned)lane | ((unsigned)(bit & 15) << 5) | ((unsigned)ray << 9) | ((unsigned)(bit >> 4) << 14));
+        fr[1][e] = rs[0][lane]; fr[2][e] = rs[1][lane];
+        fr[3][e] = rs[5][lane]; fr[4][e] = rs[6][lane]; fr[5][e] = rs[7][lane];
+      }
+      ftail += __popc(b);
+      __syncwarp();
+      if (ftail - fhead >= 32) drainFlips();
+    }
+  }
+  while (ftail > fhead) drainFlips();
+  __syncwarp();
+  if (inside) rowPtrW<uint8_t>(P.ao, y)[x] = covered ? (uint8_t)__popc(hitMask[warp][lane]) : (uint8_t)255;
+  if (COUNT) {
+    atomicAdd(P.gatherCounter, (unsigned long long)(gathers & 0xffffu));
+    atomicAdd(P.gatherCounter + 1, (unsigned long long)(gathers >> 16));
+    atomicAdd(P.gatherCounter + 2, (unsigned long long)lookups);
+    atomicAdd(P.gatherCounter + 3, (unsigned long long)tapItems);
   }
 }
 
@@ -1098,7 +1514,8 @@ void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s) {
   glossy_convolve_kernel<<<tileGrid(C.dst.w, C.y1 - C.y0), 256, 0, s>>>(C);
 }
 void launch_ssao(const FrameParams& P, cudaStream_t s) {
-  const dim3 grid((unsigned)((P.W + kSsaoTileW - 1) / kSsaoTileW), (unsigned)((P.y1 - P.y0 + kSsaoTileH - 1) / kSsaoTileH));
+  const int tiles = ((P.W + kSsaoTileW - 1) / kSsaoTileW) * ((P.y1 - P.y0 + kSsaoTileH - 1) / kSsaoTileH);
+  const dim3 grid((unsigned)(P.ssaoTileList ? (tiles + 3) / 4 : tiles)); // listed tiles: four consecutive entries per CTA
   if (P.quadKind) {
     if (P.gatherCounter) ssao_kernel<true, 1><<<grid, 256, 0, s>>>(P);
     else ssao_kernel<false, 1><<<grid, 256, 0, s>>>(P);
@@ -1106,6 +1523,17 @@ void launch_ssao(const FrameParams& P, cudaStream_t s) {
     if (P.gatherCounter) ssao_kernel<true, 0><<<grid, 256, 0, s>>>(P);
     else ssao_kernel<false, 0><<<grid, 256, 0, s>>>(P);
   }
+}
+static_assert(kSsaoTileW == 16, "ssao_cull_kernel and ssao_kernel share the 16 x 16 tile grid");
+void launch_ssao_planes(const FrameParams& P, cudaStream_t s) {
+  long long n = 0;
+  for (int l = 0; l < 3; ++l) n += (long long)P.ssaoPlaneRow[l] * (P.ssaoPlaneNy[l] + 2 * kSsaoPlanePad + 1);
+  ssao_planes_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(P);
+}
+void launch_ssao_cull(const FrameParams& P, cudaStream_t s) {
+  const dim3 grid((unsigned)((P.W + 15) / 16), (unsigned)((P.y1 - P.y0 + 15) / 16));
+  if (P.gatherCounter) ssao_cull_kernel<true><<<grid, 256, 0, s>>>(P);
+  else ssao_cull_kernel<false><<<grid, 256, 0, s>>>(P);
 }
 void launch_ssao_exact(const FrameParams& P, cudaStream_t s) { ssao_exact_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
 void launch_ssao_quads(const FrameParams& P, cudaStream_t s) {

@@ -3,6 +3,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <vector_types.h>
 
 #include "../../include/althea_cuda.h"
 
@@ -12,6 +13,7 @@ struct ImgView { // one mip level of one layer of a linear image
   int pitch; // bytes
 };
 constexpr int kMaxMips = 14;
+constexpr int kSsaoPlanePad = 16; // blocks of padding around every level of the SSAO plane records
 struct ChainView {
   ImgView level[kMaxMips];
   int mips;
@@ -50,6 +52,18 @@ struct FrameParams {
   float ssaoGram[6]; // Dc.Dc, Dx.Dx, Dy.Dy, 2 Dc.Dx, 2 Dc.Dy, 2 Dx.Dy
   float ssaoOrigin[3]; // model coordinates of the world origin: Dc o0 + Dx o1 + Dy o2 = -cam (where empty pixels' cleared positions lie)
   int quadKind;
+  // SSAO coarse sign test: per level l (blocks of 8 << l texels) one 16-byte record per block:
+  // {alpha, beta, gamma, r}: reciprocal eye depth of every texel the block covers lies within r of alpha + beta x + gamma y
+  // (texel coordinates); r = +inf where the block cannot decide. Padded by kSsaoPlanePad blocks of r = +inf on every side.
+  const float4* ssaoPlanes[3]; // record of block (0, 0) of each level
+  int ssaoPlaneRow[3];         // records per padded row
+  int ssaoPlaneNx[3], ssaoPlaneNy[3]; // blocks per level (unpadded)
+  float ssaoFocalPx;           // focal length in pixels (the larger axis): level choice per tile
+  float ssaoDmax1;             // max |D(x, y)|_1 over the image
+  float ssaoDmag;              // |Dc|_1 + |Dx|_1 W + |Dy|_1 H: bounds the rounding of dot(D(x, y), v)
+  float ssaoCamL1;             // |cam|_1
+  unsigned* ssaoTileList;       // [0]: number of 16 x 16 tiles the cull kernel handed over to the march kernel, [1 + k]: tile ids
+  float* ssaoRecip;             // W x H: reciprocal eye depth of every position texel (NaN: off the camera model), by ssao_quads_kernel
   unsigned long long* gatherCounter; // diagnostics (ALTHEA_CTX_SSAO_COUNT_TAPS): proxy records gathered by the SSAO march; else null
   // SSR padded depth (engine scratch): the depth image with a one-texel CLAMP_TO_EDGE border, (W+2) x (H+2) floats
   const float* depthPad;

@@ -189,6 +189,13 @@ class Context:
         self._check(self._lib.althea_cuda_diag_ssao_exact_fallbacks(self._ptr, C.byref(out)))
         return int(out.value)
 
+    def ssao_cull_counts(self) -> dict:
+        """All counters of that launch: position records gathered, exact re-evaluations, plane-record lookups of the coarse
+        sign test, and the march steps it could not drop (diagnostics)."""
+        out = (C.c_uint64 * 4)()
+        self._check(self._lib.althea_cuda_diag_ssao_cull(self._ptr, out))
+        return {"records": int(out[0]), "exact_taps": int(out[1]), "plane_lookups": int(out[2]), "exact_steps": int(out[3])}
+
     def gather_ceiling(self, w: int, h: int, radius: int, taps_per_pixel: int = 64) -> float:
         """Measured records/s of divergent 32-byte gathers within +-radius records of each 16x16 tile (diagnostics)."""
         out = C.c_double(0.0)

@@ -72,6 +72,7 @@ int althea_cuda_abi_version(void);
 #define ALTHEA_CTX_SSAO_EXACT_TAPS 2u /* SSAO marches the fp32 position texels directly (4 loads per tap) instead of the packed proxy with exact re-evaluation; same counts, slower: A/B switch for tests and profiling */
 #define ALTHEA_CTX_SSAO_RAY_DEPTH_PROXY 8u /* SSAO marches 16-byte ray-depth records (eye depth of a footprint's four texels along the camera's view rays) instead of the 32-byte position records; same counts bit for bit; faster on frames without sky, slightly slower with it: opt-in */
 #define ALTHEA_CTX_SSAO_COUNT_TAPS 4u /* diagnostics: the SSAO march also counts the proxy records it gathers (read with althea_cuda_diag_ssao_gathers); slower */
+#define ALTHEA_CTX_SSAO_NO_CULL 16u /* SSAO without the coarse sign test (per-block plane records in shared memory that drop the march steps which cannot flip): every tap gathers its position record, as in round 1; same counts bit for bit: A/B switch */
 int althea_cuda_set_flags(althea_cuda_ctx* ctx, uint32_t flags);
 
 /* Row bands (multi-GPU split of ONE frame, BASELINE configs[3]): restricts ssr_capture / glossy_convolve / deferred_shade on
@@ -98,6 +99,9 @@ uint64_t althea_cuda_launch_count(const althea_cuda_ctx* ctx);
 int althea_cuda_diag_ssao_gathers(althea_cuda_ctx* ctx, uint64_t* out_records);
 /* ... and the taps of that launch that had to be re-evaluated from the fp32 texels (ray-depth proxy only). */
 int althea_cuda_diag_ssao_exact_fallbacks(althea_cuda_ctx* ctx, uint64_t* out_taps);
+/* All four counters of that launch: position records gathered, taps re-evaluated from the fp32 texels, plane-record lookups
+ * of the coarse sign test (shared memory), and march steps it could not drop (evaluated exactly). */
+int althea_cuda_diag_ssao_cull(althea_cuda_ctx* ctx, uint64_t out_counts[4]);
 int althea_cuda_diag_gather_ceiling(althea_cuda_ctx* ctx, uint32_t w, uint32_t h, uint32_t radius, uint32_t taps_per_pixel,
                                     double* out_records_per_second);
 

@@ -375,24 +375,35 @@ def test_properties_at_4k(ctx_fast):
 
 
 def test_gather_diagnostics(ctx_fast):
-    """bench.py's roofline evidence for the SSAO march: the counting instantiation returns the same AO counts and a gather
-    count inside the march's bounds (<= 24 rays x 11 taps per shaded pixel), and the ceiling measurement returns a rate."""
+    """bench.py's roofline evidence for SSAO: the counting instantiations return the same AO counts. The round-1 march
+    (CTX_SSAO_NO_CULL) gathers at most 24 rays x 11 taps of position records per shaded pixel; with the coarse sign test the
+    plane-record lookups obey that bound instead, the taps it could not call are a fraction of them, and the records gathered
+    are one per such tap plus two per step that changes sign. The ceiling measurement returns a rate."""
     from althea_b200 import _capi
     fd = FrameData("scene", 192, 108, n_lights=0)
     gf = GpuFrame(ctx_fast, fd)
     gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
     plain = gf.ao_counts().copy()
-    ctx_fast.set_flags(_capi.CTX_SSAO_COUNT_TAPS)
-    gf.deferred.aoCounts.tensor.zero_()
-    gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
-    counted = gf.ao_counts().copy()
-    gathers = ctx_fast.ssao_gathers()
-    assert 0 <= ctx_fast.ssao_exact_fallbacks() < gathers // 4
-    ctx_fast.set_flags(0)
-    assert np.array_equal(plain, counted)
     shaded = int((plain < 255).sum())
-    assert 0 < gathers <= shaded * 24 * 11
-    assert gathers > shaded * 24  # more than one tap per ray on average
+    try:
+        ctx_fast.set_flags(_capi.CTX_SSAO_COUNT_TAPS | _capi.CTX_SSAO_NO_CULL)
+        gf.deferred.aoCounts.tensor.zero_()
+        gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+        assert np.array_equal(plain, gf.ao_counts())
+        gathers = ctx_fast.ssao_gathers()
+        assert 0 <= ctx_fast.ssao_exact_fallbacks() < gathers // 4
+        assert shaded * 24 < gathers <= shaded * 24 * 11  # more than one tap per ray on average
+        ctx_fast.set_flags(_capi.CTX_SSAO_COUNT_TAPS)
+        gf.deferred.aoCounts.tensor.zero_()
+        gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+        assert np.array_equal(plain, gf.ao_counts())
+        c = ctx_fast.ssao_cull_counts()
+        assert shaded * 24 < c["plane_lookups"] <= shaded * 24 * 11
+        assert 0 < c["exact_steps"] < c["plane_lookups"]           # the taps the plane records could not call (most, at this size:
+        # a ray is ~8 texels long here; ~11 % at 4K)
+        assert c["exact_steps"] <= c["records"] <= c["exact_steps"] + 2 * shaded * 24 * 10
+    finally:
+        ctx_fast.set_flags(0)
     rate = ctx_fast.gather_ceiling(512, 512, 32, 16)
     assert rate > 1e9
 
