@@ -25,6 +25,7 @@ CTX_SSAO_EXACT_TAPS = 2
 CTX_SSAO_COUNT_TAPS = 4
 CTX_SSAO_RAY_DEPTH_PROXY = 8
 CTX_SSAO_NO_CULL = 16
+CTX_SSR_PLANE_SKIP = 32
 SHADE_SKIP_TONEMAP = 1
 SHADE_NO_SSAO = 2
 SHADE_AO_FROM_IMAGE = 4

@@ -72,6 +72,7 @@ struct althea_cuda_ctx {
   // internal scratch: SSR padded depth, (W+2) x (H+2) floats (frame_kernels.cu, ssr_depth_pad_kernel)
   void* depthPadScratch = nullptr;
   size_t depthPadScratchBytes = 0;
+  void* ssrPlaneScratch = nullptr; // SSR plane records, kSsrPlaneStride x kSsrPlaneRows x 16 B
   // timing
   bool timing = false;
   std::vector<TimingEntry> pending;
@@ -456,6 +457,7 @@ void althea_cuda_destroy(althea_cuda_ctx* ctx) {
   if (ctx->positionScratch) cudaFree(ctx->positionScratch);
   if (ctx->quadScratch) cudaFree(ctx->quadScratch);
   if (ctx->planeScratch) cudaFree(ctx->planeScratch);
+  if (ctx->ssrPlaneScratch) cudaFree(ctx->ssrPlaneScratch);
   if (ctx->depthPadScratch) cudaFree(ctx->depthPadScratch);
   if (ctx->gatherCounter) cudaFree(ctx->gatherCounter);
   freeRasterScratch(ctx->raster);
@@ -752,10 +754,31 @@ int althea_cuda_ssr_capture(althea_cuda_ctx* ctx, const althea_global_uniforms* 
     P.depthPad = static_cast<const float*>(ctx->depthPadScratch);
     P.depthPadOrigin = P.depthPad + P.depthPadRow + 1;
   }
+  P.ssrPlanes = nullptr;
+  if (ctx->flags & ALTHEA_CTX_SSR_PLANE_SKIP) { // sign test over plane records of the depth buffer: the smallest blocks that cover the frame
+    int shift = 3;
+    while (((P.W + (1 << shift) - 1) >> shift) > kSsrPlaneStride - 1 || ((P.H + (1 << shift) - 1) >> shift) > kSsrPlaneRows - 1) ++shift;
+    if (!ctx->ssrPlaneScratch) {
+      cudaError_t e = cudaMalloc(&ctx->ssrPlaneScratch, (size_t)kSsrPlaneStride * kSsrPlaneRows * 16);
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(ssr plane records): %s", cudaGetErrorString(e)); }
+    }
+    P.ssrPlanes = static_cast<const float4*>(ctx->ssrPlaneScratch);
+    if (const char* e = getenv("ALTHEA_SSR_PLANE_SHIFT")) shift = std::max(shift, atoi(e)); // tuning: coarser blocks
+    P.ssrPlaneShift = shift;
+  }
+  if (P.ssrPlanes && (ctx->flags & ALTHEA_CTX_SSAO_COUNT_TAPS)) { // diagnostics: the skip kernel's tap counters (read with althea_cuda_diag_ssao_cull)
+    if (!ctx->gatherCounter) {
+      cudaError_t e = cudaMalloc(&ctx->gatherCounter, 4 * sizeof(unsigned long long));
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(gather counter): %s", cudaGetErrorString(e)); }
+    }
+    P.gatherCounter = ctx->gatherCounter;
+  }
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  if (P.gatherCounter) cudaMemsetAsync(P.gatherCounter, 0, 4 * sizeof(unsigned long long), stream);
   const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
   timedLaunch(ctx, "ssr_depth_pad", stream, [&] { parity ? althea_parity::launch_ssr_depth_pad(P, stream) : althea_fast::launch_ssr_depth_pad(P, stream); });
+  if (P.ssrPlanes) timedLaunch(ctx, "ssr_planes", stream, [&] { parity ? althea_parity::launch_ssr_planes(P, stream) : althea_fast::launch_ssr_planes(P, stream); });
   timedLaunch(ctx, "ssr_capture", stream, [&] { parity ? althea_parity::launch_ssr_capture(P, stream) : althea_fast::launch_ssr_capture(P, stream); });
   return endWork(ctx, sync, stream);
 }

@@ -163,6 +163,30 @@ ADEV V2 projectUv(const FrameParams& P, V3 p) { // 0.5 * clip.xy / clip.w + 0.5
   return uv;
 }
 
+// ---- TMA bulk copies into shared memory, completion on an mbarrier (UBLKCP + SYNCS in SASS) -------------------------------
+ADEV uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+ADEV void mbarInit(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+ADEV void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+ADEV void bulkCopyG2S(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)), "l"(src), "r"(bytes),
+               "r"(smemAddr(bar))
+               : "memory");
+}
+ADEV void mbarWait(uint64_t* bar, uint32_t phase) {
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra WAIT_%=;\n}\n" ::"r"(smemAddr(bar)), "r"(phase)
+               : "memory");
+}
+
+
+// margins shared by the SSAO and SSR sign tests over plane records (derivation at ssao_cull_kernel)
+constexpr float kNu = 1.7e-5f;  // sqrt(3) * 4e-6 (true model error) + 2^-20 (coefficients) + 64 ulp (the fp32 tap), rounded up
+constexpr float kTiny = 1e-15f; // decisions on |value| <= kTiny are always re-evaluated (products must not underflow)
+
 // ---- SSR ------------------------------------------------------------------------------------------------------------
 // Padded depth (engine scratch, written by ssr_depth_pad_kernel once per frame): the depth image with a one-texel CLAMP_TO_EDGE
 // border, (W + 2) x (H + 2) floats. The footprint whose top-left tap is texel (ix, iy), ix in [-1, W-1], iy in [-1, H-1], is the
@@ -227,6 +251,10 @@ __global__ void __launch_bounds__(256, ALTHEA_SSR_MIN_BLOCKS) ssr_capture_kernel
     const float stepX = (dx / dl) * 0.005f, stepY = (dy / dl) * 0.005f;
     const V3 perpRef = normalize3(cross3(cross3(rayDir, normal), rayDir));
     float cu = u, cv = v;
+    // a hit is shaded after the march: inside the loop every lane of a warp would run the 16-light shading on its own at the
+    // step where it hits
+    bool hit = false;
+    V3 hitPos = worldPos, hitNormal = normal;
 #ifdef ALTHEA_PARITY
     float prevProjection = 0.0f;
 #else
@@ -246,7 +274,7 @@ __global__ void __launch_bounds__(256, ALTHEA_SSR_MIN_BLOCKS) ssr_capture_kernel
       if (currentProjection * prevProjection <= 0.0f && f > 0.999f && i > 0) {
         V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, cu, cv)));
         if (dot3(currentNormal, rayDir) < 0.0f) {
-          out = environmentLitSample(P, currentPos, cu, cv, rayDir, currentNormal);
+          hit = true; hitPos = currentPos; hitNormal = currentNormal;
           break;
         }
       }
@@ -296,7 +324,7 @@ __global__ void __launch_bounds__(256, ALTHEA_SSR_MIN_BLOCKS) ssr_capture_kernel
           if (dot3(currentNormal, rayDir) < 0.0f) {
             const V3 wd = mk3(fmaf(Wu.x, cu, fmaf(Wv.x, cv, W0.x)), fmaf(Wu.y, cu, fmaf(Wv.y, cv, W0.y)), fmaf(Wu.z, cu, fmaf(Wv.z, cv, W0.z)));
             const V3 vv = mk3(fmaf(wd.x, k, camMinusPos.x), fmaf(wd.y, k, camMinusPos.y), fmaf(wd.z, k, camMinusPos.z));
-            out = environmentLitSample(P, worldPos + vv, cu, cv, rayDir, currentNormal);
+            hit = true; hitPos = worldPos + vv; hitNormal = currentNormal;
             break;
           }
         }
@@ -304,9 +332,239 @@ __global__ void __launch_bounds__(256, ALTHEA_SSR_MIN_BLOCKS) ssr_capture_kernel
       prevProjection = currentProjection;
     }
 #endif
+    if (hit) out = environmentLitSample(P, hitPos, cu, cv, rayDir, hitNormal);
   }
   // blend-on-write over the (0,0,0,0) clear (GraphicsPipeline.cpp:138-154): rgb*a, a
   rowPtrW<uint2>(P.refl.level[0], y)[x] = packHalf4(mk4(out.x * out.w, out.y * out.w, out.z * out.w, out.w));
+}
+
+// ---- SSR, round 2: sign test over plane records of the depth buffer ------------------------------------------------------
+// A march step can only hit when the projection of the tapped surface on perpRef changes sign (or vanishes) between two
+// consecutive taps (SSR.frag:118). The tap is reconstructPosition(uv, bilinear depth) = cam + D(uv) t, t the eye depth, so its
+// projection is t c0 (w - L(uv)) with w = 1 / t = (far - dRaw (far - near)) / (far near), AFFINE in the raw depth: the tap's w is
+// the bilinear combination of its four texels' w, and bilinear weights reproduce affine functions. With one record
+// {alpha, beta, gamma, r} per block of depth texels, |w_k - (alpha + beta x_k + gamma y_k)| <= r for every texel the block
+// answers for, the tap's w lies within r of the plane AT THE TAP, and sign(w - L) is known whenever |w_plane - L| exceeds r plus
+// the ray's slack (rounding of the fp32 evaluation, depth-buffer cancellation). Steps whose two taps have known, equal signs are
+// skipped without touching the depth buffer; every other step is evaluated exactly as before (the previous tap's projection is
+// re-evaluated when it was skipped), so the hit mask is that of the plain march. Neighbouring pixels reflect in neighbouring
+// directions, so a warp's taps share a few records: they are read through L1 (the whole frame's records take 150 KB at 4K).
+__global__ void __launch_bounds__(256) ssr_planes_kernel(const __grid_constant__ FrameParams P) {
+  const int lane = threadIdx.x & 31;
+  const int rec = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (rec >= kSsrPlaneStride * kSsrPlaneRows) return;
+  const int S = 1 << P.ssrPlaneShift;
+  // record (bx + 1, by + 1) of the array is block (bx, by): a tap up to half a texel left of / above the image lands in column /
+  // row 0, which cannot decide (the march's masked block index must stay inside the array for every in-screen tap)
+  const int bx = rec % kSsrPlaneStride - 1, by = rec / kSsrPlaneStride - 1;
+  float4* out = const_cast<float4*>(P.ssrPlanes) + rec;
+  const float inf = __int_as_float(0x7f800000);
+  const int X0 = bx * S, Y0 = by * S;
+  if (bx < 0 || by < 0 || X0 >= P.W || Y0 >= P.H) {
+    if (lane == 0) *out = make_float4(0.0f, 0.0f, 0.0f, inf);
+    return;
+  }
+  // texels the record answers for: the block and an apron: the march assigns a tap to a block by x / S rounded to 1 / 16
+  // (S / 32 texels) and y / S to 2^-9 or finer, its tap coordinate is within 1e-3 texels of the restatement's, and the
+  // footprint is the two texels from floor(x); inside the image (a footprint that clamps at the border repeats a covered texel)
+  const int xlo = max(X0 - 2 - (S >> 5), 0), xhi = min(X0 + S + 1, P.W - 1), ylo = max(Y0 - 2, 0), yhi = min(Y0 + S + 1, P.H - 1);
+  const int nx = xhi - xlo + 1, ny = yhi - ylo + 1;
+  auto recip = [&](int x, int y) { // (far - dRaw (far - near)) / (far near), ReconstructPosition.glsl:6-8
+    const float dRaw = __ldg(rowPtr<float>(P.depth, y) + x);
+    return fmaf(dRaw, -(1000.0f - 0.01f), 1000.0f) * (1.0f / (1000.0f * 0.01f));
+  };
+  const int xc = (xlo + xhi) >> 1, yc = (ylo + yhi) >> 1;
+  const float beta = nx > 1 ? (recip(xhi, yc) - recip(xlo, yc)) / (float)(xhi - xlo) : 0.0f;
+  const float gamma = ny > 1 ? (recip(xc, yhi) - recip(xc, ylo)) / (float)(yhi - ylo) : 0.0f;
+  const float alpha = recip(xc, yc) - (beta * (float)xc + gamma * (float)yc);
+  float rlo = inf, rhi = -inf, wmax = 0.0f;
+  bool ok = true;
+  for (int k = lane; k < nx * ny; k += 32) {
+    const int x = xlo + k % nx, y = ylo + k / nx;
+    const float w = recip(x, y);
+    const float res = w - fmaf(beta, (float)x, fmaf(gamma, (float)y, alpha));
+    ok = ok && (w > 0.0f) && (res == res) && (w < inf);
+    rlo = fminf(rlo, res);
+    rhi = fmaxf(rhi, res);
+    wmax = fmaxf(wmax, w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rlo = fminf(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
+    rhi = fmaxf(rhi, __shfl_xor_sync(0xffffffffu, rhi, o));
+    wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    ok = __shfl_xor_sync(0xffffffffu, (int)ok, o) && ok;
+  }
+  if (lane == 0) {
+    const float mid = 0.5f * (rlo + rhi);
+    const float a2 = alpha + mid;
+    float r = 0.5f * (rhi - rlo) + 4.0e-7f * (fabsf(mid) + fabsf(rlo) + fabsf(rhi));
+    // a footprint that clamps at the image border repeats a texel: its weights no longer reproduce the plane, by up to half a
+    // texel of slope; the march's tap coordinate is within 1e-3 texels of the restatement's
+    const bool border = X0 == 0 || Y0 == 0 || X0 + S >= P.W || Y0 + S >= P.H;
+    r += (border ? 0.51f : 0.001f) * (fabsf(beta) + fabsf(gamma));
+    // rounding of the plane's evaluation here and in the march; the depth buffer's cancellation: the restatement's fp32 lerps
+    // of the raw depth carry 4 ulp of 1.0, times (far - near) / (far near)
+    r += 4.8e-7f * (fabsf(a2) + fabsf(alpha) + fabsf(beta) * (float)(xhi + 1) + fabsf(gamma) * (float)(yhi + 1));
+    r += 2.4e-7f * wmax + 3.0e-5f;
+    r *= 1.000001f;
+    const bool fin = ok && isfinite(a2) && isfinite(beta) && isfinite(gamma) && isfinite(r);
+    *out = fin ? make_float4(a2, beta, gamma, r) : make_float4(0.0f, 0.0f, 0.0f, inf);
+  }
+}
+
+__global__ void __launch_bounds__(256, ALTHEA_SSR_MIN_BLOCKS) ssr_capture_skip_kernel(const __grid_constant__ FrameParams P) {
+  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int y = P.y0 + blockIdx.y * 16 + (threadIdx.x >> 4); // rows [y0, y1): the scissor (whole frame by default)
+  const bool inside = x < P.W && y < P.y1;
+  const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
+  V4 normal4 = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (inside) normal4 = FmtRGBA16F::load(P.normal, x, y);
+  V4 out = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (normal4.w != 0.0f) { // SSR.frag:136-141
+    const float dOwn = __ldg(rowPtr<float>(P.depth, y) + x);
+    const V3 worldPos = reconstructPosition(P, u, v, dOwn);
+    const V3 normal = normalize3(xyz(normal4));
+    const V3 rayDir = reflect3(normalize3(viewDirection(P, u, v)), normal);
+    // raymarchGBuffer, SSR.frag:80-133
+    V2 uvEnd = projectUv(P, worldPos + rayDir * 10000.0f);
+    float dx = uvEnd.x - u, dy = uvEnd.y - v;
+    float dl = sqrtf(dx * dx + dy * dy);
+    const float stepX = (dx / dl) * 0.005f, stepY = (dy / dl) * 0.005f;
+    const V3 perpRef = normalize3(cross3(cross3(rayDir, normal), rayDir));
+    // ---- constants of the sign test: L(x, y) = -dot(D(x, y), perpRef) / c0 in tap coordinates x = u W - 0.5, y = v H - 0.5
+    const V3 camMinusPos = mk3(P.g.inverseView[12], P.g.inverseView[13], P.g.inverseView[14]) - worldPos;
+    float Lc, Lx, Ly, rayConst;
+    bool c0neg;
+    {
+      const float c0 = dot3(camMinusPos, perpRef);
+      float invC0;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(invC0) : "f"(c0));
+      const float aInv = fabsf(invC0);
+      c0neg = c0 < 0.0f;
+      Lc = -dot3(mk3(P.ssaoDc[0], P.ssaoDc[1], P.ssaoDc[2]), perpRef) * invC0;
+      Lx = -dot3(mk3(P.ssaoDx[0], P.ssaoDx[1], P.ssaoDx[2]), perpRef) * invC0;
+      Ly = -dot3(mk3(P.ssaoDy[0], P.ssaoDy[1], P.ssaoDy[2]), perpRef) * invC0;
+      const float Labs = fabsf(Lc) + fabsf(Lx) * P.Wf + fabsf(Ly) * P.Hf;
+      const float posL1 = fabsf(worldPos.x) + fabsf(worldPos.y) + fabsf(worldPos.z);
+      const float kappa = (kNu * (2.0f * P.ssaoCamL1 + posL1) + kTiny) * aInv;
+      // the margin rule of the SSAO sign test (same projection, same model), the rounding of L, the tap coordinate's 1e-3 texels
+      rayConst = 1.0102f * fmaf(kappa, Labs, kNu * P.ssaoDmax1 * aInv) + 9.6e-7f * P.ssaoDmag * aInv + 4.8e-7f * Labs + 1e-3f * (fabsf(Lx) + fabsf(Ly));
+      if (!(kappa <= 0.01f)) rayConst = __int_as_float(0x7f800000);
+    }
+    const float Sf = (float)(1 << P.ssrPlaneShift), invS = 1.0f / Sf;
+    const float sxPx = stepX * P.Wf, syPx = stepY * P.Hf; // the step in texels, and taps per texel along each axis
+    const float rsx = 1.0f / sxPx, rsy = 1.0f / syPx;
+    const char* planeBytes = reinterpret_cast<const char*>(P.ssrPlanes);
+    unsigned nSkip = 0u, nSpan = 0u, nExact = 0u, nUndecided = 0u, nWarpExact = 0u;
+    bool hit = false; // shaded after the march, see ssr_capture_kernel
+    V3 hitPos = worldPos, hitNormal = normal;
+    float cu = u, cv = v, pu = u, pv = v;
+    int prevCls = 0;       // sign class of the previous tap's projection: +-1 known, 0 unknown
+    bool prevExact = true; // prevProjection is the previous tap's projection as the march computes it
+#ifdef ALTHEA_PARITY
+    float prevProjection = 0.0f;
+#else
+    float prevProjection = __int_as_float(0x7fc00000); // carries the i > 0 test, see ssr_capture_kernel
+    const V3 W0 = mk3(P.ssrW0[0], P.ssrW0[1], P.ssrW0[2]), Wu = mk3(P.ssrWu[0], P.ssrWu[1], P.ssrWu[2]), Wv = mk3(P.ssrWv[0], P.ssrWv[1], P.ssrWv[2]);
+    const float cR = dot3(camMinusPos, rayDir), cP = dot3(camMinusPos, perpRef);
+    // the fast march's folded step (ssr_capture_kernel) at tap coordinates (tu, tv): projection, and what the cone test needs
+    auto fastTap = [&](float tu, float tv, float& along, float& len2, float& k) {
+      const DepthTap q = depthTapPadded(P, tu, tv);
+      const float top = fmaf(q.t10 - q.t00, q.fx, q.t00), bot = fmaf(q.t11 - q.t01, q.fx, q.t01);
+      const float dRaw = fmaf(bot - top, q.fy, top);
+      const V3 wd = mk3(fmaf(Wu.x, tu, fmaf(Wv.x, tv, W0.x)), fmaf(Wu.y, tu, fmaf(Wv.y, tv, W0.y)), fmaf(Wu.z, tu, fmaf(Wv.z, tv, W0.z)));
+      const float den = fmaf(dRaw, 1000.0f - 0.01f, -1000.0f) * fmaf(P.ssrS[1], tu, fmaf(P.ssrS[2], tv, P.ssrS[0]));
+      k = (1000.0f * 0.01f) * rcpf(den);
+      along = fmaf(k, dot3(wd, rayDir), cR);
+      const V3 vv = mk3(fmaf(wd.x, k, camMinusPos.x), fmaf(wd.y, k, camMinusPos.y), fmaf(wd.z, k, camMinusPos.z));
+      len2 = dot3(vv, vv);
+      return fmaf(k, dot3(wd, perpRef), cP);
+    };
+#endif
+    for (int i = 0; i < 128; ++i) {
+      cu += stepX;
+      cv += stepY;
+      if (outside01(cu, cv)) break;
+      // ---- sign class of this tap from the plane records
+      int cls = 0;
+      const float tx = fmaf(cu, P.Wf, -0.5f), ty = fmaf(cv, P.Hf, -0.5f);
+      const float vx = fmaf(tx, invS, 786433.0f), vy = fmaf(ty, invS, 6145.0f); // 1.5 * 2^19 + 1, 1.5 * 2^12 + 1: (block + 1) << 4, << 11
+      // the masked offset stays inside the 128 x 128 records whatever the coordinate (a NaN coordinate is not "outside": it
+      // lands on some record, and NaN never compares as decided)
+      const unsigned bxs = __float_as_uint(vx) & 0x7f0u, bys = __float_as_uint(vy) & 0x3f800u;
+      const float4 rec = __ldg(reinterpret_cast<const float4*>(planeBytes + (bxs | bys)));
+      const float d = fmaf(rec.y, tx, fmaf(rec.z, ty, rec.x)) - fmaf(Lx, tx, fmaf(Ly, ty, Lc));
+      const float slack = rec.w + rayConst;
+      if (fabsf(d) > slack) cls = ((d < 0.0f) != c0neg) ? -1 : 1;
+      if (cls != 0 && cls == prevCls) { // both projections known, nonzero, of one sign: SSR.frag:118 cannot hold
+        // Inside one block w_plane - L is affine along the ray: if the last tap before the ray leaves the block (and the image)
+        // is decided with the same sign, so is every tap in between: they are skipped with their coordinate updates only.
+        const float ex0 = (float)((int)(bxs >> 4) - 1) * Sf, ey0 = (float)((int)(bys >> 11) - 1) * Sf; // the record's own block
+        const float toX = sxPx > 0.0f ? fminf(ex0 + Sf, P.Wf - 1.0f) - tx : fmaxf(ex0, 0.0f) - tx;
+        const float toY = syPx > 0.0f ? fminf(ey0 + Sf, P.Hf - 1.0f) - ty : fmaxf(ey0, 0.0f) - ty;
+        // taps that certainly stay inside: one less than fit (accumulated coordinates drift by < 0.05 texels over a march)
+        const float mf = fminf(fminf(toX * rsx, toY * rsy), (float)(126 - i)) - 1.0f;
+        int m = mf >= 1.0f ? (int)mf : 0; // NaN (a zero step component times an infinite reciprocal): no span
+        if (m > 0) {
+          const float dLast = fmaf((float)m, fmaf(rec.y - Lx, sxPx, (rec.z - Ly) * syPx), d);
+          if (!(fabsf(dLast) > slack && dLast * d > 0.0f)) m = 0;
+        }
+        for (int j = 0; j < m; ++j) { cu += stepX; cv += stepY; }
+        i += m;
+        if (P.gatherCounter) { nSkip += 1u + (unsigned)m; nSpan += m > 0 ? 1u : 0u; }
+        prevExact = false;
+        pu = cu; pv = cv;
+        continue;
+      }
+#ifdef ALTHEA_PARITY
+      if (!prevExact) {
+        const DepthTap q = depthTapPadded(P, pu, pv);
+        const float dRaw = mixf(mixf(q.t00, q.t10, q.fx), mixf(q.t01, q.t11, q.fx), q.fy);
+        prevProjection = dot3(normalize3(reconstructPosition(P, pu, pv, dRaw) - worldPos), perpRef);
+      }
+      const DepthTap q = depthTapPadded(P, cu, cv);
+      float dRaw = mixf(mixf(q.t00, q.t10, q.fx), mixf(q.t01, q.t11, q.fx), q.fy); // == bilinearR32F<AddrClamp>(P.depth, cu, cv)
+      V3 currentPos = reconstructPosition(P, cu, cv, dRaw);
+      V3 dir = normalize3(currentPos - worldPos);
+      float currentProjection = dot3(dir, perpRef);
+      float f = dot3(dir, rayDir);
+      if (currentProjection * prevProjection <= 0.0f && f > 0.999f && i > 0) {
+        V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, cu, cv)));
+        if (dot3(currentNormal, rayDir) < 0.0f) {
+          hit = true; hitPos = currentPos; hitNormal = currentNormal;
+          break;
+        }
+      }
+#else
+      float along, len2, k;
+      if (!prevExact) prevProjection = fastTap(pu, pv, along, len2, k);
+      const float currentProjection = fastTap(cu, cv, along, len2, k);
+      if (currentProjection * prevProjection <= 0.0f && along > 0.0f && along * along > (0.999f * 0.999f) * len2) {
+        V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, cu, cv)));
+        if (dot3(currentNormal, rayDir) < 0.0f) {
+          const V3 wd = mk3(fmaf(Wu.x, cu, fmaf(Wv.x, cv, W0.x)), fmaf(Wu.y, cu, fmaf(Wv.y, cv, W0.y)), fmaf(Wu.z, cu, fmaf(Wv.z, cv, W0.z)));
+          const V3 vv = mk3(fmaf(wd.x, k, camMinusPos.x), fmaf(wd.y, k, camMinusPos.y), fmaf(wd.z, k, camMinusPos.z));
+          hit = true; hitPos = worldPos + vv; hitNormal = currentNormal;
+          break;
+        }
+      }
+#endif
+      if (P.gatherCounter) { nExact += 1u; nUndecided += cls == 0 ? 1u : 0u; nWarpExact += (threadIdx.x & 31) == (__ffs(__activemask()) - 1) ? 1u : 0u; }
+      prevProjection = currentProjection;
+      prevExact = true;
+      // known sign of an exact value large enough that its product with a decided projection cannot underflow
+      prevCls = currentProjection > 1e-15f ? 1 : currentProjection < -1e-15f ? -1 : 0;
+      pu = cu; pv = cv;
+    }
+    if (hit) out = environmentLitSample(P, hitPos, cu, cv, rayDir, hitNormal);
+    if (P.gatherCounter) { // diagnostics: taps skipped, spans, taps evaluated exactly, of those undecided by the records, warp-level exact steps
+      atomicAdd(P.gatherCounter, (unsigned long long)nSkip); atomicAdd(P.gatherCounter + 1, (unsigned long long)nSpan);
+      atomicAdd(P.gatherCounter + 2, (unsigned long long)nExact); atomicAdd(P.gatherCounter + 3, (unsigned long long)(nUndecided | ((unsigned long long)nWarpExact << 32)));
+    }
+  }
+  // blend-on-write over the (0,0,0,0) clear (GraphicsPipeline.cpp:138-154): rgb*a, a
+  if (inside) rowPtrW<uint2>(P.refl.level[0], y)[x] = packHalf4(mk4(out.x * out.w, out.y * out.w, out.z * out.w, out.w));
 }
 
 // ---- glossy convolve ------------------------------------------------------------------------------------------------
@@ -338,24 +596,6 @@ __global__ void __launch_bounds__(256) glossy_convolve_kernel(const __grid_const
 // The arithmetic (coordinates, tap order, lerps) is the direct kernel's, so the results are identical bit for bit.
 // Preconditions (checked by the launcher, which otherwise uses the direct kernel): source width even and level base 16-byte
 // aligned, so that every staged row segment starts and ends on a 16-byte boundary.
-ADEV uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-ADEV void mbarInit(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-ADEV void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
-}
-ADEV void bulkCopyG2S(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)), "l"(src), "r"(bytes),
-               "r"(smemAddr(bar))
-               : "memory");
-}
-ADEV void mbarWait(uint64_t* bar, uint32_t phase) {
-  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra WAIT_%=;\n}\n" ::"r"(smemAddr(bar)), "r"(phase)
-               : "memory");
-}
-
 struct StagedTile { // the staged source window: columns [x0, x0 + cols), rows [y0, y0 + rows) of the source level
   const uint2* texels;
   int x0, y0, cols, rows;
@@ -516,7 +756,6 @@ constexpr float kSqrt3Up = 1.7320509f;
 // fp32 rounding slop, as a multiple of the coordinate magnitude in play: both the restatement's evaluation and the
 // proxy's are within a few ulp of real arithmetic (two lerp levels, a subtraction, a 3-term dot product); 64 ulp is generous
 constexpr float kRoundSlop = 64.0f * 1.1920929e-7f;
-constexpr float kTiny = 1e-15f; // decisions on |value| <= kTiny are always re-evaluated (products must not underflow)
 
 ADEV uint32_t halfBits(float v) { return (uint32_t)__half_as_ushort(__float2half_rn(v)); }
 ADEV float lowHalfToFloat(uint32_t w) { return __low2float(*reinterpret_cast<const __half2*>(&w)); }
@@ -1054,10 +1293,9 @@ template <bool COUNT, int KIND> __global__ void __launch_bounds__(256, ALTHEA_SS
 // With |p_k|_1 <= |cam|_1 + Dmax1 / w_k and w_k <= |L_k| + |w_k - L_k| the sign of the tap is that of w - L whenever
 //   |w_k - L_k| (1 - kappa) > kappa |L_k| + kNu Dmax1 / |c0|,  kappa = kNu (2 |cam|_1 + |pos|_1) / |c0|,
 // at all four texels; rays with kappa > 0.01 take the exact path for all their steps (1 / (1 - kappa) <= 1.0102 otherwise).
-constexpr float kNu = 1.7e-5f;       // sqrt(3) * 4e-6 (true model error) + 2^-20 (coefficients) + 64 ulp (the fp32 tap), rounded up
 constexpr int kPlaneWin = 32;        // blocks per side of the staged window
 #ifndef ALTHEA_CULL_REACH
-#define ALTHEA_CULL_REACH 0.6f
+#define ALTHEA_CULL_REACH 0.5f
 #endif
 constexpr float kCullReach = ALTHEA_CULL_REACH; // screen reach of a tile's rays, in focal lengths per unit of (depth - 0.5): picks the window's block size
 
@@ -1082,11 +1320,11 @@ __global__ void __launch_bounds__(256) ssao_planes_kernel(const __grid_constant_
     if (lane == 0) *out = make_float4(0.0f, 0.0f, 0.0f, inf);
     return;
   }
-  // texels the record answers for: the block, one texel before it and two after it (a tap assigned to this block by the
-  // march's rounded coordinates has its footprint in there), inside the image (taps whose footprint clamps are left to the
-  // exact path by the march)
+  // texels the record answers for: the block and an apron: the march assigns a tap to a block by x / S rounded to 1 / 16
+  // (S / 32 texels) and y / S to 2^-9 or finer, its tap coordinate is within 1e-3 texels of the restatement's, and the
+  // footprint is the two texels from floor(x); inside the image (a footprint that clamps at the border repeats a covered texel)
   const int X0 = bx * S, Y0 = by * S;
-  const int xlo = max(X0 - 1, 0), xhi = min(X0 + S + 1, P.W - 1), ylo = max(Y0 - 1, 0), yhi = min(Y0 + S + 1, P.H - 1);
+  const int xlo = max(X0 - 2 - (S >> 5), 0), xhi = min(X0 + S + 1, P.W - 1), ylo = max(Y0 - 2, 0), yhi = min(Y0 + S + 1, P.H - 1);
   const int nx = xhi - xlo + 1, ny = yhi - ylo + 1;
   auto recip = [&](int x, int y) { return __ldg(P.ssaoRecip + ((size_t)y * P.W + x)); }; // NaN: texel off the camera model
   // plane through the centre texel with the secant slopes of the middle row / column (for a quadratic surface these are the
@@ -1482,7 +1720,11 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const __grid_consta
 // ---- launchers ------------------------------------------------------------------------------------------------------
 static inline dim3 tileGrid(int w, int h) { return dim3((unsigned)((w + 15) / 16), (unsigned)((h + 15) / 16)); }
 
-void launch_ssr_capture(const FrameParams& P, cudaStream_t s) { ssr_capture_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
+void launch_ssr_capture(const FrameParams& P, cudaStream_t s) {
+  if (P.ssrPlanes) ssr_capture_skip_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P);
+  else ssr_capture_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P);
+}
+void launch_ssr_planes(const FrameParams& P, cudaStream_t s) { ssr_planes_kernel<<<(kSsrPlaneStride * kSsrPlaneRows + 7) / 8, 256, 0, s>>>(P); }
 void launch_ssr_depth_pad(const FrameParams& P, cudaStream_t s) {
   ssr_depth_pad_kernel<<<dim3((unsigned)((P.W + 2 + 31) / 32), (unsigned)((P.H + 2 + 7) / 8)), 256, 0, s>>>(P);
 }

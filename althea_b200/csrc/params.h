@@ -13,6 +13,7 @@ struct ImgView { // one mip level of one layer of a linear image
   int pitch; // bytes
 };
 constexpr int kMaxMips = 14;
+constexpr int kSsrPlaneStride = 128, kSsrPlaneRows = 128; // records of the SSR plane image (global memory, L1 / L2 resident)
 constexpr int kSsaoPlanePad = 16; // blocks of padding around every level of the SSAO plane records
 struct ChainView {
   ImgView level[kMaxMips];
@@ -65,6 +66,10 @@ struct FrameParams {
   unsigned* ssaoTileList;       // [0]: number of 16 x 16 tiles the cull kernel handed over to the march kernel, [1 + k]: tile ids
   float* ssaoRecip;             // W x H: reciprocal eye depth of every position texel (NaN: off the camera model), by ssao_quads_kernel
   unsigned long long* gatherCounter; // diagnostics (ALTHEA_CTX_SSAO_COUNT_TAPS): proxy records gathered by the SSAO march; else null
+  // SSR sign test: one plane record {alpha, beta, gamma, r} of reciprocal eye depth per block of
+  // (1 << ssrPlaneShift)^2 depth texels, the whole frame in kSsrPlaneStride x kSsrPlaneRows records (r = +inf outside). Null: plain march
+  const float4* ssrPlanes;
+  int ssrPlaneShift;
   // SSR padded depth (engine scratch): the depth image with a one-texel CLAMP_TO_EDGE border, (W+2) x (H+2) floats
   const float* depthPad;
   const float* depthPadOrigin; // &padded(1, 1), i.e. texel (0, 0)

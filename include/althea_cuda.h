@@ -73,6 +73,7 @@ int althea_cuda_abi_version(void);
 #define ALTHEA_CTX_SSAO_RAY_DEPTH_PROXY 8u /* SSAO marches 16-byte ray-depth records (eye depth of a footprint's four texels along the camera's view rays) instead of the 32-byte position records; same counts bit for bit; faster on frames without sky, slightly slower with it: opt-in */
 #define ALTHEA_CTX_SSAO_COUNT_TAPS 4u /* diagnostics: the SSAO march also counts the proxy records it gathers (read with althea_cuda_diag_ssao_gathers); slower */
 #define ALTHEA_CTX_SSAO_NO_CULL 16u /* SSAO without the coarse sign test (per-block plane records in shared memory that drop the march steps which cannot flip): every tap gathers its position record, as in round 1; same counts bit for bit: A/B switch */
+#define ALTHEA_CTX_SSR_PLANE_SKIP 32u /* SSR skips the march steps whose two taps the plane records of the depth buffer (one {alpha, beta, gamma, r} of reciprocal eye depth per 32 x 32 texels) prove to project on one side of the ray, and whole runs of them inside a block; same hit mask bit for bit in the parity build. Opt-in: 95 % of the taps are skipped at 4K, but a skipped tap costs ~45 instructions against the fast march's ~55, so it only pays in the parity build */
 int althea_cuda_set_flags(althea_cuda_ctx* ctx, uint32_t flags);
 
 /* Row bands (multi-GPU split of ONE frame, BASELINE configs[3]): restricts ssr_capture / glossy_convolve / deferred_shade on

@@ -335,7 +335,11 @@ def test_properties_at_4k(ctx_fast):
     # the packed-proxy march against the fp32-texel march. With -fmad=false every decision is the same IEEE
     # operation in both kernels: bit for bit. In the fast build the compiler contracts the two kernels' inlined copies of
     # the tap arithmetic separately, so a projection within an ulp of zero can flip: at most a handful of pixels in 8.3 M.
-    for flags, bar in ((_capi.CTX_PARITY_MATH, 0), (0, 8), (_capi.CTX_PARITY_MATH | _capi.CTX_SSAO_RAY_DEPTH_PROXY, 0), (_capi.CTX_SSAO_RAY_DEPTH_PROXY, 8)):
+    # Round 2: the default path classifies taps from per-block plane records first (ssao_cull_kernel); CTX_SSAO_NO_CULL is the
+    # round-1 march over the position records. Both against the fp32-texel march.
+    NC = _capi.CTX_SSAO_NO_CULL
+    for flags, bar in ((_capi.CTX_PARITY_MATH, 0), (0, 8), (_capi.CTX_PARITY_MATH | NC, 0), (NC, 8), (_capi.CTX_PARITY_MATH | _capi.CTX_SSAO_RAY_DEPTH_PROXY, 0),
+                       (_capi.CTX_SSAO_RAY_DEPTH_PROXY, 8)):
         ctx_fast.set_flags(flags)
         _, _, ap = run()
         ctx_fast.set_flags(flags | _capi.CTX_SSAO_EXACT_TAPS)
@@ -343,6 +347,20 @@ def test_properties_at_4k(ctx_fast):
         ctx_fast.set_flags(0)
         assert int((ap != ae).sum()) <= bar, "proxy vs fp32-texel SSAO counts differ on %d pixels (flags %d)" % (int((ap != ae).sum()), flags)
         assert int((ap.int() - ae.int()).abs().max()) <= 1
+    # SSR with the plane-record sign test (opt-in) against the plain march: the same reflection image bit for bit in the parity
+    # build, hit masks within the 0.1 % bar in the fast build (whose folded step algebra differs between the two kernels)
+    n0r = W * H * 8
+    for flags, bar in ((_capi.CTX_PARITY_MATH, 0.0), (0, MASK_BAR)):
+        ctx_fast.set_flags(flags)
+        rm, _, _ = run()
+        ctx_fast.set_flags(flags | _capi.CTX_SSR_PLANE_SKIP)
+        rs, _, _ = run()
+        ctx_fast.set_flags(0)
+        am = rm[:n0r].view(torch.float16).view(H, W, 4)[..., 3] != 0
+        as_ = rs[:n0r].view(torch.float16).view(H, W, 4)[..., 3] != 0
+        assert float((am != as_).float().mean()) <= bar
+        if bar == 0.0:
+            assert torch.equal(rm, rs)
     ao = a1.view(H, W)
     empty = gbd.position[..., 3] == 0
     assert bool((ao[empty] == 255).all()) and bool((ao[~empty] <= 24).all())

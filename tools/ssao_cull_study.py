@@ -32,6 +32,7 @@ LOOSE = os.environ.get("LOOSE", "0") == "1"
 MULTI = os.environ.get("MULTI", "")  # "ray": finest level whose window holds the ray, "tap": per tap, "tile": per tile (kernel)
 UND = {}
 REACH = float(os.environ.get("REACH", "0.75"))
+ETA = os.environ.get("ETA", "0") == "1"
 KERNEL = os.environ.get("KERNEL", "0") == "1"
 SKY = os.environ.get("SKY", "1") == "1"
 
@@ -171,8 +172,21 @@ def study(kind="scene", B=8, ntiles=400, seed=1):
                     Labs = np.maximum(np.abs(-(ac + au * xx + av * yy) / c0), np.abs(L11)) + np.abs(Lx) + np.abs(Ly)
                     rayc = 1.01 * (np.abs(Lx) + np.abs(Ly)) + 1.0102 * (kappa * Labs + kNu * DMAX1 * aInv) + 9.6e-7 * DMAG * aInv + 4.8e-7 * Labs
                     rayc = np.where(kappa <= 0.01, rayc, np.inf)
-                    rr = 0.5 * (rec["rhi"][by, bx] - rec["rlo"][by, bx]) + 1.01 * (np.abs(rec["beta"][by, bx]) + np.abs(rec["gamma"][by, bx])) + 1e-6 * rec["wmax"][by, bx]
+                    rraw = 0.5 * (rec["rhi"][by, bx] - rec["rlo"][by, bx])
+                    grec = np.abs(rec["beta"][by, bx]) + np.abs(rec["gamma"][by, bx])
                     mid = wpl + 0.5 * (rec["rhi"][by, bx] + rec["rlo"][by, bx]) - L
+                    if ETA:  # the footprint's texels enter with weights lambda_k t_k: sharper rule
+                        wbar = wpl + 0.5 * (rec["rhi"][by, bx] + rec["rlo"][by, bx])
+                        dw = grec + rraw
+                        eta = dw / np.maximum(wbar - dw, 1e-30) + 2e-3
+                        eta = np.where((wbar - dw > 0) & (eta < 0.05), eta, np.inf)
+                        border = (bx == 0) | (by == 0) | (bx == rec["kind"].shape[1] - 1) | (by == rec["kind"].shape[0] - 1)
+                        eta = np.where(border, np.inf, eta)
+                        gray = np.abs(Lx) + np.abs(Ly)
+                        rr = (rraw * (1 + eta) + eta * (grec + gray)) / (1 - eta) + 1e-6 * rec["wmax"][by, bx]
+                        rayc = rayc - 1.01 * gray
+                    else:
+                        rr = rraw + 1.01 * grec + 1e-6 * rec["wmax"][by, bx]
                     lo, hi = mid - rr - rayc, mid + rr + rayc
                 else:
                     lo = wpl + rec["rlo"][by, bx] - L - slack - pad
