@@ -42,19 +42,90 @@ def broadcast_tensors(tensors: Sequence, src: int = 0, group=None, async_op: boo
     return works if async_op else None
 
 
-def allgather_rows(buf, row_bytes: int, band_rows: int, group=None):
+def allgather_rows(buf, row_bytes: int, band_rows: int, group=None, async_op: bool = False):
     """In-place all-gather of row bands: `buf` is a flat uint8 tensor of world * band_rows * row_bytes bytes whose rank-th
-    chunk has been written by this rank; on return every chunk is filled in."""
+    chunk has been written by this rank; on return (or once the returned work has been waited for) every chunk is filled in."""
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n = band_rows * row_bytes
     flat = buf.view(-1)[: world * n]
     mine = flat[rank * n:(rank + 1) * n]
     if flat.is_cuda:
-        dist.all_gather_into_tensor(flat, mine, group=group)  # NCCL in place: input is the rank-th slice of the output
-    else:
-        chunks = [flat[r * n:(r + 1) * n] for r in range(world)]
-        dist.all_gather(chunks, mine.clone(), group=group)
+        return dist.all_gather_into_tensor(flat, mine, group=group, async_op=async_op)  # NCCL in place: input is the rank-th slice of the output
+    chunks = [flat[r * n:(r + 1) * n] for r in range(world)]
+    return dist.all_gather(chunks, mine.clone(), group=group, async_op=async_op)
+
+
+class BandPipeline:
+    """Keeps `frames_in_flight` frames in flight (the reference engine keeps two, Include/Althea/Library.h:3): the replication
+    of frame k + 1's G-buffer and the assembly of frame k - 1's bands run on the collective stream while frame k's band is
+    being rendered, so in steady state a step costs max(render, collectives) instead of their sum. The collectives are issued
+    in the same order on every rank: broadcast(0), [broadcast(k + 1), render(k), all-gather(k)] for k = 0, 1, ...
+
+    `slots` are per-frame resources (each with its own G-buffer tensors, colour target, reflection buffer); `replicate(slot)`
+    and `assemble(slot)` issue the collectives and return what must be waited for (a list of works or None), `render(slot)`
+    enqueues the band's kernels on the current stream. On CUDA the collectives are issued under a side stream, so that they
+    only order after the work they depend on (recorded events), not after whatever the compute stream holds."""
+
+    def __init__(self, slots, replicate, render, assemble, cuda: bool = True):
+        self.slots, self.replicate, self.render, self.assemble, self.cuda = list(slots), replicate, render, assemble, cuda
+        n = len(self.slots)
+        self._replicated = [None] * n   # works of the broadcast into slot i
+        self._assembled = [None] * n    # works of the all-gather out of slot i
+        self._rendered = [None] * n     # CUDA event: the band of the frame in slot i has been rendered
+        self._side = None
+        self.issued = []                # ("replicate" | "render" | "assemble", frame): the order the work was enqueued in
+        if cuda:
+            import torch
+            self._side = torch.cuda.Stream()
+
+    @staticmethod
+    def _wait(works):
+        if works is None:
+            return
+        for w in works if isinstance(works, (list, tuple)) else [works]:
+            if w is not None:
+                w.wait()  # CUDA: makes the current stream wait for the collective; CPU: blocks
+
+    def _on_side(self, fn, slot, after=None):
+        if not self.cuda:
+            return fn(slot)
+        import torch
+        if after is not None:
+            self._side.wait_event(after)
+        with torch.cuda.stream(self._side):
+            return fn(slot)
+
+    def _replicate(self, k):
+        i = k % len(self.slots)
+        # the slot's G-buffer may be overwritten once the frame that used it has been rendered
+        self._replicated[i] = self._on_side(self.replicate, self.slots[i], self._rendered[i])
+        self.issued.append(("replicate", k))
+
+    def run(self, frames: int):
+        """Renders `frames` frames; returns when everything has been enqueued (CUDA) / finished (CPU)."""
+        n = len(self.slots)
+        self._replicate(0)
+        for k in range(frames):
+            i = k % n
+            if k + 1 < frames and n > 1:
+                self._replicate(k + 1)
+            self._wait(self._replicated[i])   # the G-buffer of frame k has arrived
+            self._wait(self._assembled[i])    # the colour target of slot i has been read by the all-gather of frame k - n
+            self.render(self.slots[i])
+            self.issued.append(("render", k))
+            ev = None
+            if self.cuda:
+                import torch
+                ev = torch.cuda.Event()
+                ev.record()
+                self._rendered[i] = ev
+            self._assembled[i] = self._on_side(self.assemble, self.slots[i], ev)
+            self.issued.append(("assemble", k))
+            if k + 1 < frames and n == 1:
+                self._replicate(k + 1)
+        for i in range(n):
+            self._wait(self._assembled[i])
 
 
 class BandedFrame:
@@ -86,10 +157,17 @@ class BandedFrame:
         self.deferred.aoCounts = ctx.new_image(_capi.FORMAT_R8_UINT, width, height)
         self.ssr = engine.ScreenSpaceReflection(ctx, width, height)
 
-    def broadcast_gbuffer(self, gbuffer, src: int = 0):
+    @staticmethod
+    def gbuffer_tensors(gbuffer):
+        """The attachments a rank needs replicated: depth / normal / albedo / MRO, plus the legacy position attachment when the
+        G-buffer has one (mode P; 36 B/px instead of 20)."""
+        imgs = ([gbuffer.position] if gbuffer.position is not None else []) + [gbuffer.depth, gbuffer.normal, gbuffer.albedo, gbuffer.mro]
+        return [i.tensor for i in imgs]
+
+    def broadcast_gbuffer(self, gbuffer, src: int = 0, async_op: bool = False):
         if self.world > 1:
-            broadcast_tensors([gbuffer.position.tensor, gbuffer.depth.tensor, gbuffer.normal.tensor, gbuffer.albedo.tensor, gbuffer.mro.tensor],
-                              src=src, group=self.group)
+            return broadcast_tensors(self.gbuffer_tensors(gbuffer), src=src, group=self.group, async_op=async_op)
+        return None
 
     def render(self, uniforms, gbuffer, ibl, lights, flags: int = _capi.SHADE_SKIP_TONEMAP, stream: int = 0):
         if self.y1 <= self.y0:
@@ -102,9 +180,10 @@ class BandedFrame:
         finally:
             self.ctx.set_scissor_rows(0, 0)
 
-    def gather(self):
+    def gather(self, async_op: bool = False):
         if self.world > 1:
-            allgather_rows(self._color_t, self.row_bytes, self.band, self.group)
+            return allgather_rows(self._color_t, self.row_bytes, self.band, self.group, async_op=async_op)
+        return None
 
     def color_rows(self):
         """(H, W * bytes_per_texel) uint8 view of the assembled colour target."""

@@ -125,84 +125,115 @@ def ncu_traffic(kernel: str):
     return None
 
 
-def main_bands8k(args, ctx, rank, local_rank, world, device):
-    """BASELINE configs[3]: one synthetic 7680x4320 S-rand G-buffer, rendered in row bands over the ranks."""
+def measure_bands8k(ctx, rank, local_rank, world, device, ibl, lights, steps, warmup, mode_p=False):
+    """BASELINE configs[3]: one synthetic 7680x4320 S-rand G-buffer, rendered in row bands over the ranks. Every step = NCCL
+    broadcast of the producing rank's G-buffer + band render (reflection halo recomputed locally) + NCCL all-gather of the
+    RGBA16F bands. Two measurements: `latency`, the three phases back to back for one frame, and the headline `ms_per_step`
+    with two frames in flight (althea_b200.bands.BandPipeline: the collectives of the neighbouring frames run under the band
+    render, as the reference engine's MAX_FRAMES_IN_FLIGHT = 2 would have them). Returns the record on rank 0."""
     import torch
     import torch.distributed as dist
 
     from althea_b200 import _capi, bands, engine, scene
     W8, H8 = 7680, 4320
-    ibl, lights, _, _ = build_rank_inputs(ctx, rank, 0, device, quick_ibl=True)
     g = scene.make_uniforms(W8, H8, pos=(0.0, 0.0, 0.0), yaw=0.0, pitch=0.0, light_count=N_LIGHTS)
-    gb = engine.GBufferResources(ctx, W8, H8)
-    if rank == 0:  # the producing rank; the others receive it by broadcast every step
-        gbd = scene.s_rand(g, W8, H8, device=device)
-        gb.upload(position=gbd.position, depth=gbd.depth, normal=gbd.normal, albedo=gbd.albedo, mro=gbd.mro)
-        del gbd
-    bf = bands.BandedFrame(ctx, W8, H8)
     stream = engine.current_stream_ptr(local_rank)
+    slots = []
+    gbd = scene.s_rand(g, W8, H8, device=device) if rank == 0 else None
+    for _ in range(2):
+        gb = engine.GBufferResources(ctx, W8, H8, with_position=mode_p)
+        if rank == 0:  # the producing rank; the others receive it by broadcast every step
+            gb.upload(position=gbd.position, depth=gbd.depth, normal=gbd.normal, albedo=gbd.albedo, mro=gbd.mro)
+        slots.append((gb, bands.BandedFrame(ctx, W8, H8)))
+    del gbd
+    bf0 = slots[0][1]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    comm_ms = [0.0, 0.0]
+    def render(slot):
+        slot[1].render(g, slot[0], ibl, lights, _capi.SHADE_SKIP_TONEMAP, stream)
 
-    def step(timed=False):
-        if timed:
-            ev[0].record()
-        bf.broadcast_gbuffer(gb, src=0)
-        if timed:
-            ev[1].record()
-        bf.render(g, gb, ibl, lights, _capi.SHADE_SKIP_TONEMAP, stream)
-        if timed:
-            ev[2].record()
-        bf.gather()
-        if timed:
-            ev[3].record()
-            torch.cuda.synchronize()
-            comm_ms[0] += ev[0].elapsed_time(ev[1])
-            comm_ms[1] += ev[2].elapsed_time(ev[3])
-
-    for _ in range(args.warmup):
-        step()
+    pipe = bands.BandPipeline(slots, lambda sl: sl[1].broadcast_gbuffer(sl[0], src=0, async_op=True), render, lambda sl: sl[1].gather(async_op=True))
+    pipe.run(max(warmup, 1))
     launches0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        step()
+    pipe.run(steps)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-    clocks = sampler.stop() if sampler else None
     launches = ctx.launch_count() - launches0
-    for _ in range(2):  # untimed-by-the-headline pass that splits communication from compute
-        step(timed=True)
+    # ---- one frame, phases back to back (no overlap): latency and the split between collectives and render
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    lat = torch.zeros(3, dtype=torch.float64, device=device)
+    reps = 2
+    for _ in range(reps):
+        barrier()
+        ev[0].record()
+        bf0.broadcast_gbuffer(slots[0][0], src=0)
+        ev[1].record()
+        render(slots[0])
+        ev[2].record()
+        bf0.gather()
+        ev[3].record()
+        torch.cuda.synchronize()
+        lat += torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])], dtype=torch.float64, device=device)
+    lat /= reps
+    # ---- the same frame on ONE GPU (rank 0, whole frame): the denominator of the strong-scaling efficiency
+    single = torch.zeros(1, dtype=torch.float64, device=device)
+    if rank == 0 and world > 1:
+        whole = bands.BandedFrame(ctx, W8, H8, rank=0, world=1)
+        whole.render(g, slots[0][0], ibl, lights, _capi.SHADE_SKIP_TONEMAP, stream)
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(reps):
+            whole.render(g, slots[0][0], ibl, lights, _capi.SHADE_SKIP_TONEMAP, stream)
+        ev[1].record()
+        torch.cuda.synchronize()
+        single[0] = ev[0].elapsed_time(ev[1]) / reps
+        del whole
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+        dist.all_reduce(lat, op=dist.ReduceOp.MAX)
+        dist.all_reduce(single, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    ms_step = float(t.item()) / steps
+    bcast, rend, gath = (float(v) for v in lat.tolist())
+    one = float(single.item()) if world > 1 else rend
+    gbytes = W8 * H8 * (36 if mode_p else 20)
+    return {"metric": "deferred+SSAO+SSR Mpixel/s, one 8K frame in row bands", "value": W8 * H8 / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": max(warmup, 1), "ms_per_step": ms_step, "scaling": "strong", "frames_in_flight": 2,
+            "workload": "configs[3]: one 7680x4320 S-rand G-buffer (random depth/normal/albedo/MRO, 5 %% empty), 16 lights; rows split over %d rank(s); every "
+                        "step = NCCL broadcast of the G-buffer (%.2f GB, mode %s) + band render with locally recomputed reflection halo + NCCL all-gather of "
+                        "the RGBA16F bands (%.0f MB)" % (world, gbytes / 1e9, "P" if mode_p else "D", W8 * H8 * 8 / 1e6),
+            "band_rows": bf0.band, "gpu_launches": int(launches) * world,
+            "latency": {"broadcast_ms": bcast, "render_ms": rend, "allgather_ms": gath, "frame_ms": bcast + rend + gath,
+                        "note": "one frame, phases back to back, max over ranks, device events"},
+            "exposed_comm_frac": max(0.0, ms_step - rend) / ms_step,
+            "single_gpu_ms": one, "strong_scaling_efficiency": one / (world * ms_step),
+            "roofline_chain": {"bytes_per_px": 92.0, "achieved_GBps": 92.0 * W8 * H8 / (ms_step * 1e-3) / 1e9}}
+
+
+def main_bands8k(args, ctx, rank, local_rank, world, device):
+    import torch.distributed as dist
+    ibl, lights, _, _ = build_rank_inputs(ctx, rank, 0, device, quick_ibl=True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    rec = measure_bands8k(ctx, rank, local_rank, world, device, ibl, lights, args.steps, args.warmup, mode_p=args.gbuffer_mode == "P")
+    clocks = sampler.stop() if sampler else None
     if rank == 0:
         hbm_peak, peak_src, _ = peaks()
-        gbytes = W8 * H8 * 36
-        line = {"metric": "deferred+SSAO+SSR Mpixel/s, one 8K frame in row bands", "value": W8 * H8 / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "configs[3]: one 7680x4320 S-rand G-buffer (random depth/normal/albedo/MRO, 5 %% empty), 16 lights; rows split over %d "
-                                       "rank(s); every step = NCCL broadcast of the G-buffer (%.2f GB) + band render with locally recomputed reflection halo + "
-                                       "NCCL all-gather of the RGBA16F bands (%.0f MB)" % (world, gbytes / 1e9, W8 * H8 * 8 / 1e6),
-                           "band_rows": bf.band, "l2_policy": "inputs (1.2 GB) exceed the 126 MB L2"},
-                "gpu_launches": int(launches) * world, "clocks": clocks,
-                "comm": {"broadcast_ms": comm_ms[0] / 2, "allgather_ms": comm_ms[1] / 2, "note": "rank 0, device events, second pass after the timed region"},
-                "roofline_chain": {"bytes_per_px": 92.0, "achieved_GBps": 92.0 * W8 * H8 / (ms_step * 1e-3) / 1e9,
-                                   "hbm_frac": 92.0 * W8 * H8 / (ms_step * 1e-3) / 1e9 / (hbm_peak * world), "peak_source": peak_src}}
-        print(json.dumps(line))
+        rec.update({"higher_is_better": True, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "clocks": clocks,
+                    "config": {"workload": rec.pop("workload"), "band_rows": rec.pop("band_rows"), "l2_policy": "inputs (0.66 GB) exceed the 126 MB L2"}})
+        rec["roofline_chain"]["hbm_frac"] = rec["roofline_chain"]["achieved_GBps"] / (hbm_peak * world)
+        rec["roofline_chain"]["peak_source"] = peak_src
+        print(json.dumps(rec))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -461,6 +492,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-producers", action="store_true")
+    ap.add_argument("--no-bands", action="store_true", help="with more than one rank: skip the bands8k (configs[3]) object of the line")
     ap.add_argument("--gbuffer-mode", default="D", choices=["D", "P"],
                     help="D (default): depth / normal / albedo / MRO, what the reference's GBufferResources holds; positions are reconstructed from "
                          "depth inside the frame. P: the legacy RGBA32F position attachment is an input too (SURVEY.md 8(c-bis) R5)")
@@ -647,6 +679,12 @@ def main():
                "how": "C ABI with pinned host buffers: upload of the %d G-buffer attachments per view, frame, download of the RGBA16F colour target; " % len(fmts) +
                       "double-buffered, copies overlapped with kernels on separate streams"}
 
+    # ---- BASELINE configs[3] beside the headline whenever there is more than one rank: one 8K frame in row bands, the only
+    # mode with data-path collectives (NCCL broadcast + all-gather). Outside the timed region of the headline.
+    bands8k = None
+    if world > 1 and not args.no_bands:
+        bands8k = measure_bands8k(ctx, rank, local_rank, world, device, ibl, lights, max(2, min(args.steps, 4)), 1, mode_p=False)
+
     if rank == 0:
         hbm_peak, peak_src, sm_max = peaks()
         px_frame = W4K * H4K
@@ -697,6 +735,8 @@ def main():
                                                "(10000 Hammersley samples/texel) + 512^2 BRDF LUT (1024 samples); second of two runs" % (ENV_W, ENV_H),
                                "reference_shape": "the reference's own layout: 5 equirect GGX mips 2048x1024..128x64, 10000 hash-RNG samples/texel; irradiance "
                                                   "at 512x256 (the reference's 4096x2048 irradiance is 64x the work)"}}
+        if bands8k is not None:
+            line["bands8k"] = bands8k
         if not args.no_cpu_baseline:
             from oracle import oracle as O
             O.build()

@@ -171,3 +171,80 @@ def test_bands_over_two_gpus_nccl():
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(2))
     assert res == {0: True, 1: True}
+
+
+def _pipeline_worker(rank, world, port, out):
+    """BandPipeline over gloo: frames in flight share nothing but the slot they cycle through, collectives are issued in the same
+    order on both ranks, and every assembled frame equals the single-process result."""
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        H, W, frames = 37, 16, 5
+        bh = bands.band_height(H, world)
+        y0, y1 = bands.split_rows(H, world)[rank]
+        produced = [torch.full((H, W), 10 * k + 1, dtype=torch.uint8) + torch.arange(H, dtype=torch.uint8)[:, None] for k in range(frames)]
+        slots = [dict(gb=torch.zeros(H, W, dtype=torch.uint8), out=torch.zeros(bands.padded_rows(H, world) * W, dtype=torch.uint8), frame=-1) for _ in range(2)]
+        state = dict(next_replicate=0, next_render=0, results=[])
+
+        def replicate(slot):
+            k = state["next_replicate"]
+            state["next_replicate"] += 1
+            slot["frame"] = k
+            if rank == 0:
+                slot["gb"].copy_(produced[k])   # the producing rank wrote frame k's G-buffer into the slot
+            return bands.broadcast_tensors([slot["gb"]], src=0, async_op=True)
+
+        def render(slot):
+            k = state["next_render"]
+            state["next_render"] += 1
+            assert slot["frame"] == k and torch.equal(slot["gb"], produced[k]), "frame %d rendered from a slot holding %d" % (k, slot["frame"])
+            band = (slot["gb"][y0:y1].to(torch.int32) * 2 + slot["gb"].flip(0)[y0:y1].to(torch.int32)).to(torch.uint8)  # reads far rows, as SSR does
+            slot["out"][y0 * W:y1 * W] = band.reshape(-1)
+
+        def assemble(slot):
+            w = bands.allgather_rows(slot["out"], W, bh, async_op=True)
+            state["results"].append((slot["frame"], slot, w))
+            return w
+
+        pipe = bands.BandPipeline(slots, replicate, render, assemble, cuda=False)
+        checked = []
+
+        def check_done():
+            for k, slot, w in state["results"]:
+                if k not in checked:
+                    w.wait()
+                    want = (produced[k].to(torch.int32) * 2 + produced[k].flip(0).to(torch.int32)).to(torch.uint8)
+                    assert torch.equal(slot["out"][: H * W].view(H, W), want), "frame %d on rank %d" % (k, rank)
+                    checked.append(k)
+
+        orig_render = pipe.render
+
+        def render_and_check(slot):  # a slot's previous result must be consumed before the slot is rendered into again
+            check_done()
+            orig_render(slot)
+        pipe.render = render_and_check
+        pipe.run(frames)
+        check_done()
+        assert checked == list(range(frames))
+        kinds = [k for k, _ in pipe.issued]
+        assert pipe.issued[0] == ("replicate", 0) and kinds.count("render") == frames and kinds.count("assemble") == frames
+        # frame k + 1 is replicated before frame k is rendered (two frames in flight)
+        assert pipe.issued.index(("replicate", 1)) < pipe.issued.index(("render", 0))
+        out.put((rank, pipe.issued))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_band_pipeline_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(2))
+    assert res[0] == res[1]  # the same issue order on both ranks
