@@ -974,21 +974,17 @@ int althea_cuda_ibl_precompute(althea_cuda_ctx* ctx, uint64_t env_with_mips, con
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
   const uint32_t layers = cube ? 6u : 1u;
-  if (irr)
-    for (uint32_t face = 0; face < layers; ++face) {
-      levelView(*irr, 0, face, &I.out);
-      I.face = (int)face;
-      timedLaunch(ctx, "ibl_irradiance", stream, [&] { althea_iblk::launch_ibl_irradiance(I, stream); });
-    }
+  I.faces = (int)layers; // all faces of a level in one launch (blockIdx.y): small cube levels do not fill the GPU face by face
+  if (irr) {
+    for (uint32_t face = 0; face < layers; ++face) levelView(*irr, 0, face, &I.out[face]);
+    timedLaunch(ctx, "ibl_irradiance", stream, [&] { althea_iblk::launch_ibl_irradiance(I, stream); });
+  }
   if (pre)
     for (uint32_t level = 0; level < pre->mips; ++level) {
       // equirect (reference): roughness = i/4 for the 5 images (ImageBasedLighting.cpp:384); cube: k/(n-1)
       I.roughness = cube ? (pre->mips > 1 ? (float)level / (float)(pre->mips - 1) : 0.0f) : (float)level / 4.0f;
-      for (uint32_t face = 0; face < layers; ++face) {
-        levelView(*pre, level, face, &I.out);
-        I.face = (int)face;
-        timedLaunch(ctx, "ibl_prefilter", stream, [&] { althea_iblk::launch_ibl_prefilter(I, stream); });
-      }
+      for (uint32_t face = 0; face < layers; ++face) levelView(*pre, level, face, &I.out[face]);
+      timedLaunch(ctx, "ibl_prefilter", stream, [&] { althea_iblk::launch_ibl_prefilter(I, stream); });
     }
   return endWork(ctx, sync, stream);
 }

@@ -17,7 +17,7 @@ namespace althea_iblk {
 // The precompute is a Monte-Carlo / Riemann integral checked against the oracle to 1e-3 (tests/test_ibl_parity.py), not a
 // chain of threshold decisions, so IEEE division / sqrt / libm transcendentals (10-40 SASS instructions each) are replaced
 // by MUFU forms and short polynomials with ~1e-7 error. This is where the instruction count per sample went from ~700 to
-// ~200 (profiles/r1d_ibl_*).
+// ~200 (profiles/r2_ibl_full.md).
 ADEV float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 ADEV float lg2_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 // atan on [0, 1]: Abramowitz & Stegun 4.4.49, |error| <= 2e-8 in exact arithmetic, 1.1e-7 in fp32
@@ -90,17 +90,17 @@ ADEV V3 sampleEnvMapPrecompute(const ChainView& env, V3 dir, float mip) {
   return mk3(fmaf(s1.x - s0.x, f, s0.x), fmaf(s1.y - s0.y, f, s0.y), fmaf(s1.z - s0.z, f, s0.z));
 }
 
-ADEV V3 texelNormal(const IblParams& I, int x, int y) {
+ADEV V3 texelNormal(const IblParams& I, int face, int x, int y) {
   if (I.layout == ALTHEA_IBL_LAYOUT_EQUIRECT) { // texelPos / size -> (yaw, pitch)
-    float u = (float)x / (float)I.out.w, v = (float)y / (float)I.out.h;
+    float u = (float)x / (float)I.out[0].w, v = (float)y / (float)I.out[0].h;
     float yaw = kPi * (2.0f * u - 1.0f);
     float pitch = kPi * (v - 0.5f);
     return mk3(cosf(pitch) * cosf(yaw), sinf(pitch), cosf(pitch) * sinf(yaw));
   }
-  float sc = 2.0f * (((float)x + 0.5f) / (float)I.out.w) - 1.0f;
-  float tc = 2.0f * (((float)y + 0.5f) / (float)I.out.h) - 1.0f;
+  float sc = 2.0f * (((float)x + 0.5f) / (float)I.out[0].w) - 1.0f;
+  float tc = 2.0f * (((float)y + 0.5f) / (float)I.out[0].h) - 1.0f;
   V3 d;
-  switch (I.face) {
+  switch (face) {
   case 0: d = mk3(1.0f, -tc, -sc); break;
   case 1: d = mk3(-1.0f, -tc, sc); break;
   case 2: d = mk3(sc, 1.0f, tc); break;
@@ -134,26 +134,36 @@ __global__ void __launch_bounds__(256) mip_downsample_kernel(const __grid_consta
 
 constexpr int kMaxPhiTable = 512;
 
+// LANES threads per texel: 1, 32 (a warp strides over theta), or 256 (a CTA: 64 theta lanes x 4 phi lanes, for outputs of a
+// few thousand texels such as the 32^2 cube of BASELINE configs[1], which a warp per texel leaves 148 SMs mostly idle on).
+// blockIdx.y = cube face.
 template <int LANES> __global__ void __launch_bounds__(256) ibl_irradiance_kernel(const __grid_constant__ IblParams I) {
   __shared__ float2 phiTable[kMaxPhiTable]; // (cosPhi, sinPhi), identical for every texel
+  __shared__ float4 partial[8];
   for (int j = threadIdx.x; j < I.phiSamples && j < kMaxPhiTable; j += blockDim.x) {
     float phi = (float)j * 0.5f * kPi / (float)I.phiSamples;
     phiTable[j] = make_float2(cosf(phi), sinf(phi));
   }
   __syncthreads();
+  const int face = blockIdx.y;
+  const ImgView& out = I.out[face];
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long texel = gtid / LANES;
   const int lane = (int)(gtid % LANES);
-  const long long total = (long long)I.out.w * I.out.h;
+  const long long total = (long long)out.w * out.h;
   if (texel >= total) return; // whole LANES-group exits together
-  const int x = (int)(texel % I.out.w), y = (int)(texel / I.out.w);
-  const V3 nor = texelNormal(I, x, y);
+  const int x = (int)(texel % out.w), y = (int)(texel / out.w);
+  const V3 nor = texelNormal(I, face, x, y);
   const TangentFrame tbn = localToWorld(nor);
+  // theta lanes x phi lanes of the group (lanes over phi instead, i.e. neighbouring taps per warp, measured slower: 69.9 vs
+  // 53.6 ms at 512 x 256: the integrator is bound by instruction issue, not by its loads, profiles/r2_ibl_full.md)
+  constexpr int TL = LANES == 256 ? 64 : LANES, PL = LANES == 256 ? 4 : 1;
+  const int tl = lane % TL, pl = lane / TL;
   V3 irradiance = mk3(0.0f, 0.0f, 0.0f);
-  for (int i = lane; i < I.thetaSamples; i += LANES) {
+  for (int i = tl; i < I.thetaSamples; i += TL) {
     float theta = (float)(i * 2) * kPi / (float)I.thetaSamples;
     float cosTheta = cosf(theta), sinTheta = sinf(theta);
-    for (int j = 0; j < I.phiSamples; ++j) {
+    for (int j = pl; j < I.phiSamples; j += PL) {
       float cosPhi, sinPhi;
       if (j < kMaxPhiTable) { float2 cs = phiTable[j]; cosPhi = cs.x; sinPhi = cs.y; }
       else { float phi = (float)j * 0.5f * kPi / (float)I.phiSamples; cosPhi = cosf(phi); sinPhi = sinf(phi); }
@@ -161,21 +171,31 @@ template <int LANES> __global__ void __launch_bounds__(256) ibl_irradiance_kerne
       irradiance = irradiance + (sampleEnvMapPrecompute(I.env, sampleDir, I.mip) * cosPhi) * sinPhi;
     }
   }
-  V4 r = laneReduce<LANES>(mk4(irradiance.x, irradiance.y, irradiance.z, 0.0f));
+  V4 r = laneReduce<(LANES > 32 ? 32 : LANES)>(mk4(irradiance.x, irradiance.y, irradiance.z, 0.0f));
+  if (LANES == 256) { // the CTA is one texel: add the eight warps' sums
+    if ((threadIdx.x & 31) == 0) partial[threadIdx.x >> 5] = make_float4(r.x, r.y, r.z, 0.0f);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      r = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+      for (int k = 0; k < 8; ++k) r = r + mk4(partial[k].x, partial[k].y, partial[k].z, 0.0f);
+    }
+  }
   if (lane == 0) {
     V3 c = ((kPi * xyz(r)) / (float)I.thetaSamples) / (float)I.phiSamples;
-    rowPtrW<float4>(I.out, y)[x] = make_float4(c.x, c.y, c.z, 1.0f);
+    rowPtrW<float4>(out, y)[x] = make_float4(c.x, c.y, c.z, 1.0f);
   }
 }
 
 template <int LANES> __global__ void __launch_bounds__(256) ibl_prefilter_kernel(const __grid_constant__ IblParams I) {
+  const int face = blockIdx.y;
+  const ImgView& out = I.out[face];
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long texel = gtid / LANES;
   const int lane = (int)(gtid % LANES);
-  const long long total = (long long)I.out.w * I.out.h;
+  const long long total = (long long)out.w * out.h;
   if (texel >= total) return;
-  const int x = (int)(texel % I.out.w), y = (int)(texel / I.out.w);
-  const V3 N = texelNormal(I, x, y);
+  const int x = (int)(texel % out.w), y = (int)(texel / out.w);
+  const V3 N = texelNormal(I, face, x, y);
   const V3 V = N;
   const TangentFrame tbn = localToWorld(N);
   const float a2 = I.roughness * I.roughness;
@@ -231,7 +251,7 @@ template <int LANES> __global__ void __launch_bounds__(256) ibl_prefilter_kernel
     }
   }
   V4 r = laneReduce<LANES>(mk4(acc.x, acc.y, acc.z, totalWeight));
-  if (lane == 0) rowPtrW<float4>(I.out, y)[x] = make_float4(r.x / r.w, r.y / r.w, r.z / r.w, 1.0f);
+  if (lane == 0) rowPtrW<float4>(out, y)[x] = make_float4(r.x / r.w, r.y / r.w, r.z / r.w, 1.0f);
 }
 
 __global__ void __launch_bounds__(256) brdf_lut_kernel(const __grid_constant__ LutParams Lp) {
@@ -284,17 +304,19 @@ constexpr long long kThreadPerTexelMin = 148LL * 2048LL * 2LL; // below ~2 resid
 void launch_mip_downsample(const MipGenParams& M, cudaStream_t s) { mip_downsample_kernel<<<tileGrid(M.dst.w, M.dst.h), 256, 0, s>>>(M); }
 
 void launch_ibl_irradiance(const IblParams& I, cudaStream_t s) {
-  long long texels = (long long)I.out.w * I.out.h;
-  if (texels >= kThreadPerTexelMin) ibl_irradiance_kernel<1><<<linearGrid(texels), 256, 0, s>>>(I);
-  else ibl_irradiance_kernel<32><<<linearGrid(texels * 32), 256, 0, s>>>(I);
+  const long long texels = (long long)I.out[0].w * I.out[0].h, all = texels * I.faces;
+  const unsigned faces = (unsigned)I.faces;
+  if (all >= kThreadPerTexelMin) ibl_irradiance_kernel<1><<<dim3(linearGrid(texels), faces), 256, 0, s>>>(I);
+  else if (all * 32 >= kThreadPerTexelMin) ibl_irradiance_kernel<32><<<dim3(linearGrid(texels * 32), faces), 256, 0, s>>>(I);
+  else ibl_irradiance_kernel<256><<<dim3((unsigned)texels, faces), 256, 0, s>>>(I);
 }
 
 void launch_ibl_prefilter(const IblParams& I, cudaStream_t s) {
-  long long texels = (long long)I.out.w * I.out.h;
+  const long long texels = (long long)I.out[0].w * I.out[0].h * I.faces;
   // Hash RNG: neighbouring texels draw unrelated directions, so there is no coherence to lose by giving every texel a
   // warp. Hammersley: all texels share the sequence, so one thread per texel keeps a warp's taps adjacent.
-  if (I.roughness == 0.0f || (I.sequence == ALTHEA_IBL_SEQ_HAMMERSLEY && texels >= kThreadPerTexelMin)) ibl_prefilter_kernel<1><<<linearGrid(texels), 256, 0, s>>>(I);
-  else ibl_prefilter_kernel<32><<<linearGrid(texels * 32), 256, 0, s>>>(I);
+  if (I.roughness == 0.0f || (I.sequence == ALTHEA_IBL_SEQ_HAMMERSLEY && texels >= kThreadPerTexelMin)) ibl_prefilter_kernel<1><<<dim3(linearGrid(texels / I.faces), (unsigned)I.faces), 256, 0, s>>>(I);
+  else ibl_prefilter_kernel<32><<<dim3(linearGrid(texels / I.faces * 32), (unsigned)I.faces), 256, 0, s>>>(I);
 }
 
 void launch_brdf_lut(const LutParams& L, cudaStream_t s) { brdf_lut_kernel<<<tileGrid(L.out.w, L.out.h), 256, 0, s>>>(L); }

@@ -89,9 +89,9 @@ struct MipGenParams {
 
 struct IblParams {
   ChainView env; // RGBA32F equirect with full mip chain
-  ImgView out;   // one mip level of one layer of the output (RGBA32F)
-  int layout;    // ALTHEA_IBL_LAYOUT_*
-  int face;      // cube face of `out`
+  ImgView out[6]; // one mip level of every layer (cube face) of the output (RGBA32F); blockIdx.y picks the face
+  int faces;      // 1 (equirect) or 6
+  int layout;     // ALTHEA_IBL_LAYOUT_*
   int sequence;  // ALTHEA_IBL_SEQ_*
   int numSamples;
   int thetaSamples, phiSamples;

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--env", type=int, default=4096)
     ap.add_argument("--samples", type=int, default=10000)
     ap.add_argument("--which", default="both")
+    ap.add_argument("--full-irradiance", action="store_true")
     args = ap.parse_args()
     W, H = args.env, args.env // 2
     ctx = engine.Context(0)
@@ -45,6 +46,9 @@ def main():
         irr = ctx.new_image(F32, 512, 256)
         timed("reference_shape_prefilter_5mips_hash", lambda: engine.ImageBasedLighting.precomputeResources(ctx, chain, None, pre, prefilter_samples=args.samples))
         timed("irradiance_equirect_512x256", lambda: engine.ImageBasedLighting.precomputeResources(ctx, chain, irr, None))
+        if args.full_irradiance:  # the reference's own shape: an irradiance image the size of the environment map (ImageBasedLighting.cpp:315-343)
+            irrf = ctx.new_image(F32, W, H)
+            timed("irradiance_equirect_%dx%d_reference_shape" % (W, H), lambda: engine.ImageBasedLighting.precomputeResources(ctx, chain, irrf, None))
     if args.which in ("cube", "both"):
         prec = ctx.new_image(F32, 512, 512, 6, 6)
         irrc = ctx.new_image(F32, 32, 32, 1, 6)
