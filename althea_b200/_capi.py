@@ -20,6 +20,8 @@ FORMAT_D32_SFLOAT = 126
 BYTES_PER_TEXEL = {FORMAT_R8_UINT: 1, FORMAT_R8G8B8A8_UNORM: 4, FORMAT_R16G16B16A16_SFLOAT: 8, FORMAT_R32_SFLOAT: 4,
                    FORMAT_R32G32B32A32_SFLOAT: 16, FORMAT_D32_SFLOAT: 4}
 
+IMAGE_CUBE = 1
+IMAGE_OPTIMAL_TILING = 2
 CTX_PARITY_MATH = 1
 CTX_SSAO_EXACT_TAPS = 2
 CTX_SSAO_COUNT_TAPS = 4

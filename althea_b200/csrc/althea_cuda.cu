@@ -55,24 +55,20 @@ struct althea_cuda_ctx {
   uint64_t nextHandle = 1;
   uint64_t launches = 0;
   uint32_t scissorY0 = 0, scissorY1 = 0; // rows of the final image this ctx shades; y1 == 0 => whole frame
-  // internal scratch: SSAO occluded-ray counts
-  void* aoScratch = nullptr;
-  size_t aoScratchBytes = 0;
-  // internal scratch: positions reconstructed from depth when the G-buffer has no position attachment (mode D)
-  void* positionScratch = nullptr;
-  size_t positionScratchBytes = 0;
-  // internal scratch: SSAO position-quad proxy, (W+1) x (H+1) x 32 B
-  void* quadScratch = nullptr;
-  size_t quadScratchBytes = 0;
+  // Engine-internal scratch of the per-frame stages, one set per CUDA stream the stages are called on: the reference keeps
+  // MAX_FRAMES_IN_FLIGHT = 2 frames in flight (Include/Althea/Library.h:3) and althea_sync.cuda_stream lets a host do the same
+  // here, so two frames' scratch must not alias. A set is written and consumed inside ONE stage call, in stream order.
+  struct Scratch {
+    void* ao = nullptr; size_t aoBytes = 0;             // SSAO occluded-ray counts (when the caller passes no ao_counts image)
+    void* position = nullptr; size_t positionBytes = 0; // mode D: positions reconstructed from depth
+    void* quad = nullptr; size_t quadBytes = 0;         // SSAO position-quad proxy, (W+1) x (H+1) x 32 B
+    void* plane = nullptr; size_t planeBytes = 0;       // SSAO plane records (three levels, padded), tile hand-over list, reciprocal depths
+    void* depthPad = nullptr; size_t depthPadBytes = 0; // SSR padded depth, (W+2) x (H+2) floats
+    void* ssrPlane = nullptr;                           // SSR plane records, kSsrPlaneStride x kSsrPlaneRows x 16 B
+  };
+  std::map<cudaStream_t, Scratch> scratch;
   struct RasterScratch* raster = nullptr; // scratch of the rasterising producers (draw_gbuffer / draw_shadow_cubes)
   unsigned long long* gatherCounter = nullptr; // device counters (4) of the ALTHEA_CTX_SSAO_COUNT_TAPS diagnostic
-  // internal scratch: SSAO plane records (three levels, padded) and the per-tile hand-over flags of the cull kernel
-  void* planeScratch = nullptr;
-  size_t planeScratchBytes = 0;
-  // internal scratch: SSR padded depth, (W+2) x (H+2) floats (frame_kernels.cu, ssr_depth_pad_kernel)
-  void* depthPadScratch = nullptr;
-  size_t depthPadScratchBytes = 0;
-  void* ssrPlaneScratch = nullptr; // SSR plane records, kSsrPlaneStride x kSsrPlaneRows x 16 B
   // timing
   bool timing = false;
   std::vector<TimingEntry> pending;
@@ -97,7 +93,10 @@ int fail(althea_cuda_ctx* ctx, int code, const char* fmt, ...) {
 #define CUDA_TRY(ctx, expr)                                                                              \
   do {                                                                                                   \
     cudaError_t e_ = (expr);                                                                             \
-    if (e_ != cudaSuccess) return fail(ctx, ALTHEA_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    if (e_ != cudaSuccess) {                                                                             \
+      cudaGetLastError(); /* the runtime's sticky last error must not surface in a later, unrelated call */ \
+      return fail(ctx, ALTHEA_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));                 \
+    }                                                                                                    \
   } while (0)
 
 size_t bytesPerTexel(uint32_t fmt) {
@@ -165,8 +164,21 @@ struct Scope {
   cudaStream_t stream;
 };
 
+cudaStream_t workStream(althea_cuda_ctx* ctx, const althea_sync* sync) { return (sync && sync->cuda_stream) ? (cudaStream_t)sync->cuda_stream : ctx->stream; }
+// grows one scratch allocation of the calling stream's set; contents are not preserved
+int growScratchBuf(althea_cuda_ctx* ctx, void** ptr, size_t* have, size_t need, const char* what) {
+  if (*have >= need) return ALTHEA_OK;
+  if (*ptr) { cudaDeviceSynchronize(); cudaFree(*ptr); *ptr = nullptr; *have = 0; }
+  cudaError_t e = cudaMalloc(ptr, need);
+  if (e != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(%s %zu): %s", what, need, cudaGetErrorString(e)); }
+  *have = need;
+  return ALTHEA_OK;
+}
 int beginWork(althea_cuda_ctx* ctx, const althea_sync* sync, cudaStream_t* stream) {
   *stream = (sync && sync->cuda_stream) ? (cudaStream_t)sync->cuda_stream : ctx->stream;
+  // both handles are checked before anything is enqueued: a stage never waits on a semaphore it will not signal
+  if (sync && sync->signal_sem && !find(ctx, sync->signal_sem, ResKind::Semaphore))
+    return fail(ctx, ALTHEA_ERR_BAD_HANDLE, "signal_sem %llu is not a live semaphore", (unsigned long long)sync->signal_sem);
   if (sync && sync->wait_sem) {
     Resource* s = find(ctx, sync->wait_sem, ResKind::Semaphore);
     if (!s) return fail(ctx, ALTHEA_ERR_BAD_HANDLE, "wait_sem %llu is not a live semaphore", (unsigned long long)sync->wait_sem);
@@ -453,12 +465,9 @@ void althea_cuda_destroy(althea_cuda_ctx* ctx) {
     else if (r.owned && r.dptr) cudaFree(r.dptr);
   }
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
-  if (ctx->aoScratch) cudaFree(ctx->aoScratch);
-  if (ctx->positionScratch) cudaFree(ctx->positionScratch);
-  if (ctx->quadScratch) cudaFree(ctx->quadScratch);
-  if (ctx->planeScratch) cudaFree(ctx->planeScratch);
-  if (ctx->ssrPlaneScratch) cudaFree(ctx->ssrPlaneScratch);
-  if (ctx->depthPadScratch) cudaFree(ctx->depthPadScratch);
+  for (auto& kv : ctx->scratch)
+    for (void* p : {kv.second.ao, kv.second.position, kv.second.quad, kv.second.plane, kv.second.depthPad, kv.second.ssrPlane})
+      if (p) cudaFree(p);
   if (ctx->gatherCounter) cudaFree(ctx->gatherCounter);
   freeRasterScratch(ctx->raster);
   cudaStreamDestroy(ctx->stream);
@@ -543,6 +552,9 @@ static int registerImage(althea_cuda_ctx* ctx, Resource& r, size_t pitch, size_t
 int althea_cuda_import_image(althea_cuda_ctx* ctx, int fd, uint64_t alloc_size, uint64_t offset, uint32_t vk_format, uint32_t w, uint32_t h,
                              uint32_t mips, uint32_t layers, uint32_t flags, uint64_t pitch, uint64_t* out_handle) {
   if (!ctx || !out_handle) return ALTHEA_ERR_INVALID_ARGUMENT;
+  if (fd < 0) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "import_image: fd %d is not a file descriptor", fd);
+  if (alloc_size == 0 || offset >= alloc_size) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "import_image: offset %llu does not lie inside the allocation of %llu bytes", (unsigned long long)offset, (unsigned long long)alloc_size);
+  if (!w || !h || !mips || !layers) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "import_image: empty extent %ux%u, %u mips, %u layers", w, h, mips, layers);
   if (flags & ALTHEA_IMAGE_OPTIMAL_TILING)
     return fail(ctx, ALTHEA_ERR_UNSUPPORTED,
                 "optimal-tiled images cannot be mapped as linear memory; create the image with VK_IMAGE_TILING_LINEAR or copy it to an "
@@ -571,6 +583,8 @@ int althea_cuda_import_image(althea_cuda_ctx* ctx, int fd, uint64_t alloc_size, 
 
 int althea_cuda_import_buffer(althea_cuda_ctx* ctx, int fd, uint64_t size, uint64_t offset, uint64_t* out_handle) {
   if (!ctx || !out_handle) return ALTHEA_ERR_INVALID_ARGUMENT;
+  if (fd < 0) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "import_buffer: fd %d is not a file descriptor", fd);
+  if (size == 0 || offset >= size) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "import_buffer: offset %llu does not lie inside the allocation of %llu bytes", (unsigned long long)offset, (unsigned long long)size);
   cudaExternalMemoryHandleDesc hd;
   memset(&hd, 0, sizeof hd);
   hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
@@ -597,6 +611,7 @@ int althea_cuda_import_buffer(althea_cuda_ctx* ctx, int fd, uint64_t size, uint6
 
 int althea_cuda_import_semaphore(althea_cuda_ctx* ctx, int fd, int is_timeline, uint64_t* out_handle) {
   if (!ctx || !out_handle) return ALTHEA_ERR_INVALID_ARGUMENT;
+  if (fd < 0) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "import_semaphore: fd %d is not a file descriptor", fd);
   cudaExternalSemaphoreHandleDesc sd;
   memset(&sd, 0, sizeof sd);
   sd.type = is_timeline ? cudaExternalSemaphoreHandleTypeTimelineSemaphoreFd : cudaExternalSemaphoreHandleTypeOpaqueFd;
@@ -742,27 +757,20 @@ int althea_cuda_ssr_capture(althea_cuda_ctx* ctx, const althea_global_uniforms* 
     P.y0 = (int)lo[0];
     P.y1 = (int)hi[0];
   }
+  althea_cuda_ctx::Scratch& S = ctx->scratch[workStream(ctx, sync)];
   { // the padded depth covers the whole frame even under a scissor: a ray may leave the band
-    size_t need = ((size_t)P.W + 2) * ((size_t)P.H + 2) * sizeof(float);
-    if (ctx->depthPadScratchBytes < need) {
-      if (ctx->depthPadScratch) { cudaDeviceSynchronize(); cudaFree(ctx->depthPadScratch); ctx->depthPadScratch = nullptr; ctx->depthPadScratchBytes = 0; }
-      cudaError_t e = cudaMalloc(&ctx->depthPadScratch, need);
-      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(ssr padded depth %zu): %s", need, cudaGetErrorString(e)); }
-      ctx->depthPadScratchBytes = need;
-    }
+    if ((rc = growScratchBuf(ctx, &S.depthPad, &S.depthPadBytes, ((size_t)P.W + 2) * ((size_t)P.H + 2) * sizeof(float), "ssr padded depth"))) return rc;
     P.depthPadRow = P.W + 2;
-    P.depthPad = static_cast<const float*>(ctx->depthPadScratch);
+    P.depthPad = static_cast<const float*>(S.depthPad);
     P.depthPadOrigin = P.depthPad + P.depthPadRow + 1;
   }
   P.ssrPlanes = nullptr;
   if (ctx->flags & ALTHEA_CTX_SSR_PLANE_SKIP) { // sign test over plane records of the depth buffer: the smallest blocks that cover the frame
     int shift = 3;
     while (((P.W + (1 << shift) - 1) >> shift) > kSsrPlaneStride - 1 || ((P.H + (1 << shift) - 1) >> shift) > kSsrPlaneRows - 1) ++shift;
-    if (!ctx->ssrPlaneScratch) {
-      cudaError_t e = cudaMalloc(&ctx->ssrPlaneScratch, (size_t)kSsrPlaneStride * kSsrPlaneRows * 16);
-      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(ssr plane records): %s", cudaGetErrorString(e)); }
-    }
-    P.ssrPlanes = static_cast<const float4*>(ctx->ssrPlaneScratch);
+    size_t have = S.ssrPlane ? (size_t)kSsrPlaneStride * kSsrPlaneRows * 16 : 0;
+    if ((rc = growScratchBuf(ctx, &S.ssrPlane, &have, (size_t)kSsrPlaneStride * kSsrPlaneRows * 16, "ssr plane records"))) return rc;
+    P.ssrPlanes = static_cast<const float4*>(S.ssrPlane);
     if (const char* e = getenv("ALTHEA_SSR_PLANE_SHIFT")) shift = std::max(shift, atoi(e)); // tuning: coarser blocks
     P.ssrPlaneShift = shift;
   }
@@ -788,9 +796,8 @@ int althea_cuda_glossy_convolve(althea_cuda_ctx* ctx, uint64_t reflection, const
   Resource* refl;
   int rc = getImage(ctx, reflection, ALTHEA_FORMAT_R16G16B16A16_SFLOAT, "reflection", &refl);
   if (rc) return rc;
-  cudaStream_t stream;
-  if ((rc = beginWork(ctx, sync, &stream))) return rc;
-  const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
+  // everything that can fail is checked before beginWork enqueues the wait on the caller's semaphore: an error return after it
+  // would leave signal_sem unsignalled and the Vulkan side waiting for a timeline value that never arrives
   uint32_t lo[kMaxMips], hi[kMaxMips];
   if (ctx->scissorY1) {
     if (ctx->scissorY1 > refl->h) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "scissor rows exceed the frame height %u", refl->h);
@@ -798,6 +805,9 @@ int althea_cuda_glossy_convolve(althea_cuda_ctx* ctx, uint64_t reflection, const
   } else {
     for (uint32_t level = 0; level < refl->mips; ++level) { lo[level] = 0; hi[level] = mipDim(refl->h, level); }
   }
+  cudaStream_t stream;
+  if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
   for (uint32_t level = 1; level < refl->mips; ++level) { // ReflectionBuffer.cpp:224-278
     if (hi[level] <= lo[level]) continue;
     ConvolveParams C;
@@ -829,49 +839,31 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
   if ((rc = getImage(ctx, ao_counts, ALTHEA_FORMAT_R8_UINT, "ao_counts", &ao, true))) return rc;
   if ((flags & ALTHEA_SHADE_AO_FROM_IMAGE) && !ao) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "AO_FROM_IMAGE needs ao_counts");
   const bool needAo = !(flags & ALTHEA_SHADE_NO_SSAO);
+  althea_cuda_ctx::Scratch& S = ctx->scratch[workStream(ctx, sync)];
   if (needAo) {
     if (ao) {
       if ((int)ao->w != P.W || (int)ao->h != P.H) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "ao_counts must be %dx%d", P.W, P.H);
       levelView(*ao, 0, 0, &P.ao);
     } else {
-      size_t need = (size_t)P.W * P.H;
-      if (ctx->aoScratchBytes < need) {
-        if (ctx->aoScratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->aoScratch); ctx->aoScratch = nullptr; ctx->aoScratchBytes = 0; }
-        cudaError_t e = cudaMalloc(&ctx->aoScratch, need);
-        if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(ao scratch %zu): %s", need, cudaGetErrorString(e)); }
-        ctx->aoScratchBytes = need;
-      }
-      P.ao.ptr = ctx->aoScratch; P.ao.w = P.W; P.ao.h = P.H; P.ao.pitch = P.W;
+      if ((rc = growScratchBuf(ctx, &S.ao, &S.aoBytes, (size_t)P.W * P.H, "ao scratch"))) return rc;
+      P.ao.ptr = S.ao; P.ao.w = P.W; P.ao.h = P.H; P.ao.pitch = P.W;
     }
   }
   const bool reconstruct = P.position.ptr == nullptr; // mode D
   if (reconstruct) {
-    size_t need = (size_t)P.W * P.H * 16;
-    if (ctx->positionScratchBytes < need) {
-      if (ctx->positionScratch) { cudaDeviceSynchronize(); cudaFree(ctx->positionScratch); ctx->positionScratch = nullptr; ctx->positionScratchBytes = 0; }
-      cudaError_t e = cudaMalloc(&ctx->positionScratch, need);
-      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(position scratch %zu): %s", need, cudaGetErrorString(e)); }
-      ctx->positionScratchBytes = need;
-    }
-    P.position.ptr = ctx->positionScratch; P.position.w = P.W; P.position.h = P.H; P.position.pitch = P.W * 16;
+    if ((rc = growScratchBuf(ctx, &S.position, &S.positionBytes, (size_t)P.W * P.H * 16, "position scratch"))) return rc;
+    P.position.ptr = S.position; P.position.w = P.W; P.position.h = P.H; P.position.pitch = P.W * 16;
   }
   const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
   const bool computeAo = needAo && !(flags & ALTHEA_SHADE_AO_FROM_IMAGE);
   const bool exactTaps = ctx->flags & ALTHEA_CTX_SSAO_EXACT_TAPS;
   if (computeAo && !exactTaps) {
-    P.quadPitch = ((size_t)P.W + 1) * 32;
-    size_t need = P.quadPitch * ((size_t)P.H + 1);
-    if (ctx->quadScratchBytes < need) {
-      if (ctx->quadScratch) { cudaStreamSynchronize(ctx->stream); cudaDeviceSynchronize(); cudaFree(ctx->quadScratch); ctx->quadScratch = nullptr; ctx->quadScratchBytes = 0; }
-      cudaError_t e = cudaMalloc(&ctx->quadScratch, need);
-      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(ssao quad scratch %zu): %s", need, cudaGetErrorString(e)); }
-      ctx->quadScratchBytes = need;
-    }
-    P.quads = ctx->quadScratch;
+    if ((rc = growScratchBuf(ctx, &S.quad, &S.quadBytes, ((size_t)P.W + 1) * 32 * ((size_t)P.H + 1), "ssao quad scratch"))) return rc;
+    P.quads = S.quad;
     P.quadRow = P.W + 1;
     P.quadKind = (ctx->flags & ALTHEA_CTX_SSAO_RAY_DEPTH_PROXY) ? 1 : 0;
     P.quadPitch = ((size_t)P.W + 1) * (P.quadKind ? 16 : 32);
-    P.quadsOrigin = static_cast<const char*>(ctx->quadScratch) + ((size_t)P.quadRow + 1) * (P.quadKind ? 16 : 32);
+    P.quadsOrigin = static_cast<const char*>(S.quad) + ((size_t)P.quadRow + 1) * (P.quadKind ? 16 : 32);
   }
   // the coarse sign test needs a perspective camera's G-buffer model (it degrades to the march tile by tile when the
   // positions do not fit it) and the position records; the ray-depth records keep their own march
@@ -892,16 +884,11 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
     need += ((size_t)((P.W + 15) / 16) * ((P.H + 15) / 16) + 1) * sizeof(unsigned);
     const size_t recipOff = (need + 255) & ~(size_t)255;
     need = recipOff + (size_t)P.W * P.H * sizeof(float);
-    if (ctx->planeScratchBytes < need) {
-      if (ctx->planeScratch) { cudaDeviceSynchronize(); cudaFree(ctx->planeScratch); ctx->planeScratch = nullptr; ctx->planeScratchBytes = 0; }
-      cudaError_t e = cudaMalloc(&ctx->planeScratch, need);
-      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(ssao plane scratch %zu): %s", need, cudaGetErrorString(e)); }
-      ctx->planeScratchBytes = need;
-    }
+    if ((rc = growScratchBuf(ctx, &S.plane, &S.planeBytes, need, "ssao plane scratch"))) return rc;
     for (int l = 0; l < 3; ++l)
-      P.ssaoPlanes[l] = reinterpret_cast<const float4*>(static_cast<const char*>(ctx->planeScratch) + off[l]) + ((size_t)kSsaoPlanePad * P.ssaoPlaneRow[l] + kSsaoPlanePad);
-    P.ssaoTileList = reinterpret_cast<unsigned*>(static_cast<char*>(ctx->planeScratch) + listOff);
-    P.ssaoRecip = reinterpret_cast<float*>(static_cast<char*>(ctx->planeScratch) + recipOff);
+      P.ssaoPlanes[l] = reinterpret_cast<const float4*>(static_cast<const char*>(S.plane) + off[l]) + ((size_t)kSsaoPlanePad * P.ssaoPlaneRow[l] + kSsaoPlanePad);
+    P.ssaoTileList = reinterpret_cast<unsigned*>(static_cast<char*>(S.plane) + listOff);
+    P.ssaoRecip = reinterpret_cast<float*>(static_cast<char*>(S.plane) + recipOff);
   }
   if (computeAo && !exactTaps && (ctx->flags & ALTHEA_CTX_SSAO_COUNT_TAPS)) {
     if (!ctx->gatherCounter) {

@@ -485,4 +485,4 @@ class DeferredPass:
         self.ctx._check(self.ctx._lib.althea_cuda_deferred_shade(
             self.ctx._ptr, C.byref(globalUniforms), C.byref(gb), C.byref(ib), lights.buffer.handle if lights else 0,
             lights.shadow_handle if lights else 0, ssr.getReflectionBuffer().image.handle, self.colorTarget.handle,
-            self.aoCounts.handle, flags, ref))
+            self.aoCounts.handle if self.aoCounts is not None else 0, flags, ref))  # no image: the ctx's per-stream AO scratch

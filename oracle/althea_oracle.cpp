@@ -291,6 +291,20 @@ void oracle_reconstruct_position(const OracleGlobalUniforms* g, float u, float v
   V3 p = reconstructPosition(*g, u, v, dRaw); out3[0] = p.x; out3[1] = p.y; out3[2] = p.z;
 }
 
+// Mode D (today's GBufferResources has no position attachment, Src/DeferredRendering.cpp:42-99): the position image the lighting
+// pass works on = reconstructPosition(uv, depth) at every pixel centre, empty (0, 0, 0, 0) where normal.a == 0 (SSR.frag:136-141).
+void oracle_reconstruct_positions(const OracleGlobalUniforms* g, int W, int H, const float* depth, const uint16_t* normal16, float* outPosition) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      float* o = outPosition + 4 * ((size_t)y * W + x);
+      if (halfToFloat(normal16[4 * ((size_t)y * W + x) + 3]) == 0.0f) { o[0] = o[1] = o[2] = o[3] = 0.0f; continue; }
+      const float u = ((float)x + 0.5f) / (float)W, v = ((float)y + 0.5f) / (float)H;
+      V3 p = reconstructPosition(*g, u, v, depth[(size_t)y * W + x]);
+      o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = 1.0f;
+    }
+}
+
 // SSR.frag main (:135-149) + A9 blend-on-write onto a (0,0,0,0) clear, stored RGBA16F.
 // outHit (optional): 1 where the march returned a lit sample. outSteps (optional): march steps taken.
 void oracle_ssr_capture(const OracleGlobalUniforms* g, const OracleGBuffer* gb, const OracleIBL* ibl, const OracleLights* li,

@@ -83,6 +83,7 @@ def lib():
         _lib.oracle_sample_cube.restype = C.c_float
         _lib.oracle_sample_cube.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
         _lib.oracle_reconstruct_position.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        _lib.oracle_reconstruct_positions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.oracle_ibl_prefilter.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                               C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     return _lib
@@ -124,6 +125,14 @@ def sample(data, w, h, mips, fmt, addr, uvl):
     uvl = _c(uvl, np.float32).reshape(-1, 3)
     out = np.empty((uvl.shape[0], 4), np.float32)
     lib().oracle_sample(_p(data), w, h, mips, fmt, addr, _p(uvl), uvl.shape[0], _p(out))
+    return out
+
+
+def reconstruct_positions(g: GlobalUniforms, W, H, depth, normal_u16):
+    """(H, W, 4) float32 position image of mode D: reconstructPosition at every pixel centre, empty where normal.a == 0."""
+    depth, normal_u16 = _c(depth, np.float32), _c(normal_u16, np.uint16)
+    out = np.zeros((H, W, 4), np.float32)
+    lib().oracle_reconstruct_positions(C.addressof(g), int(W), int(H), _p(depth), _p(normal_u16), _p(out))
     return out
 
 

@@ -459,3 +459,77 @@ def test_mode_d_positions_from_depth(request, oracle, which):
         ok = (np.abs(got_col - want_col) <= 1e-3 * np.maximum(1.0, np.abs(want_col))).all(axis=-1)
         assert ok.mean() >= 0.999
     assert (got_ao[nrm_a == 0] == 255).all() and (got_ao[nrm_a != 0] <= 24).all()
+    # ... and against the ORACLE directly (mode D in the fast build is what bench.py times): SSR hit mask, AO counts, colour
+    gd.ssr.captureReflection(fd.uniforms, gd.gbuffer, gd.ibl, gd.lights)
+    gd.ssr.convolveReflectionBuffer()
+    gd.deferred.draw(fd.uniforms, gd.gbuffer, gd.ibl, gd.lights, gd.ssr, _capi.SHADE_SKIP_TONEMAP)
+    fr = fd.oracle_frame()  # fd.position now holds the restatement's reconstructed positions
+    refl, hit, _ = oracle.ssr_capture(fr)
+    chain = oracle.glossy_convolve(refl)
+    ao = oracle.ssao(fr)
+    col = oracle.deferred_shade(fr, chain, 5, oracle.SKIP_TONEMAP, ao)
+    got_hit = half_to_float(gd.reflection_level(0))[..., 3] != 0
+    got_ao, got_col = gd.ao_counts(), gd.color()
+    if which == "parity":
+        assert np.array_equal(got_hit, hit != 0) and np.array_equal(got_ao, ao)
+    else:
+        assert (got_hit != (hit != 0)).mean() <= MASK_BAR and (got_ao != ao).mean() <= MASK_BAR
+    same = (got_hit == (hit != 0)) & (got_ao == ao)
+    ok = close(got_col, col).all(axis=-1)
+    assert ok[same].mean() >= 0.999, "max abs colour error %.3g" % np.abs(got_col - col)[same].max()
+
+
+def test_4k_frame_against_the_oracle(ctx_parity, oracle):
+    """BASELINE configs[2]'s shape against the oracle itself (not against another GPU path): one 3840 x 2160 S-scene frame, four
+    lights with 64^2 shadow cubes, parity build, mode D. SSR hit mask and SSAO counts bit for bit over all 8.3 M pixels (the
+    coarse sign test, the tap compaction and the position-record filter all sit in front of these decisions at this size);
+    colour on the RGBA32F target to the relative bar, with the absolute error reported."""
+    import torch
+
+    from althea_b200 import _capi, engine, scene
+    from helpers import golden_env, golden_lut, ibl_standins
+    W, H, dev, n_lights, res = 3840, 2160, "cuda:0", 4, 64
+    ctx = ctx_parity
+    g = scene.make_uniforms(W, H, pos=(0.0, 2.0, 6.0), yaw=0.0, pitch=-0.25, light_count=n_lights)
+    sc = scene.make_scene(64, device=dev)
+    gbd = scene.s_scene(g, W, H, sc, device=dev)
+    lights_t = scene.make_lights(n_lights, device=dev)
+    cubes = scene.shadow_cubes(sc, lights_t, res)
+    gb = engine.GBufferResources(ctx, W, H, with_position=False)
+    gb.upload(depth=gbd.depth, normal=gbd.normal, albedo=gbd.albedo, mro=gbd.mro)
+    lights = engine.PointLightCollection(ctx, n_lights, res, True)
+    lnp = lights_t.cpu().numpy()
+    for i in range(n_lights):
+        lights.setLight(i, engine.PointLight(lnp[i, 0:3], lnp[i, 4:7]))
+    lights.updateResource()
+    lights.setShadowMaps(cubes.cpu().numpy())
+    env, lut = golden_env(), golden_lut()
+    pre, pre_size, irr = ibl_standins(env)
+    F32 = _capi.FORMAT_R32G32B32A32_SFLOAT
+    ibl = engine.IBLResources(ctx.image_from_numpy(env, F32, env.shape[1], env.shape[0]), ctx.image_from_numpy(pre, F32, pre_size[0], pre_size[1], 5),
+                              ctx.image_from_numpy(irr, F32, irr.shape[1], irr.shape[0]), ctx.image_from_numpy(lut, _capi.FORMAT_R8G8B8A8_UNORM, lut.shape[1], lut.shape[0]))
+    ssr = engine.ScreenSpaceReflection(ctx, W, H)
+    dp = engine.DeferredPass(ctx, W, H, F32)
+    ssr.captureReflection(g, gb, ibl, lights)
+    ssr.convolveReflectionBuffer()
+    dp.draw(g, gb, ibl, lights, ssr, _capi.SHADE_SKIP_TONEMAP)
+    torch.cuda.synchronize()
+    # the oracle on the same inputs; its position attachment = its own reconstructPosition of every covered pixel, which the
+    # parity build reproduces bit for bit (test_mode_d_positions_from_depth): read back from the engine's scratch via mode P
+    d = gbd.numpy()
+    og = oracle.GlobalUniforms.from_buffer_copy(bytes(g))
+    pos = oracle.reconstruct_positions(og, W, H, d["depth"], d["normal"])
+    fr = oracle.Frame(og, W, H, pos, d["depth"], d["normal"], d["albedo"], d["mro"], env, pre, pre_size, 5, irr, lut, lnp, cubes.cpu().numpy(), res)
+    refl, hit, _ = oracle.ssr_capture(fr)
+    chain = oracle.glossy_convolve(refl)
+    ao = oracle.ssao(fr)
+    col = oracle.deferred_shade(fr, chain, 5, oracle.SKIP_TONEMAP, ao)
+    got_refl = ssr.getReflectionBuffer().image.level_numpy(0).view(np.uint16).reshape(H, W, 4)
+    assert np.array_equal(half_to_float(got_refl)[..., 3] != 0, hit != 0)
+    assert 0.05 < hit.mean() < 0.6
+    assert np.array_equal(dp.aoCounts.tensor.view(H, W).cpu().numpy(), ao)
+    got_col = dp.colorTarget.tensor.view(torch.float32).view(H, W, 4).cpu().numpy()
+    err = np.abs(got_col - col)
+    ok = close(got_col, col).all(axis=-1)
+    assert ok.mean() >= 0.9995, "colour off the bar on %.4f %% of pixels, max abs error %.3g" % (100 * (1 - ok.mean()), err.max())
+    assert float(np.percentile(err, 99.9)) <= 1e-3, "99.9th percentile of the absolute colour error: %.3g" % np.percentile(err, 99.9)

@@ -92,6 +92,38 @@ def test_cube_layout_hammersley(ctx_fast, oracle, env_setup):
         assert rel_close(got, want, 1e-3).all(), level
 
 
+def test_config1_shape_probe_texels(ctx_fast, oracle):
+    """BASELINE configs[1] at its own shape: 4096 x 2048 equirect environment -> 32^2 irradiance cube (300 x 150 samples) and
+    512^2 six-mip GGX prefilter cube with 10 000 Hammersley samples per texel; probe texels of levels 0, 3 and 5 (and of the
+    irradiance cube) against the oracle."""
+    import torch
+
+    from althea_b200 import _capi, engine, scene
+    W, H = 4096, 2048
+    env = scene.procedural_env(W, H).numpy()
+    chain_ref, mips = oracle.env_mip_chain(env)
+    F32 = _capi.FORMAT_R32G32B32A32_SFLOAT
+    img = ctx_fast.new_image(F32, W, H, mips)
+    img.tensor[: W * H * 16].copy_(torch.from_numpy(env.view(np.uint8).reshape(-1)))
+    engine.ImageBasedLighting.generateMipMaps(ctx_fast, img)
+    irr = ctx_fast.new_image(F32, 32, 32, 1, 6)
+    pre = ctx_fast.new_image(F32, 512, 512, 6, 6)
+    engine.ImageBasedLighting.precomputeResources(ctx_fast, img, irr, pre, layout=_capi.IBL_LAYOUT_CUBE, sequence=_capi.IBL_SEQ_HAMMERSLEY,
+                                                  prefilter_samples=10000)
+    torch.cuda.synchronize()
+    tex = [(x, y, f) for f in range(6) for (x, y) in ((0, 0), (13, 21), (31, 31))]
+    want = oracle.ibl_irradiance(chain_ref, W, H, mips, 32, 32, tex, layout=oracle.LAYOUT_CUBE)
+    got = np.array([irr.level_numpy(0, f).view(np.float32).reshape(32, 32, 4)[y, x] for x, y, f in tex])
+    assert rel_close(got, want, 1e-3).all(), float(np.abs(got - want).max())
+    for level in (0, 3, 5):
+        s = 512 >> level
+        tex = [(x % s, y % s, f) for f in range(6) for (x, y) in ((0, 0), (101, 377), (511, 511))]
+        want = oracle.ibl_prefilter(chain_ref, W, H, mips, s, s, level / 5.0, tex, layout=oracle.LAYOUT_CUBE, num_samples=10000, sequence=oracle.SEQ_HAMMERSLEY)
+        got = np.array([pre.level_numpy(level, f).view(np.float32).reshape(s, s, 4)[y, x] for x, y, f in tex])
+        assert rel_close(got, want, 1e-3).all(), (level, float(np.max(np.abs(got - want) / np.maximum(1, np.abs(want)))))
+        assert np.isfinite(pre.level_numpy(level, 0).view(np.float32)).all()
+
+
 def test_brdf_lut(ctx_fast, oracle):
     import torch
 

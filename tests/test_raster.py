@@ -827,40 +827,73 @@ def test_helmet_fixture_answer_is_reproducible(oracle):
 
 
 @pytest.mark.gpu
-def test_gpu_helmet_frame(ctx_fast, oracle):
-    """configs[0] end to end on the GPU: G-buffer of the helmet at 1280 x 720 (depth CRC equal to the committed answer, attributes
-    against the live restatement), then SSR, glossy mips, SSAO and deferred shading on it in the parity build against the
-    frame oracle fed with the same G-buffer."""
+def test_gpu_helmet_frame(ctx_fast, ctx_parity, oracle):
+    """BASELINE configs[0] end to end on the GPU at its own shape: G-buffer of the helmet at 1280 x 720 (depth CRC equal to the
+    committed answer, attributes against the live restatement), omni shadow cubes of two lights rendered from the same mesh,
+    then SSR, glossy mips, SSAO and deferred shading in the PARITY build with a real IBL set, against the frame oracle fed with
+    the same G-buffer and cubes: hit mask and AO counts bit for bit, colour to the bar (max abs error reported)."""
     import zlib
 
     import torch
 
     from althea_b200 import _capi, engine
     from helmet_fixture import CAMERA, GOLDEN, SIZE, helmet_primitives
+    from helpers import FrameData, GpuFrame, half_to_float
     d = np.load(GOLDEN)
     prims = helmet_primitives()
     W, H = SIZE
     g = CAMERA()
-    got, gb = _gpu_gbuffer(ctx_fast, g, prims, W, H)
+    got, gb_fast = _gpu_gbuffer(ctx_fast, g, prims, W, H)
     assert zlib.crc32(np.ascontiguousarray(got["depth"]).tobytes()) == int(d["depth_crc"][0])
     assert int((got["depth"] < 1).sum()) == int(d["coverage"][0])
     want = oracle.draw_gbuffer(list(g.projection), list(g.view), prims, W, H)
     _compare_gbuffer(got, want)
-    # the deferred chain on the produced G-buffer
-    from helpers import FrameData, GpuFrame
-    small = GpuFrame(ctx_fast, FrameData("scene", 32, 18, n_lights=0))
-    ssr = engine.ScreenSpaceReflection(ctx_fast, W, H)
-    dp = engine.DeferredPass(ctx_fast, W, H, _capi.FORMAT_R32G32B32A32_SFLOAT)
-    ssr.captureReflection(g, gb, small.ibl, None)
-    ssr.convolveReflectionBuffer()
-    dp.draw(g, gb, small.ibl, None, ssr, _capi.SHADE_SKIP_TONEMAP)
+    cov = want["tri"] != NONE
+    # ---- the deferred chain on that G-buffer, parity build
+    ctx = ctx_parity
+    up = model.UploadedModel(ctx, prims)
+    gb = engine.GBufferResources(ctx, W, H)
+    engine.SceneToGBufferPass(ctx).draw(g, up, gb)
+    n_lights, res = 2, 128
+    g.lightCount = n_lights
+    lights = engine.PointLightCollection(ctx, n_lights, res, True)
+    lights.setLight(0, engine.PointLight((1.5, 1.2, 2.0), (30.0, 26.0, 20.0)))
+    lights.setLight(1, engine.PointLight((-2.0, 0.5, 1.0), (8.0, 12.0, 20.0)))
+    lights.updateResource()
+    lights.drawShadowMaps([up])
     torch.cuda.synchronize()
-    col = dp.colorTarget.tensor.view(torch.float32).view(H, W, 4)
-    cov = torch.from_numpy(want["tri"] != NONE).to(col.device)
-    assert bool(torch.isfinite(col).all())
-    assert float(col[..., :3][cov].mean()) > 0.01
-    ao = dp.aoCounts.tensor.view(H, W)
-    assert bool((ao[cov] <= 24).all()) and bool((ao[~cov] == 255).all()) and float((ao[cov] > 0).float().mean()) > 0.2
+    tiny = FrameData("scene", 32, 18, n_lights=0)  # for its IBL set: the golden environment, its mips, the reference's LUT
+    ibl = GpuFrame(ctx, tiny).ibl
+    ssr = engine.ScreenSpaceReflection(ctx, W, H)
+    dp = engine.DeferredPass(ctx, W, H, _capi.FORMAT_R32G32B32A32_SFLOAT)
+    ssr.captureReflection(g, gb, ibl, lights)
+    ssr.convolveReflectionBuffer()
+    dp.draw(g, gb, ibl, lights, ssr, _capi.SHADE_SKIP_TONEMAP)
+    torch.cuda.synchronize()
+    arr = lambda img, dt, c: img.tensor.view(dt).view(H, W, c).cpu().numpy()  # noqa: E731
+    position, depth = arr(gb.position, torch.float32, 4), gb.depth.tensor.view(torch.float32).view(H, W).cpu().numpy()
+    normal = gb.normal.tensor.view(torch.int16).view(H, W, 4).cpu().numpy().view(np.uint16)
+    albedo, mro = arr(gb.albedo, torch.uint8, 4), arr(gb.mro, torch.uint8, 4)
+    cubes = lights.shadow_map.tensor.view(torch.float32).view(n_lights, 6, res, res).cpu().numpy()
+    assert 0.01 < float((cubes < 1).mean()) < 0.9                       # the helmet shadows part of every cube
+    og = oracle.GlobalUniforms.from_buffer_copy(bytes(g))
+    fr = oracle.Frame(og, W, H, position, depth, normal, albedo, mro, tiny.env, tiny.pre, tiny.pre_size, 5, tiny.irr, tiny.lut, lights._lights.copy(), cubes, res)
+    refl, hit, _ = oracle.ssr_capture(fr)
+    chain = oracle.glossy_convolve(refl)
+    ao = oracle.ssao(fr)
+    col = oracle.deferred_shade(fr, chain, 5, oracle.SKIP_TONEMAP, ao)
+    got_refl = ssr.getReflectionBuffer().image.level_numpy(0).view(np.uint16).reshape(H, W, 4)
+    got_hit = half_to_float(got_refl)[..., 3] != 0
+    assert hit[cov].mean() > 0.01, "the helmet must reflect itself somewhere"
+    assert np.array_equal(got_hit, hit != 0)
+    got_ao = dp.aoCounts.tensor.view(H, W).cpu().numpy()
+    assert np.array_equal(got_ao, ao)
+    assert (ao[cov] <= 24).all() and (ao[~cov] == 255).all() and (ao[cov] > 0).mean() > 0.2
+    got_col = dp.colorTarget.tensor.view(torch.float32).view(H, W, 4).cpu().numpy()
+    err = np.abs(got_col - col)
+    ok = (err <= 1e-3 * np.maximum(1.0, np.abs(col))).all(axis=-1)
+    assert ok.mean() >= 0.9995, "colour off the bar on %.4f %% of pixels, max abs error %.3g" % (100 * (1 - ok.mean()), err.max())
+    assert float(np.percentile(err, 99.9)) <= 1e-3, "99.9th percentile of the absolute colour error on the RGBA32F target: %.3g" % np.percentile(err, 99.9)
 
 
 @pytest.mark.gpu
