@@ -776,14 +776,14 @@ int althea_cuda_ssr_capture(althea_cuda_ctx* ctx, const althea_global_uniforms* 
   }
   if (P.ssrPlanes && (ctx->flags & ALTHEA_CTX_SSAO_COUNT_TAPS)) { // diagnostics: the skip kernel's tap counters (read with althea_cuda_diag_ssao_cull)
     if (!ctx->gatherCounter) {
-      cudaError_t e = cudaMalloc(&ctx->gatherCounter, 4 * sizeof(unsigned long long));
+      cudaError_t e = cudaMalloc(&ctx->gatherCounter, 80 * sizeof(unsigned long long));
       if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(gather counter): %s", cudaGetErrorString(e)); }
     }
     P.gatherCounter = ctx->gatherCounter;
   }
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
-  if (P.gatherCounter) cudaMemsetAsync(P.gatherCounter, 0, 4 * sizeof(unsigned long long), stream);
+  if (P.gatherCounter) cudaMemsetAsync(P.gatherCounter, 0, 80 * sizeof(unsigned long long), stream);
   const bool parity = ctx->flags & ALTHEA_CTX_PARITY_MATH;
   timedLaunch(ctx, "ssr_depth_pad", stream, [&] { parity ? althea_parity::launch_ssr_depth_pad(P, stream) : althea_fast::launch_ssr_depth_pad(P, stream); });
   if (P.ssrPlanes) timedLaunch(ctx, "ssr_planes", stream, [&] { parity ? althea_parity::launch_ssr_planes(P, stream) : althea_fast::launch_ssr_planes(P, stream); });
@@ -892,14 +892,14 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
   }
   if (computeAo && !exactTaps && (ctx->flags & ALTHEA_CTX_SSAO_COUNT_TAPS)) {
     if (!ctx->gatherCounter) {
-      cudaError_t e = cudaMalloc(&ctx->gatherCounter, 4 * sizeof(unsigned long long));
+      cudaError_t e = cudaMalloc(&ctx->gatherCounter, 80 * sizeof(unsigned long long));
       if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(gather counter): %s", cudaGetErrorString(e)); }
     }
     P.gatherCounter = ctx->gatherCounter;
   }
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
-  if (P.gatherCounter) cudaMemsetAsync(P.gatherCounter, 0, 4 * sizeof(unsigned long long), stream);
+  if (P.gatherCounter) cudaMemsetAsync(P.gatherCounter, 0, 80 * sizeof(unsigned long long), stream);
   if (reconstruct)
     timedLaunch(ctx, "reconstruct_position", stream, [&] { parity ? althea_parity::launch_reconstruct_position(P, stream) : althea_fast::launch_reconstruct_position(P, stream); });
   if (computeAo) {
@@ -1040,6 +1040,13 @@ int althea_cuda_diag_ssao_exact_fallbacks(althea_cuda_ctx* ctx, uint64_t* out_ta
   return ALTHEA_OK;
 }
 
+// undocumented tuning aid: the per-level / per-tap histogram the counting cull kernel fills (76 values after the four counters)
+int althea_cuda_diag_ssao_cull_histogram(althea_cuda_ctx* ctx, uint64_t* out76) {
+  if (!ctx || !out76 || !ctx->gatherCounter) return ALTHEA_ERR_INVALID_ARGUMENT;
+  CUDA_TRY(ctx, cudaDeviceSynchronize());
+  CUDA_TRY(ctx, cudaMemcpy(out76, ctx->gatherCounter + 4, 76 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return ALTHEA_OK;
+}
 int althea_cuda_diag_ssao_cull(althea_cuda_ctx* ctx, uint64_t out_counts[4]) {
   if (!ctx || !out_counts) return ALTHEA_ERR_INVALID_ARGUMENT;
   if (!ctx->gatherCounter) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "no SSAO launch has run with ALTHEA_CTX_SSAO_COUNT_TAPS set");

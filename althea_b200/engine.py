@@ -155,7 +155,9 @@ class Context:
         self._check(self._lib.althea_cuda_download(self._ptr, res.handle, C.c_void_p(host_ptr), nbytes, C.c_void_p(stream)))
 
     def synchronize(self, stream: int = 0):
-        self._check(self._lib.althea_cuda_synchronize(self._ptr, C.c_void_p(stream)))
+        """Waits for the work issued on `stream`. stream None/0 => torch's current stream, the one the engine's calls run on by
+        default (_sync_ref); the ctx's private stream carries nothing unless a host without torch drives the C ABI."""
+        self._check(self._lib.althea_cuda_synchronize(self._ptr, C.c_void_p(stream if stream else current_stream_ptr(self.device))))
 
     # ---- instrumentation ----
     def enable_timing(self, on: bool = True):
@@ -387,6 +389,8 @@ class ImageBasedLighting:
         chain = ctx.new_image(_capi.FORMAT_R32G32B32A32_SFLOAT, W, H, mips)
         torch = _torch()
         chain.tensor[: W * H * 16].copy_(torch.from_numpy(env_rgba.view(np.uint8).reshape(-1)))
+        if stream and stream != current_stream_ptr(ctx.device):
+            torch.cuda.current_stream(ctx.device).synchronize()  # the upload ran on torch's stream, the kernels run on `stream`
         ImageBasedLighting.generateMipMaps(ctx, chain, stream)
         irr = ctx.new_image(_capi.FORMAT_R32G32B32A32_SFLOAT, W, H)
         pre = ctx.new_image(_capi.FORMAT_R32G32B32A32_SFLOAT, W >> 1, H >> 1, 5)
@@ -399,6 +403,8 @@ class ImageBasedLighting:
             ImageBasedLighting.generateBrdfLut(ctx, lut, stream=stream)
         res = IBLResources(env, pre, irr, lut)
         res._chain = chain
+        if stream and stream != current_stream_ptr(ctx.device):
+            ctx.synchronize(stream)  # callers read the maps on torch's stream (level_numpy, uploads of the next frame)
         return res
 
 
@@ -415,7 +421,7 @@ class ImageBasedLighting:
         env_rgba = np.concatenate([env_rgb, np.ones(env_rgb.shape[:2] + (1,), np.float32)], -1)
         if not hdr_cache.cache_complete(content_dir, env_name):
             fresh = ImageBasedLighting.createResources(ctx, env_rgba, lut_size=16, stream=stream)
-            ctx.synchronize()
+            ctx.synchronize(stream)  # the stream the precompute was issued on, before the maps are read back and cached on disk
             hdr_cache.save_precomputed_maps(content_dir, env_name, fresh.irradianceMap, fresh.prefilteredMap)
             del fresh
         irr, pre = hdr_cache.load_precomputed_maps(content_dir, env_name)

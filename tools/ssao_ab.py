@@ -58,3 +58,21 @@ print("march counters", ctx.ssao_cull_counts())
 cov = (res["fast_exact"] != 255)
 print("covered", float(cov.float().mean()), "mean count", float(res["fast_exact"][cov].float().mean()))
 print("lib", os.path.basename(_capi.library_path()))
+try:
+    import ctypes as C
+    ctx.set_flags(_capi.CTX_SSAO_COUNT_TAPS)
+    dp.draw(g, gb, ibl, lights, ssr, _capi.SHADE_SKIP_TONEMAP, stream)
+    torch.cuda.synchronize()
+    hist = (C.c_uint64 * 76)()
+    fn = C.CDLL(_capi.library_path()).althea_cuda_diag_ssao_cull_histogram
+    fn.argtypes = [C.c_void_p, C.c_void_p]
+    if fn(ctx._ptr, hist) == 0:
+        for lv in range(3):
+            row = [(hist[(lv * 12 + i) * 2], hist[(lv * 12 + i) * 2 + 1]) for i in range(1, 12)]
+            tot = sum(a for a, _ in row)
+            if tot:
+                print("level %d: %5.1f %% of the lookups; undecided per tap 1..11: %s; rays with no decided tap: %d" % (
+                    lv, 100.0 * tot / max(1, sum(hist[(l * 12 + i) * 2] for l in range(3) for i in range(1, 12))),
+                    " ".join("%.1f" % (100.0 * b / max(a, 1)) for a, b in row), hist[lv * 24]))
+except Exception as e:  # tuning aid only
+    print("histogram unavailable:", e)
