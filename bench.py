@@ -38,10 +38,25 @@ BYTES_PER_PX = {
     "ssr_depth_pad": 8.0,     # depth 4 read + padded copy 4 written per pixel (engine scratch)
     "glossy_convolve": 13.28,  # read 8*(1+1/4+1/16+1/64) + write 8*(1/4+...+1/256)
     "ssao": 25.0,             # position 16 + normal 8 + write count 1 (the proxy records are engine scratch, not algorithmic)
-    "ssao_quads": 48.0,       # position 16 read + 32-byte proxy record written per pixel
+    "ssao_cull": 25.0,        # the same stage with the coarse sign test in front (round 2): same algorithmic bytes
+    "ssao_quads": 52.0,       # position 16 read + 32-byte proxy record + 4-byte reciprocal depth written per pixel (engine scratch)
+    "ssao_planes": 4.5,       # reciprocal depths 4 read, plane records (three levels) ~0.33 written per pixel (engine scratch)
     "deferred_shade": 51.66,  # position 16 + normal 8 + albedo 4 + MRO 4 + AO count 1 + reflection mips (upper bound) 10.66 + write RGBA16F 8
 }
-FLOPS_PER_PX = {"ssao": 14400.0, "ssr_capture": 11500.0, "deferred_shade": 200.0 + 80.0 * N_LIGHTS, "glossy_convolve": 7 * 4 * 8.0}
+BOUND_NAMES = {"L1 data pipe (LSU wavefronts)": "l1_gather", "instruction issue": "issue", "DRAM": "hbm", "L2 (lts throughput)": "l2",
+               "FMA pipe": "fp32", "XU pipe": "xu"}
+
+
+def workload_config(V: int, mode: str):
+    """The `config` object of the headline workload: shared by this arm and `--impl reference` (same workload, same words)."""
+    px_frame = W4K * H4K
+    return {"workload": "C3/C5 stand-in: %d views/GPU of a 3840x2160 S-scene deferred+SSAO+SSR+glossy frame, 16 point lights + 256^2 omni "
+                        "shadow cubes, view-sharded (no collective)" % V,
+            "views_per_gpu": V, "resolution": [W4K, H4K], "lights": N_LIGHTS, "shadow_res": SHADOW_RES,
+            "l2_policy": "inputs (%.1f GB/step/GPU) exceed the 126 MB L2" % (V * px_frame * (36 if mode == "P" else 20) / 1e9),
+            "math": "fast build (FFMA); parity build checked in tests",
+            "gbuffer": "mode %s: %s" % (mode, "depth + normal + albedo + MRO attachments (20 B/px), positions reconstructed from depth inside the frame"
+                                        if mode != "P" else "legacy position attachment as input (36 B/px)")}
 
 
 def peaks():
@@ -407,8 +422,12 @@ def run_frame(view, ibl, lights, stream):
     dp.draw(g, gb, ibl, lights, ssr, _capi.SHADE_SKIP_TONEMAP, stream)
 
 
+_CPU_INPUTS = {}
+
+
 def cpu_baseline_sample(repeats: int = 1):
-    """The oracle (CPU port of the reference's GLSL) on a bounded sample of the same workload, all host threads."""
+    """The oracle (CPU port of the reference's GLSL) on a bounded sample of the same workload, all host threads: one 1280x720
+    view of the same S-scene with the workload's own 16 lights and 256^2 shadow cubes (per-pixel cost is the workload's)."""
     import numpy as np
     import torch
 
@@ -421,22 +440,25 @@ def cpu_baseline_sample(repeats: int = 1):
         pass
     O.set_num_threads(len(os.sched_getaffinity(0)))
     sw, sh = 1280, 720
-    sc = scene.make_ring_scene(160)
-    g = scene.make_uniforms(sw, sh, pos=(0.0, 2.0, 0.0), yaw=0.0, pitch=-0.2, light_count=N_LIGHTS)
-    gbd = scene.s_scene(g, sw, sh, sc).numpy()
-    lights_t = scene.make_lights(N_LIGHTS, ring=True)
-    cubes = scene.shadow_cubes(sc, lights_t, 64).numpy()
-    env = scene.procedural_env(512, 256).numpy()
-    chain, mips = O.env_mip_chain(env)
-    l0 = 512 * 256 * 4
-    pre = chain[l0:l0 + O.chain_texels(256, 128, 5) * 4].copy()
-    off4 = O.chain_texels(512, 256, 4) * 4
-    irr = chain[off4:off4 + 32 * 16 * 4].reshape(16, 32, 4).copy()
-    lut = np.zeros((64, 64, 4), np.uint8)
-    lut[..., :2] = (np.clip(O.brdf_lut(64, 64)[::-1], 0, 1) * 255 + 0.5).astype(np.uint8)
-    og = O.GlobalUniforms.from_buffer_copy(bytes(g))
-    fr = O.Frame(og, sw, sh, gbd["position"], gbd["depth"], gbd["normal"], gbd["albedo"], gbd["mro"], env, pre, (256, 128), 5, irr, lut,
-                 lights_t.numpy(), cubes, 64)
+    if "frame" not in _CPU_INPUTS:  # inputs are built once (the cubes on the GPU when there is one: they are inputs, not the measured work)
+        dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+        sc = scene.make_ring_scene(160, device=dev)
+        g = scene.make_uniforms(sw, sh, pos=(0.0, 2.0, 0.0), yaw=0.0, pitch=-0.2, light_count=N_LIGHTS)
+        gbd = scene.s_scene(g, sw, sh, sc, device=dev).numpy()
+        lights_t = scene.make_lights(N_LIGHTS, ring=True, device=dev)
+        cubes = scene.shadow_cubes(sc, lights_t, SHADOW_RES).cpu().numpy()
+        env = scene.procedural_env(512, 256).numpy()
+        chain, mips = O.env_mip_chain(env)
+        l0 = 512 * 256 * 4
+        pre = chain[l0:l0 + O.chain_texels(256, 128, 5) * 4].copy()
+        off4 = O.chain_texels(512, 256, 4) * 4
+        irr = chain[off4:off4 + 32 * 16 * 4].reshape(16, 32, 4).copy()
+        lut = np.zeros((64, 64, 4), np.uint8)
+        lut[..., :2] = (np.clip(O.brdf_lut(64, 64)[::-1], 0, 1) * 255 + 0.5).astype(np.uint8)
+        og = O.GlobalUniforms.from_buffer_copy(bytes(g))
+        _CPU_INPUTS["frame"] = O.Frame(og, sw, sh, gbd["position"], gbd["depth"], gbd["normal"], gbd["albedo"], gbd["mro"], env, pre, (256, 128), 5, irr, lut,
+                                       lights_t.cpu().numpy(), cubes, SHADOW_RES)
+    fr = _CPU_INPUTS["frame"]
     times = []
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -446,30 +468,32 @@ def cpu_baseline_sample(repeats: int = 1):
         times.append(time.perf_counter() - t0)
     t = min(times)
     return {"value": sw * sh / t / 1e6, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
-            "sample": "1 view of the same S-scene at 1280x720 (1/9 of a 4K view), 16 lights, 64^2 shadow cubes; %d run(s), best %.2f s" % (repeats, t),
+            "sample": "1 view of the same S-scene at 1280x720 (1/9 of a 4K view), 16 lights, 256^2 shadow cubes; %d run(s), best %.2f s" % (repeats, t),
             "seconds": t}
 
 
 def main_reference(args):
     """--impl reference: the reference's own algorithm on the host CPU. The reference's path is GLSL + Vulkan and cannot be
-    compiled or run here (no Vulkan loader / lavapipe / glslc), so this is the oracle port, all host threads."""
+    compiled or run here (no Vulkan loader / lavapipe / glslc), so this is the oracle port, all host threads. A step is
+    a bounded sample of the workload (one 1280x720 view of the 3840x2160 views: the metric is per pixel); exactly --warmup
+    untimed and --steps timed samples."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as O
     O.build()
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):
         cpu_baseline_sample(1)
-    samples = [cpu_baseline_sample(1) for _ in range(max(1, min(args.steps, 5)))]
+    samples = [cpu_baseline_sample(1) for _ in range(max(1, args.steps))]
     secs = sum(s["seconds"] for s in samples) / len(samples)
     value = 1280 * 720 / secs / 1e6
     cb = dict(samples[0])
     cb["value"] = value
+    cb["sample"] = cb["sample"].split(";")[0] + "; mean of %d timed samples of %.2f s" % (len(samples), secs)
     cb.pop("seconds")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(samples), "warmup": min(args.warmup, 1),
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(samples), "warmup": args.warmup,
             "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3/C5 stand-in: S-scene deferred+SSAO+SSR+glossy frame, 16 point lights + omni shadow cubes; CPU arm renders a "
-                                   "bounded sample (one 1280x720 view per step) of the 3840x2160 views"},
+            "config": workload_config(args.views, args.gbuffer_mode),
             "cpu_baseline": cb, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -575,14 +599,19 @@ def main():
         ctx.set_flags(_capi.CTX_SSAO_COUNT_TAPS)
         run_frame(views[0], ibl, lights, stream)
         torch.cuda.synchronize()
-        records = ctx.ssao_gathers()
+        counts = ctx.ssao_cull_counts()
+        ctx.set_flags(_capi.CTX_SSAO_COUNT_TAPS | _capi.CTX_SSAO_NO_CULL)
+        run_frame(views[0], ibl, lights, stream)
+        torch.cuda.synchronize()
+        records_march = ctx.ssao_gathers()
         ctx.set_flags(0)
         ceilings = {str(r): ctx.gather_ceiling(W4K, H4K, r, 64) for r in (32, 96)}
-        gather = {"records_per_frame": records, "ceiling_records_per_s": ceilings}
+        gather = {"records_per_frame": counts["records"], "plane_lookups": counts["plane_lookups"], "exact_steps": counts["exact_steps"],
+                  "records_march": records_march, "ceiling_records_per_s": ceilings}
 
     # ---- the rasterising producers upstream of the path, informational, outside the timed region:
     # G-buffer pass at 4K and the 16 x 6 shadow-cube faces of a 1.06 M triangle mesh scene (tools/raster_bench.py)
-    producers = None
+    producers, indoor = None, None
     if rank == 0 and not args.no_producers:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import numpy as np
@@ -607,7 +636,26 @@ def main():
             p1.record()
             torch.cuda.synchronize()
             producers[name] = p0.elapsed_time(p1) / 3
-        del up, pgb, pl
+        # ... and the deferred chain on THAT G-buffer: an indoor, sky-free view (every SSAO ray stays on screen, every SSR ray has
+        # something to hit), beside the S-scene of the headline whose 27 % sky flatters it
+        ssr_i = engine.ScreenSpaceReflection(ctx, W4K, H4K)
+        dp_i = engine.DeferredPass(ctx, W4K, H4K, _capi.FORMAT_R16G16B16A16_SFLOAT)
+        iview = (pg, pgb, ssr_i, dp_i)
+        run_frame(iview, ibl, pl, stream)
+        torch.cuda.synchronize()
+        ctx.enable_timing(True)
+        ctx.reset_timings()
+        for _ in range(3):
+            run_frame(iview, ibl, pl, stream)
+        torch.cuda.synchronize()
+        it = {k: v["total_ms"] / 3 for k, v in ctx.timings().items()}
+        ctx.enable_timing(False)
+        ctx.reset_timings()
+        covered = float((pgb.position.tensor.view(torch.float32).view(H4K, W4K, 4)[..., 3] != 0).float().mean())
+        indoor = {"scene": producers["scene"] + ", camera inside the room, 16 lights with the shadow cubes rendered from the mesh; G-buffer mode P",
+                  "covered_fraction": covered, "ms_per_4k_frame": sum(it.values()), "Mpixel_per_s": W4K * H4K / (sum(it.values()) * 1e-3) / 1e6,
+                  "stages_ms": it}
+        del up, pgb, pl, ssr_i, dp_i
 
     # ---- e2e: same metric through the C ABI with HOST buffers (pinned), copies inside the timed region ----
     e2e = None
@@ -694,26 +742,31 @@ def main():
             # glossy_convolve: 4 launches per frame, bytes accounted per frame
             per_frame_ms = rec["total_ms"] / (args.steps * V)
             gbs = BYTES_PER_PX.get(name, 0.0) * px_frame / (per_frame_ms * 1e-3) / 1e9 if per_frame_ms > 0 else 0.0
-            tfl = FLOPS_PER_PX.get(name, 0.0) * px_frame / (per_frame_ms * 1e-3) / 1e12 if per_frame_ms > 0 else 0.0
-            stages[name] = {"ms_per_frame": per_frame_ms, "launches": n, "algorithmic_GBps": gbs, "hbm_frac": gbs / hbm_peak,
-                            "algorithmic_TFLOPs": tfl, "fp32_frac_at_sm_max": tfl / (148 * 128 * 2 * sm_max * 1e6 / 1e12)}
+            stages[name] = {"ms_per_frame": per_frame_ms, "launches": n, "algorithmic_GBps": gbs, "hbm_frac": gbs / hbm_peak}
+            tr = ncu_traffic(name)
+            if tr:  # what binds the kernel, from the committed ncu --set full capture of this workload (not a flop model)
+                stages[name]["ncu"] = {"binding_resource": tr["binding_resource"], "utilisation_pct": tr["utilisation_pct"], "source": tr["source"]}
         dom = max(stages, key=lambda k: stages[k]["ms_per_frame"]) if stages else None
         roofline = None
         if dom:
             s = stages[dom]
             tr = ncu_traffic(dom)
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": s["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": s["hbm_frac"],
-                        "traffic": tr["dram_bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,
+            top = tr["binding_resource"].rsplit(" ", 5)[0] if tr else None
+            roofline = {"kernel": dom, "bound": BOUND_NAMES.get(top, "issue") if tr else "issue", "achieved": s["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": s["hbm_frac"], "traffic": tr["dram_bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,
                         "binding_resource": tr.get("binding_resource") if tr else None, "peak_source": peak_src,
-                        "note": "%s is FP32-issue / L1-tap bound, not HBM bound (SURVEY.md 8d): fp32 frac %.3f of 148 SM x 128 lanes x 2 x %.0f MHz"
-                                % (dom, s["fp32_frac_at_sm_max"], sm_max)}
-        if roofline and dom == "ssao" and gather:
+                        "note": "achieved / peak / frac are the ALGORITHMIC bytes of the stage (25 B/px: position 16 + normal 8 + count 1) over its measured time "
+                                "against the measured HBM copy rate, as the contract defines them; the stage is not HBM-bound: `bound` and `binding` name the "
+                                "unit ncu finds busiest (instruction issue and the L1 data pipe, both ~80 %, profiles/)"}
+        if roofline and dom in ("ssao", "ssao_cull") and gather:
             peak = max(gather["ceiling_records_per_s"].values())
-            ach = gather["records_per_frame"] / (stages["ssao"]["ms_per_frame"] * 1e-3)
+            ach = gather["records_per_frame"] / (stages[dom]["ms_per_frame"] * 1e-3)
             roofline["binding"] = {
-                "resource": "divergent 32-byte gathers (L1 data pipe: one wavefront per distinct 128-byte line)",
-                "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "Grecords/s", "frac": ach / peak,
-                "records_per_launch": gather["records_per_frame"],
+                "resource": "plane-record lookups in shared memory (LDS.128, ~7 wavefronts each) + divergent 32-byte gathers of position records (one L1 wavefront "
+                            "per distinct 128-byte line) + instruction issue",
+                "plane_lookups_per_launch": gather.get("plane_lookups"), "taps_left_to_exact_path_per_launch": gather.get("exact_steps"),
+                "records_per_launch": gather["records_per_frame"], "records_per_launch_round1_march": gather.get("records_march"),
+                "gather_rate_Grecords_per_s": ach / 1e9, "gather_ceiling_Grecords_per_s": peak / 1e9,
                 "peak_how": "althea_cuda_diag_gather_ceiling measured in this run: one 256-bit load per lane at random positions within "
                             "+-32 / +-96 records of the lane's 16x16 tile over the 3841x2161 record grid (the larger rate is the peak)",
                 "ceilings": {k: v / 1e9 for k, v in gather["ceiling_records_per_s"].items()}}
@@ -722,13 +775,8 @@ def main():
                  "ms_per_4k_frame": frame_ms, "frames_per_s": 1e3 / frame_ms * world}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "C3/C5 stand-in: %d views/GPU of a 3840x2160 S-scene deferred+SSAO+SSR+glossy frame, 16 point lights + 256^2 omni "
-                                       "shadow cubes, view-sharded (no collective)" % V,
-                           "views_per_gpu": V, "resolution": [W4K, H4K], "lights": N_LIGHTS, "l2_policy": "inputs (%.1f GB/step/GPU) exceed the 126 MB L2"
-                                                                                                      % (V * px_frame * (36 if mode_p else 20) / 1e9),
-                           "math": "fast build (FFMA); parity build checked in tests",
-                           "gbuffer": "mode %s: %s" % (args.gbuffer_mode, "depth + normal + albedo + MRO attachments (20 B/px), positions reconstructed from depth inside the frame" if not mode_p else "legacy position attachment as input (36 B/px)")},
-                "gpu_launches": int(launches) * world, "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_chain": chain, "stages": stages, "producers": producers,
+                "config": workload_config(V, args.gbuffer_mode),
+                "gpu_launches": int(launches) * world, "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_chain": chain, "stages": stages, "producers": producers, "indoor_view": indoor,
                 "ibl_prefilter_ms": ibl_t.get("config1_cube", {}).get("ibl_prefilter"),
                 "ibl_precompute_ms": ibl_t,
                 "ibl_config": {"config1_cube": "BASELINE configs[1]: %dx%d equirect env -> 32^2 irradiance cube (300x150 samples) + 512^2 6-mip GGX prefilter cube "
