@@ -28,8 +28,10 @@ CTX_SSAO_COUNT_TAPS = 4
 CTX_SSAO_RAY_DEPTH_PROXY = 8
 CTX_SSAO_NO_CULL = 16
 CTX_SSR_PLANE_SKIP = 32
+CTX_BAND_EXCHANGE_HALO = 64
 SHADE_SKIP_TONEMAP = 1
 SHADE_NO_SSAO = 2
+SHADE_AO_ONLY = 8
 SHADE_AO_FROM_IMAGE = 4
 IBL_LAYOUT_EQUIRECT, IBL_LAYOUT_CUBE = 0, 1
 IBL_SEQ_REFERENCE_HASH, IBL_SEQ_HAMMERSLEY = 0, 1

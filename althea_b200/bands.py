@@ -56,6 +56,26 @@ def allgather_rows(buf, row_bytes: int, band_rows: int, group=None, async_op: bo
     return dist.all_gather(chunks, mine.clone(), group=group, async_op=async_op)
 
 
+def halo_plan(width: int, height: int, mips: int, world: int, rank: int):
+    """Rows of reflection mip 0 that `rank`'s glossy mips read but other ranks own, and the rows it owns that others read:
+    ([(peer, y0, y1)] to receive, [(peer, y0, y1)] to send), from althea_cuda_band_rows of every rank's band."""
+    from . import engine
+    spans = split_rows(height, world)
+    need = [engine.band_rows(width, height, mips, y0, y1)[0] if y1 > y0 else (0, 0) for (y0, y1) in spans]
+    my0, my1 = spans[rank]
+    recv, send = [], []
+    for q, (q0, q1) in enumerate(spans):
+        if q == rank or q1 <= q0 or my1 <= my0:
+            continue
+        lo, hi = max(need[rank][0], q0), min(need[rank][1], q1)   # rows of q's band inside my halo
+        if hi > lo:
+            recv.append((q, lo, hi))
+        lo, hi = max(need[q][0], my0), min(need[q][1], my1)       # rows of my band inside q's halo
+        if hi > lo:
+            send.append((q, lo, hi))
+    return recv, send
+
+
 class BandPipeline:
     """Keeps `frames_in_flight` frames in flight (the reference engine keeps two, Include/Althea/Library.h:3): the replication
     of frame k + 1's G-buffer and the assembly of frame k - 1's bands run on the collective stream while frame k's band is
@@ -156,6 +176,7 @@ class BandedFrame:
         self.deferred.colorTarget = ctx.wrap_tensor(self._color_t, out_format, width, height)
         self.deferred.aoCounts = ctx.new_image(_capi.FORMAT_R8_UINT, width, height)
         self.ssr = engine.ScreenSpaceReflection(ctx, width, height)
+        self._halo_stream = None
 
     @staticmethod
     def gbuffer_tensors(gbuffer):
@@ -169,15 +190,74 @@ class BandedFrame:
             return broadcast_tensors(self.gbuffer_tensors(gbuffer), src=src, group=self.group, async_op=async_op)
         return None
 
-    def render(self, uniforms, gbuffer, ibl, lights, flags: int = _capi.SHADE_SKIP_TONEMAP, stream: int = 0):
+    def halo_rows(self):
+        """Rows [lo, hi) of reflection mip 0 the band's glossy mips read (the band and its halo)."""
+        from . import engine
+        return engine.band_rows(self.W, self.H, self.ssr.getReflectionBuffer().image.mips, self.y0, self.y1)[0]
+
+    def halo_plan(self):
+        return halo_plan(self.W, self.H, self.ssr.getReflectionBuffer().image.mips, self.world, self.rank)
+
+    def exchange_halo(self):
+        """Point-to-point exchange of the reflection rows (mip 0, RGBA16F) between the ranks whose bands border each other:
+        a few MB per neighbour over NVLink instead of every rank ray-marching its halo again. Returns the requests to wait for."""
+        dist = _dist()
+        if self.world == 1:
+            return []
+        recv, send = self.halo_plan()
+        t = self.ssr.getReflectionBuffer().image.tensor
+        rb = self.W * 8  # bytes per row of mip 0
+        ops = []
+        # the same global order on every rank (by the lower rank of the pair, then direction): what NCCL's grouped P2P needs
+        for q, lo, hi in send:
+            ops.append(((min(self.rank, q), max(self.rank, q), 0 if self.rank < q else 1), dist.P2POp(dist.isend, t[lo * rb:hi * rb], q, group=self.group)))
+        for q, lo, hi in recv:
+            ops.append(((min(self.rank, q), max(self.rank, q), 0 if q < self.rank else 1), dist.P2POp(dist.irecv, t[lo * rb:hi * rb], q, group=self.group)))
+        ops.sort(key=lambda o: o[0])
+        return dist.batch_isend_irecv([o[1] for o in ops]) if ops else []
+
+    def render(self, uniforms, gbuffer, ibl, lights, flags: int = _capi.SHADE_SKIP_TONEMAP, stream: int = 0, exchange_halo: Optional[bool] = None):
+        """The band's frame. With more than one rank the reflection halo (the mip-0 rows around the band its glossy mips read) comes
+        from the ranks that own those rows (exchange_halo, default) while this rank's SSAO runs; with exchange_halo=False every rank
+        ray-marches its halo itself (no collective inside the frame, ~35 % more SSR work at 8 ranks of an 8K frame). Either way the
+        band is bit-identical to the same rows of a single-GPU frame."""
         if self.y1 <= self.y0:
+            if self.world > 1 and exchange_halo is not False:
+                for w in self.exchange_halo():  # an empty band still owes nothing, but the grouped call must match its peers'
+                    w.wait()
             return
+        if exchange_halo is None:  # worth a synchronisation point between neighbours once the halo is a fair share of the band
+            lo, hi = self.halo_rows()
+            exchange_halo = self.world > 1 and (hi - lo) - (self.y1 - self.y0) >= 0.15 * (self.y1 - self.y0)
         self.ctx.set_scissor_rows(self.y0, self.y1)
+        base = self.ctx.flags
         try:
-            self.ssr.captureReflection(uniforms, gbuffer, ibl, lights, stream)
+            if not exchange_halo:
+                self.ssr.captureReflection(uniforms, gbuffer, ibl, lights, stream)
+                self.ssr.convolveReflectionBuffer(stream)
+                self.deferred.draw(uniforms, gbuffer, ibl, lights, self.ssr, flags, stream)
+                return
+            import torch
+            self.ctx.set_flags(base | _capi.CTX_BAND_EXCHANGE_HALO)
+            self.ssr.captureReflection(uniforms, gbuffer, ibl, lights, stream)      # the band's own rows only
+            cuda = self.ssr.getReflectionBuffer().image.tensor.is_cuda
+            if cuda:
+                done = torch.cuda.Event()
+                done.record()
+                if self._halo_stream is None:
+                    self._halo_stream = torch.cuda.Stream()
+                self._halo_stream.wait_event(done)
+                with torch.cuda.stream(self._halo_stream):
+                    works = self.exchange_halo()
+            else:
+                works = self.exchange_halo()
+            self.deferred.draw(uniforms, gbuffer, ibl, lights, self.ssr, _capi.SHADE_AO_ONLY, stream)  # SSAO while the halo travels
+            for w in works:
+                w.wait()
             self.ssr.convolveReflectionBuffer(stream)
-            self.deferred.draw(uniforms, gbuffer, ibl, lights, self.ssr, flags, stream)
+            self.deferred.draw(uniforms, gbuffer, ibl, lights, self.ssr, flags | _capi.SHADE_AO_FROM_IMAGE, stream)
         finally:
+            self.ctx.set_flags(base)
             self.ctx.set_scissor_rows(0, 0)
 
     def gather(self, async_op: bool = False):

@@ -750,8 +750,8 @@ int althea_cuda_ssr_capture(althea_cuda_ctx* ctx, const althea_global_uniforms* 
   FrameParams P;
   int rc = fillFrameParams(ctx, uniforms, gbuffer, ibl, lights_buf, shadow_cube_array, reflection, /*needPosition=*/false, &P);
   if (rc) return rc;
-  if (ctx->scissorY1) { // the glossy mips of the band need a halo of mip-0 rows: recompute them locally
-    Resource* refl = find(ctx, reflection, ResKind::Image);
+  if (ctx->scissorY1 && !(ctx->flags & ALTHEA_CTX_BAND_EXCHANGE_HALO)) { // the glossy mips of the band need a halo of mip-0 rows: recomputed locally
+    Resource* refl = find(ctx, reflection, ResKind::Image);                 // (DESIGN.md 6), unless the host exchanges them between the ranks
     uint32_t lo[kMaxMips], hi[kMaxMips];
     bandRows(refl->w, refl->h, refl->mips, ctx->scissorY0, ctx->scissorY1, lo, hi);
     P.y0 = (int)lo[0];
@@ -828,16 +828,20 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
   FrameParams P;
   int rc = fillFrameParams(ctx, uniforms, gbuffer, ibl, lights_buf, shadow_cube_array, reflection, /*needPosition=*/true, &P);
   if (rc) return rc;
-  Resource *out, *ao;
-  if ((rc = getImage(ctx, out_color, 0, "out_color", &out))) return rc;
-  if (out->format != ALTHEA_FORMAT_R16G16B16A16_SFLOAT && out->format != ALTHEA_FORMAT_R32G32B32A32_SFLOAT)
-    return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "out_color must be RGBA16F or RGBA32F (has VkFormat %u)", out->format);
-  if ((int)out->w != P.W || (int)out->h != P.H) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "out_color must be %dx%d", P.W, P.H);
-  levelView(*out, 0, 0, &P.out);
-  P.outIsF32 = out->format == ALTHEA_FORMAT_R32G32B32A32_SFLOAT;
+  Resource *out = nullptr, *ao;
+  const bool aoOnly = flags & ALTHEA_SHADE_AO_ONLY;
+  if (aoOnly && (flags & (ALTHEA_SHADE_NO_SSAO | ALTHEA_SHADE_AO_FROM_IMAGE))) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "AO_ONLY excludes NO_SSAO and AO_FROM_IMAGE");
+  if (!aoOnly) {
+    if ((rc = getImage(ctx, out_color, 0, "out_color", &out))) return rc;
+    if (out->format != ALTHEA_FORMAT_R16G16B16A16_SFLOAT && out->format != ALTHEA_FORMAT_R32G32B32A32_SFLOAT)
+      return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "out_color must be RGBA16F or RGBA32F (has VkFormat %u)", out->format);
+    if ((int)out->w != P.W || (int)out->h != P.H) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "out_color must be %dx%d", P.W, P.H);
+    levelView(*out, 0, 0, &P.out);
+    P.outIsF32 = out->format == ALTHEA_FORMAT_R32G32B32A32_SFLOAT;
+  }
   P.flags = flags;
   if ((rc = getImage(ctx, ao_counts, ALTHEA_FORMAT_R8_UINT, "ao_counts", &ao, true))) return rc;
-  if ((flags & ALTHEA_SHADE_AO_FROM_IMAGE) && !ao) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "AO_FROM_IMAGE needs ao_counts");
+  if ((flags & (ALTHEA_SHADE_AO_FROM_IMAGE | ALTHEA_SHADE_AO_ONLY)) && !ao) return fail(ctx, ALTHEA_ERR_INVALID_ARGUMENT, "AO_FROM_IMAGE / AO_ONLY need ao_counts");
   const bool needAo = !(flags & ALTHEA_SHADE_NO_SSAO);
   althea_cuda_ctx::Scratch& S = ctx->scratch[workStream(ctx, sync)];
   if (needAo) {
@@ -869,6 +873,7 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
   // positions do not fit it) and the position records; the ray-depth records keep their own march
   const bool cull = computeAo && !exactTaps && !(ctx->flags & (ALTHEA_CTX_SSAO_NO_CULL | ALTHEA_CTX_SSAO_RAY_DEPTH_PROXY));
   P.ssaoTileList = nullptr;
+  P.ssaoPlaneStats = nullptr;
   P.ssaoRecip = nullptr;
   if (cull) {
     size_t need = 0, off[3];
@@ -880,14 +885,15 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
       off[l] = need;
       need += (size_t)P.ssaoPlaneRow[l] * (P.ssaoPlaneNy[l] + 2 * kSsaoPlanePad + 1) * 16;
     }
-    const size_t listOff = need;
-    need += ((size_t)((P.W + 15) / 16) * ((P.H + 15) / 16) + 1) * sizeof(unsigned);
+    const size_t listOff = need; // two words of record statistics, then the tile list
+    need += ((size_t)((P.W + 15) / 16) * ((P.H + 15) / 16) + 3) * sizeof(unsigned);
     const size_t recipOff = (need + 255) & ~(size_t)255;
     need = recipOff + (size_t)P.W * P.H * sizeof(float);
     if ((rc = growScratchBuf(ctx, &S.plane, &S.planeBytes, need, "ssao plane scratch"))) return rc;
     for (int l = 0; l < 3; ++l)
       P.ssaoPlanes[l] = reinterpret_cast<const float4*>(static_cast<const char*>(S.plane) + off[l]) + ((size_t)kSsaoPlanePad * P.ssaoPlaneRow[l] + kSsaoPlanePad);
-    P.ssaoTileList = reinterpret_cast<unsigned*>(static_cast<char*>(S.plane) + listOff);
+    P.ssaoPlaneStats = reinterpret_cast<unsigned*>(static_cast<char*>(S.plane) + listOff);
+    P.ssaoTileList = P.ssaoPlaneStats + 2;
     P.ssaoRecip = reinterpret_cast<float*>(static_cast<char*>(S.plane) + recipOff);
   }
   if (computeAo && !exactTaps && (ctx->flags & ALTHEA_CTX_SSAO_COUNT_TAPS)) {
@@ -908,13 +914,15 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
     } else {
       timedLaunch(ctx, "ssao_quads", stream, [&] { parity ? althea_parity::launch_ssao_quads(P, stream) : althea_fast::launch_ssao_quads(P, stream); });
       if (cull) {
-        timedLaunch(ctx, "ssao_planes", stream, [&] { parity ? althea_parity::launch_ssao_planes(P, stream) : althea_fast::launch_ssao_planes(P, stream); });
+        for (bool coarsest : {true, false})
+          timedLaunch(ctx, "ssao_planes", stream, [&] { parity ? althea_parity::launch_ssao_planes(P, stream, coarsest) : althea_fast::launch_ssao_planes(P, stream, coarsest); });
         timedLaunch(ctx, "ssao_cull", stream, [&] { parity ? althea_parity::launch_ssao_cull(P, stream) : althea_fast::launch_ssao_cull(P, stream); });
       }
       timedLaunch(ctx, "ssao", stream, [&] { parity ? althea_parity::launch_ssao(P, stream) : althea_fast::launch_ssao(P, stream); });
     }
   }
-  timedLaunch(ctx, "deferred_shade", stream, [&] { parity ? althea_parity::launch_deferred_shade(P, stream) : althea_fast::launch_deferred_shade(P, stream); });
+  if (!aoOnly)
+    timedLaunch(ctx, "deferred_shade", stream, [&] { parity ? althea_parity::launch_deferred_shade(P, stream) : althea_fast::launch_deferred_shade(P, stream); });
   return endWork(ctx, sync, stream);
 }
 

@@ -780,6 +780,7 @@ __global__ void __launch_bounds__(256) ssao_quads_kernel(const __grid_constant__
   const int j0 = AddrClamp::wrap(qy - 1, P.H), j1 = AddrClamp::wrap(qy, P.H);
   const V4 p00 = FmtRGBA32F::load(P.position, i0, j0), p10 = FmtRGBA32F::load(P.position, i1, j0);
   const V4 p01 = FmtRGBA32F::load(P.position, i0, j1), p11 = FmtRGBA32F::load(P.position, i1, j1);
+  if (P.ssaoPlaneStats && qx == 0 && qy == 0) { P.ssaoPlaneStats[0] = 0u; P.ssaoPlaneStats[1] = 0u; P.ssaoTileList[0] = 0u; }
   if (P.ssaoRecip && qx < P.W && qy < P.H) { // this thread's p11 is texel (qx, qy): its reciprocal eye depth for ssao_planes_kernel
     const V3 cam = mk3(P.ssaoCam[0], P.ssaoCam[1], P.ssaoCam[2]);
     const float t = dot3(xyz(p11) - cam, mk3(P.ssaoFwd[0], P.ssaoFwd[1], P.ssaoFwd[2]));
@@ -1319,18 +1320,22 @@ constexpr float kCullReach = ALTHEA_CULL_REACH; // screen reach of a tile's rays
 #ifndef ALTHEA_CULL_SKY_CLASS
 #define ALTHEA_CULL_SKY_CLASS 0
 #endif
-// one warp per record
-__global__ void __launch_bounds__(256) ssao_planes_kernel(const __grid_constant__ FrameParams P) {
+// A frame whose coarsest records almost never decide (random depth, foliage everywhere) is marched tile by tile anyway: the finer
+// levels are not built and ssao_cull_kernel hands every tile over without staging anything.
+ADEV bool planesHopeless(const FrameParams& P) { return P.ssaoPlaneStats[1] * 16u < P.ssaoPlaneStats[0]; }
+
+// one warp per record. COARSEST: the level-2 records, counting how many can decide; else levels 0 and 1, unless hopeless
+template <bool COARSEST> __global__ void __launch_bounds__(256) ssao_planes_kernel(const __grid_constant__ FrameParams P) {
   const int lane = threadIdx.x & 31;
   long long rec = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  int level = 0;
-  for (; level < 3; ++level) {
+  int level = COARSEST ? 2 : 0;
+  for (; level < (COARSEST ? 3 : 2); ++level) {
     const long long n = (long long)P.ssaoPlaneRow[level] * (P.ssaoPlaneNy[level] + 2 * kSsaoPlanePad + 1);
     if (rec < n) break;
     rec -= n;
   }
-  if (level == 3) return;
-  if (blockIdx.x == 0 && threadIdx.x == 0) P.ssaoTileList[0] = 0u; // the list ssao_cull_kernel (next in the stream) appends to
+  if (level == (COARSEST ? 3 : 2)) return;
+  if (!COARSEST && planesHopeless(P)) return;
   const int S = 8 << level;
   const int row = P.ssaoPlaneRow[level];
   const int bx = (int)(rec % row) - kSsaoPlanePad, by = (int)(rec / row) - kSsaoPlanePad;
@@ -1375,7 +1380,7 @@ __global__ void __launch_bounds__(256) ssao_planes_kernel(const __grid_constant_
   }
   if (lane == 0 && cleared) { // every texel the record answers for is the clear colour: r = -1 marks the class
     *out = make_float4(0.0f, 0.0f, 0.0f, ALTHEA_CULL_SKY_CLASS ? -1.0f : inf);
-    return;
+    return; // (not counted in the statistics: empty sky says nothing about whether surfaces decide)
   }
   if (lane == 0) {
     const float mid = 0.5f * (rlo + rhi);
@@ -1399,6 +1404,10 @@ __global__ void __launch_bounds__(256) ssao_planes_kernel(const __grid_constant_
     r *= 1.000001f;
     const bool fin = ok && !border && eta <= kPlaneEtaMax && isfinite(a2) && isfinite(beta) && isfinite(gamma) && isfinite(r);
     *out = fin ? make_float4(a2, beta, gamma, r) : make_float4(0.0f, 0.0f, 0.0f, inf);
+    if (COARSEST) { // blocks on the image border never decide: not counted either way
+      if (!border) atomicAdd(P.ssaoPlaneStats, 1u);
+      if (fin) atomicAdd(P.ssaoPlaneStats + 1, 1u);
+    }
   }
 }
 
@@ -1509,6 +1518,10 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
   tmin = fminf(fminf(fminf(redMin[0], redMin[1]), fminf(redMin[2], redMin[3])), fminf(fminf(redMin[4], redMin[5]), fminf(redMin[6], redMin[7])));
   if (tmin == __int_as_float(0x7f800000)) { // nothing to shade in this tile
     if (inside) rowPtrW<uint8_t>(P.ao, y)[x] = 255;
+    return;
+  }
+  if (planesHopeless(P)) { // no plane records worth staging in this frame
+    if (threadIdx.x == 0) P.ssaoTileList[1u + atomicAdd(P.ssaoTileList, 1u)] = blockIdx.y * gridDim.x + blockIdx.x;
     return;
   }
   const float reach = kCullReach * P.ssaoFocalPx / fmaxf(tmin - 0.5f, 1e-3f);
@@ -1829,10 +1842,11 @@ void launch_ssao(const FrameParams& P, cudaStream_t s) {
   }
 }
 static_assert(kSsaoTileW == 16, "ssao_cull_kernel and ssao_kernel share the 16 x 16 tile grid");
-void launch_ssao_planes(const FrameParams& P, cudaStream_t s) {
-  long long n = 0;
-  for (int l = 0; l < 3; ++l) n += (long long)P.ssaoPlaneRow[l] * (P.ssaoPlaneNy[l] + 2 * kSsaoPlanePad + 1);
-  ssao_planes_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(P);
+void launch_ssao_planes(const FrameParams& P, cudaStream_t s, bool coarsest) { // the coarsest level first, then the finer ones if worth it
+  long long n[3];
+  for (int l = 0; l < 3; ++l) n[l] = (long long)P.ssaoPlaneRow[l] * (P.ssaoPlaneNy[l] + 2 * kSsaoPlanePad + 1);
+  if (coarsest) ssao_planes_kernel<true><<<(unsigned)((n[2] + 7) / 8), 256, 0, s>>>(P);
+  else ssao_planes_kernel<false><<<(unsigned)((n[0] + n[1] + 7) / 8), 256, 0, s>>>(P);
 }
 void launch_ssao_cull(const FrameParams& P, cudaStream_t s) {
   const dim3 grid((unsigned)((P.W + 15) / 16), (unsigned)((P.y1 - P.y0 + 15) / 16));

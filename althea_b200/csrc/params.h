@@ -64,6 +64,7 @@ struct FrameParams {
   float ssaoDmag;              // |Dc|_1 + |Dx|_1 W + |Dy|_1 H: bounds the rounding of dot(D(x, y), v)
   float ssaoCamL1;             // |cam|_1
   unsigned* ssaoTileList;       // [0]: number of 16 x 16 tiles the cull kernel handed over to the march kernel, [1 + k]: tile ids
+  unsigned* ssaoPlaneStats;     // [0]: level-2 records inside the image, [1]: those that can decide (zeroed by ssao_quads_kernel)
   float* ssaoRecip;             // W x H: reciprocal eye depth of every position texel (NaN: off the camera model), by ssao_quads_kernel
   unsigned long long* gatherCounter; // diagnostics (ALTHEA_CTX_SSAO_COUNT_TAPS): proxy records gathered by the SSAO march; else null
   // SSR sign test: one plane record {alpha, beta, gamma, r} of reciprocal eye depth per block of

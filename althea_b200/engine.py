@@ -83,6 +83,7 @@ class Context:
             raise AltheaError("althea_cuda_create failed (%d): %s" % (rc, (self._lib.althea_cuda_last_error(None) or b"").decode()))
         self._ptr = p
         self.device = device
+        self.flags = 0
         if parity_math:
             self.set_flags(_capi.CTX_PARITY_MATH)
 
@@ -103,6 +104,7 @@ class Context:
 
     def set_flags(self, flags: int):
         self._check(self._lib.althea_cuda_set_flags(self._ptr, flags))
+        self.flags = flags
 
     def set_scissor_rows(self, y0: int = 0, y1: int = 0):
         """Restricts the per-frame stages to what rows [y0, y1) of the final image need (row-band multi-GPU mode);

@@ -221,11 +221,15 @@ def measure_bands8k(ctx, rank, local_rank, world, device, ibl, lights, steps, wa
     bcast, rend, gath = (float(v) for v in lat.tolist())
     one = float(single.item()) if world > 1 else rend
     gbytes = W8 * H8 * (36 if mode_p else 20)
+    lo, hi = bf0.halo_rows()
+    exchanged = world > 1 and (hi - lo) - (bf0.y1 - bf0.y0) >= 0.15 * (bf0.y1 - bf0.y0)
+    halo_how = ("exchanged point to point with the neighbouring ranks while SSAO runs: %d rows of mip 0 around a band of %d" % ((hi - lo) - (bf0.y1 - bf0.y0), bf0.band)
+                if exchanged else "recomputed locally, no collective inside the frame: %d rows around a band of %d" % ((hi - lo) - (bf0.y1 - bf0.y0), bf0.band))
     return {"metric": "deferred+SSAO+SSR Mpixel/s, one 8K frame in row bands", "value": W8 * H8 / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": max(warmup, 1), "ms_per_step": ms_step, "scaling": "strong", "frames_in_flight": 2,
             "workload": "configs[3]: one 7680x4320 S-rand G-buffer (random depth/normal/albedo/MRO, 5 %% empty), 16 lights; rows split over %d rank(s); every "
-                        "step = NCCL broadcast of the G-buffer (%.2f GB, mode %s) + band render with locally recomputed reflection halo + NCCL all-gather of "
-                        "the RGBA16F bands (%.0f MB)" % (world, gbytes / 1e9, "P" if mode_p else "D", W8 * H8 * 8 / 1e6),
+                        "step = NCCL broadcast of the G-buffer (%.2f GB, mode %s) + band render (reflection halo %s) + NCCL all-gather of "
+                        "the RGBA16F bands (%.0f MB)" % (world, gbytes / 1e9, "P" if mode_p else "D", halo_how, W8 * H8 * 8 / 1e6),
             "band_rows": bf0.band, "gpu_launches": int(launches) * world,
             "latency": {"broadcast_ms": bcast, "render_ms": rend, "allgather_ms": gath, "frame_ms": bcast + rend + gath,
                         "note": "one frame, phases back to back, max over ranks, device events"},
@@ -663,23 +667,34 @@ def main():
         F = _capi
         fmts = ([("position", F.FORMAT_R32G32B32A32_SFLOAT)] if mode_p else []) + [
             ("depth", F.FORMAT_R32_SFLOAT), ("normal", F.FORMAT_R16G16B16A16_SFLOAT), ("albedo", F.FORMAT_R8G8B8A8_UNORM), ("mro", F.FORMAT_R8G8B8A8_UNORM)]
+        # one PACKED staging buffer per view (the attachments back to back, 256-byte aligned): one H2D copy per view instead of four
+        sizes = [_capi.BYTES_PER_TEXEL[f] * W4K * H4K for _, f in fmts]
+        offs = [0]
+        for sz in sizes:
+            offs.append((offs[-1] + sz + 255) & ~255)
+        packed = offs[-1]
         host_in = []
         for (g, gb, ssr, dp) in views:
-            host_in.append({n: getattr(gb, n).tensor.cpu().pin_memory() for n, _ in fmts})
+            hp = torch.empty(packed, dtype=torch.uint8).pin_memory()
+            for (n, _), o, sz in zip(fmts, offs, sizes):
+                hp[o:o + sz].copy_(getattr(gb, n).tensor.view(-1)[:sz])
+            host_in.append(hp)
         host_out = [torch.empty(W4K * H4K * 8, dtype=torch.uint8).pin_memory() for _ in views]
-        h2d = sum(t_.numel() for t_ in host_in[0].values()) * V
+        h2d = packed * V
         d2h = host_out[0].numel() * V
-        # device side: TWO sets of ctx-owned G-buffer images and colour targets (double buffering, what a host engine with
-        # MAX_FRAMES_IN_FLIGHT = 2 keeps, Include/Althea/Library.h:3). Uploads run on a copy-in stream, the frame on the
-        # compute stream, the colour read-back on a copy-out stream; CUDA events order them, so the H2D of view i+1 and the
-        # D2H of view i-1 overlap the kernels of view i. Every byte still crosses PCIe inside the timed region.
+        # device side: TWO sets of G-buffer images (views into one packed device buffer each) and colour targets (double buffering,
+        # what a host engine with MAX_FRAMES_IN_FLIGHT = 2 keeps, Include/Althea/Library.h:3). Uploads run on a copy-in stream, the
+        # frame on the compute stream, the colour read-back on a copy-out stream; CUDA events order them, so the H2D of view i+1 and
+        # the D2H of view i-1 overlap the kernels of view i. Every byte still crosses PCIe inside the timed region.
         NBUF = 2
-        dgbs, ddps = [], []
+        dgbs, ddps, dpacked = [], [], []
         for _ in range(NBUF):
+            dev_t = torch.empty(packed, dtype=torch.uint8, device=device)
+            dpacked.append(ctx.wrap_buffer(dev_t))
             dgb = engine.GBufferResources.__new__(engine.GBufferResources)
             dgb.ctx, dgb.width, dgb.height, dgb.position = ctx, W4K, H4K, None
-            for n, f in fmts:
-                setattr(dgb, n, ctx.create_image(f, W4K, H4K))
+            for (n, f), o, sz in zip(fmts, offs, sizes):
+                setattr(dgb, n, ctx.wrap_tensor(dev_t[o:o + sz], f, W4K, H4K))
             dgbs.append(dgb)
             ddps.append(engine.DeferredPass(ctx, W4K, H4K, F.FORMAT_R16G16B16A16_SFLOAT))
         dssr = engine.ScreenSpaceReflection(ctx, W4K, H4K)
@@ -697,8 +712,7 @@ def main():
                 counter[0] += 1
                 if not first:
                     s_in.wait_event(ev_cmp[k])     # the previous frame on this set has consumed it
-                for n, _ in fmts:
-                    ctx.upload(getattr(dgbs[k], n), host_in[i][n].data_ptr(), host_in[i][n].numel(), s_in.cuda_stream)
+                ctx.upload(dpacked[k], host_in[i].data_ptr(), packed, s_in.cuda_stream)
                 ev_in[k].record(s_in)
                 s_cmp.wait_event(ev_in[k])
                 if not first:
@@ -724,8 +738,9 @@ def main():
         ms2 = float(t2.item()) / k2
         e2e = {"value": world * px_per_step / (ms2 * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms2, "steps": k2, "numa_node": numa_node,
-               "how": "C ABI with pinned host buffers: upload of the %d G-buffer attachments per view, frame, download of the RGBA16F colour target; " % len(fmts) +
-                      "double-buffered, copies overlapped with kernels on separate streams"}
+               "pcie_GBps_per_rank": {"h2d": h2d / (ms2 * 1e-3) / 1e9, "d2h": d2h / (ms2 * 1e-3) / 1e9},
+               "how": "C ABI with pinned host buffers: ONE packed upload of the %d G-buffer attachments per view, frame, download of the RGBA16F colour " % len(fmts) +
+                      "target; double-buffered, copies overlapped with kernels on separate streams"}
 
     # ---- BASELINE configs[3] beside the headline whenever there is more than one rank: one 8K frame in row bands, the only
     # mode with data-path collectives (NCCL broadcast + all-gather). Outside the timed region of the headline.

@@ -74,6 +74,7 @@ int althea_cuda_abi_version(void);
 #define ALTHEA_CTX_SSAO_COUNT_TAPS 4u /* diagnostics: the SSAO march also counts the proxy records it gathers (read with althea_cuda_diag_ssao_gathers); slower */
 #define ALTHEA_CTX_SSAO_NO_CULL 16u /* SSAO without the coarse sign test (per-block plane records in shared memory that drop the march steps which cannot flip): every tap gathers its position record, as in round 1; same counts bit for bit: A/B switch */
 #define ALTHEA_CTX_SSR_PLANE_SKIP 32u /* SSR skips the march steps whose two taps the plane records of the depth buffer (one {alpha, beta, gamma, r} of reciprocal eye depth per 32 x 32 texels) prove to project on one side of the ray, and whole runs of them inside a block; same hit mask bit for bit in the parity build. Opt-in: 95 % of the taps are skipped at 4K, but a skipped tap costs ~45 instructions against the fast march's ~55, so it only pays in the parity build */
+#define ALTHEA_CTX_BAND_EXCHANGE_HALO 64u /* row bands: ssr_capture writes only the scissor's own rows of reflection mip 0; the host fills the halo rows the band's glossy mips read (althea_cuda_band_rows) from the ranks that own them before glossy_convolve, instead of every rank recomputing them */
 int althea_cuda_set_flags(althea_cuda_ctx* ctx, uint32_t flags);
 
 /* Row bands (multi-GPU split of ONE frame, BASELINE configs[3]): restricts ssr_capture / glossy_convolve / deferred_shade on
@@ -184,7 +185,8 @@ int althea_cuda_glossy_convolve(althea_cuda_ctx* ctx, uint64_t reflection, const
 
 #define ALTHEA_SHADE_SKIP_TONEMAP 1u /* DeferredPass.frag:48-50,86-88 */
 #define ALTHEA_SHADE_NO_SSAO 2u      /* keep the G-buffer occlusion channel instead of computeSSAO */
-#define ALTHEA_SHADE_AO_FROM_IMAGE 4u /* read occluded-ray counts from ao_counts instead of computing them (tests) */
+#define ALTHEA_SHADE_AO_FROM_IMAGE 4u /* read occluded-ray counts from ao_counts instead of computing them (tests; second half of a split frame) */
+#define ALTHEA_SHADE_AO_ONLY 8u       /* compute the occluded-ray counts into ao_counts (required) and stop: no shading, out_color and reflection are not touched. With AO_FROM_IMAGE on a later call this splits the stage, so that a row-band host can run SSAO while the reflection halo is exchanged */
 /* out_color: RGBA16F or RGBA32F, frame-sized. ao_counts: optional R8_UINT frame-sized image; when non-zero the SSAO
  * kernel writes its per-pixel occluded-ray counts there (or, with AO_FROM_IMAGE, reads them). 0 => internal scratch. */
 int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniforms* uniforms, const althea_gbuffer* gbuffer,

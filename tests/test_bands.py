@@ -48,6 +48,31 @@ def test_band_rows_contain_what_the_band_reads(lib_built):
         engine.band_rows(W, H, mips, 10, 10)
 
 
+def test_halo_plan_is_symmetric_and_covers_what_a_band_reads(lib_built):
+    """Every row of reflection mip 0 a band's glossy mips read lies in the band itself or in exactly one receive of its plan, and
+    what rank r receives from q is what q sends to r."""
+    from althea_b200 import engine
+    for (W, H) in ((7680, 4320), (320, 181)):
+        for world in (2, 3, 8):
+            plans = [bands.halo_plan(W, H, 5, world, r) for r in range(world)]
+            spans = bands.split_rows(H, world)
+            for r, (recv, send) in enumerate(plans):
+                y0, y1 = spans[r]
+                if y1 <= y0:
+                    assert not recv and not send
+                    continue
+                lo, hi = engine.band_rows(W, H, 5, y0, y1)[0]
+                got = np.zeros(H, np.int32)
+                got[y0:y1] += 1
+                for q, a, b in recv:
+                    assert spans[q][0] <= a < b <= spans[q][1]
+                    got[a:b] += 1
+                    assert (r, a, b) in plans[q][1]
+                assert (got[lo:hi] == 1).all() and got[:lo].sum() == 0 and got[hi:].sum() == 0
+                for q, a, b in send:
+                    assert (r, a, b) in plans[q][0]
+
+
 def _gloo_worker(rank, world, port, H, W, out):
     import torch.distributed as dist
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
@@ -123,7 +148,56 @@ def test_bands_equal_whole_frame_on_one_gpu(request, which):
     ctx.set_scissor_rows(0, 0)
 
 
-def _nccl_worker(rank, world, port, q):
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["parity", "fast"])
+def test_band_with_exchanged_halo_equals_whole_frame(request, which):
+    """The split the multi-GPU path runs (ALTHEA_CTX_BAND_EXCHANGE_HALO + ALTHEA_SHADE_AO_ONLY / AO_FROM_IMAGE): the band's own
+    reflection rows, the halo rows copied in from whoever owns them (here: from the whole-frame result, as a neighbour's band would
+    hold them), SSAO on its own, then convolve and shading: the band's rows come out bit-identical to the whole frame's."""
+    from helpers import FrameData, GpuFrame
+    from althea_b200 import _capi, engine
+    ctx = request.getfixturevalue("ctx_parity" if which == "parity" else "ctx_fast")
+    fd = FrameData("scene", 320, 181, n_lights=2, shadow_res=32)
+    gf = GpuFrame(ctx, fd)
+    base = ctx.flags
+    gf.ssr.captureReflection(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights)
+    gf.ssr.convolveReflectionBuffer()
+    gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+    torch.cuda.synchronize()
+    full_c = gf.deferred.colorTarget.tensor.clone().view(fd.H, -1)
+    full_r = gf.ssr.getReflectionBuffer().image.tensor.clone()
+    rb = fd.W * 8
+    try:
+        for world in (2, 5):
+            for rank, (y0, y1) in enumerate(bands.split_rows(fd.H, world)):
+                refl = gf.ssr.getReflectionBuffer().image.tensor
+                refl.fill_(0xFF)
+                gf.deferred.colorTarget.tensor.fill_(0x7F)
+                gf.deferred.aoCounts.tensor.fill_(0x7F)
+                ctx.set_scissor_rows(y0, y1)
+                ctx.set_flags(base | _capi.CTX_BAND_EXCHANGE_HALO)
+                gf.ssr.captureReflection(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights)
+                torch.cuda.synchronize()
+                assert torch.equal(refl[y0 * rb:y1 * rb], full_r[y0 * rb:y1 * rb])
+                assert bool((refl[:y0 * rb] == 0xFF).all()) and bool((refl[y1 * rb:fd.H * rb] == 0xFF).all())  # own rows only
+                recv, _ = bands.halo_plan(fd.W, fd.H, 5, world, rank)
+                for _, a, b in recv:
+                    refl[a * rb:b * rb] = full_r[a * rb:b * rb]
+                gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_AO_ONLY)
+                assert bool((gf.deferred.colorTarget.tensor == 0x7F).all())  # AO_ONLY does not shade
+                gf.ssr.convolveReflectionBuffer()
+                gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP | _capi.SHADE_AO_FROM_IMAGE)
+                torch.cuda.synchronize()
+                c = gf.deferred.colorTarget.tensor.view(fd.H, -1)
+                assert torch.equal(c[y0:y1], full_c[y0:y1]), (world, rank)
+                ctx.set_flags(base)
+                ctx.set_scissor_rows(0, 0)
+    finally:
+        ctx.set_flags(base)
+        ctx.set_scissor_rows(0, 0)
+
+
+def _nccl_worker(rank, world, port, q, rank_mode=1):
     import torch.distributed as dist
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world, device_id=torch.device("cuda:%d" % rank))
@@ -145,7 +219,7 @@ def _nccl_worker(rank, world, port, q):
                 img.tensor.zero_()
         bf = bands.BandedFrame(ctx, fd.W, fd.H, out_format=_capi.FORMAT_R32G32B32A32_SFLOAT)
         bf.broadcast_gbuffer(gf.gbuffer, src=0)
-        bf.render(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights)
+        bf.render(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, exchange_halo=(rank_mode == 1))
         bf.gather()
         torch.cuda.synchronize()
         ok = torch.equal(bf.color_rows().reshape(-1), want)
@@ -156,14 +230,16 @@ def _nccl_worker(rank, world, port, q):
 
 
 @pytest.mark.gpu
-def test_bands_over_two_gpus_nccl():
+@pytest.mark.parametrize("exchange", [1, 0])
+def test_bands_over_two_gpus_nccl(exchange):
+    """exchange = 1: the reflection halo comes from the neighbour (P2P inside the frame); 0: every rank recomputes it."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q, exchange)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
