@@ -65,6 +65,7 @@ struct althea_cuda_ctx {
     void* plane = nullptr; size_t planeBytes = 0;       // SSAO plane records (three levels, padded), tile hand-over list, reciprocal depths
     void* depthPad = nullptr; size_t depthPadBytes = 0; // SSR padded depth, (W+2) x (H+2) floats
     void* ssrPlane = nullptr;                           // SSR plane records, kSsrPlaneStride x kSsrPlaneRows x 16 B
+    void* ssrHits = nullptr; size_t ssrHitsBytes = 0;   // SSR hit list: a counter, then 12 floats per pixel of the launch (worst case: every pixel hits)
   };
   std::map<cudaStream_t, Scratch> scratch;
   struct RasterScratch* raster = nullptr; // scratch of the rasterising producers (draw_gbuffer / draw_shadow_cubes)
@@ -466,7 +467,7 @@ void althea_cuda_destroy(althea_cuda_ctx* ctx) {
   }
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   for (auto& kv : ctx->scratch)
-    for (void* p : {kv.second.ao, kv.second.position, kv.second.quad, kv.second.plane, kv.second.depthPad, kv.second.ssrPlane})
+    for (void* p : {kv.second.ao, kv.second.position, kv.second.quad, kv.second.plane, kv.second.depthPad, kv.second.ssrPlane, kv.second.ssrHits})
       if (p) cudaFree(p);
   if (ctx->gatherCounter) cudaFree(ctx->gatherCounter);
   freeRasterScratch(ctx->raster);
@@ -764,6 +765,15 @@ int althea_cuda_ssr_capture(althea_cuda_ctx* ctx, const althea_global_uniforms* 
     P.depthPad = static_cast<const float*>(S.depthPad);
     P.depthPadOrigin = P.depthPad + P.depthPadRow + 1;
   }
+  P.ssrHits = nullptr;
+  P.ssrHitCount = nullptr;
+  if (!(ctx->flags & ALTHEA_CTX_SSR_PLANE_SKIP)) { // the march's hit list (the plane-skip variant shades in place)
+    const size_t cap = (size_t)P.W * (size_t)(P.y1 - P.y0);
+    if ((rc = growScratchBuf(ctx, &S.ssrHits, &S.ssrHitsBytes, 256 + cap * 12 * sizeof(float), "ssr hit list"))) return rc;
+    P.ssrHitCount = static_cast<unsigned*>(S.ssrHits);
+    P.ssrHits = reinterpret_cast<float*>(static_cast<char*>(S.ssrHits) + 256);
+    P.ssrHitCap = (unsigned)cap;
+  }
   P.ssrPlanes = nullptr;
   if (ctx->flags & ALTHEA_CTX_SSR_PLANE_SKIP) { // sign test over plane records of the depth buffer: the smallest blocks that cover the frame
     int shift = 3;
@@ -788,6 +798,7 @@ int althea_cuda_ssr_capture(althea_cuda_ctx* ctx, const althea_global_uniforms* 
   timedLaunch(ctx, "ssr_depth_pad", stream, [&] { parity ? althea_parity::launch_ssr_depth_pad(P, stream) : althea_fast::launch_ssr_depth_pad(P, stream); });
   if (P.ssrPlanes) timedLaunch(ctx, "ssr_planes", stream, [&] { parity ? althea_parity::launch_ssr_planes(P, stream) : althea_fast::launch_ssr_planes(P, stream); });
   timedLaunch(ctx, "ssr_capture", stream, [&] { parity ? althea_parity::launch_ssr_capture(P, stream) : althea_fast::launch_ssr_capture(P, stream); });
+  if (P.ssrHits) timedLaunch(ctx, "ssr_shade_hits", stream, [&] { parity ? althea_parity::launch_ssr_shade_hits(P, stream) : althea_fast::launch_ssr_shade_hits(P, stream); });
   return endWork(ctx, sync, stream);
 }
 

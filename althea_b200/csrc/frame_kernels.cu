@@ -198,6 +198,7 @@ constexpr float kTiny = 1e-15f; // decisions on |value| <= kTiny are always re-e
 __global__ void __launch_bounds__(256) ssr_depth_pad_kernel(const __grid_constant__ FrameParams P) {
   const int qx = blockIdx.x * 32 + (threadIdx.x & 31);
   const int qy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (qx == 0 && qy == 0 && P.ssrHitCount) *P.ssrHitCount = 0u; // the hit list ssr_capture_kernel (next in the stream) appends to
   if (qx > P.W + 1 || qy > P.H + 1) return;
   const float d = __ldg(rowPtr<float>(P.depth, AddrClamp::wrap(qy - 1, P.H)) + AddrClamp::wrap(qx - 1, P.W));
   const_cast<float*>(P.depthPad)[(size_t)qy * P.depthPadRow + qx] = d;
@@ -234,13 +235,23 @@ ADEV V4 environmentLitSample(const FrameParams& P, V3 currentPos, float u, float
 #ifndef ALTHEA_SSR_MIN_BLOCKS
 #define ALTHEA_SSR_MIN_BLOCKS 4 // 64 registers: the march is latency-bound, a fourth resident CTA is worth more than the registers
 #endif
-__global__ void __launch_bounds__(256, ALTHEA_SSR_MIN_BLOCKS) ssr_capture_kernel(const __grid_constant__ FrameParams P) {
+// The march and the shading of its hits are two kernels. The march is bound by the latency of its dependent depth taps
+// (long_scoreboard, profiles/r2_frame_full.md): without the 16-light shading of a hit (SSR.frag:55-78) in the same kernel it needs
+// 48 registers instead of 64 (five CTAs per SM instead of four; six or eight were measured no faster). Hits (~18 % of the pixels, scattered over most
+// warps) are appended to a list and shaded packed, every lane of every warp busy, by ssr_shade_hits_kernel.
+#ifndef ALTHEA_SSR_MARCH_MIN_BLOCKS
+#define ALTHEA_SSR_MARCH_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(256, ALTHEA_SSR_MARCH_MIN_BLOCKS) ssr_capture_kernel(const __grid_constant__ FrameParams P) {
   const int x = blockIdx.x * 16 + (threadIdx.x & 15);
   const int y = P.y0 + blockIdx.y * 16 + (threadIdx.x >> 4); // rows [y0, y1): the scissor (whole frame by default)
-  if (x >= P.W || y >= P.y1) return;
+  const bool inside = x < P.W && y < P.y1;
   const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
-  V4 normal4 = FmtRGBA16F::load(P.normal, x, y);
-  V4 out = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+  V4 normal4 = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (inside) normal4 = FmtRGBA16F::load(P.normal, x, y);
+  bool hit = false;
+  float hcu = 0.0f, hcv = 0.0f;
+  V3 hitPos = mk3(0.0f, 0.0f, 0.0f), hitNormal = hitPos, hitRay = hitPos;
   if (normal4.w != 0.0f) { // SSR.frag:136-141
     const float dOwn = __ldg(rowPtr<float>(P.depth, y) + x);
     const V3 worldPos = reconstructPosition(P, u, v, dOwn);
@@ -253,10 +264,6 @@ __global__ void __launch_bounds__(256, ALTHEA_SSR_MIN_BLOCKS) ssr_capture_kernel
     const float stepX = (dx / dl) * 0.005f, stepY = (dy / dl) * 0.005f;
     const V3 perpRef = normalize3(cross3(cross3(rayDir, normal), rayDir));
     float cu = u, cv = v;
-    // a hit is shaded after the march: inside the loop every lane of a warp would run the 16-light shading on its own at the
-    // step where it hits
-    bool hit = false;
-    V3 hitPos = worldPos, hitNormal = normal;
 #ifdef ALTHEA_PARITY
     float prevProjection = 0.0f;
 #else
@@ -334,10 +341,39 @@ __global__ void __launch_bounds__(256, ALTHEA_SSR_MIN_BLOCKS) ssr_capture_kernel
       prevProjection = currentProjection;
     }
 #endif
-    if (hit) out = environmentLitSample(P, hitPos, cu, cv, rayDir, hitNormal);
+    hcu = cu; hcv = cv; hitRay = rayDir;
   }
-  // blend-on-write over the (0,0,0,0) clear (GraphicsPipeline.cpp:138-154): rgb*a, a
-  rowPtrW<uint2>(P.refl.level[0], y)[x] = packHalf4(mk4(out.x * out.w, out.y * out.w, out.z * out.w, out.w));
+  // no hit: (0, 0, 0, 0), the clear the blend-on-write leaves (GraphicsPipeline.cpp:138-154)
+  if (inside && !hit) rowPtrW<uint2>(P.refl.level[0], y)[x] = make_uint2(0u, 0u);
+  // hits: one record each, appended with one atomic per warp
+  const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+  if (ballot) {
+    const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
+    unsigned base = 0u;
+    if (lane == leader) base = atomicAdd(P.ssrHitCount, (unsigned)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (hit) {
+      float* r = P.ssrHits + (base + __popc(ballot & ((1u << lane) - 1u)));
+      const unsigned cap = P.ssrHitCap;
+      r[0] = __int_as_float(x | (y << 16));
+      r[cap] = hcu; r[2 * cap] = hcv;
+      r[3 * cap] = hitPos.x; r[4 * cap] = hitPos.y; r[5 * cap] = hitPos.z;
+      r[6 * cap] = hitNormal.x; r[7 * cap] = hitNormal.y; r[8 * cap] = hitNormal.z;
+      r[9 * cap] = hitRay.x; r[10 * cap] = hitRay.y; r[11 * cap] = hitRay.z;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) ssr_shade_hits_kernel(const __grid_constant__ FrameParams P) {
+  const unsigned count = *P.ssrHitCount, cap = P.ssrHitCap;
+  for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < count; k += gridDim.x * 256u) {
+    const float* r = P.ssrHits + k;
+    const int xy = __float_as_int(r[0]);
+    const V4 out = environmentLitSample(P, mk3(r[3 * cap], r[4 * cap], r[5 * cap]), r[cap], r[2 * cap], mk3(r[9 * cap], r[10 * cap], r[11 * cap]),
+                                        mk3(r[6 * cap], r[7 * cap], r[8 * cap]));
+    // blend-on-write over the (0,0,0,0) clear: rgb*a, a
+    rowPtrW<uint2>(P.refl.level[0], xy >> 16)[xy & 0xffff] = packHalf4(mk4(out.x * out.w, out.y * out.w, out.z * out.w, out.w));
+  }
 }
 
 // ---- SSR, round 2: sign test over plane records of the depth buffer ------------------------------------------------------
@@ -1796,6 +1832,7 @@ void launch_ssr_capture(const FrameParams& P, cudaStream_t s) {
   if (P.ssrPlanes) ssr_capture_skip_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P);
   else ssr_capture_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P);
 }
+void launch_ssr_shade_hits(const FrameParams& P, cudaStream_t s) { ssr_shade_hits_kernel<<<148 * 8, 256, 0, s>>>(P); }
 void launch_ssr_planes(const FrameParams& P, cudaStream_t s) { ssr_planes_kernel<<<(kSsrPlaneStride * kSsrPlaneRows + 7) / 8, 256, 0, s>>>(P); }
 void launch_ssr_depth_pad(const FrameParams& P, cudaStream_t s) {
   ssr_depth_pad_kernel<<<dim3((unsigned)((P.W + 2 + 31) / 32), (unsigned)((P.H + 2 + 7) / 8)), 256, 0, s>>>(P);

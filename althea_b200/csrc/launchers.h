@@ -10,6 +10,7 @@
   void launch_ssr_capture(const FrameParams& P, cudaStream_t s);             \
   void launch_ssr_depth_pad(const FrameParams& P, cudaStream_t s);           \
   void launch_ssr_planes(const FrameParams& P, cudaStream_t s);              \
+  void launch_ssr_shade_hits(const FrameParams& P, cudaStream_t s);          \
   void launch_reconstruct_position(const FrameParams& P, cudaStream_t s);    \
   void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s);      \
   void launch_ssao(const FrameParams& P, cudaStream_t s);                    \

@@ -71,6 +71,11 @@ struct FrameParams {
   // (1 << ssrPlaneShift)^2 depth texels, the whole frame in kSsrPlaneStride x kSsrPlaneRows records (r = +inf outside). Null: plain march
   const float4* ssrPlanes;
   int ssrPlaneShift;
+  // SSR hit list (engine scratch): the march appends one record per hit pixel (12 floats, structure of arrays with stride
+  // ssrHitCap), a second kernel shades them packed. ssrHitCount is zeroed by ssr_depth_pad_kernel
+  float* ssrHits;
+  unsigned* ssrHitCount;
+  unsigned ssrHitCap;
   // SSR padded depth (engine scratch): the depth image with a one-texel CLAMP_TO_EDGE border, (W+2) x (H+2) floats
   const float* depthPad;
   const float* depthPadOrigin; // &padded(1, 1), i.e. texel (0, 0)

@@ -12,6 +12,10 @@ top = int(sys.argv[4]) if len(sys.argv) > 4 else 60
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass", "--csv", "--kernel-name", "regex:" + kern],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
+for k in range(1, len(rows)):  # several launches match: keep the first one's table
+    if rows[k] and rows[k][0] == "Kernel Name":
+        rows = rows[:k]
+        break
 name = rows[0][1]
 hdr = rows[1]
 iA, iS, iE, iN = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
