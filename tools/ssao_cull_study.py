@@ -31,6 +31,10 @@ W, H = 3840, 2160
 LOOSE = os.environ.get("LOOSE", "0") == "1"
 MULTI = os.environ.get("MULTI", "")  # "ray": finest level whose window holds the ray, "tap": per tap, "tile": per tile (kernel)
 UND = {}
+PRE = os.environ.get("PRE", "0") == "1"
+PRE_OVERLAP = os.environ.get("PRE_OVERLAP", "1") == "1"
+PRE_BLOCKS = (64, 128, 256)
+PRESTAT, PREOK, PREBAD = {}, {}, {}
 REACH = float(os.environ.get("REACH", "0.75"))
 ETA = os.environ.get("ETA", "0") == "1"
 KERNEL = os.environ.get("KERNEL", "0") == "1"
@@ -54,16 +58,16 @@ def make_view(kind):
     return d["position"], d["normal"], gm
 
 
-def block_records(pos, cam, fwd, B):
+def block_records(pos, cam, fwd, B, ox=0, oy=0):
     """Per B x B block (+ one texel of apron to the right / below): plane fit of w = 1 / eye depth and the residual range."""
     covered = pos[..., 3] != 0
     t = (pos[..., :3].astype(np.float64) - cam) @ fwd
     with np.errstate(divide="ignore"):
         w = np.where(covered, 1.0 / t, 0.0)
-    nbx, nby = (W + B - 1) // B, (H + B - 1) // B
-    # gather the (B + 1)^2 texels of every block (clamped at the image edge)
-    ys = np.minimum(np.arange(nby)[:, None] * B + np.arange(B + 1)[None, :], H - 1)   # (nby, B+1)
-    xs = np.minimum(np.arange(nbx)[:, None] * B + np.arange(B + 1)[None, :], W - 1)
+    nbx, nby = (W + ox + B - 1) // B, (H + oy + B - 1) // B
+    # gather the (B + 1)^2 texels of every block (clamped at the image edge); block b covers texels b * B - o .. b * B - o + B
+    ys = np.clip(np.arange(nby)[:, None] * B - oy + np.arange(B + 1)[None, :], 0, H - 1)   # (nby, B+1)
+    xs = np.clip(np.arange(nbx)[:, None] * B - ox + np.arange(B + 1)[None, :], 0, W - 1)
     wb = w[ys[:, None, :, None], xs[None, :, None, :]]                                # (nby, nbx, B+1, B+1)
     cb = covered[ys[:, None, :, None], xs[None, :, None, :]]
     allc, anyc = cb.all((2, 3)), cb.any((2, 3))
@@ -87,6 +91,8 @@ def study(kind="scene", B=8, ntiles=400, seed=1):
     PV = proj @ view
     cam, fwd = invV[:3, 3], -invV[:3, 2]
     recs = {b: block_records(pos, cam, fwd, b) for b in ((8, 16, 32) if MULTI else (B,))}
+    global recs_pre
+    recs_pre = {pb: {(ox, oy): block_records(pos, cam, fwd, pb, ox, oy) for ox, oy in ((0, 0), (pb // 2, 0), (0, pb // 2), (pb // 2, pb // 2))} for pb in PRE_BLOCKS} if PRE else {}
     pos_img = pos[..., :3].astype(np.float64)
     nrm_img = T._f16(nrm_u16)[..., :3]
     # D(x, y): direction through texel (x, y) scaled to eye depth 1, affine in (x, y)
@@ -137,6 +143,37 @@ def study(kind="scene", B=8, ntiles=400, seed=1):
         with np.errstate(divide="ignore", invalid="ignore"):
             x11, y11 = (uv0[..., 0] / 12 + uv1[..., 0] * 11 / 12) * W - 0.5, (uv0[..., 1] / 12 + uv1[..., 1] * 11 / 12) * H - 0.5
             L11 = -(ac + au * x11 + av * y11) / c0
+        # ---- per-ray pre-test: taps 1 and 11 inside ONE coarse block whose record decides both with the same sign
+        if PRE:
+            for PB in PRE_BLOCKS:
+                rp = recs_pre[PB]
+                xa, ya = (uv0[..., 0] * 11 / 12 + uv1[..., 0] / 12) * W - 0.5, (uv0[..., 1] * 11 / 12 + uv1[..., 1] / 12) * H - 0.5
+                ok_any = np.zeros(shp, bool)
+                for ox, oy in (((0, 0), (PB // 2, 0), (0, PB // 2), (PB // 2, PB // 2)) if PRE_OVERLAP else ((0, 0),)):
+                    r_ = rp[(ox, oy)]
+                    with np.errstate(invalid="ignore"):
+                        bxa, bya = np.floor((xa + ox) / PB), np.floor((ya + oy) / PB)
+                        bxb, byb = np.floor((x11 + ox) / PB), np.floor((y11 + oy) / PB)
+                        same = (bxa == bxb) & (bya == byb) & np.isfinite(x11) & np.isfinite(y11) & (x11 >= 0) & (x11 <= W - 1) & (y11 >= 0) & (y11 <= H - 1)
+                    bxi = np.clip(np.where(same, bxa, 0), 0, r_["kind"].shape[1] - 1).astype(int)
+                    byi = np.clip(np.where(same, bya, 0), 0, r_["kind"].shape[0] - 1).astype(int)
+                    k_ = r_["kind"][byi, bxi]
+                    def dval(xq, yq):
+                        wpl = r_["w0"][byi, bxi] + r_["beta"][byi, bxi] * (xq + ox - bxi * PB) + r_["gamma"][byi, bxi] * (yq + oy - byi * PB)
+                        with np.errstate(divide="ignore", invalid="ignore"):
+                            return wpl + 0.5 * (r_["rhi"][byi, bxi] + r_["rlo"][byi, bxi]) + (ac + au * xq + av * yq) / c0
+                    rraw = 0.5 * (r_["rhi"][byi, bxi] - r_["rlo"][byi, bxi])
+                    grec = np.abs(r_["beta"][byi, bxi]) + np.abs(r_["gamma"][byi, bxi])
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        gray = np.abs(au / c0) + np.abs(av / c0)
+                        slack = 1.02 * rraw + 0.06 * (grec + gray) + 3e-5 * np.abs(r_["wmax"][byi, bxi]) / np.maximum(np.abs(c0), 1e-30) + 1e-6 * r_["wmax"][byi, bxi]
+                        da, db = dval(xa, ya), dval(x11, y11)
+                        ok = same & (k_ == 1) & (np.abs(da) > slack) & (np.abs(db) > slack) & (da * db > 0)
+                    ok_any |= ok
+                PRESTAT.setdefault(PB, [0, 0])
+                PRESTAT[PB][0] += int((covered & ok_any).sum())
+                PRESTAT[PB][1] += int(covered.sum())
+                PREOK[PB] = ok_any
         prev_pos, prev_proj = P.copy(), np.zeros(shp)
         live = covered.copy()
         cls_prev = np.zeros(shp, np.int8)          # coarse class of the previous tap: +1 / -1 / 0 undecided
@@ -233,6 +270,10 @@ def study(kind="scene", B=8, ntiles=400, seed=1):
                 live &= ~hit
             prev_pos = np.where(live[..., None], cur, prev_pos)
             prev_proj = np.where(live, pr, prev_proj)
+        if PRE:
+            flipped = (covered & ~live)  # rays that scored (a flip happened) ...
+            for PB in PRE_BLOCKS:
+                PREBAD[PB] = PREBAD.get(PB, 0) + int((PREOK[PB] & flipped).sum())
         stats["rays"] += int(covered.sum())
         stats["rays_all_decided"] += int((covered & ~detail.any(0)).sum())
         stats["detail_steps"] += int(detail.sum())
@@ -248,6 +289,7 @@ def study(kind="scene", B=8, ntiles=400, seed=1):
     print("  coarse-decided taps: %.1f %%   unsound: %d" % (100.0 * s["decided"] / s["taps_old"], s["unsound"]))
     print("  rays with no detailed step: %.1f %%   hits: %.1f %% of rays" % (100.0 * s["rays_all_decided"] / s["rays"], 100.0 * s["hits"] / s["rays"]))
     print("  gathers: old %d -> new %d (%.1f %%), detailed steps %d" % (s["taps_old"], s["gathers_new"], 100.0 * s["gathers_new"] / s["taps_old"], s["detail_steps"]))
+    for PB in PRESTAT: print("   pre-test, %3d-texel blocks%s: %.1f %% of the rays pass; passed rays that scored (unsound): %d" % (PB, " (overlapping)" if PRE_OVERLAP else "", 100.0 * PRESTAT[PB][0] / max(1, PRESTAT[PB][1]), PREBAD.get(PB, 0)))
     for i in sorted(UND): print("   tap %2d: undecided mixed %6d sky %6d surface %6d of %d" % (i, *UND[i]))
     print("  warp iterations: old march %d; two-phase coarse %d + detail %d" % (s["warp_iters_old"], s["warp_iters_coarse"], s["warp_iters_detail"]))
     return s
