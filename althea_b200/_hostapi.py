@@ -13,6 +13,7 @@ SIGNATURES = {
     "althea_host_compute_flat_normals": (C.c_int, [_P, C.c_uint64, _P]),
     "althea_host_compute_tangent_space": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P]),
     "althea_host_save_hdri": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, _P]),
+    "althea_host_save_exr": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, _P]),
     "althea_host_load_hdri_info": (C.c_int, [C.c_char_p, _I32P, _I32P]),
     "althea_host_load_hdri": (C.c_int, [C.c_char_p, _P, C.c_uint64]),
     "althea_host_camera": (C.c_int, [_F, _F, _F, _F, _P, _F, _F, _P, _P, _P, _P]),

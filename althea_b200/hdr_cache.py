@@ -119,3 +119,14 @@ def load_precomputed_maps(content_dir: str, env_name: str):
         return np.concatenate([a, np.ones(a.shape[:2] + (1,), np.float32)], -1)
 
     return rgba(read_hdr(irr_path)), [rgba(read_hdr(p)) for p in pre_paths]
+
+
+def save_exr(path: str, rgba: np.ndarray):
+    """Utilities::saveExr through libalthea_host.so: (H, W, 4) float32 -> an OpenEXR file in the layout the reference writes
+    (Src/Utilities.cpp:258-271), the dump format of a golden frame."""
+    a = np.ascontiguousarray(rgba, np.float32)
+    if a.ndim != 3 or a.shape[2] != 4:
+        raise ValueError("save_exr needs an (H, W, 4) float32 image")
+    rc = _host().althea_host_save_exr(os.fsencode(path), a.shape[1], a.shape[0], a.ctypes.data)
+    if rc != 0:
+        raise OSError("althea_host_save_exr(%s) failed: %d" % (path, rc))

@@ -174,6 +174,52 @@ public:
     if (n != file.size()) throw std::runtime_error("Failed to write file: " + path);
   }
 
+  // Src/Utilities.cpp:258-271: `data` holds width * height RGBA32F texels; tinyexr's SaveEXR(data, w, h, 4, /*fp16*/0, path): an
+  // OpenEXR 2 scan-line file with the four channels A, B, G, R as 32-bit FLOAT, increasing-y line order, data window
+  // (0, 0)-(w-1, h-1). Written here uncompressed (tinyexr deflates blocks of 16 lines; every OpenEXR reader, tinyexr's LoadEXR
+  // included, reads either): the decoded image is the same bits.
+  static void saveExr(const std::string& path, int width, int height, const std::byte* data, size_t bytes) {
+    if (width <= 0 || height <= 0 || bytes < (size_t)width * height * 16) throw std::runtime_error("saveExr: buffer smaller than the image");
+    const float* rgba = reinterpret_cast<const float*>(data);
+    std::vector<uint8_t> f;
+    auto u8 = [&](uint8_t v) { f.push_back(v); };
+    auto i32 = [&](int32_t v) { for (int k = 0; k < 4; ++k) f.push_back((uint8_t)((uint32_t)v >> (8 * k))); };
+    auto f32 = [&](float v) { uint32_t b; std::memcpy(&b, &v, 4); i32((int32_t)b); };
+    auto str = [&](const char* z) { while (*z) f.push_back((uint8_t)*z++); f.push_back(0); };
+    auto attr = [&](const char* name, const char* type, int32_t size) { str(name); str(type); i32(size); };
+    i32(20000630); // magic
+    i32(2);        // version 2, single-part scan lines
+    attr("channels", "chlist", 4 * 18 + 1);
+    for (const char* c : {"A", "B", "G", "R"}) { str(c); i32(2 /*FLOAT*/); u8(0); u8(0); u8(0); u8(0); i32(1); i32(1); }
+    u8(0);
+    attr("compression", "compression", 1); u8(0 /*NO_COMPRESSION*/);
+    attr("dataWindow", "box2i", 16); i32(0); i32(0); i32(width - 1); i32(height - 1);
+    attr("displayWindow", "box2i", 16); i32(0); i32(0); i32(width - 1); i32(height - 1);
+    attr("lineOrder", "lineOrder", 1); u8(0 /*INCREASING_Y*/);
+    attr("pixelAspectRatio", "float", 4); f32(1.0f);
+    attr("screenWindowCenter", "v2f", 8); f32(0.0f); f32(0.0f);
+    attr("screenWindowWidth", "float", 4); f32(1.0f);
+    u8(0); // end of header
+    const size_t lineBytes = (size_t)width * 16, block = 8 + lineBytes;
+    const uint64_t first = f.size() + (uint64_t)height * 8;
+    for (int y = 0; y < height; ++y) { // offset table: one block per scan line
+      const uint64_t o = first + (uint64_t)y * block;
+      for (int k = 0; k < 8; ++k) f.push_back((uint8_t)(o >> (8 * k)));
+    }
+    f.reserve(f.size() + (size_t)height * block);
+    for (int y = 0; y < height; ++y) {
+      i32(y);
+      i32((int32_t)lineBytes);
+      for (int c : {3, 2, 1, 0}) // channel-planar lines in the order of the channel list: A, B, G, R
+        for (int x = 0; x < width; ++x) f32(rgba[((size_t)y * width + x) * 4 + c]);
+    }
+    FILE* out = std::fopen(path.c_str(), "wb");
+    if (!out) throw std::runtime_error("Failed to open file for writing: " + path);
+    const size_t n = std::fwrite(f.data(), 1, f.size(), out);
+    std::fclose(out);
+    if (n != f.size()) throw std::runtime_error("Failed to write file: " + path);
+  }
+
   static std::vector<uint8_t> readFile(const std::string& path) {
     FILE* f = std::fopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("Failed to open file: " + path);

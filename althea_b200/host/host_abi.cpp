@@ -61,6 +61,16 @@ int althea_host_save_hdri(const char* path, int32_t width, int32_t height, const
   return 0;
 }
 
+int althea_host_save_exr(const char* path, int32_t width, int32_t height, const float* rgba) {
+  if (!path || !rgba || width <= 0 || height <= 0) return -1;
+  try {
+    AltheaEngine::Utilities::saveExr(path, width, height, reinterpret_cast<const std::byte*>(rgba), (size_t)width * height * 16);
+  } catch (const std::exception&) {
+    return -2;
+  }
+  return 0;
+}
+
 static int loadHdri(const char* path, int32_t* width, int32_t* height, std::vector<float>& rgba) {
   std::vector<uint8_t> file;
   try {

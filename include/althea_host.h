@@ -10,6 +10,8 @@
  *                                         m_setTSpaceBasic callback)
  *   althea_host_save_hdri              <- Utilities::saveHdri                       Src/Utilities.cpp:244-255
  *                                         (stb_image_write.h stbi_write_hdr: Radiance RGBE, run-length coded rows)
+ *   althea_host_save_exr               <- Utilities::saveExr                        Src/Utilities.cpp:258-271
+ *                                         (tinyexr SaveEXR, 4 x FLOAT, scan lines)
  *   althea_host_load_hdri(_info)       <- Utilities::loadHdri                       Src/Utilities.cpp:189-213
  *                                         (stb_image.h stbi_loadf_from_memory, 4 channels requested)
  *     the pair ImageBasedLighting::createResources uses for its on-disk cache, Src/ImageBasedLighting.cpp:415-446
@@ -49,6 +51,12 @@ int althea_host_compute_tangent_space(const float* position /* 9 per face */, co
 /* Writes width x height RGBA32F texels (row 0 first; alpha is not stored) as a Radiance .hdr file, byte-identical to
  * stbi_write_hdr's output except for the header's comment line. -1: bad argument, -2: the file cannot be written. */
 int althea_host_save_hdri(const char* path, int32_t width, int32_t height, const float* rgba);
+
+/* Writes width x height RGBA32F texels as an OpenEXR file with the layout Utilities::saveExr produces (Src/Utilities.cpp:258-271,
+ * tinyexr SaveEXR with four FLOAT channels A, B, G, R, scan lines, increasing y), uncompressed; the reference's LoadEXR decodes it
+ * to the same bits (tests/test_hdr_cache.py). The dump format of BASELINE configs[0]'s golden frame. -1: bad argument, -2: the
+ * file cannot be written. */
+int althea_host_save_exr(const char* path, int32_t width, int32_t height, const float* rgba);
 
 /* Size of a .hdr file's image. -1: bad argument, -2: cannot be read, -3: not a Radiance RGBE file stbi_loadf would accept. */
 int althea_host_load_hdri_info(const char* path, int32_t* width, int32_t* height);

@@ -296,3 +296,93 @@ uint64_t probe(const CudaApplication& app) {
 ''')
     subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
                     "-I", os.path.join(ROOT, "althea_b200", "host"), str(src)], check=True)
+
+
+# ---- Utilities::saveExr (Src/Utilities.cpp:258-271): the dump format of a golden frame ------------------------------------
+def _exr_header(path):
+    """(attributes {name: (type, bytes)}, header end offset) of a single-part OpenEXR file."""
+    import struct
+    b = open(path, "rb").read()
+    assert struct.unpack_from("<I", b, 0)[0] == 20000630 and (struct.unpack_from("<I", b, 4)[0] & 0xFF) == 2
+    o, attrs = 8, {}
+    while b[o] != 0:
+        e = b.index(b"\0", o); name = b[o:e].decode(); o = e + 1
+        e = b.index(b"\0", o); typ = b[o:e].decode(); o = e + 1
+        size = struct.unpack_from("<i", b, o)[0]; o += 4
+        attrs[name] = (typ, b[o:o + size]); o += size
+    return attrs, o + 1
+
+
+def _tinyexr():
+    import ctypes as C
+    import subprocess
+
+    from helpers import ROOT
+    if os.path.isdir(os.path.join(REFERENCE, "Extern", "tinyexr")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    path = os.path.join(ROOT, "oracle", "_ref", "libtinyexr_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("reference sources not mounted and oracle/_ref not built")
+    lib = C.CDLL(path)
+    lib.ref_load_exr.argtypes = [C.c_char_p, C.c_void_p, C.c_ulonglong, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.ref_save_exr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+    return lib
+
+
+def test_exr_writer_has_the_layout_the_reference_writes(tmp_path):
+    """An uncompressed scan-line file with the channel list, windows and line order of tinyexr's SaveEXR(data, w, h, 4, 0, path);
+    every line decodes back to the bits that went in (own reader here: the file is plain enough to parse in ten lines)."""
+    import struct
+    rs = np.random.default_rng(3)
+    for (w, h) in ((1, 1), (5, 3), (64, 17), (130, 33)):
+        img = rs.normal(0, 50, (h, w, 4)).astype(np.float32)
+        img[0, 0] = [np.inf, -0.0, 1e-42, 3.4e38]  # specials survive: the payload is raw fp32
+        path = str(tmp_path / ("o_%dx%d.exr" % (w, h)))
+        hdr_cache.save_exr(path, img)
+        attrs, end = _exr_header(path)
+        assert attrs["channels"][0] == "chlist"
+        names, o, c = [], 0, attrs["channels"][1]
+        while c[o] != 0:
+            e = c.index(b"\0", o); names.append(c[o:e].decode())
+            ptype, plinear, xs, ys = struct.unpack_from("<iB3xii", c, e + 1)
+            assert (ptype, xs, ys) == (2, 1, 1)  # FLOAT, no subsampling
+            o = e + 1 + 16
+        assert names == ["A", "B", "G", "R"]
+        assert attrs["compression"][1] == b"\0" and attrs["lineOrder"][1] == b"\0"
+        assert struct.unpack("<4i", attrs["dataWindow"][1]) == (0, 0, w - 1, h - 1) == struct.unpack("<4i", attrs["displayWindow"][1])
+        b = open(path, "rb").read()
+        offs = struct.unpack_from("<%dQ" % h, b, end)
+        got = np.zeros_like(img)
+        for y, o in enumerate(offs):
+            yy, size = struct.unpack_from("<ii", b, o)
+            assert (yy, size) == (y, w * 16)
+            planes = np.frombuffer(b, np.float32, 4 * w, o + 8).reshape(4, w)  # A, B, G, R
+            got[y] = planes[::-1].T
+        assert np.array_equal(got.view(np.uint32), img.view(np.uint32))
+    with pytest.raises(ValueError):
+        hdr_cache.save_exr(str(tmp_path / "bad.exr"), np.zeros((4, 4, 3), np.float32))
+    with pytest.raises(OSError):
+        hdr_cache.save_exr(str(tmp_path / "no" / "such" / "dir.exr"), np.zeros((4, 4, 4), np.float32))
+
+
+def test_exr_against_the_references_tinyexr(tmp_path):
+    """The reference's own library (Extern/tinyexr, compiled into oracle/_ref) reads the product's file back to the same bits,
+    and the file the reference writes for the same image has the same channel list, windows and line order (it deflates its
+    blocks, the product does not: the one attribute allowed to differ)."""
+    import ctypes as C
+    lib = _tinyexr()
+    rs = np.random.default_rng(4)
+    for (w, h) in ((7, 5), (64, 40), (257, 19)):
+        img = np.exp(rs.uniform(-12, 9, (h, w, 4))).astype(np.float32)
+        ours, theirs = str(tmp_path / "ours.exr"), str(tmp_path / "theirs.exr")
+        hdr_cache.save_exr(ours, img)
+        out = np.zeros_like(img)
+        ww, hh = C.c_int(), C.c_int()
+        assert lib.ref_load_exr(os.fsencode(ours), out.ctypes.data, out.size, C.byref(ww), C.byref(hh)) == 0
+        assert (ww.value, hh.value) == (w, h) and np.array_equal(out.view(np.uint32), img.view(np.uint32))
+        assert lib.ref_save_exr(os.fsencode(theirs), w, h, img.ctypes.data) == 0
+        a, _ = _exr_header(ours)
+        b, _ = _exr_header(theirs)
+        for key in ("channels", "dataWindow", "displayWindow", "lineOrder", "pixelAspectRatio", "screenWindowCenter", "screenWindowWidth"):
+            assert a[key] == b[key], key
+        assert set(a) == set(b)

@@ -827,7 +827,7 @@ def test_helmet_fixture_answer_is_reproducible(oracle):
 
 
 @pytest.mark.gpu
-def test_gpu_helmet_frame(ctx_fast, ctx_parity, oracle):
+def test_gpu_helmet_frame(ctx_fast, ctx_parity, oracle, tmp_path):
     """BASELINE configs[0] end to end on the GPU at its own shape: G-buffer of the helmet at 1280 x 720 (depth CRC equal to the
     committed answer, attributes against the live restatement), omni shadow cubes of two lights rendered from the same mesh,
     then SSR, glossy mips, SSAO and deferred shading in the PARITY build with a real IBL set, against the frame oracle fed with
@@ -894,6 +894,22 @@ def test_gpu_helmet_frame(ctx_fast, ctx_parity, oracle):
     ok = (err <= 1e-3 * np.maximum(1.0, np.abs(col))).all(axis=-1)
     assert ok.mean() >= 0.9995, "colour off the bar on %.4f %% of pixels, max abs error %.3g" % (100 * (1 - ok.mean()), err.max())
     assert float(np.percentile(err, 99.9)) <= 1e-3, "99.9th percentile of the absolute colour error on the RGBA32F target: %.3g" % np.percentile(err, 99.9)
+    # the golden dump of configs[0]: the frame as the EXR file Utilities::saveExr writes (Src/Utilities.cpp:258-271), read back by
+    # the reference's own tinyexr where oracle/_ref carries it
+    import ctypes as C
+
+    from althea_b200 import hdr_cache
+    exr = str(tmp_path / "helmet_1280x720.exr")
+    hdr_cache.save_exr(exr, got_col)
+    assert os.path.getsize(exr) > W * H * 16
+    ref_lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libtinyexr_ref.so")
+    if os.path.exists(ref_lib):
+        lib = C.CDLL(ref_lib)
+        lib.ref_load_exr.argtypes = [C.c_char_p, C.c_void_p, C.c_ulonglong, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        back = np.zeros_like(got_col)
+        ww, hh = C.c_int(), C.c_int()
+        assert lib.ref_load_exr(os.fsencode(exr), back.ctypes.data, back.size, C.byref(ww), C.byref(hh)) == 0
+        assert (ww.value, hh.value) == (W, H) and np.array_equal(back.view(np.uint32), np.ascontiguousarray(got_col).view(np.uint32))
 
 
 @pytest.mark.gpu

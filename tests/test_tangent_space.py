@@ -50,7 +50,7 @@ def test_host_library_exports_what_the_header_declares():
     header = open(os.path.join(ROOT, "include", "althea_host.h")).read()
     declared = set(re.findall(r"\b(althea_host_\w+)\s*\(", header))
     assert declared == {"althea_host_abi_version", "althea_host_compute_flat_normals", "althea_host_compute_tangent_space",
-                        "althea_host_save_hdri", "althea_host_load_hdri_info", "althea_host_load_hdri", "althea_host_camera",
+                        "althea_host_save_hdri", "althea_host_save_exr", "althea_host_load_hdri_info", "althea_host_load_hdri", "althea_host_camera",
                         "althea_host_point_light_constants"}
     exported = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
     assert set(re.findall(r"\bT (althea_host_\w+)", exported)) == declared
