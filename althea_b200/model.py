@@ -402,9 +402,14 @@ def load_gltf(path: str, max_texture_size: Optional[int] = None) -> List[Primiti
                 pos = _accessor(gltf, buffers, at["POSITION"]).astype(np.float32)
                 nrm = _accessor(gltf, buffers, at["NORMAL"]).astype(np.float32) if "NORMAL" in at else None
                 tan4 = _accessor(gltf, buffers, at["TANGENT"]).astype(np.float32) if "TANGENT" in at else None
-                uvs = [_accessor(gltf, buffers, at["TEXCOORD_%d" % k]).astype(np.float32) for k in range(4) if "TEXCOORD_%d" % k in at]
+                uvs = []  # Primitive.cpp:126-134: the sets stop at the first missing TEXCOORD_i (no compaction past a gap)
+                for k in range(4):
+                    if "TEXCOORD_%d" % k not in at:
+                        break
+                    uvs.append(_accessor(gltf, buffers, at["TEXCOORD_%d" % k]).astype(np.float32))
                 idx = _accessor(gltf, buffers, prim["indices"]).reshape(-1).astype(np.uint32) if "indices" in prim else np.arange(len(pos), dtype=np.uint32)
                 mat = material(prim.get("material"))
+                had_normals = nrm is not None
                 duplicate = nrm is None or tan4 is None  # Primitive.cpp:147: flat normals / generated tangents need unshared vertices
                 idx = idx[: len(idx) // 3 * 3]
                 src_index = idx.copy() if duplicate else None
@@ -419,9 +424,12 @@ def load_gltf(path: str, max_texture_size: Optional[int] = None) -> List[Primiti
                         nuv = int((gltf["materials"][prim["material"]].get("normalTexture") or {}).get("texCoord", 0)) if "material" in prim else 0
                         uvn = uvs[nuv] if len(uvs) > nuv else np.zeros((len(pos), 2), np.float32)
                         tang, bit = compute_tangent_space(pos, nrm, uvn)
-                    else:
+                    elif had_normals:
                         tang = tan4[:, :3]
                         bit = tan4[:, 3:4] * np.cross(nrm, tang)
+                    else:  # TANGENT without NORMAL: Primitive.cpp:336-345 reads tangents only inside `if (hasNormals)`, and
+                        tang = np.zeros_like(pos)  # :189 generates none either: both stay zero-initialised
+                        bit = np.zeros_like(pos)
                 else:
                     tang = tan4[:, :3]
                     bit = tan4[:, 3:4] * np.cross(nrm, tang)  # Primitive.cpp:341-343
@@ -429,10 +437,16 @@ def load_gltf(path: str, max_texture_size: Optional[int] = None) -> List[Primiti
                 v[:, 0:3], v[:, 3:6], v[:, 6:9], v[:, 9:12] = pos, tang, bit, nrm
                 for k, u in enumerate(uvs[:4]):
                     v[:, 12 + 2 * k: 14 + 2 * k] = u
-                prim_world = world.astype(np.float32)
+                # Model.cpp:349: the matrix a primitive is drawn with is global * inverseBindPose of ITS node (identity unless the node is
+                # also a joint of some skin)
+                prim_world = node_matrix[node_idx] if node_matrix[node_idx] is not None else world.astype(np.float32)
                 if "JOINTS_0" in at and "WEIGHTS_0" in at and "skin" in node:  # Primitive.cpp:320: isSkinned
                     joints = _accessor(gltf, buffers, at["JOINTS_0"])
-                    weights = _accessor(gltf, buffers, at["WEIGHTS_0"]).astype(np.float32)  # u8 / u16 weights arrive normalised
+                    wacc = gltf["accessors"][at["WEIGHTS_0"]]
+                    weights = _accessor(gltf, buffers, at["WEIGHTS_0"]).astype(np.float32)
+                    if wacc["componentType"] in (5121, 5123) and not wacc.get("normalized"):
+                        # Primitive.cpp:354-359 divides u8 / u16 weights by 255 / 65535 whether or not the accessor says `normalized`
+                        weights = weights / np.float32(255.0 if wacc["componentType"] == 5121 else 65535.0)
                     if src_index is not None:
                         joints, weights = joints[src_index], weights[src_index]
                     v[:, 20:24] = weights

@@ -987,3 +987,75 @@ def test_gpu_translucent_layers_blend_like_the_restatement(ctx_fast, oracle):
         _compare_gbuffer(got, want)
     mixed = oracle.draw_gbuffer(proj, view, [back, front], W, H)
     assert ((mixed["albedo"][..., 0] > 0) & (mixed["albedo"][..., 1] > 0)).any()  # red showing through green somewhere
+
+
+def _write_gltf_json(path, attrs_arrays, extra=None, idx=None):
+    """A .gltf with one embedded base64 buffer: attrs_arrays = {name: (array, componentType, type)}."""
+    import base64
+    import json
+    blob, views, accessors, attrs = b"", [], [], {}
+    for name, (arr, ctype, typ) in attrs_arrays.items():
+        data = np.ascontiguousarray(arr).tobytes()
+        views.append({"buffer": 0, "byteOffset": len(blob), "byteLength": len(data)})
+        blob += data + b"\0" * ((-len(data)) % 4)
+        accessors.append({"bufferView": len(views) - 1, "componentType": ctype, "count": len(arr), "type": typ})
+        attrs[name] = len(accessors) - 1
+    prim = {"attributes": {k: v for k, v in attrs.items() if k != "_indices" and k != "_ibm"}}
+    if "_indices" in attrs:
+        prim["indices"] = attrs["_indices"]
+    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}], "meshes": [{"primitives": [prim]}],
+         "bufferViews": views, "accessors": accessors,
+         "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}]}
+    if extra:
+        extra(g, attrs)
+    with open(path, "w") as f:
+        json.dump(g, f)
+
+
+def test_loader_edge_cases_follow_primitive_cpp(tmp_path):
+    """Four corners where a tidy loader and Src/Primitive.cpp disagree; the loader follows the reference:
+    TEXCOORD sets stop at the first missing index (:126-134); TANGENT without NORMAL leaves tangent and bitangent zero (:336-345);
+    u8 / u16 WEIGHTS_0 are divided by 255 / 65535 whatever the accessor's `normalized` says (:354-359); a primitive is drawn with
+    global * inverseBindPose of its own node (Model.cpp:349)."""
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    uv0 = np.array([[0, 0], [1, 0], [0, 1]], np.float32)
+    uv2 = uv0 + 5.0
+    tan = np.tile(np.array([[1, 0, 0, 1]], np.float32), (3, 1))
+    path = str(tmp_path / "gap.gltf")
+    _write_gltf_json(path, {"POSITION": (pos, 5126, "VEC3"), "TANGENT": (tan, 5126, "VEC4"), "TEXCOORD_0": (uv0, 5126, "VEC2"),
+                            "TEXCOORD_2": (uv2, 5126, "VEC2")})
+    (p,) = model.load_gltf(path)
+    v = p.vertices
+    assert np.array_equal(v[:, 12:14], uv0) and not v[:, 14:20].any()          # set 2 is behind a gap: not loaded, not moved to slot 1
+    assert np.allclose(v[:, 9:12], [0, 0, 1]) and not v[:, 3:9].any()          # flat normal generated; tangent frame left at zero
+    # skinned: one joint translated by (1, 0, 0), u8 weights (255, 0, 0, 0) WITHOUT the normalized flag
+    nrm = np.tile(np.array([[0, 0, 1]], np.float32), (3, 1))
+    joints = np.zeros((3, 4), np.uint8)
+    weights = np.tile(np.array([[255, 0, 0, 0]], np.uint8), (3, 1))
+    ibm = np.eye(4, dtype=np.float32).reshape(1, 16)
+
+    def skin(g, attrs):
+        g["nodes"] = [{"mesh": 0, "skin": 0}, {"translation": [1.0, 0.0, 0.0]}]
+        g["scenes"][0]["nodes"] = [0, 1]
+        g["skins"] = [{"joints": [1], "inverseBindMatrices": attrs["_ibm"]}]
+
+    path = str(tmp_path / "skin.gltf")
+    _write_gltf_json(path, {"POSITION": (pos, 5126, "VEC3"), "NORMAL": (nrm, 5126, "VEC3"), "TANGENT": (tan, 5126, "VEC4"), "TEXCOORD_0": (uv0, 5126, "VEC2"),
+                            "JOINTS_0": (joints, 5121, "VEC4"), "WEIGHTS_0": (weights, 5121, "VEC4"), "_ibm": (ibm, 5126, "MAT4")}, extra=skin)
+    (p,) = model.load_gltf(path)
+    assert np.allclose(p.vertices[:, 0:3], pos + [1, 0, 0])                    # weight 1, not 255
+    assert np.allclose(p.vertices[:, 20:24], [1, 0, 0, 0])
+    # a mesh on a node that is itself a joint with a non-identity inverse bind pose: drawn with global * inverseBind
+    ibm2 = np.eye(4, dtype=np.float32)
+    ibm2[3, 0] = -3.0  # column-major storage: translation by (-3, 0, 0)
+
+    def joint_mesh(g, attrs):
+        g["nodes"] = [{"mesh": 0, "translation": [1.0, 2.0, 0.0]}, {"skin": 0}]
+        g["scenes"][0]["nodes"] = [0, 1]
+        g["skins"] = [{"joints": [0], "inverseBindMatrices": attrs["_ibm"]}]
+
+    path = str(tmp_path / "jointmesh.gltf")
+    _write_gltf_json(path, {"POSITION": (pos, 5126, "VEC3"), "NORMAL": (nrm, 5126, "VEC3"), "TANGENT": (tan, 5126, "VEC4"), "_ibm": (ibm2.reshape(1, 16), 5126, "MAT4")},
+                     extra=joint_mesh)
+    (p,) = model.load_gltf(path)
+    assert np.allclose(p.model[:3, 3], [1.0 - 3.0, 2.0, 0.0])
