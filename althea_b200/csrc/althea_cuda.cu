@@ -203,6 +203,27 @@ int endWork(althea_cuda_ctx* ctx, const althea_sync* sync, cudaStream_t stream) 
   return ALTHEA_OK;
 }
 
+// A stage that fails AFTER beginWork has enqueued the wait still signals its semaphore when it returns: the host's timeline must
+// not be left waiting for a value that never arrives (the status and message of the failure are what the caller gets).
+struct WorkGuard {
+  althea_cuda_ctx* ctx;
+  const althea_sync* sync;
+  cudaStream_t stream;
+  bool armed;
+  WorkGuard(althea_cuda_ctx* c, const althea_sync* s, cudaStream_t st) : ctx(c), sync(s), stream(st), armed(true) {}
+  int finish() { armed = false; return endWork(ctx, sync, stream); }
+  ~WorkGuard() {
+    if (!armed || !sync || !sync->signal_sem) return;
+    if (Resource* s = find(ctx, sync->signal_sem, ResKind::Semaphore)) {
+      cudaExternalSemaphoreSignalParams sp;
+      memset(&sp, 0, sizeof sp);
+      sp.params.fence.value = sync->signal_value;
+      cudaSignalExternalSemaphoresAsync(&s->extSem, &sp, 1, stream);
+      cudaGetLastError();
+    }
+  }
+};
+
 cudaEvent_t takeEvent(althea_cuda_ctx* ctx) {
   if (!ctx->eventPool.empty()) {
     cudaEvent_t e = ctx->eventPool.back();
@@ -1303,6 +1324,7 @@ int althea_cuda_draw_gbuffer(althea_cuda_ctx* ctx, const althea_global_uniforms*
   if ((rc = rasterScratch(ctx, &R))) return rc;
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  WorkGuard work(ctx, sync, stream);
   RasterJob J;
   memset(&J, 0, sizeof J);
   if ((rc = buildPrims(ctx, R, primitives, primitive_count, stream, &J.triTotal))) return rc;
@@ -1361,7 +1383,7 @@ int althea_cuda_draw_gbuffer(althea_cuda_ctx* ctx, const althea_global_uniforms*
       if ((rc = rasterOverflow(ctx, R, stream, &again, &open))) return rc;
     }
   }
-  return endWork(ctx, sync, stream);
+  return work.finish();
 }
 
 int althea_cuda_draw_shadow_cubes(althea_cuda_ctx* ctx, uint64_t lights_buf, uint32_t light_count, const althea_point_light_constants* constants,
@@ -1381,6 +1403,7 @@ int althea_cuda_draw_shadow_cubes(althea_cuda_ctx* ctx, uint64_t lights_buf, uin
   if ((rc = rasterScratch(ctx, &R))) return rc;
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
+  WorkGuard work(ctx, sync, stream);
   std::vector<althea_point_light> lights(light_count);
   if (light_count) {
     CUDA_TRY(ctx, cudaMemcpyAsync(lights.data(), lb->dptr, light_count * sizeof(althea_point_light), cudaMemcpyDeviceToHost, stream));
@@ -1448,6 +1471,6 @@ int althea_cuda_draw_shadow_cubes(althea_cuda_ctx* ctx, uint64_t lights_buf, uin
     if (!again) break;
     if (attempt >= 2) return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "raster lists overflowed three times");
   }
-  return endWork(ctx, sync, stream);
+  return work.finish();
 }
 } // extern "C"

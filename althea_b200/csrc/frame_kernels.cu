@@ -198,7 +198,7 @@ constexpr float kTiny = 1e-15f; // decisions on |value| <= kTiny are always re-e
 __global__ void __launch_bounds__(256) ssr_depth_pad_kernel(const __grid_constant__ FrameParams P) {
   const int qx = blockIdx.x * 32 + (threadIdx.x & 31);
   const int qy = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (qx == 0 && qy == 0 && P.ssrHitCount) *P.ssrHitCount = 0u; // the hit list ssr_capture_kernel (next in the stream) appends to
+  if (qx == 0 && qy == 0 && P.ssrHitCount) { P.ssrHitCount[0] = 0u; P.ssrHitCount[1] = 0u; } // the hit list the march (next in the stream) appends to, and its chunk counter
   if (qx > P.W + 1 || qy > P.H + 1) return;
   const float d = __ldg(rowPtr<float>(P.depth, AddrClamp::wrap(qy - 1, P.H)) + AddrClamp::wrap(qx - 1, P.W));
   const_cast<float*>(P.depthPad)[(size_t)qy * P.depthPadRow + qx] = d;
@@ -231,6 +231,93 @@ ADEV V4 environmentLitSample(const FrameParams& P, V3 currentPos, float u, float
   V3 m = pbrMaterial(P, currentPos, rd, normal, baseColor, reflectedColor, irradianceColor, mro.x, mro.y, 1.0f);
   return mk4(m.x, m.y, m.z, 1.0f);
 }
+
+#ifndef ALTHEA_PARITY
+// ---- fast build: the march of raymarchGBuffer (SSR.frag:97-130) with its per-step algebra folded ---------------------------
+// The fast build's contract is the 0.1 % hit-mask bar, not the op order:
+//  * reconstructPosition's matrix products are affine in (cu, cv): wd = W0 + Wu cu + Wv cv, dot(wd, zAxis) = S0 + Su cu + Sv cv
+//    (FrameParams::ssr*, folded on the host), and along the march (cu, cv) = (u, v) + i step, so both are affine in the step
+//    number. pos - worldPos = (cam - worldPos) + wd k, k = far near / den, den = (dRaw (far - near) - far) dot(wd, zAxis);
+//  * dir = normalize(pos - worldPos) is never formed, and neither is k: the sign test of SSR.frag:118 only needs the sign of
+//    projection = cP + k aP(i), and projection * den = cP den + far near aP(i) has that sign times sign(den), which does not
+//    change along a ray (the first factor of den is negative for every depth in [0, 1], the second is the view-space z of the
+//    texel's direction). One step is the bilinear depth tap, den, one FFMA and one product against the previous step's value;
+//    the reciprocal, `dot(dir, rayDir) > 0.999` and the normal test run on the steps that flip (a handful per ray);
+//  * the tap's footprint comes out of the mantissa of cu W + (1.5 * 2^23 - 1): no F2I / I2F round trip (quarter-rate on sm_100);
+//    a tap exactly on a texel centre may take the footprint to its left with weight 1, the same value;
+//  * the ray leaves [0, 1]^2 at a step number known to within a fraction of a step when it starts: the per-step test is one
+//    compare against that number minus two, the exact outside01 test of SSR.frag:106 runs on the last steps only.
+struct SsrRayFast {
+  float cu, cv, stepX, stepY;
+  float fi, fSafe;       // steps taken so far; steps <= fSafe are inside the screen and below the 128-step cap for certain
+  float S0, dS;          // dot(wd, zAxis) at step fi: S0 + fi dS
+  float cP, aP0, daP;    // projection * den = cP den + aP0 + fi daP  (far near folded into aP)
+  float prev;            // that value at the previous step; NaN before the first (`i > 0`, SSR.frag:118: NaN <= 0 is false)
+};
+constexpr float kFloorMagic = 12582912.0f; // 1.5 * 2^23: floats in [2^23, 2^24) are integers, their low mantissa bits the value
+ADEV bool ssrRayFastSetup(const FrameParams& P, float u, float v, V3 worldPos, V3 rayDir, V3 perpRef, float stepX, float stepY, float dl, SsrRayFast& M) {
+  // a ray whose end point projects to the pixel itself, to infinity or to NaN has NaN steps in the restatement: no tap of it can hit
+  if (!(dl > 0.0f && dl < __int_as_float(0x7f800000))) return false;
+  const V3 camMinusPos = mk3(P.g.inverseView[12], P.g.inverseView[13], P.g.inverseView[14]) - worldPos;
+  const V3 W0 = mk3(P.ssrW0[0], P.ssrW0[1], P.ssrW0[2]), Wu = mk3(P.ssrWu[0], P.ssrWu[1], P.ssrWu[2]), Wv = mk3(P.ssrWv[0], P.ssrWv[1], P.ssrWv[2]);
+  const V3 dW = mk3(fmaf(Wu.x, stepX, Wv.x * stepY), fmaf(Wu.y, stepX, Wv.y * stepY), fmaf(Wu.z, stepX, Wv.z * stepY));
+  const V3 Wat = mk3(fmaf(Wu.x, u, fmaf(Wv.x, v, W0.x)), fmaf(Wu.y, u, fmaf(Wv.y, v, W0.y)), fmaf(Wu.z, u, fmaf(Wv.z, v, W0.z)));
+  M.cu = u; M.cv = v; M.stepX = stepX; M.stepY = stepY;
+  M.fi = 0.0f;
+  // steps to the border the ray heads for (iterated fp32 sums drift by < 1e-5 of [0, 1] in 128 steps: a thousandth of a step)
+  const float tX = (stepX > 0.0f ? 1.0f - u : u) / fabsf(stepX), tY = (stepY > 0.0f ? 1.0f - v : v) / fabsf(stepY);
+  M.fSafe = fminf(fminf(tX, tY) - 2.0f, 128.0f);
+  M.S0 = fmaf(P.ssrS[1], u, fmaf(P.ssrS[2], v, P.ssrS[0]));
+  M.dS = fmaf(P.ssrS[1], stepX, P.ssrS[2] * stepY);
+  M.cP = dot3(camMinusPos, perpRef);
+  M.aP0 = (1000.0f * 0.01f) * dot3(Wat, perpRef);
+  M.daP = (1000.0f * 0.01f) * dot3(dW, perpRef);
+  M.prev = __int_as_float(0x7fc00000);
+  return true;
+}
+// one step of the march: 0 = go on, 1 = the ray left the screen or took its 128 steps, 2 = hit (hitPos, hitNormal; M.cu, M.cv the tap)
+ADEV int ssrRayFastStep(const FrameParams& P, SsrRayFast& M, V3 worldPos, V3 rayDir, V3& hitPos, V3& hitNormal) {
+  M.cu += M.stepX;
+  M.cv += M.stepY;
+  M.fi += 1.0f;
+  if (M.fi > M.fSafe) {
+    if (M.fi > 128.0f || outside01(M.cu, M.cv)) return 1;
+  }
+  // bilinear depth tap, CLAMP_TO_EDGE (rule A1/A2) from the padded copy; a + t (b - a) lerps
+  const float mx = fmaf(M.cu, P.Wf, kFloorMagic - 1.0f), my = fmaf(M.cv, P.Hf, kFloorMagic - 1.0f); // round(x - 0.5) + magic, x = cu W - 0.5
+  const float fx = fmaf(M.cu, P.Wf, -0.5f) - (mx - kFloorMagic), fy = fmaf(M.cv, P.Hf, -0.5f) - (my - kFloorMagic);
+  const int ix = __float_as_int(mx) - 0x4b400000, iy = __float_as_int(my) - 0x4b400000; // in [-1, W-1] x [-1, H-1]
+  const float* r0 = P.depthPadOrigin + (iy * P.depthPadRow + ix);
+  const float* r1 = r0 + P.depthPadRow;
+  const float t00 = __ldg(r0), t10 = __ldg(r0 + 1), t01 = __ldg(r1), t11 = __ldg(r1 + 1);
+  const float top = fmaf(t10 - t00, fx, t00), bot = fmaf(t11 - t01, fx, t01);
+  const float dRaw = fmaf(bot - top, fy, top);
+  const float den = fmaf(dRaw, 1000.0f - 0.01f, -1000.0f) * fmaf(M.fi, M.dS, M.S0);
+  const float projDen = fmaf(M.cP, den, fmaf(M.fi, M.daP, M.aP0));
+  const bool flips = projDen * M.prev <= 0.0f;
+  M.prev = projDen;
+  if (flips) {
+    // pos - worldPos = (cam - worldPos) + wd * (far near / den)
+    const float k = (1000.0f * 0.01f) * rcpf(den);
+    const V3 camMinusPos = mk3(P.g.inverseView[12], P.g.inverseView[13], P.g.inverseView[14]) - worldPos;
+    const V3 wd = mk3(fmaf(P.ssrWu[0], M.cu, fmaf(P.ssrWv[0], M.cv, P.ssrW0[0])), fmaf(P.ssrWu[1], M.cu, fmaf(P.ssrWv[1], M.cv, P.ssrW0[1])),
+                      fmaf(P.ssrWu[2], M.cu, fmaf(P.ssrWv[2], M.cv, P.ssrW0[2])));
+    const V3 vv = mk3(fmaf(wd.x, k, camMinusPos.x), fmaf(wd.y, k, camMinusPos.y), fmaf(wd.z, k, camMinusPos.z));
+    // dot(dir, rayDir) > 0.999  <=>  dot(vv, rayDir) > 0 and dot(vv, rayDir)^2 > 0.999^2 |vv|^2. A tap exactly AT worldPos (where the
+    // restatement's normalize(0) is NaN) fails `along > 0` here too; only the step after it could differ, on nothing we render.
+    const float along = dot3(vv, rayDir);
+    if (along > 0.0f && along * along > (0.999f * 0.999f) * dot3(vv, vv)) {
+      const V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, M.cu, M.cv)));
+      if (dot3(currentNormal, rayDir) < 0.0f) {
+        hitPos = worldPos + vv;
+        hitNormal = currentNormal;
+        return 2;
+      }
+    }
+  }
+  return 0;
+}
+#endif
 
 #ifndef ALTHEA_SSR_MIN_BLOCKS
 #define ALTHEA_SSR_MIN_BLOCKS 4 // 64 registers: the march is latency-bound, a fourth resident CTA is worth more than the registers
@@ -266,10 +353,6 @@ __global__ void __launch_bounds__(256, ALTHEA_SSR_MARCH_MIN_BLOCKS) ssr_capture_
     float cu = u, cv = v;
 #ifdef ALTHEA_PARITY
     float prevProjection = 0.0f;
-#else
-    float prevProjection = __int_as_float(0x7fc00000);
-#endif
-#ifdef ALTHEA_PARITY
     for (int i = 0; i < 128; ++i) {
       cu += stepX;
       cv += stepY;
@@ -290,56 +373,14 @@ __global__ void __launch_bounds__(256, ALTHEA_SSR_MARCH_MIN_BLOCKS) ssr_capture_
       prevProjection = currentProjection;
     }
 #else
-    // Same march with the per-step algebra folded (the fast build's contract is the 0.1 % mask bar, not op order):
-    //  * reconstructPosition's matrix products are affine in (cu, cv): wd = W0 + Wu cu + Wv cv, dot(wd, zAxis) = S0 + Su cu +
-    //    Sv cv, precomputed on the host (FrameParams::ssr*), and its two divisions become one reciprocal;
-    //  * dir = normalize(pos - worldPos) is never formed: sign(dot(dir, perpRef)) = sign(dot(v, perpRef)) and
-    //    dot(dir, rayDir) > 0.999  <=>  dot(v, rayDir) > 0 and dot(v, rayDir)^2 > 0.999^2 |v|^2.
-    const V3 camMinusPos = mk3(P.g.inverseView[12], P.g.inverseView[13], P.g.inverseView[14]) - worldPos;
-    const V3 W0 = mk3(P.ssrW0[0], P.ssrW0[1], P.ssrW0[2]), Wu = mk3(P.ssrWu[0], P.ssrWu[1], P.ssrWu[2]), Wv = mk3(P.ssrWv[0], P.ssrWv[1], P.ssrWv[2]);
-    //  * along the march (cu, cv) = (u, v) + (i + 1) step, so wd and dot(wd, zAxis) are affine in the step number, and so are
-    //    dot(wd, rayDir) and dot(wd, perpRef): the two tests of a step need  along = cR + k aR(i),  projection = cP + k aP(i)
-    //    with k the reciprocal above: seven arithmetic instructions instead of the twenty-two of forming wd, vv and two dot
-    //    products. The vector itself is only built on the rare step that passes both sign tests.
-    const V3 dW = mk3(fmaf(Wu.x, stepX, Wv.x * stepY), fmaf(Wu.y, stepX, Wv.y * stepY), fmaf(Wu.z, stepX, Wv.z * stepY));
-    const V3 Wat = mk3(fmaf(Wu.x, u, fmaf(Wv.x, v, W0.x)), fmaf(Wu.y, u, fmaf(Wv.y, v, W0.y)), fmaf(Wu.z, u, fmaf(Wv.z, v, W0.z)));
-    const float aR0 = dot3(Wat, rayDir), daR = dot3(dW, rayDir), aP0 = dot3(Wat, perpRef), daP = dot3(dW, perpRef);
-    const float cR = dot3(camMinusPos, rayDir), cP = dot3(camMinusPos, perpRef);
-    const float S0 = fmaf(P.ssrS[1], u, fmaf(P.ssrS[2], v, P.ssrS[0])), dS = fmaf(P.ssrS[1], stepX, P.ssrS[2] * stepY);
-    // |vv|^2 = |cam - pos|^2 + 2 k dot(cam - pos, wd) + k^2 |wd|^2 with dot(cam - pos, wd) affine and |wd|^2 quadratic in the step
-    const float cc = dot3(camMinusPos, camMinusPos), cw0 = 2.0f * dot3(camMinusPos, Wat), dcw = 2.0f * dot3(camMinusPos, dW);
-    const float ww0 = dot3(Wat, Wat), ww1 = 2.0f * dot3(Wat, dW), ww2 = dot3(dW, dW);
-    float fi = 0.0f;
-    for (int i = 0; i < 128; ++i) {
-      cu += stepX;
-      cv += stepY;
-      fi += 1.0f;
-      if (outside01(cu, cv)) break;
-      // bilinear depth tap, CLAMP_TO_EDGE (rule A1/A2) from the padded copy; a + t (b - a) lerps
-      const DepthTap q = depthTapPadded(P, cu, cv);
-      const float top = fmaf(q.t10 - q.t00, q.fx, q.t00), bot = fmaf(q.t11 - q.t01, q.fx, q.t01);
-      const float dRaw = fmaf(bot - top, q.fy, top);
-      // pos - worldPos = (cam - worldPos) + wd * (far near / ((dRaw (far - near) - far) * dot(wd, zAxis)))
-      const float den = fmaf(dRaw, 1000.0f - 0.01f, -1000.0f) * fmaf(fi, dS, S0);
-      const float k = (1000.0f * 0.01f) * rcpf(den);
-      const float along = fmaf(k, fmaf(fi, daR, aR0), cR);
-      const float currentProjection = fmaf(k, fmaf(fi, daP, aP0), cP);
-      // i > 0 is carried by prevProjection's NaN start value (NaN <= 0 is false). A tap exactly AT worldPos (where the
-      // restatement's normalize(0) is NaN) fails `along > 0` here too; only the step after it could differ, on nothing we render.
-      if (currentProjection * prevProjection <= 0.0f && along > 0.0f) {
-        const float len2 = fmaf(k, fmaf(k, fmaf(fi, fmaf(fi, ww2, ww1), ww0), fmaf(fi, dcw, cw0)), cc);
-        if (along * along > (0.999f * 0.999f) * len2) {
-          V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, cu, cv)));
-          if (dot3(currentNormal, rayDir) < 0.0f) {
-            const V3 wd = mk3(fmaf(Wu.x, cu, fmaf(Wv.x, cv, W0.x)), fmaf(Wu.y, cu, fmaf(Wv.y, cv, W0.y)), fmaf(Wu.z, cu, fmaf(Wv.z, cv, W0.z)));
-            const V3 vv = mk3(fmaf(wd.x, k, camMinusPos.x), fmaf(wd.y, k, camMinusPos.y), fmaf(wd.z, k, camMinusPos.z));
-            hit = true; hitPos = worldPos + vv; hitNormal = currentNormal;
-            break;
-          }
-        }
+    SsrRayFast M;
+    if (ssrRayFastSetup(P, u, v, worldPos, rayDir, perpRef, stepX, stepY, dl, M)) {
+      for (;;) {
+        const int r = ssrRayFastStep(P, M, worldPos, rayDir, hitPos, hitNormal);
+        if (r) { hit = r == 2; break; }
       }
-      prevProjection = currentProjection;
     }
+    cu = M.cu; cv = M.cv;
 #endif
     hcu = cu; hcv = cv; hitRay = rayDir;
   }
@@ -363,6 +404,118 @@ __global__ void __launch_bounds__(256, ALTHEA_SSR_MARCH_MIN_BLOCKS) ssr_capture_
     }
   }
 }
+
+#ifndef ALTHEA_PARITY
+// ---- fast build: the same march on persistent warps whose idle lanes are refilled (warp ballots) ----------------------------
+// The march of a pixel ends after 1 .. 128 steps (hit, screen border, sky pixels never start): with one pixel per thread a warp
+// iterates as long as its slowest lane and the lanes that finished ride along. Here every warp pulls pixels from a queue: chunks
+// of 16 x 8 pixels in tile order from one global counter, one pixel per idle lane, whenever a ballot shows at least
+// kSsrRefillIdle lanes idle (the setup of a pixel runs with only the refilled lanes active: worth batching). A lane that hits parks
+// its record in the warp's shared-memory slots; parked hits are appended to the hit list with one atomic per warp at the next refill.
+// Pixels that do not hit are not written at all: the launcher clears the rows first (the blend-on-write over the clear,
+// GraphicsPipeline.cpp:138-154, leaves (0, 0, 0, 0) there).
+#ifndef ALTHEA_SSR_REFILL
+#define ALTHEA_SSR_REFILL 0
+#endif
+#ifndef ALTHEA_SSR_REFILL_IDLE
+#define ALTHEA_SSR_REFILL_IDLE 8
+#endif
+constexpr int kSsrRefillIdle = ALTHEA_SSR_REFILL_IDLE;
+constexpr int kSsrChunkW = 16, kSsrChunkH = 8, kSsrChunk = kSsrChunkW * kSsrChunkH;
+__global__ void __launch_bounds__(256, ALTHEA_SSR_MARCH_MIN_BLOCKS) ssr_capture_refill_kernel(const __grid_constant__ FrameParams P) {
+  __shared__ float parked[8][11][32]; // per warp and lane: cu, cv, hitPos, hitNormal, rayDir of a hit waiting for the next append
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned ltMask = (1u << lane) - 1u;
+  float (*park)[32] = parked[warp];
+  const int chunksX = (P.W + kSsrChunkW - 1) / kSsrChunkW;
+  const int chunks = chunksX * ((P.y1 - P.y0 + kSsrChunkH - 1) / kSsrChunkH);
+  unsigned* const chunkCounter = P.ssrHitCount + 1; // zeroed with the hit count by ssr_depth_pad_kernel
+  int next = 0, end = 0; // pixels [next, end) of the warp's current chunk are still to be handed out (warp-uniform)
+  int chunkX = 0, chunkY = 0;
+  bool exhausted = false;
+  bool active = false, hitParked = false;
+  int pixel = 0; // x | y << 16 of the lane's current (or parked) pixel
+  SsrRayFast M;
+  V3 worldPos = mk3(0.0f, 0.0f, 0.0f), rayDir = worldPos;
+  for (;;) {
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (__popc(act) <= 32 - kSsrRefillIdle && !exhausted || act == 0u) {
+      // ---- parked hits first: one atomic for the warp, every parked lane writes its own record
+      const unsigned hits = __ballot_sync(0xffffffffu, hitParked);
+      if (hits) {
+        const int leader = __ffs(hits) - 1;
+        unsigned base = 0u;
+        if (lane == leader) base = atomicAdd(P.ssrHitCount, (unsigned)__popc(hits));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (hitParked) {
+          float* r = P.ssrHits + (base + __popc(hits & ltMask));
+          const unsigned cap = P.ssrHitCap;
+          r[0] = __int_as_float(pixel);
+#pragma unroll
+          for (int k = 0; k < 11; ++k) r[(k + 1) * cap] = park[k][lane];
+          hitParked = false;
+        }
+      }
+      if (exhausted) {
+        if (act == 0u) break;
+      } else {
+        if (next >= end) { // the warp's next chunk
+          unsigned c = 0u;
+          if (lane == 0) c = atomicAdd(chunkCounter, 1u);
+          c = __shfl_sync(0xffffffffu, c, 0);
+          if (c >= (unsigned)chunks) {
+            exhausted = true;
+            continue;
+          }
+          chunkX = (int)(c % (unsigned)chunksX) * kSsrChunkW;
+          chunkY = P.y0 + (int)(c / (unsigned)chunksX) * kSsrChunkH;
+          next = 0;
+          end = kSsrChunk;
+        }
+        const unsigned idle = ~act;
+        const int rank = __popc(idle & ltMask);
+        const int take = min(__popc(idle), end - next);
+        if (!active && rank < take) {
+          const int j = next + rank;
+          const int x = chunkX + (j & (kSsrChunkW - 1)), y = chunkY + (j / kSsrChunkW);
+          if (x < P.W && y < P.y1) {
+            const V4 normal4 = FmtRGBA16F::load(P.normal, x, y);
+            if (normal4.w != 0.0f) { // SSR.frag:136-141
+              const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
+              const float dOwn = __ldg(rowPtr<float>(P.depth, y) + x);
+              worldPos = reconstructPosition(P, u, v, dOwn);
+              const V3 normal = normalize3(xyz(normal4));
+              rayDir = reflect3(normalize3(viewDirection(P, u, v)), normal);
+              const V2 uvEnd = projectUv(P, worldPos + rayDir * 10000.0f); // raymarchGBuffer, SSR.frag:80-95
+              const float dx = uvEnd.x - u, dy = uvEnd.y - v;
+              const float dl = sqrtf(dx * dx + dy * dy);
+              const V3 perpRef = normalize3(cross3(cross3(rayDir, normal), rayDir));
+              pixel = x | (y << 16);
+              active = ssrRayFastSetup(P, u, v, worldPos, rayDir, perpRef, (dx / dl) * 0.005f, (dy / dl) * 0.005f, dl, M);
+            }
+          }
+        }
+        next += take;
+        continue; // vote again: the new pixels may be sky, the chunk may have ended before every idle lane had one
+      }
+    }
+    if (active) {
+      V3 hitPos, hitNormal;
+      const int r = ssrRayFastStep(P, M, worldPos, rayDir, hitPos, hitNormal);
+      if (r) {
+        active = false;
+        if (r == 2) {
+          hitParked = true;
+          park[0][lane] = M.cu; park[1][lane] = M.cv;
+          park[2][lane] = hitPos.x; park[3][lane] = hitPos.y; park[4][lane] = hitPos.z;
+          park[5][lane] = hitNormal.x; park[6][lane] = hitNormal.y; park[7][lane] = hitNormal.z;
+          park[8][lane] = rayDir.x; park[9][lane] = rayDir.y; park[10][lane] = rayDir.z;
+        }
+      }
+    }
+  }
+}
+#endif
 
 __global__ void __launch_bounds__(256) ssr_shade_hits_kernel(const __grid_constant__ FrameParams P) {
   const unsigned count = *P.ssrHitCount, cap = P.ssrHitCap;
@@ -1526,16 +1679,21 @@ constexpr int kFlipRing = 64; // flip items waiting per warp: at most 31 left ov
 #define ALTHEA_CULL_MIN_BLOCKS 4
 #endif
 template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLOCKS) ssao_cull_kernel(const __grid_constant__ FrameParams P) {
+  // Per-thread arrays are indexed [field][thread of the CTA]: a lane's own slot is one register (its thread index) plus a
+  // constant, another lane's slot is the warp's first thread + that lane: no per-warp base pointers to keep or rebuild.
   __shared__ __align__(128) float4 win[kPlaneWin * kPlaneWin];
   __shared__ uint16_t tapQueue[8][32 * 11];      // (lane, tap) of the current ray's undecided taps
-  __shared__ unsigned tapResult[8][32];          // per lane: bit i = tap i negative, bit 16 + i = tap i of class 0
-  __shared__ float flipRing[8][6][kFlipRing];    // tag, uvEnd, rayDir of the steps that change sign
-  __shared__ float rayState[8][8][32];           // the current ray of every lane: uvEnd, perpRef, rayDir (read across lanes)
-  __shared__ unsigned hitMask[8][32];
+  __shared__ unsigned tapResult[256];            // per lane: bit i = tap i negative, bit 16 + i = tap i of class 0
+  __shared__ float flipRing[6][8 * kFlipRing];   // tag, uvEnd, rayDir of the steps that change sign: field, then warp, then slot
+  __shared__ float rayState[8][256];             // the current ray of every lane: uvEnd, perpRef, rayDir (read across lanes)
+  __shared__ unsigned hitMask[256];
   __shared__ float redMin[8];
   __shared__ int badSum[8];
   __shared__ __align__(8) uint64_t bar;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wb = tid & ~31;           // the warp's first thread
+  const int fw = warp * kFlipRing;    // the warp's first flip slot
   const int tileX = blockIdx.x * 16, tileY = P.y0 + blockIdx.y * 16;
   const int x = tileX + (lane & 15), y = tileY + warp * 2 + (lane >> 4);
   const bool inside = x < P.W && y < P.y1;
@@ -1571,7 +1729,7 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
     const float4* src = P.ssaoPlanes[level] + ((long long)(wby + lane) * P.ssaoPlaneRow[level] + wbx);
     bulkCopyG2S(&win[lane * kPlaneWin], src, kPlaneWin * 16, &bar);
   }
-  hitMask[warp][lane] = 0u;
+  hitMask[tid] = 0u;
   mbarWait(&bar, 0);
   { // a neighbourhood that mostly cannot decide is marched by ssao_kernel instead: undecidable records among the blocks the
     // tile's rays can reach
@@ -1611,8 +1769,6 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
   const char* winBytes = reinterpret_cast<const char*>(win);
   const float xs0 = (float)x, ys0 = (float)y;
   uint16_t* tq = tapQueue[warp];
-  float (*fr)[kFlipRing] = flipRing[warp];
-  float (*rs)[32] = rayState[warp];
   int fhead = 0, ftail = 0; // FIFO of flip items, warp-uniform
   unsigned gathers = 0u, lookups = 0u, tapItems = 0u;
   // evaluates min(32, waiting) flip items, oldest first, one per lane
@@ -1620,27 +1776,29 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
     const int count = min(ftail - fhead, 32);
     const bool live = lane < count;
     const int e = (fhead + (live ? lane : 0)) & (kFlipRing - 1);
-    const unsigned tag = __float_as_uint(fr[0][e]); // lane | step << 5 | ray << 9 | exact << 14
+    const unsigned tag = __float_as_uint(flipRing[0][fw + e]); // lane | step << 5 | ray << 9 | exact << 14
     const int src = (int)(tag & 31u);
     const V3 sp = mk3(__shfl_sync(0xffffffffu, worldPos.x, src), __shfl_sync(0xffffffffu, worldPos.y, src), __shfl_sync(0xffffffffu, worldPos.z, src));
     const float su = __shfl_sync(0xffffffffu, u0, src), sv = __shfl_sync(0xffffffffu, v0, src);
     const V3 sn = mk3(__shfl_sync(0xffffffffu, normal.x, src), __shfl_sync(0xffffffffu, normal.y, src), __shfl_sync(0xffffffffu, normal.z, src));
     if (live) {
-      const V3 rd = mk3(fr[3][e], fr[4][e], fr[5][e]);
+      const V3 rd = mk3(flipRing[3][fw + e], flipRing[4][fw + e], flipRing[5][fw + e]);
       const bool exact = (tag >> 14) & 1u;
       // perpRef only enters the projections of a class-0 step (rare): rebuilt as ssaoRay builds it
       const V3 pr = exact ? perpRefOf(rd, sn) : rd;
-      if (ssaoFlipScores<COUNT>(P, su, sv, sp, rd, pr, fr[1][e], fr[2][e], (int)((tag >> 5) & 15u), exact, gathers)) atomicOr(&hitMask[warp][src], 1u << ((tag >> 9) & 31u));
+      if (ssaoFlipScores<COUNT>(P, su, sv, sp, rd, pr, flipRing[1][fw + e], flipRing[2][fw + e], (int)((tag >> 5) & 15u), exact, gathers)) atomicOr(&hitMask[wb + src], 1u << ((tag >> 9) & 31u));
     }
     fhead += count;
     __syncwarp();
   };
-  for (int ray = 0; ray < 24; ++ray) {
+  // a warp without a covered pixel has nothing to count (no block-wide barrier below this point)
+  const int rays = __any_sync(0xffffffffu, covered) ? 24 : 0;
+  for (int ray = 0; ray < rays; ++ray) {
     const SsaoRay R = ssaoRay(P, tbn, worldPos, normal, x, y, ray);
     const int n = covered ? ssaoTapCount(u0, v0, R.uvEnd) : 0;
-    rs[0][lane] = R.uvEnd.x; rs[1][lane] = R.uvEnd.y;
-    rs[2][lane] = R.perpRef.x; rs[3][lane] = R.perpRef.y; rs[4][lane] = R.perpRef.z;
-    rs[5][lane] = R.rayDir.x; rs[6][lane] = R.rayDir.y; rs[7][lane] = R.rayDir.z;
+    rayState[0][tid] = R.uvEnd.x; rayState[1][tid] = R.uvEnd.y;
+    rayState[2][tid] = R.perpRef.x; rayState[3][tid] = R.perpRef.y; rayState[4][tid] = R.perpRef.z;
+    rayState[5][tid] = R.rayDir.x; rayState[6][tid] = R.rayDir.y; rayState[7][tid] = R.rayDir.z;
     unsigned decMask = 0u, negMask = 0u;
     { // ray constants of the coarse test
       const V3 cam = mk3(P.ssaoCam[0], P.ssaoCam[1], P.ssaoCam[2]);
@@ -1686,12 +1844,21 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
         const bool clearedRec = rec.w < 0.0f;
         const float d = clearedRec ? dSky : fmaf(rec.y, tx, fmaf(rec.z, ty, rec.x)) - fmaf(fi, dL, L0);
         if (fabsf(d) > (clearedRec ? 0.0f : rec.w + rayConst)) decMask |= 1u << i;
-#else
-        const float d = fmaf(rec.y, tx, fmaf(rec.z, ty, rec.x)) - fmaf(fi, dL, L0);
-        if (fabsf(d) > rec.w + rayConst) decMask |= 1u << i;
-#endif
         if (d < 0.0f) negMask |= 1u << i;
+#else
+        // both masks are shifted in from the sign bits (one funnel shift each): tap i ends up at bit 11 - i. `decided` is
+        // |d| > rec.w + rayConst, i.e. (rec.w + rayConst) - |d| negative; +inf thresholds give +inf, never negative
+        const float d = fmaf(rec.y, tx, fmaf(rec.z, ty, rec.x)) - fmaf(fi, dL, L0);
+        decMask = __funnelshift_l(__float_as_uint((rec.w + rayConst) - fabsf(d)), decMask, 1);
+        negMask = __funnelshift_l(__float_as_uint(d), negMask, 1);
+#endif
       }
+#if !ALTHEA_CULL_SKY_CLASS
+      decMask = __brev(decMask) >> 20; // bit 11 - i -> bit i
+      negMask = __brev(negMask) >> 20;
+      // a NaN difference (only possible on a ray the records cannot answer for: c0 = 0, wild coordinates) has no sign to trust
+      if (!answerable) decMask = 0u;
+#endif
       if (c0 < 0.0f) negMask = ~negMask; // the projection is t c0 (w - L): its sign, not that of w - L
     }
     // taps 1 .. n - 1 take part in steps 2 .. n - 1 (none when n < 3)
@@ -1708,7 +1875,7 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
       if (tapMask && decMask == 0u) atomicAdd(P.gatherCounter + 4 + (level * 12) * 2, 1ull); // rays with no decided tap at all
     }
     // ---- the undecided taps of this ray, compacted over the warp and classified from the position records
-    tapResult[warp][lane] = 0u;
+    tapResult[tid] = 0u;
     const int cnt = __popc(undecided);
     int incl = cnt;
 #pragma unroll
@@ -1730,13 +1897,14 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
       const V3 sp = mk3(__shfl_sync(0xffffffffu, worldPos.x, src), __shfl_sync(0xffffffffu, worldPos.y, src), __shfl_sync(0xffffffffu, worldPos.z, src));
       const float su = __shfl_sync(0xffffffffu, u0, src), sv = __shfl_sync(0xffffffffu, v0, src);
       if (live) {
-        const int cls = ssaoTapClass<COUNT>(P, marchCoord(su, rs[0][src], i), marchCoord(sv, rs[1][src], i), sp, mk3(rs[2][src], rs[3][src], rs[4][src]), gathers);
-        if (cls <= 0) atomicOr(&tapResult[warp][src], cls < 0 ? 1u << i : 0x10000u << i);
+        const int cls = ssaoTapClass<COUNT>(P, marchCoord(su, rayState[0][wb + src], i), marchCoord(sv, rayState[1][wb + src], i), sp,
+                                            mk3(rayState[2][wb + src], rayState[3][wb + src], rayState[4][wb + src]), gathers);
+        if (cls <= 0) atomicOr(&tapResult[wb + src], cls < 0 ? 1u << i : 0x10000u << i);
       }
     }
     __syncwarp();
     // ---- steps whose taps differ in sign (or have a class-0 tap) go on the flip ring with what their evaluation needs
-    const unsigned res = tapResult[warp][lane];
+    const unsigned res = tapResult[tid];
     negMask |= res & 0xffffu;
     const unsigned zero = res >> 16;
     const unsigned stepMask = tapMask & ~2u; // steps 2 .. n - 1
@@ -1749,9 +1917,9 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
         const int bit = __ffs(flips) - 1;
         flips &= flips - 1u;
         const int e = (ftail + __popc(b & ((1u << lane) - 1u))) & (kFlipRing - 1);
-        fr[0][e] = __uint_as_float((unsigned)lane | ((unsigned)(bit & 15) << 5) | ((unsigned)ray << 9) | ((unsigned)(bit >> 4) << 14));
-        fr[1][e] = rs[0][lane]; fr[2][e] = rs[1][lane];
-        fr[3][e] = rs[5][lane]; fr[4][e] = rs[6][lane]; fr[5][e] = rs[7][lane];
+        flipRing[0][fw + e] = __uint_as_float((unsigned)lane | ((unsigned)(bit & 15) << 5) | ((unsigned)ray << 9) | ((unsigned)(bit >> 4) << 14));
+        flipRing[1][fw + e] = rayState[0][tid]; flipRing[2][fw + e] = rayState[1][tid];
+        flipRing[3][fw + e] = rayState[5][tid]; flipRing[4][fw + e] = rayState[6][tid]; flipRing[5][fw + e] = rayState[7][tid];
       }
       ftail += __popc(b);
       __syncwarp();
@@ -1760,7 +1928,7 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
   }
   while (ftail > fhead) drainFlips();
   __syncwarp();
-  if (inside) rowPtrW<uint8_t>(P.ao, y)[x] = covered ? (uint8_t)__popc(hitMask[warp][lane]) : (uint8_t)255;
+  if (inside) rowPtrW<uint8_t>(P.ao, y)[x] = covered ? (uint8_t)__popc(hitMask[tid]) : (uint8_t)255;
   if (COUNT) {
     atomicAdd(P.gatherCounter, (unsigned long long)(gathers & 0xffffu));
     atomicAdd(P.gatherCounter + 1, (unsigned long long)(gathers >> 16));
@@ -1829,8 +1997,19 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const __grid_consta
 static inline dim3 tileGrid(int w, int h) { return dim3((unsigned)((w + 15) / 16), (unsigned)((h + 15) / 16)); }
 
 void launch_ssr_capture(const FrameParams& P, cudaStream_t s) {
-  if (P.ssrPlanes) ssr_capture_skip_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P);
-  else ssr_capture_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P);
+  if (P.ssrPlanes) { ssr_capture_skip_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); return; }
+#if !defined(ALTHEA_PARITY) && ALTHEA_SSR_REFILL
+  if (P.ssrHits) { // persistent warps, idle lanes refilled: pixels without a hit keep the clear
+    cudaMemsetAsync(const_cast<char*>(static_cast<const char*>(P.refl.level[0].ptr)) + (size_t)P.y0 * P.refl.level[0].pitch, 0,
+                    (size_t)(P.y1 - P.y0) * P.refl.level[0].pitch, s);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    ssr_capture_refill_kernel<<<(unsigned)(sms * ALTHEA_SSR_MARCH_MIN_BLOCKS), 256, 0, s>>>(P);
+    return;
+  }
+#endif
+  ssr_capture_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P);
 }
 void launch_ssr_shade_hits(const FrameParams& P, cudaStream_t s) { ssr_shade_hits_kernel<<<148 * 8, 256, 0, s>>>(P); }
 void launch_ssr_planes(const FrameParams& P, cudaStream_t s) { ssr_planes_kernel<<<(kSsrPlaneStride * kSsrPlaneRows + 7) / 8, 256, 0, s>>>(P); }
