@@ -106,8 +106,18 @@ ADEV V3 pbrMaterial(const FrameParams& P, V3 worldPos, V3 V, V3 N, V3 baseColor,
     float4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
     V3 L = mk3(l0.x, l0.y, l0.z) - worldPos;
     float LdistSq = dot3(L, L);
+#ifdef ALTHEA_PARITY
     float Ldist = fsqrt(LdistSq);
     L = L / Ldist;
+#else
+    // a light behind the surface contributes (diffuse + specular) * radiance * max(dot(N, L), 0) = +0 (the specular term's
+    // geometry factor vanishes with NdotL, its denominator does not): no shadow lookup, no BRDF. Neighbouring pixels share
+    // their normals' side of a light, so warps skip together. One MUFU.RSQ serves the length and the normalisation.
+    if (!(dot3(N, L) > 0.0f)) continue;
+    const float invLdist = rsqrtf(LdistSq);
+    const float Ldist = LdistSq * invLdist;
+    L = L * invLdist;
+#endif
     if (P.shadowRes > 0) {
       float closestDepth = sampleShadowCube(P, mk3(L.x, -L.y, -L.z), i);
       closestDepth *= 1000.0f;
@@ -570,8 +580,13 @@ __global__ void __launch_bounds__(256) ssr_planes_kernel(const __grid_constant__
   const float alpha = recip(xc, yc) - (beta * (float)xc + gamma * (float)yc);
   float rlo = inf, rhi = -inf, wmax = 0.0f;
   bool ok = true;
+  // texel k = lane, lane + 32, ... of the nx x ny box, row by row: the (column, row) pair is stepped, not divided out
+  const int q32 = 32 / nx, r32 = 32 - q32 * nx;
+  int kx = lane % nx, ky = lane / nx;
   for (int k = lane; k < nx * ny; k += 32) {
-    const int x = xlo + k % nx, y = ylo + k / nx;
+    const int x = xlo + kx, y = ylo + ky;
+    kx += r32; ky += q32;
+    if (kx >= nx) { kx -= nx; ky += 1; }
     const float w = recip(x, y);
     const float res = w - fmaf(beta, (float)x, fmaf(gamma, (float)y, alpha));
     ok = ok && (w > 0.0f) && (res == res) && (w < inf);
@@ -961,14 +976,46 @@ ADEV uint32_t hiWord(float target, uint32_t lo) {
   return w;
 }
 
-__global__ void __launch_bounds__(256) ssao_quads_kernel(const __grid_constant__ FrameParams P) {
-  const int qx = blockIdx.x * 32 + (threadIdx.x & 31); // record column = ix + 1
-  const int qy = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (qx > P.W || qy > P.H) return;
-  const int i0 = AddrClamp::wrap(qx - 1, P.W), i1 = AddrClamp::wrap(qx, P.W);
-  const int j0 = AddrClamp::wrap(qy - 1, P.H), j1 = AddrClamp::wrap(qy, P.H);
-  const V4 p00 = FmtRGBA32F::load(P.position, i0, j0), p10 = FmtRGBA32F::load(P.position, i1, j0);
-  const V4 p01 = FmtRGBA32F::load(P.position, i0, j1), p11 = FmtRGBA32F::load(P.position, i1, j1);
+// position of texel (x, y) in mode D, exactly as reconstruct_position_kernel writes it (coordinates clamped to the image first)
+ADEV float4 reconstructedTexel(const FrameParams& P, int x, int y) {
+  x = AddrClamp::wrap(x, P.W);
+  y = AddrClamp::wrap(y, P.H);
+  float4 out = make_float4(0.0f, 0.0f, 0.0f, 0.0f); // the attachment's clear colour where nothing was drawn
+  const V4 normal4 = FmtRGBA16F::load(P.normal, x, y);
+  if (normal4.w != 0.0f) {
+    const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
+    const V3 p = reconstructPosition(P, u, v, __ldg(rowPtr<float>(P.depth, y) + x));
+    out = make_float4(p.x, p.y, p.z, 1.0f);
+  }
+  return out;
+}
+// RECON (mode D): the pass also IS reconstruct_position_kernel: every position is reconstructed from depth once per 32 x 8 block
+// (+ a one-texel apron) into a shared tile, written to the position scratch by the thread that owns it, and the footprint reads
+// its four corners from the tile: the 16 B/px the separate pass wrote are not read back from memory, and one launch goes.
+template <bool RECON> __global__ void __launch_bounds__(256) ssao_quads_kernel(const __grid_constant__ FrameParams P) {
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int qx = blockIdx.x * 32 + lane; // record column = ix + 1
+  const int qy = blockIdx.y * 8 + ty;
+  V4 p00, p10, p01, p11;
+  if (RECON) {
+    __shared__ float4 tile[9][33]; // texels [qx0 - 1, qx0 + 32) x [qy0 - 1, qy0 + 8) of the block
+    tile[ty + 1][lane + 1] = reconstructedTexel(P, qx, qy);
+    if (ty == 0) tile[0][lane + 1] = reconstructedTexel(P, qx, qy - 1);
+    if (lane == 0) tile[ty + 1][0] = reconstructedTexel(P, qx - 1, qy);
+    if (threadIdx.x == 0) tile[0][0] = reconstructedTexel(P, qx - 1, qy - 1);
+    __syncthreads();
+    if (qx > P.W || qy > P.H) return;
+    const float4 t11 = tile[ty + 1][lane + 1], t01 = tile[ty + 1][lane], t10 = tile[ty][lane + 1], t00 = tile[ty][lane];
+    p00 = mk4(t00.x, t00.y, t00.z, t00.w); p10 = mk4(t10.x, t10.y, t10.z, t10.w);
+    p01 = mk4(t01.x, t01.y, t01.z, t01.w); p11 = mk4(t11.x, t11.y, t11.z, t11.w);
+    if (qx < P.W && qy < P.H) rowPtrW<float4>(P.position, qy)[qx] = t11;
+  } else {
+    if (qx > P.W || qy > P.H) return;
+    const int i0 = AddrClamp::wrap(qx - 1, P.W), i1 = AddrClamp::wrap(qx, P.W);
+    const int j0 = AddrClamp::wrap(qy - 1, P.H), j1 = AddrClamp::wrap(qy, P.H);
+    p00 = FmtRGBA32F::load(P.position, i0, j0); p10 = FmtRGBA32F::load(P.position, i1, j0);
+    p01 = FmtRGBA32F::load(P.position, i0, j1); p11 = FmtRGBA32F::load(P.position, i1, j1);
+  }
   if (P.ssaoPlaneStats && qx == 0 && qy == 0) { P.ssaoPlaneStats[0] = 0u; P.ssaoPlaneStats[1] = 0u; P.ssaoTileList[0] = 0u; }
   if (P.ssaoRecip && qx < P.W && qy < P.H) { // this thread's p11 is texel (qx, qy): its reciprocal eye depth for ssao_planes_kernel
     const V3 cam = mk3(P.ssaoCam[0], P.ssaoCam[1], P.ssaoCam[2]);
@@ -1549,8 +1596,13 @@ template <bool COARSEST> __global__ void __launch_bounds__(256) ssao_planes_kern
   const float alpha = recip(xc, yc) - (beta * (float)xc + gamma * (float)yc);
   float rlo = inf, rhi = -inf, wmax = 0.0f;
   bool ok = true, cleared = true;
+  // texel k = lane, lane + 32, ... of the nx x ny box, row by row: the (column, row) pair is stepped, not divided out
+  const int q32 = 32 / nx, r32 = 32 - q32 * nx;
+  int kx = lane % nx, ky = lane / nx;
   for (int k = lane; k < nx * ny; k += 32) {
-    const int x = xlo + k % nx, y = ylo + k / nx;
+    const int x = xlo + kx, y = ylo + ky;
+    kx += r32; ky += q32;
+    if (kx >= nx) { kx -= nx; ky += 1; }
     const float w = recip(x, y);
     const float res = w - fmaf(beta, (float)x, fmaf(gamma, (float)y, alpha));
     ok = ok && (res == res) && (w > 0.0f);
@@ -1945,14 +1997,7 @@ __global__ void __launch_bounds__(256) reconstruct_position_kernel(const __grid_
   const int x = blockIdx.x * 16 + (threadIdx.x & 15);
   const int y = blockIdx.y * 16 + (threadIdx.x >> 4); // whole frame: SSAO taps reach outside a scissor band
   if (x >= P.W || y >= P.H) return;
-  float4 out = make_float4(0.0f, 0.0f, 0.0f, 0.0f); // the attachment's clear colour where nothing was drawn
-  const V4 normal4 = FmtRGBA16F::load(P.normal, x, y);
-  if (normal4.w != 0.0f) {
-    const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
-    const V3 p = reconstructPosition(P, u, v, __ldg(rowPtr<float>(P.depth, y) + x));
-    out = make_float4(p.x, p.y, p.z, 1.0f);
-  }
-  rowPtrW<float4>(P.position, y)[x] = out;
+  rowPtrW<float4>(P.position, y)[x] = reconstructedTexel(P, x, y);
 }
 
 // ---- deferred shading -----------------------------------------------------------------------------------------------
@@ -2070,10 +2115,12 @@ void launch_ssao_cull(const FrameParams& P, cudaStream_t s) {
   else ssao_cull_kernel<false><<<grid, 256, 0, s>>>(P);
 }
 void launch_ssao_exact(const FrameParams& P, cudaStream_t s) { ssao_exact_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
-void launch_ssao_quads(const FrameParams& P, cudaStream_t s) {
+bool launch_ssao_quads(const FrameParams& P, cudaStream_t s, bool reconstruct) { // returns whether it wrote the mode-D positions as well
   const dim3 grid((unsigned)((P.W + 1 + 31) / 32), (unsigned)((P.H + 1 + 7) / 8));
-  if (P.quadKind) ssao_rayquads_kernel<<<grid, 256, 0, s>>>(P);
-  else ssao_quads_kernel<<<grid, 256, 0, s>>>(P);
+  if (P.quadKind) { ssao_rayquads_kernel<<<grid, 256, 0, s>>>(P); return false; }
+  if (reconstruct) ssao_quads_kernel<true><<<grid, 256, 0, s>>>(P);
+  else ssao_quads_kernel<false><<<grid, 256, 0, s>>>(P);
+  return reconstruct;
 }
 void launch_reconstruct_position(const FrameParams& P, cudaStream_t s) { reconstruct_position_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
 void launch_deferred_shade(const FrameParams& P, cudaStream_t s) { deferred_shade_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
