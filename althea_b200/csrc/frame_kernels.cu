@@ -327,6 +327,67 @@ ADEV int ssrRayFastStep(const FrameParams& P, SsrRayFast& M, V3 worldPos, V3 ray
   }
   return 0;
 }
+// Two steps per call: the depth taps of both are requested before either is evaluated, so the dependent chain
+// tap -> den -> sign test of a step overlaps the next step's memory latency (the march's top stall is long_scoreboard on these taps).
+// Same values and the same order of decisions as two calls of ssrRayFastStep.
+struct SsrTap { float t00, t10, t01, t11, fx, fy; };
+ADEV SsrTap ssrTapFast(const FrameParams& P, float cu, float cv) {
+  const float mx = fmaf(cu, P.Wf, kFloorMagic - 1.0f), my = fmaf(cv, P.Hf, kFloorMagic - 1.0f);
+  SsrTap q;
+  q.fx = fmaf(cu, P.Wf, -0.5f) - (mx - kFloorMagic);
+  q.fy = fmaf(cv, P.Hf, -0.5f) - (my - kFloorMagic);
+  const int ix = __float_as_int(mx) - 0x4b400000, iy = __float_as_int(my) - 0x4b400000;
+  const float* r0 = P.depthPadOrigin + (iy * P.depthPadRow + ix);
+  const float* r1 = r0 + P.depthPadRow;
+  q.t00 = __ldg(r0); q.t10 = __ldg(r0 + 1); q.t01 = __ldg(r1); q.t11 = __ldg(r1 + 1);
+  return q;
+}
+// the part of a step after its tap: 0 = go on, 2 = hit
+ADEV int ssrEvalFast(const FrameParams& P, SsrRayFast& M, const SsrTap& q, float cu, float cv, float fi, V3 worldPos, V3 rayDir, V3& hitPos, V3& hitNormal) {
+  const float top = fmaf(q.t10 - q.t00, q.fx, q.t00), bot = fmaf(q.t11 - q.t01, q.fx, q.t01);
+  const float dRaw = fmaf(bot - top, q.fy, top);
+  const float den = fmaf(dRaw, 1000.0f - 0.01f, -1000.0f) * fmaf(fi, M.dS, M.S0);
+  const float projDen = fmaf(M.cP, den, fmaf(fi, M.daP, M.aP0));
+  const bool flips = projDen * M.prev <= 0.0f;
+  M.prev = projDen;
+  if (flips) {
+    const float k = (1000.0f * 0.01f) * rcpf(den);
+    const V3 camMinusPos = mk3(P.g.inverseView[12], P.g.inverseView[13], P.g.inverseView[14]) - worldPos;
+    const V3 wd = mk3(fmaf(P.ssrWu[0], cu, fmaf(P.ssrWv[0], cv, P.ssrW0[0])), fmaf(P.ssrWu[1], cu, fmaf(P.ssrWv[1], cv, P.ssrW0[1])),
+                      fmaf(P.ssrWu[2], cu, fmaf(P.ssrWv[2], cv, P.ssrW0[2])));
+    const V3 vv = mk3(fmaf(wd.x, k, camMinusPos.x), fmaf(wd.y, k, camMinusPos.y), fmaf(wd.z, k, camMinusPos.z));
+    const float along = dot3(vv, rayDir);
+    if (along > 0.0f && along * along > (0.999f * 0.999f) * dot3(vv, vv)) {
+      const V3 currentNormal = normalize3(xyz(bilinear<FmtRGBA16F, AddrClamp>(P.normal, cu, cv)));
+      if (dot3(currentNormal, rayDir) < 0.0f) {
+        hitPos = worldPos + vv;
+        hitNormal = currentNormal;
+        return 2;
+      }
+    }
+  }
+  return 0;
+}
+ADEV int ssrRayFastStep2(const FrameParams& P, SsrRayFast& M, V3 worldPos, V3 rayDir, V3& hitPos, V3& hitNormal) {
+  const float cuA = M.cu + M.stepX, cvA = M.cv + M.stepY, fiA = M.fi + 1.0f;
+  const float cuB = cuA + M.stepX, cvB = cvA + M.stepY, fiB = fiA + 1.0f;
+  M.cu = cuA; M.cv = cvA; M.fi = fiA;
+  if (fiA > M.fSafe) {
+    if (fiA > 128.0f || outside01(cuA, cvA)) return 1;
+  }
+  bool endB = false;
+  if (fiB > M.fSafe) endB = fiB > 128.0f || outside01(cuB, cvB);
+  const SsrTap qA = ssrTapFast(P, cuA, cvA);
+  const SsrTap qB = ssrTapFast(P, endB ? cuA : cuB, endB ? cvA : cvB); // a step that will not be taken re-reads A's footprint
+  int r = ssrEvalFast(P, M, qA, cuA, cvA, fiA, worldPos, rayDir, hitPos, hitNormal);
+  if (r) return r;
+  M.cu = cuB; M.cv = cvB; M.fi = fiB;
+  if (endB) return 1;
+  return ssrEvalFast(P, M, qB, cuB, cvB, fiB, worldPos, rayDir, hitPos, hitNormal);
+}
+#ifndef ALTHEA_SSR_STEPS2
+#define ALTHEA_SSR_STEPS2 0 // measured: 1.43 ms (48 registers, spills) / 1.39 ms (64 registers) against 1.36 ms one step at a time
+#endif
 #endif
 
 #ifndef ALTHEA_SSR_MIN_BLOCKS
@@ -386,7 +447,7 @@ __global__ void __launch_bounds__(256, ALTHEA_SSR_MARCH_MIN_BLOCKS) ssr_capture_
     SsrRayFast M;
     if (ssrRayFastSetup(P, u, v, worldPos, rayDir, perpRef, stepX, stepY, dl, M)) {
       for (;;) {
-        const int r = ssrRayFastStep(P, M, worldPos, rayDir, hitPos, hitNormal);
+        const int r = ALTHEA_SSR_STEPS2 ? ssrRayFastStep2(P, M, worldPos, rayDir, hitPos, hitNormal) : ssrRayFastStep(P, M, worldPos, rayDir, hitPos, hitNormal);
         if (r) { hit = r == 2; break; }
       }
     }
@@ -1823,6 +1884,9 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
   uint16_t* tq = tapQueue[warp];
   int fhead = 0, ftail = 0; // FIFO of flip items, warp-uniform
   unsigned gathers = 0u, lookups = 0u, tapItems = 0u;
+#if defined(ALTHEA_CULL_PROBE_LDS) || defined(ALTHEA_CULL_PROBE_ALU)
+  float probe = 0.0f;
+#endif
   // evaluates min(32, waiting) flip items, oldest first, one per lane
   auto drainFlips = [&]() {
     const int count = min(ftail - fhead, 32);
@@ -1901,6 +1965,12 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
         // both masks are shifted in from the sign bits (one funnel shift each): tap i ends up at bit 11 - i. `decided` is
         // |d| > rec.w + rayConst, i.e. (rec.w + rayConst) - |d| negative; +inf thresholds give +inf, never negative
         const float d = fmaf(rec.y, tx, fmaf(rec.z, ty, rec.x)) - fmaf(fi, dL, L0);
+#if defined(ALTHEA_CULL_PROBE_LDS)   // tuning probe: a second, equally conflicting record read per tap (what does the L1 data pipe cost?)
+        { const float4 rec2 = *reinterpret_cast<const float4*>(winBytes + (off ^ 0x2010u)); probe += rec2.x + rec2.w; }
+#elif defined(ALTHEA_CULL_PROBE_ALU) // tuning probe: sixteen more dependent FFMAs per tap (what does an issue slot cost?)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) probe = fmaf(probe, d, tx);
+#endif
         decMask = __funnelshift_l(__float_as_uint((rec.w + rayConst) - fabsf(d)), decMask, 1);
         negMask = __funnelshift_l(__float_as_uint(d), negMask, 1);
 #endif
@@ -1981,6 +2051,9 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
   while (ftail > fhead) drainFlips();
   __syncwarp();
   if (inside) rowPtrW<uint8_t>(P.ao, y)[x] = covered ? (uint8_t)__popc(hitMask[tid]) : (uint8_t)255;
+#if defined(ALTHEA_CULL_PROBE_LDS) || defined(ALTHEA_CULL_PROBE_ALU)
+  if (probe == 123.456f && inside) rowPtrW<uint8_t>(P.ao, y)[x] = 7; // keeps the probe's work alive
+#endif
   if (COUNT) {
     atomicAdd(P.gatherCounter, (unsigned long long)(gathers & 0xffffu));
     atomicAdd(P.gatherCounter + 1, (unsigned long long)(gathers >> 16));
