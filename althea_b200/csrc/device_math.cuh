@@ -133,7 +133,30 @@ struct AddrClamp { static ADEV int wrap(int i, int n) { return min(max(i, 0), n 
 struct AddrRepeat { static ADEV int wrap(int i, int n) { int m = i % n; return m < 0 ? m + n : m; } };
 
 struct BilinearSetup { int i0, i1, j0, j1; float fx, fy; };
-template <typename Addr> ADEV BilinearSetup bilinearSetup(int w, int h, float u, float v) {
+// FAST (only ever true in the fast build, see kFastTex) is for the shading passes: their bar is 1e-3 on colours and no threshold
+// test hangs on a footprint.
+#ifdef ALTHEA_PARITY
+constexpr bool kFastTex = false;
+#else
+constexpr bool kFastTex = true;
+#endif
+template <typename Addr, bool FAST = false> ADEV BilinearSetup bilinearSetup(int w, int h, float u, float v) {
+  // FAST:
+  // floor(x) comes out of the mantissa of u w - 1 + 1.5 * 2^23 (round to nearest of x - 0.5) instead of FRND + F2I on the
+  // quarter-rate XU pipe. A coordinate exactly on a texel centre may take the footprint to its left with weight 1 (the same
+  // value); NaN / huge coordinates give an arbitrary index, which Addr::wrap brings inside the image like any other.
+  if (FAST) {
+    const float kMagic = 12582912.0f;
+    const float fw = (float)w, fh = (float)h;
+    const float mx = fmaf(u, fw, kMagic - 1.0f), my = fmaf(v, fh, kMagic - 1.0f);
+    BilinearSetup s;
+    s.fx = fmaf(u, fw, -0.5f) - (mx - kMagic);
+    s.fy = fmaf(v, fh, -0.5f) - (my - kMagic);
+    const int ix = __float_as_int(mx) - 0x4b400000, iy = __float_as_int(my) - 0x4b400000;
+    s.i0 = Addr::wrap(ix, w); s.i1 = Addr::wrap(ix + 1, w);
+    s.j0 = Addr::wrap(iy, h); s.j1 = Addr::wrap(iy + 1, h);
+    return s;
+  }
   // rule A1. __fmul_rn/__fsub_rn are never contracted: the coordinate must round the same way in both builds.
   float x = __fsub_rn(__fmul_rn(u, (float)w), 0.5f), y = __fsub_rn(__fmul_rn(v, (float)h), 0.5f);
   if (!(x == x)) x = 0.0f;
@@ -147,31 +170,31 @@ template <typename Addr> ADEV BilinearSetup bilinearSetup(int w, int h, float u,
   s.j0 = Addr::wrap(iy, h); s.j1 = Addr::wrap(iy + 1, h);
   return s;
 }
-template <typename Fmt, typename Addr> ADEV V4 bilinear(const ImgView& im, float u, float v) {
-  BilinearSetup s = bilinearSetup<Addr>(im.w, im.h, u, v);
+template <typename Fmt, typename Addr, bool FAST = false> ADEV V4 bilinear(const ImgView& im, float u, float v) {
+  BilinearSetup s = bilinearSetup<Addr, FAST>(im.w, im.h, u, v);
   V4 t00 = Fmt::load(im, s.i0, s.j0), t10 = Fmt::load(im, s.i1, s.j0);
   V4 t01 = Fmt::load(im, s.i0, s.j1), t11 = Fmt::load(im, s.i1, s.j1);
   return mix4(mix4(t00, t10, s.fx), mix4(t01, t11, s.fx), s.fy);
 }
-template <typename Addr> ADEV float bilinearR32F(const ImgView& im, float u, float v) {
-  BilinearSetup s = bilinearSetup<Addr>(im.w, im.h, u, v);
+template <typename Addr, bool FAST = false> ADEV float bilinearR32F(const ImgView& im, float u, float v) {
+  BilinearSetup s = bilinearSetup<Addr, FAST>(im.w, im.h, u, v);
   const float* r0 = rowPtr<float>(im, s.j0);
   const float* r1 = rowPtr<float>(im, s.j1);
   float t00 = __ldg(r0 + s.i0), t10 = __ldg(r0 + s.i1), t01 = __ldg(r1 + s.i0), t11 = __ldg(r1 + s.i1);
   return mixf(mixf(t00, t10, s.fx), mixf(t01, t11, s.fx), s.fy);
 }
 // rule A5: explicit LOD clamped to [0, mips-1], LINEAR mip mode
-template <typename Fmt, typename Addr> ADEV V4 trilinear(const ChainView& c, float u, float v, float lod) {
+template <typename Fmt, typename Addr, bool FAST = false> ADEV V4 trilinear(const ChainView& c, float u, float v, float lod) {
   float maxLod = (float)(c.mips - 1);
   if (!(lod == lod)) lod = 0.0f;
   lod = fminf(fmaxf(lod, 0.0f), maxLod);
   float l0f = floorf(lod);
   int l0 = (int)l0f;
   float f = lod - l0f;
-  V4 s0 = bilinear<Fmt, Addr>(c.level[l0], u, v);
+  V4 s0 = bilinear<Fmt, Addr, FAST>(c.level[l0], u, v);
   if (f == 0.0f) return s0;
   int l1 = min(l0 + 1, c.mips - 1);
-  V4 s1 = bilinear<Fmt, Addr>(c.level[l1], u, v);
+  V4 s1 = bilinear<Fmt, Addr, FAST>(c.level[l1], u, v);
   return mix4(s0, s1, f);
 }
 

@@ -30,15 +30,15 @@ ADEV V2 equirectUv(V3 d) { // PBRMaterial.glsl:5-7
 }
 ADEV V3 sampleEnvMapLod0(const FrameParams& P, V3 dir) { // DeferredPass.frag:33-39
   V2 uv = equirectUv(dir);
-  return xyz(bilinear<FmtRGBA32F, AddrClamp>(P.env, uv.x, uv.y));
+  return xyz(bilinear<FmtRGBA32F, AddrClamp, kFastTex>(P.env, uv.x, uv.y));
 }
 ADEV V3 sampleEnvMapRough(const FrameParams& P, V3 dir, float roughness) { // PBRMaterial.glsl:4-11
   V2 uv = equirectUv(dir);
-  return xyz(trilinear<FmtRGBA32F, AddrClamp>(P.pre, uv.x, uv.y, 4.0f * roughness));
+  return xyz(trilinear<FmtRGBA32F, AddrClamp, kFastTex>(P.pre, uv.x, uv.y, 4.0f * roughness));
 }
 ADEV V3 sampleIrrMap(const FrameParams& P, V3 n) { // PBRMaterial.glsl:13-19
   V2 uv = equirectUv(n);
-  return xyz(bilinear<FmtRGBA32F, AddrClamp>(P.irr, uv.x, uv.y));
+  return xyz(bilinear<FmtRGBA32F, AddrClamp, kFastTex>(P.irr, uv.x, uv.y));
 }
 
 // cube-array lookup (Vulkan face selection table; the bilinear footprint clamps inside the face)
@@ -57,7 +57,7 @@ ADEV float sampleShadowCube(const FrameParams& P, V3 q, int light) {
 #endif
   ImgView layer = P.shadow;
   layer.ptr = static_cast<const char*>(P.shadow.ptr) + (size_t)(6 * light + face) * P.shadowLayerStride;
-  return bilinearR32F<AddrClamp>(layer, s, t);
+  return bilinearR32F<AddrClamp, kFastTex>(layer, s, t);
 }
 
 // ---- PBRMaterial.glsl:41-70 ---------------------------------------------------------------------------------------
@@ -96,7 +96,7 @@ ADEV V3 pbrMaterial(const FrameParams& P, V3 worldPos, V3 V, V3 N, V3 baseColor,
   {
     V3 F = fresnelSchlick(NdotV, F0, roughness);
     V3 diffuseColor = (one - F) * dielectricBase;
-    V4 lut = bilinear<FmtRGBA8, AddrClamp>(P.lut, NdotV, roughness);
+    V4 lut = bilinear<FmtRGBA8, AddrClamp, kFastTex>(P.lut, NdotV, roughness);
     V3 ambientSpecular = reflectedColor * (F * lut.x + mk3(lut.y, lut.y, lut.y));
     color = color + (irradianceColor * diffuseColor + ambientSpecular) * ambientOcclusion;
   }
@@ -232,8 +232,8 @@ ADEV DepthTap depthTapPadded(const FrameParams& P, float u, float v) {
 }
 
 ADEV V4 environmentLitSample(const FrameParams& P, V3 currentPos, float u, float v, V3 rayDir, V3 normal) { // SSR.frag:55-78
-  V3 baseColor = xyz(bilinear<FmtRGBA8, AddrClamp>(P.albedo, u, v));
-  V3 mro = xyz(bilinear<FmtRGBA8, AddrClamp>(P.mro, u, v));
+  V3 baseColor = xyz(bilinear<FmtRGBA8, AddrClamp, kFastTex>(P.albedo, u, v));
+  V3 mro = xyz(bilinear<FmtRGBA8, AddrClamp, kFastTex>(P.mro, u, v));
   V3 rd = normalize3(rayDir);
   V3 reflectedDirection = reflect3(rd, normal);
   V3 reflectedColor = sampleEnvMapRough(P, reflectedDirection, mro.y);
@@ -2108,7 +2108,7 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const __grid_consta
     V3 mro = xyz(FmtRGBA8::load(P.mro, x, y));
     V3 vdir = normalize3(direction);
     V3 reflectedDirection = reflect3(vdir, normal);
-    V4 reflectedColor = trilinear<FmtRGBA16F, AddrClamp>(P.refl, u, v, 4.0f * mro.y);
+    V4 reflectedColor = trilinear<FmtRGBA16F, AddrClamp, kFastTex>(P.refl, u, v, 4.0f * mro.y);
     V3 envReflected = sampleEnvMapRough(P, reflectedDirection, mro.y);
     V3 rc;
     if (reflectedColor.w < 0.01f) rc = envReflected;
