@@ -588,7 +588,10 @@ __global__ void __launch_bounds__(256, ALTHEA_SSR_MARCH_MIN_BLOCKS) ssr_capture_
 }
 #endif
 
-__global__ void __launch_bounds__(256) ssr_shade_hits_kernel(const __grid_constant__ FrameParams P) {
+#ifndef ALTHEA_SSR_SHADE_MIN_BLOCKS
+#define ALTHEA_SSR_SHADE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, ALTHEA_SSR_SHADE_MIN_BLOCKS) ssr_shade_hits_kernel(const __grid_constant__ FrameParams P) {
   const unsigned count = *P.ssrHitCount, cap = P.ssrHitCap;
   for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < count; k += gridDim.x * 256u) {
     const float* r = P.ssrHits + k;
