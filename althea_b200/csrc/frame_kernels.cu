@@ -1624,48 +1624,48 @@ constexpr float kCullReach = ALTHEA_CULL_REACH; // screen reach of a tile's rays
 // levels are not built and ssao_cull_kernel hands every tile over without staging anything.
 ADEV bool planesHopeless(const FrameParams& P) { return P.ssaoPlaneStats[1] * 16u < P.ssaoPlaneStats[0]; }
 
-// one warp per record. COARSEST: the level-2 records, counting how many can decide; else levels 0 and 1, unless hopeless
-template <bool COARSEST> __global__ void __launch_bounds__(256) ssao_planes_kernel(const __grid_constant__ FrameParams P) {
-  const int lane = threadIdx.x & 31;
-  long long rec = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  int level = COARSEST ? 2 : 0;
-  for (; level < (COARSEST ? 3 : 2); ++level) {
-    const long long n = (long long)P.ssaoPlaneRow[level] * (P.ssaoPlaneNy[level] + 2 * kSsaoPlanePad + 1);
-    if (rec < n) break;
-    rec -= n;
-  }
-  if (level == (COARSEST ? 3 : 2)) return;
+// G lanes per record (8 for the 8-texel blocks of level 0: four records per warp, their reductions share the shuffles; a warp for
+// the larger blocks). LEVEL 2 goes first and counts how many of its records can decide; levels 0 and 1 are skipped when hopeless.
+template <int LEVEL, int G> ADEV void ssaoPlaneRecords(const FrameParams& P, unsigned block) {
+  constexpr bool COARSEST = LEVEL == 2;
+  const int lane = threadIdx.x & (G - 1);
+  const long long rec = ((long long)block * 256 + threadIdx.x) / G;
+  constexpr int level = LEVEL;
+  const long long n = (long long)P.ssaoPlaneRow[level] * (P.ssaoPlaneNy[level] + 2 * kSsaoPlanePad + 1);
+  // records beyond the level's end keep their lanes in the warp's shuffles (G < 32): clamped to the last record, not written
+  const bool live = rec < n;
+  const long long r = live ? rec : n - 1;
   if (!COARSEST && planesHopeless(P)) return;
-  const int S = 8 << level;
+  constexpr int S = 8 << level;
   const int row = P.ssaoPlaneRow[level];
-  const int bx = (int)(rec % row) - kSsaoPlanePad, by = (int)(rec / row) - kSsaoPlanePad;
+  const int bx = (int)(r % row) - kSsaoPlanePad, by = (int)(r / row) - kSsaoPlanePad;
   float4* out = const_cast<float4*>(P.ssaoPlanes[level]) + ((long long)by * row + bx);
   const float inf = __int_as_float(0x7f800000);
-  if (bx < 0 || by < 0 || bx >= P.ssaoPlaneNx[level] || by >= P.ssaoPlaneNy[level]) {
-    if (lane == 0) *out = make_float4(0.0f, 0.0f, 0.0f, inf);
-    return;
-  }
+  const bool padding = bx < 0 || by < 0 || bx >= P.ssaoPlaneNx[level] || by >= P.ssaoPlaneNy[level];
   // texels the record answers for: the block and an apron: the march assigns a tap to a block by x / S rounded to 1 / 16
   // (S / 32 texels) and y / S to 2^-9 or finer, its tap coordinate is within 1e-3 texels of the restatement's, and the
   // footprint is the two texels from floor(x); inside the image (a footprint that clamps at the border repeats a covered texel)
   const int X0 = bx * S, Y0 = by * S;
   const int xlo = max(X0 - 2 - (S >> 5), 0), xhi = min(X0 + S + 1, P.W - 1), ylo = max(Y0 - 2, 0), yhi = min(Y0 + S + 1, P.H - 1);
-  const int nx = xhi - xlo + 1, ny = yhi - ylo + 1;
+  const int nx = padding ? 1 : xhi - xlo + 1, ny = padding ? 0 : yhi - ylo + 1; // padding records read nothing
   auto recip = [&](int x, int y) { return __ldg(P.ssaoRecip + ((size_t)y * P.W + x)); }; // NaN: texel off the camera model
   // plane through the centre texel with the secant slopes of the middle row / column (for a quadratic surface these are the
   // least-squares slopes); the offset is re-centred on the residual range below
   const int xc = (xlo + xhi) >> 1, yc = (ylo + yhi) >> 1;
-  const float beta = nx > 1 ? (recip(xhi, yc) - recip(xlo, yc)) / (float)(xhi - xlo) : 0.0f;
-  const float gamma = ny > 1 ? (recip(xc, yhi) - recip(xc, ylo)) / (float)(yhi - ylo) : 0.0f;
-  const float alpha = recip(xc, yc) - (beta * (float)xc + gamma * (float)yc);
+  float beta = 0.0f, gamma = 0.0f, alpha = 0.0f;
+  if (!padding) {
+    beta = nx > 1 ? (recip(xhi, yc) - recip(xlo, yc)) / (float)(xhi - xlo) : 0.0f;
+    gamma = ny > 1 ? (recip(xc, yhi) - recip(xc, ylo)) / (float)(yhi - ylo) : 0.0f;
+    alpha = recip(xc, yc) - (beta * (float)xc + gamma * (float)yc);
+  }
   float rlo = inf, rhi = -inf, wmax = 0.0f;
   bool ok = true, cleared = true;
-  // texel k = lane, lane + 32, ... of the nx x ny box, row by row: the (column, row) pair is stepped, not divided out
-  const int q32 = 32 / nx, r32 = 32 - q32 * nx;
+  // texel k = lane, lane + G, ... of the nx x ny box, row by row: the (column, row) pair is stepped, not divided out
+  const int qG = G / nx, rG = G - qG * nx;
   int kx = lane % nx, ky = lane / nx;
-  for (int k = lane; k < nx * ny; k += 32) {
+  for (int k = lane; k < nx * ny; k += G) {
     const int x = xlo + kx, y = ylo + ky;
-    kx += r32; ky += q32;
+    kx += rG; ky += qG;
     if (kx >= nx) { kx -= nx; ky += 1; }
     const float w = recip(x, y);
     const float res = w - fmaf(beta, (float)x, fmaf(gamma, (float)y, alpha));
@@ -1676,18 +1676,23 @@ template <bool COARSEST> __global__ void __launch_bounds__(256) ssao_planes_kern
     wmax = fmaxf(wmax, w);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = G / 2; o > 0; o >>= 1) {
     rlo = fminf(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
     rhi = fmaxf(rhi, __shfl_xor_sync(0xffffffffu, rhi, o));
     wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
     ok = __shfl_xor_sync(0xffffffffu, (int)ok, o) && ok;
     cleared = __shfl_xor_sync(0xffffffffu, (int)cleared, o) && cleared;
   }
-  if (lane == 0 && cleared) { // every texel the record answers for is the clear colour: r = -1 marks the class
+  if (lane != 0 || !live) return;
+  if (padding) {
+    *out = make_float4(0.0f, 0.0f, 0.0f, inf);
+    return;
+  }
+  if (cleared) { // every texel the record answers for is the clear colour: r = -1 marks the class
     *out = make_float4(0.0f, 0.0f, 0.0f, ALTHEA_CULL_SKY_CLASS ? -1.0f : inf);
     return; // (not counted in the statistics: empty sky says nothing about whether surfaces decide)
   }
-  if (lane == 0) {
+  {
     const float mid = 0.5f * (rlo + rhi);
     const float a2 = alpha + mid;
     // The tap is the bilinear combination of its footprint's texels, whose projections are t_k c0 (w_k - L_k): the weights
@@ -1714,6 +1719,14 @@ template <bool COARSEST> __global__ void __launch_bounds__(256) ssao_planes_kern
       if (fin) atomicAdd(P.ssaoPlaneStats + 1, 1u);
     }
   }
+}
+
+// level 2 alone (its statistics decide whether the finer levels are built), then levels 0 and 1 in one launch: blocks [0, blocks0) build
+// level 0, the rest level 1
+__global__ void __launch_bounds__(256) ssao_planes_coarsest_kernel(const __grid_constant__ FrameParams P) { ssaoPlaneRecords<2, 32>(P, blockIdx.x); }
+__global__ void __launch_bounds__(256) ssao_planes_finer_kernel(const __grid_constant__ FrameParams P, unsigned blocks0) {
+  if (blockIdx.x < blocks0) ssaoPlaneRecords<0, 8>(P, blockIdx.x);
+  else ssaoPlaneRecords<1, 32>(P, blockIdx.x - blocks0);
 }
 
 // the ray of one pixel: SSAO.glsl:36-45 (the hash RNG's state after k draws is seed + k, so ray r starts at seed + 3 r)
@@ -2196,8 +2209,11 @@ static_assert(kSsaoTileW == 16, "ssao_cull_kernel and ssao_kernel share the 16 x
 void launch_ssao_planes(const FrameParams& P, cudaStream_t s, bool coarsest) { // the coarsest level first, then the finer ones if worth it
   long long n[3];
   for (int l = 0; l < 3; ++l) n[l] = (long long)P.ssaoPlaneRow[l] * (P.ssaoPlaneNy[l] + 2 * kSsaoPlanePad + 1);
-  if (coarsest) ssao_planes_kernel<true><<<(unsigned)((n[2] + 7) / 8), 256, 0, s>>>(P);
-  else ssao_planes_kernel<false><<<(unsigned)((n[0] + n[1] + 7) / 8), 256, 0, s>>>(P);
+  if (coarsest) ssao_planes_coarsest_kernel<<<(unsigned)((n[2] + 7) / 8), 256, 0, s>>>(P);
+  else {
+    const unsigned blocks0 = (unsigned)((n[0] + 31) / 32), blocks1 = (unsigned)((n[1] + 7) / 8);
+    ssao_planes_finer_kernel<<<blocks0 + blocks1, 256, 0, s>>>(P, blocks0);
+  }
 }
 void launch_ssao_cull(const FrameParams& P, cudaStream_t s) {
   const dim3 grid((unsigned)((P.W + 15) / 16), (unsigned)((P.y1 - P.y0 + 15) / 16));
