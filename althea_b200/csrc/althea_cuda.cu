@@ -938,15 +938,13 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;
   if (P.gatherCounter) cudaMemsetAsync(P.gatherCounter, 0, 80 * sizeof(unsigned long long), stream);
-  // mode D: the position-record pass reconstructs the positions itself when it runs (one launch, no read-back of the positions)
-  const bool fusedReconstruct = reconstruct && computeAo && !exactTaps && P.quadKind == 0;
-  if (reconstruct && !fusedReconstruct)
+  if (reconstruct)
     timedLaunch(ctx, "reconstruct_position", stream, [&] { parity ? althea_parity::launch_reconstruct_position(P, stream) : althea_fast::launch_reconstruct_position(P, stream); });
   if (computeAo) {
     if (exactTaps) {
       timedLaunch(ctx, "ssao_exact", stream, [&] { parity ? althea_parity::launch_ssao_exact(P, stream) : althea_fast::launch_ssao_exact(P, stream); });
     } else {
-      timedLaunch(ctx, "ssao_quads", stream, [&] { parity ? althea_parity::launch_ssao_quads(P, stream, fusedReconstruct) : althea_fast::launch_ssao_quads(P, stream, fusedReconstruct); });
+      timedLaunch(ctx, "ssao_quads", stream, [&] { parity ? althea_parity::launch_ssao_quads(P, stream) : althea_fast::launch_ssao_quads(P, stream); });
       if (cull) {
         for (bool coarsest : {true, false})
           timedLaunch(ctx, "ssao_planes", stream, [&] { parity ? althea_parity::launch_ssao_planes(P, stream, coarsest) : althea_fast::launch_ssao_planes(P, stream, coarsest); });

@@ -1053,33 +1053,17 @@ ADEV float4 reconstructedTexel(const FrameParams& P, int x, int y) {
   }
   return out;
 }
-// RECON (mode D): the pass also IS reconstruct_position_kernel: every position is reconstructed from depth once per 32 x 8 block
-// (+ a one-texel apron) into a shared tile, written to the position scratch by the thread that owns it, and the footprint reads
-// its four corners from the tile: the 16 B/px the separate pass wrote are not read back from memory, and one launch goes.
-template <bool RECON> __global__ void __launch_bounds__(256) ssao_quads_kernel(const __grid_constant__ FrameParams P) {
-  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int qx = blockIdx.x * 32 + lane; // record column = ix + 1
-  const int qy = blockIdx.y * 8 + ty;
-  V4 p00, p10, p01, p11;
-  if (RECON) {
-    __shared__ float4 tile[9][33]; // texels [qx0 - 1, qx0 + 32) x [qy0 - 1, qy0 + 8) of the block
-    tile[ty + 1][lane + 1] = reconstructedTexel(P, qx, qy);
-    if (ty == 0) tile[0][lane + 1] = reconstructedTexel(P, qx, qy - 1);
-    if (lane == 0) tile[ty + 1][0] = reconstructedTexel(P, qx - 1, qy);
-    if (threadIdx.x == 0) tile[0][0] = reconstructedTexel(P, qx - 1, qy - 1);
-    __syncthreads();
-    if (qx > P.W || qy > P.H) return;
-    const float4 t11 = tile[ty + 1][lane + 1], t01 = tile[ty + 1][lane], t10 = tile[ty][lane + 1], t00 = tile[ty][lane];
-    p00 = mk4(t00.x, t00.y, t00.z, t00.w); p10 = mk4(t10.x, t10.y, t10.z, t10.w);
-    p01 = mk4(t01.x, t01.y, t01.z, t01.w); p11 = mk4(t11.x, t11.y, t11.z, t11.w);
-    if (qx < P.W && qy < P.H) rowPtrW<float4>(P.position, qy)[qx] = t11;
-  } else {
-    if (qx > P.W || qy > P.H) return;
-    const int i0 = AddrClamp::wrap(qx - 1, P.W), i1 = AddrClamp::wrap(qx, P.W);
-    const int j0 = AddrClamp::wrap(qy - 1, P.H), j1 = AddrClamp::wrap(qy, P.H);
-    p00 = FmtRGBA32F::load(P.position, i0, j0); p10 = FmtRGBA32F::load(P.position, i1, j0);
-    p01 = FmtRGBA32F::load(P.position, i0, j1); p11 = FmtRGBA32F::load(P.position, i1, j1);
-  }
+// (Reconstructing the mode-D positions inside this pass, through a shared tile, instead of reading back what
+// reconstruct_position_kernel wrote was built and measured: 0.164 ms against 0.057 + 0.093 ms for the two passes at 4K with a cold
+// L2. Both are bound by their writes (52 B/px here); the read-back it saves comes from L2.)
+__global__ void __launch_bounds__(256) ssao_quads_kernel(const __grid_constant__ FrameParams P) {
+  const int qx = blockIdx.x * 32 + (threadIdx.x & 31); // record column = ix + 1
+  const int qy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (qx > P.W || qy > P.H) return;
+  const int i0 = AddrClamp::wrap(qx - 1, P.W), i1 = AddrClamp::wrap(qx, P.W);
+  const int j0 = AddrClamp::wrap(qy - 1, P.H), j1 = AddrClamp::wrap(qy, P.H);
+  const V4 p00 = FmtRGBA32F::load(P.position, i0, j0), p10 = FmtRGBA32F::load(P.position, i1, j0);
+  const V4 p01 = FmtRGBA32F::load(P.position, i0, j1), p11 = FmtRGBA32F::load(P.position, i1, j1);
   if (P.ssaoPlaneStats && qx == 0 && qy == 0) { P.ssaoPlaneStats[0] = 0u; P.ssaoPlaneStats[1] = 0u; P.ssaoTileList[0] = 0u; }
   if (P.ssaoRecip && qx < P.W && qy < P.H) { // this thread's p11 is texel (qx, qy): its reciprocal eye depth for ssao_planes_kernel
     const V3 cam = mk3(P.ssaoCam[0], P.ssaoCam[1], P.ssaoCam[2]);
@@ -2221,12 +2205,10 @@ void launch_ssao_cull(const FrameParams& P, cudaStream_t s) {
   else ssao_cull_kernel<false><<<grid, 256, 0, s>>>(P);
 }
 void launch_ssao_exact(const FrameParams& P, cudaStream_t s) { ssao_exact_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
-bool launch_ssao_quads(const FrameParams& P, cudaStream_t s, bool reconstruct) { // returns whether it wrote the mode-D positions as well
+void launch_ssao_quads(const FrameParams& P, cudaStream_t s) {
   const dim3 grid((unsigned)((P.W + 1 + 31) / 32), (unsigned)((P.H + 1 + 7) / 8));
-  if (P.quadKind) { ssao_rayquads_kernel<<<grid, 256, 0, s>>>(P); return false; }
-  if (reconstruct) ssao_quads_kernel<true><<<grid, 256, 0, s>>>(P);
-  else ssao_quads_kernel<false><<<grid, 256, 0, s>>>(P);
-  return reconstruct;
+  if (P.quadKind) ssao_rayquads_kernel<<<grid, 256, 0, s>>>(P);
+  else ssao_quads_kernel<<<grid, 256, 0, s>>>(P);
 }
 void launch_reconstruct_position(const FrameParams& P, cudaStream_t s) { reconstruct_position_kernel<<<tileGrid(P.W, P.H), 256, 0, s>>>(P); }
 void launch_deferred_shade(const FrameParams& P, cudaStream_t s) { deferred_shade_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }

@@ -14,7 +14,7 @@
   void launch_reconstruct_position(const FrameParams& P, cudaStream_t s);    \
   void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s);      \
   void launch_ssao(const FrameParams& P, cudaStream_t s);                    \
-  bool launch_ssao_quads(const FrameParams& P, cudaStream_t s, bool reconstruct); \
+  void launch_ssao_quads(const FrameParams& P, cudaStream_t s);              \
   void launch_ssao_planes(const FrameParams& P, cudaStream_t s, bool coarsest); \
   void launch_ssao_cull(const FrameParams& P, cudaStream_t s);               \
   void launch_ssao_exact(const FrameParams& P, cudaStream_t s);              \

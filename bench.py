@@ -39,9 +39,7 @@ BYTES_PER_PX = {
     "glossy_convolve": 13.28,  # read 8*(1+1/4+1/16+1/64) + write 8*(1/4+...+1/256)
     "ssao": 25.0,             # position 16 + normal 8 + write count 1 (the proxy records are engine scratch, not algorithmic)
     "ssao_cull": 25.0,        # the same stage with the coarse sign test in front (round 2): same algorithmic bytes
-    "ssao_quads": 52.0,       # mode P: position 16 read + 32-byte proxy record + 4-byte reciprocal depth written per pixel (engine scratch);
-                              # mode D (64, set in main): depth 4 + normal 8 read, position 16 + record 32 + reciprocal depth 4 written (the pass
-                              # reconstructs the positions itself: no separate reconstruct_position launch)
+    "ssao_quads": 52.0,       # position 16 read + 32-byte proxy record + 4-byte reciprocal depth written per pixel (engine scratch)
     "ssao_planes": 4.5,       # reciprocal depths 4 read, plane records (three levels) ~0.33 written per pixel (engine scratch)
     "deferred_shade": 51.66,  # position 16 + normal 8 + albedo 4 + MRO 4 + AO count 1 + reflection mips (upper bound) 10.66 + write RGBA16F 8
 }
@@ -553,8 +551,6 @@ def main():
     if args.workload == "mesh4k":
         return main_mesh4k(args, ctx, rank, local_rank, world, device)
     mode_p = args.gbuffer_mode == "P"
-    if not mode_p:
-        BYTES_PER_PX["ssao_quads"] = 64.0
     ibl, lights, views, ibl_t = build_rank_inputs(ctx, rank, args.views, device, with_position=mode_p)
     stream = engine.current_stream_ptr(local_rank)
     V = len(views)

@@ -21,13 +21,15 @@ from althea_b200 import _capi, engine  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--views", type=int, default=2)
+    ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--exact-taps", action="store_true")
     ap.add_argument("--parity", action="store_true")
+    ap.add_argument("--mode-p", action="store_true", help="legacy position attachment as an input (default: mode D, what bench.py times)")
+    ap.add_argument("--views-cycle", type=int, default=8, help="views cycled through, so that inputs exceed L2 as in bench.py")
     args = ap.parse_args()
     ctx = engine.Context(0)
     flags = (_capi.CTX_PARITY_MATH if args.parity else 0) | (_capi.CTX_SSAO_EXACT_TAPS if args.exact_taps else 0)
-    ibl, lights, views, _ = bench.build_rank_inputs(ctx, 0, args.views, "cuda:0", quick_ibl=True)
+    ibl, lights, views, _ = bench.build_rank_inputs(ctx, 0, args.views, "cuda:0", quick_ibl=True, with_position=args.mode_p)
     ctx.set_flags(flags)
     stream = engine.current_stream_ptr(0)
     for _ in range(2):
