@@ -400,9 +400,16 @@ ADEV int ssrRayFastStep2(const FrameParams& P, SsrRayFast& M, V3 worldPos, V3 ra
 #ifndef ALTHEA_SSR_MARCH_MIN_BLOCKS
 #define ALTHEA_SSR_MARCH_MIN_BLOCKS 5
 #endif
+#ifndef ALTHEA_SSR_TILE_W
+#define ALTHEA_SSR_TILE_W 16 // measured at 4K: 8 x 4 pixels per warp 1.40 ms, 16 x 2 1.37 ms, 32 x 1 1.47 ms, 64-wide tiles 1.50 ms
+#endif
+constexpr int kSsrTileW = ALTHEA_SSR_TILE_W, kSsrTileH = 256 / kSsrTileW;
 __global__ void __launch_bounds__(256, ALTHEA_SSR_MARCH_MIN_BLOCKS) ssr_capture_kernel(const __grid_constant__ FrameParams P) {
-  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
-  const int y = P.y0 + blockIdx.y * 16 + (threadIdx.x >> 4); // rows [y0, y1): the scissor (whole frame by default)
+  // A warp is min(kSsrTileW, 32) x (32 / kSsrTileW) pixels of a kSsrTileW x kSsrTileH tile. The march is bound by the L1 data pipe as
+  // much as by issue (72 % / 65 %, profiles/): a depth tap of a warp costs a wavefront per 128-byte line it touches. Fewer image
+  // rows per warp mean fewer lines per tap but lanes whose marches end further apart: 16 x 2 is the measured optimum.
+  const int x = blockIdx.x * kSsrTileW + (threadIdx.x % kSsrTileW);
+  const int y = P.y0 + blockIdx.y * kSsrTileH + (threadIdx.x / kSsrTileW); // rows [y0, y1): the scissor (whole frame by default)
   const bool inside = x < P.W && y < P.y1;
   const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
   V4 normal4 = mk4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -2141,7 +2148,7 @@ void launch_ssr_capture(const FrameParams& P, cudaStream_t s) {
     return;
   }
 #endif
-  ssr_capture_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P);
+  ssr_capture_kernel<<<dim3((unsigned)((P.W + kSsrTileW - 1) / kSsrTileW), (unsigned)((P.y1 - P.y0 + kSsrTileH - 1) / kSsrTileH)), 256, 0, s>>>(P);
 }
 void launch_ssr_shade_hits(const FrameParams& P, cudaStream_t s) { ssr_shade_hits_kernel<<<148 * 8, 256, 0, s>>>(P); }
 void launch_ssr_planes(const FrameParams& P, cudaStream_t s) { ssr_planes_kernel<<<(kSsrPlaneStride * kSsrPlaneRows + 7) / 8, 256, 0, s>>>(P); }

@@ -25,7 +25,6 @@ def main():
     ap.add_argument("--exact-taps", action="store_true")
     ap.add_argument("--parity", action="store_true")
     ap.add_argument("--mode-p", action="store_true", help="legacy position attachment as an input (default: mode D, what bench.py times)")
-    ap.add_argument("--views-cycle", type=int, default=8, help="views cycled through, so that inputs exceed L2 as in bench.py")
     args = ap.parse_args()
     ctx = engine.Context(0)
     flags = (_capi.CTX_PARITY_MATH if args.parity else 0) | (_capi.CTX_SSAO_EXACT_TAPS if args.exact_taps else 0)
