@@ -780,11 +780,18 @@ int althea_cuda_ssr_capture(althea_cuda_ctx* ctx, const althea_global_uniforms* 
     P.y1 = (int)hi[0];
   }
   althea_cuda_ctx::Scratch& S = ctx->scratch[workStream(ctx, sync)];
-  { // the padded depth covers the whole frame even under a scissor: a ray may leave the band
-    if ((rc = growScratchBuf(ctx, &S.depthPad, &S.depthPadBytes, ((size_t)P.W + 2) * ((size_t)P.H + 2) * sizeof(float), "ssr padded depth"))) return rc;
+  { // the padded depth covers the whole frame even under a scissor: a ray may leave the band. The fast build's plain march reads
+    // it as one 16-byte record per bilinear footprint instead ((W + 1) x (H + 1) records in the same scratch allocation)
+    const bool parityMath = ctx->flags & ALTHEA_CTX_PARITY_MATH;
+    const bool quads = !(ctx->flags & ALTHEA_CTX_SSR_PLANE_SKIP) && (parityMath ? althea_parity::ssr_march_reads_depth_quads() : althea_fast::ssr_march_reads_depth_quads());
+    const size_t need = quads ? ((size_t)P.W + 1) * ((size_t)P.H + 1) * sizeof(float4) : ((size_t)P.W + 2) * ((size_t)P.H + 2) * sizeof(float);
+    if ((rc = growScratchBuf(ctx, &S.depthPad, &S.depthPadBytes, need, "ssr padded depth"))) return rc;
     P.depthPadRow = P.W + 2;
     P.depthPad = static_cast<const float*>(S.depthPad);
     P.depthPadOrigin = P.depthPad + P.depthPadRow + 1;
+    P.depthQuadOrigin = nullptr;
+    P.depthQuadRow = P.W + 1;
+    if (quads) P.depthQuadOrigin = static_cast<const float4*>(S.depthPad) + ((size_t)P.depthQuadRow + 1);
   }
   P.ssrHits = nullptr;
   P.ssrHitCount = nullptr;

@@ -211,6 +211,14 @@ __global__ void __launch_bounds__(256) ssr_depth_pad_kernel(const __grid_constan
   if (qx == 0 && qy == 0 && P.ssrHitCount) { P.ssrHitCount[0] = 0u; P.ssrHitCount[1] = 0u; } // the hit list the march (next in the stream) appends to, and its chunk counter
   if (qx > P.W + 1 || qy > P.H + 1) return;
   const float d = __ldg(rowPtr<float>(P.depth, AddrClamp::wrap(qy - 1, P.H)) + AddrClamp::wrap(qx - 1, P.W));
+  if (P.depthQuadOrigin) { // footprint records instead: this thread's texel is the footprint's top-left tap (qx - 1, qy - 1)
+    if (qx > P.W || qy > P.H) return;
+    const int i1 = AddrClamp::wrap(qx, P.W), j1 = AddrClamp::wrap(qy, P.H);
+    const float* r0 = rowPtr<float>(P.depth, AddrClamp::wrap(qy - 1, P.H));
+    const float* r1 = rowPtr<float>(P.depth, j1);
+    const_cast<float4*>(P.depthQuadOrigin)[(qy - 1) * P.depthQuadRow + (qx - 1)] = make_float4(d, __ldg(r0 + i1), __ldg(r1 + AddrClamp::wrap(qx - 1, P.W)), __ldg(r1 + i1));
+    return;
+  }
   const_cast<float*>(P.depthPad)[(size_t)qy * P.depthPadRow + qx] = d;
 }
 struct DepthTap { float t00, t10, t01, t11, fx, fy; };
@@ -257,6 +265,12 @@ ADEV V4 environmentLitSample(const FrameParams& P, V3 currentPos, float u, float
 //    a tap exactly on a texel centre may take the footprint to its left with weight 1, the same value;
 //  * the ray leaves [0, 1]^2 at a step number known to within a fraction of a step when it starts: the per-step test is one
 //    compare against that number minus two, the exact outside01 test of SSR.frag:106 runs on the last steps only.
+// One 16-byte record per bilinear footprint instead of four floats of the padded copy: a tap becomes one 128-bit load (the march's
+// loads touch 10.4 sectors per warp-level request, its rays being as incoherent as the normals they reflect off), but the records
+// are four times the bytes through L1 and L2: 1.76 ms against 1.37 ms at 4K. Off; round 1 had measured the same with the old step.
+#ifndef ALTHEA_SSR_DEPTH_QUADS
+#define ALTHEA_SSR_DEPTH_QUADS 0
+#endif
 struct SsrRayFast {
   float cu, cv, stepX, stepY;
   float fi, fSafe;       // steps taken so far; steps <= fSafe are inside the screen and below the 128-step cap for certain
@@ -297,9 +311,15 @@ ADEV int ssrRayFastStep(const FrameParams& P, SsrRayFast& M, V3 worldPos, V3 ray
   const float mx = fmaf(M.cu, P.Wf, kFloorMagic - 1.0f), my = fmaf(M.cv, P.Hf, kFloorMagic - 1.0f); // round(x - 0.5) + magic, x = cu W - 0.5
   const float fx = fmaf(M.cu, P.Wf, -0.5f) - (mx - kFloorMagic), fy = fmaf(M.cv, P.Hf, -0.5f) - (my - kFloorMagic);
   const int ix = __float_as_int(mx) - 0x4b400000, iy = __float_as_int(my) - 0x4b400000; // in [-1, W-1] x [-1, H-1]
-  const float* r0 = P.depthPadOrigin + (iy * P.depthPadRow + ix);
-  const float* r1 = r0 + P.depthPadRow;
-  const float t00 = __ldg(r0), t10 = __ldg(r0 + 1), t01 = __ldg(r1), t11 = __ldg(r1 + 1);
+  float t00, t10, t01, t11;
+  if (ALTHEA_SSR_DEPTH_QUADS) { // one record per footprint (launch_ssr_capture's callers set it up whenever this build marches)
+    const float4 q = __ldg(P.depthQuadOrigin + (iy * P.depthQuadRow + ix));
+    t00 = q.x; t10 = q.y; t01 = q.z; t11 = q.w;
+  } else {
+    const float* r0 = P.depthPadOrigin + (iy * P.depthPadRow + ix);
+    const float* r1 = r0 + P.depthPadRow;
+    t00 = __ldg(r0); t10 = __ldg(r0 + 1); t01 = __ldg(r1); t11 = __ldg(r1 + 1);
+  }
   const float top = fmaf(t10 - t00, fx, t00), bot = fmaf(t11 - t01, fx, t01);
   const float dRaw = fmaf(bot - top, fy, top);
   const float den = fmaf(dRaw, 1000.0f - 0.01f, -1000.0f) * fmaf(M.fi, M.dS, M.S0);
@@ -337,6 +357,11 @@ ADEV SsrTap ssrTapFast(const FrameParams& P, float cu, float cv) {
   q.fx = fmaf(cu, P.Wf, -0.5f) - (mx - kFloorMagic);
   q.fy = fmaf(cv, P.Hf, -0.5f) - (my - kFloorMagic);
   const int ix = __float_as_int(mx) - 0x4b400000, iy = __float_as_int(my) - 0x4b400000;
+  if (ALTHEA_SSR_DEPTH_QUADS) {
+    const float4 r = __ldg(P.depthQuadOrigin + (iy * P.depthQuadRow + ix));
+    q.t00 = r.x; q.t10 = r.y; q.t01 = r.z; q.t11 = r.w;
+    return q;
+  }
   const float* r0 = P.depthPadOrigin + (iy * P.depthPadRow + ix);
   const float* r1 = r0 + P.depthPadRow;
   q.t00 = __ldg(r0); q.t10 = __ldg(r0 + 1); q.t01 = __ldg(r1); q.t11 = __ldg(r1 + 1);
@@ -2149,6 +2174,13 @@ void launch_ssr_capture(const FrameParams& P, cudaStream_t s) {
   }
 #endif
   ssr_capture_kernel<<<dim3((unsigned)((P.W + kSsrTileW - 1) / kSsrTileW), (unsigned)((P.y1 - P.y0 + kSsrTileH - 1) / kSsrTileH)), 256, 0, s>>>(P);
+}
+bool ssr_march_reads_depth_quads() {
+#ifdef ALTHEA_PARITY
+  return false;
+#else
+  return ALTHEA_SSR_DEPTH_QUADS != 0;
+#endif
 }
 void launch_ssr_shade_hits(const FrameParams& P, cudaStream_t s) { ssr_shade_hits_kernel<<<148 * 8, 256, 0, s>>>(P); }
 void launch_ssr_planes(const FrameParams& P, cudaStream_t s) { ssr_planes_kernel<<<(kSsrPlaneStride * kSsrPlaneRows + 7) / 8, 256, 0, s>>>(P); }

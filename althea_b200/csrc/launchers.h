@@ -8,6 +8,7 @@
 #define ALTHEA_DECLARE_FRAME_LAUNCHERS(ns)                                   \
   namespace ns {                                                             \
   void launch_ssr_capture(const FrameParams& P, cudaStream_t s);             \
+  bool ssr_march_reads_depth_quads();                                        \
   void launch_ssr_depth_pad(const FrameParams& P, cudaStream_t s);           \
   void launch_ssr_planes(const FrameParams& P, cudaStream_t s);              \
   void launch_ssr_shade_hits(const FrameParams& P, cudaStream_t s);          \

@@ -80,6 +80,10 @@ struct FrameParams {
   const float* depthPad;
   const float* depthPadOrigin; // &padded(1, 1), i.e. texel (0, 0)
   int depthPadRow;             // floats per padded row = W + 2
+  // fast-build march: the same depths as one 16-byte record {t00, t10, t01, t11} per bilinear footprint (ix, iy), ix in [-1, W-1],
+  // iy in [-1, H-1]: a tap is ONE 128-bit load. (W + 1) x (H + 1) records; null: the march reads the padded floats
+  const float4* depthQuadOrigin; // record of footprint (0, 0)
+  int depthQuadRow;              // records per row = W + 1
 };
 
 struct ConvolveParams {
