@@ -1,0 +1,277 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. Runs the REFERENCE'S OWN SHADER TEXT on the CPU: oracle/_ref/libshader_ref.so.
+//
+// The reference's per-frame path is GLSL that a Vulkan driver compiles at run time; this image has neither. What it does have
+// is g++, and GLSL's expression language is (nearly) C++'s: `make -C oracle ref` lets oracle/glsl2cpp.py rewrite each shader,
+// read where it lies under /root/reference/Shaders, into oracle/_ref/gen/*.inc (declarations and literals only, see its header),
+// and this file includes those bodies into one struct per shader stage, with oracle/glsl_compat.h standing in for the GPU
+// (types, built-ins, texture unit). The entry points below take the arguments of liboracle.so's, so a test hands both the same
+// frame and compares: the restatement (oracle/althea_oracle.cpp) against the text it restates, executed.
+//
+// What this does and does not pin. It pins the READING of the shaders: control flow, operand order, which map at which LOD,
+// every constant. It does not pin what GLSL leaves to the implementation (the rounding order inside dot / normalize / matrix
+// products, the texture filter's arithmetic): those are oracle_math.h's in both, on purpose. The bit-rot of SURVEY.md 8(c-bis)
+// is handled by the patches spelled out in oracle/Makefile (DeferredPass.frag's stale pbrMaterial call and missing
+// declarations) and by the one overload SSR.frag calls but nobody defines, added below.
+#include "glsl_compat.h"
+#include <omp.h>
+#include <vector>
+
+extern "C" {
+// the argument blocks of liboracle.so (oracle/althea_oracle.cpp), same layouts
+struct OracleGlobalUniforms { float m[6][16]; float mouseUV[2]; int32_t lightCount; uint32_t lightBufferHandle; float time, exposure; uint32_t inputMask, frameCount; };
+struct OracleGBuffer { int32_t W, H; const float* position; const float* depth; const uint16_t* normal; const uint8_t* albedo; const uint8_t* mro; };
+struct OracleIBL { const float* env; int32_t envW, envH; const float* prefiltered; int32_t preW, preH, preMips; const float* irradiance; int32_t irrW, irrH; const uint8_t* lut; int32_t lutW, lutH; };
+struct OracleLights { const float* lights; const float* shadow; int32_t shadowRes; };
+}
+static_assert(sizeof(OracleGlobalUniforms) == 416, "GlobalUniforms.h:15-31");
+
+namespace glsl {
+
+struct SsrVert : ShaderBase {
+#include "_ref/gen/ssr_vert.inc"
+};
+struct SsrFrag : ShaderBase {
+#include "_ref/gen/ssr_frag.inc"
+  // SSR.frag:44 calls reconstructPosition(uv, dRaw); the tree defines (uv) and (uv, dRaw, inverseProjection, inverseView) only
+  // (SURVEY.md 8c-bis defect 5). The missing overload can only mean the frame's own matrices:
+  vec3 reconstructPosition(vec2 uv, float dRaw) {
+    return reconstructPosition(uv, dRaw, globalUniforms[pushConstants.globalUniformsHandle].inverseProjection,
+                               globalUniforms[pushConstants.globalUniformsHandle].inverseView);
+  }
+};
+struct DeferredVert : ShaderBase {
+#include "_ref/gen/deferred_vert.inc"
+};
+struct DeferredFrag : ShaderBase {
+#include "_ref/gen/deferred_frag.inc"
+};
+struct DeferredFragLinear : ShaderBase { // -DSKIP_TONEMAP
+#include "_ref/gen/deferred_frag_linear.inc"
+};
+struct ConvolveComp : ShaderBase {
+#include "_ref/gen/glossy_convolve_comp.inc"
+};
+
+static_assert(sizeof(SsrFrag::GlobalUniforms) == 416, "the GLSL block is the C++ block (Global/GlobalUniforms.glsl:8-24)");
+
+// texture handles of the bindless heap (any distinct numbers do)
+enum { H_ENV, H_PRE, H_IRR, H_LUT, H_DEPTH, H_NORMAL, H_ALBEDO, H_MRO, H_POSITION, H_COUNT };
+
+struct Bound { // one frame's resources in the shapes the shaders index
+  sampler2D tex[H_COUNT];
+  samplerCubeArray cubes;
+  std::vector<SsrFrag::PointLight> lights;
+  Bound(const OracleGBuffer& gb, const OracleIBL* ibl, const OracleLights* li, int lightCount) {
+    using namespace oracle;
+    auto one = [](const void* p, int w, int h, Format f) { sampler2D s; s.chain = TexChain{p, w, h, 1, f}; return s; };
+    tex[H_DEPTH] = one(gb.depth, gb.W, gb.H, FMT_R32F);
+    tex[H_NORMAL] = one(gb.normal, gb.W, gb.H, FMT_RGBA16F);
+    tex[H_ALBEDO] = one(gb.albedo, gb.W, gb.H, FMT_RGBA8);
+    tex[H_MRO] = one(gb.mro, gb.W, gb.H, FMT_RGBA8);
+    tex[H_POSITION] = one(gb.position, gb.W, gb.H, FMT_RGBA32F);
+    if (ibl) { // run-time samplers of the maps: CLAMP_TO_EDGE (Src/ImageBasedLighting.cpp:469-475)
+      tex[H_ENV] = one(ibl->env, ibl->envW, ibl->envH, FMT_RGBA32F);
+      tex[H_PRE].chain = TexChain{ibl->prefiltered, ibl->preW, ibl->preH, ibl->preMips, FMT_RGBA32F};
+      tex[H_IRR] = one(ibl->irradiance, ibl->irrW, ibl->irrH, FMT_RGBA32F);
+      tex[H_LUT] = one(ibl->lut, ibl->lutW, ibl->lutH, FMT_RGBA8);
+    }
+    if (li) {
+      cubes.layers = li->shadow; cubes.res = li->shadowRes;
+      for (int i = 0; i < lightCount; ++i) { // PointLight.h:31-34: 32-byte records {position, pad, emission, pad}
+        SsrFrag::PointLight l;
+        l.position = vec3(li->lights[i * 8 + 0], li->lights[i * 8 + 1], li->lights[i * 8 + 2]);
+        l.emission = vec3(li->lights[i * 8 + 4], li->lights[i * 8 + 5], li->lights[i * 8 + 6]);
+        lights.push_back(l);
+      }
+    }
+  }
+};
+
+// direction at a pixel: the rasteriser's interpolation of the three vertices' outputs over the full-screen triangle
+// (0,0) (2,0) (0,2) in uv: weights 1 - u/2 - v/2, u/2, v/2
+template <class Vert, class Bind> static void vertexDirections(Bind&& bind, double d[3][3]) {
+  for (int id = 0; id < 3; ++id) {
+    Vert vs;
+    bind(vs);
+    vs.gl_VertexIndex = id;
+    vs.main();
+    for (int k = 0; k < 3; ++k) d[id][k] = vs.direction[k];
+  }
+}
+static void announce(int x, int y, int W, int H, float u, float v) { gFrag.u = u; gFrag.v = v; gFrag.x = x; gFrag.y = y; gFrag.W = W; gFrag.H = H; gFrag.on = true; }
+static vec3 interpolate(const double d[3][3], double u, double v) {
+  const double l1 = 0.5 * u, l2 = 0.5 * v, l0 = 1.0 - l1 - l2;
+  return vec3((float)(l0 * d[0][0] + l1 * d[1][0] + l2 * d[2][0]), (float)(l0 * d[0][1] + l1 * d[1][1] + l2 * d[2][1]),
+              (float)(l0 * d[0][2] + l1 * d[1][2] + l2 * d[2][2]));
+}
+
+} // namespace glsl
+
+using namespace glsl;
+
+extern "C" {
+
+// Misc/ReconstructPosition.glsl:4-22 through SSR.frag's own wrapper chain
+void shaderref_reconstruct_position(const OracleGlobalUniforms* g, float u, float v, float dRaw, float* out3) {
+  SsrFrag fs;
+  SsrFrag::GlobalUniforms gu; memcpy(&gu, g, sizeof gu);
+  fs.globalUniforms = &gu;
+  fs.pushConstants.globalUniformsHandle = 0;
+  const vec3 p = fs.reconstructPosition(vec2(u, v), dRaw);
+  out3[0] = p.x; out3[1] = p.y; out3[2] = p.z;
+}
+
+// SSR.vert + SSR.frag main, then the blend-on-write onto a (0,0,0,0) clear and the RGBA16F store of the colour attachment
+// (Src/ScreenSpaceReflection.cpp:37-44, Src/GraphicsPipeline.cpp:138-154)
+void shaderref_ssr_capture(const OracleGlobalUniforms* g, const OracleGBuffer* gb, const OracleIBL* ibl, const OracleLights* li,
+                           uint16_t* outReflection, uint8_t* outHit) {
+  const int W = gb->W, H = gb->H;
+  Bound b(*gb, ibl, li, g->lightCount);
+  SsrFrag::GlobalUniforms gu; memcpy(&gu, g, sizeof gu);
+  gu.lightBufferHandle = 0;
+  SsrFrag::GlobalResources res{};
+  res.ibl.environmentMapHandle = H_ENV; res.ibl.prefilteredMapHandle = H_PRE; res.ibl.irradianceMapHandle = H_IRR; res.ibl.brdfLutHandle = H_LUT;
+  res.gBuffer.depthAHandle = H_DEPTH; res.gBuffer.normalHandle = H_NORMAL; res.gBuffer.albedoHandle = H_ALBEDO;
+  res.gBuffer.metallicRoughnessOcclusionHandle = H_MRO;
+  res.shadowMapArray = 0;
+  SsrFrag::POINT_LIGHTS pl{b.lights.data()};
+  double vd[3][3];
+  SsrVert::GlobalUniforms vgu; memcpy(&vgu, g, sizeof vgu);
+  vertexDirections<SsrVert>([&](SsrVert& vs) { vs.globalUniforms = &vgu; vs.pushConstants.globalUniformsHandle = 0; }, vd);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      SsrFrag fs;
+      fs.globalUniforms = &gu; fs.globalResources = &res; fs.pointLights = &pl;
+      fs.textureHeap = b.tex; fs.cubemapHeap = &b.cubes;
+      fs.pushConstants.globalUniformsHandle = 0; fs.pushConstants.globalResourcesHandle = 0;
+      const double u = (x + 0.5) / W, v = (y + 0.5) / H;
+      fs.inUv = vec2((float)u, (float)v);
+      announce(x, y, W, H, fs.inUv.x, fs.inUv.y);
+      fs.inDirection = interpolate(vd, u, v);
+      fs.gl_FragCoord = vec4(x + 0.5f, y + 0.5f, 0.0f, 1.0f);
+      fs.main();
+      const vec4 c = fs.reflectedColor;
+      const size_t idx = (size_t)y * W + x;
+      outReflection[idx * 4 + 0] = oracle::floatToHalf(c.x * c.w);
+      outReflection[idx * 4 + 1] = oracle::floatToHalf(c.y * c.w);
+      outReflection[idx * 4 + 2] = oracle::floatToHalf(c.z * c.w);
+      outReflection[idx * 4 + 3] = oracle::floatToHalf(c.w);
+      if (outHit) outHit[idx] = c.w != 0.0f;
+    }
+}
+
+// SSRGlossyConvolve.comp main, dispatched as ReflectionBuffer::convolveReflectionBuffer does (Src/ReflectionBuffer.cpp:224-278):
+// for mip L = 1.. : source = single-mip view of L - 1, target = L, width / height of L, direction (0,1) for odd L, (1,0) for even
+void shaderref_glossy_convolve(uint16_t* mips, int W, int H, int mipCount) {
+  oracle::TexChain ch{mips, W, H, mipCount, oracle::FMT_RGBA16F};
+  for (int level = 1; level < mipCount; ++level) {
+    const oracle::Tex src = ch.level(level - 1), dst = ch.level(level);
+    sampler2D s; s.chain = oracle::TexChain{src.data, src.w, src.h, 1, oracle::FMT_RGBA16F};
+    image2D img; img.texels = (uint16_t*)dst.data; img.w = dst.w; img.h = dst.h;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < dst.h; ++y)
+      for (int x = 0; x < dst.w; ++x) {
+        ConvolveComp cs;
+        cs.samplerHeap = &s; cs.imageHeap = &img;
+        cs.pushConstants.srcMipTexHandle = 0; cs.pushConstants.targetMipImgHandle = 0;
+        cs.pushConstants.width = (uint)dst.w; cs.pushConstants.height = (uint)dst.h;
+        cs.pushConstants.direction = (level & 1) ? vec2(0.0f, 1.0f) : vec2(1.0f, 0.0f);
+        cs.pushConstants.roughness = 0.0f;
+        cs.gl_GlobalInvocationID = uvec3((uint)x, (uint)y, 0u);
+        cs.main();
+      }
+  }
+}
+
+} // extern "C"
+
+template <class Frag> static void bindDeferred(Frag& fs, Bound& b, typename Frag::GlobalUniforms* gu, typename Frag::POINT_LIGHTS* pl, const sampler2D* refl) {
+  fs.globalUniforms = gu; fs.pointLights = pl;
+  fs.environmentMap = b.tex[H_ENV]; fs.prefilteredMap = b.tex[H_PRE]; fs.irradianceMap = b.tex[H_IRR]; fs.brdfLut = b.tex[H_LUT];
+  fs.gBufferPosition = b.tex[H_POSITION]; fs.gBufferNormal = b.tex[H_NORMAL]; fs.gBufferAlbedo = b.tex[H_ALBEDO];
+  fs.gBufferMetallicRoughnessOcclusion = b.tex[H_MRO];
+  if (refl) fs.reflectionBuffer = *refl;
+  fs.shadowMapArray = b.cubes;
+}
+
+extern "C" {
+
+// computeSSAO (SSAO.glsl:31-84) seeded as DeferredPass.frag:42 seeds it and called as :72 calls it; count = 24 (1 - result)
+void shaderref_ssao(const OracleGlobalUniforms* g, const OracleGBuffer* gb, uint8_t* outCount) {
+  const int W = gb->W, H = gb->H;
+  Bound b(*gb, nullptr, nullptr, 0);
+  DeferredFrag::GlobalUniforms gu; memcpy(&gu, g, sizeof gu);
+  DeferredFrag::POINT_LIGHTS pl{nullptr};
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const size_t idx = (size_t)y * W + x;
+      DeferredFrag fs;
+      bindDeferred(fs, b, &gu, &pl, nullptr);
+      fs.gl_FragCoord = vec4(x + 0.5f, y + 0.5f, 0.0f, 1.0f);
+      fs.uv = vec2((float)((x + 0.5) / W), (float)((y + 0.5) / H));
+      announce(x, y, W, H, fs.uv.x, fs.uv.y);
+      fs.seed = uvec2(fs.gl_FragCoord.xy);                          // DeferredPass.frag:42
+      const vec4 position = texture(fs.gBufferPosition, fs.uv).rgba; // :44
+      if (position.a == 0.0f) { outCount[idx] = 255; continue; }      // :45 (the pass never calls computeSSAO there)
+      const vec3 normal = normalize(texture(fs.gBufferNormal, fs.uv).xyz); // :55
+      const float ao = fs.computeSSAO(fs.uv, position.xyz, normal);  // :72
+      outCount[idx] = (uint8_t)lrintf((1.0f - ao) * 24.0f);
+    }
+}
+
+} // extern "C"
+
+// DeferredPass.vert + DeferredPass.frag main (patched per R1 / R2, oracle/Makefile); flags & 1 = SKIP_TONEMAP
+template <class Frag> static void deferred(const OracleGlobalUniforms* g, const OracleGBuffer* gb, const OracleIBL* ibl, const OracleLights* li,
+                                           const uint16_t* reflectionMips, int reflMipCount, float* outColor) {
+  const int W = gb->W, H = gb->H;
+  Bound b(*gb, ibl, li, g->lightCount);
+  typename Frag::GlobalUniforms gu; memcpy(&gu, g, sizeof gu);
+  typename Frag::POINT_LIGHTS pl;
+  static_assert(sizeof(typename Frag::PointLight) == sizeof(SsrFrag::PointLight), "same struct text");
+  pl.pointLightArr = reinterpret_cast<typename Frag::PointLight*>(b.lights.data());
+  sampler2D refl; refl.chain = oracle::TexChain{reflectionMips, W, H, reflMipCount, oracle::FMT_RGBA16F};
+  double vd[3][3];
+  DeferredVert::GlobalUniforms vgu; memcpy(&vgu, g, sizeof vgu);
+  vertexDirections<DeferredVert>([&](DeferredVert& vs) { vs.globalUniforms = &vgu; }, vd);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      Frag fs;
+      bindDeferred(fs, b, &gu, &pl, &refl);
+      const double u = (x + 0.5) / W, v = (y + 0.5) / H;
+      fs.uv = vec2((float)u, (float)v);
+      announce(x, y, W, H, fs.uv.x, fs.uv.y);
+      fs.direction = interpolate(vd, u, v);
+      fs.gl_FragCoord = vec4(x + 0.5f, y + 0.5f, 0.0f, 1.0f);
+      fs.main();
+      float* o = outColor + ((size_t)y * W + x) * 4;
+      o[0] = fs.outColor.x; o[1] = fs.outColor.y; o[2] = fs.outColor.z; o[3] = fs.outColor.w;
+    }
+}
+extern "C" {
+
+void shaderref_deferred_shade(const OracleGlobalUniforms* g, const OracleGBuffer* gb, const OracleIBL* ibl, const OracleLights* li,
+                              const uint16_t* reflectionMips, int reflMipCount, uint32_t flags, float* outColor) {
+  if (flags & 1u) deferred<DeferredFragLinear>(g, gb, ibl, li, reflectionMips, reflMipCount, outColor);
+  else deferred<DeferredFrag>(g, gb, ibl, li, reflectionMips, reflMipCount, outColor);
+}
+
+// DeferredPass.vert's direction at every pixel centre (3 floats per pixel)
+void shaderref_view_directions(const OracleGlobalUniforms* g, int W, int H, float* out) {
+  double vd[3][3];
+  DeferredVert::GlobalUniforms vgu; memcpy(&vgu, g, sizeof vgu);
+  vertexDirections<DeferredVert>([&](DeferredVert& vs) { vs.globalUniforms = &vgu; }, vd);
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const vec3 d = interpolate(vd, (x + 0.5) / W, (y + 0.5) / H);
+      float* o = out + ((size_t)y * W + x) * 3;
+      o[0] = d.x; o[1] = d.y; o[2] = d.z;
+    }
+}
+
+void shaderref_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
+} // extern "C"
