@@ -226,7 +226,7 @@ struct sampler2D {
   oracle::Address address = oracle::ADDR_CLAMP;
 };
 struct samplerCubeArray { const float* layers = nullptr; int res = 0; }; // R32F, layer = 6 * cube + face
-struct image2D { uint16_t* texels = nullptr; int w = 0, h = 0; };        // RGBA16F storage image
+struct image2D { uint16_t* texels = nullptr; float* texels32 = nullptr; int w = 0, h = 0; }; // RGBA16F (or RGBA32F) storage image
 inline vec4 fromV4(oracle::V4 v) { return vec4(v.x, v.y, v.z, v.w); }
 // Rule A3: a fragment's uv is its pixel centre ((x + .5) / W, (y + .5) / H), and a fetch AT THAT uv from an image of
 // the frame's size returns the pixel's own texel exactly: a texture unit's fixed-point weights (8 sub-texel bits) are 0 there,
@@ -263,7 +263,8 @@ inline vec4 texture(const samplerCubeArray& s, const vec4& q) { // Vulkan 1.3 sp
   const float* p = s.layers + (size_t)layer * s.res * s.res;
   return fromV4(oracle::bilinear(oracle::Tex{p, s.res, s.res, oracle::FMT_R32F}, u, v, oracle::ADDR_CLAMP));
 }
-inline void imageStore(const image2D& img, const ivec2& p, const vec4& c) { // RGBA16F, round to nearest even
+inline void imageStore(const image2D& img, const ivec2& p, const vec4& c) { // RGBA16F: round to nearest even
+  if (img.texels32) { float* t = img.texels32 + ((size_t)p.y * img.w + p.x) * 4; t[0] = c.x; t[1] = c.y; t[2] = c.z; t[3] = c.w; return; }
   uint16_t* t = img.texels + ((size_t)p.y * img.w + p.x) * 4;
   t[0] = oracle::floatToHalf(c.x); t[1] = oracle::floatToHalf(c.y); t[2] = oracle::floatToHalf(c.z); t[3] = oracle::floatToHalf(c.w);
 }

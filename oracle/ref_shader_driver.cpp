@@ -51,6 +51,12 @@ struct DeferredFragLinear : ShaderBase { // -DSKIP_TONEMAP
 struct ConvolveComp : ShaderBase {
 #include "_ref/gen/glossy_convolve_comp.inc"
 };
+struct IrradianceComp : ShaderBase {
+#include "_ref/gen/gen_irradiance_comp.inc"
+};
+struct PrefilterComp : ShaderBase {
+#include "_ref/gen/prefilter_comp.inc"
+};
 
 static_assert(sizeof(SsrFrag::GlobalUniforms) == 416, "the GLSL block is the C++ block (Global/GlobalUniforms.glsl:8-24)");
 
@@ -270,6 +276,43 @@ void shaderref_view_directions(const OracleGlobalUniforms* g, int W, int H, floa
       float* o = out + ((size_t)y * W + x) * 3;
       o[0] = d.x; o[1] = d.y; o[2] = d.z;
     }
+}
+
+// IBL_Precompute/GenIrradianceMap.comp main at probe texels (x, y, face = 0) of an outW x outH equirect image, dispatched as
+// ImageBasedLighting.cpp:315-343 does: environment map with its blit mip chain and a REPEAT sampler (:168-174), push constants =
+// the output size
+void shaderref_ibl_irradiance(const float* chain, int W, int H, int mips, int outW, int outH, const int32_t* texels, int n, float* out) {
+  sampler2D env; env.chain = oracle::TexChain{chain, W, H, mips, oracle::FMT_RGBA32F}; env.address = oracle::ADDR_REPEAT;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int t = 0; t < n; ++t) {
+    std::vector<float> dst((size_t)outW * outH * 4, 0.0f);
+    IrradianceComp cs;
+    cs.environmentMap = env;
+    cs.irradianceMap.texels32 = dst.data(); cs.irradianceMap.w = outW; cs.irradianceMap.h = outH;
+    cs.pushConstants.width = (float)outW; cs.pushConstants.height = (float)outH;
+    const int x = texels[t * 3], y = texels[t * 3 + 1];
+    cs.gl_GlobalInvocationID = uvec3((uint)x, (uint)y, 0u);
+    cs.main();
+    memcpy(out + (size_t)t * 4, dst.data() + ((size_t)y * outW + x) * 4, 16);
+  }
+}
+// IBL_Precompute/PreFilterEnvMap.comp main at probe texels of one outW x outH level (ImageBasedLighting.cpp:351-402)
+void shaderref_ibl_prefilter(const float* chain, int W, int H, int mips, int outW, int outH, float roughness, const int32_t* texels, int n, float* out) {
+  sampler2D env; env.chain = oracle::TexChain{chain, W, H, mips, oracle::FMT_RGBA32F}; env.address = oracle::ADDR_REPEAT;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int t = 0; t < n; ++t) {
+    std::vector<float> dst((size_t)outW * outH * 4, 0.0f);
+    PrefilterComp cs;
+    cs.environmentMap = env;
+    cs.prefilteredMip.texels32 = dst.data(); cs.prefilteredMip.w = outW; cs.prefilteredMip.h = outH;
+    cs.pushConstants.envMapWidth = (float)W; cs.pushConstants.envMapHeight = (float)H;
+    cs.pushConstants.width = (float)outW; cs.pushConstants.height = (float)outH;
+    cs.pushConstants.roughness = roughness;
+    const int x = texels[t * 3], y = texels[t * 3 + 1];
+    cs.gl_GlobalInvocationID = uvec3((uint)x, (uint)y, 0u);
+    cs.main();
+    memcpy(out + (size_t)t * 4, dst.data() + ((size_t)y * outW + x) * 4, 16);
+  }
 }
 
 void shaderref_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }

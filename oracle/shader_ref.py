@@ -84,3 +84,19 @@ def view_directions(g: O.GlobalUniforms, W, H):
     out = np.zeros((H, W, 3), np.float32)
     lib().shaderref_view_directions(C.byref(g), W, H, O._p(out))
     return out
+
+
+def ibl_irradiance(chain, W, H, mips, out_w, out_h, texels):
+    """IBL_Precompute/GenIrradianceMap.comp main at probe texels (x, y, 0) -> (n, 4) float32."""
+    t, n = O._texels(texels)
+    out = np.empty((n, 4), np.float32)
+    lib().shaderref_ibl_irradiance(O._p(chain), W, H, mips, out_w, out_h, O._p(t), n, O._p(out))
+    return out
+
+
+def ibl_prefilter(chain, W, H, mips, out_w, out_h, roughness, texels):
+    """IBL_Precompute/PreFilterEnvMap.comp main (10 000 hash-RNG samples) at probe texels of one level -> (n, 4) float32."""
+    t, n = O._texels(texels)
+    out = np.empty((n, 4), np.float32)
+    lib().shaderref_ibl_prefilter(O._p(chain), W, H, mips, out_w, out_h, C.c_float(roughness), O._p(t), n, O._p(out))
+    return out

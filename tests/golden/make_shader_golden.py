@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from helpers import FrameData  # noqa: E402
+from helpers import FrameData, golden_env  # noqa: E402
 from oracle import oracle as O, shader_ref as S  # noqa: E402
 
 FRAMES = {"scene": ("scene", 128, 72), "rand": ("rand", 96, 54)}  # name -> FrameData(kind, W, H), 4 lights, 64^2 shadow cubes
@@ -33,6 +33,19 @@ def main():
         if name == "scene":
             out[name + "_color_tonemapped"] = S.deferred_shade(fr, chain, flags=0)
         out[name + "_dir"] = S.view_directions(fr.g, W, H)
+    # IBL_Precompute: GenIrradianceMap.comp and PreFilterEnvMap.comp at probe texels, in the reference's own layout (equirect output
+    # of the environment's size / of level i + 1, hash RNG, 300 x 150 and 10 000 samples) on the committed 512 x 256 environment
+    env = golden_env()
+    H, W = env.shape[:2]
+    chain, mips = O.env_mip_chain(env)
+    rng = np.random.default_rng(3)
+    tex = np.stack([rng.integers(0, W, 12), rng.integers(0, H, 12), np.zeros(12, int)], -1)
+    tex[0], tex[1], tex[2] = (0, 0, 0), (W - 1, H - 1, 0), (W // 2, 0, 0)
+    out["irr_texels"], out["irr"] = tex, S.ibl_irradiance(chain, W, H, mips, W, H, tex)
+    for i, r in enumerate((0.0, 0.25, 0.5, 0.75, 1.0)):
+        ow, oh = W >> (i + 1), H >> (i + 1)
+        tx = np.stack([rng.integers(0, ow, 8), rng.integers(0, oh, 8), np.zeros(8, int)], -1)
+        out["pre%d_texels" % i], out["pre%d" % i] = tx, S.ibl_prefilter(chain, W, H, mips, ow, oh, r, tx)
     path = os.path.join(HERE, "shader_ref.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

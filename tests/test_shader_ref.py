@@ -1,7 +1,7 @@
 """The restatement and the CUDA path against the REFERENCE'S OWN SHADER TEXT, executed.
 
 oracle/_ref/libshader_ref.so runs SSR.vert/.frag, DeferredPass.vert/.frag (with SSAO.glsl and PBR/PBRMaterial.glsl),
-SSRGlossyConvolve.comp and Misc/ReconstructPosition.glsl on the CPU: oracle/glsl2cpp.py rewrites the GLSL where it lies under
+SSRGlossyConvolve.comp, Misc/ReconstructPosition.glsl and the two IBL_Precompute integrators on the CPU: oracle/glsl2cpp.py rewrites the GLSL where it lies under
 /root/reference/Shaders (declarations, literals, constructor braces; never an expression) and oracle/glsl_compat.h supplies the
 language. What it yields on two seeded frames is committed as tests/golden/shader_ref.npz (make_shader_golden.py), so these tests
 run wherever the tree goes; where the reference is mounted the library is rebuilt and checked against the fixture as well.
@@ -18,7 +18,7 @@ import tempfile
 import numpy as np
 import pytest
 
-from helpers import GOLDEN, ROOT, FrameData, GpuFrame, half_to_float
+from helpers import GOLDEN, ROOT, FrameData, GpuFrame, golden_env, half_to_float
 
 FRAMES = {"scene": ("scene", 128, 72), "rand": ("rand", 96, 54)}
 MASK_BAR = 1e-3
@@ -65,6 +65,19 @@ def test_restatement_equals_the_executed_shader_text(oracle, golden, frames, nam
         assert _close(got, want, 1e-5).mean() >= 0.999
 
 
+def test_ibl_integrators_equal_the_executed_shader_text(oracle, golden):
+    """GenIrradianceMap.comp (300 x 150 samples) and PreFilterEnvMap.comp (10 000 hash-RNG samples, the five roughnesses) at probe
+    texels of the reference's own equirect layout: every float of the restatement is the shader's."""
+    env = golden_env()
+    H, W = env.shape[:2]
+    chain, mips = oracle.env_mip_chain(env)
+    assert np.array_equal(oracle.ibl_irradiance(chain, W, H, mips, W, H, golden["irr_texels"]), golden["irr"])
+    for i, r in enumerate((0.0, 0.25, 0.5, 0.75, 1.0)):
+        got = oracle.ibl_prefilter(chain, W, H, mips, W >> (i + 1), H >> (i + 1), r, golden["pre%d_texels" % i])
+        assert np.array_equal(got, golden["pre%d" % i]), r
+        assert np.isfinite(got).all() and got[:, :3].max() > 0.05
+
+
 def test_view_direction_of_the_vertex_stage(golden, frames):
     """DeferredPass.vert's varying at the pixel centres == the closed form every kernel evaluates."""
     fd = frames["scene"]
@@ -93,6 +106,10 @@ def test_live_library_reproduces_the_fixture(oracle, golden, frames):
     r2, h2, _ = oracle.ssr_capture(fr2)
     assert np.array_equal(S.glossy_convolve(r2), oracle.glossy_convolve(r2))
     assert np.mean(S.ssr_capture(fr2)[1] != h2) <= 2 * MASK_BAR
+    env = golden_env()
+    chain, mips = oracle.env_mip_chain(env)
+    assert np.array_equal(S.ibl_irradiance(chain, 512, 256, mips, 512, 256, golden["irr_texels"][:3]), golden["irr"][:3])
+    assert np.array_equal(S.ibl_prefilter(chain, 512, 256, mips, 128, 64, 0.25, golden["pre1_texels"][:3]), golden["pre1"][:3])
     # Misc/ReconstructPosition.glsl: the restatement fuses dRaw (far - near) - far (one FFMA, as GPU compilers emit it); the text
     # run by g++ is unfused, and the cancellation shows: agreement to ~1e-3 relative only, which is why the choice is pinned
     p0, p1 = oracle.reconstruct_position(fr.g, 0.3, 0.6, 0.9991), S.reconstruct_position(fr.g, 0.3, 0.6, 0.9991)
