@@ -430,8 +430,10 @@ _CPU_INPUTS = {}
 
 
 def cpu_baseline_sample(repeats: int = 1):
-    """The oracle (CPU port of the reference's GLSL) on a bounded sample of the same workload, all host threads: one 1280x720
-    view of the same S-scene with the workload's own 16 lights and 256^2 shadow cubes (per-pixel cost is the workload's)."""
+    """The reference's algorithm on the host CPU on a bounded sample of the same workload, all host threads: one 1280x720 view of
+    the same S-scene with the workload's own 16 lights and 256^2 shadow cubes (per-pixel cost is the workload's). `kind` says what
+    ran: "reference" = the reference's own shader text executed by oracle/_ref/libshader_ref.so, "port" = the oracle (when that
+    library did not travel); `port_value` is the oracle's rate either way."""
     import numpy as np
     import torch
 
@@ -463,22 +465,46 @@ def cpu_baseline_sample(repeats: int = 1):
         _CPU_INPUTS["frame"] = O.Frame(og, sw, sh, gbd["position"], gbd["depth"], gbd["normal"], gbd["albedo"], gbd["mro"], env, pre, (256, 128), 5, irr, lut,
                                        lights_t.cpu().numpy(), cubes, SHADOW_RES)
     fr = _CPU_INPUTS["frame"]
-    times = []
-    for _ in range(repeats):
-        t0 = time.perf_counter()
+    # oracle/_ref/libshader_ref.so = the reference's own shader text run on the CPU (oracle/ref_shader_driver.cpp): when it is there (it
+    # is built where /root/reference is mounted and travels with the tree) it IS the reference arm; the port is timed beside it
+    from oracle import shader_ref as S
+    use_text = S.available()
+    S_threads = len(os.sched_getaffinity(0))
+
+    def run_port():
         refl, hit, _ = O.ssr_capture(fr)
         ch = O.glossy_convolve(refl)
         O.deferred_shade(fr, ch, 5, O.SKIP_TONEMAP, None)  # SSAO computed inside, as the shader does
-        times.append(time.perf_counter() - t0)
-    t = min(times)
-    return {"value": sw * sh / t / 1e6, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
-            "sample": "1 view of the same S-scene at 1280x720 (1/9 of a 4K view), 16 lights, 256^2 shadow cubes; %d run(s), best %.2f s" % (repeats, t),
-            "seconds": t}
+
+    def run_text():
+        refl, hit = S.ssr_capture(fr)          # SSR.vert + SSR.frag main
+        ch = S.glossy_convolve(refl)           # SSRGlossyConvolve.comp x 4
+        S.deferred_shade(fr, ch, 5, O.SKIP_TONEMAP)  # DeferredPass.vert + .frag main (computeSSAO inside)
+
+    def best(fn):
+        times = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            fn()
+            times.append(time.perf_counter() - t0)
+        return min(times)
+
+    t_port = best(run_port)
+    if use_text:
+        S.lib().shaderref_set_num_threads(S_threads)
+        t = best(run_text)
+    else:
+        t = t_port
+    what = "the reference's GLSL text run on the CPU (oracle/_ref/libshader_ref.so)" if use_text else "the CPU port of the oracle"
+    return {"value": sw * sh / t / 1e6, "unit": UNIT, "cores": O.num_threads(), "kind": "reference" if use_text else "port",
+            "sample": "%s: 1 view of the same S-scene at 1280x720 (1/9 of a 4K view), 16 lights, 256^2 shadow cubes; %d run(s), best %.2f s" % (what, repeats, t),
+            "port_value": sw * sh / t_port / 1e6, "seconds": t}
 
 
 def main_reference(args):
-    """--impl reference: the reference's own algorithm on the host CPU. The reference's path is GLSL + Vulkan and cannot be
-    compiled or run here (no Vulkan loader / lavapipe / glslc), so this is the oracle port, all host threads. A step is
+    """--impl reference: the reference's own algorithm on the host CPU. The reference's path is GLSL + Vulkan and cannot run here as
+    a Vulkan program (no loader / lavapipe / glslc); what runs is its shader text, compiled as C++ into
+    oracle/_ref/libshader_ref.so (kind "reference"), or the oracle port where that library is absent, all host threads. A step is
     a bounded sample of the workload (one 1280x720 view of the 3840x2160 views: the metric is per pixel); exactly --warmup
     untimed and --steps timed samples."""
     rank = int(os.environ.get("RANK", "0"))

@@ -1,8 +1,12 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity for the per-frame stages is
-// UNPINNED by the reference: it ships no fixture, test or golden image for SSAO, SSR, the glossy
-// convolve or the deferred shading. The authority is the GLSL text, read as
-// reconciled in SURVEY.md 8(c-bis) R1-R7. The IBL half (althea_oracle_ibl.cpp) IS pinned by the
-// reference's shipped Content/PrecomputedMaps.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). The reference ships no fixture, test or golden image for SSAO, SSR,
+// the glossy convolve or the deferred shading; the authority is the GLSL text, read as reconciled in
+// SURVEY.md 8(c-bis) R1-R7. Round 2 pins this restatement against THAT TEXT, EXECUTED: oracle/_ref/libshader_ref.so runs the
+// reference's shaders on the CPU (oracle/glsl2cpp.py rewrites them where they lie, oracle/glsl_compat.h supplies the language),
+// and tests/test_shader_ref.py holds every function below to what the text yields (SSAO counts and the convolve levels bit
+// for bit, SSR hit masks within 0.1 %, colour within 2e-4; vectors committed as tests/golden/shader_ref.npz). What stays
+// unpinned is what GLSL leaves to the implementation and no run of the reference on a GPU is available for: the rounding
+// order inside built-ins and the texture filter's arithmetic (rules A1-A11). The IBL half (althea_oracle_ibl.cpp) is pinned
+// twice: by the executed text and by the reference's shipped Content/PrecomputedMaps.
 //
 // Per-frame stages of Althea's deferred screen-space path, restated on the CPU:
 //   oracle_ssr_capture      <- Shaders/SSR.vert:15-23, Shaders/SSR.frag:42-149,
