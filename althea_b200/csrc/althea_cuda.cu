@@ -70,6 +70,9 @@ struct althea_cuda_ctx {
   std::map<cudaStream_t, Scratch> scratch;
   struct RasterScratch* raster = nullptr; // scratch of the rasterising producers (draw_gbuffer / draw_shadow_cubes)
   unsigned long long* gatherCounter = nullptr; // device counters (4) of the ALTHEA_CTX_SSAO_COUNT_TAPS diagnostic
+  // SSAO ray-direction table (FrameParams::ssaoDirs): read-only once built, shared by every stream; rebuilt when a larger frame arrives
+  void* ssaoDirs = nullptr; int ssaoDirRow = 0, ssaoDirRows = 0; bool ssaoDirsParity = false; // (which build's arithmetic filled it)
+  bool ssaoDirTable = true; // ALTHEA_SSAO_DIR_TABLE=0 in the environment: hash inline instead (A/B switch)
   // timing
   bool timing = false;
   std::vector<TimingEntry> pending;
@@ -471,6 +474,7 @@ int althea_cuda_create(althea_cuda_ctx** out_ctx, int cuda_device, const uint8_t
     delete ctx;
     return fail(nullptr, ALTHEA_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
+  if (const char* t = getenv("ALTHEA_SSAO_DIR_TABLE")) ctx->ssaoDirTable = atoi(t) != 0; // tuning / A-B: 0 = hash the ray directions inline
   *out_ctx = ctx;
   return ALTHEA_OK;
 }
@@ -491,6 +495,7 @@ void althea_cuda_destroy(althea_cuda_ctx* ctx) {
     for (void* p : {kv.second.ao, kv.second.position, kv.second.quad, kv.second.plane, kv.second.depthPad, kv.second.ssrPlane, kv.second.ssrHits})
       if (p) cudaFree(p);
   if (ctx->gatherCounter) cudaFree(ctx->gatherCounter);
+  if (ctx->ssaoDirs) cudaFree(ctx->ssaoDirs);
   freeRasterScratch(ctx->raster);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -941,6 +946,29 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
       if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(gather counter): %s", cudaGetErrorString(e)); }
     }
     P.gatherCounter = ctx->gatherCounter;
+  }
+  P.ssaoDirs = nullptr;
+  P.ssaoDirRow = 0;
+  if (cull && ctx->ssaoDirTable) {
+    // seeds reach (W - 1 + 3 * 23, H - 1 + 3 * 23); rows padded to whole 128-byte lines. Built on the ctx's own stream and waited
+    // for (once per frame size): the table is shared by every stream a host renders on, and a rebuild must not free entries a
+    // frame in flight still reads
+    const int row = (P.W + 72 + 7) & ~7, rows = P.H + 72;
+    if (row > ctx->ssaoDirRow || rows > ctx->ssaoDirRows || parity != ctx->ssaoDirsParity) { // (the two builds normalise differently)
+      const int nrow = std::max(row, ctx->ssaoDirRow), nrows = std::max(rows, ctx->ssaoDirRows);
+      CUDA_TRY(ctx, cudaDeviceSynchronize());
+      if (ctx->ssaoDirs) cudaFree(ctx->ssaoDirs);
+      ctx->ssaoDirs = nullptr; ctx->ssaoDirRow = ctx->ssaoDirRows = 0;
+      cudaError_t e = cudaMalloc(&ctx->ssaoDirs, (size_t)nrow * nrows * 16);
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(ssao direction table, %zu bytes): %s", (size_t)nrow * nrows * 16, cudaGetErrorString(e)); }
+      parity ? althea_parity::launch_ssao_dirs(static_cast<float4*>(ctx->ssaoDirs), nrow, nrows, ctx->stream)
+             : althea_fast::launch_ssao_dirs(static_cast<float4*>(ctx->ssaoDirs), nrow, nrows, ctx->stream);
+      ctx->launches += 1;
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      ctx->ssaoDirRow = nrow; ctx->ssaoDirRows = nrows; ctx->ssaoDirsParity = parity;
+    }
+    P.ssaoDirs = static_cast<const float4*>(ctx->ssaoDirs);
+    P.ssaoDirRow = ctx->ssaoDirRow;
   }
   cudaStream_t stream;
   if ((rc = beginWork(ctx, sync, &stream))) return rc;

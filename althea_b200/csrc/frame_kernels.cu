@@ -1747,13 +1747,32 @@ __global__ void __launch_bounds__(256) ssao_planes_finer_kernel(const __grid_con
 
 // the ray of one pixel: SSAO.glsl:36-45 (the hash RNG's state after k draws is seed + k, so ray r starts at seed + 3 r)
 struct SsaoRay { V3 rayDir, perpRef; V2 uvEnd; };
-ADEV SsaoRay ssaoRay(const FrameParams& P, const TangentFrame& tbn, V3 worldPos, V3 normal, int px, int py, int ray) {
+// tangent-space direction of the ray whose RNG state starts at (sx, sy): three draws, SSAO.glsl:37-38
+ADEV V3 ssaoLocalDir(uint32_t sx, uint32_t sy) {
   HashRng rng;
-  rng.sx = (uint32_t)px + 3u * (uint32_t)ray;
-  rng.sy = (uint32_t)py + 3u * (uint32_t)ray;
+  rng.sx = sx;
+  rng.sy = sy;
   const float x0 = rng.next(), x1 = rng.next(), x2 = rng.next();
+  return normalize3(mk3(2.0f * x0 - 1.0f, 2.0f * x1 - 1.0f, x2));
+}
+// The same for every seed a frame of this size can reach, once (FrameParams::ssaoDirs): the values the inline code computes, in
+// this build's arithmetic, so a kernel reading them counts exactly what it would count hashing.
+__global__ void __launch_bounds__(256) ssao_dirs_kernel(float4* dirs, int row, int rows) {
+  const int a = blockIdx.x * 32 + (threadIdx.x & 31), b = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (a >= row || b >= rows) return;
+  const V3 d = ssaoLocalDir((uint32_t)a, (uint32_t)b);
+  dirs[(size_t)b * row + a] = make_float4(d.x, d.y, d.z, 0.0f);
+}
+ADEV SsaoRay ssaoRay(const FrameParams& P, const TangentFrame& tbn, V3 worldPos, V3 normal, int px, int py, int ray) {
+  V3 local;
+  if (P.ssaoDirs) { // coalesced: the lanes of a warp read two runs of 16 neighbouring entries
+    const float4 t = __ldg(P.ssaoDirs + ((size_t)(py + 3 * ray) * P.ssaoDirRow + (px + 3 * ray)));
+    local = mk3(t.x, t.y, t.z);
+  } else {
+    local = ssaoLocalDir((uint32_t)px + 3u * (uint32_t)ray, (uint32_t)py + 3u * (uint32_t)ray);
+  }
   SsaoRay r;
-  r.rayDir = frameApply(tbn, normalize3(mk3(2.0f * x0 - 1.0f, 2.0f * x1 - 1.0f, x2)));
+  r.rayDir = frameApply(tbn, local);
   r.uvEnd = projectUv(P, worldPos + r.rayDir * 0.5f);
   r.perpRef = normalize3(cross3(cross3(r.rayDir, normal), r.rayDir));
   return r;
@@ -1943,7 +1962,9 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
   const int rays = __any_sync(0xffffffffu, covered) ? 24 : 0;
   for (int ray = 0; ray < rays; ++ray) {
     const SsaoRay R = ssaoRay(P, tbn, worldPos, normal, x, y, ray);
-    const int n = covered ? ssaoTapCount(u0, v0, R.uvEnd) : 0;
+    // the bisection runs for the warp only when some lane's ray ends off the screen (a vote: tiles away from the border skip it)
+    int n = covered ? 12 : 0;
+    if (__any_sync(0xffffffffu, covered && outside01(R.uvEnd.x, R.uvEnd.y))) n = covered ? ssaoTapCount(u0, v0, R.uvEnd) : 0;
     rayState[0][tid] = R.uvEnd.x; rayState[1][tid] = R.uvEnd.y;
     rayState[2][tid] = R.perpRef.x; rayState[3][tid] = R.perpRef.y; rayState[4][tid] = R.perpRef.z;
     rayState[5][tid] = R.rayDir.x; rayState[6][tid] = R.rayDir.y; rayState[7][tid] = R.rayDir.z;
@@ -2242,6 +2263,9 @@ void launch_ssao_cull(const FrameParams& P, cudaStream_t s) {
   const dim3 grid((unsigned)((P.W + 15) / 16), (unsigned)((P.y1 - P.y0 + 15) / 16));
   if (P.gatherCounter) ssao_cull_kernel<true><<<grid, 256, 0, s>>>(P);
   else ssao_cull_kernel<false><<<grid, 256, 0, s>>>(P);
+}
+void launch_ssao_dirs(float4* dirs, int row, int rows, cudaStream_t s) {
+  ssao_dirs_kernel<<<dim3((unsigned)((row + 31) / 32), (unsigned)((rows + 7) / 8)), 256, 0, s>>>(dirs, row, rows);
 }
 void launch_ssao_exact(const FrameParams& P, cudaStream_t s) { ssao_exact_kernel<<<tileGrid(P.W, P.y1 - P.y0), 256, 0, s>>>(P); }
 void launch_ssao_quads(const FrameParams& P, cudaStream_t s) {

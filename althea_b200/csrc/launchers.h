@@ -18,6 +18,7 @@
   void launch_ssao_quads(const FrameParams& P, cudaStream_t s);              \
   void launch_ssao_planes(const FrameParams& P, cudaStream_t s, bool coarsest); \
   void launch_ssao_cull(const FrameParams& P, cudaStream_t s);               \
+  void launch_ssao_dirs(float4* dirs, int row, int rows, cudaStream_t s);    \
   void launch_ssao_exact(const FrameParams& P, cudaStream_t s);              \
   void launch_deferred_shade(const FrameParams& P, cudaStream_t s);          \
   }

@@ -66,6 +66,11 @@ struct FrameParams {
   unsigned* ssaoTileList;       // [0]: number of 16 x 16 tiles the cull kernel handed over to the march kernel, [1 + k]: tile ids
   unsigned* ssaoPlaneStats;     // [0]: level-2 records inside the image, [1]: those that can decide (zeroed by ssao_quads_kernel)
   float* ssaoRecip;             // W x H: reciprocal eye depth of every position texel (NaN: off the camera model), by ssao_quads_kernel
+  // SSAO ray directions (engine scratch, built once per frame size): computeSSAO seeds its hash RNG with the pixel's coordinates
+  // (DeferredPass.frag:42) and ray r starts at seed + 3 r, so the tangent-space direction normalize(2 xi.xy - 1, xi.z) of
+  // (pixel, ray) is a function of (px + 3 r, py + 3 r) alone, the same in every frame: entry (a, b) holds it for seed (a, b). Null: hashed inline
+  const float4* ssaoDirs;
+  int ssaoDirRow;               // entries per row
   unsigned long long* gatherCounter; // diagnostics (ALTHEA_CTX_SSAO_COUNT_TAPS): proxy records gathered by the SSAO march; else null
   // SSR sign test: one plane record {alpha, beta, gamma, r} of reciprocal eye depth per block of
   // (1 << ssrPlaneShift)^2 depth texels, the whole frame in kSsrPlaneStride x kSsrPlaneRows records (r = +inf outside). Null: plain march

@@ -306,6 +306,34 @@ def test_ssao_proxy_equals_exact_taps_on_hostile_positions(request, which):
     assert (b[b < 255] > 0).mean() > 0.02
 
 
+@pytest.mark.parametrize("parity", [True, False])
+def test_ssao_direction_table_is_what_the_hash_yields(lib_built, parity):
+    """The SSAO rays' tangent-space directions come from a table built once per frame size (a function of pixel + 3 ray alone,
+    params.h); ALTHEA_SSAO_DIR_TABLE=0 hashes them inline as the shader does. Same counts bit for bit in both builds, also after the
+    table has been rebuilt for a larger frame."""
+    from althea_b200 import _capi, engine
+    os.environ["ALTHEA_SSAO_DIR_TABLE"] = "0"
+    try:
+        ctx_inline = engine.Context(0, parity_math=parity)
+    finally:
+        del os.environ["ALTHEA_SSAO_DIR_TABLE"]
+    ctx_table = engine.Context(0, parity_math=parity)
+    try:
+        for kind, W, H in (("rand", 83, 47), ("scene", 200, 113)):  # the second frame is larger: the table grows
+            fd = FrameData(kind, W, H, n_lights=0)
+            counts = []
+            for ctx in (ctx_inline, ctx_table):
+                gf = GpuFrame(ctx, fd)
+                gf.ssr.convolveReflectionBuffer()
+                gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP)
+                counts.append(gf.ao_counts().copy())
+            assert (counts[0][counts[0] < 255] > 0).mean() > 0.02
+            assert np.array_equal(counts[0], counts[1])
+    finally:
+        ctx_inline.close()
+        ctx_table.close()
+
+
 # ---- size-independent properties at the full 4K size (BASELINE configs C3/C5) -------------------------------------------
 def test_properties_at_4k(ctx_fast):
     import torch
