@@ -956,8 +956,10 @@ int althea_cuda_deferred_shade(althea_cuda_ctx* ctx, const althea_global_uniform
     const int row = (P.W + 72 + 7) & ~7, rows = P.H + 72;
     if (row > ctx->ssaoDirRow || rows > ctx->ssaoDirRows || parity != ctx->ssaoDirsParity) { // (the two builds normalise differently)
       const int nrow = std::max(row, ctx->ssaoDirRow), nrows = std::max(rows, ctx->ssaoDirRows);
-      CUDA_TRY(ctx, cudaDeviceSynchronize());
-      if (ctx->ssaoDirs) cudaFree(ctx->ssaoDirs);
+      if (ctx->ssaoDirs) { // a frame in flight on another stream may still read the old table
+        CUDA_TRY(ctx, cudaDeviceSynchronize());
+        cudaFree(ctx->ssaoDirs);
+      }
       ctx->ssaoDirs = nullptr; ctx->ssaoDirRow = ctx->ssaoDirRows = 0;
       cudaError_t e = cudaMalloc(&ctx->ssaoDirs, (size_t)nrow * nrows * 16);
       if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, ALTHEA_ERR_OUT_OF_MEMORY, "cudaMalloc(ssao direction table, %zu bytes): %s", (size_t)nrow * nrows * 16, cudaGetErrorString(e)); }
