@@ -965,6 +965,100 @@ template <int TW, int TH> __global__ void __launch_bounds__(256) glossy_convolve
   }
 }
 
+#ifndef ALTHEA_PARITY
+// ---- glossy convolve, fast build, exact 2 : 1 levels --------------------------------------------------------------------------
+// For a source of exactly twice the target's size the pass is a FIXED filter: texelPos / size has no half texel, so the centre tap
+// falls on the corner between source texels 2 p - 1 and 2 p (weights 1/2, 1/2) and the six offset taps land a constant distance
+// from it (+-off_k ws / w texels along x, +-off_k hs / w rows along y: `resolution` is the width for both axes), the same fractional
+// weights for every output texel. Across the filter direction every tap averages the two texels around the corner. The host folds
+// the seven taps' bilinear weights into one coefficient per source offset (FirTable, double precision); the kernels below apply
+// them: ~140 instructions per output texel instead of ~680 for seven general bilinear taps, no staging (rows are read through
+// L1, neighbouring outputs share them). Same sums in a different order: within half an ulp of the RGBA16F store of the general
+// kernel's result (tests), which the parity build keeps.
+struct FirTable {
+  int lo, hi;    // source offsets (relative to 2 p) with a non-zero coefficient: [lo, hi], inside [-12, 12]
+  float c[25];   // coefficient of offset o at c[o + 12]
+  int n;         // the non-zero ones again as a list (seven taps x two texels: at most 14)
+  int o[14];
+  float w[14];
+};
+ADEV V4 firPairAverage(const uint2* row, int c0, int c1) { // 0.5 t(c0) + 0.5 t(c1)
+  const V4 a = unpackHalf4(__ldg(row + c0)), b = unpackHalf4(__ldg(row + c1));
+  return mk4(0.5f * (a.x + b.x), 0.5f * (a.y + b.y), 0.5f * (a.z + b.z), 0.5f * (a.w + b.w));
+}
+// vertical passes (levels 1, 3): a thread owns R consecutive target rows of one column; every source row it reads feeds up to R of them
+template <int R> __global__ void __launch_bounds__(256) glossy_fir_vertical_kernel(const __grid_constant__ ConvolveParams C, const __grid_constant__ FirTable T) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y0 = C.y0 + (blockIdx.y * 8 + (threadIdx.x >> 5)) * R;
+  if (x >= C.dst.w || y0 >= C.y1) return;
+  const int ws = C.src.w, hs = C.src.h;
+  const int c0 = max(2 * x - 1, 0), c1 = min(2 * x, ws - 1);
+  V4 acc[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) acc[k] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll 4
+  for (int r = T.lo; r <= T.hi + 2 * (R - 1); ++r) { // (unrolled by four: eight row loads in flight per thread)
+    const int row = min(max(2 * y0 + r, 0), hs - 1); // CLAMP_TO_EDGE on the tap's row
+    const V4 v = firPairAverage(rowPtr<uint2>(C.src, row), c0, c1);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int o = r - 2 * k;
+      if (o >= T.lo && o <= T.hi) { // warp-uniform
+        const float c = T.c[o + 12];
+        acc[k] = mk4(fmaf(c, v.x, acc[k].x), fmaf(c, v.y, acc[k].y), fmaf(c, v.z, acc[k].z), fmaf(c, v.w, acc[k].w));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k)
+    if (y0 + k < C.y1) rowPtrW<uint2>(C.dst, y0 + k)[x] = packHalf4(acc[k]);
+}
+// horizontal passes (levels 2, 4: a sixteenth of the frame and less)
+__global__ void __launch_bounds__(256) glossy_fir_horizontal_kernel(const __grid_constant__ ConvolveParams C, const __grid_constant__ FirTable T) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = C.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= C.dst.w || y >= C.y1) return;
+  const int ws = C.src.w, hs = C.src.h;
+  const uint2* ra = rowPtr<uint2>(C.src, max(2 * y - 1, 0));
+  const uint2* rb = rowPtr<uint2>(C.src, min(2 * y, hs - 1));
+  V4 acc = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+  for (int i = 0; i < 14; ++i) { // unrolled over the list: the 28 loads of a texel are independent
+    if (i < T.n) {               // warp-uniform
+      const int col = min(max(2 * x + T.o[i], 0), ws - 1);
+      const V4 a = unpackHalf4(__ldg(ra + col)), b = unpackHalf4(__ldg(rb + col));
+      const float h = 0.5f * T.w[i];
+      acc = mk4(fmaf(h, a.x + b.x, acc.x), fmaf(h, a.y + b.y, acc.y), fmaf(h, a.z + b.z, acc.z), fmaf(h, a.w + b.w, acc.w));
+    }
+  }
+  rowPtrW<uint2>(C.dst, y)[x] = packHalf4(acc);
+}
+// the seven taps of SSRGlossyConvolve.comp:41-52 as coefficients per source offset; false when a tap falls outside [-12, 12]
+static bool firTable(const ConvolveParams& C, FirTable* T) {
+  const double off[7] = {0.0, 1.411764705882353, -1.411764705882353, 3.2941176470588234, -3.2941176470588234, 5.176470588235294, -5.176470588235294};
+  const double wt[7] = {0.1964825501511404, 0.2969069646728344, 0.2969069646728344, 0.09447039785044732, 0.09447039785044732, 0.010381362401148057, 0.010381362401148057};
+  const double scale = (C.vertical ? (double)C.src.h : (double)C.src.w) / (double)C.dst.w; // source texels per unit of off / resolution
+  double c[25] = {0.0};
+  for (int t = 0; t < 7; ++t) {
+    const double p = off[t] * scale - 0.5;
+    const double o = floor(p), f = p - o;
+    if (o < -12.0 || o + 1.0 > 12.0) return false;
+    c[(int)o + 12] += wt[t] * (1.0 - f);
+    c[(int)o + 13] += wt[t] * f;
+  }
+  T->lo = 12; T->hi = -12; T->n = 0;
+  for (int i = 0; i < 25; ++i) {
+    T->c[i] = (float)c[i];
+    if (T->c[i] != 0.0f) {
+      T->lo = std::min(T->lo, i - 12); T->hi = std::max(T->hi, i - 12);
+      if (T->n == 14) return false;
+      T->o[T->n] = i - 12; T->w[T->n] = T->c[i]; ++T->n;
+    }
+  }
+  return T->lo <= T->hi;
+}
+#endif // !ALTHEA_PARITY
+
 // ---- SSAO -----------------------------------------------------------------------------------------------------------
 // computeSSAO (SSAO.glsl:31-84) counts, per pixel, the rays (24) whose 12-step screen-space march over the POSITION
 // G-buffer finds an occluder. Each march step is one bilinear RGBA32F tap whose location is effectively random over a
@@ -2216,6 +2310,21 @@ static size_t stagedWindowBytes(const ConvolveParams& C, int TW, int TH) {
   return cols * rows * 8;
 }
 void launch_glossy_convolve(const ConvolveParams& C, cudaStream_t s) {
+#ifndef ALTHEA_PARITY
+  { // exact 2 : 1 levels (every level of an even-sized chain): the fixed-filter kernels
+    static const bool general = getenv("ALTHEA_CONVOLVE_GENERAL") != nullptr; // A/B switch: the seven general bilinear taps
+    FirTable T;
+    if (!general && C.src.w == 2 * C.dst.w && C.src.h == 2 * C.dst.h && firTable(C, &T)) {
+      static const int R = getenv("ALTHEA_CONVOLVE_R") ? atoi(getenv("ALTHEA_CONVOLVE_R")) : 4; // tuning: target rows per thread
+      const unsigned gx = (unsigned)((C.dst.w + 31) / 32);
+      if (C.vertical && R == 2) glossy_fir_vertical_kernel<2><<<dim3(gx, (unsigned)((C.y1 - C.y0 + 15) / 16)), 256, 0, s>>>(C, T);
+      else if (C.vertical && R == 8) glossy_fir_vertical_kernel<8><<<dim3(gx, (unsigned)((C.y1 - C.y0 + 63) / 64)), 256, 0, s>>>(C, T);
+      else if (C.vertical) glossy_fir_vertical_kernel<4><<<dim3(gx, (unsigned)((C.y1 - C.y0 + 31) / 32)), 256, 0, s>>>(C, T);
+      else glossy_fir_horizontal_kernel<<<dim3((unsigned)((C.dst.w + 31) / 32), (unsigned)((C.y1 - C.y0 + 7) / 8)), 256, 0, s>>>(C, T);
+      return;
+    }
+  }
+#endif
   constexpr int VW = 32, VH = 32, HW = 64, HH = 16; // vertical passes want tall tiles (halo in y), horizontal ones wide tiles
   const bool aligned = (C.src.w % 2 == 0) && ((uintptr_t)C.src.ptr % 16 == 0) && (C.src.pitch % 16 == 0);
   const size_t smem = C.vertical ? stagedWindowBytes(C, VW, VH) : stagedWindowBytes(C, HW, HH);
