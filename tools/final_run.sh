@@ -10,7 +10,7 @@ python bench.py --workload mesh4k --steps 5 --warmup 2 > gpurun_out/${TAG}_bench
 python - <<P
 import json
 d=json.load(open('gpurun_out/${TAG}_bench.json'))
-print(d['value'], d['e2e']['value'], d['roofline']['binding']['frac'], {k:round(v['ms_per_frame'],3) for k,v in d['stages'].items()}, d['producers'])
+print(d['value'], d['e2e']['value'], d['roofline']['frac'], {k:round(v['ms_per_frame'],3) for k,v in d['stages'].items()}, d['producers'])
 print(open('gpurun_out/${TAG}_raster_bench.json').read().strip())
 m=json.load(open('gpurun_out/${TAG}_bench_mesh4k.json')); print('mesh4k', m['value'], m['ms_per_step'])
 P
