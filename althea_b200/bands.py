@@ -97,7 +97,7 @@ class BandPipeline:
         self.issued = []                # ("replicate" | "render" | "assemble", frame): the order the work was enqueued in
         if cuda:
             import torch
-            self._side = torch.cuda.Stream()
+            self._side = torch.cuda.Stream(priority=-1)  # collectives ahead of the render kernels that fill the SMs
 
     @staticmethod
     def _wait(works):
