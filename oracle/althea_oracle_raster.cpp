@@ -6,8 +6,12 @@
 //                                clears Src/DeferredRendering.cpp:101-106 (colour 0, depth 1)
 //   oracle_draw_shadow_cubes  <- Shaders/ShadowMapBindless.vert:33-50, Shaders/ShadowMapBindless.frag:22-42,
 //                                Src/PointLight.cpp:235-282 (one multiview pass per light, 6 views)
-// PARITY UNPINNED: the reference ships no golden G-buffer or shadow map, and fixed-function rasterisation (sub-pixel snapping,
-// derivative quads, anisotropic filtering) is implementation-defined in Vulkan. This file states the rules the CUDA path
+// PINNING. The PROGRAMMABLE stages below (vertex transform, TBN, fetchMaterial, alpha test, the three outputs; the shadow pass's
+// light-space position and depth) are pinned by the reference's own shader text, executed: with the stage hooks further down
+// installed (oracle/ref_shader_driver.cpp runs Gltf.vert / Gltf.frag / ShadowMapBindless.vert / .frag from their text) a draw
+// reproduces the plain draw bit for bit on every attachment (tests/test_shader_ref.py, vectors in tests/golden/shader_ref.npz).
+// The FIXED-FUNCTION part stays unpinned: the reference ships no golden G-buffer or shadow map, and rasterisation (sub-pixel
+// snapping, derivative quads, anisotropic filtering) is implementation-defined in Vulkan. This file states the rules the CUDA path
 // implements, in scalar form and in draw order, so that the two can be compared bit for bit on coverage, triangle ids and depth:
 //   * a fragment exists where the pixel centre is inside the triangle (top-left rule), evaluated with edge functions in
 //     2-D homogeneous coordinates (x, y, w) so triangles that cross the eye plane need no geometric clipping;
@@ -72,10 +76,26 @@ struct OraclePrim {
   OracleTex base, normal, mr;
 };
 
+// Stage hooks (oracle/ref_shader_driver.cpp installs them): the programmable stages of the two passes taken from the reference's
+// SHADER TEXT, executed, while the fixed-function part (coverage, depth test, interpolation, derivatives, blending) stays this
+// file's. A draw with hooks must reproduce the draw without them: that is the pin of the stages' restatement below.
+struct OracleStageHooks {
+  // Gltf/Gltf.vert main for vertex i of p: gl_Position, worldPosition, vertTbn (columns tangent, bitangent, normal)
+  void (*gbufferVertex)(const OraclePrim* p, uint32_t i, const float* projection, const float* view, float clip[4], float world[3], float tbn[9]);
+  // Gltf/Gltf.frag main on interpolated inputs (uv sets with their screen-space derivatives); returns 0 when the fragment is discarded
+  int (*gbufferFragment)(const OraclePrim* p, const float tbn[9], const float uvs[4][2], const float ddx[4][2], const float ddy[4][2],
+                         float outNormal[4], float outAlbedo[4], float outMro[4]);
+  // ShadowMapBindless.vert main for view `view` of the light at lightPos: gl_Position and worldPosCS
+  void (*shadowVertex)(const OraclePrim* p, uint32_t i, const float* lightPos, const float* view, const float* projection, float clip[4], float cs[3]);
+  // ShadowMapBindless.frag main: gl_FragDepth, or 0 returned on discard
+  int (*shadowFragment)(const OraclePrim* p, const float cs[3], const float uv[2], const float ddx[2], const float ddy[2], float* depth);
+};
+
 } // extern "C"
 
 namespace {
 
+const OracleStageHooks* g_hooks = nullptr;
 constexpr int kVertexFloats = 26;
 
 float srgbToLinear(int i) {
@@ -165,20 +185,39 @@ struct Tri {
   uint32_t vi[3];
   V4 world[3], clip[3];
   float cs[3][3];
+  float tbn[3][9]; // G-buffer pass: mat3(model) * tbn per vertex (Gltf.vert:59), columns tangent, bitangent, normal
   float A[3], B[3], C[3], rdet;
   bool ok;
 };
 
 // vertex stage + triangle setup for one view. viewA/viewB/off: clip = viewB ? viewB * (viewA * (world - off)) : viewA * world
-Tri setupTriangle(const OraclePrim& p, uint32_t t, const float* viewA, const float* viewB, const float* off, int W, int H) {
+// hookProj / hookView: the unmultiplied matrices of the G-buffer pass, for the vertex hook (viewA is their product there)
+Tri setupTriangle(const OraclePrim& p, uint32_t t, const float* viewA, const float* viewB, const float* off, int W, int H,
+                  const float* hookProj = nullptr, const float* hookView = nullptr) {
   Tri g;
   g.ok = false;
   for (int k = 0; k < 3; ++k) {
     const uint32_t i = p.idx[3u * t + k];
     g.vi[k] = i;
     const float* pos = p.verts + (size_t)i * kVertexFloats;
+    if (g_hooks && !viewB && g_hooks->gbufferVertex && hookProj) {
+      float c[4], w3[3];
+      g_hooks->gbufferVertex(&p, i, hookProj, hookView, c, w3, g.tbn[k]);
+      g.clip[k] = V4{c[0], c[1], c[2], c[3]};
+      g.world[k] = V4{w3[0], w3[1], w3[2], 1.0f};
+      g.cs[k][0] = g.cs[k][1] = g.cs[k][2] = 0.0f;
+      continue;
+    }
+    if (g_hooks && viewB && g_hooks->shadowVertex) {
+      float c[4];
+      g_hooks->shadowVertex(&p, i, off, viewA, viewB, c, g.cs[k]);
+      g.clip[k] = V4{c[0], c[1], c[2], c[3]};
+      g.world[k] = V4{0, 0, 0, 1};
+      continue;
+    }
     const V4 w = mulMV(p.model, pos[0], pos[1], pos[2], 1.0f);
     g.world[k] = w;
+    if (!viewB) { mulM3V(p.model, pos + 3, g.tbn[k]); mulM3V(p.model, pos + 6, g.tbn[k] + 3); mulM3V(p.model, pos + 9, g.tbn[k] + 6); }
     if (viewB) {
       const V4 c = mulMV(viewA, w.x - off[0], w.y - off[1], w.z - off[2], w.w);
       g.clip[k] = mulMV(viewB, c.x, c.y, c.z, c.w);
@@ -253,6 +292,23 @@ float fragmentAlpha(const Tri& g, const Frag& f, const OraclePrim& p) {
   return sampleTexture(p.base, V4{1, 1, 1, 1}, u.uv, u.ddx, u.ddy).w * p.baseColorFactor[3];
 }
 
+// what the rasteriser hands Gltf.frag: the interpolated TBN columns and the four uv sets with their derivatives
+void fragmentInputs(const Tri& g, const Frag& f, const OraclePrim& p, float tbn[9], float uvs[4][2], float ddx[4][2], float ddy[4][2]) {
+  const float b[3] = {f.e[0] / f.S, f.e[1] / f.S, f.e[2] / f.S};
+  for (int c = 0; c < 9; ++c) tbn[c] = 0.0f;
+  for (int q = 0; q < 3; ++q)
+    for (int c = 0; c < 9; ++c) tbn[c] += b[q] * g.tbn[q][c];
+  for (int set = 0; set < 4; ++set) {
+    const UvSample u = interpUv(g, f, p, set);
+    for (int c = 0; c < 2; ++c) { uvs[set][c] = u.uv[c]; ddx[set][c] = u.ddx[c]; ddy[set][c] = u.ddy[c]; }
+  }
+}
+bool hookedFragment(const Tri& g, const Frag& f, const OraclePrim& p, float n[4], float a[4], float m[4]) {
+  float tbn[9], uvs[4][2], ddx[4][2], ddy[4][2];
+  fragmentInputs(g, f, p, tbn, uvs, ddx, ddy);
+  return g_hooks->gbufferFragment(&p, tbn, uvs, ddx, ddy, n, a, m) != 0;
+}
+
 uint8_t unorm8(float v) {
   v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
   return (uint8_t)std::nearbyintf(v * 255.0f); // round to nearest even (default rounding mode)
@@ -261,6 +317,13 @@ uint8_t unorm8(float v) {
 } // namespace
 
 extern "C" {
+
+void oracle_set_stage_hooks(const OracleStageHooks* h) { g_hooks = h; }
+// the texture unit of the two passes, for the hooks (same filter, same level of detail from the derivatives)
+void oracle_sample_texture(const OracleTex* t, const float dflt[4], const float uv[2], const float ddx[2], const float ddy[2], float out[4]) {
+  const V4 r = sampleTexture(*t, V4{dflt[0], dflt[1], dflt[2], dflt[3]}, uv, ddx, ddy);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
 
 // Outputs (any may be null): depth W*H floats, position W*H*4 floats, normal W*H*4 floats (before the RGBA16F store),
 // albedo / mro W*H*4 bytes, triId W*H uint32 (global triangle ordinal in draw order, 0xffffffff = none).
@@ -278,7 +341,7 @@ void oracle_draw_gbuffer(const float* projection, const float* view, const Oracl
   for (int pi = 0; pi < nPrims; ++pi) {
     const OraclePrim& p = prims[pi];
     for (uint32_t t = 0; t < p.triCount; ++t) {
-      const Tri g = setupTriangle(p, t, pv, nullptr, nullptr, W, H);
+      const Tri g = setupTriangle(p, t, pv, nullptr, nullptr, W, H, projection, view);
       if (!g.ok) continue;
       // screen bounds when the whole triangle is in front of the eye (a superset, padded); the whole viewport otherwise
       int x0 = 0, y0 = 0, x1 = W - 1, y1 = H - 1;
@@ -297,7 +360,10 @@ void oracle_draw_gbuffer(const float* projection, const float* view, const Oracl
         for (int px = x0; px <= x1; ++px) {
           Frag f;
           if (!fragment(g, px, py, f)) continue;
-          if (p.alphaCutoff > 0.0f && fragmentAlpha(g, f, p) < p.alphaCutoff) continue; // discard (Gltf.frag:38-40)
+          if (p.alphaCutoff > 0.0f) { // discard (Gltf.frag:38-40)
+            float hn[4], ha[4], hm[4];
+            if (g_hooks && g_hooks->gbufferFragment ? !hookedFragment(g, f, p, hn, ha, hm) : fragmentAlpha(g, f, p) < p.alphaCutoff) continue;
+          }
           const size_t o = (size_t)py * W + px;
           if (!(f.z < zbuf[o])) continue; // VK_COMPARE_OP_LESS
           zbuf[o] = f.z;
@@ -324,23 +390,23 @@ void oracle_draw_gbuffer(const float* projection, const float* view, const Oracl
         int pi = 0;
         while (offsets[pi + 1] <= ch[k]) ++pi;
         const OraclePrim& p = prims[pi];
-        const Tri g = setupTriangle(p, ch[k] - offsets[pi], pv, nullptr, nullptr, W, H);
+        const Tri g = setupTriangle(p, ch[k] - offsets[pi], pv, nullptr, nullptr, W, H, projection, view);
         Frag f;
         fragment(g, px, py, f);
         const float b[3] = {f.e[0] / f.S, f.e[1] / f.S, f.e[2] / f.S};
         float T[3] = {0, 0, 0}, Bt[3] = {0, 0, 0}, N[3] = {0, 0, 0};
-        for (int q = 0; q < 3; ++q) { // Gltf.vert:59: vertTbn = mat3(model) * tbn
-          const float* v = p.verts + (size_t)g.vi[q] * kVertexFloats;
-          float tw[3], bw[3], nw[3];
-          mulM3V(p.model, v + 3, tw);
-          mulM3V(p.model, v + 6, bw);
-          mulM3V(p.model, v + 9, nw);
-          for (int c = 0; c < 3; ++c) { T[c] += b[q] * tw[c]; Bt[c] += b[q] * bw[c]; N[c] += b[q] * nw[c]; }
-        }
+        for (int q = 0; q < 3; ++q) // Gltf.vert:59: vertTbn = mat3(model) * tbn, interpolated
+          for (int c = 0; c < 3; ++c) { T[c] += b[q] * g.tbn[q][c]; Bt[c] += b[q] * g.tbn[q][3 + c]; N[c] += b[q] * g.tbn[q][6 + c]; }
         Layer L;
         L.pos[0] = b[0] * g.world[0].x + b[1] * g.world[1].x + b[2] * g.world[2].x;
         L.pos[1] = b[0] * g.world[0].y + b[1] * g.world[1].y + b[2] * g.world[2].y;
         L.pos[2] = b[0] * g.world[0].z + b[1] * g.world[1].z + b[2] * g.world[2].z;
+        if (g_hooks && g_hooks->gbufferFragment) { // the same fragment through Gltf.frag's own text
+          hookedFragment(g, f, p, L.n, L.a, L.m);
+          layers.push_back(L);
+          if (L.a[3] == 1.0f) break;
+          continue;
+        }
         const UvSample ub = interpUv(g, f, p, p.baseUv), um = interpUv(g, f, p, p.mrUv);
         V4 base = sampleTexture(p.base, V4{1, 1, 1, 1}, ub.uv, ub.ddx, ub.ddy);
         base.x *= p.baseColorFactor[0]; base.y *= p.baseColorFactor[1]; base.z *= p.baseColorFactor[2]; base.w *= p.baseColorFactor[3];
@@ -407,12 +473,18 @@ void oracle_draw_shadow_cubes(const float* lights, int nLights, const float* pro
             for (int px = 0; px < res; ++px) {
               Frag f;
               if (!fragment(g, px, py, f)) continue;
-              if (p.alphaCutoff > 0.0f && fragmentAlpha(g, f, p) < p.alphaCutoff) continue; // ShadowMapBindless.frag:33-38
+              const bool hooked = g_hooks && g_hooks->shadowFragment;
+              if (!hooked && p.alphaCutoff > 0.0f && fragmentAlpha(g, f, p) < p.alphaCutoff) continue; // ShadowMapBindless.frag:33-38
               const float b0 = f.e[0] / f.S, b1 = f.e[1] / f.S, b2 = f.e[2] / f.S;
               const float cx = (b0 * g.cs[0][0] + b1 * g.cs[1][0]) + b2 * g.cs[2][0];
               const float cy = (b0 * g.cs[0][1] + b1 * g.cs[1][1]) + b2 * g.cs[2][1];
               const float cz = (b0 * g.cs[0][2] + b1 * g.cs[1][2]) + b2 * g.cs[2][2];
-              const float d = std::sqrt((cx * cx + cy * cy) + cz * cz) / 1000.0f; // gl_FragDepth = length(worldPosCS) / zFar
+              float d = std::sqrt((cx * cx + cy * cy) + cz * cz) / 1000.0f; // gl_FragDepth = length(worldPosCS) / zFar
+              if (hooked) {
+                const float cs3[3] = {cx, cy, cz};
+                const UvSample u = interpUv(g, f, p, p.baseUv);
+                if (!g_hooks->shadowFragment(&p, cs3, u.uv, u.ddx, u.ddy, &d)) continue;
+              }
               float& dst = layer[(size_t)py * res + px];
               if (d >= 0.0f && d < dst) dst = d; // LESS
             }

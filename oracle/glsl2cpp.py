@@ -10,7 +10,7 @@ The rewrite is mechanical and token-level; it never touches an expression:
      included), so that every declaration appears in plain GLSL;
   3. interface declarations lose their `layout(...)` and storage qualifiers: `uniform sampler2D heap[];` -> `sampler2D* heap;`,
      `uniform Block {..} name[];` -> `struct Block {..}; Block* name;`, `in vec3 x;` -> `vec3 x;`; an unsized array member
-     `T arr[];` becomes `T* arr;`
+     `T arr[];` becomes `T* arr;`, a sized array `T a[N];` the value type `arr<T, N> a;`
   4. `out T p` / `inout T p` parameters become `T& p`, `in T p` becomes `T p`;
   5. floating-point literals get the `f` suffix (a GLSL `1.0` is a float, a C++ `1.0` a double);
   6. vector / matrix constructor calls are written with braces, `vec3(a, b, c)` -> `vec3{a, b, c}`: GLSL evaluates arguments left
@@ -65,6 +65,7 @@ def declarations(text: str) -> str:
         return "struct %s {%s}; %s%s %s;" % (name, body, name, "*" if arr else "", inst)
 
     text = re.sub(r"GLSL_DECL\s+(\w+)\s*\{([^{}]*)\}\s*(\w+)\s*(\[\s*\])?\s*;", block, text)
+    text = re.sub(r"GLSL_DECL\s+(\w+)\s+(\w+)\s*\[\s*(\d+)\s*\]\s*;", r"\1 \2[\3];", text)  # sized interface array: arrays() below
     text = re.sub(r"GLSL_DECL\s+(\w+)\s+(\w+)\s*\[\s*\]\s*;", r"\1* \2;", text)
     text = re.sub(r"GLSL_DECL\s+(\w+)\s+(\w+)\s*;", r"\1 \2;", text)
     text = re.sub(r"GLSL_DECL\s*;", "", text)  # layout(local_size_x = ..) in;
@@ -74,13 +75,18 @@ def declarations(text: str) -> str:
     return text
 
 
+def arrays(text: str) -> str:
+    """`T name[N];` -> `arr<T, N> name;`: a GLSL array is a value (assignable, copied with the struct that holds it)."""
+    return re.sub(r"\b(u?vec[234]|ivec2|mat[34]|float|int|uint)\s+(\w+)\s*\[\s*(\d+)\s*\]\s*;", r"arr<\1, \3> \2;", text)
+
+
 def parameters(text: str) -> str:
     text = re.sub(r"\b(?:inout|out)\s+(\w+)\s+(\w+)", r"\1& \2", text)
     text = re.sub(r"\bin\s+(\w+)\s+(\w+)", r"\1 \2", text)
     return text
 
 
-CTOR = re.compile(r"\b(u?vec[234]|ivec2|mat3)\s*\(")
+CTOR = re.compile(r"\b(u?vec[234]|ivec2|mat[34])\s*\(")
 
 
 def constructors(text: str) -> str:
@@ -129,7 +135,7 @@ def main(argv):
     pre = subprocess.run(["g++", "-E", "-P", "-undef", "-nostdinc", "-x", "c", "-"] + defines, input=text, capture_output=True, text=True)
     if pre.returncode != 0:
         raise SystemExit("glsl2cpp: preprocessor failed:\n" + pre.stderr)
-    text = literals(constructors(parameters(declarations(pre.stdout))))
+    text = literals(constructors(parameters(arrays(declarations(pre.stdout)))))
     os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
     with open(out, "w") as f:
         f.write("// generated by oracle/glsl2cpp.py from %s (and %d includes) -- build output, do not commit\n" % (rel, len(seen) - 1))

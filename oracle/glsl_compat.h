@@ -77,6 +77,7 @@ template <class T> struct tvec4 {
     Swz<tvec2<T>, T, 4, 0, 2> xz;
     Swz<tvec3<T>, T, 4, 0, 1, 2> xyz, rgb;
     Swz<tvec4<T>, T, 4, 0, 1, 2, 3> xyzw, rgba;
+    Swz<tvec2<T>, T, 4, 2, 1> bg;
   };
   tvec4(const tvec4& o) { x = o.x; y = o.y; z = o.z; w = o.w; }
   tvec4& operator=(const tvec4& o) { x = o.x; y = o.y; z = o.z; w = o.w; return *this; }
@@ -87,6 +88,11 @@ template <class T> struct tvec4 {
   template <class C, class D> tvec4(const tvec2<T>& a, C c, D d) { x = a.x; y = a.y; z = (T)c; w = (T)d; }
   T& operator[](int i) { return (&x)[i]; }
   const T& operator[](int i) const { return (&x)[i]; }
+};
+template <class T, int N> struct arr { // a GLSL array: a value
+  T v[N];
+  T& operator[](int i) { return v[i]; }
+  const T& operator[](int i) const { return v[i]; }
 };
 typedef tvec2<float> vec2;
 typedef tvec3<float> vec3;
@@ -201,9 +207,14 @@ struct mat3 {
 };
 struct mat4 {
   vec4 c[4];
+  mat4() {}
+  explicit mat4(float d) { c[0] = vec4(d, 0.0f, 0.0f, 0.0f); c[1] = vec4(0.0f, d, 0.0f, 0.0f); c[2] = vec4(0.0f, 0.0f, d, 0.0f); c[3] = vec4(0.0f, 0.0f, 0.0f, d); }
   vec4& operator[](int i) { return c[i]; }
   const vec4& operator[](int i) const { return c[i]; }
 };
+inline mat4 operator*(float s, const mat4& m) { mat4 r; for (int i = 0; i < 4; ++i) r[i] = s * m[i]; return r; }
+inline mat4 operator+(const mat4& a, const mat4& b) { mat4 r; for (int i = 0; i < 4; ++i) r[i] = a[i] + b[i]; return r; }
+inline mat4& operator+=(mat4& a, const mat4& b) { a = a + b; return a; }
 inline mat3::mat3(const mat4& m) { for (int i = 0; i < 3; ++i) c[i] = vec3(m[i].x, m[i].y, m[i].z); }
 static_assert(sizeof(mat4) == 64 && sizeof(vec2) == 8 && sizeof(vec3) == 12 && sizeof(vec4) == 16, "tight layouts");
 // oracle_math.h's orders: mat4 * vec4 = ((c0 x + c1 y) + c2 z) + c3 w per row; mat3 * vec3 = (c0 x + c1 y) + c2 z
@@ -218,13 +229,23 @@ inline vec3 operator*(const mat3& m, const vec3& v) {
   return r;
 }
 inline mat4 operator*(const mat4& a, const mat4& b) { mat4 r; for (int j = 0; j < 4; ++j) r[j] = a * b[j]; return r; }
+inline mat3 operator*(const mat3& a, const mat3& b) { mat3 r; for (int j = 0; j < 3; ++j) r[j] = a * b[j]; return r; }
 inline mat3 transpose(const mat3& m) { mat3 r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r[i][j] = m[j][i]; return r; }
 
 // ---- texture unit: oracle_math.h's (Vulkan's LINEAR filter, CLAMP_TO_EDGE / REPEAT, explicit LOD, cube face selection) -----
 struct sampler2D {
   oracle::TexChain chain{nullptr, 0, 0, 1, oracle::FMT_RGBA32F};
   oracle::Address address = oracle::ADDR_CLAMP;
+  // material textures of the rasterising passes: an OracleTex of althea_oracle_raster.cpp (RGBA8 mip chain + sampler word; null texels
+  // = the engine's 1 x 1 default of that slot), sampled by that file's texture unit at the implicit level of detail
+  const void* materialTex = nullptr;
+  float dflt[4] = {1.0f, 1.0f, 1.0f, 1.0f};
 };
+// implicit derivatives: a fragment stage samples its material textures at one of its interpolated uv sets, whose screen-space
+// derivatives the rasteriser knows; the stage driver announces them, texture() picks the set its coordinate is
+struct ImplicitLod { const float (*uvs)[2] = nullptr; const float (*ddx)[2] = nullptr; const float (*ddy)[2] = nullptr; int sets = 0; };
+inline thread_local ImplicitLod gImplicit;
+inline void (*gSampleMaterial)(const void* tex, const float dflt[4], const float uv[2], const float ddx[2], const float ddy[2], float out[4]) = nullptr;
 struct samplerCubeArray { const float* layers = nullptr; int res = 0; }; // R32F, layer = 6 * cube + face
 struct image2D { uint16_t* texels = nullptr; float* texels32 = nullptr; int w = 0, h = 0; }; // RGBA16F (or RGBA32F) storage image
 inline vec4 fromV4(oracle::V4 v) { return vec4(v.x, v.y, v.z, v.w); }
@@ -251,7 +272,18 @@ inline vec4 textureLod(const sampler2D& s, const vec2& uv, float lod) {
   return fromV4(oracle::mix(s0, oracle::bilinear(s.chain.level(l1), uv.x, uv.y, s.address), f));
 }
 // implicit-LOD fetch of a fragment shader: every image the path samples this way has one level (rule A10)
-inline vec4 texture(const sampler2D& s, const vec2& uv) { return fromV4(fetchLevel0(s, uv)); }
+inline vec4 texture(const sampler2D& s, const vec2& uv) {
+  if (s.materialTex) {
+    const float zero[2] = {0.0f, 0.0f}, c[2] = {uv.x, uv.y};
+    const float *dx = zero, *dy = zero;
+    for (int k = 0; k < gImplicit.sets; ++k)
+      if (gImplicit.uvs[k][0] == uv.x && gImplicit.uvs[k][1] == uv.y) { dx = gImplicit.ddx[k]; dy = gImplicit.ddy[k]; break; }
+    float out[4];
+    gSampleMaterial(s.materialTex, s.dflt, c, dx, dy, out);
+    return vec4(out[0], out[1], out[2], out[3]);
+  }
+  return fromV4(fetchLevel0(s, uv));
+}
 inline vec4 texture(const samplerCubeArray& s, const vec4& q) { // Vulkan 1.3 spec 16.5.1 (cube map face selection), bilinear inside the face
   const float ax = ::fabsf(q.x), ay = ::fabsf(q.y), az = ::fabsf(q.z);
   int face; float sc, tc, ma;
@@ -272,8 +304,10 @@ inline void imageStore(const image2D& img, const ivec2& p, const vec4& c) { // R
 // what every shader stage inherits
 struct ShaderBase {
   vec4 gl_FragCoord, gl_Position;
-  int gl_VertexIndex = 0;
+  int gl_VertexIndex = 0, gl_ViewIndex = 0;
   uvec3 gl_GlobalInvocationID;
+  bool gl_Discarded = false;
 };
+#define discard do { gl_Discarded = true; return; } while (0)
 
 } // namespace glsl

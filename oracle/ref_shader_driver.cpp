@@ -58,6 +58,22 @@ struct PrefilterComp : ShaderBase {
 #include "_ref/gen/prefilter_comp.inc"
 };
 
+// the rasterising producers: G-buffer pass and omni shadow pass
+struct GltfVert : ShaderBase {
+#include "_ref/gen/gltf_vert.inc"
+};
+struct GltfFrag : ShaderBase {
+#include "_ref/gen/gltf_frag.inc"
+};
+struct ShadowVert : ShaderBase {
+#include "_ref/gen/shadow_vert.inc"
+  MaterialConstants legacyMaterial; // see oracle/Makefile: the fields the legacy shader reads from `PrimitiveConstants` live here today
+};
+struct ShadowFrag : ShaderBase {
+#include "_ref/gen/shadow_frag.inc"
+  MaterialConstants legacyMaterial;
+};
+
 static_assert(sizeof(SsrFrag::GlobalUniforms) == 416, "the GLSL block is the C++ block (Global/GlobalUniforms.glsl:8-24)");
 
 // texture handles of the bindless heap (any distinct numbers do)
@@ -313,6 +329,114 @@ void shaderref_ibl_prefilter(const float* chain, int W, int H, int mips, int out
     cs.main();
     memcpy(out + (size_t)t * 4, dst.data() + ((size_t)y * outW + x) * 4, 16);
   }
+}
+
+// ---- the programmable stages of the rasterising passes, as hooks of althea_oracle_raster.cpp ------------------------------------
+struct OracleTex { const uint8_t* texels; int32_t w, h, mips; uint32_t sampler; };
+struct OraclePrim { // oracle/althea_oracle_raster.cpp, same layout
+  const float* verts; const uint32_t* idx; uint32_t triCount; uint32_t frontCW; float model[16]; float baseColorFactor[4];
+  int32_t baseUv, mrUv; float normalScale, metallicFactor, roughnessFactor, alphaCutoff; OracleTex base, normal, mr;
+};
+struct OracleStageHooks {
+  void (*gbufferVertex)(const OraclePrim*, uint32_t, const float*, const float*, float*, float*, float*);
+  int (*gbufferFragment)(const OraclePrim*, const float*, const float (*)[2], const float (*)[2], const float (*)[2], float*, float*, float*);
+  void (*shadowVertex)(const OraclePrim*, uint32_t, const float*, const float*, const float*, float*, float*);
+  int (*shadowFragment)(const OraclePrim*, const float*, const float*, const float*, const float*, float*);
+};
+}
+namespace {
+constexpr int kVertexFloats = 26; // InstanceDataCommon.h:45-53: position 0, tangent 3, bitangent 6, normal 9, uvs 12
+template <class M> void fillMaterial(M& m, const OraclePrim* p) { // MaterialConstants as Src/Primitive.cpp fills it
+  memset(&m, 0, sizeof m);
+  m.baseColorFactor = vec4(p->baseColorFactor[0], p->baseColorFactor[1], p->baseColorFactor[2], p->baseColorFactor[3]);
+  m.baseTextureCoordinateIndex = p->baseUv;
+  m.normalMapTextureCoordinateIndex = p->baseUv;
+  m.metallicRoughnessTextureCoordinateIndex = p->mrUv;
+  m.normalScale = p->normalScale; m.metallicFactor = p->metallicFactor; m.roughnessFactor = p->roughnessFactor;
+  m.alphaCutoff = p->alphaCutoff;
+  m.baseTextureHandle = 0; m.normalTextureHandle = 1; m.metallicRoughnessTextureHandle = 2;
+}
+void materialSamplers(sampler2D s[3], const OraclePrim* p) { // missing textures: the engine binds 1 x 1 defaults (white, flat normal, white)
+  s[0].materialTex = &p->base; s[1].materialTex = &p->normal; s[2].materialTex = &p->mr;
+  s[1].dflt[0] = s[1].dflt[1] = 128.0f / 255.0f;
+}
+template <class VS> void vertexInputs(VS& vs, const OraclePrim* p, uint32_t i) {
+  const float* v = p->verts + (size_t)i * kVertexFloats;
+  vs.position = vec3(v[0], v[1], v[2]);
+  vs.tbn = mat3(vec3(v[3], v[4], v[5]), vec3(v[6], v[7], v[8]), vec3(v[9], v[10], v[11]));
+  for (int k = 0; k < 4; ++k) vs.uvs[k] = vec2(v[12 + 2 * k], v[13 + 2 * k]);
+}
+void hookGbufferVertex(const OraclePrim* p, uint32_t i, const float* projection, const float* view, float clip[4], float world[3], float tbn[9]) {
+  GltfVert vs;
+  vertexInputs(vs, p, i);
+  GltfVert::GlobalUniforms gu; memset(&gu, 0, sizeof gu);
+  memcpy(&gu.projection, projection, 64); memcpy(&gu.view, view, 64);
+  for (int c = 0; c < 4; ++c) gu.inverseView[c] = vec4(c == 0, c == 1, c == 2, c == 3); // only `direction` reads it, which no stage of the path consumes
+  GltfVert::_primitiveConstants_BUFFER pc; memset(&pc, 0, sizeof pc); // nodeIdx 0, not skinned
+  mat4 model; memcpy(&model, p->model, 64);
+  GltfVert::_transformBuffer_BUFFER tb{&model};
+  vs.globalUniforms = &gu; vs._primitiveConstantsHeap = &pc; vs._transformBufferHeap = &tb;
+  vs.pushConstants.matrixBufferHandle = 0; vs.pushConstants.primConstantsBuffer = 0; vs.pushConstants.globalUniformsHandle = 0;
+  vs.main();
+  for (int c = 0; c < 4; ++c) clip[c] = vs.gl_Position[c];
+  for (int c = 0; c < 3; ++c) world[c] = vs.worldPosition[c];
+  for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) tbn[3 * c + r] = vs.vertTbn[c][r];
+}
+int hookGbufferFragment(const OraclePrim* p, const float tbn[9], const float (*uvs)[2], const float (*ddx)[2], const float (*ddy)[2],
+                        float outN[4], float outA[4], float outM[4]) {
+  GltfFrag fs;
+  for (int k = 0; k < 4; ++k) fs.uvs[k] = vec2(uvs[k][0], uvs[k][1]);
+  fs.fragTBN = mat3(vec3(tbn[0], tbn[1], tbn[2]), vec3(tbn[3], tbn[4], tbn[5]), vec3(tbn[6], tbn[7], tbn[8]));
+  GltfFrag::_materialConstants_BUFFER mc; fillMaterial(mc.val, p);
+  GltfFrag::_primitiveConstants_BUFFER pc; memset(&pc, 0, sizeof pc); // materialHandle 0
+  sampler2D tex[3]; materialSamplers(tex, p);
+  fs._materialConstantsHeap = &mc; fs._primitiveConstantsHeap = &pc; fs._materialSamplerHeap = tex;
+  fs.pushConstants.primConstantsBuffer = 0;
+  gImplicit.uvs = uvs; gImplicit.ddx = ddx; gImplicit.ddy = ddy; gImplicit.sets = 4;
+  fs.main();
+  gImplicit.sets = 0;
+  if (fs.gl_Discarded) return 0;
+  for (int c = 0; c < 4; ++c) { outN[c] = fs.GBuffer_Normal[c]; outA[c] = fs.GBuffer_Albedo[c]; outM[c] = fs.GBuffer_MetallicRoughnessOcclusion[c]; }
+  return 1;
+}
+void hookShadowVertex(const OraclePrim* p, uint32_t i, const float* lightPos, const float* view, const float* projection, float clip[4], float cs[3]) {
+  ShadowVert vs;
+  vertexInputs(vs, p, i);
+  ShadowVert::PointLight light; light.position = vec3(lightPos[0], lightPos[1], lightPos[2]);
+  ShadowVert::POINT_LIGHTS pl{&light};
+  ShadowVert::PointLightConstants lc; memset(&lc, 0, sizeof lc);
+  memcpy(&lc.projection, projection, 64); memcpy(&lc.views[0], view, 64);
+  fillMaterial(vs.legacyMaterial, p);
+  vs.pointLights = &pl; vs.pointLightConstants = &lc;
+  memcpy(&vs.pushConstants.model, p->model, 64);
+  vs.pushConstants.lightIdx = 0; vs.pushConstants.pointLightBufferHandle = 0; vs.pushConstants.pointLightConstantsHandle = 0;
+  vs.gl_ViewIndex = 0;
+  vs.main();
+  for (int c = 0; c < 4; ++c) clip[c] = vs.gl_Position[c];
+  for (int c = 0; c < 3; ++c) cs[c] = vs.worldPosCS[c];
+}
+int hookShadowFragment(const OraclePrim* p, const float cs[3], const float uv[2], const float ddx[2], const float ddy[2], float* depth) {
+  ShadowFrag fs;
+  fs.worldPosCS = vec3(cs[0], cs[1], cs[2]);
+  fs.baseColorUV = vec2(uv[0], uv[1]);
+  fillMaterial(fs.legacyMaterial, p);
+  sampler2D tex[3]; materialSamplers(tex, p);
+  fs.textureHeap = tex;
+  const float u1[1][2] = {{uv[0], uv[1]}}, dx1[1][2] = {{ddx[0], ddx[1]}}, dy1[1][2] = {{ddy[0], ddy[1]}};
+  gImplicit.uvs = u1; gImplicit.ddx = dx1; gImplicit.ddy = dy1; gImplicit.sets = 1;
+  fs.main();
+  gImplicit.sets = 0;
+  if (fs.gl_Discarded) return 0;
+  *depth = fs.gl_FragDepth;
+  return 1;
+}
+const OracleStageHooks kHooks{hookGbufferVertex, hookGbufferFragment, hookShadowVertex, hookShadowFragment};
+}
+extern "C" {
+// `sampleMaterial` = liboracle.so's oracle_sample_texture (the passes' texture unit); returns what oracle_set_stage_hooks takes
+const void* shaderref_raster_hooks(void (*sampleMaterial)(const void*, const float*, const float*, const float*, const float*, float*)) {
+  gSampleMaterial = sampleMaterial;
+  return &kHooks;
 }
 
 void shaderref_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }

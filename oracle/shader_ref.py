@@ -1,6 +1,6 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY. ctypes binding of oracle/_ref/libshader_ref.so: the reference's own GLSL text
 (SSR.vert/.frag, DeferredPass.vert/.frag with SSAO.glsl and PBR/PBRMaterial.glsl, SSRGlossyConvolve.comp,
-Misc/ReconstructPosition.glsl) rewritten by oracle/glsl2cpp.py where it lies and run on the CPU over oracle/glsl_compat.h.
+Misc/ReconstructPosition.glsl, the two IBL_Precompute integrators, Gltf/Gltf.vert/.frag, ShadowMapBindless.vert/.frag) rewritten by oracle/glsl2cpp.py where it lies and run on the CPU over oracle/glsl_compat.h.
 
 It exists to pin the restatement (oracle/althea_oracle.cpp) against the text it restates. It can only be BUILT where
 /root/reference is mounted (`make -C oracle ref`); the prebuilt library travels with the tree, and the vectors it produced are
@@ -100,3 +100,16 @@ def ibl_prefilter(chain, W, H, mips, out_w, out_h, roughness, texels):
     out = np.empty((n, 4), np.float32)
     lib().shaderref_ibl_prefilter(O._p(chain), W, H, mips, out_w, out_h, C.c_float(roughness), O._p(t), n, O._p(out))
     return out
+
+
+def set_raster_stage_hooks(on: bool) -> None:
+    """Makes liboracle.so's two rasterising passes (oracle.draw_gbuffer / draw_shadow_cubes) take their PROGRAMMABLE stages from the
+    reference's shader text (Gltf/Gltf.vert + .frag with InstanceData.glsl's fetchMaterial; ShadowMapBindless.vert + .frag), keeping
+    their own fixed-function part (coverage, depth test, interpolation, derivatives, blending). A hooked draw must equal the plain one."""
+    L = O.lib()
+    if not on:
+        L.oracle_set_stage_hooks(None)
+        return
+    lib().shaderref_raster_hooks.restype = C.c_void_p
+    hooks = lib().shaderref_raster_hooks(C.cast(L.oracle_sample_texture, C.c_void_p))
+    L.oracle_set_stage_hooks(C.c_void_p(hooks))

@@ -46,6 +46,19 @@ def main():
         ow, oh = W >> (i + 1), H >> (i + 1)
         tx = np.stack([rng.integers(0, ow, 8), rng.integers(0, oh, 8), np.zeros(8, int)], -1)
         out["pre%d_texels" % i], out["pre%d" % i] = tx, S.ibl_prefilter(chain, W, H, mips, ow, oh, r, tx)
+    # the rasterising producers: liboracle.so's fixed-function rasteriser with the PROGRAMMABLE stages taken from the shader text
+    # (Gltf/Gltf.vert + .frag, ShadowMapBindless.vert + .frag) through its stage hooks
+    from producer_scene import gbuffer_case, shadow_case
+    S.set_raster_stage_hooks(True)
+    try:
+        proj, view, prims, W, H = gbuffer_case()
+        gb = O.draw_gbuffer(proj, view, prims, W, H)
+        for k, v in gb.items():
+            out["gbuffer_" + k] = v
+        lights, projection, views, sc, res = shadow_case()
+        out["shadow_cubes"] = O.draw_shadow_cubes(lights, projection, views, sc, res)
+    finally:
+        S.set_raster_stage_hooks(False)
     path = os.path.join(HERE, "shader_ref.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -78,6 +78,23 @@ def test_ibl_integrators_equal_the_executed_shader_text(oracle, golden):
         assert np.isfinite(got).all() and got[:, :3].max() > 0.05
 
 
+def test_producer_stages_equal_the_executed_shader_text(oracle, golden):
+    """G-buffer pass and omni shadow pass: the fixture was drawn by the restatement's rasteriser with its
+    vertex and fragment STAGES replaced by the reference's shader text (Gltf/Gltf.vert + .frag with InstanceData.glsl's fetchMaterial,
+    ShadowMapBindless.vert + .frag) through althea_oracle_raster.cpp's stage hooks. The restatement's own stages must draw the same
+    attachments bit for bit: textures with sRGB / mirror / clamp / nearest-mip samplers, a normal map, alpha cutout, blending."""
+    from producer_scene import gbuffer_case, shadow_case
+    proj, view, prims, W, H = gbuffer_case()
+    got = oracle.draw_gbuffer(proj, view, prims, W, H)
+    assert 0.3 < (golden["gbuffer_tri"] != 0xFFFFFFFF).mean() < 1.0
+    for k, v in got.items():
+        assert np.array_equal(v, golden["gbuffer_" + k]), k
+    lights, projection, views, sc, res = shadow_case()
+    cubes = oracle.draw_shadow_cubes(lights, projection, views, sc, res)
+    assert (golden["shadow_cubes"] < 1).mean() > 0.99
+    assert np.array_equal(cubes, golden["shadow_cubes"])
+
+
 def test_view_direction_of_the_vertex_stage(golden, frames):
     """DeferredPass.vert's varying at the pixel centres == the closed form every kernel evaluates."""
     fd = frames["scene"]
@@ -110,6 +127,17 @@ def test_live_library_reproduces_the_fixture(oracle, golden, frames):
     chain, mips = oracle.env_mip_chain(env)
     assert np.array_equal(S.ibl_irradiance(chain, 512, 256, mips, 512, 256, golden["irr_texels"][:3]), golden["irr"][:3])
     assert np.array_equal(S.ibl_prefilter(chain, 512, 256, mips, 128, 64, 0.25, golden["pre1_texels"][:3]), golden["pre1"][:3])
+    # the producers, drawn again with the stages hooked to the shader text
+    from producer_scene import gbuffer_case, shadow_case
+    S.set_raster_stage_hooks(True)
+    try:
+        proj, view, prims, W, H = gbuffer_case()
+        for k, v in oracle.draw_gbuffer(proj, view, prims, W, H).items():
+            assert np.array_equal(v, golden["gbuffer_" + k]), k
+        lights, projection, views, sc, res = shadow_case()
+        assert np.array_equal(oracle.draw_shadow_cubes(lights, projection, views, sc, res), golden["shadow_cubes"])
+    finally:
+        S.set_raster_stage_hooks(False)
     # Misc/ReconstructPosition.glsl: the restatement fuses dRaw (far - near) - far (one FFMA, as GPU compilers emit it); the text
     # run by g++ is unfused, and the cancellation shows: agreement to ~1e-3 relative only, which is why the choice is pinned
     p0, p1 = oracle.reconstruct_position(fr.g, 0.3, 0.6, 0.9991), S.reconstruct_position(fr.g, 0.3, 0.6, 0.9991)
@@ -200,3 +228,19 @@ def test_cuda_path_against_the_executed_shader_text(request, golden, frames, whi
     gf.deferred.draw(fd.uniforms, gf.gbuffer, gf.ibl, gf.lights, gf.ssr, _capi.SHADE_SKIP_TONEMAP | _capi.SHADE_AO_FROM_IMAGE)
     got, want = gf.color(), golden[name + "_color_linear"]
     assert _close(got, want, 1e-3).all(), "max rel err %g" % float(np.max(np.abs(got - want) / np.maximum(1, np.abs(want))))
+
+
+@pytest.mark.gpu
+def test_cuda_producers_against_the_executed_shader_text(ctx_fast, golden):
+    """The visibility-buffer rasteriser through the C ABI against attachments drawn with the reference's own vertex / fragment text."""
+    import torch
+
+    import test_raster as TR
+    from althea_b200 import engine, scene
+    from producer_scene import gbuffer_case, shadow_case
+    proj, view, prims, W, H = gbuffer_case()
+    g = scene.make_uniforms(W, H, pos=(0.3, 0.8, 3.5), yaw=0.1, pitch=-0.2)
+    got, _ = TR._gpu_gbuffer(ctx_fast, g, prims, W, H)
+    want = {k[len("gbuffer_"):]: golden[k] for k in golden.files if k.startswith("gbuffer_")}
+    # (the cutout's alpha test compares a filtered value with the cutoff: contraction may move a handful of pixels)
+    TR._compare_gbuffer(got, want, exact=False, max_bad=int(0.001 * W * H))
