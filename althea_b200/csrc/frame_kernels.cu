@@ -1936,6 +1936,9 @@ constexpr int kFlipRing = 64; // flip items waiting per warp: at most 31 left ov
 #ifndef ALTHEA_CULL_MIN_BLOCKS
 #define ALTHEA_CULL_MIN_BLOCKS 4
 #endif
+#ifndef ALTHEA_CULL_RAY_PRETEST
+#define ALTHEA_CULL_RAY_PRETEST 1
+#endif
 template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLOCKS) ssao_cull_kernel(const __grid_constant__ FrameParams P) {
   // Per-thread arrays are indexed [field][thread of the CTA]: a lane's own slot is one register (its thread index) plus a
   // constant, another lane's slot is the warp's first thread + that lane: no per-warp base pointers to keep or rebuild.
@@ -1947,6 +1950,7 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
   __shared__ unsigned hitMask[256];
   __shared__ float redMin[8];
   __shared__ int badSum[8];
+  __shared__ float redDev[8];
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -1989,6 +1993,8 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
   }
   hitMask[tid] = 0u;
   mbarWait(&bar, 0);
+  float4 planeM = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  float planeR = __int_as_float(0x7f800000), planeRb = 0.0f;
   { // a neighbourhood that mostly cannot decide is marched by ssao_kernel instead: undecidable records among the blocks the
     // tile's rays can reach
     const int rb = min(15, (int)(reach * invSf(level)) + 2);
@@ -2009,6 +2015,42 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
     if (all * 8 > 7 * (2 * rb + 2) * (2 * rb + 2)) { // the exact evaluations run at full lane occupancy here: worth it up to ~7 / 8 undecidable
       if (threadIdx.x == 0) P.ssaoTileList[1u + atomicAdd(P.ssaoTileList, 1u)] = blockIdx.y * gridDim.x + blockIdx.x;
       return;
+    }
+    // ---- a neighbourhood that is ONE plane (ground, a wall): every record the tile's rays can reach decides, and all of them lie
+    // within planeR of the tile's own record planeM. A tap in block j is decided by record j's rule when |plane_j - L| > r_j + rayConst;
+    // with planeR >= r_j + |plane_j - planeM| over block j's texels, |planeM - L| > planeR + rayConst implies that, with the sign of
+    // planeM - L. planeM - L is affine along a ray, so a ray whose first and last taps clear planeR + rayConst on the same side has
+    // no step that changes sign: it scores nothing and needs no lookup at all (the pre-test of the ray loop below).
+    planeR = __int_as_float(0x7f800000);
+    if (ALTHEA_CULL_RAY_PRETEST && all == 0) {
+      planeM = win[15 * kPlaneWin + 15];
+      float dev = 0.0f;
+      if (row >= 15 - rb && row <= 16 + rb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int col = col0 + k;
+          if (col >= 15 - rb && col <= 16 + rb) {
+            const float4 rj = win[row * kPlaneWin + col];
+            const float da = rj.x - planeM.x, db = rj.y - planeM.y, dc = rj.z - planeM.z;
+            // the texels record (row, col) answers for (ssaoPlaneRecords: the block and its apron), as tap coordinates
+            const float x0 = (float)((wbx + col) * S - 3 - (S >> 5)), x1 = (float)((wbx + col) * S + S + 2);
+            const float y0 = (float)((wby + row) * S - 3), y1 = (float)((wby + row) * S + S + 2);
+            const float ex = fmaxf(fabsf(x0), fabsf(x1)), ey = fmaxf(fabsf(y0), fabsf(y1));
+            float d = fmaxf(fmaxf(fabsf(fmaf(db, x0, fmaf(dc, y0, da))), fabsf(fmaf(db, x1, fmaf(dc, y0, da)))),
+                            fmaxf(fabsf(fmaf(db, x0, fmaf(dc, y1, da))), fabsf(fmaf(db, x1, fmaf(dc, y1, da)))));
+            // rounding of the differences and of planeM's evaluation in the pre-test
+            d += 1e-6f * (fabsf(rj.x) + fabsf(planeM.x) + (fabsf(rj.y) + fabsf(planeM.y)) * ex + (fabsf(rj.z) + fabsf(planeM.z)) * ey);
+            dev = fmaxf(dev, d + rj.w);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dev = fmaxf(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+      if (lane == 0) redDev[warp] = dev;
+      __syncthreads();
+      dev = fmaxf(fmaxf(fmaxf(redDev[0], redDev[1]), fmaxf(redDev[2], redDev[3])), fmaxf(fmaxf(redDev[4], redDev[5]), fmaxf(redDev[6], redDev[7])));
+      planeR = dev * 1.000001f; // +inf or NaN: no pre-test
+      planeRb = (float)rb;
     }
   }
   // ---- per pixel
@@ -2052,42 +2094,82 @@ template <bool COUNT> __global__ void __launch_bounds__(256, ALTHEA_CULL_MIN_BLO
     fhead += count;
     __syncwarp();
   };
-  // a warp without a covered pixel has nothing to count (no block-wide barrier below this point)
-  const int rays = __any_sync(0xffffffffu, covered) ? 24 : 0;
-  for (int ray = 0; ray < rays; ++ray) {
-    const SsaoRay R = ssaoRay(P, tbn, worldPos, normal, x, y, ray);
+  // ---- what the coarse test needs of a ray: L(i) = L0 + i dL along its taps (xs0 + i dxs, ys0 + i dys), the slack rayConst
+  struct RayCoarse { float c0, dxs, dys, L0, dL, rayConst, lastI; bool answerable; };
+  auto rayCoarse = [&](const SsaoRay& R, int n) {
+    RayCoarse C;
+    const V3 cam = mk3(P.ssaoCam[0], P.ssaoCam[1], P.ssaoCam[2]);
+    C.c0 = dot3(cam - worldPos, R.perpRef);
+    const float au = dot3(mk3(P.ssaoDx[0], P.ssaoDx[1], P.ssaoDx[2]), R.perpRef), av = dot3(mk3(P.ssaoDy[0], P.ssaoDy[1], P.ssaoDy[2]), R.perpRef);
+    const float ac = dot3(mk3(P.ssaoDc[0], P.ssaoDc[1], P.ssaoDc[2]), R.perpRef);
+    float invC0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(invC0) : "f"(C.c0));
+    const float aInv = fabsf(invC0);
+    const float Lx = -au * invC0, Ly = -av * invC0;
+    const float xEnd = fmaf(R.uvEnd.x, P.Wf, -0.5f), yEnd = fmaf(R.uvEnd.y, P.Hf, -0.5f);
+    C.dxs = (xEnd - xs0) * (1.0f / 12.0f); C.dys = (yEnd - ys0) * (1.0f / 12.0f);
+    C.L0 = -(fmaf(au, xs0, fmaf(av, ys0, ac))) * invC0;
+    C.dL = fmaf(Lx, C.dxs, Ly * C.dys);
+    const float Labs = fmaxf(fabsf(C.L0), fabsf(fmaf(11.0f, C.dL, C.L0))) + (fabsf(Lx) + fabsf(Ly));
+    const float kappa = kappaNum * aInv;
+    // slack of the ray: its share of the footprint term at the largest eta a record may have (kEtaRay), the margin rule with
+    // its (1 - eta) and (1 - kappa) factors folded into the constants, the rounding of L (16 ulp of the largest term of
+    // dot(D, perpRef) / c0) and of w - L
+    C.rayConst = kEtaRay * (fabsf(Lx) + fabsf(Ly)) + kEtaKappa * kappa * Labs + kEtaDmax * kNu * P.ssaoDmax1 * aInv + 9.6e-7f * P.ssaoDmag * aInv + 4.8e-7f * Labs;
+    // rays the records cannot answer for take the exact path for all their taps: a last tap outside the window, a plane
+    // through (nearly) the camera. (A footprint that clamps at the image border repeats a texel the block covers.)
+    C.lastI = (float)(max(n, 2) - 1);
+    const float xl = fmaf(C.lastI, C.dxs, xs0), yl = fmaf(C.lastI, C.dys, ys0);
+    const float wx = xl * invS - (float)wbx, wy = yl * invS - (float)wby; // window coordinates of the last tap, in blocks
+    C.answerable = wx >= 0.25f && wx <= (float)kPlaneWin - 0.25f && wy >= 0.25f && wy <= (float)kPlaneWin - 0.25f && kappa <= 0.01f;
+    return C;
+  };
+  auto tapCount = [&](const SsaoRay& R, bool active) {
     // the bisection runs for the warp only when some lane's ray ends off the screen (a vote: tiles away from the border skip it)
-    int n = covered ? 12 : 0;
-    if (__any_sync(0xffffffffu, covered && outside01(R.uvEnd.x, R.uvEnd.y))) n = covered ? ssaoTapCount(u0, v0, R.uvEnd) : 0;
+    int n = active ? 12 : 0;
+    if (__any_sync(0xffffffffu, active && outside01(R.uvEnd.x, R.uvEnd.y))) n = active ? ssaoTapCount(u0, v0, R.uvEnd) : 0;
+    return n;
+  };
+  // Rays still to be looked at, a bit per ray. A warp without a covered pixel has nothing to count (no block-wide barrier below
+  // this point). In a planar neighbourhood (planeR finite) a first sweep generates every ray and keeps only those the tile's one
+  // plane cannot clear (grazing rays, rays leaving the region: a few per cent); the loop below then runs as many times as the
+  // busiest lane has rays left instead of 24 times.
+  unsigned todo = covered ? 0xffffffu : 0u;
+  if (COUNT && threadIdx.x == 0) atomicAdd(P.gatherCounter + (planeR < __int_as_float(0x7f800000) ? 77 : 78), 1ull); // planar / other tiles
+  if (planeR < __int_as_float(0x7f800000) && __any_sync(0xffffffffu, covered)) {
+    unsigned fail = 0u;
+    const float regLo = 15.0f - planeRb + 0.25f, regHi = 17.0f + planeRb - 0.25f; // the blocks planeR answers for, in window coordinates
+    for (int ray = 0; ray < 24; ++ray) {
+      const SsaoRay R = ssaoRay(P, tbn, worldPos, normal, x, y, ray);
+      const int n = tapCount(R, covered);
+      const RayCoarse C = rayCoarse(R, n);
+      const float xl = fmaf(C.lastI, C.dxs, xs0), yl = fmaf(C.lastI, C.dys, ys0);
+      const float wx = xl * invS - (float)wbx, wy = yl * invS - (float)wby;
+      const float x1 = xs0 + C.dxs, y1 = ys0 + C.dys;
+      const float d1 = fmaf(planeM.y, x1, fmaf(planeM.z, y1, planeM.x)) - (C.L0 + C.dL);
+      const float dl = fmaf(planeM.y, xl, fmaf(planeM.z, yl, planeM.x)) - fmaf(C.lastI, C.dL, C.L0);
+      const float thr = planeR + C.rayConst;
+      const bool clear = C.answerable && wx >= regLo && wx <= regHi && wy >= regLo && wy <= regHi && fabsf(d1) > thr && fabsf(dl) > thr && (d1 > 0.0f) == (dl > 0.0f);
+      if (covered && n >= 3 && !clear) fail |= 1u << ray; // (n < 3: no step to test)
+      if (COUNT && covered && n >= 3) atomicAdd(P.gatherCounter + (clear ? 76 : 79), 1ull); // diagnostics: rays of planar tiles cleared / kept
+    }
+    todo = fail;
+  }
+  while (__any_sync(0xffffffffu, todo != 0u)) {
+    const bool active = todo != 0u;
+    const int ray = active ? __ffs(todo) - 1 : 0;
+    todo &= todo - 1u;
+    const SsaoRay R = ssaoRay(P, tbn, worldPos, normal, x, y, ray);
+    const int n = tapCount(R, active);
     rayState[0][tid] = R.uvEnd.x; rayState[1][tid] = R.uvEnd.y;
     rayState[2][tid] = R.perpRef.x; rayState[3][tid] = R.perpRef.y; rayState[4][tid] = R.perpRef.z;
     rayState[5][tid] = R.rayDir.x; rayState[6][tid] = R.rayDir.y; rayState[7][tid] = R.rayDir.z;
     unsigned decMask = 0u, negMask = 0u;
-    { // ray constants of the coarse test
-      const V3 cam = mk3(P.ssaoCam[0], P.ssaoCam[1], P.ssaoCam[2]);
-      const float c0 = dot3(cam - worldPos, R.perpRef);
-      const float au = dot3(mk3(P.ssaoDx[0], P.ssaoDx[1], P.ssaoDx[2]), R.perpRef), av = dot3(mk3(P.ssaoDy[0], P.ssaoDy[1], P.ssaoDy[2]), R.perpRef);
-      const float ac = dot3(mk3(P.ssaoDc[0], P.ssaoDc[1], P.ssaoDc[2]), R.perpRef);
-      float invC0;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(invC0) : "f"(c0));
-      const float aInv = fabsf(invC0);
-      const float Lx = -au * invC0, Ly = -av * invC0;
-      const float xEnd = fmaf(R.uvEnd.x, P.Wf, -0.5f), yEnd = fmaf(R.uvEnd.y, P.Hf, -0.5f);
-      const float dxs = (xEnd - xs0) * (1.0f / 12.0f), dys = (yEnd - ys0) * (1.0f / 12.0f);
-      const float L0 = -(fmaf(au, xs0, fmaf(av, ys0, ac))) * invC0;
-      const float dL = fmaf(Lx, dxs, Ly * dys);
-      const float Labs = fmaxf(fabsf(L0), fabsf(fmaf(11.0f, dL, L0))) + (fabsf(Lx) + fabsf(Ly));
-      const float kappa = kappaNum * aInv;
-      // slack of the ray: its share of the footprint term at the largest eta a record may have (kEtaRay), the margin rule with
-      // its (1 - eta) and (1 - kappa) factors folded into the constants, the rounding of L (16 ulp of the largest term of
-      // dot(D, perpRef) / c0) and of w - L
-      float rayConst = kEtaRay * (fabsf(Lx) + fabsf(Ly)) + kEtaKappa * kappa * Labs + kEtaDmax * kNu * P.ssaoDmax1 * aInv + 9.6e-7f * P.ssaoDmag * aInv + 4.8e-7f * Labs;
-      // rays the records cannot answer for take the exact path for all their taps: a last tap outside the window, a plane
-      // through (nearly) the camera. (A footprint that clamps at the image border repeats a texel the block covers.)
-      const float lastI = (float)(max(n, 2) - 1);
-      const float xl = fmaf(lastI, dxs, xs0), yl = fmaf(lastI, dys, ys0);
-      const float wx = xl * invS - (float)wbx, wy = yl * invS - (float)wby; // window coordinates of the last tap, in blocks
-      const bool answerable = wx >= 0.25f && wx <= (float)kPlaneWin - 0.25f && wy >= 0.25f && wy <= (float)kPlaneWin - 0.25f && kappa <= 0.01f;
+    { // the coarse test
+      const RayCoarse C = rayCoarse(R, n);
+      const float c0 = C.c0, dxs = C.dxs, dys = C.dys, L0 = C.L0, dL = C.dL;
+      const bool answerable = C.answerable;
+      float rayConst = C.rayConst;
       if (!answerable) rayConst = __int_as_float(0x7f800000);
       // a footprint of cleared texels (empty pixels) interpolates to exactly (0, 0, 0): its projection is -dot(pos, perpRef)
       // whatever the tap; known when it clears the rounding of the dot product. Stored with the sign the c0 flip below undoes.
