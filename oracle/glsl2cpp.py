@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """ORACLE — TEST INFRASTRUCTURE ONLY. Turns one of the reference's GLSL shaders, READ WHERE IT LIES under /root/reference/Shaders,
 into text g++ accepts as the body of a C++ struct (oracle/glsl_compat.h supplies GLSL's types and built-ins). The output goes to
-oracle/_ref/gen/ (git-ignored build output): no shader text is committed to this repository.
+oracle/_ref/gen/ (git-ignored build output, deleted by the Makefile rule once the library is linked): no shader text is committed to or kept in this repository.
 
 The rewrite is mechanical and token-level; it never touches an expression:
   1. `#include <...>` resolved against the Shaders directory (textually, as the reference's shaderc includer does,

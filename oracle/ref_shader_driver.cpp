@@ -2,7 +2,7 @@
 //
 // The reference's per-frame path is GLSL that a Vulkan driver compiles at run time; this image has neither. What it does have
 // is g++, and GLSL's expression language is (nearly) C++'s: `make -C oracle ref` lets oracle/glsl2cpp.py rewrite each shader,
-// read where it lies under /root/reference/Shaders, into oracle/_ref/gen/*.inc (declarations and literals only, see its header),
+// read where it lies under /root/reference/Shaders, into oracle/_ref/gen/*.inc (declarations and literals only, see its header; removed again once the library is linked),
 // and this file includes those bodies into one struct per shader stage, with oracle/glsl_compat.h standing in for the GPU
 // (types, built-ins, texture unit). The entry points below take the arguments of liboracle.so's, so a test hands both the same
 // frame and compares: the restatement (oracle/althea_oracle.cpp) against the text it restates, executed.
