@@ -56,6 +56,26 @@ def allgather_rows(buf, row_bytes: int, band_rows: int, group=None, async_op: bo
     return dist.all_gather(chunks, mine.clone(), group=group, async_op=async_op)
 
 
+HALO_EXCHANGE_MIN_SHARE = 0.2  # of a band's rows
+
+
+def exchanges_halo(width: int, height: int, mips: int, world: int) -> bool:
+    """Whether the ranks exchange their reflection halos (True) or every rank ray-marches its own (False). THE SAME ANSWER ON EVERY
+    RANK: the exchange is a rendezvous between neighbours, so it cannot depend on a rank's own band. (An earlier rule compared each
+    rank's own halo with its band: the outermost bands have a halo on one side only, and at 4 ranks of an 8K frame the inner ranks
+    exchanged while the outer ones did not: a deadlock.) True when the largest halo of any band is at least HALO_EXCHANGE_MIN_SHARE
+    of a band: 0.30 at 8 ranks of an 8K frame (35 % more SSR when recomputed), 0.15 at 4, 0.04 at 2."""
+    if world <= 1:
+        return False
+    from . import engine
+    worst = 0
+    for (y0, y1) in split_rows(height, world):
+        if y1 > y0:
+            lo, hi = engine.band_rows(width, height, mips, y0, y1)[0]
+            worst = max(worst, (hi - lo) - (y1 - y0))
+    return worst >= HALO_EXCHANGE_MIN_SHARE * band_height(height, world)
+
+
 def halo_plan(width: int, height: int, mips: int, world: int, rank: int):
     """Rows of reflection mip 0 that `rank`'s glossy mips read but other ranks own, and the rows it owns that others read:
     ([(peer, y0, y1)] to receive, [(peer, y0, y1)] to send), from althea_cuda_band_rows of every rank's band."""
@@ -221,14 +241,13 @@ class BandedFrame:
         from the ranks that own those rows (exchange_halo, default) while this rank's SSAO runs; with exchange_halo=False every rank
         ray-marches its halo itself (no collective inside the frame, ~35 % more SSR work at 8 ranks of an 8K frame). Either way the
         band is bit-identical to the same rows of a single-GPU frame."""
+        if exchange_halo is None:  # worth a synchronisation point between neighbours once the halo is a fair share of a band
+            exchange_halo = exchanges_halo(self.W, self.H, self.ssr.getReflectionBuffer().image.mips, self.world)  # rank-independent
         if self.y1 <= self.y0:
-            if self.world > 1 and exchange_halo is not False:
+            if self.world > 1 and exchange_halo:
                 for w in self.exchange_halo():  # an empty band still owes nothing, but the grouped call must match its peers'
                     w.wait()
             return
-        if exchange_halo is None:  # worth a synchronisation point between neighbours once the halo is a fair share of the band
-            lo, hi = self.halo_rows()
-            exchange_halo = self.world > 1 and (hi - lo) - (self.y1 - self.y0) >= 0.15 * (self.y1 - self.y0)
         self.ctx.set_scissor_rows(self.y0, self.y1)
         base = self.ctx.flags
         try:

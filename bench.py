@@ -222,7 +222,7 @@ def measure_bands8k(ctx, rank, local_rank, world, device, ibl, lights, steps, wa
     one = float(single.item()) if world > 1 else rend
     gbytes = W8 * H8 * (36 if mode_p else 20)
     lo, hi = bf0.halo_rows()
-    exchanged = world > 1 and (hi - lo) - (bf0.y1 - bf0.y0) >= 0.15 * (bf0.y1 - bf0.y0)
+    exchanged = bands.exchanges_halo(W8, H8, bf0.ssr.getReflectionBuffer().image.mips, world)
     halo_how = ("exchanged point to point with the neighbouring ranks while SSAO runs: %d rows of mip 0 around a band of %d" % ((hi - lo) - (bf0.y1 - bf0.y0), bf0.band)
                 if exchanged else "recomputed locally, no collective inside the frame: %d rows around a band of %d" % ((hi - lo) - (bf0.y1 - bf0.y0), bf0.band))
     return {"metric": "deferred+SSAO+SSR Mpixel/s, one 8K frame in row bands", "value": W8 * H8 / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,

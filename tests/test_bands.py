@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from althea_b200 import bands
+from althea_b200 import bands, engine
 
 
 def _free_port():
@@ -71,6 +71,25 @@ def test_halo_plan_is_symmetric_and_covers_what_a_band_reads(lib_built):
                 assert (got[lo:hi] == 1).all() and got[:lo].sum() == 0 and got[hi:].sum() == 0
                 for q, a, b in send:
                     assert (r, a, b) in plans[q][0]
+
+
+def test_halo_exchange_decision_is_the_same_on_every_rank():
+    """The exchange of the reflection halos is a rendezvous between neighbouring ranks: whether it happens must not depend on a
+    rank's own band. The rule this replaced compared each rank's halo with its band; the outermost bands have a halo on one side
+    only, so at 4 ranks of the 8K frame of BASELINE configs[3] the inner ranks exchanged and the outer ones did not (a deadlock,
+    seen on 4 GPUs). `exchanges_halo` takes the largest halo of ANY band."""
+    W, H = 7680, 4320
+    assert [bands.exchanges_halo(W, H, 5, w) for w in (1, 2, 4, 8)] == [False, False, False, True]
+    spans = bands.split_rows(H, 4)
+    own = []
+    for y0, y1 in spans:
+        lo, hi = engine.band_rows(W, H, 5, y0, y1)[0]
+        own.append((hi - lo) - (y1 - y0) >= 0.15 * (y1 - y0))  # the old, per-rank rule
+    assert own == [False, True, True, False]
+    for size in ((7680, 4320), (3840, 2160), (320, 181), (64, 9)):
+        for world in range(1, 10):
+            assert bands.exchanges_halo(size[0], size[1], 5, world) in (True, False)
+    assert not bands.exchanges_halo(64, 9, 5, 1)
 
 
 def _gloo_worker(rank, world, port, H, W, out):
