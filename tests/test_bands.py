@@ -343,3 +343,48 @@ def test_band_pipeline_world2_gloo():
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(2))
     assert res[0] == res[1]  # the same issue order on both ranks
+
+
+def _halo_worker(rank, world, port, out):
+    """BandedFrame.exchange_halo over gloo with CPU tensors: every rank writes its own band of mip 0, the grouped send / recv plan
+    brings in exactly the halo rows its glossy mips read, on every rank, without a rendezvous left open."""
+    import types
+
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        W, H, mips = 64, 360, 5
+        y0, y1 = bands.split_rows(H, world)[rank]
+        rb = W * 8
+        t = torch.zeros(H * rb, dtype=torch.uint8)
+        rows = torch.arange(H, dtype=torch.int32)
+        pattern = ((rows * 7 + 3) % 251).to(torch.uint8)[:, None].expand(H, rb).contiguous()
+        t.view(H, rb)[y0:y1] = pattern[y0:y1]
+        image = types.SimpleNamespace(tensor=t, mips=mips)
+        stub = types.SimpleNamespace(W=W, H=H, world=world, rank=rank, group=None,
+                                     ssr=types.SimpleNamespace(getReflectionBuffer=lambda: types.SimpleNamespace(image=image)))
+        stub.halo_plan = lambda: bands.halo_plan(W, H, mips, world, rank)
+        for w in bands.BandedFrame.exchange_halo(stub):
+            w.wait()
+        lo, hi = engine.band_rows(W, H, mips, y0, y1)[0]
+        got = t.view(H, rb)
+        assert torch.equal(got[lo:hi], pattern[lo:hi]), "rank %d: halo rows [%d, %d)" % (rank, lo, hi)
+        assert int(got[:lo].sum()) == 0 and int(got[hi:].sum()) == 0
+        out.put((rank, True))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_halo_exchange_over_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5)[0] for _ in range(world)) == list(range(world))
