@@ -776,7 +776,17 @@ def main():
     # mode with data-path collectives (NCCL broadcast + all-gather). Outside the timed region of the headline.
     bands8k = None
     if world > 1 and not args.no_bands:
+        # (fail fast rather than hang: this is the only part of the bench with data-path collectives; it takes a few seconds)
+        bands_done = threading.Event()
+
+        def bands_watchdog():
+            if not bands_done.wait(300.0):
+                sys.stderr.write("bench.py: the bands8k measurement did not finish within 300 s on rank %d; giving up\n" % rank)
+                sys.stderr.flush()
+                os._exit(3)
+        threading.Thread(target=bands_watchdog, daemon=True).start()
         bands8k = measure_bands8k(ctx, rank, local_rank, world, device, ibl, lights, 16, 2, mode_p=False)  # 16 frames: the pipeline's fill and drain (one exposed broadcast + all-gather per run) weigh 1-2 %, as in a running engine
+        bands_done.set()
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = peaks()
