@@ -113,12 +113,13 @@ def literals(text: str) -> str:
 
 def main(argv):
     root = "/root/reference/Shaders"
-    patches, defines, prelude = [], [], ""
+    patches, patches_all, defines, prelude = [], [], [], ""
     pos = []
     it = iter(argv)
     for a in it:
         if a == "--root": root = next(it)
         elif a == "--patch": patches.append(next(it))
+        elif a == "--patch-all": patches_all.append(next(it))  # applied after include resolution (the expression lives in an included file)
         elif a == "--prelude": prelude += open(next(it)).read() + "\n"
         elif a.startswith("-D"): defines.append(a)
         else: pos.append(a)
@@ -130,6 +131,11 @@ def main(argv):
         m = re.match(r'\s*#\s*include\s*[<"]([^>"]+)[>"]', line)
         text += inline_includes(root, m.group(1), seen) if m else line + "\n"
     text += inline_includes(root, rel, seen, patches)
+    for p in patches_all:
+        pat, rep = p.split("=>", 1)
+        text, n = re.subn(pat, rep, text)
+        if n == 0:
+            raise SystemExit("glsl2cpp: patch did not apply: " + pat)
     text = re.sub(r"//[^\n]*", "", text)  # comments may hold apostrophes the C preprocessor trips over
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     pre = subprocess.run(["g++", "-E", "-P", "-undef", "-nostdinc", "-x", "c", "-"] + defines, input=text, capture_output=True, text=True)

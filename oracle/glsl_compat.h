@@ -163,6 +163,7 @@ inline float log(float x) { return ::logf(x); }
 inline float pow(float x, float y) { return ::powf(x, y); }
 inline float floor(float x) { return ::floorf(x); }
 inline float fract(float x) { return x - ::floorf(x); }
+inline float fma(float a, float b, float c) { return ::fmaf(a, b, c); }
 inline float radians(float d) { return d * (3.14159265358979323846f / 180.0f); }
 inline bool isinf(float x) { return __builtin_isinf(x); }
 inline bool isnan(float x) { return x != x; }

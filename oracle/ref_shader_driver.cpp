@@ -39,6 +39,13 @@ struct SsrFrag : ShaderBase {
                                globalUniforms[pushConstants.globalUniformsHandle].inverseView);
   }
 };
+struct SsrFragFused : ShaderBase { // the same text with ReconstructPosition.glsl:8 contracted to one fma() (oracle/Makefile)
+#include "_ref/gen/ssr_frag_fused.inc"
+  vec3 reconstructPosition(vec2 uv, float dRaw) {
+    return reconstructPosition(uv, dRaw, globalUniforms[pushConstants.globalUniformsHandle].inverseProjection,
+                               globalUniforms[pushConstants.globalUniformsHandle].inverseView);
+  }
+};
 struct DeferredVert : ShaderBase {
 #include "_ref/gen/deferred_vert.inc"
 };
@@ -144,33 +151,42 @@ void shaderref_reconstruct_position(const OracleGlobalUniforms* g, float u, floa
 }
 
 // SSR.vert + SSR.frag main, then the blend-on-write onto a (0,0,0,0) clear and the RGBA16F store of the colour attachment
-// (Src/ScreenSpaceReflection.cpp:37-44, Src/GraphicsPipeline.cpp:138-154)
-void shaderref_ssr_capture(const OracleGlobalUniforms* g, const OracleGBuffer* gb, const OracleIBL* ibl, const OracleLights* li,
-                           uint16_t* outReflection, uint8_t* outHit) {
+// (Src/ScreenSpaceReflection.cpp:37-44, Src/GraphicsPipeline.cpp:138-154). flags: 1 = the fused reading of ReconstructPosition.glsl:8;
+// 2 = the varying evaluated per pixel from SSR.vert's own expression (screenPos := the pixel's uv) instead of interpolated from the
+// three vertices: the two choices GLSL / the rasteriser leave open, aligned with the restatement's
+} // extern "C"
+template <class Frag> static void ssrCapture(const OracleGlobalUniforms* g, const OracleGBuffer* gb, const OracleIBL* ibl, const OracleLights* li,
+                                             uint16_t* outReflection, uint8_t* outHit, bool closedForm) {
   const int W = gb->W, H = gb->H;
   Bound b(*gb, ibl, li, g->lightCount);
-  SsrFrag::GlobalUniforms gu; memcpy(&gu, g, sizeof gu);
+  typename Frag::GlobalUniforms gu; memcpy(&gu, g, sizeof gu);
   gu.lightBufferHandle = 0;
-  SsrFrag::GlobalResources res{};
+  typename Frag::GlobalResources res{};
   res.ibl.environmentMapHandle = H_ENV; res.ibl.prefilteredMapHandle = H_PRE; res.ibl.irradianceMapHandle = H_IRR; res.ibl.brdfLutHandle = H_LUT;
   res.gBuffer.depthAHandle = H_DEPTH; res.gBuffer.normalHandle = H_NORMAL; res.gBuffer.albedoHandle = H_ALBEDO;
   res.gBuffer.metallicRoughnessOcclusionHandle = H_MRO;
   res.shadowMapArray = 0;
-  SsrFrag::POINT_LIGHTS pl{b.lights.data()};
+  typename Frag::POINT_LIGHTS pl;
+  pl.pointLightArr = reinterpret_cast<typename Frag::PointLight*>(b.lights.data());
   double vd[3][3];
   SsrVert::GlobalUniforms vgu; memcpy(&vgu, g, sizeof vgu);
   vertexDirections<SsrVert>([&](SsrVert& vs) { vs.globalUniforms = &vgu; vs.pushConstants.globalUniformsHandle = 0; }, vd);
 #pragma omp parallel for schedule(dynamic, 4)
   for (int y = 0; y < H; ++y)
     for (int x = 0; x < W; ++x) {
-      SsrFrag fs;
+      Frag fs;
       fs.globalUniforms = &gu; fs.globalResources = &res; fs.pointLights = &pl;
       fs.textureHeap = b.tex; fs.cubemapHeap = &b.cubes;
       fs.pushConstants.globalUniformsHandle = 0; fs.pushConstants.globalResourcesHandle = 0;
       const double u = (x + 0.5) / W, v = (y + 0.5) / H;
-      fs.inUv = vec2((float)u, (float)v);
+      fs.inUv = vec2(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
       announce(x, y, W, H, fs.inUv.x, fs.inUv.y);
-      fs.inDirection = interpolate(vd, u, v);
+      if (closedForm) { // SSR.vert:16-21 with screenPos := this pixel's uv
+        const vec4 pos = vec4(fs.inUv * 2.0f - 1.0f, 0.0f, 1.0f);
+        fs.inDirection = mat3(vgu.inverseView) * (vgu.inverseProjection * pos).xyz;
+      } else {
+        fs.inDirection = interpolate(vd, u, v);
+      }
       fs.gl_FragCoord = vec4(x + 0.5f, y + 0.5f, 0.0f, 1.0f);
       fs.main();
       const vec4 c = fs.reflectedColor;
@@ -181,6 +197,16 @@ void shaderref_ssr_capture(const OracleGlobalUniforms* g, const OracleGBuffer* g
       outReflection[idx * 4 + 3] = oracle::floatToHalf(c.w);
       if (outHit) outHit[idx] = c.w != 0.0f;
     }
+}
+extern "C" {
+void shaderref_ssr_capture(const OracleGlobalUniforms* g, const OracleGBuffer* gb, const OracleIBL* ibl, const OracleLights* li,
+                           uint16_t* outReflection, uint8_t* outHit) {
+  ssrCapture<SsrFrag>(g, gb, ibl, li, outReflection, outHit, false);
+}
+void shaderref_ssr_capture_flags(const OracleGlobalUniforms* g, const OracleGBuffer* gb, const OracleIBL* ibl, const OracleLights* li,
+                                 uint16_t* outReflection, uint8_t* outHit, uint32_t flags) {
+  if (flags & 1u) ssrCapture<SsrFragFused>(g, gb, ibl, li, outReflection, outHit, (flags & 2u) != 0);
+  else ssrCapture<SsrFrag>(g, gb, ibl, li, outReflection, outHit, (flags & 2u) != 0);
 }
 
 // SSRGlossyConvolve.comp main, dispatched as ReflectionBuffer::convolveReflectionBuffer does (Src/ReflectionBuffer.cpp:224-278):
@@ -247,7 +273,7 @@ void shaderref_ssao(const OracleGlobalUniforms* g, const OracleGBuffer* gb, uint
 
 // DeferredPass.vert + DeferredPass.frag main (patched per R1 / R2, oracle/Makefile); flags & 1 = SKIP_TONEMAP
 template <class Frag> static void deferred(const OracleGlobalUniforms* g, const OracleGBuffer* gb, const OracleIBL* ibl, const OracleLights* li,
-                                           const uint16_t* reflectionMips, int reflMipCount, float* outColor) {
+                                           const uint16_t* reflectionMips, int reflMipCount, float* outColor, bool closedForm) {
   const int W = gb->W, H = gb->H;
   Bound b(*gb, ibl, li, g->lightCount);
   typename Frag::GlobalUniforms gu; memcpy(&gu, g, sizeof gu);
@@ -266,7 +292,12 @@ template <class Frag> static void deferred(const OracleGlobalUniforms* g, const 
       const double u = (x + 0.5) / W, v = (y + 0.5) / H;
       fs.uv = vec2((float)u, (float)v);
       announce(x, y, W, H, fs.uv.x, fs.uv.y);
-      fs.direction = interpolate(vd, u, v);
+      if (closedForm) { // DeferredPass.vert:11-19 with screenPos := this pixel's uv
+        const vec4 pos = vec4(fs.uv * 2.0f - 1.0f, 0.0f, 1.0f);
+        fs.direction = mat3(vgu.inverseView) * (vgu.inverseProjection * pos).xyz;
+      } else {
+        fs.direction = interpolate(vd, u, v);
+      }
       fs.gl_FragCoord = vec4(x + 0.5f, y + 0.5f, 0.0f, 1.0f);
       fs.main();
       float* o = outColor + ((size_t)y * W + x) * 4;
@@ -277,8 +308,9 @@ extern "C" {
 
 void shaderref_deferred_shade(const OracleGlobalUniforms* g, const OracleGBuffer* gb, const OracleIBL* ibl, const OracleLights* li,
                               const uint16_t* reflectionMips, int reflMipCount, uint32_t flags, float* outColor) {
-  if (flags & 1u) deferred<DeferredFragLinear>(g, gb, ibl, li, reflectionMips, reflMipCount, outColor);
-  else deferred<DeferredFrag>(g, gb, ibl, li, reflectionMips, reflMipCount, outColor);
+  // flags: 1 = SKIP_TONEMAP; 4 = the varying evaluated per pixel from the vertex stage's expression instead of interpolated
+  if (flags & 1u) deferred<DeferredFragLinear>(g, gb, ibl, li, reflectionMips, reflMipCount, outColor, (flags & 4u) != 0);
+  else deferred<DeferredFrag>(g, gb, ibl, li, reflectionMips, reflMipCount, outColor, (flags & 4u) != 0);
 }
 
 // DeferredPass.vert's direction at every pixel centre (3 floats per pixel)

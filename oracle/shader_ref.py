@@ -44,12 +44,15 @@ def reconstruct_position(g: O.GlobalUniforms, u, v, d_raw):
     return out
 
 
-def ssr_capture(fr: O.Frame):
-    """SSR.vert + SSR.frag main over the frame -> (RGBA16F reflection mip 0 as uint16, hit mask)."""
+def ssr_capture(fr: O.Frame, fused_reconstruct: bool = False, closed_form_direction: bool = False):
+    """SSR.vert + SSR.frag main over the frame -> (RGBA16F reflection mip 0 as uint16, hit mask). The two switches align what GLSL and
+    the rasteriser leave open with the restatement's choices: `dRaw * (far - near) - far` (ReconstructPosition.glsl:8) contracted to
+    one fma, and the view-direction varying evaluated per pixel from SSR.vert's expression instead of interpolated from 3 vertices."""
     gb, ibl, li = fr._structs()
     refl = np.zeros((fr.H, fr.W, 4), np.uint16)
     hit = np.zeros((fr.H, fr.W), np.uint8)
-    lib().shaderref_ssr_capture(C.byref(fr.g), C.byref(gb), C.byref(ibl), C.byref(li), O._p(refl), O._p(hit))
+    flags = (1 if fused_reconstruct else 0) | (2 if closed_form_direction else 0)
+    lib().shaderref_ssr_capture_flags(C.byref(fr.g), C.byref(gb), C.byref(ibl), C.byref(li), O._p(refl), O._p(hit), C.c_uint32(flags))
     return refl, hit
 
 
@@ -70,8 +73,10 @@ def ssao(fr: O.Frame):
     return out
 
 
-def deferred_shade(fr: O.Frame, refl_chain_u16, refl_mips=5, flags=O.SKIP_TONEMAP):
-    """DeferredPass.vert + DeferredPass.frag main (computeSSAO included) -> RGBA32F colour."""
+def deferred_shade(fr: O.Frame, refl_chain_u16, refl_mips=5, flags=O.SKIP_TONEMAP, closed_form_direction: bool = False):
+    """DeferredPass.vert + DeferredPass.frag main (computeSSAO included) -> RGBA32F colour. closed_form_direction: the varying
+    evaluated per pixel from the vertex stage's own expression (as the restatement and the kernels do) instead of interpolated."""
+    flags = int(flags) | (4 if closed_form_direction else 0)
     gb, ibl, li = fr._structs()
     refl_chain_u16 = O._c(refl_chain_u16, np.uint16)
     out = np.zeros((fr.H, fr.W, 4), np.float32)

@@ -27,9 +27,13 @@ def main():
         out[name + "_ao"] = S.ssao(fr)
         refl, hit = S.ssr_capture(fr)
         out[name + "_refl"], out[name + "_hit"] = refl, hit
+        # the same stage with the two choices GLSL / the rasteriser leave open aligned with the restatement's (one fma in
+        # ReconstructPosition.glsl:8, the varying evaluated per pixel): what must then agree bit for bit
+        out[name + "_refl_aligned"], _ = S.ssr_capture(fr, fused_reconstruct=True, closed_form_direction=True)
         chain = S.glossy_convolve(refl)
         out[name + "_chain"] = chain
         out[name + "_color_linear"] = S.deferred_shade(fr, chain, flags=O.SKIP_TONEMAP)
+        out[name + "_color_linear_aligned"] = S.deferred_shade(fr, chain, flags=O.SKIP_TONEMAP, closed_form_direction=True)
         if name == "scene":
             out[name + "_color_tonemapped"] = S.deferred_shade(fr, chain, flags=0)
         out[name + "_dir"] = S.view_directions(fr.g, W, H)

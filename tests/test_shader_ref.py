@@ -52,6 +52,9 @@ def test_restatement_equals_the_executed_shader_text(oracle, golden, frames, nam
     same = hit == golden[name + "_hit"]
     ok = _close(half_to_float(refl), half_to_float(golden[name + "_refl"]), 2e-3).all(-1)
     assert ok[same].mean() >= 0.998
+    # ... and bit for bit once the two things GLSL and the rasteriser leave open are taken as the restatement takes them: one fma in
+    # ReconstructPosition.glsl:8 (as GPU compilers contract it), the view-direction varying evaluated at the pixel (not interpolated)
+    assert np.array_equal(refl, golden[name + "_refl_aligned"])
     # SSRGlossyConvolve.comp x 4 on the shader's own mip 0: every half
     assert np.array_equal(oracle.glossy_convolve(golden[name + "_refl"]), golden[name + "_chain"])
     # DeferredPass.frag main (its own computeSSAO included), linear and tone-mapped
@@ -63,6 +66,13 @@ def test_restatement_equals_the_executed_shader_text(oracle, golden, frames, nam
         # (the interpolated direction is an ulp off the closed form; the equirect lookups amplify that near the poles)
         assert _close(got, want, 2e-4).all(), "max abs %.3g" % np.abs(got - want).max()
         assert _close(got, want, 1e-5).mean() >= 0.999
+    # with the varying evaluated at the pixel: identical but for the few texels where the restatement's fp32 filter weights at a pixel
+    # centre leave ~1e-7 of a neighbour in the reflection fetch (rule A3 is applied to the G-buffer fetches only): two ulp at most
+    got = oracle.deferred_shade(fr, golden[name + "_chain"], flags=oracle.SKIP_TONEMAP)
+    want = golden[name + "_color_linear_aligned"]
+    assert _close(got, want, 1e-6).all() and (got == want).all(-1).mean() >= 0.99
+    if name == "scene":
+        assert np.array_equal(got, want)
 
 
 def test_ibl_integrators_equal_the_executed_shader_text(oracle, golden):
